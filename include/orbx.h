@@ -1,0 +1,159 @@
+/*
+ * orbx.h -- C ABI of liborbx.so: the B200 (sm_100a) ORB front end.
+ *
+ * This is the drop-in boundary for the one hot path this library replaces in
+ * chalmers-revere/opendlv-perception-vision-orbslam2 (paths below are relative to
+ * the reference tree):
+ *
+ *   OrbExtractor::OrbExtractor / ExtractFeatures / getters / m_vImagePyramid
+ *       include/orbextractor.hpp:90-109, src/orbextractor.cpp:476-642
+ *   ORBmatcher::DescriptorDistance and the best / second-best loop around it
+ *       include/orbmatcher.hpp:48, src/orbmatcher.cpp:1662-1677, :208-232
+ *
+ * Plain pointers and sizes only; no C++, OpenCV, torch or CUDA types appear in any
+ * signature (a CUDA stream is passed as void*).  All state lives in opaque per-instance
+ * handles that own their CUDA stream and device/pinned arenas, so -- like the reference,
+ * whose stereo path runs two OrbExtractor instances in two threads
+ * (src/orbframe.cpp:73-76) -- different handles may be used concurrently from different
+ * host threads; one handle must not be entered by two threads at once.
+ *
+ * There is no CPU fallback: every entry point that computes runs CUDA kernels and
+ * returns ORBX_ERR_CUDA when no sm_100 device is usable.
+ *
+ * The C++ adapter that keeps the reference's class signatures on top of this ABI is
+ * cpp/orbextractor_b200.hpp; the binding notes are in INTEGRATION.md.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_MAX_LEVELS 16
+
+/* status codes (the reference returns void and prints; see SURVEY.md 8b "Error conventions") */
+#define ORBX_OK 0
+#define ORBX_ERR_ARG (-1)         /* null pointer, non-positive size, batch > max_batch ...          */
+#define ORBX_ERR_SHAPE (-2)       /* image shape the reference itself cannot process (see below)     */
+#define ORBX_ERR_CAPACITY (-3)    /* caller's keypoint buffer too small                              */
+#define ORBX_ERR_CUDA (-4)        /* CUDA runtime error; text via orbx_last_error                    */
+#define ORBX_ERR_NOMEM (-5)
+
+/* 28-byte record, layout-compatible with cv::KeyPoint (pt.x, pt.y, size, angle, response,
+ * octave, class_id) as filled by orbextractor.cpp:961-988 and :631-639. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+/* Replaces the five constructor arguments of OrbExtractor (orbextractor.cpp:476) plus the
+ * capacity knobs a device arena needs. */
+typedef struct {
+    int nfeatures;        /* ORBextractor.nFeatures   (tracking.cpp:104) */
+    float scale_factor;   /* ORBextractor.scaleFactor (tracking.cpp:105) */
+    int nlevels;          /* ORBextractor.nLevels     (tracking.cpp:106), 1..ORBX_MAX_LEVELS */
+    int ini_th_fast;      /* ORBextractor.iniThFAST   (tracking.cpp:107) */
+    int min_th_fast;      /* ORBextractor.minThFAST   (tracking.cpp:108) */
+    int max_width;        /* largest image width  this handle will be given */
+    int max_height;       /* largest image height this handle will be given */
+    int max_batch;        /* frames per orbx_extract_batch call (>=1)       */
+    int device;           /* CUDA device ordinal                            */
+    int blur_taps[7];     /* 7-tap integer Gaussian (sum ~256); all zero -> {18,34,48,56,48,34,18},
+                             the taps of the executable oracle cv2 4.13             */
+    int tie_rule;         /* DistributeOctTree equal-size tie (orbextractor.cpp:825 sorts by heap
+                             address): 0 = newest node first (canonical), 1 = oldest first          */
+} orbx_config;
+
+typedef struct orbx_extractor orbx_extractor;
+
+/* OrbExtractor::OrbExtractor, orbextractor.cpp:476-548 */
+int orbx_create(const orbx_config *cfg, orbx_extractor **out);
+/* OrbExtractor::~OrbExtractor, orbextractor.cpp:552 */
+void orbx_destroy(orbx_extractor *h);
+/* text of the last error on this handle (never NULL) */
+const char *orbx_last_error(const orbx_extractor *h);
+
+/* OrbExtractor::ExtractFeatures, orbextractor.cpp:582-642: one 8-bit single-channel image
+ * (rows `pitch` bytes apart) -> up to kp_cap keypoints and kp_cap x 32 descriptor bytes,
+ * *n_out = number written.  kp_cap >= orbx_max_keypoints(h) always suffices. */
+int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, size_t pitch,
+                 orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
+
+/* The same for `batch` independent images of one size (stereo pairs / multi-frame batches;
+ * the reference runs these as separate ExtractFeatures calls, orbframe.cpp:73-76).
+ * Frame f writes kps[f*kp_cap ...], desc[f*kp_cap*32 ...], n_out[f]. */
+int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
+                       size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
+
+/* Device-resident variant: frames already in HBM (frame f at d_imgs + f*frame_stride), results
+ * stay in HBM.  Work is enqueued on `stream` (a cudaStream_t, NULL = the handle's own stream)
+ * and NOT synchronised.  Result pointers (valid until the next call on this handle):
+ * orbx_device_results. */
+int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t frame_stride, size_t pitch,
+                              int batch, int width, int height, void *stream);
+/* d_kps: batch x kp_stride records; d_desc: batch x kp_stride x 32 bytes; d_counts: batch ints */
+int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
+                        const int **d_counts, int *kp_stride);
+
+/* upper bound of keypoints per frame for this configuration */
+int orbx_max_keypoints(const orbx_extractor *h);
+
+/* m_vImagePyramid[level] of frame `frame` of the last call (orbextractor.hpp:109; read by
+ * OrbFrame::ComputeStereoMatches, orbframe.cpp:518,618-641).  Copies the level lazily to a
+ * pinned host buffer owned by the handle; pointer valid until the next extract call. */
+int orbx_get_level(orbx_extractor *h, int frame, int level, const uint8_t **host_ptr,
+                   int *width, int *height, size_t *pitch);
+
+/* getLevels / getScaleFactors / getInverseScaleFactors / getScaleSigmaSquares /
+ * getInverseScaleSigmaSquares (orbextractor.cpp:557-579) and the per-level quotas (:512-523).
+ * Any pointer may be NULL; arrays need nlevels entries. Returns nlevels. */
+int orbx_scale_tables(const orbx_extractor *h, float *scale, float *inv_scale, float *sigma2,
+                      float *inv_sigma2, int *quota);
+
+/* ---- stage taps for parity tests (host copies of device intermediates of the last call) ---- */
+/* blurred level (the GaussianBlur output of orbextractor.cpp:621-622), tightly packed w*h bytes */
+int orbx_debug_blurred(orbx_extractor *h, int frame, int level, uint8_t *dst, size_t dst_bytes, int *width, int *height);
+/* enable recording of the gridded-FAST candidates (orbextractor.cpp:930-970) for the next calls */
+int orbx_debug_enable_candidates(orbx_extractor *h, int enable);
+/* candidates of (frame, level): coords relative to (16,16) like vToDistributeKeys; unordered.
+ * Returns count (<= cap written) or <0. */
+int orbx_debug_candidates(orbx_extractor *h, int frame, int level, int *xs, int *ys, int *score, int cap);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Matcher: ORBmatcher::DescriptorDistance (orbmatcher.cpp:1662-1677) evaluated for every     */
+/* query x train pair, with the reference's best / second-best bookkeeping                     */
+/* (orbmatcher.cpp:208-232: strict '<' updates, start values 256, index -1).                   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct orbm_matcher orbm_matcher;
+
+int orbm_create(int device, int max_queries, int max_train, orbm_matcher **out);
+void orbm_destroy(orbm_matcher *m);
+const char *orbm_last_error(const orbm_matcher *m);
+
+/* host buffers: q = nq x 32 bytes, t = nt x 32 bytes -> idx[nq] (lowest train index attaining
+ * the minimum, -1 if nt == 0), d1[nq] (minimum), d2[nq] (second smallest with multiplicity). */
+int orbm_knn2(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt,
+              int32_t *idx, int32_t *d1, int32_t *d2);
+/* upload / replace the resident train set (map-point descriptors) once, then match many
+ * query blocks against it */
+int orbm_set_train(orbm_matcher *m, const uint8_t *t, int nt);
+int orbm_knn2_resident(orbm_matcher *m, const uint8_t *q, int nq, int32_t *idx, int32_t *d1, int32_t *d2);
+/* device-resident variant, enqueued on `stream` (NULL = matcher's stream), not synchronised.
+ * d_out = nq x {int32 idx, int32 d1, int32 d2, int32 pad} (16-byte records, ready to be the send
+ * buffer of the result gather when queries are sharded over GPUs). */
+int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
+                     int32_t *d_out, void *stream);
+/* DescriptorDistance for n independent pairs a[i], b[i] (32 bytes each) -> out[i] */
+int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *out);
+
+/* library build info: "orbx <version> sm_100a" */
+const char *orbx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

@@ -1,0 +1,563 @@
+// orbx_api.cu -- C ABI of the extractor (include/orbx.h): geometry, arenas, launch sequence.
+//
+// Host-side restatement of OrbExtractor's constructor tables (orbextractor.cpp:476-548) and of
+// the per-level geometry of ComputePyramid / ComputeKeyPointsOctTree / DistributeOctTree
+// (orbextractor.cpp:654-699, :906-947) with the reference's exact float32 / integer expressions.
+// No pixel arithmetic happens on the host: there is no CPU fallback in this library.
+#include "../../include/orbx.h"
+#include "orbx_internal.h"
+#include "orbx_kernels.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+inline int cvRoundF(float v) { return (int)lrintf(v); }   // SSE cvtss2si: round half to even
+inline int cvRoundD(double v) { return (int)lrint(v); }
+inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
+inline int cvCeilD(double v) { int i = (int)v; return i + (i < v); }
+inline int alignUp(int v, int a) { return (v + a - 1) / a * a; }
+
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <typename T> struct PinBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMallocHost((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+} // namespace
+
+struct orbx_extractor {
+    orbx_config cfg;
+    // constructor tables
+    float sf[ORBX_MAXL], invSf[ORBX_MAXL], sigma2[ORBX_MAXL], invSigma2[ORBX_MAXL];
+    int quota[ORBX_MAXL];
+    int umax[16];
+    int taps[7];
+    // geometry of the current image size
+    int curW = 0, curH = 0;
+    OrbxLayout L;
+    std::vector<OrbxCell> cells;
+    std::vector<OrbxRTab> rtab;
+    int maxRows = 0, maxNodes = 0, pow2Nodes = 0;
+    bool geomUploaded = false;
+    // device state
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t stream2 = nullptr;
+    DevBuf<uint8_t> dPyr, dBlur, dDesc;
+    DevBuf<uint32_t> dCnt;
+    DevBuf<unsigned long long> dBest;
+    DevBuf<int2> dSlots;
+    DevBuf<int> dLvlCount, dCounts, dDbgCount;
+    DevBuf<orbx_keypoint_pod> dKps;
+    DevBuf<OrbxCell> dCells;
+    DevBuf<OrbxRTab> dRtab;
+    DevBuf<OrbxDbgCand> dDbg;
+    PinBuf<uint8_t> hIn, hDesc, hLevel;
+    PinBuf<orbx_keypoint_pod> hKps;
+    PinBuf<int> hCounts;
+    int dbgEnabled = 0, dbgCap = 0;
+    int lastBatch = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(orbx_extractor *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+int failCuda(orbx_extractor *h, cudaError_t e, const char *where)
+{
+    return fail(h, ORBX_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return failCuda(h, e_, #call);         \
+    } while (0)
+
+// constructor tables, orbextractor.cpp:492-547
+void buildTables(orbx_extractor *h)
+{
+    const orbx_config &c = h->cfg;
+    const int nl = c.nlevels;
+    h->sf[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; i++) {
+        h->sf[i] = h->sf[i - 1] * c.scale_factor;
+        h->sigma2[i] = h->sf[i] * h->sf[i];
+    }
+    for (int i = 0; i < nl; i++) {
+        h->invSf[i] = 1.0f / h->sf[i];
+        h->invSigma2[i] = 1.0f / h->sigma2[i];
+    }
+    float factor = 1.0f / c.scale_factor;
+    float nDesired = c.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        h->quota[l] = cvRoundF(nDesired);
+        sum += h->quota[l];
+        nDesired *= factor;
+    }
+    h->quota[nl - 1] = std::max(c.nfeatures - sum, 0);
+    const int HP = 15;
+    int v, v0, vmax = cvFloorD(HP * sqrtf(2.f) / 2 + 1);
+    int vmin = cvCeilD(HP * sqrtf(2.f) / 2);
+    const double hp2 = HP * HP;
+    for (v = 0; v <= vmax; ++v) h->umax[v] = cvRoundD(sqrt(hp2 - v * v));
+    for (v = HP, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// bilinear coefficient table of one axis, SURVEY A.1
+void axisTable(int ssize, int dsize, OrbxRTab *out)
+{
+    const double invScale = (double)dsize / ssize;
+    const double scale = 1.0 / invScale;
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cvFloorD(f);
+        f -= s;
+        if (s < 0) { f = 0; s = 0; }
+        if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        out[d].ofs = (int16_t)s;
+        out[d].c0 = (int16_t)cvRoundF((1.f - f) * 2048.f);
+        out[d].c1 = (int16_t)cvRoundF(f * 2048.f);
+        out[d].pad = 0;
+    }
+}
+
+// geometry for an image size; returns ORBX_OK or ORBX_ERR_SHAPE with a message
+int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<OrbxCell> &cells,
+                  std::vector<OrbxRTab> &rtab, int &maxRows, int &maxNodes)
+{
+    const orbx_config &c = h->cfg;
+    memset(&L, 0, sizeof(L));
+    cells.clear(); rtab.clear();
+    L.nlevels = c.nlevels; L.iniTh = c.ini_th_fast; L.minTh = c.min_th_fast; L.tieRule = c.tie_rule;
+    long long off = 0;
+    int rows = 0, slots = 0;
+    maxRows = 0; maxNodes = 0;
+    char msg[256];
+    for (int l = 0; l < c.nlevels; l++) {
+        OrbxLevel &v = L.lv[l];
+        const float scale = h->invSf[l];
+        v.w = cvRoundF((float)w * scale);   // orbextractor.cpp:659
+        v.h = cvRoundF((float)h0 * scale);
+        v.pitch = alignUp(v.w, 128);
+        if (off + (long long)v.pitch * v.h > 0x7fffffffLL) return fail(h, ORBX_ERR_SHAPE, "pyramid slab exceeds 2 GiB per frame");
+        v.off = (int)off;
+        off += (long long)v.pitch * v.h;
+        // gridded FAST geometry, :914-928
+        const int maxBX = v.w - ORBX_EDGE + 3, maxBY = v.h - ORBX_EDGE + 3;
+        const float width = (float)(maxBX - ORBX_MINB), height = (float)(maxBY - ORBX_MINB);
+        v.nCols = (int)(width / ORBX_CELL_W);
+        v.nRows = (int)(height / ORBX_CELL_W);
+        if (v.nCols < 1 || v.nRows < 1) {
+            snprintf(msg, sizeof msg, "level %d is %dx%d: smaller than one 30-px FAST cell (the reference divides by zero, orbextractor.cpp:924-927)", l, v.w, v.h);
+            return fail(h, ORBX_ERR_SHAPE, msg);
+        }
+        v.wCell = (int)ceilf(width / v.nCols);
+        v.hCell = (int)ceilf(height / v.nRows);
+        if (v.wCell > 60 || v.hCell > 60 || (long long)v.nCols * v.nRows >= 65536) return fail(h, ORBX_ERR_SHAPE, "FAST grid outside supported range");
+        v.cellBase = (int)cells.size();
+        for (int i = 0; i < v.nRows; i++) {
+            const int iniY = ORBX_MINB + i * v.hCell;
+            int maxY = iniY + v.hCell + 6;
+            if (iniY >= maxBY - 3) continue;    // :935
+            if (maxY > maxBY) maxY = maxBY;
+            for (int j = 0; j < v.nCols; j++) {
+                const int iniX = ORBX_MINB + j * v.wCell;
+                int maxX = iniX + v.wCell + 6;
+                if (iniX >= maxBX - 6) continue; // :944
+                if (maxX > maxBX) maxX = maxBX;
+                OrbxCell cell;
+                cell.x0 = (uint16_t)iniX; cell.y0 = (uint16_t)iniY;
+                cell.w = (uint8_t)(maxX - iniX); cell.h = (uint8_t)(maxY - iniY);
+                cell.level = (uint8_t)l; cell.pad = 0;
+                cell.orderBase = (uint32_t)(i * v.nCols + j) << 12;
+                cells.push_back(cell);
+            }
+        }
+        v.nCells = (int)cells.size() - v.cellBase;
+        // DistributeOctTree geometry, :684-699
+        v.W = maxBX - ORBX_MINB; v.H = maxBY - ORBX_MINB;
+        if (v.H <= 0 || v.W / v.H < 1) {
+            snprintf(msg, sizeof msg, "level %d is %dx%d: portrait shapes make nIni = 0 in the reference (division by zero, orbextractor.cpp:684-686)", l, v.w, v.h);
+            return fail(h, ORBX_ERR_SHAPE, msg);
+        }
+        v.nIni = (int)round((double)(v.W / v.H));
+        v.hX = v.W / v.nIni;
+        // largest candidate x (relative) is W-4; the reference indexes vpIniNodes[x/hX] unchecked (:710)
+        if (v.nIni > ORBX_MAX_STRIPS || (v.W - 4) / v.hX >= v.nIni || v.H > 8191 || v.W > 16383) {
+            snprintf(msg, sizeof msg, "level %d is %dx%d: aspect ratio outside the supported range (nIni=%d)", l, v.w, v.h, v.nIni);
+            return fail(h, ORBX_ERR_SHAPE, msg);
+        }
+        v.quota = h->quota[l];
+        v.rowBase = rows;
+        rows += v.nIni * v.H;
+        maxRows = std::max(maxRows, v.nIni * v.H);
+        v.slotBase = slots;
+        v.slotCap = std::max(v.quota, 2 * v.nIni);   // list never exceeds max(N, first-pass size)
+        if (v.slotCap > ORBX_MAX_NODES) return fail(h, ORBX_ERR_SHAPE, "per-level feature quota exceeds 4096");
+        slots += v.slotCap;
+        maxNodes = std::max(maxNodes, v.slotCap + 2);
+        v.sf = h->sf[l];
+        v.kpSize = 31 * (int)h->sf[l];   // :978 int cast before the multiply
+        if (l > 0) {
+            const OrbxLevel &p = L.lv[l - 1];
+            v.xtabOff = (int)rtab.size();
+            rtab.resize(rtab.size() + v.w);
+            axisTable(p.w, v.w, &rtab[v.xtabOff]);
+            v.ytabOff = (int)rtab.size();
+            rtab.resize(rtab.size() + v.h);
+            axisTable(p.h, v.h, &rtab[v.ytabOff]);
+        }
+    }
+    L.slab = (off + 255) / 256 * 256;
+    L.rowsPerFrame = rows;
+    L.slotsPerFrame = slots;
+    L.kpStride = slots;
+    L.totalCells = (int)cells.size();
+    return ORBX_OK;
+}
+
+int ensureArenas(orbx_extractor *h, int batch)
+{
+    const OrbxLayout &L = h->L;
+    CK(h->dPyr.ensure((size_t)L.slab * batch + 256));
+    CK(h->dBlur.ensure((size_t)L.slab * batch + 256));
+    CK(h->dCnt.ensure((size_t)L.rowsPerFrame * batch));
+    CK(h->dBest.ensure((size_t)L.rowsPerFrame * batch));
+    CK(h->dSlots.ensure((size_t)L.slotsPerFrame * batch));
+    CK(h->dLvlCount.ensure((size_t)L.nlevels * batch));
+    CK(h->dCounts.ensure((size_t)batch));
+    CK(h->dKps.ensure((size_t)L.kpStride * batch));
+    CK(h->dDesc.ensure((size_t)L.kpStride * batch * 32));
+    if (h->dbgEnabled) {
+        h->dbgCap = 0;
+        for (int l = 0; l < L.nlevels; l++) h->dbgCap = std::max(h->dbgCap, (L.lv[l].w * L.lv[l].h) / 4 + 64);
+        CK(h->dDbg.ensure((size_t)h->dbgCap * L.nlevels * batch));
+        CK(h->dDbgCount.ensure((size_t)L.nlevels * batch));
+    }
+    return ORBX_OK;
+}
+
+int setGeometry(orbx_extractor *h, int w, int hh)
+{
+    if (w == h->curW && hh == h->curH && h->geomUploaded) return ORBX_OK;
+    OrbxLayout L; std::vector<OrbxCell> cells; std::vector<OrbxRTab> rtab; int maxRows, maxNodes;
+    int rc = buildGeometry(h, w, hh, L, cells, rtab, maxRows, maxNodes);
+    if (rc != ORBX_OK) return rc;
+    h->L = L; h->cells.swap(cells); h->rtab.swap(rtab);
+    h->maxRows = maxRows; h->maxNodes = maxNodes;
+    int p2 = 2; while (p2 < maxNodes) p2 <<= 1;
+    h->pow2Nodes = p2;
+    if (octree_smem_bytes(maxRows, maxNodes, p2) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
+    CK(h->dCells.ensure(h->cells.size()));
+    CK(h->dRtab.ensure(std::max<size_t>(h->rtab.size(), 1)));
+    // the stream may still be reading the old tables
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(h->dCells.p, h->cells.data(), h->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, h->stream));
+    if (!h->rtab.empty())
+        CK(cudaMemcpyAsync(h->dRtab.p, h->rtab.data(), h->rtab.size() * sizeof(OrbxRTab), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->curW = w; h->curH = hh; h->geomUploaded = true;
+    return ORBX_OK;
+}
+
+// enqueue every stage after level 0 is in place
+int enqueuePipeline(orbx_extractor *h, int batch, cudaStream_t st)
+{
+    const OrbxLayout &L = h->L;
+    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, h->dRtab.p, batch, st);
+    // blur only depends on the pyramid: run it on the side stream, beside FAST + octree
+    CK(cudaEventRecord(h->evFork, st));
+    CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
+    for (int l = 0; l < L.nlevels; l++) launch_blur(h->dPyr.p, h->dBlur.p, L, l, h->taps, batch, h->stream2);
+    CK(cudaEventRecord(h->evJoin, h->stream2));
+
+    CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
+    OrbxDbgCand *dbg = nullptr; int *dbgCount = nullptr;
+    if (h->dbgEnabled) {
+        dbg = h->dDbg.p; dbgCount = h->dDbgCount.p;
+        CK(cudaMemsetAsync(dbgCount, 0, (size_t)L.nlevels * batch * sizeof(int), st));
+    }
+    launch_fast(h->dPyr.p, L, h->dCells.p, h->dCnt.p, h->dBest.p, dbg, dbgCount, h->dbgCap, batch, st);
+    CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
+    CK(cudaStreamWaitEvent(st, h->evJoin, 0));
+    launch_describe(h->dPyr.p, h->dBlur.p, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
+    CK(cudaGetLastError());
+    h->lastBatch = batch;
+    return ORBX_OK;
+}
+
+bool isPinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *orbx_version(void) { return "orbx 0.1 sm_100a"; }
+
+int orbx_create(const orbx_config *cfg, orbx_extractor **out)
+{
+    if (!cfg || !out) return ORBX_ERR_ARG;
+    *out = nullptr;
+    if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
+        cfg->min_th_fast < 1 || cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
+        cfg->max_batch < 1 || cfg->max_width < 1 || cfg->max_height < 1)
+        return ORBX_ERR_ARG;
+    orbx_extractor *h = new (std::nothrow) orbx_extractor();
+    if (!h) return ORBX_ERR_NOMEM;
+    h->cfg = *cfg;
+    bool zero = true;
+    for (int k = 0; k < 7; k++) zero = zero && cfg->blur_taps[k] == 0;
+    static const int kDefaultTaps[7] = {18, 34, 48, 56, 48, 34, 18};
+    for (int k = 0; k < 7; k++) h->taps[k] = zero ? kDefaultTaps[k] : cfg->blur_taps[k];
+    buildTables(h);
+    *out = h; // returned even on failure below so the caller can read orbx_last_error, then destroy
+    int devCount = 0;
+    cudaError_t e = cudaGetDeviceCount(&devCount);
+    if (e != cudaSuccess || devCount <= cfg->device || cfg->device < 0) {
+        cudaGetLastError();
+        return fail(h, ORBX_ERR_CUDA, e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e)
+                                                        : std::string("device ordinal out of range"));
+    }
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(h, ORBX_ERR_CUDA, "liborbx is built for sm_100a only (no other code path exists)");
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    // size the arenas for the declared maximum so the hot path never allocates
+    int rc = setGeometry(h, cfg->max_width, cfg->max_height);
+    if (rc != ORBX_OK) return rc;
+    rc = ensureArenas(h, cfg->max_batch);
+    if (rc != ORBX_OK) return rc;
+    CK(h->hKps.ensure((size_t)h->L.kpStride * cfg->max_batch));
+    CK(h->hDesc.ensure((size_t)h->L.kpStride * cfg->max_batch * 32));
+    CK(h->hCounts.ensure((size_t)cfg->max_batch));
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_extractor *h)
+{
+    if (!h) return;
+    if (h->stream) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->stream); }
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    h->dPyr.release(); h->dBlur.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
+    h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
+    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dDbg.release();
+    h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    delete h;
+}
+
+const char *orbx_last_error(const orbx_extractor *h) { return h ? h->err.c_str() : "null handle"; }
+
+int orbx_max_keypoints(const orbx_extractor *h) { return h ? h->L.kpStride : ORBX_ERR_ARG; }
+
+int orbx_scale_tables(const orbx_extractor *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int *quota)
+{
+    if (!h) return ORBX_ERR_ARG;
+    for (int l = 0; l < h->cfg.nlevels; l++) {
+        if (scale) scale[l] = h->sf[l];
+        if (inv_scale) inv_scale[l] = h->invSf[l];
+        if (sigma2) sigma2[l] = h->sigma2[l];
+        if (inv_sigma2) inv_sigma2[l] = h->invSigma2[l];
+        if (quota) quota[l] = h->quota[l];
+    }
+    return h->cfg.nlevels;
+}
+
+int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t frame_stride, size_t pitch,
+                              int batch, int width, int height, void *stream)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!d_imgs || batch < 1 || batch > h->cfg.max_batch || width < 1 || height < 1 || pitch < (size_t)width)
+        return fail(h, ORBX_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = setGeometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    rc = ensureArenas(h, batch);
+    if (rc != ORBX_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
+    return enqueuePipeline(h, batch, st);
+}
+
+int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
+                        const int **d_counts, int *kp_stride)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (d_kps) *d_kps = (const orbx_keypoint *)h->dKps.p;
+    if (d_desc) *d_desc = h->dDesc.p;
+    if (d_counts) *d_counts = h->dCounts.p;
+    if (kp_stride) *kp_stride = h->L.kpStride;
+    return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
+                       size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!imgs || !kps || !desc || !n_out || batch < 1 || batch > h->cfg.max_batch || width < 1 || height < 1 ||
+        pitch < (size_t)width || kp_cap < 1)
+        return fail(h, ORBX_ERR_ARG, "bad argument");
+    for (int f = 0; f < batch; f++) if (!imgs[f]) return fail(h, ORBX_ERR_ARG, "null image pointer");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = setGeometry(h, width, height);
+    if (rc != ORBX_OK) return rc;
+    rc = ensureArenas(h, batch);
+    if (rc != ORBX_OK) return rc;
+    const OrbxLayout &L = h->L;
+    const OrbxLevel &l0 = L.lv[0];
+    cudaStream_t st = h->stream;
+    // H2D straight into the level-0 slot of each frame's slab (level 0 of ComputePyramid is a copy)
+    const bool pinned = isPinned(imgs[0]) && isPinned(imgs[batch - 1]);
+    if (!pinned) CK(h->hIn.ensure((size_t)width * height * batch));
+    for (int f = 0; f < batch; f++) {
+        const uint8_t *src = imgs[f];
+        size_t sp = pitch;
+        if (!pinned) {
+            uint8_t *stage = h->hIn.p + (size_t)f * width * height;
+            for (int y = 0; y < height; y++) memcpy(stage + (size_t)y * width, imgs[f] + (size_t)y * pitch, width);
+            src = stage; sp = width;
+        }
+        CK(cudaMemcpy2DAsync(h->dPyr.p + (size_t)f * L.slab + l0.off, l0.pitch, src, sp, width, height,
+                             cudaMemcpyHostToDevice, st));
+    }
+    rc = enqueuePipeline(h, batch, st);
+    if (rc != ORBX_OK) return rc;
+    CK(h->hKps.ensure((size_t)L.kpStride * batch));
+    CK(h->hDesc.ensure((size_t)L.kpStride * batch * 32));
+    CK(h->hCounts.ensure((size_t)batch));
+    CK(cudaMemcpyAsync(h->hCounts.p, h->dCounts.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hKps.p, h->dKps.p, sizeof(orbx_keypoint_pod) * (size_t)L.kpStride * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hDesc.p, h->dDesc.p, (size_t)L.kpStride * batch * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < batch; f++) {
+        const int n = h->hCounts.p[f];
+        if (n > kp_cap) {
+            char msg[128];
+            snprintf(msg, sizeof msg, "frame %d produced %d keypoints, kp_cap is %d", f, n, kp_cap);
+            return fail(h, ORBX_ERR_CAPACITY, msg);
+        }
+        memcpy(kps + (size_t)f * kp_cap, h->hKps.p + (size_t)f * L.kpStride, sizeof(orbx_keypoint) * n);
+        memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
+        n_out[f] = n;
+    }
+    return ORBX_OK;
+}
+
+int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, size_t pitch,
+                 orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
+{
+    const uint8_t *imgs[1] = {img};
+    return orbx_extract_batch(h, imgs, 1, width, height, pitch, kps, kp_cap, desc, n_out);
+}
+
+int orbx_get_level(orbx_extractor *h, int frame, int level, const uint8_t **host_ptr, int *width, int *height, size_t *pitch)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!host_ptr || frame < 0 || frame >= h->lastBatch || level < 0 || level >= h->L.nlevels)
+        return fail(h, ORBX_ERR_ARG, "bad frame/level");
+    CK(cudaSetDevice(h->cfg.device));
+    const OrbxLevel &l = h->L.lv[level];
+    // one pinned buffer holding all levels of all frames of the last call, filled lazily per level
+    CK(h->hLevel.ensure((size_t)h->L.slab * h->cfg.max_batch));
+    uint8_t *dst = h->hLevel.p + (size_t)frame * h->L.slab + l.off;
+    CK(cudaMemcpyAsync(dst, h->dPyr.p + (size_t)frame * h->L.slab + l.off, (size_t)l.pitch * l.h, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *host_ptr = dst;
+    if (width) *width = l.w;
+    if (height) *height = l.h;
+    if (pitch) *pitch = (size_t)l.pitch;
+    return ORBX_OK;
+}
+
+int orbx_debug_blurred(orbx_extractor *h, int frame, int level, uint8_t *dst, size_t dst_bytes, int *width, int *height)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!dst || frame < 0 || frame >= h->lastBatch || level < 0 || level >= h->L.nlevels)
+        return fail(h, ORBX_ERR_ARG, "bad frame/level");
+    const OrbxLevel &l = h->L.lv[level];
+    if (dst_bytes < (size_t)l.w * l.h) return fail(h, ORBX_ERR_CAPACITY, "dst too small");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy2D(dst, l.w, h->dBlur.p + (size_t)frame * h->L.slab + l.off, l.pitch, l.w, l.h, cudaMemcpyDeviceToHost));
+    if (width) *width = l.w;
+    if (height) *height = l.h;
+    return ORBX_OK;
+}
+
+int orbx_debug_enable_candidates(orbx_extractor *h, int enable)
+{
+    if (!h) return ORBX_ERR_ARG;
+    h->dbgEnabled = enable ? 1 : 0;
+    return ORBX_OK;
+}
+
+int orbx_debug_candidates(orbx_extractor *h, int frame, int level, int *xs, int *ys, int *score, int cap)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!h->dbgEnabled || !h->dDbg.p || frame < 0 || frame >= h->lastBatch || level < 0 || level >= h->L.nlevels)
+        return fail(h, ORBX_ERR_ARG, "candidate recording not enabled or bad frame/level");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const int slot = frame * h->L.nlevels + level;
+    int n = 0;
+    CK(cudaMemcpy(&n, h->dDbgCount.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    if (n > h->dbgCap) return fail(h, ORBX_ERR_CAPACITY, "candidate debug buffer overflow");
+    std::vector<OrbxDbgCand> tmp((size_t)std::max(n, 1));
+    if (n > 0) CK(cudaMemcpy(tmp.data(), h->dDbg.p + (size_t)slot * h->dbgCap, sizeof(OrbxDbgCand) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < cap; i++) {
+        xs[i] = tmp[i].xy & 0xffff; ys[i] = tmp[i].xy >> 16; score[i] = tmp[i].score;
+    }
+    return n;
+}
+
+} // extern "C"

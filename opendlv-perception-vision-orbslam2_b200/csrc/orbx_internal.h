@@ -1,0 +1,57 @@
+// orbx_internal.h -- shared host/device structures of liborbx (not part of the ABI).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#define ORBX_MAXL 16
+#define ORBX_EDGE 19           // EDGE_THRESHOLD, orbextractor.cpp:135
+#define ORBX_MINB 16           // EDGE_THRESHOLD-3, orbextractor.cpp:914
+#define ORBX_CELL_W 30.0f      // W, orbextractor.cpp:910
+#define ORBX_MAX_STRIPS 8      // nIni supported by the node packing (3 bits)
+#define ORBX_MAX_NODES 4096    // per-level node list capacity (quota + 2*nIni must fit)
+
+// Per-level geometry.  Everything here is a pure function of (config, image size) and is
+// computed once on the host with the reference's exact float32 expressions.
+struct OrbxLevel {
+    int w, h;            // level size, orbextractor.cpp:659
+    int pitch;           // bytes between rows of this level in the pyramid slab (multiple of 128)
+    int off;             // byte offset of the level inside one frame's slab
+    // gridded FAST, orbextractor.cpp:914-928
+    int nCols, nRows, wCell, hCell;
+    int cellBase, nCells; // processed cells of this level inside the cell table
+    // DistributeOctTree, orbextractor.cpp:684-699
+    int W, H;            // maxX-minX, maxY-minY
+    int nIni, hX, quota;
+    int rowBase;         // first entry of this level in the per-frame row-summary arrays
+    int slotBase, slotCap; // keypoint slots of this level inside a frame
+    // post-processing, orbextractor.cpp:978, :631-637
+    float sf;
+    int kpSize;          // 31 * (int)sf
+    // resize coefficient tables (entries of OrbxRTab), level l built from level l-1
+    int xtabOff, ytabOff;
+};
+
+struct OrbxLayout {
+    int nlevels;
+    int rowsPerFrame;    // sum over levels of nIni*H
+    int slotsPerFrame;   // sum over levels of slotCap
+    int kpStride;        // records per frame in the output arrays (>= slotsPerFrame)
+    int iniTh, minTh;
+    int tieRule;
+    int totalCells;
+    long long slab;      // pyramid bytes per frame
+    OrbxLevel lv[ORBX_MAXL];
+};
+
+// one processed FAST cell (window = cell + 3 px margin each side, clipped to the level border)
+struct OrbxCell {
+    uint16_t x0, y0;     // window origin in level coordinates (iniX, iniY)
+    uint8_t w, h;        // window size (maxX-iniX, maxY-iniY) <= 66
+    uint8_t level, pad;
+    uint32_t orderBase;  // (cellRow*nCols + cellCol) << 12 : position in the reference's emission order
+};
+
+// bilinear coefficient entry, SURVEY A.1
+struct OrbxRTab { int16_t ofs, c0, c1, pad; };
+
+struct OrbxDbgCand { int32_t xy; int32_t score; };

@@ -1,0 +1,19 @@
+// orbx_kernels.h -- launchers of the extractor kernels (internal).
+#pragma once
+#include "orbx_internal.h"
+#include <cuda_runtime.h>
+
+struct orbx_keypoint_pod { float x, y, size, angle, response; int32_t octave, class_id; };
+
+void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch, uint8_t *pyr,
+                        const OrbxLayout &L, int batch, cudaStream_t st);
+void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const OrbxRTab *tabs, int batch, cudaStream_t st);
+void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, int level, const int taps[7], int batch, cudaStream_t st);
+void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, uint32_t *cnt,
+                 unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st);
+size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes);
+cudaError_t launch_octree(const OrbxLayout &L, uint32_t *cnt, const unsigned long long *best, int2 *slots,
+                          int *lvlCount, int maxRows, int maxNodes, int pow2Nodes, int batch, cudaStream_t st);
+void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &L, const int2 *slots,
+                     const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
+                     int batch, cudaStream_t st);

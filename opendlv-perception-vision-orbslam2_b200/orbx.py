@@ -1,0 +1,238 @@
+"""ctypes binding of liborbx.so (include/orbx.h) for tests, bench.py and Python users.
+
+The classes mirror the reference's interface for this path:
+  Extractor  <->  OrbExtractor   (include/orbextractor.hpp:90-109 of the reference)
+  Matcher    <->  ORBmatcher::DescriptorDistance + best/second-best loop (orbmatcher.hpp:48)
+There is no fallback: if liborbx.so is missing or no sm_100 GPU is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbx.so")
+MAX_LEVELS = 16
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_SHAPE", -3: "ERR_CAPACITY", -4: "ERR_CUDA", -5: "ERR_NOMEM"}
+
+
+class Config(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int), ("max_width", C.c_int),
+                ("max_height", C.c_int), ("max_batch", C.c_int), ("device", C.c_int),
+                ("blur_taps", C.c_int * 7), ("tie_rule", C.c_int)]
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_max_keypoints", "orbx_get_level",
+           "orbx_scale_tables", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
+           "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
+           "orbm_knn2_device", "orbm_distance_pairs"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.orbx_version.restype = C.c_char_p
+    L.orbx_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_last_error.argtypes = [vp]
+    L.orbx_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, ip]
+    L.orbx_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
+    L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
+    L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
+    L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
+    L.orbx_debug_blurred.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, ip, ip]
+    L.orbx_debug_enable_candidates.argtypes = [vp, C.c_int]
+    L.orbx_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
+    L.orbm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.orbm_destroy.argtypes = [vp]
+    L.orbm_last_error.restype = C.c_char_p
+    L.orbm_last_error.argtypes = [vp]
+    L.orbm_knn2.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.orbm_set_train.argtypes = [vp, vp, C.c_int]
+    L.orbm_knn2_resident.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.orbm_knn2_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Extractor:
+    """OrbExtractor(nFeatures, scaleFactor, nLevels, iniThFAST, minThFAST) on a B200."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 max_width=1241, max_height=376, max_batch=1, device=0, taps=None, tie_rule=0):
+        cfg = Config(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width, max_height, max_batch, device,
+                     (C.c_int * 7)(*(taps if taps is not None else [0] * 7)), tie_rule)
+        self._h = C.c_void_p()
+        rc = lib().orbx_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbx_last_error(self._h).decode() if self._h else "invalid configuration"
+            if self._h:
+                lib().orbx_destroy(self._h)
+                self._h = None
+            raise OrbxError(rc, msg)
+        self.nlevels, self.nfeatures, self.max_batch = nlevels, nfeatures, max_batch
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbxError(rc, lib().orbx_last_error(self._h).decode())
+        return rc
+
+    @property
+    def max_keypoints(self):
+        return lib().orbx_max_keypoints(self._h)
+
+    # getters of orbextractor.cpp:557-579
+    def tables(self):
+        n = self.nlevels
+        arrs = [np.zeros(n, np.float32) for _ in range(4)] + [np.zeros(n, np.int32)]
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        self._check(lib().orbx_scale_tables(self._h, *[a.ctypes.data_as(fp) for a in arrs[:4]], arrs[4].ctypes.data_as(ip)))
+        return dict(zip(["scale", "inv_scale", "sigma2", "inv_sigma2", "quota"], arrs))
+
+    def extract(self, img):
+        """ExtractFeatures: 2-D uint8 array -> (keypoints[KP_DTYPE], descriptors[n,32])."""
+        kps, desc, counts = self.extract_batch([img])
+        return kps[0][:counts[0]].copy(), desc[0][:counts[0]].copy()
+
+    def extract_batch(self, imgs, out=None):
+        imgs = [i if (i.dtype == np.uint8 and i.ndim == 2 and i.strides[1] == 1) else np.ascontiguousarray(i, np.uint8) for i in imgs]
+        h, w = imgs[0].shape
+        pitch = imgs[0].strides[0]
+        for i in imgs:
+            if i.shape != (h, w) or i.strides[0] != pitch:
+                raise ValueError("all frames of a batch must share shape and pitch")
+        n = len(imgs)
+        cap = self.max_keypoints
+        if out is None:
+            out = (np.zeros((n, cap), KP_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32))
+        kps, desc, counts = out
+        ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+        self._check(lib().orbx_extract_batch(self._h, ptrs, n, w, h, pitch, _ptr(kps), kps.shape[1], _ptr(desc), _ptr(counts)))
+        return kps, desc, counts
+
+    def extract_batch_device(self, dptr, frame_stride, pitch, batch, width, height, stream=None):
+        """Frames already in HBM (raw device pointer); results stay in HBM (see device_results)."""
+        self._check(lib().orbx_extract_batch_device(self._h, C.c_void_p(dptr), frame_stride, pitch, batch, width, height,
+                                                    C.c_void_p(stream) if stream else None))
+
+    def device_results(self):
+        k, d, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(lib().orbx_device_results(self._h, C.byref(k), C.byref(d), C.byref(c), C.byref(s)))
+        return k.value, d.value, c.value, s.value
+
+    def level(self, frame, level):
+        """m_vImagePyramid[level] of `frame` of the last call, as a host array (copy)."""
+        p, w, h, pitch = C.c_void_p(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(lib().orbx_get_level(self._h, frame, level, C.byref(p), C.byref(w), C.byref(h), C.byref(pitch)))
+        buf = (C.c_uint8 * (pitch.value * h.value)).from_address(p.value)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, pitch.value)[:, :w.value].copy()
+
+    def blurred(self, frame, level, shape):
+        out = np.zeros(shape, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        self._check(lib().orbx_debug_blurred(self._h, frame, level, _ptr(out), out.size, C.byref(w), C.byref(h)))
+        assert (h.value, w.value) == tuple(shape)
+        return out
+
+    def enable_candidates(self, on=True):
+        self._check(lib().orbx_debug_enable_candidates(self._h, int(on)))
+
+    def candidates(self, frame, level, cap=1 << 22):
+        xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
+        n = self._check(lib().orbx_debug_candidates(self._h, frame, level, _ptr(xs), _ptr(ys), _ptr(sc), cap))
+        return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+class Matcher:
+    """Brute-force Hamming kNN-2 with the reference's best / second-best semantics."""
+
+    def __init__(self, max_queries=2000, max_train=100000, device=0):
+        self._h = C.c_void_p()
+        rc = lib().orbm_create(device, max_queries, max_train, C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbm_last_error(self._h).decode() if self._h else "invalid configuration"
+            if self._h:
+                lib().orbm_destroy(self._h)
+                self._h = None
+            raise OrbxError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbxError(rc, lib().orbm_last_error(self._h).decode())
+        return rc
+
+    def knn2(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        nq = len(q)
+        idx, d1, d2 = (np.zeros(nq, np.int32) for _ in range(3))
+        self._check(lib().orbm_knn2(self._h, _ptr(q), nq, _ptr(t), len(t), _ptr(idx), _ptr(d1), _ptr(d2)))
+        return idx, d1, d2
+
+    def set_train(self, t):
+        t = np.ascontiguousarray(t, np.uint8)
+        self._check(lib().orbm_set_train(self._h, _ptr(t), len(t)))
+
+    def knn2_resident(self, q):
+        q = np.ascontiguousarray(q, np.uint8)
+        nq = len(q)
+        idx, d1, d2 = (np.zeros(nq, np.int32) for _ in range(3))
+        self._check(lib().orbm_knn2_resident(self._h, _ptr(q), nq, _ptr(idx), _ptr(d1), _ptr(d2)))
+        return idx, d1, d2
+
+    def knn2_device(self, dq, nq, dt, nt, dout, stream=None):
+        self._check(lib().orbm_knn2_device(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, C.c_void_p(dout),
+                                           C.c_void_p(stream) if stream else None))
+
+    def distance_pairs(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+        out = np.zeros(len(a), np.int32)
+        self._check(lib().orbm_distance_pairs(self._h, _ptr(a), _ptr(b), len(a), _ptr(out)))
+        return out
+
+
+def ratio_test(d1, d2, ratio=0.7, th=100):
+    """Host-side acceptance exactly as the reference applies it (orbmatcher.cpp:234-236):
+    d1 <= TH and (float)d1 < ratio * (float)d2."""
+    d1f = d1.astype(np.float32); d2f = d2.astype(np.float32)
+    return (d1 <= th) & (d1f < np.float32(ratio) * d2f)

@@ -1,0 +1,117 @@
+// Minimal OpenCV header shim -- TEST INFRASTRUCTURE ONLY.
+//
+// Just enough of the cv:: surface for the reference's src/orbextractor.cpp to compile
+// UNMODIFIED (token census in SURVEY.md 8c).  OpenCV itself is a third-party dependency of the
+// reference (pinned 3.3.1, Dockerfile:29-31) whose source is not in the reference tree; the five
+// pixel primitives are therefore implemented by the C oracle (oracle/orb_oracle.c), each of which
+// is checked bit-for-bit against cv2 4.13 in tests/test_oracle_primitives.py.
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+typedef unsigned char uchar;
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_PI 3.1415926535897932384626433832795
+
+inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(float v) { return (int)lrintf(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
+inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
+
+namespace cv {
+
+template <typename T> struct Point_ {
+    T x, y;
+    Point_() : x(0), y(0) {}
+    Point_(T x_, T y_) : x(x_), y(y_) {}
+    Point_ &operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }
+};
+typedef Point_<int> Point2i;
+typedef Point2i Point;
+typedef Point_<float> Point2f;
+
+struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
+struct Rect { int x, y, width, height; Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {} };
+
+struct KeyPoint {
+    Point2f pt; float size, angle, response; int octave, class_id;
+    KeyPoint() : pt(), size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+    KeyPoint(float x, float y, float s, float a = -1, float r = 0, int o = 0, int c = -1)
+        : pt(x, y), size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
+static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
+
+struct MatZeros { int rows, cols; };
+
+class Mat {
+public:
+    int rows, cols;
+    size_t step;
+    uchar *data;
+    Mat() : rows(0), cols(0), step(0), data(nullptr) {}
+    Mat(Size sz, int) { alloc(sz.height, sz.width); }
+    Mat(int r, int c, int) { alloc(r, c); }
+    Mat(int r, int c, int, void *ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar *)ext) {}
+    static MatZeros zeros(int r, int c, int) { return MatZeros{r, c}; }
+    // Mat = MatExpr(zeros): OpenCV's create() keeps an existing buffer of the same size and zero-fills it in place
+    Mat &operator=(const MatZeros &z) {
+        if (rows != z.rows || cols != z.cols || !data) alloc(z.rows, z.cols);
+        for (int r = 0; r < rows; r++) memset(data + (size_t)r * step, 0, cols);
+        return *this;
+    }
+    void create(int r, int c, int) { if (r != rows || c != cols || !data) alloc(r, c); }
+    void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
+    Mat operator()(const Rect &r) const { Mat m(*this); m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
+    Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
+    Mat clone() const { Mat m; m.alloc(rows, cols); for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, cols); return m; }
+    template <typename T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step + c * sizeof(T)); }
+    template <typename T> const T &at(int r, int c) const { return *(const T *)(data + (size_t)r * step + c * sizeof(T)); }
+    uchar *ptr(int r = 0) { return data + (size_t)r * step; }
+    const uchar *ptr(int r = 0) const { return data + (size_t)r * step; }
+    size_t step1() const { return step; }
+    int type() const { return CV_8UC1; }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+private:
+    std::shared_ptr<std::vector<uchar>> buf;
+    void alloc(int r, int c) { buf = std::make_shared<std::vector<uchar>>((size_t)r * c); data = buf->data(); rows = r; cols = c; step = (size_t)c; }
+};
+
+class _InputArray {
+public:
+    _InputArray(const Mat &m) : m_(&m) {}
+    bool empty() const { return m_->empty(); }
+    Mat getMat() const { return *m_; }
+private:
+    const Mat *m_;
+};
+typedef const _InputArray &InputArray;
+
+class _OutputArray {
+public:
+    _OutputArray(Mat &m) : m_(&m) {}
+    void create(int r, int c, int t) const { m_->create(r, c, t); }
+    Mat getMat() const { return *m_; }
+    void release() const { m_->release(); }
+private:
+    Mat *m_;
+};
+typedef const _OutputArray &OutputArray;
+
+enum { INTER_LINEAR = 1 };
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+
+// implemented in ref_glue.cpp on top of the C oracle's primitives
+void resize(const Mat &src, Mat &dst, Size dsize, double fx, double fy, int interpolation);
+void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int borderType);
+void FAST(const Mat &image, std::vector<KeyPoint> &keypoints, int threshold, bool nonmaxSuppression);
+void GaussianBlur(const Mat &src, Mat &dst, Size ksize, double sigmaX, double sigmaY, int borderType);
+float fastAtan2(float y, float x);
+
+} // namespace cv

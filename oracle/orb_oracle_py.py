@@ -1,0 +1,262 @@
+"""ctypes binding of the CPU oracle (oracle/orb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product library
+(liborbx.so) never touches anything in this directory.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liborboracle.so")
+MAX_LEVELS = 16
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th", C.c_int), ("min_th", C.c_int), ("taps", C.c_int * 7),
+                ("sf", C.c_float * MAX_LEVELS), ("inv_sf", C.c_float * MAX_LEVELS),
+                ("sigma2", C.c_float * MAX_LEVELS), ("inv_sigma2", C.c_float * MAX_LEVELS),
+                ("quota", C.c_int * MAX_LEVELS), ("umax", C.c_int * 16)]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "orb_oracle.h", "orb_pattern.inc")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE, "_build/liborboracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+_u8p = C.POINTER(C.c_uint8)
+_ip = C.POINTER(C.c_int)
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = C.CDLL(build())
+    L.orbo_create.restype = C.c_void_p
+    L.orbo_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _ip]
+    L.orbo_destroy.argtypes = [C.c_void_p]
+    L.orbo_get_params.restype = C.POINTER(Params)
+    L.orbo_get_params.argtypes = [C.c_void_p]
+    L.orbo_set_tie_rule.argtypes = [C.c_void_p, C.c_int]
+    L.orbo_extract.restype = C.c_int
+    L.orbo_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+    L.orbo_extract_batch_mt.restype = C.c_int
+    L.orbo_extract_batch_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orbo_level.restype = C.c_void_p
+    L.orbo_level.argtypes = [C.c_void_p, C.c_int, _ip, _ip, C.POINTER(C.c_size_t)]
+    L.orbo_blurred.restype = C.c_void_p
+    L.orbo_blurred.argtypes = [C.c_void_p, C.c_int, _ip, _ip, C.POINTER(C.c_size_t)]
+    L.orbo_candidates.restype = C.c_int
+    L.orbo_candidates.argtypes = [C.c_void_p, C.c_int, C.POINTER(_ip), C.POINTER(_ip), C.POINTER(_ip)]
+    L.orbo_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+    L.orbo_border_reflect101_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t] + [C.c_int] * 4
+    L.orbo_fast9_nms.restype = C.c_int
+    L.orbo_fast9_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orbo_grid_fast.restype = C.c_int
+    L.orbo_grid_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.orbo_gaussian7_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, _ip]
+    L.orbo_fast_atan2.restype = C.c_float
+    L.orbo_fast_atan2.argtypes = [C.c_float, C.c_float]
+    L.orbo_distribute.restype = C.c_int
+    L.orbo_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p, C.c_int]
+    L.orbo_ic_angle.restype = C.c_float
+    L.orbo_ic_angle.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, _ip]
+    L.orbo_rbrief.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_void_p]
+    L.orbo_pattern.restype = _ip
+    L.orbo_descriptor_distance.restype = C.c_int
+    L.orbo_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+    L.orbo_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orbo_knn2_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c_u8(img):
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 2
+    if img.strides[1] != 1:
+        img = np.ascontiguousarray(img)
+    return img
+
+
+def resize(img, dw, dh):
+    img = _c_u8(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orbo_resize_linear_u8(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out), dw, dh, dw)
+    return out
+
+
+def border101(img, t, b, l, r):
+    img = _c_u8(img)
+    out = np.empty((img.shape[0] + t + b, img.shape[1] + l + r), np.uint8)
+    lib().orbo_border_reflect101_u8(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out), out.shape[1], t, b, l, r)
+    return out
+
+
+def fast9(img, th):
+    img = _c_u8(img)
+    cap = img.size
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orbo_fast9_nms(_ptr(img), img.shape[1], img.shape[0], img.strides[0], th, _ptr(xs), _ptr(ys), _ptr(sc), cap)
+    assert n >= 0
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def grid_fast(img, ini_th=20, min_th=7):
+    img = _c_u8(img)
+    cap = img.size
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orbo_grid_fast(_ptr(img), img.shape[1], img.shape[0], img.strides[0], ini_th, min_th, _ptr(xs), _ptr(ys), _ptr(sc), cap)
+    if n < 0:
+        raise RuntimeError(f"orbo_grid_fast failed: {n}")
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def gaussian7(img, taps=(18, 34, 48, 56, 48, 34, 18)):
+    img = _c_u8(img)
+    out = np.empty(img.shape, np.uint8)
+    t = (C.c_int * 7)(*taps)
+    lib().orbo_gaussian7_u8(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(out), out.shape[1], t)
+    return out
+
+
+def fast_atan2(y, x):
+    return lib().orbo_fast_atan2(float(y), float(x))
+
+
+def distribute(xs, ys, sc, min_x, max_x, min_y, max_y, n_quota, tie_rule=0):
+    xs = np.ascontiguousarray(xs, np.int32); ys = np.ascontiguousarray(ys, np.int32); sc = np.ascontiguousarray(sc, np.int32)
+    cap = max(len(xs), 1)
+    out = np.empty(cap, np.int32)
+    n = lib().orbo_distribute(_ptr(xs), _ptr(ys), _ptr(sc), len(xs), min_x, max_x, min_y, max_y, n_quota, tie_rule, _ptr(out), cap)
+    if n < 0:
+        raise RuntimeError(f"orbo_distribute failed: {n}")
+    return out[:n].copy()
+
+
+def ic_angle(img, cx, cy, umax):
+    img = _c_u8(img)
+    um = (C.c_int * 16)(*umax)
+    return lib().orbo_ic_angle(_ptr(img), img.strides[0], cx, cy, um)
+
+
+def rbrief(blurred, cx, cy, angle):
+    blurred = _c_u8(blurred)
+    d = np.empty(32, np.uint8)
+    lib().orbo_rbrief(_ptr(blurred), blurred.strides[0], cx, cy, float(angle), _ptr(d))
+    return d
+
+
+def pattern():
+    p = lib().orbo_pattern()
+    return np.ctypeslib.as_array(p, shape=(1024,)).copy()
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orbo_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def knn2(q, t, nthreads=1):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    nq, nt = len(q), len(t)
+    idx, d1, d2 = (np.empty(nq, np.int32) for _ in range(3))
+    if nthreads <= 1:
+        lib().orbo_knn2(_ptr(q), nq, _ptr(t), nt, _ptr(idx), _ptr(d1), _ptr(d2))
+    else:
+        lib().orbo_knn2_mt(_ptr(q), nq, _ptr(t), nt, _ptr(idx), _ptr(d1), _ptr(d2), nthreads)
+    return idx, d1, d2
+
+
+class Extractor:
+    """Mirror of OrbExtractor (orbextractor.hpp:90-109) over the C oracle."""
+
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, taps=None, tie_rule=0):
+        t = (C.c_int * 7)(*taps) if taps is not None else None
+        self._h = lib().orbo_create(nfeatures, scale_factor, nlevels, ini_th, min_th, t)
+        if not self._h:
+            raise ValueError("bad extractor parameters")
+        lib().orbo_set_tie_rule(self._h, tie_rule)
+        self.params = lib().orbo_get_params(self._h).contents
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orbo_destroy(self._h)
+            self._h = None
+
+    def cap(self, img_shape):
+        return int(sum(self.params.quota[:self.nlevels])) + 8 * self.nlevels + 64
+
+    def extract(self, img):
+        img = _c_u8(img)
+        cap = self.cap(img.shape)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib().orbo_extract(self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(kps), _ptr(desc), cap)
+        if n < 0:
+            raise RuntimeError(f"orbo_extract failed: {n}")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def extract_batch_mt(self, imgs, nthreads):
+        imgs = [np.ascontiguousarray(i) for i in imgs]
+        h, w = imgs[0].shape
+        cap = self.cap(imgs[0].shape)
+        n = len(imgs)
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        counts = np.zeros(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+        lib().orbo_extract_batch_mt(self._h, ptrs, n, w, h, w, _ptr(kps), _ptr(desc), cap, _ptr(counts), nthreads)
+        return kps, desc, counts
+
+    def level(self, l):
+        w, h, s = C.c_int(), C.c_int(), C.c_size_t()
+        p = lib().orbo_level(self._h, l, C.byref(w), C.byref(h), C.byref(s))
+        if not p:
+            return None
+        buf = (C.c_uint8 * (s.value * h.value)).from_address(p)
+        a = np.frombuffer(buf, np.uint8).reshape(h.value, s.value)[:, :w.value]
+        return a.copy()
+
+    def blurred(self, l):
+        w, h, s = C.c_int(), C.c_int(), C.c_size_t()
+        p = lib().orbo_blurred(self._h, l, C.byref(w), C.byref(h), C.byref(s))
+        if not p:
+            return None
+        buf = (C.c_uint8 * (s.value * h.value)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, s.value)[:, :w.value].copy()
+
+    def candidates(self, l):
+        xs, ys, sc = _ip(), _ip(), _ip()
+        n = lib().orbo_candidates(self._h, l, C.byref(xs), C.byref(ys), C.byref(sc))
+        if n <= 0:
+            z = np.zeros(0, np.int32)
+            return z, z, z
+        f = lambda p: np.ctypeslib.as_array(p, shape=(n,)).copy()
+        return f(xs), f(ys), f(sc)

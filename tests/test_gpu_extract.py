@@ -1,0 +1,148 @@
+"""GPU parity of the extractor path: liborbx (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): pyramid and blur bytes identical; keypoint sets, order, octaves,
+responses and descriptors identical; angles within 1e-3 degrees (we assert bit-equality and
+report the max difference); any descriptor bit flip is counted and must be zero.
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "kitti": dict(w=1241, h=376, nfeatures=2000, nlevels=8),
+    "small": dict(w=640, h=360, nfeatures=1000, nlevels=6),
+    "hd": dict(w=1920, h=1080, nfeatures=4000, nlevels=8),
+}
+
+
+def _mk(orbx, cfg, batch=1, **kw):
+    return orbx.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"], max_width=cfg["w"],
+                          max_height=cfg["h"], max_batch=batch, **kw)
+
+
+def _compare_frame(oracle, ex, oex, img, frame, kps, desc, n, stages=True):
+    okps, odesc = oex.extract(img)
+    if stages:
+        for l in range(oex.nlevels):
+            a = ex.level(frame, l); b = oex.level(l)
+            assert a.shape == b.shape, (l, a.shape, b.shape)
+            assert int((a != b).sum()) == 0, f"pyramid level {l}: {(a != b).sum()} byte mismatches"
+            ob = oex.blurred(l)
+            if ob is not None:
+                gb = ex.blurred(frame, l, ob.shape)
+                assert int((gb != ob).sum()) == 0, f"blur level {l}: {(gb != ob).sum()} byte mismatches"
+    assert n == len(okps), f"keypoint count {n} vs oracle {len(okps)}"
+    g = kps[:n]
+    for f in ("octave", "class_id"):
+        assert np.array_equal(g[f], okps[f]), f
+    for f in ("x", "y", "size", "response"):
+        assert np.array_equal(g[f].view(np.uint32), okps[f].view(np.uint32)), f"{f}: first diff at {np.flatnonzero(g[f] != okps[f])[:5]}"
+    dang = np.abs(g["angle"].astype(np.float64) - okps["angle"].astype(np.float64))
+    assert dang.max(initial=0.0) <= 1e-3, f"angle max diff {dang.max()}"
+    assert np.array_equal(g["angle"].view(np.uint32), okps["angle"].view(np.uint32)), f"angles not bit-equal, max diff {dang.max()}"
+    flips = int(np.unpackbits(desc[:n] ^ odesc).sum())
+    assert flips == 0, f"{flips} descriptor bit flips in {n} keypoints"
+
+
+@pytest.mark.parametrize("name", ["kitti", "small"])
+def test_single_frame_parity(oracle, name):
+    import orbx
+    cfg = CONFIGS[name]
+    ex = _mk(orbx, cfg)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    for seed in (1000, 1001):
+        img = synth.scene_s1(cfg["w"], cfg["h"], seed)
+        kps, desc, counts = ex.extract_batch([img])
+        _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
+
+
+def test_candidates_match_gridded_fast(oracle):
+    import orbx
+    cfg = CONFIGS["kitti"]
+    ex = _mk(orbx, cfg)
+    ex.enable_candidates(True)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    for img in (synth.scene_s1(cfg["w"], cfg["h"], 1002), synth.scene_s2(cfg["w"], cfg["h"], 7)):
+        ex.extract_batch([img])
+        oex.extract(img)
+        for l in range(cfg["nlevels"]):
+            gx, gy, gs = ex.candidates(0, l)
+            ox, oy, os_ = oex.candidates(l)
+            g = sorted(zip(gy.tolist(), gx.tolist(), gs.tolist()))
+            o = sorted(zip(oy.tolist(), ox.tolist(), os_.tolist()))
+            assert g == o, f"level {l}: {len(g)} vs {len(o)} candidates"
+    ex.close()
+
+
+def test_batch_and_stress_inputs(oracle):
+    import orbx
+    cfg = CONFIGS["kitti"]
+    imgs = synth.stereo_batch(2, cfg["w"], cfg["h"], 3)            # 6 frames: L/R pairs
+    imgs.append(synth.scene_s2(cfg["w"], cfg["h"], 11))             # uniform noise: ~1 % corners
+    imgs.append(synth.scene_s3(cfg["w"], cfg["h"], "step"))         # two-level step edge
+    imgs.append(synth.scene_s3(cfg["w"], cfg["h"], "const"))        # constant: zero keypoints
+    ex = _mk(orbx, cfg, batch=len(imgs))
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    kps, desc, counts = ex.extract_batch(imgs)
+    assert counts[-1] == 0
+    for f, img in enumerate(imgs):
+        _compare_frame(oracle, ex, oex, img, f, kps[f], desc[f], int(counts[f]), stages=(f in (0, 6)))
+    ex.close()
+
+
+def test_tie_rule_and_tap_variants(oracle):
+    import orbx
+    cfg = CONFIGS["small"]
+    img = synth.scene_s1(cfg["w"], cfg["h"], 4242)
+    taps331 = [18, 34, 49, 55, 49, 34, 18]   # the OpenCV-3.3.1-era table
+    for tie, taps in ((1, None), (0, taps331)):
+        ex = _mk(orbx, cfg, tie_rule=tie, taps=taps)
+        oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"], taps=taps, tie_rule=tie)
+        kps, desc, counts = ex.extract_batch([img])
+        _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+        ex.close()
+
+
+def test_hd_frame(oracle):
+    import orbx
+    cfg = CONFIGS["hd"]
+    ex = _mk(orbx, cfg)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    img = synth.scene_s1(cfg["w"], cfg["h"], 3000)
+    kps, desc, counts = ex.extract_batch([img])
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
+
+
+def test_strided_input_and_getters(oracle):
+    import orbx
+    cfg = CONFIGS["small"]
+    big = synth.scene_s1(cfg["w"] + 40, cfg["h"], 99)
+    img = big[:, 17:17 + cfg["w"]]            # ROI view: pitch != width (selflocalization.cpp:276-277 feeds ROIs)
+    ex = _mk(orbx, cfg)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    kps, desc, counts = ex.extract_batch([img])
+    _compare_frame(oracle, ex, oex, np.ascontiguousarray(img), 0, kps[0], desc[0], int(counts[0]))
+    t = ex.tables()
+    p = oex.params
+    assert np.array_equal(t["scale"], np.array(p.sf[:cfg["nlevels"]], np.float32))
+    assert np.array_equal(t["inv_scale"], np.array(p.inv_sf[:cfg["nlevels"]], np.float32))
+    assert np.array_equal(t["sigma2"], np.array(p.sigma2[:cfg["nlevels"]], np.float32))
+    assert np.array_equal(t["inv_sigma2"], np.array(p.inv_sigma2[:cfg["nlevels"]], np.float32))
+    assert t["quota"].tolist() == list(p.quota[:cfg["nlevels"]])
+    ex.close()
+
+
+def test_shape_errors():
+    import orbx
+    ex = orbx.Extractor(max_width=640, max_height=480)
+    with pytest.raises(orbx.OrbxError) as e:
+        ex.extract(np.zeros((480, 200), np.uint8))     # portrait: the reference divides by zero (nIni = 0)
+    assert e.value.code == -2
+    with pytest.raises(orbx.OrbxError):
+        ex.extract(np.zeros((100, 100), np.uint8))     # top levels smaller than one FAST cell
+    ex.close()

@@ -1,0 +1,82 @@
+"""GPU parity of the Hamming matcher: liborbx orbm_* vs the CPU oracle loop (bit-exact)."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_knn2_small_vs_oracle(oracle):
+    import orbx
+    q, t = synth.matching_set(300, 5000, seed=77)
+    t[100] = q[5]; t[4000] = q[5]           # exact duplicates: lowest index wins, d2 == d1 == 0
+    t[50] = t[51]                            # duplicate train rows
+    m = orbx.Matcher(max_queries=300, max_train=5000)
+    idx, d1, d2 = m.knn2(q, t)
+    oi, o1, o2 = oracle.knn2(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
+    assert idx[5] == 100 and d1[5] == 0 and d2[5] == 0
+    m.close()
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (7, 255), (129, 257), (128, 256), (33, 1000)])
+def test_knn2_ragged_sizes(oracle, nq, nt):
+    import orbx
+    rng = np.random.default_rng(nq * 1000 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    m = orbx.Matcher(max_queries=256, max_train=2048)
+    idx, d1, d2 = m.knn2(q, t)
+    oi, o1, o2 = oracle.knn2(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
+    m.close()
+
+
+def test_knn2_distance_256_is_never_a_match(oracle):
+    import orbx
+    q = np.zeros((2, 32), np.uint8)
+    t = np.full((3, 32), 255, np.uint8)      # all 256 bits differ: 'dist < 256' never fires (orbmatcher.cpp:208-232)
+    m = orbx.Matcher(max_queries=8, max_train=8)
+    idx, d1, d2 = m.knn2(q, t)
+    oi, o1, o2 = oracle.knn2(q, t)
+    assert idx.tolist() == [-1, -1] and d1.tolist() == [256, 256] and d2.tolist() == [256, 256]
+    assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
+    m.close()
+
+
+def test_knn2_full_size_properties(oracle):
+    """C5 at full size (2000 x 100000): oracle on a query sample + size-independent properties."""
+    import orbx
+    q, t = synth.matching_set(2000, 100000, seed=5000)
+    m = orbx.Matcher(max_queries=2000, max_train=100000)
+    idx, d1, d2 = m.knn2(q, t)
+    # (1) reported distance is the true distance to the reported index; (2) d1 <= d2
+    x = np.unpackbits(q ^ t[idx], axis=1).sum(1)
+    assert np.array_equal(x, d1)
+    assert (d1 <= d2).all()
+    # (3) a sample of queries against the oracle's sequential loop
+    sel = np.arange(0, 2000, 40)
+    oi, o1, o2 = oracle.knn2(q[sel], t, nthreads=8)
+    assert np.array_equal(idx[sel], oi) and np.array_equal(d1[sel], o1) and np.array_equal(d2[sel], o2)
+    # (4) resident path and permutation of the query order give the same per-query answers
+    m.set_train(t)
+    perm = np.random.default_rng(1).permutation(2000)
+    i2, a2, b2 = m.knn2_resident(q[perm])
+    assert np.array_equal(i2, idx[perm]) and np.array_equal(a2, d1[perm]) and np.array_equal(b2, d2[perm])
+    # ratio test as the reference applies it on the host
+    acc = orbx.ratio_test(d1, d2, 0.7, 100)
+    assert acc.sum() > 0
+    m.close()
+
+
+def test_distance_pairs(oracle):
+    import orbx
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    m = orbx.Matcher(max_queries=512, max_train=512)
+    d = m.distance_pairs(a, b)
+    ref = np.array([oracle.descriptor_distance(a[i], b[i]) for i in range(500)], np.int32)
+    assert np.array_equal(d, ref)
+    m.close()
