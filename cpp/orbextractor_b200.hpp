@@ -1,0 +1,152 @@
+// orbextractor_b200.hpp -- drop-in OrbExtractor for chalmers-revere/opendlv-perception-vision-orbslam2
+// backed by liborbx.so (include/orbx.h) on a B200.
+//
+// Same class name, constructor, member functions and public data member as the reference's
+// include/orbextractor.hpp:90-109, so Tracking (src/tracking.cpp:121-127), OrbFrame
+// (src/orbframe.cpp:65-78,152-158,213-223,518,618-641) and everything above them compile and
+// behave unchanged.  To switch: put this header's directory before the reference's include/ on
+// the include path under the name orbextractor.hpp (or include it from there), drop
+// src/orbextractor.cpp from the build and link -lorbx.  See INTEGRATION.md.
+//
+// Header-only on purpose: it needs the OpenCV headers of whatever build includes it; liborbx.so
+// itself has no OpenCV dependency.  (In this repository it is compiled against oracle/cvshim in
+// tests/cpp/adapter_main.cpp, because the image has no OpenCV C++ headers.)
+//
+// Behavioural notes, each mirroring the reference:
+//  * ExtractFeatures clears `keypoints` and create()s `descriptors` (N x 32, CV_8U) or release()s
+//    it when N == 0                                         (orbextractor.cpp:599-609)
+//  * m_vImagePyramid[l] are host cv::Mat headers over a pinned buffer owned by the handle, valid
+//    until the next ExtractFeatures on this instance -- the reference overwrites its pyramid on
+//    the next call too (orbextractor.cpp:654-678).  They are ROI-free level images; the 19-px
+//    REFLECT_101 frame the reference keeps around each level is never read by any caller
+//    (SURVEY.md A.2).  Define ORBX_ADAPTER_LAZY_PYRAMID to skip the per-call device-to-host copy
+//    when the caller does not read the pyramid (monocular tracking).
+//  * one instance must not be entered by two threads at once; different instances may run
+//    concurrently (the stereo path does, orbframe.cpp:73-76).
+//  * errors: the reference prints and continues into undefined behaviour; this adapter throws
+//    std::runtime_error with the library's message.
+#ifndef ORBEXTRACTOR_HPP
+#define ORBEXTRACTOR_HPP
+
+#include <opencv2/core/core.hpp>
+
+#include <algorithm>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "orbx.h"
+
+class OrbExtractor {
+ public:
+  OrbExtractor(int nFeatures, float scaleFactor, int nLevels, int initialFastTh, int minFastTh)
+      : m_vImagePyramid(), m_handle(nullptr), m_nFeatures(nFeatures), m_scaleFactor(scaleFactor), m_nLevels(nLevels),
+        m_initialFastTh(initialFastTh), m_minFastTh(minFastTh), m_maxW(0), m_maxH(0), m_device(0)
+  {
+      std::cout << "Making extractor" << std::endl;   // orbextractor.cpp:491
+      m_vImagePyramid.resize(nLevels);
+  }
+  ~OrbExtractor() { if (m_handle) orbx_destroy(m_handle); }
+  OrbExtractor(const OrbExtractor &) = delete;
+  OrbExtractor &operator=(const OrbExtractor &) = delete;
+
+  /*Called by other classes to get keypoints and descriptors*/
+  void ExtractFeatures(cv::InputArray image, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors)
+  {
+      if (image.empty()) {
+          std::cout << "No Image for ORB features" << std::endl;   // orbextractor.cpp:583-585
+          throw std::runtime_error("OrbExtractor::ExtractFeatures: empty image");
+      }
+      cv::Mat img = image.getMat();
+      if (img.type() != CV_8UC1) throw std::runtime_error("OrbExtractor::ExtractFeatures: image must be CV_8UC1");  // :588
+      ensureHandle(img.cols, img.rows);
+      const int cap = orbx_max_keypoints(m_handle);
+      m_kps.resize(cap);
+      m_desc.resize((size_t)cap * 32);
+      int n = 0;
+      check(orbx_extract(m_handle, img.ptr(0), img.cols, img.rows, (size_t)img.step, m_kps.data(), cap, m_desc.data(), &n));
+      keypoints.clear();
+      if (n == 0) {
+          descriptors.release();
+      } else {
+          descriptors.create(n, 32, CV_8U);
+          cv::Mat d = descriptors.getMat();
+          for (int i = 0; i < n; i++) std::copy(m_desc.begin() + (size_t)i * 32, m_desc.begin() + (size_t)(i + 1) * 32, d.ptr(i));
+      }
+      keypoints.reserve(n);
+      for (int i = 0; i < n; i++) {
+          const orbx_keypoint &k = m_kps[i];
+          keypoints.push_back(cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, k.class_id));
+      }
+#ifndef ORBX_ADAPTER_LAZY_PYRAMID
+      fetchPyramid();
+#endif
+  }
+
+  /*Getters for scale factors and other properties*/
+  int getLevels() { return m_nLevels; }
+  double getScaleFactor() { return m_scaleFactor; }
+  std::vector<float> getScaleFactors() { return table(0); }
+  std::vector<float> getInverseScaleFactors() { return table(1); }
+  std::vector<float> getScaleSigmaSquares() { return table(2); }
+  std::vector<float> getInverseScaleSigmaSquares() { return table(3); }
+
+  std::vector<cv::Mat> m_vImagePyramid;
+
+  // additions (not in the reference): explicit pyramid fetch for the lazy mode, device selection
+  void fetchPyramid()
+  {
+      for (int l = 0; l < m_nLevels; l++) {
+          const uint8_t *p = nullptr; int w = 0, h = 0; size_t pitch = 0;
+          check(orbx_get_level(m_handle, 0, l, &p, &w, &h, &pitch));
+          m_vImagePyramid[l] = cv::Mat(h, w, CV_8UC1, (void *)p, pitch);
+      }
+  }
+  void setDevice(int device) { m_device = device; }
+
+ private:
+  void check(int rc)
+  {
+      if (rc != ORBX_OK) throw std::runtime_error(std::string("liborbx: ") + orbx_last_error(m_handle));
+  }
+  void ensureHandle(int w, int h)
+  {
+      if (m_handle && w <= m_maxW && h <= m_maxH) return;
+      if (m_handle) { orbx_destroy(m_handle); m_handle = nullptr; }
+      orbx_config cfg = orbx_config();
+      cfg.nfeatures = m_nFeatures; cfg.scale_factor = (float)m_scaleFactor; cfg.nlevels = m_nLevels;
+      cfg.ini_th_fast = m_initialFastTh; cfg.min_th_fast = m_minFastTh;
+      cfg.max_width = m_maxW = std::max(w, m_maxW); cfg.max_height = m_maxH = std::max(h, m_maxH);
+      cfg.max_batch = 1; cfg.device = m_device;
+      int rc = orbx_create(&cfg, &m_handle);
+      if (rc != ORBX_OK) {
+          std::string msg = m_handle ? orbx_last_error(m_handle) : "invalid configuration";
+          if (m_handle) { orbx_destroy(m_handle); m_handle = nullptr; }
+          m_maxW = m_maxH = 0;
+          throw std::runtime_error("liborbx: " + msg);
+      }
+  }
+  // the constructor tables of orbextractor.cpp:492-508 are a pure function of (scaleFactor, nLevels):
+  // computed here with the same float chain so the getters work before the first image arrives
+  std::vector<float> table(int which)
+  {
+      std::vector<float> sf(m_nLevels), s2(m_nLevels), isf(m_nLevels), is2(m_nLevels);
+      sf[0] = 1.0f; s2[0] = 1.0f;
+      for (int i = 1; i < m_nLevels; i++) { sf[i] = sf[i - 1] * (float)m_scaleFactor; s2[i] = sf[i] * sf[i]; }
+      for (int i = 0; i < m_nLevels; i++) { isf[i] = 1.0f / sf[i]; is2[i] = 1.0f / s2[i]; }
+      return which == 0 ? sf : which == 1 ? isf : which == 2 ? s2 : is2;
+  }
+
+  orbx_extractor *m_handle;
+  int m_nFeatures;
+  double m_scaleFactor;
+  int m_nLevels;
+  int m_initialFastTh;
+  int m_minFastTh;
+  int m_maxW, m_maxH, m_device;
+  std::vector<orbx_keypoint> m_kps;
+  std::vector<uint8_t> m_desc;
+};
+
+#endif  // ORBEXTRACTOR_HPP

@@ -1,0 +1,71 @@
+// orbmatcher_b200.hpp -- batched Hamming matching for the loops around
+// ORBmatcher::DescriptorDistance (reference include/orbmatcher.hpp:48, src/orbmatcher.cpp:1662-1677).
+//
+// The reference's static DescriptorDistance(a, b) stays what it is -- one 32-byte pair per call is
+// below the granularity of a kernel launch and this library has no CPU path.  What moves to the
+// GPU are the LOOPS that call it: brute-force best / second-best search over a descriptor set
+// (orbmatcher.cpp:208-232 pattern) and bulk pair evaluation.  The acceptance rules stay on the host
+// exactly as written in the reference (TH_LOW / TH_HIGH, mfNNratio; orbmatcher.cpp:36-37, :234-236).
+#ifndef ORBMATCHER_B200_HPP
+#define ORBMATCHER_B200_HPP
+
+#include <opencv2/core/core.hpp>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "orbx.h"
+
+namespace orbslam_b200 {
+
+class HammingMatcher {
+ public:
+  HammingMatcher(int maxQueries, int maxTrain, int device = 0) : m_(nullptr)
+  {
+      int rc = orbm_create(device, maxQueries, maxTrain, &m_);
+      if (rc != ORBX_OK) {
+          std::string msg = m_ ? orbm_last_error(m_) : "invalid configuration";
+          if (m_) orbm_destroy(m_);
+          m_ = nullptr;
+          throw std::runtime_error("liborbx: " + msg);
+      }
+  }
+  ~HammingMatcher() { if (m_) orbm_destroy(m_); }
+  HammingMatcher(const HammingMatcher &) = delete;
+  HammingMatcher &operator=(const HammingMatcher &) = delete;
+
+  // map-point (train) descriptors: N x 32 CV_8U, continuous; stays resident on the GPU
+  void SetTrain(const cv::Mat &train) { check(orbm_set_train(m_, train.ptr(0), train.rows)); }
+
+  // for every row of `query`: bestIdx (lowest train index attaining the minimum, -1 if none < 256),
+  // bestDist1, bestDist2 -- the values the loop at orbmatcher.cpp:208-232 leaves behind
+  void KnnMatch2(const cv::Mat &query, std::vector<int> &bestIdx, std::vector<int> &bestDist1, std::vector<int> &bestDist2)
+  {
+      const int n = query.rows;
+      bestIdx.resize(n); bestDist1.resize(n); bestDist2.resize(n);
+      if (n == 0) return;
+      check(orbm_knn2_resident(m_, query.ptr(0), n, bestIdx.data(), bestDist1.data(), bestDist2.data()));
+  }
+
+  // DescriptorDistance for n independent pairs (row i of a vs row i of b)
+  void DescriptorDistanceBatch(const cv::Mat &a, const cv::Mat &b, std::vector<int> &dist)
+  {
+      dist.resize(a.rows);
+      if (a.rows == 0) return;
+      check(orbm_distance_pairs(m_, a.ptr(0), b.ptr(0), a.rows, dist.data()));
+  }
+
+  // the reference's acceptance test (orbmatcher.cpp:234-236)
+  static bool Accept(int bestDist1, int bestDist2, int th, float nnRatio)
+  {
+      return bestDist1 <= th && static_cast<float>(bestDist1) < nnRatio * static_cast<float>(bestDist2);
+  }
+
+ private:
+  void check(int rc) { if (rc != ORBX_OK) throw std::runtime_error(std::string("liborbx: ") + orbm_last_error(m_)); }
+  orbm_matcher *m_;
+};
+
+}  // namespace orbslam_b200
+#endif

@@ -114,6 +114,11 @@ int orbx_get_level(orbx_extractor *h, int frame, int level, const uint8_t **host
 int orbx_scale_tables(const orbx_extractor *h, float *scale, float *inv_scale, float *sigma2,
                       float *inv_sigma2, int *quota);
 
+/* Device time of each stage (ms, averaged over `reps` re-runs on the frames of the last call,
+ * serialised with CUDA events on the handle's stream): ms[0] pyramid resize chain, ms[1] gridded
+ * FAST, ms[2] DistributeOctTree, ms[3] Gaussian blur, ms[4] orientation + descriptors.  n_ms >= 5. */
+int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms);
+
 /* ---- stage taps for parity tests (host copies of device intermediates of the last call) ---- */
 /* blurred level (the GaussianBlur output of orbextractor.cpp:621-622), tightly packed w*h bytes */
 int orbx_debug_blurred(orbx_extractor *h, int frame, int level, uint8_t *dst, size_t dst_bytes, int *width, int *height);

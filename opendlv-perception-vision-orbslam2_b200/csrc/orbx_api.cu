@@ -65,6 +65,7 @@ struct orbx_extractor {
     OrbxLayout L;
     std::vector<OrbxCell> cells;
     std::vector<OrbxRTab> rtab;
+    std::vector<OrbxTile> tiles;
     int maxRows = 0, maxNodes = 0, pow2Nodes = 0;
     bool geomUploaded = false;
     // device state
@@ -79,6 +80,7 @@ struct orbx_extractor {
     DevBuf<orbx_keypoint_pod> dKps;
     DevBuf<OrbxCell> dCells;
     DevBuf<OrbxRTab> dRtab;
+    DevBuf<OrbxTile> dTiles;
     DevBuf<OrbxDbgCand> dDbg;
     PinBuf<uint8_t> hIn, hDesc, hLevel;
     PinBuf<orbx_keypoint_pod> hKps;
@@ -141,7 +143,7 @@ void buildTables(orbx_extractor *h)
 }
 
 // bilinear coefficient table of one axis, SURVEY A.1
-void axisTable(int ssize, int dsize, OrbxRTab *out)
+void axisTable(int ssize, int dsize, OrbxRTab *out, bool packed)
 {
     const double invScale = (double)dsize / ssize;
     const double scale = 1.0 / invScale;
@@ -151,20 +153,21 @@ void axisTable(int ssize, int dsize, OrbxRTab *out)
         f -= s;
         if (s < 0) { f = 0; s = 0; }
         if (s >= ssize - 1) { f = 0; s = ssize - 1; }
-        out[d].ofs = (int16_t)s;
-        out[d].c0 = (int16_t)cvRoundF((1.f - f) * 2048.f);
-        out[d].c1 = (int16_t)cvRoundF(f * 2048.f);
-        out[d].pad = 0;
+        const int c0 = (int16_t)cvRoundF((1.f - f) * 2048.f), c1 = (int16_t)cvRoundF(f * 2048.f);
+        out[d].a = s;
+        out[d].b = std::min(s + 1, ssize - 1);
+        if (packed) { out[d].c = (int32_t)((uint32_t)c0 | (uint32_t)c1 << 16); out[d].d = 0; }
+        else { out[d].c = c0; out[d].d = c1; }
     }
 }
 
 // geometry for an image size; returns ORBX_OK or ORBX_ERR_SHAPE with a message
 int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<OrbxCell> &cells,
-                  std::vector<OrbxRTab> &rtab, int &maxRows, int &maxNodes)
+                  std::vector<OrbxRTab> &rtab, std::vector<OrbxTile> &tiles, int &maxRows, int &maxNodes)
 {
     const orbx_config &c = h->cfg;
     memset(&L, 0, sizeof(L));
-    cells.clear(); rtab.clear();
+    cells.clear(); rtab.clear(); tiles.clear();
     L.nlevels = c.nlevels; L.iniTh = c.ini_th_fast; L.minTh = c.min_th_fast; L.tieRule = c.tie_rule;
     long long off = 0;
     int rows = 0, slots = 0;
@@ -206,7 +209,7 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
                 cell.x0 = (uint16_t)iniX; cell.y0 = (uint16_t)iniY;
                 cell.w = (uint8_t)(maxX - iniX); cell.h = (uint8_t)(maxY - iniY);
                 cell.level = (uint8_t)l; cell.pad = 0;
-                cell.orderBase = (uint32_t)(i * v.nCols + j) << 12;
+                cell.ci = (uint16_t)i; cell.cj = (uint16_t)j;
                 cells.push_back(cell);
             }
         }
@@ -235,14 +238,20 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         maxNodes = std::max(maxNodes, v.slotCap + 2);
         v.sf = h->sf[l];
         v.kpSize = 31 * (int)h->sf[l];   // :978 int cast before the multiply
+        // blur tiles: 32 words x (4 strips of 32 rows)
+        for (int ty = 0; ty < v.h; ty += 128)
+            for (int tx = 0; tx * 4 < v.w; tx += 32) {
+                OrbxTile t; t.x0 = (uint16_t)tx; t.y0 = (uint16_t)ty; t.level = (uint8_t)l; t.pad[0] = t.pad[1] = t.pad[2] = 0;
+                tiles.push_back(t);
+            }
         if (l > 0) {
             const OrbxLevel &p = L.lv[l - 1];
             v.xtabOff = (int)rtab.size();
             rtab.resize(rtab.size() + v.w);
-            axisTable(p.w, v.w, &rtab[v.xtabOff]);
+            axisTable(p.w, v.w, &rtab[v.xtabOff], true);
             v.ytabOff = (int)rtab.size();
             rtab.resize(rtab.size() + v.h);
-            axisTable(p.h, v.h, &rtab[v.ytabOff]);
+            axisTable(p.h, v.h, &rtab[v.ytabOff], false);
         }
     }
     L.slab = (off + 255) / 256 * 256;
@@ -277,19 +286,21 @@ int ensureArenas(orbx_extractor *h, int batch)
 int setGeometry(orbx_extractor *h, int w, int hh)
 {
     if (w == h->curW && hh == h->curH && h->geomUploaded) return ORBX_OK;
-    OrbxLayout L; std::vector<OrbxCell> cells; std::vector<OrbxRTab> rtab; int maxRows, maxNodes;
-    int rc = buildGeometry(h, w, hh, L, cells, rtab, maxRows, maxNodes);
+    OrbxLayout L; std::vector<OrbxCell> cells; std::vector<OrbxRTab> rtab; std::vector<OrbxTile> tiles; int maxRows, maxNodes;
+    int rc = buildGeometry(h, w, hh, L, cells, rtab, tiles, maxRows, maxNodes);
     if (rc != ORBX_OK) return rc;
-    h->L = L; h->cells.swap(cells); h->rtab.swap(rtab);
+    h->L = L; h->cells.swap(cells); h->rtab.swap(rtab); h->tiles.swap(tiles);
     h->maxRows = maxRows; h->maxNodes = maxNodes;
     int p2 = 2; while (p2 < maxNodes) p2 <<= 1;
     h->pow2Nodes = p2;
     if (octree_smem_bytes(maxRows, maxNodes, p2) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
     CK(h->dCells.ensure(h->cells.size()));
     CK(h->dRtab.ensure(std::max<size_t>(h->rtab.size(), 1)));
+    CK(h->dTiles.ensure(h->tiles.size()));
     // the stream may still be reading the old tables
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpyAsync(h->dCells.p, h->cells.data(), h->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dTiles.p, h->tiles.data(), h->tiles.size() * sizeof(OrbxTile), cudaMemcpyHostToDevice, h->stream));
     if (!h->rtab.empty())
         CK(cudaMemcpyAsync(h->dRtab.p, h->rtab.data(), h->rtab.size() * sizeof(OrbxRTab), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -301,11 +312,11 @@ int setGeometry(orbx_extractor *h, int w, int hh)
 int enqueuePipeline(orbx_extractor *h, int batch, cudaStream_t st)
 {
     const OrbxLayout &L = h->L;
-    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, h->dRtab.p, batch, st);
+    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
     // blur only depends on the pyramid: run it on the side stream, beside FAST + octree
     CK(cudaEventRecord(h->evFork, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    for (int l = 0; l < L.nlevels; l++) launch_blur(h->dPyr.p, h->dBlur.p, L, l, h->taps, batch, h->stream2);
+    launch_blur(h->dPyr.p, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, h->stream2);
     CK(cudaEventRecord(h->evJoin, h->stream2));
 
     CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
@@ -387,7 +398,7 @@ void orbx_destroy(orbx_extractor *h)
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     h->dPyr.release(); h->dBlur.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
-    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dDbg.release();
+    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
@@ -531,6 +542,41 @@ int orbx_debug_blurred(orbx_extractor *h, int frame, int level, uint8_t *dst, si
     CK(cudaMemcpy2D(dst, l.w, h->dBlur.p + (size_t)frame * h->L.slab + l.off, l.pitch, l.w, l.h, cudaMemcpyDeviceToHost));
     if (width) *width = l.w;
     if (height) *height = l.h;
+    return ORBX_OK;
+}
+
+// Per-stage device times of the pipeline, serialised on the handle's stream with CUDA events:
+// ms[0] resize chain, ms[1] FAST (incl. clearing the row summaries), ms[2] octree, ms[3] blur,
+// ms[4] describe.  Re-runs the stages on the frames of the last call (level 0 is still resident).
+int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!ms || n_ms < 5 || reps < 1 || h->lastBatch < 1) return fail(h, ORBX_ERR_ARG, "bad argument or no previous call");
+    CK(cudaSetDevice(h->cfg.device));
+    const OrbxLayout &L = h->L;
+    const int batch = h->lastBatch;
+    cudaStream_t st = h->stream;
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < 5; i++) ms[i] = 0.f;
+    for (int r = 0; r < reps; r++) {
+        CK(cudaEventRecord(ev[0], st));
+        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
+        CK(cudaEventRecord(ev[1], st));
+        CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
+        launch_fast(h->dPyr.p, L, h->dCells.p, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
+        CK(cudaEventRecord(ev[2], st));
+        CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
+        CK(cudaEventRecord(ev[3], st));
+        launch_blur(h->dPyr.p, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, st);
+        CK(cudaEventRecord(ev[4], st));
+        launch_describe(h->dPyr.p, h->dBlur.p, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
+        CK(cudaEventRecord(ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 5; i++) { float t = 0; CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / reps; }
+    }
+    for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     return ORBX_OK;
 }
 

@@ -48,10 +48,13 @@ struct OrbxCell {
     uint16_t x0, y0;     // window origin in level coordinates (iniX, iniY)
     uint8_t w, h;        // window size (maxX-iniX, maxY-iniY) <= 66
     uint8_t level, pad;
-    uint32_t orderBase;  // (cellRow*nCols + cellCol) << 12 : position in the reference's emission order
+    uint16_t ci, cj;     // cell row / column: (ci*nCols + cj) is the cell's position in the reference's emission order
 };
 
-// bilinear coefficient entry, SURVEY A.1
-struct OrbxRTab { int16_t ofs, c0, c1, pad; };
+// one blur tile: 32 words (128 px) x 4 strips of 32 rows; x0 in 4-px words, y0 in rows
+struct OrbxTile { uint16_t x0, y0; uint8_t level, pad[3]; };
+
+// bilinear coefficient entry, SURVEY A.1.  x axis: {sx0, sx1, c0 | c1 << 16, 0}; y axis: {sy0, sy1, b0, b1}
+struct OrbxRTab { int32_t a, b, c, d; };
 
 struct OrbxDbgCand { int32_t xy; int32_t score; };

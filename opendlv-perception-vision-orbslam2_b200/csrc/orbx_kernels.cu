@@ -15,7 +15,7 @@
 #include <cuda_runtime.h>
 
 // rBRIEF sampling pattern, 512 (x,y) points (data; same table as orbextractor.cpp:215-473)
-__device__ const int8_t d_pattern[1024] = {
+__device__ __align__(16) const int8_t d_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
@@ -69,21 +69,32 @@ __device__ int block_excl_scan(int *vals, int n, int *scratch)
 
 // ------------------------------------------------------------------------------------------
 // level 0: copy the caller's frame into the pyramid slab (ComputePyramid level 0; the
-// REFLECT_101 border of orbextractor.cpp:673 is never read by the extractor -- SURVEY A.2)
+// REFLECT_101 border of orbextractor.cpp:673 is never read by the extractor -- SURVEY A.2).
+// Source rows may start at any byte alignment (tightly packed 1241-wide frames): every thread
+// assembles one aligned 16-byte destination chunk from aligned 32-bit source words with funnel
+// shifts, so both sides move whole words.
 // ------------------------------------------------------------------------------------------
-__global__ void k_copy_level0(const uint8_t *__restrict__ src, size_t frameStride, size_t srcPitch,
-                              uint8_t *__restrict__ pyr, long long slab, int off, int pitch, int w, int h)
+__global__ void __launch_bounds__(128)
+k_copy_level0(const uint8_t *__restrict__ src, size_t frameStride, size_t srcPitch, const uint8_t *srcEnd,
+              uint8_t *__restrict__ pyr, long long slab, int off, int pitch, int w, int h)
 {
     const int f = blockIdx.z;
-    const int y = blockIdx.y;
-    const uint8_t *s = src + (size_t)f * frameStride + (size_t)y * srcPitch;
-    uint8_t *d = pyr + (size_t)f * slab + off + (size_t)y * pitch;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (x4 >= w) return;
-    if (((uintptr_t)(s + x4) & 15) == 0 && x4 + 16 <= w) {
-        *(uint4 *)(d + x4) = __ldg((const uint4 *)(s + x4));
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (y >= h || x >= w) return;
+    const uint8_t *s = src + (size_t)f * frameStride + (size_t)y * srcPitch + x;
+    uint8_t *d = pyr + (size_t)f * slab + off + (size_t)y * pitch + x;
+    const uintptr_t a = (uintptr_t)s;
+    const uint32_t *s4 = (const uint32_t *)(a & ~(uintptr_t)3);
+    if ((const uint8_t *)(s4 + 5) <= srcEnd) {
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2), w3 = __ldg(s4 + 3), w4 = __ldg(s4 + 4);
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+        o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+        *(uint4 *)d = o;    // bytes past w land in the row's pitch padding
     } else {
-        for (int k = 0; k < 16 && x4 + k < w; k++) d[x4 + k] = s[x4 + k];
+        for (int k = 0; k < 16 && x + k < w; k++) d[k] = s[k];
     }
 }
 
@@ -91,110 +102,192 @@ void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch,
                         const OrbxLayout &L, int batch, cudaStream_t st)
 {
     const OrbxLevel &l0 = L.lv[0];
-    dim3 block(64);
-    dim3 grid((l0.w + 16 * 64 - 1) / (16 * 64), l0.h, batch);
-    k_copy_level0<<<grid, block, 0, st>>>(src, frameStride, srcPitch, pyr, L.slab, l0.off, l0.pitch, l0.w, l0.h);
+    dim3 block(32, 4);
+    dim3 grid((l0.w + 16 * 32 - 1) / (16 * 32), (l0.h + 3) / 4, batch);
+    const uint8_t *srcEnd = src + (size_t)(batch - 1) * frameStride + (size_t)(l0.h - 1) * srcPitch + l0.w;
+    k_copy_level0<<<grid, block, 0, st>>>(src, frameStride, srcPitch, srcEnd, pyr, L.slab, l0.off, l0.pitch, l0.w, l0.h);
 }
 
 // ------------------------------------------------------------------------------------------
-// pyramid resize, 11-bit fixed-point bilinear (A.1).  Each thread produces 4 horizontally
-// adjacent output pixels and stores them as one 32-bit word.
+// pyramid resize, 11-bit fixed-point bilinear (A.1): level l from level l-1.
+// One thread owns 4 adjacent output columns (one 32-bit word per output row) and walks RS_ROWS
+// output rows downwards.  The horizontally interpolated source rows
+//   h(sy)[x] = S[sy][sx]*c0 + S[sy][sx+1]*c1        (one dp2a per pixel, coefficients packed)
+// stay in registers and are reused between consecutive output rows (at scale 1.2 consecutive
+// outputs share a source row), so every source row is interpolated once per strip.  Row base
+// addresses are uniform across the CTA; per-thread addressing is a 32-bit column offset.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, int sw, int sh,
-         int dstOff, int dstPitch, int dw, int dh,
-         const OrbxRTab *__restrict__ xtab, const OrbxRTab *__restrict__ ytab)
+#define RS_ROWS 16
+
+__device__ __forceinline__ void resize_hrow(const uint8_t *__restrict__ rowp, const int (&sx0)[4], const int (&sx1)[4],
+                                            const uint32_t (&cc)[4], int (&hv)[4])
 {
-    const int f = blockIdx.z;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (y >= dh || x0 >= dw) return;
-    const uint8_t *src = pyr + (size_t)f * slab + srcOff;
-    uint8_t *dst = pyr + (size_t)f * slab + dstOff;
-    const OrbxRTab ty = ytab[y];
-    const int sy0 = ty.ofs, sy1 = min(sy0 + 1, sh - 1);
-    const uint8_t *r0 = src + (size_t)sy0 * srcPitch, *r1 = src + (size_t)sy1 * srcPitch;
-    const int b0 = ty.c0, b1 = ty.c1;
-    uint32_t out = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int x = x0 + k;
-        if (x < dw) {
-            const OrbxRTab tx = xtab[x];
-            const int sx0 = tx.ofs, sx1 = min(sx0 + 1, sw - 1);
-            const int h0 = r0[sx0] * tx.c0 + r0[sx1] * tx.c1;
-            const int h1 = r1[sx0] * tx.c0 + r1[sx1] * tx.c1;
-            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 255) << (8 * k);
-        }
+        const uint32_t px = (uint32_t)rowp[sx0[k]] | (uint32_t)rowp[sx1[k]] << 8;
+        hv[k] = __dp2a_lo(cc[k], px, 0u);     // c0 * S[sx0] + c1 * S[sx1]
     }
-    *(uint32_t *)(dst + (size_t)y * dstPitch + x0) = out; // pitch is a multiple of 128: in-row padding absorbs the tail
 }
 
-void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const OrbxRTab *tabs, int batch, cudaStream_t st)
+__global__ void __launch_bounds__(64)
+k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, int dstOff, int dstPitch, int dw, int dh,
+         const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
+{
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y0 = blockIdx.y * RS_ROWS;
+    if (x0 >= dw) return;
+    const uint8_t *src = pyr + (size_t)f * slab + srcOff;          // uniform
+    uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch;
+    int sx0[4], sx1[4];
+    uint32_t cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int4 t = __ldg(&xtab[min(x0 + k, dw - 1)]);
+        sx0[k] = t.x; sx1[k] = t.y; cc[k] = (uint32_t)t.z;
+    }
+    const int yEnd = min(RS_ROWS, dh - y0);
+    int rb = -1;
+    int ha[4], hb[4] = {0, 0, 0, 0};
+    for (int r = 0; r < yEnd; r++) {
+        const int4 ty = __ldg(&ytab[y0 + r]);                      // {sy0, sy1, b0, b1}, uniform across the CTA
+        if (ty.x == rb) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) ha[k] = hb[k];
+        } else {
+            resize_hrow(src + (size_t)ty.x * srcPitch, sx0, sx1, cc, ha);
+        }
+        if (ty.y == ty.x) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) hb[k] = ha[k];
+        } else {
+            resize_hrow(src + (size_t)ty.y * srcPitch, sx0, sx1, cc, hb);
+        }
+        rb = ty.y;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int v = (((ty.z * (ha[k] >> 4)) >> 16) + ((ty.w * (hb[k] >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 255) << (8 * k);
+        }
+        *(uint32_t *)(dst + (size_t)r * dstPitch + x0) = out;       // bytes past dw land in the pitch padding
+    }
+}
+
+void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st)
 {
     const OrbxLevel &s = L.lv[level - 1], &d = L.lv[level];
-    dim3 block(32, 8);
-    dim3 grid((d.w + 127) / 128, (d.h + 7) / 8, batch);
-    k_resize<<<grid, block, 0, st>>>(pyr, L.slab, s.off, s.pitch, s.w, s.h, d.off, d.pitch, d.w, d.h,
+    dim3 block(64);
+    dim3 grid((d.w + 255) / 256, (d.h + RS_ROWS - 1) / RS_ROWS, batch);
+    k_resize<<<grid, block, 0, st>>>(pyr, L.slab, s.off, s.pitch, d.off, d.pitch, d.w, d.h,
                                      tabs + d.xtabOff, tabs + d.ytabOff);
 }
 
 // ------------------------------------------------------------------------------------------
-// 7x7 Gaussian blur, separable integer taps, REFLECT_101 (A.4).
-// CTA tile: 64x32 outputs; shared-memory stage with a 3-pixel halo.
+// 7x7 Gaussian blur, separable integer taps, REFLECT_101 (A.4):
+//   out = min(255, (sum_y t[y] * (sum_x t[x] * I) + 32768) >> 16)
+// One thread owns 4 adjacent columns (one 32-bit word of every output row) and walks BL_ROWS
+// rows downwards.  Per input row it reads the 12 bytes x0-4 .. x0+7 as three aligned words,
+// forms the four horizontal sums with byte-permutes + dp4a (taps packed 4 per register), and
+// keeps the last 7 of them per column in registers for the vertical sum -- the intermediate
+// never touches shared or global memory.  A warp covers 128 columns; a CTA is 4 warps working
+// on 4 vertically adjacent strips of one tile; one launch covers every level (tile table).
 // ------------------------------------------------------------------------------------------
-#define BL_TW 64
-#define BL_TH 32
+#define BL_ROWS 32
 struct BlurTaps { int t[7]; };
 
-__global__ void __launch_bounds__(256)
-k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, long long slab, int off, int pitch,
-       int w, int h, BlurTaps taps)
+// Byte-permute selectors that apply REFLECT_101 at the right image edge to the 12-byte window
+// {W0,W1,W2} = bytes x0-4 .. x0+7 (window index i = 0..11).  e = w - x0 is the number of valid
+// bytes from x0 on; index i >= e+4 lies outside the row and equals index 2(e+3)-i.  Only three
+// reflected bytes are ever consumed by valid outputs.  Interior threads get identity selectors,
+// so every thread runs the same three PRMTs per row and no warp diverges at the border.
+__device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint32_t &selT, uint32_t &sel2)
 {
-    __shared__ uint8_t raw[(BL_TH + 6) * (BL_TW + 8)];
-    __shared__ uint16_t hb[(BL_TH + 6) * BL_TW];
-    const int f = blockIdx.z;
-    const int tx0 = blockIdx.x * BL_TW, ty0 = blockIdx.y * BL_TH;
-    const uint8_t *src = pyr + (size_t)f * slab + off;
-    uint8_t *dst = blur + (size_t)f * slab + off;
-    const int tid = threadIdx.x;
-    const int RW = BL_TW + 6, RP = BL_TW + 8;
-    for (int i = tid; i < (BL_TH + 6) * RW; i += 256) {
-        const int r = i / RW, c = i - r * RW;
-        const int gy = reflect101(ty0 + r - 3, h), gx = reflect101(tx0 + c - 3, w);
-        raw[r * RP + c] = src[(size_t)gy * pitch + gx];
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_TH + 6) * BL_TW; i += 256) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        const uint8_t *p = &raw[r * RP + c];
-        uint32_t acc = 0;
+    sel1 = 0x7654u; selT = 0x3210u; sel2 = 0x7654u;
+    if (e >= 8) return;
+    sel1 = 0; sel2 = 0; selT = 0;
 #pragma unroll
-        for (int k = 0; k < 7; k++) acc += (uint32_t)taps.t[k] * p[k];
-        hb[r * BL_TW + c] = (uint16_t)acc;
+    for (int b = 0; b < 4; b++) {
+        int i = 4 + b;                                     // W1' byte b <- PRMT(W0, W1)
+        int s = (i >= e + 4 && i <= e + 6) ? 2 * (e + 3) - i : i;
+        sel1 |= (uint32_t)s << (4 * b);
+        i = 8 + b;                                         // W2' byte b <- PRMT(T, W2), T = PRMT(W0, W1, selT)
+        s = (i >= e + 4 && i <= e + 6) ? 2 * (e + 3) - i : i;
+        if (s >= 8) sel2 |= (uint32_t)(4 + s - 8) << (4 * b);
+        else { selT |= (uint32_t)s << (4 * b); sel2 |= (uint32_t)b << (4 * b); }
     }
-    __syncthreads();
-    for (int i = tid; i < BL_TH * BL_TW; i += 256) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        const int gy = ty0 + r, gx = tx0 + c;
-        if (gy < h && gx < w) {
-            uint32_t acc = 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
+       const OrbxTile *__restrict__ tiles, BlurTaps taps)
+{
+    const OrbxTile tile = tiles[blockIdx.x];
+    const OrbxLevel &lv = L.lv[tile.level];
+    const int f = blockIdx.y;
+    const int w = lv.w, h = lv.h, pitch = lv.pitch;
+    const int x0 = (tile.x0 + threadIdx.x) * 4;
+    const int y0 = tile.y0 + threadIdx.y * BL_ROWS;
+    if (x0 >= w || y0 >= h) return;
+    const uint8_t *src = pyr + (size_t)f * L.slab + lv.off + x0;
+    uint8_t *dst = blur + (size_t)f * L.slab + lv.off + x0;
+    const uint32_t Tlo = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8 | (uint32_t)taps.t[2] << 16 | (uint32_t)taps.t[3] << 24;
+    const uint32_t Thi = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8 | (uint32_t)taps.t[6] << 16;
+    uint32_t sel1, selT, sel2;
+    blur_edge_selectors(w - x0, sel1, selT, sel2);
+    const int leftOfs = x0 > 0 ? -1 : 0;                   // never read in front of the row
+    const int rows = min(BL_ROWS, h - y0) + 6;
+    uint32_t win[4][7];
 #pragma unroll
-            for (int k = 0; k < 7; k++) acc += (uint32_t)taps.t[k] * hb[(r + k) * BL_TW + c];
-            uint32_t v = (acc + 32768u) >> 16;
-            dst[(size_t)gy * pitch + gx] = (uint8_t)(v > 255u ? 255u : v);
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 7; k++) win[c][k] = 0;
+    // software pipeline: the three words of row r+1 are in flight while row r is being reduced
+    const uint32_t *p = (const uint32_t *)(src + (size_t)reflect101(y0 - 3, h) * pitch);
+    uint32_t n0 = __ldg(p + leftOfs), n1 = __ldg(p), n2 = __ldg(p + 1);
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 7) {
+#pragma unroll
+        for (int s = 0; s < 7; s++) {
+            const int r = r0 + s;
+            if (r < rows) {
+                uint32_t W0 = n0, W1 = n1, W2 = n2;
+                if (r + 1 < rows) {
+                    p = (const uint32_t *)(src + (size_t)reflect101(y0 + r - 2, h) * pitch);
+                    n0 = __ldg(p + leftOfs); n1 = __ldg(p); n2 = __ldg(p + 1);
+                }
+                if (x0 == 0) W0 = __byte_perm(W1, W2, 0x1234);          // left edge: index -k equals index k
+                const uint32_t T = __byte_perm(W0, W1, selT);
+                W2 = __byte_perm(T, W2, sel2);
+                W1 = __byte_perm(W0, W1, sel1);
+                // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
+                win[0][s] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
+                win[1][s] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
+                win[2][s] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
+                win[3][s] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
+                if (r >= 6) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        uint32_t acc = 32768u;
+#pragma unroll
+                        for (int k = 0; k < 7; k++) acc += (uint32_t)taps.t[k] * win[c][(s + 1 + k) % 7];  // oldest row first
+                        o[c] = min(acc >> 16, 255u);
+                    }
+                    *(uint32_t *)(dst + (size_t)(y0 + r - 6) * pitch) = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+                }
+            }
         }
     }
 }
 
-void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, int level, const int taps[7], int batch, cudaStream_t st)
+void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
+                 const int taps[7], int batch, cudaStream_t st)
 {
-    const OrbxLevel &l = L.lv[level];
     BlurTaps t;
     for (int k = 0; k < 7; k++) t.t[k] = taps[k];
-    dim3 grid((l.w + BL_TW - 1) / BL_TW, (l.h + BL_TH - 1) / BL_TH, batch);
-    k_blur<<<grid, 256, 0, st>>>(pyr, blur, L.slab, l.off, l.pitch, l.w, l.h, t);
+    dim3 grid(nTiles, batch);
+    k_blur<<<grid, dim3(32, 4), 0, st>>>(pyr, blur, L, tiles, t);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -207,8 +300,17 @@ void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, int lev
 //   best[frame][rowBase + strip*H + y]   = max(score<<56 | ~order<<28 | x<<14 | y)
 // `order` = (cell index << 12 | yIn << 6 | xIn) is the position in the reference's emission
 // order (cells row-major, raster inside a cell, orbextractor.cpp:930-968).
+//
+// Stages inside the CTA:
+//   0  the (w+6)x(h+6) window is staged in shared memory with aligned 32-bit loads, funnel-shifted
+//      so that the first tested pixel sits on a 4-byte boundary
+//   1  quick reject on 4 pixels per thread (packed bytes): a FAST-9 arc always contains ring
+//      pixel k or k+8, so |I(p) - I(ring_k)| > t must hold for k in {0,8} and for k in {4,12};
+//      survivors (~8 % of pixels) are compacted into a list
+//   2  exact 16-pixel ring test on the survivors; true corners are compacted again
+//   3  corner score, 3x3 NMS on the cell's score map, threshold fallback, emission
 // ------------------------------------------------------------------------------------------
-#define FW_P 72   // shared window pitch (bytes)
+#define FW_P 96   // shared window pitch in bytes (24 words: rows 0..3 of a warp hit disjoint banks)
 #define FS_P 64   // shared score-map pitch
 
 __device__ __forceinline__ int fast_score16(const int (&d)[16])
@@ -231,6 +333,15 @@ __device__ __forceinline__ int fast_score16(const int (&d)[16])
     return max(a, -b) - 1;
 }
 
+__device__ __forceinline__ void fast_ring_diffs(const uint8_t *c, int (&d)[16])
+{
+    const int v = c[0];
+    d[0] = v - c[3 * FW_P];       d[1] = v - c[3 * FW_P + 1];   d[2] = v - c[2 * FW_P + 2];   d[3] = v - c[FW_P + 3];
+    d[4] = v - c[3];              d[5] = v - c[-FW_P + 3];      d[6] = v - c[-2 * FW_P + 2];  d[7] = v - c[-3 * FW_P + 1];
+    d[8] = v - c[-3 * FW_P];      d[9] = v - c[-3 * FW_P - 1];  d[10] = v - c[-2 * FW_P - 2]; d[11] = v - c[-FW_P - 3];
+    d[12] = v - c[-3];            d[13] = v - c[FW_P - 3];      d[14] = v - c[2 * FW_P - 2];  d[15] = v - c[3 * FW_P - 1];
+}
+
 __global__ void __launch_bounds__(128)
 k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout L,
              const OrbxCell *__restrict__ cells, uint32_t *__restrict__ cnt,
@@ -240,84 +351,104 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     __shared__ __align__(16) uint8_t win[66 * FW_P];
     __shared__ __align__(16) uint8_t smap[62 * FS_P];
     __shared__ uint16_t cand[60 * 60];
-    __shared__ int ncand;
+    __shared__ uint16_t corner[60 * 60];
+    __shared__ int ncand, ncorner;
 
     const OrbxCell cell = cells[blockIdx.x];
     const int frame = blockIdx.y;
     const OrbxLevel &lv = L.lv[cell.level];
     const int wEff = (int)cell.w - 6, hEff = (int)cell.h - 6;
     if (wEff <= 0 || hEff <= 0) return;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int th = L.minTh;
 
-    // ---- stage the window: aligned 32-bit loads of each row span
-    const uint8_t *base = pyr + (size_t)frame * L.slab + lv.off;
-    const int xa = cell.x0 & ~3, shift = cell.x0 - xa;
-    const int nw = (shift + cell.w + 3) >> 2;
-    for (int i = tid; i < cell.h * nw; i += 128) {
-        const int r = i / nw, k = i - r * nw;
-        const uint32_t v = __ldg((const uint32_t *)(base + (size_t)(cell.y0 + r) * lv.pitch + xa) + k);
-        ((uint32_t *)win)[r * (FW_P / 4) + k] = v;
+    // ---- stage 0: window column c lives at shared byte (c + 1): tested pixel xIn at byte xIn + 4
+    {
+        const uint8_t *base = pyr + (size_t)frame * L.slab + lv.off + (size_t)cell.y0 * lv.pitch + (int)cell.x0 - 1;
+        const int nw = ((int)cell.w + 1 + 3) >> 2;           // words per row, <= 17
+        const unsigned M = 65536u / nw + 1;
+        for (int i = tid; i < (int)cell.h * nw; i += 128) {
+            const int r = (i * M) >> 16, k = i - r * nw;
+            const uintptr_t a = (uintptr_t)(base + (size_t)r * lv.pitch + 4 * k);
+            const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);
+            ((uint32_t *)win)[r * (FW_P / 4) + k] = __funnelshift_r(__ldg(p), __ldg(p + 1), (int)(a & 3) * 8);
+        }
+        const int zw = (wEff + 2 + 3) >> 2;                   // score map: (hEff+2) rows x (wEff+2) bytes, zero frame included
+        for (int i = tid; i < (hEff + 2) * 16; i += 128) {
+            const int r = i >> 4, k = i & 15;
+            if (k < zw) ((uint32_t *)smap)[r * (FS_P / 4) + k] = 0;
+        }
+        if (tid == 0) { ncand = 0; ncorner = 0; }
     }
-    for (int i = tid; i < 62 * FS_P / 4; i += 128) ((uint32_t *)smap)[i] = 0;
-    if (tid == 0) ncand = 0;
     __syncthreads();
 
-    // ---- stage 1: compass quick-reject at the lower threshold, warp-ballot compaction
-    const int total = wEff * hEff;
-    for (int p0 = 0; p0 < total; p0 += 128) {
-        const int p = p0 + tid;
-        bool pass = false;
-        int yIn = 0, xIn = 0;
-        if (p < total) {
-            yIn = p / wEff; xIn = p - yIn * wEff;
-            const uint8_t *c = &win[(yIn + 3) * FW_P + shift + xIn + 3];
-            const int v = c[0], hi = v + th, lo = v - th;
-            const int a0 = c[3 * FW_P], a8 = c[-3 * FW_P], a4 = c[3], a12 = c[-3];
-            const bool br = ((a0 > hi) | (a8 > hi)) & ((a4 > hi) | (a12 > hi));
-            const bool dk = ((a0 < lo) | (a8 < lo)) & ((a4 < lo) | (a12 < lo));
-            pass = br | dk;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            int b = 0;
-            if (lane == 0) b = atomicAdd(&ncand, __popc(m));
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (pass) cand[b + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(yIn << 6 | xIn);
+    // ---- stage 1: packed quick reject, 4 pixels per thread
+    {
+        const int nQ = (wEff + 3) >> 2, items = nQ * hEff;
+        const unsigned M = 65536u / nQ + 1;
+        const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
+        for (int it = tid; it < items; it += 128) {
+            const int yIn = (it * M) >> 16, q = it - yIn * nQ;
+            const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + q;
+            const uint32_t W0 = rw[0], C = rw[1], W2 = rw[2];
+            const uint32_t U = rw[1 + 3 * (FW_P / 4)], D = rw[1 - 3 * (FW_P / 4)];
+            const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
+            const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
+            const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
+            const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
+            uint32_t pass = X & Y & 0x80808080u;
+            const int left = wEff - 4 * q;                        // valid pixels in this quad
+            if (left < 4) pass &= (1u << (8 * left)) - 1u;
+            if (pass) {
+                int pos = atomicAdd(&ncand, __popc(pass));
+                const int e = yIn << 6 | (q << 2);
+                if (pass & 0x80u) cand[pos++] = (uint16_t)e;
+                if (pass & 0x8000u) cand[pos++] = (uint16_t)(e + 1);
+                if (pass & 0x800000u) cand[pos++] = (uint16_t)(e + 2);
+                if (pass & 0x80000000u) cand[pos] = (uint16_t)(e + 3);
+            }
         }
     }
     __syncthreads();
     const int nc = ncand;
 
-    // ---- stage 2: full 16-pixel ring test and corner score for the survivors
+    // ---- stage 2: exact ring test (9 contiguous brighter or darker), second compaction
     for (int i = tid; i < nc; i += 128) {
-        const int yIn = cand[i] >> 6, xIn = cand[i] & 63;
-        const uint8_t *c = &win[(yIn + 3) * FW_P + shift + xIn + 3];
-        const int v = c[0];
+        const int e = cand[i];
+        const int yIn = e >> 6, xIn = e & 63;
         int d[16];
-        d[0] = v - c[3 * FW_P];       d[1] = v - c[3 * FW_P + 1];   d[2] = v - c[2 * FW_P + 2];   d[3] = v - c[FW_P + 3];
-        d[4] = v - c[3];              d[5] = v - c[-FW_P + 3];      d[6] = v - c[-2 * FW_P + 2];  d[7] = v - c[-3 * FW_P + 1];
-        d[8] = v - c[-3 * FW_P];      d[9] = v - c[-3 * FW_P - 1];  d[10] = v - c[-2 * FW_P - 2]; d[11] = v - c[-FW_P - 3];
-        d[12] = v - c[-3];            d[13] = v - c[FW_P - 3];      d[14] = v - c[2 * FW_P - 2];  d[15] = v - c[3 * FW_P - 1];
+        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + 4], d);
         unsigned mb = 0, md = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) { mb |= (unsigned)(d[k] > th) << k; md |= (unsigned)(d[k] < -th) << k; }
         mb |= mb << 16; md |= md << 16;
         unsigned r = mb & (mb >> 1); r &= r >> 2; r &= r >> 4; r &= mb >> 8;
         unsigned q = md & (md >> 1); q &= q >> 2; q &= q >> 4; q &= md >> 8;
-        if (r | q) smap[(yIn + 1) * FS_P + xIn + 1] = (uint8_t)fast_score16(d);
+        if (r | q) corner[atomicAdd(&ncorner, 1)] = (uint16_t)e;
+    }
+    __syncthreads();
+    const int nk = ncorner;
+
+    // ---- stage 3a: corner scores into the cell's score map
+    for (int i = tid; i < nk; i += 128) {
+        const int e = corner[i];
+        const int yIn = e >> 6, xIn = e & 63;
+        int d[16];
+        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + 4], d);
+        smap[(yIn + 1) * FS_P + xIn + 1] = (uint8_t)fast_score16(d);
     }
     __syncthreads();
 
-    // ---- stage 3: 3x3 non-maximum suppression (strict >, outside the cell interior counts as 0)
+    // ---- stage 3b: 3x3 non-maximum suppression (strict >, outside the cell interior counts as 0)
     int any = 0;
-    for (int i = tid; i < nc; i += 128) {
-        const int yIn = cand[i] >> 6, xIn = cand[i] & 63;
+    for (int i = tid; i < nk; i += 128) {
+        const int e = corner[i];
+        const int yIn = e >> 6, xIn = e & 63;
         const uint8_t *s = &smap[(yIn + 1) * FS_P + xIn + 1];
         const int v = s[0];
-        if (v && v > s[-1] && v > s[1] && v > s[-FS_P - 1] && v > s[-FS_P] && v > s[-FS_P + 1] &&
+        if (v > s[-1] && v > s[1] && v > s[-FS_P - 1] && v > s[-FS_P] && v > s[-FS_P + 1] &&
             v > s[FS_P - 1] && v > s[FS_P] && v > s[FS_P + 1]) {
-            cand[i] |= 0x8000;
+            corner[i] = (uint16_t)(e | 0x8000);
             any |= (v >= L.iniTh);
         }
     }
@@ -325,21 +456,20 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     // it is non-empty after NMS; NMS(ini) == {k in NMS(min) : score >= ini}
     const int haveIni = __syncthreads_or(any);
 
-    // ---- stage 4: emit into the per-(strip,row) summaries
-    const int cellIdx = cell.orderBase >> 12;
-    const int ci = cellIdx / lv.nCols, cj = cellIdx - ci * lv.nCols;
+    // ---- stage 3c: emit into the per-(strip,row) summaries
+    const unsigned orderBase = (unsigned)(cell.ci * lv.nCols + cell.cj) << 12;
     uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
-    for (int i = tid; i < nc; i += 128) {
-        const int e = cand[i];
+    for (int i = tid; i < nk; i += 128) {
+        const int e = corner[i];
         if (!(e & 0x8000)) continue;
         const int yIn = (e >> 6) & 63, xIn = e & 63;
         const int s = smap[(yIn + 1) * FS_P + xIn + 1];
         if (haveIni && s < L.iniTh) continue;
-        const int xr = cj * lv.wCell + 3 + xIn, yr = ci * lv.hCell + 3 + yIn; // relative to (16,16), :963-964
-        const int strip = xr / lv.hX;                                         // :710
+        const int xr = cell.cj * lv.wCell + 3 + xIn, yr = cell.ci * lv.hCell + 3 + yIn; // relative to (16,16), :963-964
+        const int strip = xr / lv.hX;                                                   // :710
         const int row = strip * lv.H + yr;
-        const unsigned order = cell.orderBase | (unsigned)(yIn << 6 | xIn);
+        const unsigned order = orderBase | (unsigned)(yIn << 6 | xIn);
         const unsigned long long key = ((unsigned long long)s << 56) |
                                        ((unsigned long long)(0x0fffffffu - order) << 28) |
                                        ((unsigned long long)xr << 14) | (unsigned long long)yr;
@@ -664,85 +794,125 @@ __device__ __forceinline__ void glibc_sincosf(float y, float *sn, float *cs)
 
 struct DescUmax { int u[16]; };
 
-__global__ void __launch_bounds__(128)
+#define DS_WARPS 4          // warps per CTA
+#define DS_PER_WARP 4       // keypoint slots handled by one warp, one after the other
+#define DS_PP 40            // shared patch pitch (bytes): 37 columns + alignment slack
+
+__global__ void __launch_bounds__(DS_WARPS * 32)
 k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
            const int2 *__restrict__ slots, const int *__restrict__ lvlCount, DescUmax um,
            orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts)
 {
-    __shared__ int8_t pat[1024];
+    __shared__ __align__(16) uint8_t patch[DS_WARPS][37 * DS_PP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += 128) ((uint32_t *)pat)[i] = ((const uint32_t *)d_pattern)[i];
-    __syncthreads();
     const int frame = blockIdx.y;
-    const int slot = blockIdx.x * 4 + warp;
-    if (slot >= L.slotsPerFrame) return;
-    // level of this slot + exclusive prefix of the per-level counts
-    const int *lc = lvlCount + frame * L.nlevels;
-    int level = 0;
-    for (int l = 1; l < L.nlevels; l++) if (slot >= L.lv[l].slotBase) level = l;
-    const OrbxLevel &lv = L.lv[level];
-    const int i = slot - lv.slotBase;
-    int before = 0, total = 0;
-    for (int l = 0; l < L.nlevels; l++) { const int cnt = lc[l]; if (l < level) before += cnt; total += cnt; }
-    if (slot == 0 && lane == 0) counts[frame] = total;
-    if (i >= lc[level]) return;
-    const int2 sl = slots[(size_t)frame * L.slotsPerFrame + slot];
-    const int cx = (sl.x & 0xffff) + ORBX_MINB, cy = (sl.x >> 16) + ORBX_MINB; // :984-985
-    const size_t lbase = (size_t)frame * L.slab + lv.off;
-
-    // ---- IC_Angle: lane = column u, loop over rows v (coalesced 31-byte row reads)
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, au = u < 0 ? -u : u;
-        const uint8_t *cp = pyr + lbase + (size_t)cy * lv.pitch + cx + u;
-        int colsum = 0;
+    // this lane's 16 pattern points (descriptor byte `lane`), kept in registers across its slots
+    float px[16], py[16];
+    {
+        const int4 a = __ldg((const int4 *)(d_pattern + lane * 32)), b = __ldg((const int4 *)(d_pattern + lane * 32 + 16));
+        const int w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int v = -15; v <= 15; v++) {
-            const int av = v < 0 ? -v : v;
-            if (au <= um.u[av]) {
-                const int val = cp[v * lv.pitch];
-                colsum += val;
-                m01 += v * val;
+        for (int k = 0; k < 8; k++) {
+            px[2 * k] = (float)(int8_t)(w[k] & 0xff);         py[2 * k] = (float)(int8_t)((w[k] >> 8) & 0xff);
+            px[2 * k + 1] = (float)(int8_t)((w[k] >> 16) & 0xff); py[2 * k + 1] = (float)(int8_t)((w[k] >> 24) & 0xff);
+        }
+    }
+    // per-level counts of this frame -> exclusive prefix (lane l holds level l)
+    const int *lc = lvlCount + frame * L.nlevels;
+    const int myCnt = lane < L.nlevels ? lc[lane] : 0;
+    int incl = myCnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (blockIdx.x == 0 && tid == 0) counts[frame] = total;
+    const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
+
+    for (int j = 0; j < DS_PER_WARP; j++) {
+        const int slot = (blockIdx.x * DS_PER_WARP + j) * DS_WARPS + warp;     // warp-uniform
+        if (slot >= L.slotsPerFrame) break;
+        // level = last l with slotBase[l] <= slot
+        const unsigned ge = __ballot_sync(0xffffffffu, slot >= myBase);
+        const int level = 31 - __clz((int)ge);
+        const OrbxLevel &lv = L.lv[level];
+        const int i = slot - lv.slotBase;
+        const int cntL = __shfl_sync(0xffffffffu, myCnt, level);
+        if (i >= cntL) continue;
+        const int before = __shfl_sync(0xffffffffu, incl - myCnt, level);
+        const int2 sl = slots[(size_t)frame * L.slotsPerFrame + slot];
+        const int cx = (sl.x & 0xffff) + ORBX_MINB, cy = (sl.x >> 16) + ORBX_MINB; // :984-985
+        const int pitch = lv.pitch;
+        const size_t lbase = (size_t)frame * L.slab + lv.off;
+
+        // ---- stage the 37x37 blurred patch (rows cy-18.., cols cx-18..) with aligned word loads
+        const int xs = cx - 18, xa = xs & ~3, shiftb = xs - xa;
+        {
+            const int rr = lane / 10, wi = lane - rr * 10;
+            const uint8_t *g = blur + lbase + (size_t)(cy - 18) * pitch + xa + 4 * wi;
+            uint32_t *sp = (uint32_t *)patch[warp];
+            if (lane < 30) {
+#pragma unroll
+                for (int r0 = 0; r0 < 39; r0 += 3) {
+                    const int r = r0 + rr;
+                    if (r < 37) sp[r * (DS_PP / 4) + wi] = __ldg((const uint32_t *)(g + (size_t)r * pitch));
+                }
             }
         }
-        m10 = u * colsum;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- rBRIEF: lane = descriptor byte, 16 rotated samples each
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
-    float sa, ca;
-    glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
-    const float a = ca, b = sa;
-    const uint8_t *center = blur + lbase + (size_t)cy * lv.pitch + cx;
-    const int8_t *pp = pat + lane * 32;
-    int val = 0;
+        // ---- IC_Angle on the unblurred level: lane = column u, loop over rows v
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int u = lane - 15, au = u < 0 ? -u : u;
+            const uint8_t *cp = pyr + lbase + (size_t)(cy - 15) * pitch + cx + u;
+            int colsum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int t[2];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const float px = (float)pp[4 * k + 2 * e], py = (float)pp[4 * k + 2 * e + 1];
-            const int row = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int col = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            t[e] = center[row * lv.pitch + col];
+            for (int v = -15; v <= 15; v++) {
+                const int av = v < 0 ? -v : v;
+                if (au <= um.u[av]) {
+                    const int val = cp[(v + 15) * pitch];
+                    colsum += val;
+                    m01 += v * val;
+                }
+            }
+            m10 = u * colsum;
         }
-        val |= (t[0] < t[1]) << k;
-    }
-    const int o = before + i;
-    desc[((size_t)frame * L.kpStride + o) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        orbx_keypoint_pod kp;
-        float fx = (float)cx, fy = (float)cy;
-        if (level != 0) { fx = __fmul_rn(fx, lv.sf); fy = __fmul_rn(fy, lv.sf); }
-        kp.x = fx; kp.y = fy; kp.size = (float)lv.kpSize; kp.angle = angle; kp.response = (float)sl.y;
-        kp.octave = level; kp.class_id = -1;
-        kps[(size_t)frame * L.kpStride + o] = kp;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+        // ---- rBRIEF: lane = descriptor byte, 16 rotated samples each, gathered from shared memory
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+        float sa, ca;
+        glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
+        const float a = ca, b = sa;
+        __syncwarp();
+        const uint8_t *center = patch[warp] + 18 * DS_PP + shiftb + 18;
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int t[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const float x = px[2 * k + e], y = py[2 * k + e];
+                const int row = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));
+                const int col = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));
+                t[e] = center[row * DS_PP + col];
+            }
+            val |= (t[0] < t[1]) << k;
+        }
+        __syncwarp();     // the patch is reused by this warp's next slot
+        const int o = before + i;
+        desc[((size_t)frame * L.kpStride + o) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            orbx_keypoint_pod kp;
+            float fx = (float)cx, fy = (float)cy;
+            if (level != 0) { fx = __fmul_rn(fx, lv.sf); fy = __fmul_rn(fy, lv.sf); }
+            kp.x = fx; kp.y = fy; kp.size = (float)lv.kpSize; kp.angle = angle; kp.response = (float)sl.y;
+            kp.octave = level; kp.class_id = -1;
+            kps[(size_t)frame * L.kpStride + o] = kp;
+        }
     }
 }
 
@@ -752,6 +922,7 @@ void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &
 {
     DescUmax um;
     for (int k = 0; k < 16; k++) um.u[k] = umax[k];
-    dim3 grid((L.slotsPerFrame + 3) / 4, batch);
-    k_describe<<<grid, 128, 0, st>>>(pyr, blur, L, slots, lvlCount, um, kps, desc, counts);
+    const int perBlock = DS_WARPS * DS_PER_WARP;
+    dim3 grid((L.slotsPerFrame + perBlock - 1) / perBlock, batch);
+    k_describe<<<grid, DS_WARPS * 32, 0, st>>>(pyr, blur, L, slots, lvlCount, um, kps, desc, counts);
 }

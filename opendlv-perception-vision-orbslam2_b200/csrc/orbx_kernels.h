@@ -7,8 +7,9 @@ struct orbx_keypoint_pod { float x, y, size, angle, response; int32_t octave, cl
 
 void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch, uint8_t *pyr,
                         const OrbxLayout &L, int batch, cudaStream_t st);
-void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const OrbxRTab *tabs, int batch, cudaStream_t st);
-void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, int level, const int taps[7], int batch, cudaStream_t st);
+void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st);
+void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
+                 const int taps[7], int batch, cudaStream_t st);
 void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, uint32_t *cnt,
                  unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st);
 size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes);

@@ -36,7 +36,7 @@ class OrbxError(RuntimeError):
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
            "orbx_extract_batch_device", "orbx_device_results", "orbx_max_keypoints", "orbx_get_level",
-           "orbx_scale_tables", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
+           "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_distance_pairs"]
 
@@ -62,6 +62,7 @@ def lib():
     L.orbx_max_keypoints.argtypes = [vp]
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
+    L.orbx_profile_stages.argtypes = [vp, C.c_int, fp, C.c_int]
     L.orbx_debug_blurred.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, ip, ip]
     L.orbx_debug_enable_candidates.argtypes = [vp, C.c_int]
     L.orbx_debug_candidates.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
@@ -153,6 +154,13 @@ class Extractor:
         k, d, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
         self._check(lib().orbx_device_results(self._h, C.byref(k), C.byref(d), C.byref(c), C.byref(s)))
         return k.value, d.value, c.value, s.value
+
+    STAGES = ("resize", "fast", "octree", "blur", "describe")
+
+    def profile_stages(self, reps=5):
+        ms = np.zeros(5, np.float32)
+        self._check(lib().orbx_profile_stages(self._h, reps, ms.ctypes.data_as(C.POINTER(C.c_float)), 5))
+        return dict(zip(self.STAGES, ms.tolist()))
 
     def level(self, frame, level):
         """m_vImagePyramid[level] of `frame` of the last call, as a host array (copy)."""

@@ -6,6 +6,7 @@
 // pixel primitives are therefore implemented by the C oracle (oracle/orb_oracle.c), each of which
 // is checked bit-for-bit against cv2 4.13 in tests/test_oracle_primitives.py.
 #pragma once
+#include <algorithm>
 #include <cassert>
 #include <cmath>
 #include <cstdint>

@@ -202,7 +202,7 @@ class Extractor:
         if not self._h:
             raise ValueError("bad extractor parameters")
         lib().orbo_set_tie_rule(self._h, tie_rule)
-        self.params = lib().orbo_get_params(self._h).contents
+        self.params = Params.from_buffer_copy(lib().orbo_get_params(self._h).contents)  # own copy: outlives the handle
         self.nfeatures, self.nlevels = nfeatures, nlevels
 
     def __del__(self):

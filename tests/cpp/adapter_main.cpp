@@ -1,0 +1,63 @@
+// Drives the drop-in C++ adapter exactly the way OrbFrame does (orbframe.cpp:213-223): construct,
+// ExtractFeatures(image, keys, descriptors), read getters and m_vImagePyramid.  Compiled against
+// oracle/cvshim (this image has no OpenCV C++ headers).  Reads a raw 8-bit image, writes the
+// results as flat binary for the pytest that compares them with the oracle.
+#include "orbextractor_b200.hpp"
+#include "orbmatcher_b200.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+// the shim declares these for the reference translation unit; the adapter never calls them
+namespace cv {
+void resize(const Mat &, Mat &, Size, double, double, int) { abort(); }
+void copyMakeBorder(const Mat &, Mat &, int, int, int, int, int) { abort(); }
+void FAST(const Mat &, std::vector<KeyPoint> &, int, bool) { abort(); }
+void GaussianBlur(const Mat &, Mat &, Size, double, double, int) { abort(); }
+float fastAtan2(float, float) { abort(); }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 7) { fprintf(stderr, "usage: %s in.raw w h nfeatures nlevels out.bin\n", argv[0]); return 2; }
+    const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]), nl = atoi(argv[5]);
+    std::vector<uchar> buf((size_t)w * h);
+    FILE *f = fopen(argv[1], "rb");
+    if (!f || fread(buf.data(), 1, buf.size(), f) != buf.size()) { perror("read"); return 2; }
+    fclose(f);
+    try {
+        OrbExtractor ex(nf, 1.2f, nl, 20, 7);
+        cv::Mat image(h, w, CV_8UC1, buf.data(), (size_t)w);
+        std::vector<cv::KeyPoint> keys;
+        cv::Mat desc;
+        ex.ExtractFeatures(image, keys, desc);
+        ex.ExtractFeatures(image, keys, desc);   // second call on the same instance, like the next frame
+        FILE *o = fopen(argv[6], "wb");
+        int n = (int)keys.size(), levels = ex.getLevels();
+        fwrite(&n, 4, 1, o);
+        fwrite(keys.data(), sizeof(cv::KeyPoint), n, o);
+        for (int i = 0; i < n; i++) fwrite(desc.ptr(i), 1, 32, o);
+        fwrite(&levels, 4, 1, o);
+        std::vector<float> sf = ex.getScaleFactors(), is2 = ex.getInverseScaleSigmaSquares();
+        fwrite(sf.data(), 4, levels, o);
+        fwrite(is2.data(), 4, levels, o);
+        for (int l = 0; l < levels; l++) {
+            const cv::Mat &m = ex.m_vImagePyramid[l];
+            fwrite(&m.cols, 4, 1, o); fwrite(&m.rows, 4, 1, o);
+            for (int y = 0; y < m.rows; y++) fwrite(m.ptr(y), 1, m.cols, o);
+        }
+        // matcher adapter: the descriptors against themselves -> every best match is itself at distance 0
+        if (n > 1) {
+            orbslam_b200::HammingMatcher hm(n, n);
+            hm.SetTrain(desc);
+            std::vector<int> idx, d1, d2;
+            hm.KnnMatch2(desc, idx, d1, d2);
+            fwrite(idx.data(), 4, n, o); fwrite(d1.data(), 4, n, o); fwrite(d2.data(), 4, n, o);
+        }
+        fclose(o);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "adapter failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,66 @@
+"""The drop-in C++ adapter (cpp/orbextractor_b200.hpp, cpp/orbmatcher_b200.hpp): compiles against the
+cv shim on CPU; on the GPU it is driven like OrbFrame drives the reference class and compared with the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "opendlv-perception-vision-orbslam2_b200")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "adapter_main")
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "cpp"), "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "oracle", "cvshim"), os.path.join(ROOT, "tests", "cpp", "adapter_main.cpp"),
+                           "-o", exe, "-L", PKG, "-lorbx", f"-Wl,-rpath,{PKG}"])
+    return exe
+
+
+def test_adapter_compiles_with_reference_signatures(tmp_path):
+    exe = _build(tmp_path)
+    assert os.path.exists(exe)
+    hdr = open(os.path.join(ROOT, "cpp", "orbextractor_b200.hpp")).read()
+    # the public surface of the reference's include/orbextractor.hpp:92-109
+    for sig in ("OrbExtractor(int nFeatures, float scaleFactor, int nLevels, int initialFastTh, int minFastTh)",
+                "void ExtractFeatures(cv::InputArray image, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors)",
+                "int getLevels()", "double getScaleFactor()", "std::vector<float> getScaleFactors()",
+                "std::vector<float> getInverseScaleFactors()", "std::vector<float> getScaleSigmaSquares()",
+                "std::vector<float> getInverseScaleSigmaSquares()", "std::vector<cv::Mat> m_vImagePyramid;"):
+        assert sig in hdr, sig
+
+
+@pytest.mark.gpu
+def test_adapter_end_to_end(tmp_path, oracle):
+    exe = _build(tmp_path)
+    w, h, nf, nl = 752, 480, 1200, 8       # EuRoC-sized frame
+    img = synth.scene_s1(w, h, 2024)
+    raw = tmp_path / "in.raw"; out = tmp_path / "out.bin"
+    img.tofile(raw)
+    subprocess.check_call([exe, str(raw), str(w), str(h), str(nf), str(nl), str(out)])
+    b = open(out, "rb").read()
+    n = struct.unpack_from("<i", b, 0)[0]; o = 4
+    kps = np.frombuffer(b, oracle.KP_DTYPE, n, o); o += 28 * n
+    desc = np.frombuffer(b, np.uint8, 32 * n, o).reshape(n, 32); o += 32 * n
+    levels = struct.unpack_from("<i", b, o)[0]; o += 4
+    sf = np.frombuffer(b, np.float32, levels, o); o += 4 * levels
+    is2 = np.frombuffer(b, np.float32, levels, o); o += 4 * levels
+    oex = oracle.Extractor(nf, 1.2, nl)
+    okps, odesc = oex.extract(img)
+    assert n == len(okps) and kps.tobytes() == okps.tobytes() and np.array_equal(desc, odesc)
+    assert levels == nl and np.array_equal(sf, np.array(oex.params.sf[:nl], np.float32))
+    assert np.array_equal(is2, np.array(oex.params.inv_sigma2[:nl], np.float32))
+    for l in range(nl):
+        lw, lh = struct.unpack_from("<ii", b, o); o += 8
+        a = np.frombuffer(b, np.uint8, lw * lh, o).reshape(lh, lw); o += lw * lh
+        assert np.array_equal(a, oex.level(l)), f"m_vImagePyramid[{l}]"
+    idx = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    d1 = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    d2 = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    oi, o1, o2 = oracle.knn2(desc, desc)
+    assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
+    assert (d1 == 0).all()
