@@ -72,7 +72,8 @@ struct orbx_extractor {
     cudaStream_t stream = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaStream_t stream2 = nullptr;
-    DevBuf<uint8_t> dPyr, dBlur, dDesc;
+    DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
+    struct { uint8_t *p = nullptr; } dPyr, dBlur;    // slab bases inside the padded allocations
     DevBuf<uint32_t> dCnt;
     DevBuf<unsigned long long> dBest;
     DevBuf<int2> dSlots;
@@ -265,8 +266,11 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
 int ensureArenas(orbx_extractor *h, int batch)
 {
     const OrbxLayout &L = h->L;
-    CK(h->dPyr.ensure((size_t)L.slab * batch + 256));
-    CK(h->dBlur.ensure((size_t)L.slab * batch + 256));
+    // 256-byte pads in front of and behind the slabs: edge threads may read one word outside a row
+    CK(h->dPyrRaw.ensure((size_t)L.slab * batch + 512));
+    CK(h->dBlurRaw.ensure((size_t)L.slab * batch + 512));
+    h->dPyr.p = h->dPyrRaw.p + 256;
+    h->dBlur.p = h->dBlurRaw.p + 256;
     CK(h->dCnt.ensure((size_t)L.rowsPerFrame * batch));
     CK(h->dBest.ensure((size_t)L.rowsPerFrame * batch));
     CK(h->dSlots.ensure((size_t)L.slotsPerFrame * batch));
@@ -360,7 +364,13 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     if (!h) return ORBX_ERR_NOMEM;
     h->cfg = *cfg;
     bool zero = true;
-    for (int k = 0; k < 7; k++) zero = zero && cfg->blur_taps[k] == 0;
+    int tapSum = 0;
+    for (int k = 0; k < 7; k++) {
+        zero = zero && cfg->blur_taps[k] == 0;
+        if (cfg->blur_taps[k] < 0 || cfg->blur_taps[k] > 255) return ORBX_ERR_ARG;
+        tapSum += cfg->blur_taps[k];
+    }
+    if (tapSum > 257) return ORBX_ERR_ARG;   // horizontal sums are carried in 16 bits (255 * 257 = 65535)
     static const int kDefaultTaps[7] = {18, 34, 48, 56, 48, 34, 18};
     for (int k = 0; k < 7; k++) h->taps[k] = zero ? kDefaultTaps[k] : cfg->blur_taps[k];
     buildTables(h);
@@ -396,7 +406,7 @@ void orbx_destroy(orbx_extractor *h)
     if (!h) return;
     if (h->stream) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->stream); }
     if (h->stream2) cudaStreamSynchronize(h->stream2);
-    h->dPyr.release(); h->dBlur.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
+    h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
     h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();

@@ -117,7 +117,7 @@ void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch,
 // outputs share a source row), so every source row is interpolated once per strip.  Row base
 // addresses are uniform across the CTA; per-thread addressing is a 32-bit column offset.
 // ------------------------------------------------------------------------------------------
-#define RS_ROWS 16
+#define RS_ROWS 8
 
 __device__ __forceinline__ void resize_hrow(const uint8_t *__restrict__ rowp, const int (&sx0)[4], const int (&sx1)[4],
                                             const uint32_t (&cc)[4], int (&hv)[4])
@@ -133,9 +133,12 @@ __global__ void __launch_bounds__(64)
 k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, int dstOff, int dstPitch, int dw, int dh,
          const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
 {
+    __shared__ int4 sy[RS_ROWS];
     const int f = blockIdx.z;
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y0 = blockIdx.y * RS_ROWS;
+    if (threadIdx.x < RS_ROWS) sy[threadIdx.x] = __ldg(&ytab[min(y0 + (int)threadIdx.x, dh - 1)]);
+    __syncthreads();
     if (x0 >= dw) return;
     const uint8_t *src = pyr + (size_t)f * slab + srcOff;          // uniform
     uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch;
@@ -150,7 +153,7 @@ k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, in
     int rb = -1;
     int ha[4], hb[4] = {0, 0, 0, 0};
     for (int r = 0; r < yEnd; r++) {
-        const int4 ty = __ldg(&ytab[y0 + r]);                      // {sy0, sy1, b0, b1}, uniform across the CTA
+        const int4 ty = sy[r];                                     // {sy0, sy1, b0, b1}, uniform across the CTA
         if (ty.x == rb) {
 #pragma unroll
             for (int k = 0; k < 4; k++) ha[k] = hb[k];
@@ -233,18 +236,23 @@ k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid
     uint8_t *dst = blur + (size_t)f * L.slab + lv.off + x0;
     const uint32_t Tlo = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8 | (uint32_t)taps.t[2] << 16 | (uint32_t)taps.t[3] << 24;
     const uint32_t Thi = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8 | (uint32_t)taps.t[6] << 16;
+    const uint32_t T01 = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8, T23 = (uint32_t)taps.t[2] | (uint32_t)taps.t[3] << 8;
+    const uint32_t T45 = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8, T6 = (uint32_t)taps.t[6];
     uint32_t sel1, selT, sel2;
     blur_edge_selectors(w - x0, sel1, selT, sel2);
-    const int leftOfs = x0 > 0 ? -1 : 0;                   // never read in front of the row
+    const bool leftEdge = x0 == 0;
     const int rows = min(BL_ROWS, h - y0) + 6;
-    uint32_t win[4][7];
+    // pp[c][s]: horizontal sums of (row before, row in slot s) packed as two 16-bit halves
+    uint32_t pp[4][7], prev[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < 4; c++)
 #pragma unroll
-        for (int k = 0; k < 7; k++) win[c][k] = 0;
-    // software pipeline: the three words of row r+1 are in flight while row r is being reduced
-    const uint32_t *p = (const uint32_t *)(src + (size_t)reflect101(y0 - 3, h) * pitch);
-    uint32_t n0 = __ldg(p + leftOfs), n1 = __ldg(p), n2 = __ldg(p + 1);
+        for (int k = 0; k < 7; k++) pp[c][k] = 0;
+    // software pipeline: the three words of row r+1 are in flight while row r is being reduced.
+    // p[-1] is always addressable: the slab arena has a front pad (for x0 == 0 the value is replaced).
+    int gy = y0 - 3; gy = gy < 0 ? -gy : gy;
+    const uint32_t *p = (const uint32_t *)(src + (size_t)gy * pitch);
+    uint32_t n0 = __ldg(p - 1), n1 = __ldg(p), n2 = __ldg(p + 1);
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 7) {
 #pragma unroll
@@ -253,28 +261,36 @@ k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid
             if (r < rows) {
                 uint32_t W0 = n0, W1 = n1, W2 = n2;
                 if (r + 1 < rows) {
-                    p = (const uint32_t *)(src + (size_t)reflect101(y0 + r - 2, h) * pitch);
-                    n0 = __ldg(p + leftOfs); n1 = __ldg(p); n2 = __ldg(p + 1);
+                    int g = y0 + r - 2;                              // REFLECT_101 of the next row (|overshoot| <= 3 < h)
+                    g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
+                    p = (const uint32_t *)(src + (size_t)g * pitch);
+                    n0 = __ldg(p - 1); n1 = __ldg(p); n2 = __ldg(p + 1);
                 }
-                if (x0 == 0) W0 = __byte_perm(W1, W2, 0x1234);          // left edge: index -k equals index k
+                if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);      // left edge: index -k equals index k
                 const uint32_t T = __byte_perm(W0, W1, selT);
                 W2 = __byte_perm(T, W2, sel2);
                 W1 = __byte_perm(W0, W1, sel1);
                 // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
-                win[0][s] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
-                win[1][s] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
-                win[2][s] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
-                win[3][s] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
+                uint32_t hs[4];
+                hs[0] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
+                hs[1] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
+                hs[2] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
+                hs[3] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
+                uint32_t acc[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    pp[c][s] = __byte_perm(prev[c], hs[c], 0x5410);
+                    prev[c] = hs[c];
+                    // rows r-6..r with taps 0..6: pairs end in slots of rows r-5, r-3, r-1; row r alone
+                    uint32_t a = 32768u + T6 * hs[c];
+                    a = __dp2a_lo(pp[c][(s + 2) % 7], T01, a);
+                    a = __dp2a_lo(pp[c][(s + 4) % 7], T23, a);
+                    a = __dp2a_lo(pp[c][(s + 6) % 7], T45, a);
+                    acc[c] = min(a, 0x00ffffffu);                    // result byte = bits 16..23, saturated
+                }
                 if (r >= 6) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        uint32_t acc = 32768u;
-#pragma unroll
-                        for (int k = 0; k < 7; k++) acc += (uint32_t)taps.t[k] * win[c][(s + 1 + k) % 7];  // oldest row first
-                        o[c] = min(acc >> 16, 255u);
-                    }
-                    *(uint32_t *)(dst + (size_t)(y0 + r - 6) * pitch) = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+                    const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+                    *(uint32_t *)(dst + (size_t)(y0 + r - 6) * pitch) = __byte_perm(lo, hi, 0x5410);
                 }
             }
         }
@@ -795,15 +811,23 @@ __device__ __forceinline__ void glibc_sincosf(float y, float *sn, float *cs)
 struct DescUmax { int u[16]; };
 
 #define DS_WARPS 4          // warps per CTA
-#define DS_PER_WARP 4       // keypoint slots handled by one warp, one after the other
-#define DS_PP 40            // shared patch pitch (bytes): 37 columns + alignment slack
+#define DS_PER_WARP 8       // keypoint slots handled by one warp, one after the other
+#define DS_PP 40            // shared patch pitch (bytes): up to 10 aligned words per row
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wgt), "r"(acc));
+    return d;
+}
 
 __global__ void __launch_bounds__(DS_WARPS * 32)
 k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
            const int2 *__restrict__ slots, const int *__restrict__ lvlCount, DescUmax um,
            orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts)
 {
-    __shared__ __align__(16) uint8_t patch[DS_WARPS][37 * DS_PP];
+    __shared__ __align__(16) uint8_t patchB[DS_WARPS][37 * DS_PP];   // blurred 37x37 patch (rBRIEF samples)
+    __shared__ __align__(16) uint8_t patchA[DS_WARPS][32 * DS_PP];   // unblurred 31x31 patch (IC_Angle)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     // this lane's 16 pattern points (descriptor byte `lane`), kept in registers across its slots
@@ -817,6 +841,28 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
             px[2 * k + 1] = (float)(int8_t)((w[k] >> 16) & 0xff); py[2 * k + 1] = (float)(int8_t)((w[k] >> 24) & 0xff);
         }
     }
+    // IC_Angle weights of this lane's patch row v = lane-15: byte j of word k is column u = 4k+j-15;
+    // wu = u inside the disc (|u| <= umax[|v|], orbextractor.cpp:150-152), w1 = 1 inside, 0 outside
+    uint32_t wu[8], w1[8];
+    {
+        const int v = lane - 15, av = v < 0 ? -v : v;
+        int d = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if (k == av) d = um.u[k];
+        if (lane == 31) d = -1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t a = 0, b = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int u = 4 * k + j - 15;
+                const bool in = (u <= d) && (-u <= d);
+                a |= in ? ((uint32_t)(u & 0xff) << (8 * j)) : 0u;
+                b |= in ? (1u << (8 * j)) : 0u;
+            }
+            wu[k] = a; w1[k] = b;
+        }
+    }
     // per-level counts of this frame -> exclusive prefix (lane l holds level l)
     const int *lc = lvlCount + frame * L.nlevels;
     const int myCnt = lane < L.nlevels ? lc[lane] : 0;
@@ -826,6 +872,7 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (blockIdx.x == 0 && tid == 0) counts[frame] = total;
     const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
+    const int rr10 = lane / 10, wi10 = lane - rr10 * 10;      // staging role: 3 rows x 10 words per pass
 
     for (int j = 0; j < DS_PER_WARP; j++) {
         const int slot = (blockIdx.x * DS_PER_WARP + j) * DS_WARPS + warp;     // warp-uniform
@@ -843,38 +890,42 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
         const int pitch = lv.pitch;
         const size_t lbase = (size_t)frame * L.slab + lv.off;
 
-        // ---- stage the 37x37 blurred patch (rows cy-18.., cols cx-18..) with aligned word loads
-        const int xs = cx - 18, xa = xs & ~3, shiftb = xs - xa;
-        {
-            const int rr = lane / 10, wi = lane - rr * 10;
-            const uint8_t *g = blur + lbase + (size_t)(cy - 18) * pitch + xa + 4 * wi;
-            uint32_t *sp = (uint32_t *)patch[warp];
-            if (lane < 30) {
+        // ---- stage both patches with aligned word loads (3 rows x 10 words per pass)
+        const int xsB = cx - 18, xaB = xsB & ~3, shB = xsB - xaB;     // blurred: 37 rows from cy-18
+        const int xsA = cx - 15, xaA = xsA & ~3, shA = xsA - xaA;     // unblurred: 31 rows from cy-15
+        if (lane < 30) {
+            const uint8_t *gB = blur + lbase + (size_t)(cy - 18 + rr10) * pitch + xaB + 4 * wi10;
+            const uint8_t *gA = pyr + lbase + (size_t)(cy - 15 + rr10) * pitch + xaA + 4 * wi10;
+            uint32_t *sB = (uint32_t *)patchB[warp] + rr10 * (DS_PP / 4) + wi10;
+            uint32_t *sA = (uint32_t *)patchA[warp] + rr10 * (DS_PP / 4) + wi10;
+            const int step = 3 * pitch;
 #pragma unroll
-                for (int r0 = 0; r0 < 39; r0 += 3) {
-                    const int r = r0 + rr;
-                    if (r < 37) sp[r * (DS_PP / 4) + wi] = __ldg((const uint32_t *)(g + (size_t)r * pitch));
-                }
+            for (int r0 = 0; r0 < 33; r0 += 3) {
+                if (r0 + rr10 < 31) sA[r0 * (DS_PP / 4)] = __ldg((const uint32_t *)(gA + (size_t)(r0 / 3) * step));
+            }
+#pragma unroll
+            for (int r0 = 0; r0 < 39; r0 += 3) {
+                if (r0 + rr10 < 37) sB[r0 * (DS_PP / 4)] = __ldg((const uint32_t *)(gB + (size_t)(r0 / 3) * step));
             }
         }
+        __syncwarp();
 
-        // ---- IC_Angle on the unblurred level: lane = column u, loop over rows v
-        int m10 = 0, m01 = 0;
+        // ---- IC_Angle: lane = patch row v; 32 bytes of the row (cols cx-15 .. cx+16) against the weights
+        int m10 = 0, rowsum = 0;
         if (lane < 31) {
-            const int u = lane - 15, au = u < 0 ? -u : u;
-            const uint8_t *cp = pyr + lbase + (size_t)(cy - 15) * pitch + cx + u;
-            int colsum = 0;
+            const uint32_t *rw = (const uint32_t *)patchA[warp] + lane * (DS_PP / 4);
+            uint32_t W[9];
 #pragma unroll
-            for (int v = -15; v <= 15; v++) {
-                const int av = v < 0 ? -v : v;
-                if (au <= um.u[av]) {
-                    const int val = cp[(v + 15) * pitch];
-                    colsum += val;
-                    m01 += v * val;
-                }
+            for (int k = 0; k < 9; k++) W[k] = rw[k];
+            const int sh = shA * 8;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t B = __funnelshift_r(W[k], W[k + 1], sh);
+                m10 = dp4a_u8_s8(B, wu[k], m10);
+                rowsum = dp4a_u8_s8(B, w1[k], rowsum);
             }
-            m10 = u * colsum;
         }
+        int m01 = (lane - 15) * rowsum;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -887,8 +938,7 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
         float sa, ca;
         glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
         const float a = ca, b = sa;
-        __syncwarp();
-        const uint8_t *center = patch[warp] + 18 * DS_PP + shiftb + 18;
+        const uint8_t *center = patchB[warp] + 18 * DS_PP + shB + 18;
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -902,7 +952,7 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
             }
             val |= (t[0] < t[1]) << k;
         }
-        __syncwarp();     // the patch is reused by this warp's next slot
+        __syncwarp();     // the patches are reused by this warp's next slot
         const int o = before + i;
         desc[((size_t)frame * L.kpStride + o) * 32 + lane] = (uint8_t)val;
         if (lane == 0) {
