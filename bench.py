@@ -246,7 +246,9 @@ def main():
 
     # ---- e2e through the host entry point (pinned host frames in, keypoints + descriptors out)
     cap = ex.max_keypoints
-    out = (np.zeros((BATCH, cap), orbx.KP_DTYPE), np.zeros((BATCH, cap, 32), np.uint8), np.zeros(BATCH, np.int32))
+    # pinned result arrays with the library's stride: keypoints and descriptors are DMA'd straight into them
+    out = (torch.zeros(BATCH * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap),
+           torch.zeros((BATCH, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(BATCH, np.int32))
     host_np = [[hb[f].numpy() for f in range(BATCH)] for hb in host_pool]
 
     def step_e2e(i):

@@ -71,7 +71,9 @@ struct orbx_extractor {
     // device state
     cudaStream_t stream = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    cudaStream_t stream2 = nullptr;
+    cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
+    std::vector<cudaEvent_t> evChunk;
+    DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
     struct { uint8_t *p = nullptr; } dPyr, dBlur;    // slab bases inside the padded allocations
     DevBuf<uint32_t> dCnt;
@@ -313,29 +315,34 @@ int setGeometry(orbx_extractor *h, int w, int hh)
 }
 
 // enqueue every stage after level 0 is in place
-int enqueuePipeline(orbx_extractor *h, int batch, cudaStream_t st)
+int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
 {
     const OrbxLayout &L = h->L;
-    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
+    uint8_t *pyr = h->dPyr.p + (size_t)f0 * L.slab, *blur = h->dBlur.p + (size_t)f0 * L.slab;
+    uint32_t *cnt = h->dCnt.p + (size_t)f0 * L.rowsPerFrame;
+    unsigned long long *best = h->dBest.p + (size_t)f0 * L.rowsPerFrame;
+    int2 *slots = h->dSlots.p + (size_t)f0 * L.slotsPerFrame;
+    int *lvlCount = h->dLvlCount.p + (size_t)f0 * L.nlevels;
+    for (int l = 1; l < L.nlevels; l++) launch_resize(pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
     // blur only depends on the pyramid: run it on the side stream, beside FAST + octree
     CK(cudaEventRecord(h->evFork, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    launch_blur(h->dPyr.p, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, h->stream2);
+    launch_blur(pyr, blur, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, h->stream2);
     CK(cudaEventRecord(h->evJoin, h->stream2));
 
-    CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(best, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
     OrbxDbgCand *dbg = nullptr; int *dbgCount = nullptr;
     if (h->dbgEnabled) {
-        dbg = h->dDbg.p; dbgCount = h->dDbgCount.p;
+        dbg = h->dDbg.p + (size_t)f0 * L.nlevels * h->dbgCap; dbgCount = h->dDbgCount.p + (size_t)f0 * L.nlevels;
         CK(cudaMemsetAsync(dbgCount, 0, (size_t)L.nlevels * batch * sizeof(int), st));
     }
-    launch_fast(h->dPyr.p, L, h->dCells.p, h->dCnt.p, h->dBest.p, dbg, dbgCount, h->dbgCap, batch, st);
-    CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
+    launch_fast(pyr, L, h->dCells.p, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
+    CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
     CK(cudaStreamWaitEvent(st, h->evJoin, 0));
-    launch_describe(h->dPyr.p, h->dBlur.p, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
+    launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
+                    h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
     CK(cudaGetLastError());
-    h->lastBatch = batch;
     return ORBX_OK;
 }
 
@@ -388,6 +395,8 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     if (prop.major != 10) return fail(h, ORBX_ERR_CUDA, "liborbx is built for sm_100a only (no other code path exists)");
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
     // size the arenas for the declared maximum so the hot path never allocates
@@ -406,6 +415,10 @@ void orbx_destroy(orbx_extractor *h)
     if (!h) return;
     if (h->stream) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->stream); }
     if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->streamIn) cudaStreamSynchronize(h->streamIn);
+    if (h->streamOut) cudaStreamSynchronize(h->streamOut);
+    for (cudaEvent_t e : h->evChunk) if (e) cudaEventDestroy(e);
+    h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
     h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dDbg.release();
@@ -414,6 +427,8 @@ void orbx_destroy(orbx_extractor *h)
     if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->streamIn) cudaStreamDestroy(h->streamIn);
+    if (h->streamOut) cudaStreamDestroy(h->streamOut);
     delete h;
 }
 
@@ -447,7 +462,8 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     if (rc != ORBX_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
-    return enqueuePipeline(h, batch, st);
+    h->lastBatch = batch;
+    return enqueuePipeline(h, 0, batch, st);
 }
 
 int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
@@ -461,6 +477,9 @@ int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const ui
     return ORBX_OK;
 }
 
+// Host entry point.  The batch is cut into chunks that flow through three streams -- H2D of chunk
+// c+1, kernels of chunk c and D2H of chunk c-1 overlap -- and the host copies finished chunks into
+// the caller's arrays while later chunks are still on the GPU.
 int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
                        size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
 {
@@ -475,43 +494,86 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     rc = ensureArenas(h, batch);
     if (rc != ORBX_OK) return rc;
     const OrbxLayout &L = h->L;
-    const OrbxLevel &l0 = L.lv[0];
-    cudaStream_t st = h->stream;
-    // H2D straight into the level-0 slot of each frame's slab (level 0 of ComputePyramid is a copy)
-    const bool pinned = isPinned(imgs[0]) && isPinned(imgs[batch - 1]);
-    if (!pinned) CK(h->hIn.ensure((size_t)width * height * batch));
-    for (int f = 0; f < batch; f++) {
-        const uint8_t *src = imgs[f];
-        size_t sp = pitch;
-        if (!pinned) {
-            uint8_t *stage = h->hIn.p + (size_t)f * width * height;
-            for (int y = 0; y < height; y++) memcpy(stage + (size_t)y * width, imgs[f] + (size_t)y * pitch, width);
-            src = stage; sp = width;
-        }
-        CK(cudaMemcpy2DAsync(h->dPyr.p + (size_t)f * L.slab + l0.off, l0.pitch, src, sp, width, height,
-                             cudaMemcpyHostToDevice, st));
-    }
-    rc = enqueuePipeline(h, batch, st);
-    if (rc != ORBX_OK) return rc;
+    const size_t frameBytes = (size_t)width * height;
+    CK(h->dIn.ensure(frameBytes * batch + 64));
     CK(h->hKps.ensure((size_t)L.kpStride * batch));
     CK(h->hDesc.ensure((size_t)L.kpStride * batch * 32));
     CK(h->hCounts.ensure((size_t)batch));
-    CK(cudaMemcpyAsync(h->hCounts.p, h->dCounts.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->hKps.p, h->dKps.p, sizeof(orbx_keypoint_pod) * (size_t)L.kpStride * batch, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->hDesc.p, h->dDesc.p, (size_t)L.kpStride * batch * 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int f = 0; f < batch; f++) {
-        const int n = h->hCounts.p[f];
-        if (n > kp_cap) {
-            char msg[128];
-            snprintf(msg, sizeof msg, "frame %d produced %d keypoints, kp_cap is %d", f, n, kp_cap);
-            return fail(h, ORBX_ERR_CAPACITY, msg);
-        }
-        memcpy(kps + (size_t)f * kp_cap, h->hKps.p + (size_t)f * L.kpStride, sizeof(orbx_keypoint) * n);
-        memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
-        n_out[f] = n;
+    const bool pinnedIn = isPinned(imgs[0]) && isPinned(imgs[batch - 1]);
+    if (!pinnedIn) CK(h->hIn.ensure(frameBytes * batch));
+    // results can be DMA'd straight into the caller's arrays when those are pinned and use our stride
+    const bool directOut = kp_cap == L.kpStride && isPinned(kps) && isPinned(desc);
+    orbx_keypoint_pod *hk = directOut ? (orbx_keypoint_pod *)kps : h->hKps.p;
+    uint8_t *hd = directOut ? desc : h->hDesc.p;
+
+    const int nChunks = batch >= 32 ? 4 : (batch >= 8 ? 2 : 1);
+    if ((int)h->evChunk.size() < 2 * nChunks) {
+        const size_t old = h->evChunk.size();
+        h->evChunk.resize(2 * nChunks, nullptr);
+        for (size_t i = old; i < h->evChunk.size(); i++) CK(cudaEventCreateWithFlags(&h->evChunk[i], cudaEventDisableTiming));
     }
-    return ORBX_OK;
+    cudaStream_t sIn = h->streamIn, sK = h->stream, sOut = h->streamOut;
+    for (int c = 0; c < nChunks; c++) {
+        const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
+        const int nf = f1 - f0;
+        if (nf <= 0) continue;
+        // ---- H2D into the tight staging buffer: one copy per run of frames that are contiguous on the host
+        for (int f = f0; f < f1;) {
+            int g = f + 1;
+            if (pitch == (size_t)width && pinnedIn)
+                while (g < f1 && imgs[g] == imgs[g - 1] + frameBytes) g++;
+            uint8_t *dst = h->dIn.p + (size_t)f * frameBytes;
+            if (pinnedIn && pitch == (size_t)width) {
+                CK(cudaMemcpyAsync(dst, imgs[f], frameBytes * (g - f), cudaMemcpyHostToDevice, sIn));
+            } else if (pinnedIn) {
+                CK(cudaMemcpy2DAsync(dst, width, imgs[f], pitch, width, height, cudaMemcpyHostToDevice, sIn));
+            } else {
+                uint8_t *stage = h->hIn.p + (size_t)f * frameBytes;
+                for (int y = 0; y < height; y++) memcpy(stage + (size_t)y * width, imgs[f] + (size_t)y * pitch, width);
+                CK(cudaMemcpyAsync(dst, stage, frameBytes, cudaMemcpyHostToDevice, sIn));
+            }
+            f = g;
+        }
+        CK(cudaEventRecord(h->evChunk[2 * c], sIn));
+        // ---- kernels of this chunk
+        CK(cudaStreamWaitEvent(sK, h->evChunk[2 * c], 0));
+        launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, sK);
+        rc = enqueuePipeline(h, f0, nf, sK);
+        if (rc != ORBX_OK) return rc;
+        CK(cudaEventRecord(h->evChunk[2 * c + 1], sK));
+        // ---- D2H of this chunk's results
+        CK(cudaStreamWaitEvent(sOut, h->evChunk[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(h->hCounts.p + f0, h->dCounts.p + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, sOut));
+        CK(cudaMemcpyAsync(hk + (size_t)f0 * L.kpStride, h->dKps.p + (size_t)f0 * L.kpStride,
+                           sizeof(orbx_keypoint_pod) * (size_t)L.kpStride * nf, cudaMemcpyDeviceToHost, sOut));
+        CK(cudaMemcpyAsync(hd + (size_t)f0 * L.kpStride * 32, h->dDesc.p + (size_t)f0 * L.kpStride * 32,
+                           (size_t)L.kpStride * nf * 32, cudaMemcpyDeviceToHost, sOut));
+        CK(cudaEventRecord(h->evChunk[2 * c], sOut));   // reuse: the H2D event of this chunk has been consumed
+    }
+    h->lastBatch = batch;
+    int status = ORBX_OK;
+    for (int c = 0; c < nChunks; c++) {
+        const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
+        if (f1 <= f0) continue;
+        CK(cudaEventSynchronize(h->evChunk[2 * c]));
+        for (int f = f0; f < f1; f++) {
+            const int n = h->hCounts.p[f];
+            if (n > kp_cap) {
+                char msg[128];
+                snprintf(msg, sizeof msg, "frame %d produced %d keypoints, kp_cap is %d", f, n, kp_cap);
+                status = fail(h, ORBX_ERR_CAPACITY, msg);
+                continue;
+            }
+            if (!directOut) {
+                memcpy(kps + (size_t)f * kp_cap, h->hKps.p + (size_t)f * L.kpStride, sizeof(orbx_keypoint) * n);
+                memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
+            }
+            n_out[f] = n;
+        }
+    }
+    CK(cudaStreamSynchronize(sOut));
+    CK(cudaStreamSynchronize(sK));
+    return status;
 }
 
 int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, size_t pitch,
