@@ -195,6 +195,7 @@ def main():
     import torch
     import torch.distributed as dist
     import orbx
+    import shard
     import synth
 
     if not torch.cuda.is_available():
@@ -271,9 +272,10 @@ def main():
     # ---- matching: query-sharded kNN-2, one all_gather of the result records
     q, t = synth.matching_set(NQ, NT)
     m = orbx.Matcher(max_queries=NQ, max_train=NT, device=local_rank)
-    nq_loc = (NQ + world - 1) // world
+    nq_loc = shard.query_block(NQ, world)
     q_loc = np.zeros((nq_loc, 32), np.uint8)
-    part = q[rank * nq_loc:(rank + 1) * nq_loc]
+    qlo, qhi = shard.query_range(NQ, rank, world)
+    part = q[qlo:qhi]
     q_loc[:len(part)] = part
     dq = torch.from_numpy(q_loc).to(dev)
     dt_ = torch.from_numpy(t).to(dev)
@@ -284,7 +286,7 @@ def main():
         m.knn2_device(dq.data_ptr(), nq_loc, dt_.data_ptr(), NT, d_loc.data_ptr(), stream.cuda_stream)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(d_all, d_loc)
+                shard.gather_match_records(d_loc, NQ, out=d_all)
 
     for _ in range(max(args.warmup, 3)):
         step_match()
