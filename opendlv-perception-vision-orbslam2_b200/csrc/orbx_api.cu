@@ -73,6 +73,9 @@ struct orbx_extractor {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
     std::vector<cudaEvent_t> evChunk;
+    OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
+    DevBuf<OrbxTensorMaps> dTmaps;   // ... and where the kernels read them
+    const uint8_t *tmapBase = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
     DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
     struct { uint8_t *p = nullptr; } dPyr, dBlur;    // slab bases inside the padded allocations
@@ -265,6 +268,8 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
     return ORBX_OK;
 }
 
+int buildTensorMaps(orbx_extractor *h, int frames);
+
 int ensureArenas(orbx_extractor *h, int batch)
 {
     const OrbxLayout &L = h->L;
@@ -286,6 +291,46 @@ int ensureArenas(orbx_extractor *h, int batch)
         CK(h->dDbg.ensure((size_t)h->dbgCap * L.nlevels * batch));
         CK(h->dDbgCount.ensure((size_t)L.nlevels * batch));
     }
+    return buildTensorMaps(h, (int)((h->dPyrRaw.n - 512) / (size_t)L.slab));
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int buildTensorMaps(orbx_extractor *h, int frames)
+{
+    const OrbxLayout &L = h->L;
+    if (h->tmapBase == h->dPyr.p && h->tmapFrames >= frames && h->tmapW == h->curW && h->tmapH == h->curH) return ORBX_OK;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, ORBX_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = (EncodeTiledFn)fn;
+    }
+    for (int l = 0; l < L.nlevels; l++) {
+        const OrbxLevel &v = L.lv[l];
+        cuuint64_t gdim[3] = {(cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)frames};
+        cuuint64_t gstr[2] = {(cuuint64_t)v.pitch, (cuuint64_t)L.slab};
+        cuuint32_t box[3] = {160, 134, 1};   // BL_BOXW x BL_BOXH of k_blur
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            return fail(h, ORBX_ERR_CUDA, msg);
+        }
+    }
+    CK(h->dTmaps.ensure(1));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->stream2));
+    CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    h->tmapBase = h->dPyr.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
     return ORBX_OK;
 }
 
@@ -327,7 +372,7 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     // blur only depends on the pyramid: run it on the side stream, beside FAST + octree
     CK(cudaEventRecord(h->evFork, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    launch_blur(pyr, blur, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, h->stream2);
+    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
     CK(cudaEventRecord(h->evJoin, h->stream2));
 
     CK(cudaMemsetAsync(cnt, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
@@ -421,7 +466,7 @@ void orbx_destroy(orbx_extractor *h)
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
-    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dDbg.release();
+    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
@@ -641,7 +686,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
         CK(cudaEventRecord(ev[2], st));
         CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
         CK(cudaEventRecord(ev[3], st));
-        launch_blur(h->dPyr.p, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, batch, st);
+        launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, 0, batch, st);
         CK(cudaEventRecord(ev[4], st));
         launch_describe(h->dPyr.p, h->dBlur.p, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
         CK(cudaEventRecord(ev[5], st));

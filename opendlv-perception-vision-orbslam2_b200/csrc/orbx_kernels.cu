@@ -12,6 +12,7 @@
 #include "orbx_internal.h"
 #include "orbx_kernels.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 // rBRIEF sampling pattern, 512 (x,y) points (data; same table as orbextractor.cpp:215-473)
@@ -221,18 +222,55 @@ __device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint3
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
-       const OrbxTile *__restrict__ tiles, BlurTaps taps)
+// ------------------------------------------------------------------------------------------
+// TMA staging (cp.async.bulk.tensor): one elected thread of the CTA fetches the whole tile --
+// 128 columns + 2 x 16 bytes of halo, 128 rows + 6 rows of halo -- from the level's 3-D tensor map
+// (x, y, frame) into shared memory; the hardware zero-fills what lies outside the image, and the
+// REFLECT_101 rows/columns are resolved when the tile is READ (reflected rows are inside the box:
+// the tile keeps 3 halo rows on both sides).  Completion is signalled on an mbarrier.
+// ------------------------------------------------------------------------------------------
+#define BL_BOXW 160   // bytes: 16 left + 128 + 16 right: TMA needs the box start 16-byte aligned in the inner dimension
+#define BL_BOXH 134   // rows: 3 + 128 + 3
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar, uint32_t bytes)
 {
+    const uint32_t b = smem_u32(bar), d = smem_u32(smemDst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(b), "r"(phase) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
+       const OrbxTile *__restrict__ tiles, BlurTaps taps, int f0)
+{
+    __shared__ __align__(128) uint8_t tileS[BL_BOXH * BL_BOXW];
+    __shared__ __align__(8) uint64_t bar;
     const OrbxTile tile = tiles[blockIdx.x];
     const OrbxLevel &lv = L.lv[tile.level];
-    const int f = blockIdx.y;
+    const int f = f0 + blockIdx.y;
     const int w = lv.w, h = lv.h, pitch = lv.pitch;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        tma_load_tile_3d(tileS, maps + tile.level, (int)tile.x0 * 4 - 16, (int)tile.y0 - 3, f, &bar, BL_BOXH * BL_BOXW);
+
     const int x0 = (tile.x0 + threadIdx.x) * 4;
     const int y0 = tile.y0 + threadIdx.y * BL_ROWS;
-    if (x0 >= w || y0 >= h) return;
-    const uint8_t *src = pyr + (size_t)f * L.slab + lv.off + x0;
+    const bool active = x0 < w && y0 < h;
     uint8_t *dst = blur + (size_t)f * L.slab + lv.off + x0;
     const uint32_t Tlo = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8 | (uint32_t)taps.t[2] << 16 | (uint32_t)taps.t[3] << 24;
     const uint32_t Thi = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8 | (uint32_t)taps.t[6] << 16;
@@ -248,24 +286,22 @@ k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid
     for (int c = 0; c < 4; c++)
 #pragma unroll
         for (int k = 0; k < 7; k++) pp[c][k] = 0;
-    // software pipeline: the three words of row r+1 are in flight while row r is being reduced.
-    // p[-1] is always addressable: the slab arena has a front pad (for x0 == 0 the value is replaced).
-    int gy = y0 - 3; gy = gy < 0 ? -gy : gy;
-    const uint32_t *p = (const uint32_t *)(src + (size_t)gy * pitch);
-    uint32_t n0 = __ldg(p - 1), n1 = __ldg(p), n2 = __ldg(p + 1);
+    mbar_wait(&bar, 0);
+    if (!active) return;
+    // shared row of image row g is (g - tile.y0 + 3); the row starts 16 bytes left of the tile, so this
+    // thread's three words (bytes x0-4 .. x0+7) are words lane+3, lane+4, lane+5
+    const uint32_t *ts = (const uint32_t *)tileS + threadIdx.x + 3;
+    const int rowBias = 3 - (int)tile.y0;
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 7) {
 #pragma unroll
         for (int s = 0; s < 7; s++) {
             const int r = r0 + s;
             if (r < rows) {
-                uint32_t W0 = n0, W1 = n1, W2 = n2;
-                if (r + 1 < rows) {
-                    int g = y0 + r - 2;                              // REFLECT_101 of the next row (|overshoot| <= 3 < h)
-                    g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
-                    p = (const uint32_t *)(src + (size_t)g * pitch);
-                    n0 = __ldg(p - 1); n1 = __ldg(p); n2 = __ldg(p + 1);
-                }
+                int g = y0 + r - 3;                                  // REFLECT_101 (|overshoot| <= 3 < h)
+                g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
+                const uint32_t *p = ts + (g + rowBias) * (BL_BOXW / 4);
+                uint32_t W0 = p[0], W1 = p[1], W2 = p[2];
                 if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);      // left edge: index -k equals index k
                 const uint32_t T = __byte_perm(W0, W1, selT);
                 W2 = __byte_perm(T, W2, sel2);
@@ -297,13 +333,13 @@ k_blur(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const __grid
     }
 }
 
-void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
-                 const int taps[7], int batch, cudaStream_t st)
+void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
+                 const int taps[7], int f0, int batch, cudaStream_t st)
 {
     BlurTaps t;
     for (int k = 0; k < 7; k++) t.t[k] = taps[k];
     dim3 grid(nTiles, batch);
-    k_blur<<<grid, dim3(32, 4), 0, st>>>(pyr, blur, L, tiles, t);
+    k_blur<<<grid, dim3(32, 4), 0, st>>>(maps, blur, L, tiles, t, f0);
 }
 
 // ------------------------------------------------------------------------------------------

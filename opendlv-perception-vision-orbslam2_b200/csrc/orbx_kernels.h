@@ -1,15 +1,19 @@
 // orbx_kernels.h -- launchers of the extractor kernels (internal).
 #pragma once
 #include "orbx_internal.h"
+#include <cuda.h>
 #include <cuda_runtime.h>
+
+// one 3-D (x, y, frame) tensor map per pyramid level; the array lives in global memory
+struct OrbxTensorMaps { CUtensorMap m[ORBX_MAXL]; };
 
 struct orbx_keypoint_pod { float x, y, size, angle, response; int32_t octave, class_id; };
 
 void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch, uint8_t *pyr,
                         const OrbxLayout &L, int batch, cudaStream_t st);
 void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st);
-void launch_blur(const uint8_t *pyr, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
-                 const int taps[7], int batch, cudaStream_t st);
+void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
+                 const int taps[7], int f0, int batch, cudaStream_t st);
 void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, uint32_t *cnt,
                  unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st);
 size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes);
