@@ -414,22 +414,25 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     const int tid = threadIdx.x;
     const int th = L.minTh;
 
-    // ---- stage 0: window column c lives at shared byte (c + 1): tested pixel xIn at byte xIn + 4
+    // ---- stage 0: window column c lives at shared byte (c + 1): tested pixel xIn at byte xIn + 4.
+    // One item = 16 destination bytes of one row: five aligned source words, four funnel shifts.
     {
         const uint8_t *base = pyr + (size_t)frame * L.slab + lv.off + (size_t)cell.y0 * lv.pitch + (int)cell.x0 - 1;
-        const int nw = ((int)cell.w + 1 + 3) >> 2;           // words per row, <= 17
-        const unsigned M = 65536u / nw + 1;
-        for (int i = tid; i < (int)cell.h * nw; i += 128) {
-            const int r = (i * M) >> 16, k = i - r * nw;
-            const uintptr_t a = (uintptr_t)(base + (size_t)r * lv.pitch + 4 * k);
-            const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);
-            ((uint32_t *)win)[r * (FW_P / 4) + k] = __funnelshift_r(__ldg(p), __ldg(p + 1), (int)(a & 3) * 8);
+        const int ng = ((int)cell.w + 1 + 15) >> 4;          // 16-byte groups per row, <= 5
+        const unsigned M = 65536u / ng + 1;
+        const int sh = (int)((uintptr_t)base & 3) * 8;       // pitch is a multiple of 4: the same shift for every row
+        const uint32_t *base4 = (const uint32_t *)((uintptr_t)base & ~(uintptr_t)3);
+        const int pitch4 = lv.pitch >> 2;
+        for (int i = tid; i < (int)cell.h * ng; i += 128) {
+            const int r = (i * M) >> 16, g = i - r * ng;
+            const uint32_t *p = base4 + (size_t)r * pitch4 + 4 * g;
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+            uint4 o;
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+            ((uint4 *)win)[r * (FW_P / 16) + g] = o;
         }
-        const int zw = (wEff + 2 + 3) >> 2;                   // score map: (hEff+2) rows x (wEff+2) bytes, zero frame included
-        for (int i = tid; i < (hEff + 2) * 16; i += 128) {
-            const int r = i >> 4, k = i & 15;
-            if (k < zw) ((uint32_t *)smap)[r * (FS_P / 4) + k] = 0;
-        }
+        for (int i = tid; i < (hEff + 2) * (FS_P / 16); i += 128) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { ncand = 0; ncorner = 0; }
     }
     __syncthreads();
@@ -578,7 +581,8 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
     const int H = lv.H, nR = lv.nIni * H, N = lv.quota;
 
     unsigned long long *keys = (unsigned long long *)sm_raw;         // pow2Nodes
-    int *P = (int *)(keys + pow2Nodes);                              // maxRows + 1
+    unsigned long long *bestS = keys + pow2Nodes;                    // maxRows: best candidate of every (strip,row)
+    int *P = (int *)(bestS + maxRows);                               // maxRows + 1
     uint32_t *cur = (uint32_t *)(P + maxRows + 1);                   // maxNodes
     uint32_t *nxt = cur + maxNodes;
     int *a = (int *)(nxt + maxNodes), *b = a + maxNodes, *c = b + maxNodes, *d = c + maxNodes;
@@ -586,7 +590,7 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
     const uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     const unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
 
-    for (int i = tid; i < nR; i += OCT_T) P[i] = (int)cntF[i];
+    for (int i = tid; i < nR; i += OCT_T) { P[i] = (int)cntF[i]; bestS[i] = bestF[i]; }
     __syncthreads();
     const int totalCand = block_excl_scan(P, nR, sh.scan);
     if (tid == 0) {
@@ -605,7 +609,7 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
     bool finish = (n == 0);
     while (!finish) {
         const int prevSize = n;
-        // ---------------- main pass
+        // ---------------- main pass (one packed scan: children in the low half, untouched nodes in the high half)
         int myrec = 0;
         if (tid == 0) sh.rec = 0;
         for (int i = tid; i < n; i += OCT_T) {
@@ -615,14 +619,14 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
             if (sz > 1) {
                 const int mid = y0_ + ((y1_ - y0_) >> 1);      // :75 integer halfY
                 const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                a[i] = (c2 > 0) + (c4 > 0); b[i] = 0;
+                a[i] = (c2 > 0) + (c4 > 0);
                 myrec += (c2 > 1) + (c4 > 1);
-            } else { a[i] = 0; b[i] = 1; }
+            } else a[i] = 1 << 16;
         }
         __syncthreads();
         if (myrec) atomicAdd(&sh.rec, myrec);
-        const int totC = block_excl_scan(a, n, sh.scan);
-        const int totN = block_excl_scan(b, n, sh.scan);
+        const int tot = block_excl_scan(a, n, sh.scan);
+        const int totC = tot & 0xffff, totN = tot >> 16;
         for (int i = tid; i < n; i += OCT_T) {
             const uint32_t node = cur[i];
             NODE_DECODE(node);
@@ -630,11 +634,11 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
             if (sz > 1) {
                 const int mid = y0_ + ((y1_ - y0_) >> 1);
                 const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                int pos = totC - (a[i] + (c2 > 0) + (c4 > 0));
+                int pos = totC - ((a[i] & 0xffff) + (c2 > 0) + (c4 > 0));
                 if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
                 if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
             } else {
-                nxt[totC + b[i]] = node;
+                nxt[totC + (a[i] >> 16)] = node;
             }
         }
         __syncthreads();
@@ -747,7 +751,7 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
         NODE_DECODE(node);
         unsigned long long k = 0;
         for (int y = y0_ + lane; y < y1_; y += 32) {
-            const unsigned long long v = bestF[pb_ + y];
+            const unsigned long long v = bestS[pb_ + y];
             k = v > k ? v : k;
         }
 #pragma unroll
@@ -767,7 +771,7 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
 
 size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes)
 {
-    return (size_t)pow2Nodes * 8 + (size_t)(maxRows + 1) * 4 + (size_t)maxNodes * 4 * 6 + 16;
+    return (size_t)pow2Nodes * 8 + (size_t)maxRows * 8 + (size_t)(maxRows + 1) * 4 + (size_t)maxNodes * 4 * 6 + 16;
 }
 
 cudaError_t launch_octree(const OrbxLayout &L, uint32_t *cnt, const unsigned long long *best, int2 *slots,
