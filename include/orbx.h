@@ -99,6 +99,10 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
 int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
                         const int **d_counts, int *kp_stride);
 
+/* Copy the results of the last orbx_extract_batch_device call to host arrays (layout as in
+ * orbx_extract_batch).  Waits for `stream` (the stream that call was given; NULL = the handle's). */
+int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
+
 /* upper bound of keypoints per frame for this configuration */
 int orbx_max_keypoints(const orbx_extractor *h);
 
@@ -152,8 +156,23 @@ int orbm_knn2_resident(orbm_matcher *m, const uint8_t *q, int nq, int32_t *idx, 
  * buffer of the result gather when queries are sharded over GPUs). */
 int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
                      int32_t *d_out, void *stream);
+/* Candidate-list matching: the inner loop of SearchByProjection / SearchByBoW / SearchForTriangulation
+ * (orbmatcher.cpp:76-114, :208-232, :1337-1483).  Query i is compared with the train rows
+ * indices[offsets[i] .. offsets[i+1]) in that order (CSR); the sequential exclusion rules of the callers
+ * stay on the host, which builds the lists.  Per query: idx1/d1 = best, idx2/d2 = second best under the
+ * reference's strict '<' updates (earlier list position wins ties); -1 / 256 where absent.  idx2 lets the
+ * caller look up the octave the reference tracks as bestLevel2 (orbmatcher.cpp:105-113). */
+int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *offsets,
+                  const int32_t *indices, int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2);
+/* device-resident variant; d_out = nq x {idx1, d1, d2, idx2} int32 records; enqueued on `stream`, not synchronised */
+int orbm_knn2_csr_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, const int32_t *d_offsets,
+                         const int32_t *d_indices, int32_t *d_out, void *stream);
 /* DescriptorDistance for n independent pairs a[i], b[i] (32 bytes each) -> out[i] */
 int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *out);
+
+/* Measured POPC issue rate of this GPU in lane-operations per clock per SM (denominator of the matcher's
+ * INT-pipe roofline: pairs/s = SMs x clock x rate / 8). */
+int orbm_measure_popc(orbm_matcher *m, double *popc_per_clk_per_sm);
 
 /* library build info: "orbx <version> sm_100a" */
 const char *orbx_version(void);

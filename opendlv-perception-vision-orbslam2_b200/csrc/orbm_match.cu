@@ -5,7 +5,7 @@
 // (orbmatcher.cpp:208-232: strict '<', start values 256 / -1; lowest index wins ties and the
 // second best counts duplicates of the best).
 //
-// Kernel shape: INT pipe only (LOP3 + POPC + IADD3 + IMNMX) -- this is not a dense float
+// Kernel shape: INT pipe only (LOP3 carry-save adders + POPC + IADD3 + IMNMX) -- this is not a dense float
 // contraction, tensor cores do not apply.  One query per thread held in 8 registers; the train
 // set is streamed through shared memory in tiles that every thread of the CTA reads as 128-bit
 // broadcasts; the grid is (query blocks) x (train chunks) so that 2000 queries still fill 148 SMs.
@@ -28,6 +28,24 @@
 #define KNN_IDX_MASK 0x3fffffu
 #define KNN_INIT_KEY ((256u << KNN_IDX_BITS) | KNN_IDX_MASK)
 
+// 256-bit Hamming distance.  POPC issues at a fraction of the LOP3 rate, so the eight XOR words are
+// first compressed with carry-save adders (Harley-Seal): three words of equal weight become a sum word
+// and a carry word of double weight (2 LOP3), leaving 4 POPC instead of 8.  The result is identical to
+// the sum of the eight popcounts the reference computes (orbmatcher.cpp:1662-1677).
+__device__ __forceinline__ unsigned csa_sum(unsigned a, unsigned b, unsigned c) { return a ^ b ^ c; }
+__device__ __forceinline__ unsigned csa_carry(unsigned a, unsigned b, unsigned c) { return (a & b) | (c & (a | b)); }
+
+__device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+{
+    const unsigned x0 = qa.x ^ a.x, x1 = qa.y ^ a.y, x2 = qa.z ^ a.z, x3 = qa.w ^ a.w;
+    const unsigned x4 = qb.x ^ b.x, x5 = qb.y ^ b.y, x6 = qb.z ^ b.z, x7 = qb.w ^ b.w;
+    const unsigned s0 = csa_sum(x0, x1, x2), c0 = csa_carry(x0, x1, x2);
+    const unsigned s1 = csa_sum(x3, x4, x5), c1 = csa_carry(x3, x4, x5);
+    const unsigned s2 = csa_sum(s0, s1, x6), c2 = csa_carry(s0, s1, x6);
+    const unsigned s3 = csa_sum(c0, c1, c2), c3 = csa_carry(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
+}
+
 __global__ void __launch_bounds__(KNN_QB)
 k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
                uint2 *__restrict__ part)
@@ -48,8 +66,7 @@ k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
 #pragma unroll 4
         for (int j = 0; j < cnt; j++) {
             const uint4 a = tile[2 * j], b = tile[2 * j + 1];
-            const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
-                          __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+            const int d = hamming256(qa, qb, a, b);
             const unsigned key = ((unsigned)d << KNN_IDX_BITS) | (unsigned)(base + j);
             k2 = min(k2, max(k1, key));
             k1 = min(k1, key);
@@ -83,8 +100,70 @@ __global__ void k_distance_pairs(const uint4 *__restrict__ a, const uint4 *__res
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4 a0 = a[2 * i], a1 = a[2 * i + 1], b0 = b[2 * i], b1 = b[2 * i + 1];
-    out[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-             __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    out[i] = hamming256(a0, a1, b0, b1);
+}
+
+// Candidate-list matching (inner loop of SearchByProjection / SearchByBoW, orbmatcher.cpp:76-114):
+// one warp per query, lanes stride over the query's CSR list.  Keys are (distance << 22 | position in
+// the list): the reference's strict '<' updates keep the two smallest under exactly that order.
+__global__ void __launch_bounds__(128)
+k_knn2_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, const int *__restrict__ offsets,
+           const int *__restrict__ indices, int4 *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (qi >= nq) return;
+    const uint4 qa = __ldg(&q[2 * qi]), qb = __ldg(&q[2 * qi + 1]);
+    const int beg = offsets[qi], end = offsets[qi + 1];
+    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+    for (int p = beg + lane; p < end; p += 32) {
+        const int ti = __ldg(&indices[p]);
+        const uint4 a = __ldg(&t[2 * (size_t)ti]), b = __ldg(&t[2 * (size_t)ti + 1]);
+        const int d = hamming256(qa, qb, a, b);
+        const unsigned key = ((unsigned)d << KNN_IDX_BITS) | (unsigned)(p - beg);
+        k2 = min(k2, max(k1, key));
+        k1 = min(k1, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // merge two sorted pairs: the two smallest of four keys
+        const unsigned o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        k2 = min(min(k2, o2), max(k1, o1));
+        k1 = min(k1, o1);
+    }
+    if (lane == 0) {
+        int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
+        int i1 = d1 < 256 ? indices[beg + (int)(k1 & KNN_IDX_MASK)] : -1;
+        int i2 = d2 < 256 ? indices[beg + (int)(k2 & KNN_IDX_MASK)] : -1;
+        if (d1 >= 256) d1 = 256;
+        if (d2 >= 256) d2 = 256;
+        out[qi] = make_int4(i1, d1, d2, i2);
+    }
+}
+
+// POPC issue-rate probe for the INT roofline of the matcher (SURVEY 8d asks for a measured R_popc):
+// every thread runs 8 independent POPC->XOR chains; a CTA reports its own cycle count.
+__global__ void __launch_bounds__(256)
+k_popc_probe(unsigned seed, int iters, unsigned *sink, long long *cycles)
+{
+    unsigned a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = seed * (threadIdx.x + 1) + k * 0x9e3779b9u;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            unsigned p;
+            asm volatile("popc.b32 %0, %1;" : "=r"(p) : "r"(a[k]));
+            a[k] = p * 0x9e3779b1u + (unsigned)i;      // IMAD: the mixing runs on the FMA pipe, not beside POPC
+        }
+    }
+    const long long t1 = clock64();
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0xdeadbeefu) sink[0] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
 struct orbm_matcher {
@@ -92,6 +171,7 @@ struct orbm_matcher {
     cudaStream_t stream = nullptr;
     uint8_t *dQ = nullptr, *dT = nullptr;
     uint2 *dPart = nullptr; size_t partCap = 0;
+    int *dCsr = nullptr; size_t csrCap = 0;
     int4 *dOut = nullptr;
     int4 *hOut = nullptr;
     int residentNt = -1;
@@ -177,6 +257,7 @@ void orbm_destroy(orbm_matcher *m)
     if (m->dQ) cudaFree(m->dQ);
     if (m->dT) cudaFree(m->dT);
     if (m->dPart) cudaFree(m->dPart);
+    if (m->dCsr) cudaFree(m->dCsr);
     if (m->dOut) cudaFree(m->dOut);
     if (m->hOut) cudaFreeHost(m->hOut);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -226,6 +307,75 @@ int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t 
     if (!d_q || !d_out || (!d_t && nt > 0) || nq < 1 || nt < 0 || nt > (int)KNN_IDX_MASK - 1) return mfail(m, ORBX_ERR_ARG, "bad argument");
     MCK(cudaSetDevice(m->device));
     return enqueueKnn(m, d_q, nq, d_t, nt, (int4 *)d_out, stream ? (cudaStream_t)stream : m->stream);
+}
+
+int orbm_knn2_csr_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, const int32_t *d_offsets,
+                         const int32_t *d_indices, int32_t *d_out, void *stream)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!d_q || !d_t || !d_offsets || !d_indices || !d_out || nq < 1) return mfail(m, ORBX_ERR_ARG, "bad argument");
+    if (((uintptr_t)d_q | (uintptr_t)d_t | (uintptr_t)d_out) & 15) return mfail(m, ORBX_ERR_ARG, "device buffers must be 16-byte aligned");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    k_knn2_csr<<<(nq * 32 + 127) / 128, 128, 0, st>>>((const uint4 *)d_q, nq, (const uint4 *)d_t, d_offsets, d_indices, (int4 *)d_out);
+    MCK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *offsets,
+                  const int32_t *indices, int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!q || !offsets || !indices || !idx1 || !d1 || !idx2 || !d2 || nq < 1 || nq > m->maxQ || nt < 0 || nt > m->maxT || (!t && nt > 0))
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    const int nnz = offsets[nq];
+    if (offsets[0] != 0 || nnz < 0) return mfail(m, ORBX_ERR_ARG, "offsets must start at 0 and be non-decreasing");
+    for (int i = 0; i < nq; i++) {
+        if (offsets[i + 1] < offsets[i]) return mfail(m, ORBX_ERR_ARG, "offsets must be non-decreasing");
+        if (offsets[i + 1] - offsets[i] > (int)KNN_IDX_MASK) return mfail(m, ORBX_ERR_ARG, "candidate list too long");
+    }
+    for (int k = 0; k < nnz; k++) if (indices[k] < 0 || indices[k] >= nt) return mfail(m, ORBX_ERR_ARG, "candidate index out of range");
+    MCK(cudaSetDevice(m->device));
+    const size_t need = (size_t)nq + 1 + (size_t)nnz;
+    if (need > m->csrCap) {
+        if (m->dCsr) cudaFree(m->dCsr);
+        m->dCsr = nullptr; m->csrCap = 0;
+        MCK(cudaMalloc((void **)&m->dCsr, need * sizeof(int)));
+        m->csrCap = need;
+    }
+    MCK(cudaMemcpyAsync(m->dQ, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    if (nt > 0) MCK(cudaMemcpyAsync(m->dT, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    m->residentNt = nt;
+    MCK(cudaMemcpyAsync(m->dCsr, offsets, (size_t)(nq + 1) * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    if (nnz > 0) MCK(cudaMemcpyAsync(m->dCsr + nq + 1, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    int rc = orbm_knn2_csr_device(m, m->dQ, nq, m->dT, m->dCsr, m->dCsr + nq + 1, (int32_t *)m->dOut, m->stream);
+    if (rc != ORBX_OK) return rc;
+    MCK(cudaMemcpyAsync(m->hOut, m->dOut, (size_t)nq * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < nq; i++) { idx1[i] = m->hOut[i].x; d1[i] = m->hOut[i].y; d2[i] = m->hOut[i].z; idx2[i] = m->hOut[i].w; }
+    return ORBX_OK;
+}
+
+int orbm_measure_popc(orbm_matcher *m, double *popc_per_clk_per_sm)
+{
+    if (!m || !popc_per_clk_per_sm) return ORBX_ERR_ARG;
+    MCK(cudaSetDevice(m->device));
+    const int perSm = 8, blocks = m->smCount * perSm, iters = 4096;
+    long long *dCyc = nullptr; unsigned *dSink = nullptr;
+    MCK(cudaMalloc((void **)&dCyc, sizeof(long long) * blocks));
+    MCK(cudaMalloc((void **)&dSink, sizeof(unsigned)));
+    for (int rep = 0; rep < 2; rep++) k_popc_probe<<<blocks, 256, 0, m->stream>>>(12345u + rep, iters, dSink, dCyc);
+    MCK(cudaGetLastError());
+    std::vector<long long> cyc(blocks);
+    MCK(cudaMemcpyAsync(cyc.data(), dCyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    cudaFree(dCyc); cudaFree(dSink);
+    double mean = 0;
+    for (long long c : cyc) mean += (double)c;
+    mean /= blocks;
+    // perSm CTAs of 256 threads are co-resident on every SM for the whole probe
+    *popc_per_clk_per_sm = (double)perSm * 256.0 * iters * 8.0 / mean;
+    return ORBX_OK;
 }
 
 int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *out)

@@ -70,7 +70,7 @@ struct orbx_extractor {
     bool geomUploaded = false;
     // device state
     cudaStream_t stream = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr;
     cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
     std::vector<cudaEvent_t> evChunk;
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
@@ -368,21 +368,28 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     unsigned long long *best = h->dBest.p + (size_t)f0 * L.rowsPerFrame;
     int2 *slots = h->dSlots.p + (size_t)f0 * L.slotsPerFrame;
     int *lvlCount = h->dLvlCount.p + (size_t)f0 * L.nlevels;
-    for (int l = 1; l < L.nlevels; l++) launch_resize(pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
-    // blur only depends on the pyramid: run it on the side stream, beside FAST + octree
-    CK(cudaEventRecord(h->evFork, st));
-    CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
-    CK(cudaEventRecord(h->evJoin, h->stream2));
-
-    CK(cudaMemsetAsync(cnt, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(best, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
     OrbxDbgCand *dbg = nullptr; int *dbgCount = nullptr;
     if (h->dbgEnabled) {
         dbg = h->dDbg.p + (size_t)f0 * L.nlevels * h->dbgCap; dbgCount = h->dDbgCount.p + (size_t)f0 * L.nlevels;
         CK(cudaMemsetAsync(dbgCount, 0, (size_t)L.nlevels * batch * sizeof(int), st));
     }
-    launch_fast(pyr, L, h->dCells.p, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
+    CK(cudaMemsetAsync(cnt, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(best, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
+    // Level 0 is in place: its FAST cells (a third of all cells, issue-bound) run on the side stream
+    // beside the resize chain (7 dependent, latency-bound launches); the blur follows there once the
+    // chain is done, beside FAST of the upper levels + octree on the main stream.
+    const int cells0 = L.lv[0].nCells;
+    CK(cudaEventRecord(h->evFork, st));
+    CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
+    launch_fast(pyr, L, h->dCells.p, 0, cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, h->stream2);
+    CK(cudaEventRecord(h->evFast0, h->stream2));
+    for (int l = 1; l < L.nlevels; l++) launch_resize(pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
+    CK(cudaEventRecord(h->evPyr, st));
+    CK(cudaStreamWaitEvent(h->stream2, h->evPyr, 0));
+    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
+    CK(cudaEventRecord(h->evJoin, h->stream2));
+    launch_fast(pyr, L, h->dCells.p, cells0, L.totalCells - cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
+    CK(cudaStreamWaitEvent(st, h->evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
     CK(cudaStreamWaitEvent(st, h->evJoin, 0));
     launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
@@ -409,6 +416,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     if (!cfg || !out) return ORBX_ERR_ARG;
     *out = nullptr;
     if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
+        cfg->scale_factor > 1.85f ||   /* k_resize keeps at most 16 source rows per 8-row strip */
         cfg->min_th_fast < 1 || cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
         cfg->max_batch < 1 || cfg->max_width < 1 || cfg->max_height < 1)
         return ORBX_ERR_ARG;
@@ -444,6 +452,8 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     CK(cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evFast0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evPyr, cudaEventDisableTiming));
     // size the arenas for the declared maximum so the hot path never allocates
     int rc = setGeometry(h, cfg->max_width, cfg->max_height);
     if (rc != ORBX_OK) return rc;
@@ -470,6 +480,8 @@ void orbx_destroy(orbx_extractor *h)
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->evFast0) cudaEventDestroy(h->evFast0);
+    if (h->evPyr) cudaEventDestroy(h->evPyr);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->streamIn) cudaStreamDestroy(h->streamIn);
@@ -621,6 +633,31 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     return status;
 }
 
+int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!kps || !desc || !n_out || kp_cap < 1 || h->lastBatch < 1) return fail(h, ORBX_ERR_ARG, "bad argument or no previous call");
+    CK(cudaSetDevice(h->cfg.device));
+    const OrbxLayout &L = h->L;
+    const int batch = h->lastBatch;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(h->hKps.ensure((size_t)L.kpStride * batch));
+    CK(h->hDesc.ensure((size_t)L.kpStride * batch * 32));
+    CK(h->hCounts.ensure((size_t)batch));
+    CK(cudaMemcpyAsync(h->hCounts.p, h->dCounts.p, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hKps.p, h->dKps.p, sizeof(orbx_keypoint_pod) * (size_t)L.kpStride * batch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->hDesc.p, h->dDesc.p, (size_t)L.kpStride * batch * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int f = 0; f < batch; f++) {
+        const int n = h->hCounts.p[f];
+        if (n > kp_cap) return fail(h, ORBX_ERR_CAPACITY, "kp_cap too small");
+        memcpy(kps + (size_t)f * kp_cap, h->hKps.p + (size_t)f * L.kpStride, sizeof(orbx_keypoint) * n);
+        memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
+        n_out[f] = n;
+    }
+    return ORBX_OK;
+}
+
 int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, size_t pitch,
                  orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
 {
@@ -682,7 +719,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
-        launch_fast(h->dPyr.p, L, h->dCells.p, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
+        launch_fast(h->dPyr.p, L, h->dCells.p, 0, L.totalCells, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
         CK(cudaEventRecord(ev[2], st));
         CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
         CK(cudaEventRecord(ev[3], st));

@@ -541,11 +541,12 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     }
 }
 
-void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, uint32_t *cnt,
+void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount, uint32_t *cnt,
                  unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st)
 {
-    dim3 grid(L.totalCells, batch);
-    k_fast_cells<<<grid, 128, 0, st>>>(pyr, L, cells, cnt, best, dbg, dbgCount, dbgCap);
+    if (cellCount <= 0) return;
+    dim3 grid(cellCount, batch);
+    k_fast_cells<<<grid, 128, 0, st>>>(pyr, L, cells + cellBegin, cnt, best, dbg, dbgCount, dbgCap);
 }
 
 // ------------------------------------------------------------------------------------------

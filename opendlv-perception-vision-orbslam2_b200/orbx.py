@@ -35,10 +35,10 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_max_keypoints", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_max_keypoints", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_distance_pairs"]
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_pairs", "orbm_measure_popc"]
 
 
 def lib():
@@ -59,6 +59,7 @@ def lib():
     L.orbx_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
+    L.orbx_fetch_results.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.orbx_max_keypoints.argtypes = [vp]
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
@@ -74,6 +75,9 @@ def lib():
     L.orbm_set_train.argtypes = [vp, vp, C.c_int]
     L.orbm_knn2_resident.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.orbm_knn2_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    L.orbm_knn2_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.orbm_knn2_csr_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
     _lib = L
     return L
@@ -155,6 +159,12 @@ class Extractor:
         self._check(lib().orbx_device_results(self._h, C.byref(k), C.byref(d), C.byref(c), C.byref(s)))
         return k.value, d.value, c.value, s.value
 
+    def fetch_results(self, batch, stream=None):
+        cap = self.max_keypoints
+        kps = np.zeros((batch, cap), KP_DTYPE); desc = np.zeros((batch, cap, 32), np.uint8); counts = np.zeros(batch, np.int32)
+        self._check(lib().orbx_fetch_results(self._h, C.c_void_p(stream) if stream else None, _ptr(kps), cap, _ptr(desc), _ptr(counts)))
+        return kps, desc, counts
+
     STAGES = ("resize", "fast", "octree", "blur", "describe")
 
     def profile_stages(self, reps=5):
@@ -231,6 +241,22 @@ class Matcher:
     def knn2_device(self, dq, nq, dt, nt, dout, stream=None):
         self._check(lib().orbm_knn2_device(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, C.c_void_p(dout),
                                            C.c_void_p(stream) if stream else None))
+
+    def knn2_csr(self, q, t, offsets, indices):
+        """Per-query candidate lists (CSR): (idx1, d1, idx2, d2) as SearchByProjection's inner loop leaves them."""
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+        nq = len(q)
+        i1, d1, i2, d2 = (np.zeros(nq, np.int32) for _ in range(4))
+        self._check(lib().orbm_knn2_csr(self._h, _ptr(q), nq, _ptr(t), len(t), _ptr(offsets), _ptr(indices),
+                                        _ptr(i1), _ptr(d1), _ptr(i2), _ptr(d2)))
+        return i1, d1, i2, d2
+
+    def measure_popc(self):
+        """POPC lane-operations per clock per SM measured on this GPU."""
+        r = C.c_double()
+        self._check(lib().orbm_measure_popc(self._h, C.byref(r)))
+        return r.value
 
     def distance_pairs(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)

@@ -831,6 +831,24 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
     }
 }
 
+/* candidate-list variant: the inner loop of SearchByProjection, orbmatcher.cpp:76-114.  The reference
+ * carries the octave of the best and of the second-best candidate (bestLevel, bestLevel2); the index of
+ * the second best is returned instead so the caller can look the octave up. */
+void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *offsets, const int32_t *indices,
+                   int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2)
+{
+    for (int i = 0; i < nq; i++) {
+        int bestDist = 256, bestDist2 = 256, bestIdx = -1, bestIdx2 = -1;
+        for (int k = offsets[i]; k < offsets[i + 1]; k++) {
+            const int idx = indices[k];
+            const int dist = orbo_descriptor_distance(q + (size_t)i * 32, t + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = bestIdx; bestIdx = idx; }
+            else if (dist < bestDist2) { bestIdx2 = idx; bestDist2 = dist; }
+        }
+        idx1[i] = bestIdx; d1[i] = bestDist; idx2[i] = bestIdx2; d2[i] = bestDist2;
+    }
+}
+
 typedef struct { const uint8_t *q, *t; int q0, q1, nt; int32_t *idx, *d1, *d2; } knn_job;
 static void *knn_worker(void *arg)
 {

@@ -114,6 +114,9 @@ void orbo_set_tie_rule(orbo_extractor *e, int tie_rule);
 int orbo_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);
 void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
                int32_t *idx, int32_t *d1, int32_t *d2);
+/* per-query candidate lists (CSR): inner loop of SearchByProjection, orbmatcher.cpp:76-114 */
+void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *offsets, const int32_t *indices,
+                   int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2);
 /* multi-threaded variants for the CPU baseline (query-/frame-partitioned) */
 void orbo_knn2_mt(const uint8_t *q, int nq, const uint8_t *t, int nt,
                   int32_t *idx, int32_t *d1, int32_t *d2, int nthreads);

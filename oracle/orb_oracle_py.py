@@ -87,6 +87,7 @@ def lib():
     L.orbo_descriptor_distance.restype = C.c_int
     L.orbo_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
     L.orbo_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orbo_knn2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 6
     L.orbo_knn2_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
     return L
@@ -191,6 +192,15 @@ def knn2(q, t, nthreads=1):
     else:
         lib().orbo_knn2_mt(_ptr(q), nq, _ptr(t), nt, _ptr(idx), _ptr(d1), _ptr(d2), nthreads)
     return idx, d1, d2
+
+
+def knn2_csr(q, t, offsets, indices):
+    q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    nq = len(q)
+    i1, d1, i2, d2 = (np.empty(nq, np.int32) for _ in range(4))
+    lib().orbo_knn2_csr(_ptr(q), nq, _ptr(t), _ptr(offsets), _ptr(indices), _ptr(i1), _ptr(d1), _ptr(i2), _ptr(d2))
+    return i1, d1, i2, d2
 
 
 class Extractor:

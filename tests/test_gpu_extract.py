@@ -15,6 +15,7 @@ CONFIGS = {
     "kitti": dict(w=1241, h=376, nfeatures=2000, nlevels=8),
     "small": dict(w=640, h=360, nfeatures=1000, nlevels=6),
     "hd": dict(w=1920, h=1080, nfeatures=4000, nlevels=8),
+    "uhd": dict(w=3840, h=2160, nfeatures=8000, nlevels=12),     # BASELINE config[3]: pyramid/blur bandwidth stress
 }
 
 
@@ -115,6 +116,36 @@ def test_hd_frame(oracle):
     img = synth.scene_s1(cfg["w"], cfg["h"], 3000)
     kps, desc, counts = ex.extract_batch([img])
     _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
+
+
+def test_uhd_frame_12_levels(oracle):
+    import orbx
+    cfg = CONFIGS["uhd"]
+    ex = _mk(orbx, cfg)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    img = synth.scene_s1(cfg["w"], cfg["h"], 4000)
+    kps, desc, counts = ex.extract_batch([img])
+    assert counts[0] == 8000
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
+
+
+def test_device_resident_entry_point(oracle):
+    """orbx_extract_batch_device: frames already in HBM, results left in HBM (the path bench.py times as `value`)."""
+    import torch
+    import orbx
+    cfg = CONFIGS["small"]
+    imgs = synth.frames(5, cfg["w"], cfg["h"], 3)
+    ex = _mk(orbx, cfg, batch=3)
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    st = torch.cuda.Stream()
+    ex.extract_batch_device(d.data_ptr(), cfg["w"] * cfg["h"], cfg["w"], 3, cfg["w"], cfg["h"], st.cuda_stream)
+    kps, desc, cnt = ex.fetch_results(3, st.cuda_stream)
+    assert ex.device_results()[3] == ex.max_keypoints
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    for f, img in enumerate(imgs):
+        _compare_frame(oracle, ex, oex, img, f, kps[f], desc[f], int(cnt[f]), stages=False)
     ex.close()
 
 

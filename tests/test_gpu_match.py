@@ -80,3 +80,43 @@ def test_distance_pairs(oracle):
     ref = np.array([oracle.descriptor_distance(a[i], b[i]) for i in range(500)], np.int32)
     assert np.array_equal(d, ref)
     m.close()
+
+
+def _random_csr(rng, nq, nt, max_len):
+    lens = rng.integers(0, max_len + 1, nq)
+    lens[rng.integers(0, nq, max(1, nq // 10))] = 0            # empty lists (vIndices.empty(), orbmatcher.cpp:71)
+    offsets = np.zeros(nq + 1, np.int32); offsets[1:] = np.cumsum(lens)
+    indices = rng.integers(0, nt, int(offsets[-1])).astype(np.int32)   # unsorted, with repeats
+    return offsets, indices
+
+
+def test_knn2_csr_vs_oracle(oracle):
+    """Candidate-list matching = inner loop of SearchByProjection (orbmatcher.cpp:76-114)."""
+    import orbx
+    rng = np.random.default_rng(12)
+    q, t = synth.matching_set(500, 4000, seed=8)
+    t[17] = t[18] = q[3]                                       # equal distances inside one list: earlier position wins
+    offsets, indices = _random_csr(rng, 500, 4000, 90)
+    indices[offsets[3]:offsets[3] + 2] = [18, 17] if offsets[4] - offsets[3] >= 2 else indices[offsets[3]:offsets[3] + 2]
+    m = orbx.Matcher(max_queries=500, max_train=4000)
+    g = m.knn2_csr(q, t, offsets, indices)
+    o = oracle.knn2_csr(q, t, offsets, indices)
+    for a, b, name in zip(g, o, ("idx1", "d1", "idx2", "d2")):
+        assert np.array_equal(a, b), name
+    empty = np.flatnonzero(np.diff(offsets) == 0)
+    assert (g[0][empty] == -1).all() and (g[1][empty] == 256).all()
+    with pytest.raises(orbx.OrbxError):
+        m.knn2_csr(q, t, offsets, np.full_like(indices, 4000))  # out-of-range candidate index
+    m.close()
+
+
+def test_knn2_csr_full_lists_equal_bruteforce(oracle):
+    import orbx
+    q, t = synth.matching_set(64, 1500, seed=3)
+    offsets = (np.arange(65) * 1500).astype(np.int32)
+    indices = np.tile(np.arange(1500, dtype=np.int32), 64)
+    m = orbx.Matcher(max_queries=64, max_train=1500)
+    i1, d1, i2, d2 = m.knn2_csr(q, t, offsets, indices)
+    bi, b1, b2 = m.knn2(q, t)
+    assert np.array_equal(i1, bi) and np.array_equal(d1, b1) and np.array_equal(d2, b2)
+    m.close()
