@@ -216,6 +216,11 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
                 cell.w = (uint8_t)(maxX - iniX); cell.h = (uint8_t)(maxY - iniY);
                 cell.level = (uint8_t)l; cell.pad = 0;
                 cell.ci = (uint16_t)i; cell.cj = (uint16_t)j;
+                {
+                    const int wEff = std::max((int)cell.w - 6, 1);
+                    cell.mQ = (uint16_t)(32768 / ((wEff + 3) >> 2) + 1);
+                    cell.mG = (uint16_t)(32768 / (((int)cell.w + 1 + 15) >> 4) + 1);
+                }
                 cells.push_back(cell);
             }
         }

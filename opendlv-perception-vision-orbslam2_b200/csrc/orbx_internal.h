@@ -49,6 +49,7 @@ struct OrbxCell {
     uint8_t w, h;        // window size (maxX-iniX, maxY-iniY) <= 66
     uint8_t level, pad;
     uint16_t ci, cj;     // cell row / column: (ci*nCols + cj) is the cell's position in the reference's emission order
+    uint16_t mQ, mG;     // 32768/n + 1 for n = 4-pixel groups per interior row / 16-byte groups per window row
 };
 
 // one blur tile: 32 words (128 px) x 4 strips of 32 rows; x0 in 4-px words, y0 in rows

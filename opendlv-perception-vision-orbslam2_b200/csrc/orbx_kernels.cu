@@ -419,12 +419,12 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     {
         const uint8_t *base = pyr + (size_t)frame * L.slab + lv.off + (size_t)cell.y0 * lv.pitch + (int)cell.x0 - 1;
         const int ng = ((int)cell.w + 1 + 15) >> 4;          // 16-byte groups per row, <= 5
-        const unsigned M = 65536u / ng + 1;
+        const unsigned M = cell.mG;                          // 32768 / ng + 1 (host): i / ng == (i * M) >> 15
         const int sh = (int)((uintptr_t)base & 3) * 8;       // pitch is a multiple of 4: the same shift for every row
         const uint32_t *base4 = (const uint32_t *)((uintptr_t)base & ~(uintptr_t)3);
         const int pitch4 = lv.pitch >> 2;
         for (int i = tid; i < (int)cell.h * ng; i += 128) {
-            const int r = (i * M) >> 16, g = i - r * ng;
+            const int r = (i * M) >> 15, g = i - r * ng;
             const uint32_t *p = base4 + (size_t)r * pitch4 + 4 * g;
             const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
             uint4 o;
@@ -440,10 +440,10 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     // ---- stage 1: packed quick reject, 4 pixels per thread
     {
         const int nQ = (wEff + 3) >> 2, items = nQ * hEff;
-        const unsigned M = 65536u / nQ + 1;
+        const unsigned M = cell.mQ;                          // 32768 / nQ + 1 (host)
         const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
         for (int it = tid; it < items; it += 128) {
-            const int yIn = (it * M) >> 16, q = it - yIn * nQ;
+            const int yIn = (it * M) >> 15, q = it - yIn * nQ;
             const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + q;
             const uint32_t W0 = rw[0], C = rw[1], W2 = rw[2];
             const uint32_t U = rw[1 + 3 * (FW_P / 4)], D = rw[1 - 3 * (FW_P / 4)];
@@ -467,15 +467,21 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     __syncthreads();
     const int nc = ncand;
 
-    // ---- stage 2: exact ring test (9 contiguous brighter or darker), second compaction
+    // ---- stage 2: exact ring test (9 contiguous brighter or darker), second compaction.
+    // ring > v+t  <=>  (v+t) - ring < 0 ;  ring < v-t  <=>  ring - (v-t) < 0 : the sign bits are shifted
+    // into the two 16-bit ring masks with one funnel shift each (bit order reversed, contiguity is not).
     for (int i = tid; i < nc; i += 128) {
         const int e = cand[i];
         const int yIn = e >> 6, xIn = e & 63;
-        int d[16];
-        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + 4], d);
+        const uint8_t *c = &win[(yIn + 3) * FW_P + xIn + 4];
+        const int v = c[0], hi = v + th, lo = v - th;
         unsigned mb = 0, md = 0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) { mb |= (unsigned)(d[k] > th) << k; md |= (unsigned)(d[k] < -th) << k; }
+#define ORBX_RING(off) { const int r_ = c[off]; mb = __funnelshift_l((unsigned)(hi - r_), mb, 1); md = __funnelshift_l((unsigned)(r_ - lo), md, 1); }
+        ORBX_RING(3 * FW_P) ORBX_RING(3 * FW_P + 1) ORBX_RING(2 * FW_P + 2) ORBX_RING(FW_P + 3)
+        ORBX_RING(3) ORBX_RING(-FW_P + 3) ORBX_RING(-2 * FW_P + 2) ORBX_RING(-3 * FW_P + 1)
+        ORBX_RING(-3 * FW_P) ORBX_RING(-3 * FW_P - 1) ORBX_RING(-2 * FW_P - 2) ORBX_RING(-FW_P - 3)
+        ORBX_RING(-3) ORBX_RING(FW_P - 3) ORBX_RING(2 * FW_P - 2) ORBX_RING(3 * FW_P - 1)
+#undef ORBX_RING
         mb |= mb << 16; md |= md << 16;
         unsigned r = mb & (mb >> 1); r &= r >> 2; r &= r >> 4; r &= mb >> 8;
         unsigned q = md & (md >> 1); q &= q >> 2; q &= q >> 4; q &= md >> 8;
@@ -522,7 +528,8 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
         const int s = smap[(yIn + 1) * FS_P + xIn + 1];
         if (haveIni && s < L.iniTh) continue;
         const int xr = cell.cj * lv.wCell + 3 + xIn, yr = cell.ci * lv.hCell + 3 + yIn; // relative to (16,16), :963-964
-        const int strip = xr / lv.hX;                                                   // :710
+        int strip = 0;                                                                  // xr / hX, :710
+        for (int sB = lv.hX; sB <= xr; sB += lv.hX) strip++;
         const int row = strip * lv.H + yr;
         const unsigned order = orderBase | (unsigned)(yIn << 6 | xIn);
         const unsigned long long key = ((unsigned long long)s << 56) |
