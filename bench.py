@@ -316,6 +316,10 @@ def main():
         dom = max(stages, key=stages.get)
         dom_ms = stages[dom]
         ach = B_ALG * BATCH / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("bytes_per_step", {}).get(dom)
         pairs = NQ * NT * msteps / (ms_match * 1e-3)
         int_peak = 148 * sm_max * 1e6 * popc_rate / 8      # pairs/s at the POPC rate measured on this GPU, SURVEY 8(d)
         line = {
@@ -330,7 +334,8 @@ def main():
                     "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": n_kp},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this stage, bytes per 64-frame step)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": B_ALG * BATCH, "kernel_ms": dom_ms,
                          "whole_step_frac": B_ALG * BATCH / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
             "stages_ms": stages,
