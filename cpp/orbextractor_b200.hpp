@@ -104,6 +104,7 @@ class OrbExtractor {
       }
   }
   void setDevice(int device) { m_device = device; }
+  orbx_extractor *handle() { return m_handle; }   // for orbx_stereo_match and other device-resident consumers
 
  private:
   void check(int rc)

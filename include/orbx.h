@@ -103,6 +103,17 @@ int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const ui
  * orbx_extract_batch).  Waits for `stream` (the stream that call was given; NULL = the handle's). */
 int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
 
+/* OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705), the immediate consumer of both extractors:
+ * for every left keypoint the sub-pixel u coordinate of its match in the right image and the depth
+ * mbf/disparity, -1 where there is none.  Works on the device-resident results (keypoints, descriptors,
+ * pyramids) of the last extraction of `left` / frame_left and `right` / frame_right -- two handles as in
+ * the reference (orbframe.cpp:73-76) or two frames of one batch -- so no pyramid leaves HBM.
+ * mbf = stereo baseline * fx, mb = baseline (orbframe.cpp:545-547 use minZ = mb; pass 0 to reproduce the
+ * reference's first-frame behaviour).  n_left = left keypoints, n_matches = matches
+ * before the median filter. */
+int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *right, int frame_right, float mbf, float mb,
+                      float *u_right, float *depth, int cap, int *n_left, int *n_matches);
+
 /* upper bound of keypoints per frame for this configuration */
 int orbx_max_keypoints(const orbx_extractor *h);
 

@@ -88,6 +88,9 @@ struct orbx_extractor {
     DevBuf<OrbxRTab> dRtab;
     DevBuf<OrbxTile> dTiles;
     DevBuf<OrbxDbgCand> dDbg;
+    DevBuf<float> dStereo;          // uRight | depth of the last orbx_stereo_match
+    DevBuf<int> dStereoI;           // sad per left keypoint | match count
+    PinBuf<float> hStereo;
     PinBuf<uint8_t> hIn, hDesc, hLevel;
     PinBuf<orbx_keypoint_pod> hKps;
     PinBuf<int> hCounts;
@@ -247,7 +250,7 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         if (v.slotCap > ORBX_MAX_NODES) return fail(h, ORBX_ERR_SHAPE, "per-level feature quota exceeds 4096");
         slots += v.slotCap;
         maxNodes = std::max(maxNodes, v.slotCap + 2);
-        v.sf = h->sf[l];
+        v.sf = h->sf[l]; v.invSf = h->invSf[l];
         v.kpSize = 31 * (int)h->sf[l];   // :978 int cast before the multiply
         // blur tiles: 32 words x (4 strips of 32 rows)
         for (int ty = 0; ty < v.h; ty += 128)
@@ -481,7 +484,7 @@ void orbx_destroy(orbx_extractor *h)
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
-    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dDbg.release();
+    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
@@ -660,6 +663,46 @@ int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int 
         memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
         n_out[f] = n;
     }
+    return ORBX_OK;
+}
+
+// OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705) on the device-resident results of the last
+// extraction of `left` (frame frame_left) and `right` (frame frame_right); the two may be one handle.
+int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *right, int frame_right, float mbf, float mb,
+                      float *u_right, float *depth, int cap, int *n_left, int *n_matches)
+{
+    orbx_extractor *h = left;
+    if (!left || !right) return ORBX_ERR_ARG;
+    if (!u_right || !depth || frame_left < 0 || frame_left >= left->lastBatch || frame_right < 0 || frame_right >= right->lastBatch)
+        return fail(h, ORBX_ERR_ARG, "bad argument or no previous extraction");
+    if (left->cfg.device != right->cfg.device || left->curW != right->curW || left->curH != right->curH ||
+        left->cfg.nlevels != right->cfg.nlevels || left->cfg.scale_factor != right->cfg.scale_factor)
+        return fail(h, ORBX_ERR_ARG, "left and right extractors must share device, image size and pyramid");
+    CK(cudaSetDevice(h->cfg.device));
+    const OrbxLayout &L = left->L;
+    CK(h->dStereo.ensure((size_t)2 * L.kpStride));
+    CK(h->dStereoI.ensure((size_t)L.kpStride + 1));
+    CK(h->hStereo.ensure((size_t)2 * L.kpStride + 2));
+    if (right != left) CK(cudaStreamSynchronize(right->stream));
+    cudaStream_t st = left->stream;
+    const float maxD = mbf / mb;            // orbframe.cpp:545-547 (minZ = mb; +inf when mb is still 0)
+    float *dU = h->dStereo.p, *dD = h->dStereo.p + L.kpStride;
+    int *dSad = h->dStereoI.p, *dN = h->dStereoI.p + L.kpStride;
+    CK(launch_stereo(L, left->dPyr.p + (size_t)frame_left * L.slab, right->dPyr.p + (size_t)frame_right * right->L.slab,
+                     left->dKps.p + (size_t)frame_left * L.kpStride, left->dDesc.p + (size_t)frame_left * L.kpStride * 32,
+                     left->dCounts.p + frame_left, right->dKps.p + (size_t)frame_right * right->L.kpStride,
+                     right->dDesc.p + (size_t)frame_right * right->L.kpStride * 32, right->dCounts.p + frame_right,
+                     mbf, maxD, dU, dD, dSad, dN, st));
+    int counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(h->hStereo.p, h->dStereo.p, sizeof(float) * 2 * L.kpStride, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&counts[0], left->dCounts.p + frame_left, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&counts[1], dN, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (counts[0] > cap) return fail(h, ORBX_ERR_CAPACITY, "u_right / depth arrays too small");
+    memcpy(u_right, h->hStereo.p, sizeof(float) * counts[0]);
+    memcpy(depth, h->hStereo.p + L.kpStride, sizeof(float) * counts[0]);
+    if (n_left) *n_left = counts[0];
+    if (n_matches) *n_matches = counts[1];
     return ORBX_OK;
 }
 

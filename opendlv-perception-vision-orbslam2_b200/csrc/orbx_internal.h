@@ -25,7 +25,7 @@ struct OrbxLevel {
     int rowBase;         // first entry of this level in the per-frame row-summary arrays
     int slotBase, slotCap; // keypoint slots of this level inside a frame
     // post-processing, orbextractor.cpp:978, :631-637
-    float sf;
+    float sf, invSf;
     int kpSize;          // 31 * (int)sf
     // resize coefficient tables (entries of OrbxRTab), level l built from level l-1
     int xtabOff, ytabOff;

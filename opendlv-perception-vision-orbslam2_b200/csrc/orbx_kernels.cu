@@ -1024,3 +1024,163 @@ void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &
     dim3 grid((L.slotsPerFrame + perBlock - 1) / perBlock, batch);
     k_describe<<<grid, DS_WARPS * 32, 0, st>>>(pyr, blur, L, slots, lvlCount, um, kps, desc, counts);
 }
+
+// ------------------------------------------------------------------------------------------
+// OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705, "next" row N1 of SURVEY 8f): the immediate
+// consumer of both extractors' keypoints, descriptors and pyramids -- run here on the device-resident
+// results so neither pyramid has to leave HBM.
+//   k_stereo_match : one warp per left keypoint.  Candidates are the right keypoints whose row band
+//                    [floor(y-r), ceil(y+r)], r = 2*scale[octave], contains the left row (:527-541, the
+//                    reference's vRowIndices table, evaluated on the fly), within one octave and inside
+//                    the disparity range; best Hamming distance below TH_HIGH, lowest index on ties
+//                    (:565-597); then the 11x11 SAD over 11 offsets at the keypoint's level and the
+//                    parabola fit (:600-690), float32 without FMA.
+//   k_stereo_filter: one CTA per pair: sort (SAD, index), median, reject SAD >= 1.5*1.4*median (:693-705).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hamming256_dev(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
+{
+    return __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+           __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+}
+
+__global__ void __launch_bounds__(128)
+k_stereo_match(const __grid_constant__ OrbxLayout L, const uint8_t *__restrict__ pyrL, const uint8_t *__restrict__ pyrR,
+               const orbx_keypoint_pod *__restrict__ kl, const uint4 *__restrict__ dl, const int *__restrict__ nlPtr,
+               const orbx_keypoint_pod *__restrict__ kr, const uint4 *__restrict__ dr, const int *__restrict__ nrPtr,
+               float mbf, float maxD, float *__restrict__ uRight, float *__restrict__ depth, int *__restrict__ sad)
+{
+    __shared__ float part[4][121];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int iL = blockIdx.x * 4 + warp;
+    const int nl = *nlPtr, nr = *nrPtr;
+    if (iL >= nl) return;
+    const orbx_keypoint_pod kpL = kl[iL];
+    if (lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sad[iL] = -1; }
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const float minU = __fsub_rn(uL, maxD), maxU = uL;           // minD = 0
+    if (maxU < 0) return;
+    const uint4 qa = __ldg(&dl[2 * iL]), qb = __ldg(&dl[2 * iL + 1]);
+    const int TH_HIGH = 100, thOrbDist = 75;
+    unsigned best = (unsigned)TH_HIGH << 16;                     // dist < TH_HIGH only; lowest iR wins ties
+    for (int iR = lane; iR < nr; iR += 32) {
+        const orbx_keypoint_pod k = kr[iR];
+        const float r = __fmul_rn(2.0f, L.lv[k.octave].sf);
+        const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
+        if (row < minr || row > maxr) continue;
+        if (k.octave < levelL - 1 || k.octave > levelL + 1) continue;
+        if (!(k.x >= minU && k.x <= maxU)) continue;
+        const int d = hamming256_dev(qa, qb, __ldg(&dr[2 * iR]), __ldg(&dr[2 * iR + 1]));
+        const unsigned key = (unsigned)d << 16 | (unsigned)iR;
+        best = min(best, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    const int bestDist = (int)(best >> 16), bestIdxR = (int)(best & 0xffff);
+    if (bestDist >= thOrbDist) return;
+
+    // ---- sub-pixel match by correlation, at the left keypoint's pyramid level
+    const OrbxLevel &lv = L.lv[levelL];
+    const float uR0 = kr[bestIdxR].x;
+    const float scaleFactor = lv.invSf;
+    const float scaleduL = roundf(__fmul_rn(kpL.x, scaleFactor)), scaledvL = roundf(__fmul_rn(kpL.y, scaleFactor));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, scaleFactor));
+    const int w = 5, LL = 5;
+    const float iniu = scaleduR0 + LL - w, endu = scaleduR0 + LL + w + 1;
+    if (iniu < 0 || endu >= lv.w) return;
+    const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w), xr0 = (int)(scaleduR0 - w);
+    // the reference would throw inside cv::Mat::colRange / rowRange here; no match is reported instead
+    if (y0 < 0 || y0 + 11 > lv.h || xl0 < 0 || xl0 + 11 > lv.w || xr0 - LL < 0 || xr0 + LL + 11 > lv.w) return;
+    const uint8_t *IL = pyrL + lv.off + (size_t)y0 * lv.pitch + xl0;
+    const uint8_t *IR = pyrR + lv.off + (size_t)y0 * lv.pitch + xr0;
+    const int cL = IL[w * lv.pitch + w];
+    // item k = (offset index, window row): 121 items over 32 lanes; the centre of the right window moves with incR
+    for (int k = lane; k < 121; k += 32) {
+        const int inc = k / 11, ry = k - inc * 11;
+        const uint8_t *a = IL + ry * lv.pitch, *b = IR + ry * lv.pitch + (inc - LL);
+        const int cR = IR[w * lv.pitch + w + (inc - LL)];
+        int s = 0;
+#pragma unroll
+        for (int x = 0; x < 11; x++) { const int v = ((int)a[x] - cL) - ((int)b[x] - cR); s += v < 0 ? -v : v; }
+        part[warp][k] = (float)s;
+    }
+    __syncwarp();
+    float dist = 0.f;
+    if (lane < 11) {
+#pragma unroll
+        for (int ry = 0; ry < 11; ry++) dist += part[warp][lane * 11 + ry];   // integers < 2^24: exact in float
+    }
+    float vd[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) vd[i] = __shfl_sync(0xffffffffu, dist, i);
+    if (lane != 0) return;
+    int bestSad = 0x7fffffff, bestinc = 0;
+#pragma unroll
+    for (int i = 0; i < 11; i++)
+        if (vd[i] < (float)bestSad) { bestSad = (int)vd[i]; bestinc = i - LL; }
+    if (bestinc == -LL || bestinc == LL) return;
+    float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+    for (int i = 1; i < 10; i++) if (i == bestinc + LL) { d1 = vd[i - 1]; d2 = vd[i]; d3 = vd[i + 1]; }
+    const float deltaR = __fdiv_rn(__fsub_rn(d1, d3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2))));
+    if (deltaR < -1 || deltaR > 1) return;
+    float bestuR = __fmul_rn(lv.sf, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+    float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= 0 && disparity < maxD) {
+        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+        depth[iL] = __fdiv_rn(mbf, disparity);
+        uRight[iL] = bestuR;
+        sad[iL] = bestSad;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_stereo_filter(const int *__restrict__ nlPtr, const int *__restrict__ sad, float *__restrict__ uRight, float *__restrict__ depth,
+                int *__restrict__ nMatches, int pow2)
+{
+    extern __shared__ unsigned skeys[];
+    __shared__ int cnt;
+    const int nl = *nlPtr, tid = threadIdx.x;
+    if (tid == 0) cnt = 0;
+    __syncthreads();
+    for (int i = tid; i < pow2; i += 256) {
+        unsigned key = 0xffffffffu;
+        if (i < nl && sad[i] >= 0) { key = (unsigned)sad[i] << 16 | (unsigned)i; atomicAdd(&cnt, 1); }
+        skeys[i] = key;
+    }
+    __syncthreads();
+    const int n = cnt;
+    if (tid == 0) *nMatches = n;
+    if (n == 0) return;
+    for (int k = 2; k <= pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < pow2; t += 256) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const unsigned a = skeys[t], b = skeys[x];
+                    const bool asc = (t & k) == 0;
+                    if ((a > b) == asc) { skeys[t] = b; skeys[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    const float median = (float)(skeys[n / 2] >> 16);
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), median);
+    for (int i = tid; i < n; i += 256) {
+        const unsigned key = skeys[i];
+        if (!((float)(key >> 16) < thDist)) { uRight[key & 0xffff] = -1.0f; depth[key & 0xffff] = -1.0f; }
+    }
+}
+
+cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
+                          const uint8_t *dl, const int *nl, const orbx_keypoint_pod *kr, const uint8_t *dr, const int *nr,
+                          float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st)
+{
+    const int cap = L.kpStride;
+    if (cap > 65535) return cudaErrorInvalidValue;
+    int pow2 = 2; while (pow2 < cap) pow2 <<= 1;
+    k_stereo_match<<<(cap + 3) / 4, 128, 0, st>>>(L, pyrL, pyrR, kl, (const uint4 *)dl, nl, kr, (const uint4 *)dr, nr, mbf, maxD, uRight, depth, sad);
+    k_stereo_filter<<<1, 256, (size_t)pow2 * sizeof(unsigned), st>>>(nl, sad, uRight, depth, nMatches, pow2);
+    return cudaGetLastError();
+}

@@ -22,3 +22,6 @@ cudaError_t launch_octree(const OrbxLayout &L, uint32_t *cnt, const unsigned lon
 void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &L, const int2 *slots,
                      const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
                      int batch, cudaStream_t st);
+cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
+                          const uint8_t *dl, const int *nl, const orbx_keypoint_pod *kr, const uint8_t *dr, const int *nr,
+                          float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st);

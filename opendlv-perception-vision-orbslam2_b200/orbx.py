@@ -35,7 +35,7 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_max_keypoints", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_max_keypoints", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_pairs", "orbm_measure_popc"]
@@ -60,6 +60,7 @@ def lib():
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.orbx_fetch_results.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
@@ -193,6 +194,16 @@ class Extractor:
         xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
         n = self._check(lib().orbx_debug_candidates(self._h, frame, level, _ptr(xs), _ptr(ys), _ptr(sc), cap))
         return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def stereo_match(left, frame_left, right, frame_right, mbf, mb=0.0):
+    """OrbFrame::ComputeStereoMatches on the device-resident results of two extractions -> (uRight, depth, n_matches)."""
+    cap = left.max_keypoints
+    u = np.zeros(cap, np.float32); d = np.zeros(cap, np.float32)
+    nl, nm = C.c_int(), C.c_int()
+    left._check(lib().orbx_stereo_match(left._h, frame_left, right._h, frame_right, mbf, mb, _ptr(u), _ptr(d), cap,
+                                        C.byref(nl), C.byref(nm)))
+    return u[:nl.value].copy(), d[:nl.value].copy(), nm.value
 
 
 class Matcher:

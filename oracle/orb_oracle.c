@@ -801,6 +801,128 @@ int orbo_extract_batch_mt(const orbo_extractor *cfg, const uint8_t *const *imgs,
 }
 
 /* ------------------------------------------------------------------ */
+/* OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705 ("next" row N1). */
+/* PARITY UNPINNED: orbframe.cpp cannot be compiled here (it pulls in the  */
+/* whole SLAM data model) and the reference has no test for it; this is a  */
+/* line-by-line restatement only.                                          */
+/* ------------------------------------------------------------------ */
+typedef struct { int dist, idx; } dist_idx;
+static int dist_idx_cmp(const void *a, const void *b)
+{
+    const dist_idx *x = a, *y = b;
+    if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+int orbo_stereo_matches(const orbo_keypoint *kl, const uint8_t *dl, int nl,
+                        const orbo_keypoint *kr, const uint8_t *dr, int nr,
+                        const uint8_t *const *pyrL, const uint8_t *const *pyrR, const int *lw, const int *lh,
+                        const size_t *lstride, const float *sf, const float *inv_sf,
+                        float mbf, float mb, float *uRight, float *depth)
+{
+    const int TH_HIGH = 100, TH_LOW = 50;               /* orbmatcher.cpp:36-37 */
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;       /* :516 */
+    const int nRows = lh[0];                            /* :518 */
+    for (int i = 0; i < nl; i++) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+    /* row table :521-543 */
+    int *rowCount = calloc(nRows + 1, sizeof(int));
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * sf[kr[iR].octave];
+        const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++) if (yi >= 0 && yi < nRows) rowCount[yi]++;
+    }
+    int *rowStart = malloc(sizeof(int) * (nRows + 1));
+    rowStart[0] = 0;
+    for (int i = 0; i < nRows; i++) rowStart[i + 1] = rowStart[i] + rowCount[i];
+    int *rowIdx = malloc(sizeof(int) * (rowStart[nRows] + 1));
+    memset(rowCount, 0, sizeof(int) * (nRows + 1));
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * sf[kr[iR].octave];
+        const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++) if (yi >= 0 && yi < nRows) rowIdx[rowStart[yi] + rowCount[yi]++] = iR;
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;  /* :545-547 */
+    dist_idx *vDistIdx = malloc(sizeof(dist_idx) * (nl > 0 ? nl : 1));
+    int nDist = 0;
+    for (int iL = 0; iL < nl; iL++) {
+        const orbo_keypoint *kpL = &kl[iL];
+        const int levelL = kpL->octave;
+        const float vL = kpL->y, uL = kpL->x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows || rowCount[row] == 0) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        int bestIdxR = 0;
+        for (int iC = 0; iC < rowCount[row]; iC++) {
+            const int iR = rowIdx[rowStart[row] + iC];
+            const orbo_keypoint *kpR = &kr[iR];
+            if (kpR->octave < levelL - 1 || kpR->octave > levelL + 1) continue;
+            const float uR = kpR->x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = orbo_descriptor_distance(dl + (size_t)iL * 32, dr + (size_t)iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {                       /* :603 sub-pixel match by correlation */
+            const float uR0 = kr[bestIdxR].x;
+            const float scaleFactor = inv_sf[kpL->octave];
+            const float scaleduL = roundf(kpL->x * scaleFactor);
+            const float scaledvL = roundf(kpL->y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5, L = 5;
+            const int lv = kpL->octave;
+            const uint8_t *IL = pyrL[lv] + (size_t)((int)(scaledvL - w)) * lstride[lv] + (int)(scaleduL - w);
+            const float cL = (float)IL[(size_t)w * lstride[lv] + w];
+            int bestSad = 0x7fffffff;
+            int bestincR = 0;
+            float vDists[11];
+            const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= lw[lv]) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const uint8_t *IR = pyrR[lv] + (size_t)((int)(scaledvL - w)) * lstride[lv] + (int)(scaleduR0 + incR - w);
+                const float cR = (float)IR[(size_t)w * lstride[lv] + w];
+                double acc = 0;                            /* cv::norm(IL, IR, NORM_L1) on CV_32F */
+                for (int y = 0; y < 2 * w + 1; y++)
+                    for (int x = 0; x < 2 * w + 1; x++) {
+                        const float a = (float)IL[(size_t)y * lstride[lv] + x] - cL;
+                        const float b = (float)IR[(size_t)y * lstride[lv] + x] - cR;
+                        acc += fabs((double)(a - b));
+                    }
+                const float dist = (float)acc;
+                if (dist < (float)bestSad) { bestSad = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = sf[kpL->octave] * (scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01f; bestuR = (float)(uL - 0.01); }
+                depth[iL] = mbf / disparity;
+                uRight[iL] = bestuR;
+                vDistIdx[nDist].dist = bestSad; vDistIdx[nDist].idx = iL; nDist++;
+            }
+        }
+    }
+    if (nDist > 0) {                                      /* :693-705 (the reference reads vDistIdx[0] of an empty vector) */
+        qsort(vDistIdx, nDist, sizeof(dist_idx), dist_idx_cmp);
+        const float median = (float)vDistIdx[nDist / 2].dist;
+        const float thDist = 1.5f * 1.4f * median;
+        for (int i = nDist - 1; i >= 0; i--) {
+            if ((float)vDistIdx[i].dist < thDist) break;
+            uRight[vDistIdx[i].idx] = -1; depth[vDistIdx[i].idx] = -1;
+        }
+    }
+    free(rowCount); free(rowStart); free(rowIdx); free(vDistIdx);
+    return nDist;
+}
+
+/* ------------------------------------------------------------------ */
 /* Matcher: orbmatcher.cpp:1662-1677 and the best/second loop :208-232  */
 /* ------------------------------------------------------------------ */
 int orbo_descriptor_distance(const uint8_t a[32], const uint8_t b[32])

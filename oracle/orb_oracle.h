@@ -110,6 +110,15 @@ const uint8_t *orbo_blurred(const orbo_extractor *e, int level, int *w, int *h, 
 int orbo_candidates(const orbo_extractor *e, int level, const int **xs, const int **ys, const int **score);
 void orbo_set_tie_rule(orbo_extractor *e, int tie_rule);
 
+/* ---- OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705 (PARITY UNPINNED: restatement only) ----
+ * pyrL/pyrR[l] = level ROI pointers of the two extractors, lw/lh/lstride per level; uRight/depth get nl floats
+ * (-1 where there is no match).  Returns the number of matches before the median filter. */
+int orbo_stereo_matches(const orbo_keypoint *kl, const uint8_t *dl, int nl,
+                        const orbo_keypoint *kr, const uint8_t *dr, int nr,
+                        const uint8_t *const *pyrL, const uint8_t *const *pyrR, const int *lw, const int *lh,
+                        const size_t *lstride, const float *sf, const float *inv_sf,
+                        float mbf, float mb, float *uRight, float *depth);
+
 /* ---- matcher (orbmatcher.cpp:1662-1677, loop :208-232) ---- */
 int orbo_descriptor_distance(const uint8_t a[32], const uint8_t b[32]);
 void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,

@@ -87,6 +87,9 @@ def lib():
     L.orbo_descriptor_distance.restype = C.c_int
     L.orbo_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
     L.orbo_knn2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orbo_stereo_matches.restype = C.c_int
+    L.orbo_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + \
+                                     [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.orbo_knn2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 6
     L.orbo_knn2_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
@@ -201,6 +204,23 @@ def knn2_csr(q, t, offsets, indices):
     i1, d1, i2, d2 = (np.empty(nq, np.int32) for _ in range(4))
     lib().orbo_knn2_csr(_ptr(q), nq, _ptr(t), _ptr(offsets), _ptr(indices), _ptr(i1), _ptr(d1), _ptr(i2), _ptr(d2))
     return i1, d1, i2, d2
+
+
+def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
+    """OrbFrame::ComputeStereoMatches over two oracle extractors that just processed the left / right image."""
+    nlv = exL.nlevels
+    lvL = [np.ascontiguousarray(exL.level(l)) for l in range(nlv)]
+    lvR = [np.ascontiguousarray(exR.level(l)) for l in range(nlv)]
+    pl = (C.c_void_p * nlv)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * nlv)(*[a.ctypes.data for a in lvR])
+    lw = (C.c_int * nlv)(*[a.shape[1] for a in lvL]); lh = (C.c_int * nlv)(*[a.shape[0] for a in lvL])
+    ls = (C.c_size_t * nlv)(*[a.strides[0] for a in lvL])
+    sf = (C.c_float * nlv)(*exL.params.sf[:nlv]); isf = (C.c_float * nlv)(*exL.params.inv_sf[:nlv])
+    kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    u = np.empty(len(kl), np.float32); d = np.empty(len(kl), np.float32)
+    n = lib().orbo_stereo_matches(_ptr(kl), _ptr(dl), len(kl), _ptr(kr), _ptr(dr), len(kr), pl, pr, lw, lh, ls, sf, isf,
+                                  float(mbf), float(mb), _ptr(u), _ptr(d))
+    return u, d, n
 
 
 class Extractor:

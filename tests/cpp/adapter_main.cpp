@@ -4,6 +4,7 @@
 // results as flat binary for the pytest that compares them with the oracle.
 #include "orbextractor_b200.hpp"
 #include "orbmatcher_b200.hpp"
+#include "orbframe_stereo_b200.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,17 @@ int main(int argc, char **argv)
             std::vector<int> idx, d1, d2;
             hm.KnnMatch2(desc, idx, d1, d2);
             fwrite(idx.data(), 4, n, o); fwrite(d1.data(), 4, n, o); fwrite(d2.data(), 4, n, o);
+        }
+        // stereo adapter: the image against itself -> every match has zero disparity (clamped to 0.01, orbframe.cpp:679-683)
+        {
+            OrbExtractor exR(nf, 1.2f, nl, 20, 7);
+            std::vector<cv::KeyPoint> keysR; cv::Mat descR;
+            exR.ExtractFeatures(image, keysR, descR);
+            std::vector<float> uR, depth;
+            int nm = orbslam_b200::ComputeStereoMatches(ex, exR, 400.0f, 0.0f, uR, depth);
+            int nu = (int)uR.size();
+            fwrite(&nm, 4, 1, o); fwrite(&nu, 4, 1, o);
+            fwrite(uR.data(), 4, nu, o); fwrite(depth.data(), 4, nu, o);
         }
         fclose(o);
     } catch (const std::exception &e) {

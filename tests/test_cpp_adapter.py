@@ -64,3 +64,10 @@ def test_adapter_end_to_end(tmp_path, oracle):
     oi, o1, o2 = oracle.knn2(desc, desc)
     assert np.array_equal(idx, oi) and np.array_equal(d1, o1) and np.array_equal(d2, o2)
     assert (d1 == 0).all()
+    nm, nu = struct.unpack_from("<ii", b, o); o += 8
+    uR = np.frombuffer(b, np.float32, nu, o); o += 4 * nu
+    dep = np.frombuffer(b, np.float32, nu, o); o += 4 * nu
+    oex2 = oracle.Extractor(nf, 1.2, nl); oex2.extract(img)
+    ou, od, on = oracle.stereo_matches(oex, oex2, okps, odesc, okps, odesc, 400.0, 0.0)
+    assert nu == n and nm == on and nm > 0        # (identical images: all rejected by the median filter, as in the reference)
+    assert np.array_equal(uR.view(np.uint32), ou.view(np.uint32)) and np.array_equal(dep.view(np.uint32), od.view(np.uint32))

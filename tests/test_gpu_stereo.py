@@ -1,0 +1,54 @@
+"""GPU parity of orbx_stereo_match (OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705) against the
+oracle restatement.  (The oracle for this "next" row is a restatement only -- parity unpinned, see DESIGN.md.)"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_pair(oracle, l, r, nf, nl, mbf, mb):
+    eL = oracle.Extractor(nf, 1.2, nl); eR = oracle.Extractor(nf, 1.2, nl)
+    kl, dl = eL.extract(l); kr, dr = eR.extract(r)
+    return oracle.stereo_matches(eL, eR, kl, dl, kr, dr, mbf, mb), len(kl)
+
+
+@pytest.mark.parametrize("mb", [0.0, 0.5372])          # 0: the reference's first-frame value (maxD = +inf)
+def test_two_handles_like_orbframe(oracle, mb):
+    import orbx
+    w, h, nf, nl, mbf = 1241, 376, 2000, 8, 386.1448
+    for seed in (2000, 2001):
+        l, r = synth.stereo_pair(w, h, seed)
+        exL = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h)
+        exR = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h)
+        exL.extract(l); exR.extract(r)
+        u, d, nm = orbx.stereo_match(exL, 0, exR, 0, mbf, mb)
+        (ou, od, on), n_left = _oracle_pair(oracle, l, r, nf, nl, mbf, mb)
+        assert len(u) == n_left and nm == on and on > 50
+        assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)), f"uRight differs at {np.flatnonzero(u != ou)[:5]}"
+        assert np.array_equal(d.view(np.uint32), od.view(np.uint32))
+        exL.close(); exR.close()
+
+
+def test_one_handle_batch_of_pairs(oracle):
+    import orbx
+    w, h, nf, nl, mbf = 640, 360, 1000, 6, 300.0
+    frames = synth.stereo_batch(9, w, h, 2)              # L0 R0 L1 R1
+    ex = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h, max_batch=4)
+    ex.extract_batch(frames)
+    for p in range(2):
+        u, d, nm = orbx.stereo_match(ex, 2 * p, ex, 2 * p + 1, mbf, 0.0)
+        (ou, od, on), _ = _oracle_pair(oracle, frames[2 * p], frames[2 * p + 1], nf, nl, mbf, 0.0)
+        assert nm == on and np.array_equal(u.view(np.uint32), ou.view(np.uint32)) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
+    ex.close()
+
+
+def test_no_matches_is_not_an_error(oracle):
+    import orbx
+    w, h = 640, 360
+    ex = orbx.Extractor(500, 1.2, 4, max_width=w, max_height=h, max_batch=2)
+    ex.extract_batch([synth.scene_s1(w, h, 1), synth.scene_s3(w, h, "const")])   # right image has no keypoints
+    u, d, nm = orbx.stereo_match(ex, 0, ex, 1, 300.0, 0.0)
+    assert nm == 0 and (u == -1).all() and (d == -1).all()
+    ex.close()
