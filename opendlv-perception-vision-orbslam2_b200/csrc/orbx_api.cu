@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -74,7 +75,8 @@ struct orbx_extractor {
     cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
     std::vector<cudaEvent_t> evChunk;
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
-    DevBuf<OrbxTensorMaps> dTmaps;   // ... and where the kernels read them
+    OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (96 bytes x hCell+6 rows)
+    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes: where the kernels read them
     const uint8_t *tmapBase = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
     DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
@@ -204,6 +206,7 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         v.hCell = (int)ceilf(height / v.nRows);
         if (v.wCell > 60 || v.hCell > 60 || (long long)v.nCols * v.nRows >= 65536) return fail(h, ORBX_ERR_SHAPE, "FAST grid outside supported range");
         v.cellBase = (int)cells.size();
+        v.winH = v.hCell + 6;
         for (int i = 0; i < v.nRows; i++) {
             const int iniY = ORBX_MINB + i * v.hCell;
             int maxY = iniY + v.hCell + 6;
@@ -221,7 +224,9 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
                 cell.ci = (uint16_t)i; cell.cj = (uint16_t)j;
                 {
                     const int wEff = std::max((int)cell.w - 6, 1);
-                    cell.mQ = (uint16_t)(32768 / ((wEff + 3) >> 2) + 1);
+                    const int B0 = ((iniX - 1) & 15) + 4;      // shared byte of the first tested pixel (TMA box is 16-byte aligned)
+                    const int nQ = ((B0 + wEff - 1) >> 2) - (B0 >> 2) + 1;
+                    cell.mQ = (uint16_t)(32768 / nQ + 1);
                     cell.mG = (uint16_t)(32768 / (((int)cell.w + 1 + 15) >> 4) + 1);
                 }
                 cells.push_back(cell);
@@ -328,16 +333,21 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
+        cuuint32_t boxF[3] = {96, (cuuint32_t)v.winH, 1};             // FW_P x window rows of k_fast_cells
+        CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxF, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
             char msg[96];
-            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d / %d)", l, (int)r, (int)r2);
             return fail(h, ORBX_ERR_CUDA, msg);
         }
     }
-    CK(h->dTmaps.ensure(1));
+    CK(h->dTmaps.ensure(2));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->stream2));
     CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dTmaps.p + 1, &h->tmapsFast, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     h->tmapBase = h->dPyr.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
     return ORBX_OK;
 }
@@ -389,14 +399,14 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     const int cells0 = L.lv[0].nCells;
     CK(cudaEventRecord(h->evFork, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    launch_fast(pyr, L, h->dCells.p, 0, cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, h->stream2);
+    launch_fast(h->dTmaps.p[1].m, f0, L, h->dCells.p, 0, cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, h->stream2);
     CK(cudaEventRecord(h->evFast0, h->stream2));
     for (int l = 1; l < L.nlevels; l++) launch_resize(pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
     CK(cudaEventRecord(h->evPyr, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evPyr, 0));
     launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
     CK(cudaEventRecord(h->evJoin, h->stream2));
-    launch_fast(pyr, L, h->dCells.p, cells0, L.totalCells - cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
+    launch_fast(h->dTmaps.p[1].m, f0, L, h->dCells.p, cells0, L.totalCells - cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
     CK(cudaStreamWaitEvent(st, h->evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
     CK(cudaStreamWaitEvent(st, h->evJoin, 0));
@@ -553,6 +563,8 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         pitch < (size_t)width || kp_cap < 1)
         return fail(h, ORBX_ERR_ARG, "bad argument");
     for (int f = 0; f < batch; f++) if (!imgs[f]) return fail(h, ORBX_ERR_ARG, "null image pointer");
+    struct timespec tsB;
+    clock_gettime(CLOCK_MONOTONIC, &tsB);
     CK(cudaSetDevice(h->cfg.device));
     int rc = setGeometry(h, width, height);
     if (rc != ORBX_OK) return rc;
@@ -616,6 +628,9 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         CK(cudaEventRecord(h->evChunk[2 * c], sOut));   // reuse: the H2D event of this chunk has been consumed
     }
     h->lastBatch = batch;
+    static const bool trace = getenv("ORBX_TRACE") != nullptr;
+    struct timespec tsE;
+    if (trace) clock_gettime(CLOCK_MONOTONIC, &tsE);
     int status = ORBX_OK;
     for (int c = 0; c < nChunks; c++) {
         const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
@@ -638,6 +653,13 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     }
     CK(cudaStreamSynchronize(sOut));
     CK(cudaStreamSynchronize(sK));
+    if (trace) {
+        struct timespec tsD;
+        clock_gettime(CLOCK_MONOTONIC, &tsD);
+        fprintf(stderr, "[orbx] batch %d: enqueue %.3f ms, drain %.3f ms\n", batch,
+                (tsE.tv_sec - tsB.tv_sec) * 1e3 + (tsE.tv_nsec - tsB.tv_nsec) * 1e-6,
+                (tsD.tv_sec - tsE.tv_sec) * 1e3 + (tsD.tv_nsec - tsE.tv_nsec) * 1e-6);
+    }
     return status;
 }
 
@@ -767,7 +789,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
-        launch_fast(h->dPyr.p, L, h->dCells.p, 0, L.totalCells, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
+        launch_fast(h->dTmaps.p[1].m, 0, L, h->dCells.p, 0, L.totalCells, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
         CK(cudaEventRecord(ev[2], st));
         CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
         CK(cudaEventRecord(ev[3], st));

@@ -19,6 +19,7 @@ struct OrbxLevel {
     // gridded FAST, orbextractor.cpp:914-928
     int nCols, nRows, wCell, hCell;
     int cellBase, nCells; // processed cells of this level inside the cell table
+    int winH;            // rows of the FAST window box (hCell + 6): height of this level's TMA box
     // DistributeOctTree, orbextractor.cpp:684-699
     int W, H;            // maxX-minX, maxY-minY
     int nIni, hX, quota;

@@ -354,8 +354,7 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 // order (cells row-major, raster inside a cell, orbextractor.cpp:930-968).
 //
 // Stages inside the CTA:
-//   0  the (w+6)x(h+6) window is staged in shared memory with aligned 32-bit loads, funnel-shifted
-//      so that the first tested pixel sits on a 4-byte boundary
+//   0  the (w+6)x(h+6) window is fetched into shared memory by one TMA box load (cp.async.bulk.tensor)
 //   1  quick reject on 4 pixels per thread (packed bytes): a FAST-9 arc always contains ring
 //      pixel k or k+8, so |I(p) - I(ring_k)| > t must hold for k in {0,8} and for k in {4,12};
 //      survivors (~8 % of pixels) are compacted into a list
@@ -395,12 +394,13 @@ __device__ __forceinline__ void fast_ring_diffs(const uint8_t *c, int (&d)[16])
 }
 
 __global__ void __launch_bounds__(128)
-k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout L,
+k_fast_cells(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
              const OrbxCell *__restrict__ cells, uint32_t *__restrict__ cnt,
              unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
              int *__restrict__ dbgCount, int dbgCap)
 {
-    __shared__ __align__(16) uint8_t win[66 * FW_P];
+    __shared__ __align__(128) uint8_t win[66 * FW_P];
+    __shared__ __align__(8) uint64_t bar;
     __shared__ __align__(16) uint8_t smap[62 * FS_P];
     __shared__ uint16_t cand[60 * 60];
     __shared__ uint16_t corner[60 * 60];
@@ -414,49 +414,49 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     const int tid = threadIdx.x;
     const int th = L.minTh;
 
-    // ---- stage 0: window column c lives at shared byte (c + 1): tested pixel xIn at byte xIn + 4.
-    // One item = 16 destination bytes of one row: five aligned source words, four funnel shifts.
+    // ---- stage 0: TMA fetches the window (box = 96 bytes x the level's window height) from the level's
+    // tensor map.  The box must start 16-byte aligned in x, so window column c lands at shared byte
+    // s16 + 1 + c with s16 = (x0 - 1) & 15, and tested pixel xIn at byte B0 + xIn, B0 = s16 + 4.
+    const int s16 = ((int)cell.x0 - 1) & 15, B0 = s16 + 4;
     {
-        const uint8_t *base = pyr + (size_t)frame * L.slab + lv.off + (size_t)cell.y0 * lv.pitch + (int)cell.x0 - 1;
-        const int ng = ((int)cell.w + 1 + 15) >> 4;          // 16-byte groups per row, <= 5
-        const unsigned M = cell.mG;                          // 32768 / ng + 1 (host): i / ng == (i * M) >> 15
-        const int sh = (int)((uintptr_t)base & 3) * 8;       // pitch is a multiple of 4: the same shift for every row
-        const uint32_t *base4 = (const uint32_t *)((uintptr_t)base & ~(uintptr_t)3);
-        const int pitch4 = lv.pitch >> 2;
-        for (int i = tid; i < (int)cell.h * ng; i += 128) {
-            const int r = (i * M) >> 15, g = i - r * ng;
-            const uint32_t *p = base4 + (size_t)r * pitch4 + 4 * g;
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
-            uint4 o;
-            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
-            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
-            ((uint4 *)win)[r * (FW_P / 16) + g] = o;
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            ncand = 0; ncorner = 0;
         }
+        __syncthreads();
+        if (tid == 0)
+            tma_load_tile_3d(win, maps + cell.level, (int)cell.x0 - 1 - s16, (int)cell.y0, f0 + frame, &bar, FW_P * lv.winH);
         for (int i = tid; i < (hEff + 2) * (FS_P / 16); i += 128) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { ncand = 0; ncorner = 0; }
+        mbar_wait(&bar, 0);
     }
     __syncthreads();
 
     // ---- stage 1: packed quick reject, 4 pixels per thread
     {
-        const int nQ = (wEff + 3) >> 2, items = nQ * hEff;
+        // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
+        const int wq0 = B0 >> 2, wqL = (B0 + wEff - 1) >> 2;
+        const int nQ = wqL - wq0 + 1, items = nQ * hEff;
         const unsigned M = cell.mQ;                          // 32768 / nQ + 1 (host)
+        const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
+        const int nLast = ((B0 + wEff - 1) & 3) + 1;
+        const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
         const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
         for (int it = tid; it < items; it += 128) {
             const int yIn = (it * M) >> 15, q = it - yIn * nQ;
-            const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + q;
-            const uint32_t W0 = rw[0], C = rw[1], W2 = rw[2];
-            const uint32_t U = rw[1 + 3 * (FW_P / 4)], D = rw[1 - 3 * (FW_P / 4)];
+            const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + wq0 + q;
+            const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
+            const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
             const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
             const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
             const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
             const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
             uint32_t pass = X & Y & 0x80808080u;
-            const int left = wEff - 4 * q;                        // valid pixels in this quad
-            if (left < 4) pass &= (1u << (8 * left)) - 1u;
+            if (q == 0) pass &= maskFirst;
+            if (q == nQ - 1) pass &= maskLast;
             if (pass) {
                 int pos = atomicAdd(&ncand, __popc(pass));
-                const int e = yIn << 6 | (q << 2);
+                const int e = (yIn << 6) + 4 * (wq0 + q) - B0;      // + j = yIn << 6 | xIn for the valid pixels j of the quad
                 if (pass & 0x80u) cand[pos++] = (uint16_t)e;
                 if (pass & 0x8000u) cand[pos++] = (uint16_t)(e + 1);
                 if (pass & 0x800000u) cand[pos++] = (uint16_t)(e + 2);
@@ -473,7 +473,7 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     for (int i = tid; i < nc; i += 128) {
         const int e = cand[i];
         const int yIn = e >> 6, xIn = e & 63;
-        const uint8_t *c = &win[(yIn + 3) * FW_P + xIn + 4];
+        const uint8_t *c = &win[(yIn + 3) * FW_P + xIn + B0];
         const int v = c[0], hi = v + th, lo = v - th;
         unsigned mb = 0, md = 0;
 #define ORBX_RING(off) { const int r_ = c[off]; mb = __funnelshift_l((unsigned)(hi - r_), mb, 1); md = __funnelshift_l((unsigned)(r_ - lo), md, 1); }
@@ -495,7 +495,7 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
         const int e = corner[i];
         const int yIn = e >> 6, xIn = e & 63;
         int d[16];
-        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + 4], d);
+        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + B0], d);
         smap[(yIn + 1) * FS_P + xIn + 1] = (uint8_t)fast_score16(d);
     }
     __syncthreads();
@@ -548,12 +548,12 @@ k_fast_cells(const uint8_t *__restrict__ pyr, const __grid_constant__ OrbxLayout
     }
 }
 
-void launch_fast(const uint8_t *pyr, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount, uint32_t *cnt,
-                 unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st)
+void launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount,
+                 uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st)
 {
     if (cellCount <= 0) return;
     dim3 grid(cellCount, batch);
-    k_fast_cells<<<grid, 128, 0, st>>>(pyr, L, cells + cellBegin, cnt, best, dbg, dbgCount, dbgCap);
+    k_fast_cells<<<grid, 128, 0, st>>>(maps, f0, L, cells + cellBegin, cnt, best, dbg, dbgCount, dbgCap);
 }
 
 // ------------------------------------------------------------------------------------------
