@@ -76,7 +76,8 @@ struct orbx_extractor {
     std::vector<cudaEvent_t> evChunk;
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
     OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (96 bytes x hCell+6 rows)
-    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes: where the kernels read them
+    OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
+    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes, [2] resize boxes: where the kernels read them
     const uint8_t *tmapBase = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
     DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
@@ -337,17 +338,22 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxF, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+        cuuint32_t boxR[3] = {192, 48, 1};                             // RS_BOXW x RS_BOXH of k_resize
+        CUresult r3 = encode(&h->tmapsResize.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxR, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) {
             char msg[96];
-            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d / %d)", l, (int)r, (int)r2);
+            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d / %d / %d)", l, (int)r, (int)r2, (int)r3);
             return fail(h, ORBX_ERR_CUDA, msg);
         }
     }
-    CK(h->dTmaps.ensure(2));
+    CK(h->dTmaps.ensure(3));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->stream2));
     CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dTmaps.p + 1, &h->tmapsFast, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dTmaps.p + 2, &h->tmapsResize, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     h->tmapBase = h->dPyr.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
     return ORBX_OK;
 }
@@ -401,7 +407,7 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
     launch_fast(h->dTmaps.p[1].m, f0, L, h->dCells.p, 0, cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, h->stream2);
     CK(cudaEventRecord(h->evFast0, h->stream2));
-    for (int l = 1; l < L.nlevels; l++) launch_resize(pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
+    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
     CK(cudaEventRecord(h->evPyr, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evPyr, 0));
     launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
@@ -434,7 +440,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     if (!cfg || !out) return ORBX_ERR_ARG;
     *out = nullptr;
     if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
-        cfg->scale_factor > 1.85f ||   /* k_resize keeps at most 16 source rows per 8-row strip */
+        cfg->scale_factor > 1.35f ||   /* k_resize: the source region of a 128 x 32 tile (128 s + 17 columns) must fit its 192 x 48 TMA box */
         cfg->min_th_fast < 1 || cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
         cfg->max_batch < 1 || cfg->max_width < 1 || cfg->max_height < 1)
         return ORBX_ERR_ARG;
@@ -785,7 +791,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(ev[0], st));
-        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
+        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, 0, h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));

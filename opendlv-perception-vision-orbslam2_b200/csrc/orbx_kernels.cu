@@ -109,18 +109,40 @@ void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch,
     k_copy_level0<<<grid, block, 0, st>>>(src, frameStride, srcPitch, srcEnd, pyr, L.slab, l0.off, l0.pitch, l0.w, l0.h);
 }
 
+// ---- TMA / mbarrier helpers (cp.async.bulk.tensor box loads completing on an mbarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar, uint32_t bytes)
+{
+    const uint32_t b = smem_u32(bar), d = smem_u32(smemDst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    const uint32_t b = smem_u32(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(b), "r"(phase) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // pyramid resize, 11-bit fixed-point bilinear (A.1): level l from level l-1.
-// One thread owns 4 adjacent output columns (one 32-bit word per output row) and walks RS_ROWS
-// output rows downwards.  The horizontally interpolated source rows
-//   h(sy)[x] = S[sy][sx]*c0 + S[sy][sx+1]*c1        (one dp2a per pixel, coefficients packed)
-// stay in registers and are reused between consecutive output rows (at scale 1.2 consecutive
-// outputs share a source row), so every source row is interpolated once per strip.  Row base
-// addresses are uniform across the CTA; per-thread addressing is a 32-bit column offset.
+// CTA = 128 x 32 output tile.  One elected thread fetches the source region of the tile -- at most
+// 192 x 48 bytes at scale factors up to 1.4 -- with one TMA box load (cp.async.bulk.tensor, box start
+// 16-byte aligned in x); the 128 threads then work from shared memory: each owns 4 adjacent output
+// columns (one 32-bit store per output row) and walks 8 output rows.  Horizontally interpolated
+// source rows h(sy)[x] = S[sy][sx]*c0 + S[sy][sx+1]*c1 (one dp2a per pixel, coefficients packed) are
+// kept in registers and reused between consecutive output rows.
 // ------------------------------------------------------------------------------------------
+#define RS_TW 128
+#define RS_TH 32
 #define RS_ROWS 8
+#define RS_BOXW 192
+#define RS_BOXH 48
 
-__device__ __forceinline__ void resize_hrow(const uint8_t *__restrict__ rowp, const int (&sx0)[4], const int (&sx1)[4],
+__device__ __forceinline__ void resize_hrow(const uint8_t *rowp, const int (&sx0)[4], const int (&sx1)[4],
                                             const uint32_t (&cc)[4], int (&hv)[4])
 {
 #pragma unroll
@@ -130,42 +152,53 @@ __device__ __forceinline__ void resize_hrow(const uint8_t *__restrict__ rowp, co
     }
 }
 
-__global__ void __launch_bounds__(64)
-k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, int dstOff, int dstPitch, int dw, int dh,
-         const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
+__global__ void __launch_bounds__(128)
+k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ pyr, long long slab, int dstOff, int dstPitch,
+         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
 {
-    __shared__ int4 sy[RS_ROWS];
+    __shared__ __align__(128) uint8_t tileS[RS_BOXH * RS_BOXW];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int4 sy[RS_TH];
     const int f = blockIdx.z;
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y0 = blockIdx.y * RS_ROWS;
-    if (threadIdx.x < RS_ROWS) sy[threadIdx.x] = __ldg(&ytab[min(y0 + (int)threadIdx.x, dh - 1)]);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
+    if (tid < RS_TH) sy[tid] = __ldg(&ytab[min(ty0 + tid, dh - 1)]);          // {sy0, sy1, b0, b1}
+    const int xs = __ldg(&xtab[tx0]).x & ~15;                                  // box origin: first source column, 16-aligned
+    const int ys = __ldg(&ytab[ty0]).x;                                        //             first source row
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    if (x0 >= dw) return;
-    const uint8_t *src = pyr + (size_t)f * slab + srcOff;          // uniform
-    uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch;
+    if (tid == 0) tma_load_tile_3d(tileS, srcMap, xs, ys, f0 + f, &bar, RS_BOXH * RS_BOXW);
+    const int x0 = tx0 + threadIdx.x * 4;
+    const int y0 = ty0 + threadIdx.y * RS_ROWS;
     int sx0[4], sx1[4];
     uint32_t cc[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int4 t = __ldg(&xtab[min(x0 + k, dw - 1)]);
-        sx0[k] = t.x; sx1[k] = t.y; cc[k] = (uint32_t)t.z;
+        sx0[k] = t.x - xs; sx1[k] = t.y - xs; cc[k] = (uint32_t)t.z;
     }
+    mbar_wait(&bar, 0);
+    if (x0 >= dw || y0 >= dh) return;
+    uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch + x0;
     const int yEnd = min(RS_ROWS, dh - y0);
     int rb = -1;
     int ha[4], hb[4] = {0, 0, 0, 0};
     for (int r = 0; r < yEnd; r++) {
-        const int4 ty = sy[r];                                     // {sy0, sy1, b0, b1}, uniform across the CTA
+        const int4 ty = sy[threadIdx.y * RS_ROWS + r];                         // uniform across the warp
         if (ty.x == rb) {
 #pragma unroll
             for (int k = 0; k < 4; k++) ha[k] = hb[k];
         } else {
-            resize_hrow(src + (size_t)ty.x * srcPitch, sx0, sx1, cc, ha);
+            resize_hrow(tileS + (ty.x - ys) * RS_BOXW, sx0, sx1, cc, ha);
         }
         if (ty.y == ty.x) {
 #pragma unroll
             for (int k = 0; k < 4; k++) hb[k] = ha[k];
         } else {
-            resize_hrow(src + (size_t)ty.y * srcPitch, sx0, sx1, cc, hb);
+            resize_hrow(tileS + (ty.y - ys) * RS_BOXW, sx0, sx1, cc, hb);
         }
         rb = ty.y;
         uint32_t out = 0;
@@ -174,17 +207,16 @@ k_resize(uint8_t *__restrict__ pyr, long long slab, int srcOff, int srcPitch, in
             const int v = (((ty.z * (ha[k] >> 4)) >> 16) + ((ty.w * (hb[k] >> 4)) >> 16) + 2) >> 2;
             out |= (uint32_t)(v & 255) << (8 * k);
         }
-        *(uint32_t *)(dst + (size_t)r * dstPitch + x0) = out;       // bytes past dw land in the pitch padding
+        *(uint32_t *)(dst + (size_t)r * dstPitch) = out;                        // bytes past dw land in the pitch padding
     }
 }
 
-void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st)
+void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st)
 {
-    const OrbxLevel &s = L.lv[level - 1], &d = L.lv[level];
-    dim3 block(64);
-    dim3 grid((d.w + 255) / 256, (d.h + RS_ROWS - 1) / RS_ROWS, batch);
-    k_resize<<<grid, block, 0, st>>>(pyr, L.slab, s.off, s.pitch, d.off, d.pitch, d.w, d.h,
-                                     tabs + d.xtabOff, tabs + d.ytabOff);
+    const OrbxLevel &d = L.lv[level];
+    dim3 grid((d.w + RS_TW - 1) / RS_TW, (d.h + RS_TH - 1) / RS_TH, batch);
+    k_resize<<<grid, dim3(32, 4), 0, st>>>(srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
+                                           tabs + d.xtabOff, tabs + d.ytabOff);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -231,23 +263,6 @@ __device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint3
 // ------------------------------------------------------------------------------------------
 #define BL_BOXW 160   // bytes: 16 left + 128 + 16 right: TMA needs the box start 16-byte aligned in the inner dimension
 #define BL_BOXH 134   // rows: 3 + 128 + 3
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar, uint32_t bytes)
-{
-    const uint32_t b = smem_u32(bar), d = smem_u32(smemDst);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
-{
-    const uint32_t b = smem_u32(bar);
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
-                 ::"r"(b), "r"(phase) : "memory");
-}
 
 __global__ void __launch_bounds__(128)
 k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,

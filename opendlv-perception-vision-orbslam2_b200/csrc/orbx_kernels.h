@@ -11,7 +11,7 @@ struct orbx_keypoint_pod { float x, y, size, angle, response; int32_t octave, cl
 
 void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch, uint8_t *pyr,
                         const OrbxLayout &L, int batch, cudaStream_t st);
-void launch_resize(uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st);
+void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st);
 void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
                  const int taps[7], int f0, int batch, cudaStream_t st);
 void launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount,
