@@ -876,6 +876,7 @@ struct DescUmax { int u[16]; };
 #define DS_WARPS 4          // warps per CTA
 #define DS_PER_WARP 8       // keypoint slots handled by one warp, one after the other
 #define DS_PP 40            // shared patch pitch (bytes): up to 10 aligned words per row
+#define DS_BUF (37 * DS_PP + 32 * DS_PP)   // one stage: blurred 37 rows + unblurred 31(+1) rows
 
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
 {
@@ -884,13 +885,21 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
     return d;
 }
 
+__device__ __forceinline__ void cp_async4(void *smemDst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smemDst)), "l"(gsrc) : "memory");
+}
+
+struct DescSlot { int valid, cx, cy, level, out, score; };
+
 __global__ void __launch_bounds__(DS_WARPS * 32)
 k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
            const int2 *__restrict__ slots, const int *__restrict__ lvlCount, DescUmax um,
            orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts)
 {
-    __shared__ __align__(16) uint8_t patchB[DS_WARPS][37 * DS_PP];   // blurred 37x37 patch (rBRIEF samples)
-    __shared__ __align__(16) uint8_t patchA[DS_WARPS][32 * DS_PP];   // unblurred 31x31 patch (IC_Angle)
+    // per warp two stages of {blurred 37x37 patch (rBRIEF samples), unblurred 31x31 patch (IC_Angle)}: the
+    // patches of the warp's next keypoint stream in (cp.async) while the current one is being processed
+    __shared__ __align__(16) uint8_t patch[DS_WARPS][2][DS_BUF];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     // this lane's 16 pattern points (descriptor byte `lane`), kept in registers across its slots
@@ -937,95 +946,113 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
     const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
     const int rr10 = lane / 10, wi10 = lane - rr10 * 10;      // staging role: 3 rows x 10 words per pass
 
-    for (int j = 0; j < DS_PER_WARP; j++) {
+    // resolve slot j of this warp and start streaming its two patches into stage `buf`
+    auto issue = [&](int j, int buf) -> DescSlot {
+        DescSlot s; s.valid = 0; s.cx = s.cy = s.level = s.out = s.score = 0;
         const int slot = (blockIdx.x * DS_PER_WARP + j) * DS_WARPS + warp;     // warp-uniform
-        if (slot >= L.slotsPerFrame) break;
-        // level = last l with slotBase[l] <= slot
-        const unsigned ge = __ballot_sync(0xffffffffu, slot >= myBase);
+        if (j >= DS_PER_WARP || slot >= L.slotsPerFrame) return s;
+        const unsigned ge = __ballot_sync(0xffffffffu, slot >= myBase);        // level = last l with slotBase[l] <= slot
         const int level = 31 - __clz((int)ge);
         const OrbxLevel &lv = L.lv[level];
         const int i = slot - lv.slotBase;
         const int cntL = __shfl_sync(0xffffffffu, myCnt, level);
-        if (i >= cntL) continue;
         const int before = __shfl_sync(0xffffffffu, incl - myCnt, level);
+        if (i >= cntL) return s;
         const int2 sl = slots[(size_t)frame * L.slotsPerFrame + slot];
-        const int cx = (sl.x & 0xffff) + ORBX_MINB, cy = (sl.x >> 16) + ORBX_MINB; // :984-985
-        const int pitch = lv.pitch;
-        const size_t lbase = (size_t)frame * L.slab + lv.off;
-
-        // ---- stage both patches with aligned word loads (3 rows x 10 words per pass)
-        const int xsB = cx - 18, xaB = xsB & ~3, shB = xsB - xaB;     // blurred: 37 rows from cy-18
-        const int xsA = cx - 15, xaA = xsA & ~3, shA = xsA - xaA;     // unblurred: 31 rows from cy-15
+        s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
+        s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
         if (lane < 30) {
-            const uint8_t *gB = blur + lbase + (size_t)(cy - 18 + rr10) * pitch + xaB + 4 * wi10;
-            const uint8_t *gA = pyr + lbase + (size_t)(cy - 15 + rr10) * pitch + xaA + 4 * wi10;
-            uint32_t *sB = (uint32_t *)patchB[warp] + rr10 * (DS_PP / 4) + wi10;
-            uint32_t *sA = (uint32_t *)patchA[warp] + rr10 * (DS_PP / 4) + wi10;
-            const int step = 3 * pitch;
+            const int pitch = lv.pitch;
+            const size_t lbase = (size_t)frame * L.slab + lv.off;
+            const int xaB = (s.cx - 18) & ~3, xaA = (s.cx - 15) & ~3;
+            const uint8_t *gB = blur + lbase + (size_t)(s.cy - 18 + rr10) * pitch + xaB + 4 * wi10;
+            const uint8_t *gA = pyr + lbase + (size_t)(s.cy - 15 + rr10) * pitch + xaA + 4 * wi10;
+            uint8_t *sB = patch[warp][buf] + (rr10 * DS_PP + 4 * wi10);
+            uint8_t *sA = sB + 37 * DS_PP;
+            const size_t step = (size_t)3 * pitch;
 #pragma unroll
             for (int r0 = 0; r0 < 33; r0 += 3) {
-                if (r0 + rr10 < 31) sA[r0 * (DS_PP / 4)] = __ldg((const uint32_t *)(gA + (size_t)(r0 / 3) * step));
+                if (r0 + rr10 < 31) cp_async4(sA + r0 * DS_PP, gA);
+                gA += step;
             }
 #pragma unroll
             for (int r0 = 0; r0 < 39; r0 += 3) {
-                if (r0 + rr10 < 37) sB[r0 * (DS_PP / 4)] = __ldg((const uint32_t *)(gB + (size_t)(r0 / 3) * step));
+                if (r0 + rr10 < 37) cp_async4(sB + r0 * DS_PP, gB);
+                gB += step;
             }
         }
-        __syncwarp();
+        return s;
+    };
 
-        // ---- IC_Angle: lane = patch row v; 32 bytes of the row (cols cx-15 .. cx+16) against the weights
-        int m10 = 0, rowsum = 0;
-        if (lane < 31) {
-            const uint32_t *rw = (const uint32_t *)patchA[warp] + lane * (DS_PP / 4);
-            uint32_t W[9];
+    DescSlot cur = issue(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int j = 0; j < DS_PER_WARP; j++) {
+        const int buf = j & 1;
+        const DescSlot nxt = issue(j + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group has landed
+        __syncwarp();
+        if (cur.valid) {
+            const OrbxLevel &lv = L.lv[cur.level];
+            const uint8_t *pB = patch[warp][buf], *pA = pB + 37 * DS_PP;
+            const int shB = (cur.cx - 18) & 3, shA = (cur.cx - 15) & 3;
+            // ---- IC_Angle: lane = patch row v; 32 bytes of the row (cols cx-15 .. cx+16) against the weights
+            int m10 = 0, rowsum = 0;
+            if (lane < 31) {
+                const uint32_t *rw = (const uint32_t *)pA + lane * (DS_PP / 4);
+                uint32_t W[9];
 #pragma unroll
-            for (int k = 0; k < 9; k++) W[k] = rw[k];
-            const int sh = shA * 8;
+                for (int k = 0; k < 9; k++) W[k] = rw[k];
+                const int sh = shA * 8;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t B = __funnelshift_r(W[k], W[k + 1], sh);
+                    m10 = dp4a_u8_s8(B, wu[k], m10);
+                    rowsum = dp4a_u8_s8(B, w1[k], rowsum);
+                }
+            }
+            int m01 = (lane - 15) * rowsum;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            }
+            const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+            // ---- rBRIEF: lane = descriptor byte, 16 rotated samples each, gathered from shared memory.
+            // cvRound = round-half-even: adding 1.5 * 2^23 leaves exactly that integer in the low mantissa bits.
+            const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
+            float sa, ca;
+            glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
+            const float a = ca, b = sa;
+            const float MAGIC = 12582912.0f;                       // 0x4B400000
+            const uint8_t *center = pB + 18 * DS_PP + shB + 18;
+            const unsigned BIAS = 0x4B400000u * (unsigned)(DS_PP + 1);   // both magic offsets, removed in one subtraction (mod 2^32)
+            int val = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const uint32_t B = __funnelshift_r(W[k], W[k + 1], sh);
-                m10 = dp4a_u8_s8(B, wu[k], m10);
-                rowsum = dp4a_u8_s8(B, w1[k], rowsum);
+                int t[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const float x = px[2 * k + e], y = py[2 * k + e];
+                    const int row = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)), MAGIC));
+                    const int col = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)), MAGIC));
+                    t[e] = center[(int)((unsigned)row * (unsigned)DS_PP + (unsigned)col - BIAS)];
+                }
+                val |= (t[0] < t[1]) << k;
+            }
+            desc[((size_t)frame * L.kpStride + cur.out) * 32 + lane] = (uint8_t)val;
+            if (lane == 0) {
+                orbx_keypoint_pod kp;
+                float fx = (float)cur.cx, fy = (float)cur.cy;
+                if (cur.level != 0) { fx = __fmul_rn(fx, lv.sf); fy = __fmul_rn(fy, lv.sf); }
+                kp.x = fx; kp.y = fy; kp.size = (float)lv.kpSize; kp.angle = angle; kp.response = (float)cur.score;
+                kp.octave = cur.level; kp.class_id = -1;
+                kps[(size_t)frame * L.kpStride + cur.out] = kp;
             }
         }
-        int m01 = (lane - 15) * rowsum;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-        // ---- rBRIEF: lane = descriptor byte, 16 rotated samples each, gathered from shared memory
-        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.0);
-        float sa, ca;
-        glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
-        const float a = ca, b = sa;
-        const uint8_t *center = patchB[warp] + 18 * DS_PP + shB + 18;
-        int val = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int t[2];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const float x = px[2 * k + e], y = py[2 * k + e];
-                const int row = __float2int_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)));
-                const int col = __float2int_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)));
-                t[e] = center[row * DS_PP + col];
-            }
-            val |= (t[0] < t[1]) << k;
-        }
-        __syncwarp();     // the patches are reused by this warp's next slot
-        const int o = before + i;
-        desc[((size_t)frame * L.kpStride + o) * 32 + lane] = (uint8_t)val;
-        if (lane == 0) {
-            orbx_keypoint_pod kp;
-            float fx = (float)cx, fy = (float)cy;
-            if (level != 0) { fx = __fmul_rn(fx, lv.sf); fy = __fmul_rn(fy, lv.sf); }
-            kp.x = fx; kp.y = fy; kp.size = (float)lv.kpSize; kp.angle = angle; kp.response = (float)sl.y;
-            kp.octave = level; kp.class_id = -1;
-            kps[(size_t)frame * L.kpStride + o] = kp;
-        }
+        __syncwarp();     // stage `buf` is refilled two iterations from now
+        cur = nxt;
     }
 }
 
