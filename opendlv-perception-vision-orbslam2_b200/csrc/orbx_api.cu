@@ -589,7 +589,8 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     orbx_keypoint_pod *hk = directOut ? (orbx_keypoint_pod *)kps : h->hKps.p;
     uint8_t *hd = directOut ? desc : h->hDesc.p;
 
-    const int nChunks = batch >= 32 ? 4 : (batch >= 8 ? 2 : 1);
+    int nChunks = batch >= 32 ? 4 : (batch >= 8 ? 2 : 1);
+    if (const char *e = getenv("ORBX_CHUNKS")) nChunks = std::max(1, std::min(batch, atoi(e)));
     if ((int)h->evChunk.size() < 2 * nChunks) {
         const size_t old = h->evChunk.size();
         h->evChunk.resize(2 * nChunks, nullptr);
