@@ -64,10 +64,11 @@ struct orbx_extractor {
     // geometry of the current image size
     int curW = 0, curH = 0;
     OrbxLayout L;
-    std::vector<OrbxCell> cells;
+    std::vector<OrbxSeg> segs;
     std::vector<OrbxRTab> rtab;
     std::vector<OrbxTile> tiles;
     int maxRows = 0, maxNodes = 0, pow2Nodes = 0;
+    int fastWinRows = 0, fastListCap = 0;   // shared-memory geometry of k_fast_segs
     bool geomUploaded = false;
     // device state
     cudaStream_t stream = nullptr;
@@ -75,7 +76,7 @@ struct orbx_extractor {
     cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
     std::vector<cudaEvent_t> evChunk;
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
-    OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (96 bytes x hCell+6 rows)
+    OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (256 bytes x hCell+6 rows)
     OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
     DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes, [2] resize boxes: where the kernels read them
     const uint8_t *tmapBase = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
@@ -87,7 +88,7 @@ struct orbx_extractor {
     DevBuf<int2> dSlots;
     DevBuf<int> dLvlCount, dCounts, dDbgCount;
     DevBuf<orbx_keypoint_pod> dKps;
-    DevBuf<OrbxCell> dCells;
+    DevBuf<OrbxSeg> dSegs;
     DevBuf<OrbxRTab> dRtab;
     DevBuf<OrbxTile> dTiles;
     DevBuf<OrbxDbgCand> dDbg;
@@ -174,12 +175,13 @@ void axisTable(int ssize, int dsize, OrbxRTab *out, bool packed)
 }
 
 // geometry for an image size; returns ORBX_OK or ORBX_ERR_SHAPE with a message
-int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<OrbxCell> &cells,
-                  std::vector<OrbxRTab> &rtab, std::vector<OrbxTile> &tiles, int &maxRows, int &maxNodes)
+int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<OrbxSeg> &segs,
+                  std::vector<OrbxRTab> &rtab, std::vector<OrbxTile> &tiles, int &maxRows, int &maxNodes, int &winRows, int &listCap)
 {
     const orbx_config &c = h->cfg;
     memset(&L, 0, sizeof(L));
-    cells.clear(); rtab.clear(); tiles.clear();
+    segs.clear(); rtab.clear(); tiles.clear();
+    winRows = 0; listCap = 0;
     L.nlevels = c.nlevels; L.iniTh = c.ini_th_fast; L.minTh = c.min_th_fast; L.tieRule = c.tie_rule;
     long long off = 0;
     int rows = 0, slots = 0;
@@ -206,34 +208,39 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         v.wCell = (int)ceilf(width / v.nCols);
         v.hCell = (int)ceilf(height / v.nRows);
         if (v.wCell > 60 || v.hCell > 60 || (long long)v.nCols * v.nRows >= 65536) return fail(h, ORBX_ERR_SHAPE, "FAST grid outside supported range");
-        v.cellBase = (int)cells.size();
+        v.segBase = (int)segs.size();
         v.winH = v.hCell + 6;
+        // cells of one cell row whose windows are processed (:935, :944), grouped into runs of <= ORBX_SEG_W tested columns
+        int nProc = 0;
+        for (int j = 0; j < v.nCols; j++) if (ORBX_MINB + j * v.wCell < maxBX - 6) nProc++;
+        const int perSegMax = std::max(1, std::min(8, ORBX_SEG_W / v.wCell));
+        const int nSegRow = (nProc + perSegMax - 1) / perSegMax;
+        const int perSeg = nSegRow ? (nProc + nSegRow - 1) / nSegRow : 0;
         for (int i = 0; i < v.nRows; i++) {
             const int iniY = ORBX_MINB + i * v.hCell;
             int maxY = iniY + v.hCell + 6;
             if (iniY >= maxBY - 3) continue;    // :935
             if (maxY > maxBY) maxY = maxBY;
-            for (int j = 0; j < v.nCols; j++) {
-                const int iniX = ORBX_MINB + j * v.wCell;
-                int maxX = iniX + v.wCell + 6;
-                if (iniX >= maxBX - 6) continue; // :944
+            if (maxY - iniY - 6 <= 0) continue; // no tested row (cv::FAST on a window under 7 rows finds nothing)
+            for (int j0 = 0; j0 < nProc; j0 += perSeg) {
+                const int j1 = std::min(j0 + perSeg, nProc);
+                const int iniX = ORBX_MINB + j0 * v.wCell;
+                int maxX = ORBX_MINB + (j1 - 1) * v.wCell + v.wCell + 6;   // right end of the last cell's window, :942-946
                 if (maxX > maxBX) maxX = maxBX;
-                OrbxCell cell;
-                cell.x0 = (uint16_t)iniX; cell.y0 = (uint16_t)iniY;
-                cell.w = (uint8_t)(maxX - iniX); cell.h = (uint8_t)(maxY - iniY);
-                cell.level = (uint8_t)l; cell.pad = 0;
-                cell.ci = (uint16_t)i; cell.cj = (uint16_t)j;
-                {
-                    const int wEff = std::max((int)cell.w - 6, 1);
-                    const int B0 = ((iniX - 1) & 15) + 4;      // shared byte of the first tested pixel (TMA box is 16-byte aligned)
-                    const int nQ = ((B0 + wEff - 1) >> 2) - (B0 >> 2) + 1;
-                    cell.mQ = (uint16_t)(32768 / nQ + 1);
-                    cell.mG = (uint16_t)(32768 / (((int)cell.w + 1 + 15) >> 4) + 1);
-                }
-                cells.push_back(cell);
+                OrbxSeg sg;
+                sg.x0 = (uint16_t)iniX; sg.y0 = (uint16_t)iniY;
+                sg.wT = (uint16_t)(maxX - iniX - 6); sg.hT = (uint8_t)(maxY - iniY - 6);
+                sg.level = (uint8_t)l;
+                sg.ci = (uint16_t)i; sg.cj0 = (uint16_t)j0;
+                const int B0 = iniX + 3 - ((iniX - 4) & ~15);   // shared byte of the first tested pixel (TMA box is 16-byte aligned)
+                const int nQ = ((B0 + (int)sg.wT - 1) >> 2) - (B0 >> 2) + 1;
+                sg.mQ = (uint32_t)((1u << 20) / nQ + 1);
+                segs.push_back(sg);
+                listCap = std::max(listCap, (int)sg.wT * (int)sg.hT);
             }
         }
-        v.nCells = (int)cells.size() - v.cellBase;
+        v.nSegs = (int)segs.size() - v.segBase;
+        winRows = std::max(winRows, v.winH);
         // DistributeOctTree geometry, :684-699
         v.W = maxBX - ORBX_MINB; v.H = maxBY - ORBX_MINB;
         if (v.H <= 0 || v.W / v.H < 1) {
@@ -278,7 +285,8 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
     L.rowsPerFrame = rows;
     L.slotsPerFrame = slots;
     L.kpStride = slots;
-    L.totalCells = (int)cells.size();
+    L.totalSegs = (int)segs.size();
+    listCap = (listCap + 7) & ~7;
     return ORBX_OK;
 }
 
@@ -334,7 +342,7 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        cuuint32_t boxF[3] = {96, (cuuint32_t)v.winH, 1};             // FW_P x window rows of k_fast_cells
+        cuuint32_t boxF[3] = {256, (cuuint32_t)v.winH, 1};            // FW_P x window rows of k_fast_segs
         CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxF, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -361,20 +369,21 @@ int buildTensorMaps(orbx_extractor *h, int frames)
 int setGeometry(orbx_extractor *h, int w, int hh)
 {
     if (w == h->curW && hh == h->curH && h->geomUploaded) return ORBX_OK;
-    OrbxLayout L; std::vector<OrbxCell> cells; std::vector<OrbxRTab> rtab; std::vector<OrbxTile> tiles; int maxRows, maxNodes;
-    int rc = buildGeometry(h, w, hh, L, cells, rtab, tiles, maxRows, maxNodes);
+    OrbxLayout L; std::vector<OrbxSeg> segs; std::vector<OrbxRTab> rtab; std::vector<OrbxTile> tiles; int maxRows, maxNodes, winRows, listCap;
+    int rc = buildGeometry(h, w, hh, L, segs, rtab, tiles, maxRows, maxNodes, winRows, listCap);
     if (rc != ORBX_OK) return rc;
-    h->L = L; h->cells.swap(cells); h->rtab.swap(rtab); h->tiles.swap(tiles);
+    h->L = L; h->segs.swap(segs); h->rtab.swap(rtab); h->tiles.swap(tiles);
     h->maxRows = maxRows; h->maxNodes = maxNodes;
+    h->fastWinRows = winRows; h->fastListCap = listCap;
     int p2 = 2; while (p2 < maxNodes) p2 <<= 1;
     h->pow2Nodes = p2;
     if (octree_smem_bytes(maxRows, maxNodes, p2) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
-    CK(h->dCells.ensure(h->cells.size()));
+    CK(h->dSegs.ensure(h->segs.size()));
     CK(h->dRtab.ensure(std::max<size_t>(h->rtab.size(), 1)));
     CK(h->dTiles.ensure(h->tiles.size()));
     // the stream may still be reading the old tables
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpyAsync(h->dCells.p, h->cells.data(), h->cells.size() * sizeof(OrbxCell), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->dSegs.p, h->segs.data(), h->segs.size() * sizeof(OrbxSeg), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dTiles.p, h->tiles.data(), h->tiles.size() * sizeof(OrbxTile), cudaMemcpyHostToDevice, h->stream));
     if (!h->rtab.empty())
         CK(cudaMemcpyAsync(h->dRtab.p, h->rtab.data(), h->rtab.size() * sizeof(OrbxRTab), cudaMemcpyHostToDevice, h->stream));
@@ -399,20 +408,20 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     }
     CK(cudaMemsetAsync(cnt, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(best, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
-    // Level 0 is in place: its FAST cells (a third of all cells, issue-bound) run on the side stream
+    // Level 0 is in place: its FAST segments (a third of all tested pixels, issue-bound) run on the side stream
     // beside the resize chain (7 dependent, latency-bound launches); the blur follows there once the
     // chain is done, beside FAST of the upper levels + octree on the main stream.
-    const int cells0 = L.lv[0].nCells;
+    const int segs0 = L.lv[0].nSegs;
     CK(cudaEventRecord(h->evFork, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    launch_fast(h->dTmaps.p[1].m, f0, L, h->dCells.p, 0, cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, h->stream2);
+    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, h->stream2));
     CK(cudaEventRecord(h->evFast0, h->stream2));
     for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
     CK(cudaEventRecord(h->evPyr, st));
     CK(cudaStreamWaitEvent(h->stream2, h->evPyr, 0));
     launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
     CK(cudaEventRecord(h->evJoin, h->stream2));
-    launch_fast(h->dTmaps.p[1].m, f0, L, h->dCells.p, cells0, L.totalCells - cells0, cnt, best, dbg, dbgCount, h->dbgCap, batch, st);
+    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
     CK(cudaStreamWaitEvent(st, h->evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
     CK(cudaStreamWaitEvent(st, h->evJoin, 0));
@@ -500,7 +509,7 @@ void orbx_destroy(orbx_extractor *h)
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
-    h->dKps.release(); h->dCells.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
+    h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
@@ -796,7 +805,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
-        launch_fast(h->dTmaps.p[1].m, 0, L, h->dCells.p, 0, L.totalCells, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, batch, st);
+        CK(launch_fast(h->dTmaps.p[1].m, 0, L, h->dSegs.p, 0, L.totalSegs, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, h->fastWinRows, h->fastListCap, batch, st));
         CK(cudaEventRecord(ev[2], st));
         CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
         CK(cudaEventRecord(ev[3], st));

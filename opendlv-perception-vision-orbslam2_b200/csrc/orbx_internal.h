@@ -18,7 +18,7 @@ struct OrbxLevel {
     int off;             // byte offset of the level inside one frame's slab
     // gridded FAST, orbextractor.cpp:914-928
     int nCols, nRows, wCell, hCell;
-    int cellBase, nCells; // processed cells of this level inside the cell table
+    int segBase, nSegs;  // FAST segments (runs of cells in one cell row) of this level inside the segment table
     int winH;            // rows of the FAST window box (hCell + 6): height of this level's TMA box
     // DistributeOctTree, orbextractor.cpp:684-699
     int W, H;            // maxX-minX, maxY-minY
@@ -39,18 +39,22 @@ struct OrbxLayout {
     int kpStride;        // records per frame in the output arrays (>= slotsPerFrame)
     int iniTh, minTh;
     int tieRule;
-    int totalCells;
+    int totalSegs;
     long long slab;      // pyramid bytes per frame
     OrbxLevel lv[ORBX_MAXL];
 };
 
-// one processed FAST cell (window = cell + 3 px margin each side, clipped to the level border)
-struct OrbxCell {
-    uint16_t x0, y0;     // window origin in level coordinates (iniX, iniY)
-    uint8_t w, h;        // window size (maxX-iniX, maxY-iniY) <= 66
-    uint8_t level, pad;
-    uint16_t ci, cj;     // cell row / column: (ci*nCols + cj) is the cell's position in the reference's emission order
-    uint16_t mQ, mG;     // 32768/n + 1 for n = 4-pixel groups per interior row / 16-byte groups per window row
+// One FAST segment: a run of up to ORBX_SEG_W tested columns of horizontally adjacent cells of one cell row
+// (orbextractor.cpp:930-947).  The tested pixels of the cells tile the run without gaps: cell j of the run
+// covers tested columns [j*wCell, (j+1)*wCell), the last one clipped by the level border.
+#define ORBX_SEG_W 224
+struct OrbxSeg {
+    uint16_t x0, y0;     // window origin in level coordinates (iniX of the first cell, iniY)
+    uint16_t wT;         // tested columns of the run (sum over its cells of window width - 6)
+    uint8_t hT;          // tested rows (window height - 6)
+    uint8_t level;
+    uint16_t ci, cj0;    // cell row / first cell column: (ci*nCols + cj) is a cell's position in the reference's emission order
+    uint32_t mQ;         // 2^20/nQ + 1, nQ = aligned 4-pixel groups covering one tested row of the run
 };
 
 // one blur tile: 32 words (128 px) x 4 strips of 32 rows; x0 in 4-px words, y0 in rows

@@ -5,7 +5,7 @@
 //
 //   k_copy_level0     level-0 copy of ComputePyramid            orbextractor.cpp:654-678
 //   k_resize          cv::resize(INTER_LINEAR) level l <- l-1   orbextractor.cpp:666      (A.1)
-//   k_fast_cells      gridded FAST-9 + NMS + threshold fallback orbextractor.cpp:906-970  (A.3)
+//   k_fast_segs       gridded FAST-9 + NMS + threshold fallback orbextractor.cpp:906-970  (A.3)
 //   k_octree          DistributeOctTree + DivideNode            orbextractor.cpp:680-904, :72-128 (A.5)
 //   k_blur            cv::GaussianBlur 7x7 sigma 2 REFLECT_101  orbextractor.cpp:621-622  (A.4)
 //   k_describe        IC_Angle + rBRIEF + keypoint assembly     orbextractor.cpp:136-211, :978-988, :631-639
@@ -359,9 +359,11 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 
 // ------------------------------------------------------------------------------------------
 // Gridded FAST-9/16 with 3x3 NMS per cell and the ini/min threshold fallback (A.3).
-// One CTA per (cell, frame).  Output is not a keypoint list: DistributeOctTree in this fork only
-// ever splits along y inside fixed x-strips (A.5), so all it needs per (strip, row) is the number
-// of candidates and the best candidate (max response, first in the reference's emission order).
+// One CTA per (segment, frame); a segment is a run of horizontally adjacent cells of one cell
+// row (<= 224 tested columns, 7 cells of 30-31 px), so the candidate lists of several cells share
+// the CTA's lanes.  Output is not a keypoint list: DistributeOctTree in this fork only ever
+// splits along y inside fixed x-strips (A.5), so all it needs per (strip, row) is the number of
+// candidates and the best candidate (max response, first in the reference's emission order).
 // Both are accumulated here with atomics:
 //   cnt [frame][rowBase + strip*H + y]  += 1
 //   best[frame][rowBase + strip*H + y]   = max(score<<56 | ~order<<28 | x<<14 | y)
@@ -369,96 +371,113 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 // order (cells row-major, raster inside a cell, orbextractor.cpp:930-968).
 //
 // Stages inside the CTA:
-//   0  the (w+6)x(h+6) window is fetched into shared memory by one TMA box load (cp.async.bulk.tensor)
+//   0  the run's window (256 bytes x hCell+6 rows) is fetched by one TMA box load (cp.async.bulk.tensor)
 //   1  quick reject on 4 pixels per thread (packed bytes): a FAST-9 arc always contains ring
 //      pixel k or k+8, so |I(p) - I(ring_k)| > t must hold for k in {0,8} and for k in {4,12};
-//      survivors (~8 % of pixels) are compacted into a list
-//   2  exact 16-pixel ring test on the survivors; true corners are compacted again
-//   3  corner score, 3x3 NMS on the cell's score map, threshold fallback, emission
+//      survivors (~10 % of pixels) are compacted into a list
+//   2  exact test and corner score in one pass: with d_k = I(p) - I(ring_k),
+//        A = max( max_k min(d_k..d_k+8), -min_k max(d_k..d_k+8) )
+//      is the largest threshold margin of the pixel: it is a corner at threshold t iff A > t, and its
+//      cv::FAST response is A - 1.  The sliding 9-windows are evaluated on 16-bit pairs (d_k, d_k+8)
+//      with three-input packed min/max (VIMNMX3.S16x2): 16 + 16 of them cover all 16 windows.
+//   3  3x3 NMS on the run's score map (neighbours in another cell count as 0, as each cell is an
+//      isolated cv::FAST call), per-cell threshold fallback, emission
 // ------------------------------------------------------------------------------------------
-#define FW_P 96   // shared window pitch in bytes (24 words: rows 0..3 of a warp hit disjoint banks)
-#define FS_P 64   // shared score-map pitch
+#define FS_T 256  // threads per CTA
+#define FW_P 256  // shared window pitch in bytes = TMA box width
+#define FM_P 256  // shared score-map pitch
 
-__device__ __forceinline__ int fast_score16(const int (&d)[16])
+__device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
+
+// largest threshold margin A of the pixel at c (window pitch FW_P); see stage 2 above
+__device__ __forceinline__ int fast_margin(const uint8_t *c)
 {
-    int mn1[16], mx1[16];
+    // P[j] = (256 + v - ring_j) | (256 + v - ring_j+8) << 16 : both halves in [1, 511], so the packed
+    // subtraction never borrows across the halves
+    const uint32_t V2 = (uint32_t)c[0] * 0x10001u + 0x01000100u;
+    uint32_t E[10];
+#define ORBX_PAIR(o1, o2) (V2 - ((uint32_t)c[o1] | (uint32_t)c[o2] << 16))
+    E[0] = ORBX_PAIR(3 * FW_P, -3 * FW_P);          E[1] = ORBX_PAIR(3 * FW_P + 1, -3 * FW_P - 1);
+    E[2] = ORBX_PAIR(2 * FW_P + 2, -2 * FW_P - 2);  E[3] = ORBX_PAIR(FW_P + 3, -FW_P - 3);
+    E[4] = ORBX_PAIR(3, -3);                        E[5] = ORBX_PAIR(-FW_P + 3, FW_P - 3);
+    E[6] = ORBX_PAIR(-2 * FW_P + 2, 2 * FW_P - 2);  E[7] = ORBX_PAIR(-3 * FW_P + 1, 3 * FW_P - 1);
+#undef ORBX_PAIR
+    E[8] = swap16(E[0]); E[9] = swap16(E[1]);       // E[j+8] = halves of E[j] swapped: (d_j+8, d_j)
+    uint32_t tn[14], tx[14];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { mn1[k] = min(d[k], d[(k + 1) & 15]); mx1[k] = max(d[k], d[(k + 1) & 15]); }
-    int mn2[16], mx2[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { mn2[k] = min(mn1[k], mn1[(k + 2) & 15]); mx2[k] = max(mx1[k], mx1[(k + 2) & 15]); }
-    int a = -256, b = 256;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        // window of 9 starting at k: [k..k+3] U [k+4..k+7] U {k+8}
-        int mn = min(min(mn2[k], mn2[(k + 4) & 15]), d[(k + 8) & 15]);
-        int mx = max(max(mx2[k], mx2[(k + 4) & 15]), d[(k + 8) & 15]);
-        a = max(a, mn);
-        b = min(b, mx);
+    for (int j = 0; j < 8; j++) {
+        tn[j] = __vmins2(__vmins2(E[j], E[j + 1]), E[j + 2]);    // min / max of d_j..d_j+2 | d_j+8..d_j+10
+        tx[j] = __vmaxs2(__vmaxs2(E[j], E[j + 1]), E[j + 2]);
     }
-    return max(a, -b) - 1;
+#pragma unroll
+    for (int j = 0; j < 6; j++) { tn[8 + j] = swap16(tn[j]); tx[8 + j] = swap16(tx[j]); }
+    uint32_t a = 0u, b = 0x7fff7fffu;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // windows d_k..d_k+8 (low half) and d_k+8..d_k+16 (high half)
+        a = __vmaxs2(a, __vmins2(__vmins2(tn[k], tn[k + 3]), tn[k + 6]));
+        b = __vmins2(b, __vmaxs2(__vmaxs2(tx[k], tx[k + 3]), tx[k + 6]));
+    }
+    const int a0 = (int)max(a & 0xffffu, a >> 16) - 256, b0 = (int)min(b & 0xffffu, b >> 16) - 256;
+    return max(a0, -b0);
 }
 
-__device__ __forceinline__ void fast_ring_diffs(const uint8_t *c, int (&d)[16])
+__global__ void __launch_bounds__(FS_T)
+k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
+            const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
+            unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
+            int *__restrict__ dbgCount, int dbgCap, int winRows, int listCap)
 {
-    const int v = c[0];
-    d[0] = v - c[3 * FW_P];       d[1] = v - c[3 * FW_P + 1];   d[2] = v - c[2 * FW_P + 2];   d[3] = v - c[FW_P + 3];
-    d[4] = v - c[3];              d[5] = v - c[-FW_P + 3];      d[6] = v - c[-2 * FW_P + 2];  d[7] = v - c[-3 * FW_P + 1];
-    d[8] = v - c[-3 * FW_P];      d[9] = v - c[-3 * FW_P - 1];  d[10] = v - c[-2 * FW_P - 2]; d[11] = v - c[-FW_P - 3];
-    d[12] = v - c[-3];            d[13] = v - c[FW_P - 3];      d[14] = v - c[2 * FW_P - 2];  d[15] = v - c[3 * FW_P - 1];
-}
-
-__global__ void __launch_bounds__(128)
-k_fast_cells(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
-             const OrbxCell *__restrict__ cells, uint32_t *__restrict__ cnt,
-             unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
-             int *__restrict__ dbgCount, int dbgCap)
-{
-    __shared__ __align__(128) uint8_t win[66 * FW_P];
+    extern __shared__ __align__(128) uint8_t fsm[];
+    uint8_t *win = fsm;                                              // winRows x FW_P (TMA destination)
+    uint8_t *smap = win + winRows * FW_P;                            // (winRows - 4) x FM_P: scores with a zero border
+    uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn << 8 | xs
+    uint16_t *corner = cand + listCap;                               // listCap
     __shared__ __align__(8) uint64_t bar;
-    __shared__ __align__(16) uint8_t smap[62 * FS_P];
-    __shared__ uint16_t cand[60 * 60];
-    __shared__ uint16_t corner[60 * 60];
     __shared__ int ncand, ncorner;
+    __shared__ int anyIni[8];
+    __shared__ uint8_t cellOf[ORBX_SEG_W];
 
-    const OrbxCell cell = cells[blockIdx.x];
+    const OrbxSeg seg = segs[blockIdx.x];
     const int frame = blockIdx.y;
-    const OrbxLevel &lv = L.lv[cell.level];
-    const int wEff = (int)cell.w - 6, hEff = (int)cell.h - 6;
-    if (wEff <= 0 || hEff <= 0) return;
-    const int tid = threadIdx.x;
+    const OrbxLevel &lv = L.lv[seg.level];
+    const int wT = seg.wT, hT = seg.hT;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int th = L.minTh;
 
-    // ---- stage 0: TMA fetches the window (box = 96 bytes x the level's window height) from the level's
-    // tensor map.  The box must start 16-byte aligned in x, so window column c lands at shared byte
-    // s16 + 1 + c with s16 = (x0 - 1) & 15, and tested pixel xIn at byte B0 + xIn, B0 = s16 + 4.
-    const int s16 = ((int)cell.x0 - 1) & 15, B0 = s16 + 4;
-    {
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            ncand = 0; ncorner = 0;
-        }
-        __syncthreads();
-        if (tid == 0)
-            tma_load_tile_3d(win, maps + cell.level, (int)cell.x0 - 1 - s16, (int)cell.y0, f0 + frame, &bar, FW_P * lv.winH);
-        for (int i = tid; i < (hEff + 2) * (FS_P / 16); i += 128) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
-        mbar_wait(&bar, 0);
+    // ---- stage 0: TMA fetches the window from the level's tensor map.  The box must start 16-byte aligned
+    // in x and the word left of the first tested pixel's word is read too: box x = (x0 - 4) & ~15, and tested
+    // column xs sits at shared byte B0 + xs of its row.
+    const int bx = ((int)seg.x0 - 4) & ~15, B0 = (int)seg.x0 + 3 - bx;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ncand = 0; ncorner = 0;
     }
+    if (tid < 8) anyIni[tid] = 0;
+    __syncthreads();
+    if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);
+    for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < wT) {
+        int cl = 0;
+        for (int b = lv.wCell; b <= tid; b += lv.wCell) cl++;
+        cellOf[tid] = (uint8_t)cl;
+    }
+    mbar_wait(&bar, 0);
     __syncthreads();
 
     // ---- stage 1: packed quick reject, 4 pixels per thread
     {
         // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
-        const int wq0 = B0 >> 2, wqL = (B0 + wEff - 1) >> 2;
-        const int nQ = wqL - wq0 + 1, items = nQ * hEff;
-        const unsigned M = cell.mQ;                          // 32768 / nQ + 1 (host)
+        const int wq0 = B0 >> 2, wqL = (B0 + wT - 1) >> 2;
+        const int nQ = wqL - wq0 + 1, items = nQ * hT;
+        const unsigned M = seg.mQ;                           // 2^20 / nQ + 1 (host)
         const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
-        const int nLast = ((B0 + wEff - 1) & 3) + 1;
+        const int nLast = ((B0 + wT - 1) & 3) + 1;
         const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
         const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
-        for (int it = tid; it < items; it += 128) {
-            const int yIn = (it * M) >> 15, q = it - yIn * nQ;
+        for (int it = tid; it < items; it += FS_T) {
+            const int yIn = (int)(((unsigned)it * M) >> 20), q = it - yIn * nQ;
             const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + wq0 + q;
             const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
             const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
@@ -471,7 +490,7 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant
             if (q == nQ - 1) pass &= maskLast;
             if (pass) {
                 int pos = atomicAdd(&ncand, __popc(pass));
-                const int e = (yIn << 6) + 4 * (wq0 + q) - B0;      // + j = yIn << 6 | xIn for the valid pixels j of the quad
+                const int e = (yIn << 8) + 4 * (wq0 + q) - B0;      // + j = yIn << 8 | xs for the valid pixels j of the quad
                 if (pass & 0x80u) cand[pos++] = (uint16_t)e;
                 if (pass & 0x8000u) cand[pos++] = (uint16_t)(e + 1);
                 if (pass & 0x800000u) cand[pos++] = (uint16_t)(e + 2);
@@ -482,78 +501,73 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant
     __syncthreads();
     const int nc = ncand;
 
-    // ---- stage 2: exact ring test (9 contiguous brighter or darker), second compaction.
-    // ring > v+t  <=>  (v+t) - ring < 0 ;  ring < v-t  <=>  ring - (v-t) < 0 : the sign bits are shifted
-    // into the two 16-bit ring masks with one funnel shift each (bit order reversed, contiguity is not).
-    for (int i = tid; i < nc; i += 128) {
-        const int e = cand[i];
-        const int yIn = e >> 6, xIn = e & 63;
-        const uint8_t *c = &win[(yIn + 3) * FW_P + xIn + B0];
-        const int v = c[0], hi = v + th, lo = v - th;
-        unsigned mb = 0, md = 0;
-#define ORBX_RING(off) { const int r_ = c[off]; mb = __funnelshift_l((unsigned)(hi - r_), mb, 1); md = __funnelshift_l((unsigned)(r_ - lo), md, 1); }
-        ORBX_RING(3 * FW_P) ORBX_RING(3 * FW_P + 1) ORBX_RING(2 * FW_P + 2) ORBX_RING(FW_P + 3)
-        ORBX_RING(3) ORBX_RING(-FW_P + 3) ORBX_RING(-2 * FW_P + 2) ORBX_RING(-3 * FW_P + 1)
-        ORBX_RING(-3 * FW_P) ORBX_RING(-3 * FW_P - 1) ORBX_RING(-2 * FW_P - 2) ORBX_RING(-FW_P - 3)
-        ORBX_RING(-3) ORBX_RING(FW_P - 3) ORBX_RING(2 * FW_P - 2) ORBX_RING(3 * FW_P - 1)
-#undef ORBX_RING
-        mb |= mb << 16; md |= md << 16;
-        unsigned r = mb & (mb >> 1); r &= r >> 2; r &= r >> 4; r &= mb >> 8;
-        unsigned q = md & (md >> 1); q &= q >> 2; q &= q >> 4; q &= md >> 8;
-        if (r | q) corner[atomicAdd(&ncorner, 1)] = (uint16_t)e;
+    // ---- stage 2: threshold margin of every survivor; corners (margin > min threshold) get their score
+    // written to the score map and are compacted (one shared atomic per warp)
+    for (int i0 = 0; i0 < nc; i0 += FS_T) {
+        const int i = i0 + tid;
+        int e = 0, A = 0;
+        if (i < nc) {
+            e = cand[i];
+            A = fast_margin(&win[((e >> 8) + 3) * FW_P + (e & 255) + B0]);
+        }
+        const bool isCorner = A > th;
+        const unsigned bal = __ballot_sync(0xffffffffu, isCorner);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ncorner, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (isCorner) {
+                corner[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+                smap[((e >> 8) + 1) * FM_P + (e & 255) + 1] = (uint8_t)(A - 1);
+            }
+        }
     }
     __syncthreads();
     const int nk = ncorner;
 
-    // ---- stage 3a: corner scores into the cell's score map
-    for (int i = tid; i < nk; i += 128) {
+    // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0)
+    const int wCell = lv.wCell;
+    for (int i = tid; i < nk; i += FS_T) {
         const int e = corner[i];
-        const int yIn = e >> 6, xIn = e & 63;
-        int d[16];
-        fast_ring_diffs(&win[(yIn + 3) * FW_P + xIn + B0], d);
-        smap[(yIn + 1) * FS_P + xIn + 1] = (uint8_t)fast_score16(d);
-    }
-    __syncthreads();
-
-    // ---- stage 3b: 3x3 non-maximum suppression (strict >, outside the cell interior counts as 0)
-    int any = 0;
-    for (int i = tid; i < nk; i += 128) {
-        const int e = corner[i];
-        const int yIn = e >> 6, xIn = e & 63;
-        const uint8_t *s = &smap[(yIn + 1) * FS_P + xIn + 1];
+        const int yIn = e >> 8, xs = e & 255;
+        const int cl = cellOf[xs], xIn = xs - cl * wCell;
+        const uint8_t *s = &smap[(yIn + 1) * FM_P + xs + 1];
         const int v = s[0];
-        if (v > s[-1] && v > s[1] && v > s[-FS_P - 1] && v > s[-FS_P] && v > s[-FS_P + 1] &&
-            v > s[FS_P - 1] && v > s[FS_P] && v > s[FS_P + 1]) {
+        const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
+        const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
+        const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
+        const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
+        if (v > m) {
             corner[i] = (uint16_t)(e | 0x8000);
-            any |= (v >= L.iniTh);
+            if (v >= L.iniTh) anyIni[cl] = 1;
         }
     }
     // per-cell threshold fallback, orbextractor.cpp:950-957: the ini-threshold result is used iff
     // it is non-empty after NMS; NMS(ini) == {k in NMS(min) : score >= ini}
-    const int haveIni = __syncthreads_or(any);
+    __syncthreads();
 
-    // ---- stage 3c: emit into the per-(strip,row) summaries
-    const unsigned orderBase = (unsigned)(cell.ci * lv.nCols + cell.cj) << 12;
+    // ---- stage 3b: emit into the per-(strip,row) summaries
     uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
-    for (int i = tid; i < nk; i += 128) {
+    for (int i = tid; i < nk; i += FS_T) {
         const int e = corner[i];
         if (!(e & 0x8000)) continue;
-        const int yIn = (e >> 6) & 63, xIn = e & 63;
-        const int s = smap[(yIn + 1) * FS_P + xIn + 1];
-        if (haveIni && s < L.iniTh) continue;
-        const int xr = cell.cj * lv.wCell + 3 + xIn, yr = cell.ci * lv.hCell + 3 + yIn; // relative to (16,16), :963-964
+        const int yIn = (e >> 8) & 127, xs = e & 255;
+        const int s = smap[(yIn + 1) * FM_P + xs + 1];
+        const int cl = cellOf[xs], xIn = xs - cl * wCell;
+        if (anyIni[cl] && s < L.iniTh) continue;
+        const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
         int strip = 0;                                                                  // xr / hX, :710
         for (int sB = lv.hX; sB <= xr; sB += lv.hX) strip++;
         const int row = strip * lv.H + yr;
-        const unsigned order = orderBase | (unsigned)(yIn << 6 | xIn);
+        const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
         const unsigned long long key = ((unsigned long long)s << 56) |
                                        ((unsigned long long)(0x0fffffffu - order) << 28) |
                                        ((unsigned long long)xr << 14) | (unsigned long long)yr;
         atomicAdd(&cntF[row], 1u);
         atomicMax(&bestF[row], key);
         if (dbg) {
-            const int slot = frame * L.nlevels + cell.level;
+            const int slot = frame * L.nlevels + seg.level;
             const int pos = atomicAdd(&dbgCount[slot], 1);
             if (pos < dbgCap) {
                 OrbxDbgCand c; c.xy = xr | (yr << 16); c.score = s;
@@ -563,12 +577,26 @@ k_fast_cells(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant
     }
 }
 
-void launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount,
-                 uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st)
+size_t fast_smem_bytes(int winRows, int listCap)
 {
-    if (cellCount <= 0) return;
-    dim3 grid(cellCount, batch);
-    k_fast_cells<<<grid, 128, 0, st>>>(maps, f0, L, cells + cellBegin, cnt, best, dbg, dbgCount, dbgCap);
+    return (size_t)winRows * FW_P + (size_t)(winRows - 4) * FM_P + (size_t)listCap * 4;
+}
+
+cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
+                        uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap,
+                        int winRows, int listCap, int batch, cudaStream_t st)
+{
+    if (segCount <= 0) return cudaSuccess;
+    const size_t smem = fast_smem_bytes(winRows, listCap);
+    static size_t optedIn = 48 * 1024;     // grows monotonically; the attribute is per function and device-wide
+    if (smem > optedIn) {
+        cudaError_t e = cudaFuncSetAttribute(k_fast_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        optedIn = smem;
+    }
+    dim3 grid(segCount, batch);
+    k_fast_segs<<<grid, FS_T, smem, st>>>(maps, f0, L, segs + segBegin, cnt, best, dbg, dbgCount, dbgCap, winRows, listCap);
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -14,8 +14,10 @@ void launch_copy_level0(const uint8_t *src, size_t frameStride, size_t srcPitch,
 void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st);
 void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
                  const int taps[7], int f0, int batch, cudaStream_t st);
-void launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxCell *cells, int cellBegin, int cellCount,
-                 uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap, int batch, cudaStream_t st);
+size_t fast_smem_bytes(int winRows, int listCap);
+cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
+                        uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap,
+                        int winRows, int listCap, int batch, cudaStream_t st);
 size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes);
 cudaError_t launch_octree(const OrbxLayout &L, uint32_t *cnt, const unsigned long long *best, int2 *slots,
                           int *lvlCount, int maxRows, int maxNodes, int pow2Nodes, int batch, cudaStream_t st);
