@@ -72,8 +72,14 @@ struct orbx_extractor {
     bool geomUploaded = false;
     // device state
     cudaStream_t stream = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr;
-    cudaStream_t stream2 = nullptr, streamIn = nullptr, streamOut = nullptr;
+    // Two lanes: the frames of a call are cut in two halves (or its chunks alternate) that run side by side,
+    // so the latency-bound stretches of one half (octree, kernel tails) are filled by the other half's work.
+    // A lane is a main stream (lane 0: `stream`), a side stream (level-0 FAST, blur) and its fork/join events.
+    struct Lane {
+        cudaStream_t main = nullptr, side = nullptr;
+        cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr, evStart = nullptr, evDone = nullptr;
+    } lane[2];
+    cudaStream_t streamIn = nullptr, streamOut = nullptr;
     std::vector<cudaEvent_t> evChunk;
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
     OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (256 bytes x hCell+6 rows)
@@ -357,8 +363,10 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         }
     }
     CK(h->dTmaps.ensure(3));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaStreamSynchronize(h->stream2));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaStreamSynchronize(h->lane[i].main));
+        CK(cudaStreamSynchronize(h->lane[i].side));
+    }
     CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dTmaps.p + 1, &h->tmapsFast, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dTmaps.p + 2, &h->tmapsResize, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
@@ -393,7 +401,7 @@ int setGeometry(orbx_extractor *h, int w, int hh)
 }
 
 // enqueue every stage after level 0 is in place
-int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
+int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const orbx_extractor::Lane &ln)
 {
     const OrbxLayout &L = h->L;
     uint8_t *pyr = h->dPyr.p + (size_t)f0 * L.slab, *blur = h->dBlur.p + (size_t)f0 * L.slab;
@@ -412,19 +420,19 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st)
     // beside the resize chain (7 dependent, latency-bound launches); the blur follows there once the
     // chain is done, beside FAST of the upper levels + octree on the main stream.
     const int segs0 = L.lv[0].nSegs;
-    CK(cudaEventRecord(h->evFork, st));
-    CK(cudaStreamWaitEvent(h->stream2, h->evFork, 0));
-    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, h->stream2));
-    CK(cudaEventRecord(h->evFast0, h->stream2));
+    CK(cudaEventRecord(ln.evFork, st));
+    CK(cudaStreamWaitEvent(ln.side, ln.evFork, 0));
+    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, ln.side));
+    CK(cudaEventRecord(ln.evFast0, ln.side));
     for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
-    CK(cudaEventRecord(h->evPyr, st));
-    CK(cudaStreamWaitEvent(h->stream2, h->evPyr, 0));
-    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, h->stream2);
-    CK(cudaEventRecord(h->evJoin, h->stream2));
+    CK(cudaEventRecord(ln.evPyr, st));
+    CK(cudaStreamWaitEvent(ln.side, ln.evPyr, 0));
+    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
+    CK(cudaEventRecord(ln.evJoin, ln.side));
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
-    CK(cudaStreamWaitEvent(st, h->evFast0, 0));
+    CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
-    CK(cudaStreamWaitEvent(st, h->evJoin, 0));
+    CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
     launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
     CK(cudaGetLastError());
@@ -479,14 +487,16 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(h, ORBX_ERR_CUDA, "liborbx is built for sm_100a only (no other code path exists)");
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        orbx_extractor::Lane &ln = h->lane[i];
+        CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
+        cudaEvent_t *evs[6] = {&ln.evFork, &ln.evJoin, &ln.evFast0, &ln.evPyr, &ln.evStart, &ln.evDone};
+        for (cudaEvent_t *e : evs) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    h->stream = h->lane[0].main;
     CK(cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->evFast0, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->evPyr, cudaEventDisableTiming));
     // size the arenas for the declared maximum so the hot path never allocates
     int rc = setGeometry(h, cfg->max_width, cfg->max_height);
     if (rc != ORBX_OK) return rc;
@@ -501,8 +511,11 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
 void orbx_destroy(orbx_extractor *h)
 {
     if (!h) return;
-    if (h->stream) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->stream); }
-    if (h->stream2) cudaStreamSynchronize(h->stream2);
+    cudaSetDevice(h->cfg.device);
+    for (int i = 0; i < 2; i++) {
+        if (h->lane[i].main) cudaStreamSynchronize(h->lane[i].main);
+        if (h->lane[i].side) cudaStreamSynchronize(h->lane[i].side);
+    }
     if (h->streamIn) cudaStreamSynchronize(h->streamIn);
     if (h->streamOut) cudaStreamSynchronize(h->streamOut);
     for (cudaEvent_t e : h->evChunk) if (e) cudaEventDestroy(e);
@@ -511,12 +524,13 @@ void orbx_destroy(orbx_extractor *h)
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
     h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
-    if (h->evFork) cudaEventDestroy(h->evFork);
-    if (h->evJoin) cudaEventDestroy(h->evJoin);
-    if (h->evFast0) cudaEventDestroy(h->evFast0);
-    if (h->evPyr) cudaEventDestroy(h->evPyr);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
+    for (int i = 0; i < 2; i++) {
+        orbx_extractor::Lane &ln = h->lane[i];
+        cudaEvent_t evs[6] = {ln.evFork, ln.evJoin, ln.evFast0, ln.evPyr, ln.evStart, ln.evDone};
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+        if (ln.main) cudaStreamDestroy(ln.main);
+        if (ln.side) cudaStreamDestroy(ln.side);
+    }
     if (h->streamIn) cudaStreamDestroy(h->streamIn);
     if (h->streamOut) cudaStreamDestroy(h->streamOut);
     delete h;
@@ -551,9 +565,27 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     rc = ensureArenas(h, batch);
     if (rc != ORBX_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
     h->lastBatch = batch;
-    return enqueuePipeline(h, 0, batch, st);
+    static const int splitEnv = getenv("ORBX_SPLIT") ? atoi(getenv("ORBX_SPLIT")) : 0;
+    const int nSplit = splitEnv > 0 ? std::min(splitEnv, 2) : (batch >= 16 ? 2 : 1);
+    if (nSplit == 1 || batch < 2) {
+        launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
+        return enqueuePipeline(h, 0, batch, st, h->lane[0]);
+    }
+    // two halves side by side: the first on the caller's stream, the second on lane 1, joined back at the end
+    const int b0 = batch / 2;
+    const orbx_extractor::Lane &l1 = h->lane[1];
+    CK(cudaEventRecord(l1.evStart, st));
+    CK(cudaStreamWaitEvent(l1.main, l1.evStart, 0));
+    launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, b0, st);
+    rc = enqueuePipeline(h, 0, b0, st, h->lane[0]);
+    if (rc != ORBX_OK) return rc;
+    launch_copy_level0(d_imgs + (size_t)b0 * frame_stride, frame_stride, pitch, h->dPyr.p + (size_t)b0 * h->L.slab, h->L, batch - b0, l1.main);
+    rc = enqueuePipeline(h, b0, batch - b0, l1.main, l1);
+    if (rc != ORBX_OK) return rc;
+    CK(cudaEventRecord(l1.evDone, l1.main));
+    CK(cudaStreamWaitEvent(st, l1.evDone, 0));
+    return ORBX_OK;
 }
 
 int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
@@ -605,7 +637,7 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         h->evChunk.resize(2 * nChunks, nullptr);
         for (size_t i = old; i < h->evChunk.size(); i++) CK(cudaEventCreateWithFlags(&h->evChunk[i], cudaEventDisableTiming));
     }
-    cudaStream_t sIn = h->streamIn, sK = h->stream, sOut = h->streamOut;
+    cudaStream_t sIn = h->streamIn, sOut = h->streamOut;
     for (int c = 0; c < nChunks; c++) {
         const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
         const int nf = f1 - f0;
@@ -628,10 +660,12 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
             f = g;
         }
         CK(cudaEventRecord(h->evChunk[2 * c], sIn));
-        // ---- kernels of this chunk
+        // ---- kernels of this chunk (chunks alternate between the two lanes)
+        const orbx_extractor::Lane &ln = h->lane[c & 1];
+        cudaStream_t sK = ln.main;
         CK(cudaStreamWaitEvent(sK, h->evChunk[2 * c], 0));
         launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, sK);
-        rc = enqueuePipeline(h, f0, nf, sK);
+        rc = enqueuePipeline(h, f0, nf, sK, ln);
         if (rc != ORBX_OK) return rc;
         CK(cudaEventRecord(h->evChunk[2 * c + 1], sK));
         // ---- D2H of this chunk's results
@@ -668,7 +702,8 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         }
     }
     CK(cudaStreamSynchronize(sOut));
-    CK(cudaStreamSynchronize(sK));
+    CK(cudaStreamSynchronize(h->lane[0].main));
+    CK(cudaStreamSynchronize(h->lane[1].main));
     if (trace) {
         struct timespec tsD;
         clock_gettime(CLOCK_MONOTONIC, &tsD);
