@@ -80,7 +80,14 @@ struct orbx_extractor {
         cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr, evStart = nullptr, evDone = nullptr;
     } lane[2];
     cudaStream_t streamIn = nullptr, streamOut = nullptr;
+    // CUDA graphs of the per-chunk kernel pipeline of the host entry point (level-0 copy .. describe, both
+    // streams of a lane): one cudaGraphLaunch replaces ~25 launches / event calls per chunk.  Keyed by
+    // (first frame, frames, lane); dropped whenever geometry or an arena pointer changes.
+    struct ChunkGraph { int f0, nf, lane; cudaGraphExec_t exec; };
+    std::vector<ChunkGraph> graphs;
+    uint64_t graphSig = 0;
     std::vector<cudaEvent_t> evChunk;
+    std::vector<cudaEvent_t> evTrace;      // ORBX_TRACE only: timing events, 1 + 3 per chunk
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
     OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (256 bytes x hCell+6 rows)
     OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
@@ -439,6 +446,47 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     return ORBX_OK;
 }
 
+uint64_t arenaSignature(const orbx_extractor *h)
+{
+    const void *ptrs[] = {h->dIn.p, h->dPyr.p, h->dBlur.p, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->dCounts.p,
+                          h->dKps.p, h->dDesc.p, h->dSegs.p, h->dRtab.p, h->dTiles.p, h->dTmaps.p, h->dDbg.p, h->dDbgCount.p};
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&x](uint64_t v) { x = (x ^ v) * 1099511628211ull; };
+    for (const void *q : ptrs) mix((uint64_t)(uintptr_t)q);
+    mix((uint64_t)h->curW); mix((uint64_t)h->curH); mix((uint64_t)h->dbgEnabled); mix((uint64_t)h->dbgCap);
+    return x;
+}
+
+void dropGraphs(orbx_extractor *h)
+{
+    for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// the kernel pipeline of frames [f0, f0+nf) of the host staging buffer as an executable graph on lane `li`
+int chunkGraph(orbx_extractor *h, int f0, int nf, int li, size_t frameBytes, int width, cudaGraphExec_t *out)
+{
+    const uint64_t sig = arenaSignature(h);
+    if (sig != h->graphSig) { dropGraphs(h); h->graphSig = sig; }
+    for (auto &g : h->graphs) if (g.f0 == f0 && g.nf == nf && g.lane == li) { *out = g.exec; return ORBX_OK; }
+    const orbx_extractor::Lane &ln = h->lane[li];
+    const OrbxLayout &L = h->L;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeRelaxed));
+    launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, ln.main);
+    int rc = enqueuePipeline(h, f0, nf, ln.main, ln);
+    cudaError_t e = cudaStreamEndCapture(ln.main, &graph);
+    if (rc != ORBX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return failCuda(h, e, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return failCuda(h, e, "cudaGraphInstantiate");
+    h->graphs.push_back({f0, nf, li, exec});
+    *out = exec;
+    return ORBX_OK;
+}
+
 bool isPinned(const void *p)
 {
     cudaPointerAttributes a;
@@ -518,7 +566,9 @@ void orbx_destroy(orbx_extractor *h)
     }
     if (h->streamIn) cudaStreamSynchronize(h->streamIn);
     if (h->streamOut) cudaStreamSynchronize(h->streamOut);
+    dropGraphs(h);
     for (cudaEvent_t e : h->evChunk) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->evTrace) if (e) cudaEventDestroy(e);
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
@@ -638,6 +688,12 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         for (size_t i = old; i < h->evChunk.size(); i++) CK(cudaEventCreateWithFlags(&h->evChunk[i], cudaEventDisableTiming));
     }
     cudaStream_t sIn = h->streamIn, sOut = h->streamOut;
+    static const bool trace = getenv("ORBX_TRACE") != nullptr;
+    if (trace) {
+        while ((int)h->evTrace.size() < 1 + 3 * nChunks) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->evTrace.push_back(e); }
+        CK(cudaEventRecord(h->evTrace[0], sIn));
+    }
+    static const bool useGraphs = !(getenv("ORBX_NO_GRAPH") && atoi(getenv("ORBX_NO_GRAPH")));
     for (int c = 0; c < nChunks; c++) {
         const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
         const int nf = f1 - f0;
@@ -660,14 +716,23 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
             f = g;
         }
         CK(cudaEventRecord(h->evChunk[2 * c], sIn));
+        if (trace) CK(cudaEventRecord(h->evTrace[1 + 3 * c], sIn));
         // ---- kernels of this chunk (chunks alternate between the two lanes)
         const orbx_extractor::Lane &ln = h->lane[c & 1];
         cudaStream_t sK = ln.main;
         CK(cudaStreamWaitEvent(sK, h->evChunk[2 * c], 0));
-        launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, sK);
-        rc = enqueuePipeline(h, f0, nf, sK, ln);
-        if (rc != ORBX_OK) return rc;
+        if (useGraphs) {
+            cudaGraphExec_t g = nullptr;
+            rc = chunkGraph(h, f0, nf, c & 1, frameBytes, width, &g);
+            if (rc != ORBX_OK) return rc;
+            CK(cudaGraphLaunch(g, sK));
+        } else {
+            launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, sK);
+            rc = enqueuePipeline(h, f0, nf, sK, ln);
+            if (rc != ORBX_OK) return rc;
+        }
         CK(cudaEventRecord(h->evChunk[2 * c + 1], sK));
+        if (trace) CK(cudaEventRecord(h->evTrace[2 + 3 * c], sK));
         // ---- D2H of this chunk's results
         CK(cudaStreamWaitEvent(sOut, h->evChunk[2 * c + 1], 0));
         CK(cudaMemcpyAsync(h->hCounts.p + f0, h->dCounts.p + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, sOut));
@@ -676,9 +741,9 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         CK(cudaMemcpyAsync(hd + (size_t)f0 * L.kpStride * 32, h->dDesc.p + (size_t)f0 * L.kpStride * 32,
                            (size_t)L.kpStride * nf * 32, cudaMemcpyDeviceToHost, sOut));
         CK(cudaEventRecord(h->evChunk[2 * c], sOut));   // reuse: the H2D event of this chunk has been consumed
+        if (trace) CK(cudaEventRecord(h->evTrace[3 + 3 * c], sOut));
     }
     h->lastBatch = batch;
-    static const bool trace = getenv("ORBX_TRACE") != nullptr;
     struct timespec tsE;
     if (trace) clock_gettime(CLOCK_MONOTONIC, &tsE);
     int status = ORBX_OK;
@@ -707,6 +772,13 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     if (trace) {
         struct timespec tsD;
         clock_gettime(CLOCK_MONOTONIC, &tsD);
+        for (int c = 0; c < nChunks; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, h->evTrace[0], h->evTrace[1 + 3 * c]);
+            cudaEventElapsedTime(&b, h->evTrace[0], h->evTrace[2 + 3 * c]);
+            cudaEventElapsedTime(&d, h->evTrace[0], h->evTrace[3 + 3 * c]);
+            fprintf(stderr, "[orbx]   chunk %d: h2d done %.3f, kernels done %.3f, d2h done %.3f ms\n", c, a, b, d);
+        }
         fprintf(stderr, "[orbx] batch %d: enqueue %.3f ms, drain %.3f ms\n", batch,
                 (tsE.tv_sec - tsB.tv_sec) * 1e3 + (tsE.tv_nsec - tsB.tv_nsec) * 1e-6,
                 (tsD.tv_sec - tsE.tv_sec) * 1e3 + (tsD.tv_nsec - tsE.tv_nsec) * 1e-6);
