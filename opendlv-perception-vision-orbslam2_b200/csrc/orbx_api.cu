@@ -168,11 +168,14 @@ void buildTables(orbx_extractor *h)
     }
 }
 
-// bilinear coefficient table of one axis, SURVEY A.1
-void axisTable(int ssize, int dsize, OrbxRTab *out, bool packed)
+// bilinear coefficient table of one axis, SURVEY A.1.  x axis: {sx0, sx1, c0 | c1 << 16, 0}; y axis: {sy0, sy1, b0, b1}.
+// Returns false when the axis is not a strict downscale in the sense k_resize relies on: source index strictly
+// increasing, and the second tap either the next source pixel or weightless.
+bool axisTable(int ssize, int dsize, OrbxRTab *out, bool xAxis)
 {
     const double invScale = (double)dsize / ssize;
     const double scale = 1.0 / invScale;
+    bool ok = true;
     for (int d = 0; d < dsize; d++) {
         float f = (float)((d + 0.5) * scale - 0.5);
         int s = cvFloorD(f);
@@ -182,9 +185,13 @@ void axisTable(int ssize, int dsize, OrbxRTab *out, bool packed)
         const int c0 = (int16_t)cvRoundF((1.f - f) * 2048.f), c1 = (int16_t)cvRoundF(f * 2048.f);
         out[d].a = s;
         out[d].b = std::min(s + 1, ssize - 1);
-        if (packed) { out[d].c = (int32_t)((uint32_t)c0 | (uint32_t)c1 << 16); out[d].d = 0; }
+        if (xAxis) { out[d].c = (int32_t)((uint32_t)c0 | (uint32_t)c1 << 16); out[d].d = 0; }
         else { out[d].c = c0; out[d].d = c1; }
+        if (c0 < 0 || c1 < 0 || (out[d].b != s + 1 && c1 != 0) || (d > 0 && s <= out[d - 1].a)) ok = false;
+        if (xAxis && d >= 3 && s - out[d - 3].a > 4) ok = false;   // four adjacent outputs read at most 6 adjacent source bytes
+        if (!xAxis && d >= 7 && s - out[d - 7].a > 10) ok = false; // eight adjacent output rows span at most 12 source rows
     }
+    return ok;
 }
 
 // geometry for an image size; returns ORBX_OK or ORBX_ERR_SHAPE with a message
@@ -288,10 +295,14 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
             const OrbxLevel &p = L.lv[l - 1];
             v.xtabOff = (int)rtab.size();
             rtab.resize(rtab.size() + v.w);
-            axisTable(p.w, v.w, &rtab[v.xtabOff], true);
+            const bool okX = axisTable(p.w, v.w, &rtab[v.xtabOff], true);
             v.ytabOff = (int)rtab.size();
             rtab.resize(rtab.size() + v.h);
-            axisTable(p.h, v.h, &rtab[v.ytabOff], false);
+            const bool okY = axisTable(p.h, v.h, &rtab[v.ytabOff], false);
+            if (!okX || !okY) {
+                snprintf(msg, sizeof msg, "level %d (%dx%d from %dx%d) is not a strict downscale by at most 1.35", l, v.w, v.h, p.w, p.h);
+                return fail(h, ORBX_ERR_SHAPE, msg);
+            }
         }
     }
     L.slab = (off + 255) / 256 * 256;

@@ -130,26 +130,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 // ------------------------------------------------------------------------------------------
 // pyramid resize, 11-bit fixed-point bilinear (A.1): level l from level l-1.
 // CTA = 128 x 32 output tile.  One elected thread fetches the source region of the tile -- at most
-// 192 x 48 bytes at scale factors up to 1.4 -- with one TMA box load (cp.async.bulk.tensor, box start
-// 16-byte aligned in x); the 128 threads then work from shared memory: each owns 4 adjacent output
-// columns (one 32-bit store per output row) and walks 8 output rows.  Horizontally interpolated
-// source rows h(sy)[x] = S[sy][sx]*c0 + S[sy][sx+1]*c1 (one dp2a per pixel, coefficients packed) are
-// kept in registers and reused between consecutive output rows.
+// 192 x 48 bytes at scale factors up to 1.35 -- with one TMA box load (cp.async.bulk.tensor, box start
+// 16-byte aligned in x); the 128 threads then work from shared memory.  A thread owns 4 adjacent
+// output columns (one 32-bit store per output row) and 8 output rows, and walks the SOURCE rows of
+// its band top to bottom: per source row it forms the four horizontal interpolations
+//   h[x] = S[sx]*c0 + S[sx+1]*c1      (3 aligned word loads, 2 funnel shifts, 4 PRMT, 4 dp2a)
+// once, keeps the previous row's in registers, and emits an output row whenever the pair
+// (previous, current) is the pair (sy, sy+1) the next output row interpolates between -- every
+// source row is loaded and interpolated exactly once per thread.  Downscaling makes sx and sy
+// strictly increasing, so at most one output row is emitted per source row (checked on the host).
+//   v = ((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2, two pixels per register in 16-bit halves
 // ------------------------------------------------------------------------------------------
 #define RS_TW 128
 #define RS_TH 32
 #define RS_ROWS 8
+#define RS_SRC_ROWS 12   // source rows a band of 8 output rows can touch at scale <= 1.35: 7*1.35 + 2
 #define RS_BOXW 192
 #define RS_BOXH 48
 
-__device__ __forceinline__ void resize_hrow(const uint8_t *rowp, const int (&sx0)[4], const int (&sx1)[4],
-                                            const uint32_t (&cc)[4], int (&hv)[4])
+__device__ __forceinline__ void resize_hrow(const uint8_t *p, int sh, const uint32_t (&sel)[4], const uint32_t (&cc)[4], uint32_t (&hv)[4])
 {
+    const uint32_t w0 = *(const uint32_t *)p, w1 = *(const uint32_t *)(p + 4), w2 = *(const uint32_t *)(p + 8);
+    const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);   // bytes sx .. sx+7
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t px = (uint32_t)rowp[sx0[k]] | (uint32_t)rowp[sx1[k]] << 8;
-        hv[k] = __dp2a_lo(cc[k], px, 0u);     // c0 * S[sx0] + c1 * S[sx1]
-    }
+    for (int k = 0; k < 4; k++)
+        hv[k] = __dp2a_lo(cc[k], __byte_perm(lo, hi, sel[k]), 0u) >> 4;                 // (c0*S[sx0] + c1*S[sx0+1]) >> 4
 }
 
 __global__ void __launch_bounds__(128)
@@ -162,7 +167,7 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
     const int f = blockIdx.z;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
-    if (tid < RS_TH) sy[tid] = __ldg(&ytab[min(ty0 + tid, dh - 1)]);          // {sy0, sy1, b0, b1}
+    if (tid < RS_TH) sy[tid] = __ldg(&ytab[min(ty0 + tid, dh - 1)]);          // {sy0, sy0+1, b0, b1}
     const int xs = __ldg(&xtab[tx0]).x & ~15;                                  // box origin: first source column, 16-aligned
     const int ys = __ldg(&ytab[ty0]).x;                                        //             first source row
     if (tid == 0) {
@@ -173,41 +178,40 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
     if (tid == 0) tma_load_tile_3d(tileS, srcMap, xs, ys, f0 + f, &bar, RS_BOXH * RS_BOXW);
     const int x0 = tx0 + threadIdx.x * 4;
     const int y0 = ty0 + threadIdx.y * RS_ROWS;
-    int sx0[4], sx1[4];
-    uint32_t cc[4];
+    uint32_t sel[4], cc[4];
+    const int sxa = __ldg(&xtab[min(x0, dw - 1)]).x;                           // this thread's first source column
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int4 t = __ldg(&xtab[min(x0 + k, dw - 1)]);
-        sx0[k] = t.x - xs; sx1[k] = t.y - xs; cc[k] = (uint32_t)t.z;
+        const uint32_t o = (uint32_t)(t.x - sxa);                              // 0..4 at scale factors <= 1.35
+        sel[k] = o | (o + 1) << 4;
+        cc[k] = (uint32_t)t.z;
     }
+    const int sh = ((sxa - xs) & 3) * 8;
     mbar_wait(&bar, 0);
     if (x0 >= dw || y0 >= dh) return;
     uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch + x0;
     const int yEnd = min(RS_ROWS, dh - y0);
-    int rb = -1;
-    int ha[4], hb[4] = {0, 0, 0, 0};
-    for (int r = 0; r < yEnd; r++) {
-        const int4 ty = sy[threadIdx.y * RS_ROWS + r];                         // uniform across the warp
-        if (ty.x == rb) {
+    int4 ty = sy[threadIdx.y * RS_ROWS];                                       // uniform across the warp
+    const int s0 = ty.x;
+    const uint8_t *base = tileS + (s0 - ys) * RS_BOXW + ((sxa - xs) & ~3);
+    uint32_t prev[4], cur[4];
+    resize_hrow(base, sh, sel, cc, prev);
+    int r = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) ha[k] = hb[k];
-        } else {
-            resize_hrow(tileS + (ty.x - ys) * RS_BOXW, sx0, sx1, cc, ha);
+    for (int j = 1; j < RS_SRC_ROWS; j++) {
+        resize_hrow(base + j * RS_BOXW, sh, sel, cc, cur);
+        if (ty.x - s0 == j - 1) {                                              // (prev, cur) = source rows (sy0, sy0+1) of output row r
+            // 16-bit pairs: (b0*h0 >> 16 | b0*h0' >> 16 << 16) + (b1*h1 ...) + (2 | 2 << 16), each half <= 1023
+            const uint32_t b0 = (uint32_t)ty.z, b1 = (uint32_t)ty.w;
+            const uint32_t w01 = __byte_perm(b0 * prev[0], b0 * prev[1], 0x7632) + __byte_perm(b1 * cur[0], b1 * cur[1], 0x7632) + 0x00020002u;
+            const uint32_t w23 = __byte_perm(b0 * prev[2], b0 * prev[3], 0x7632) + __byte_perm(b1 * cur[2], b1 * cur[3], 0x7632) + 0x00020002u;
+            *(uint32_t *)(dst + (size_t)r * dstPitch) = __byte_perm(w01 >> 2, w23 >> 2, 0x6420);     // bytes past dw land in the pitch padding
+            if (++r >= yEnd) return;
+            ty = sy[threadIdx.y * RS_ROWS + r];
         }
-        if (ty.y == ty.x) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) hb[k] = ha[k];
-        } else {
-            resize_hrow(tileS + (ty.y - ys) * RS_BOXW, sx0, sx1, cc, hb);
-        }
-        rb = ty.y;
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int v = (((ty.z * (ha[k] >> 4)) >> 16) + ((ty.w * (hb[k] >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 255) << (8 * k);
-        }
-        *(uint32_t *)(dst + (size_t)r * dstPitch) = out;                        // bytes past dw land in the pitch padding
+        for (int k = 0; k < 4; k++) prev[k] = cur[k];
     }
 }
 
