@@ -113,6 +113,7 @@ struct orbx_extractor {
     PinBuf<int> hCounts;
     int dbgEnabled = 0, dbgCap = 0;
     int lastBatch = 0;
+    int nSM = 148;
     std::string err;
 };
 
@@ -403,7 +404,7 @@ int setGeometry(orbx_extractor *h, int w, int hh)
     h->fastWinRows = winRows; h->fastListCap = listCap;
     int p2 = 2; while (p2 < maxNodes) p2 <<= 1;
     h->pow2Nodes = p2;
-    if (octree_smem_bytes(maxRows, maxNodes, p2) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
+    if (octree_smem_bytes(maxRows, maxNodes) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
     CK(h->dSegs.ensure(h->segs.size()));
     CK(h->dRtab.ensure(std::max<size_t>(h->rtab.size(), 1)));
     CK(h->dTiles.ensure(h->tiles.size()));
@@ -442,14 +443,14 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     CK(cudaStreamWaitEvent(ln.side, ln.evFork, 0));
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, ln.side));
     CK(cudaEventRecord(ln.evFast0, ln.side));
-    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, st);
+    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
     CK(cudaEventRecord(ln.evPyr, st));
     CK(cudaStreamWaitEvent(ln.side, ln.evPyr, 0));
     launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
     CK(cudaEventRecord(ln.evJoin, ln.side));
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
-    CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
+    CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
     launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
@@ -546,6 +547,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(h, ORBX_ERR_CUDA, "liborbx is built for sm_100a only (no other code path exists)");
+    h->nSM = prop.multiProcessorCount;
     for (int i = 0; i < 2; i++) {
         orbx_extractor::Lane &ln = h->lane[i];
         CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
@@ -919,13 +921,13 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(ev[0], st));
-        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, 0, h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, st);
+        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, 0, h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
         CK(launch_fast(h->dTmaps.p[1].m, 0, L, h->dSegs.p, 0, L.totalSegs, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, h->fastWinRows, h->fastListCap, batch, st));
         CK(cudaEventRecord(ev[2], st));
-        CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, h->pow2Nodes, batch, st));
+        CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, batch, st));
         CK(cudaEventRecord(ev[3], st));
         launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, 0, batch, st);
         CK(cudaEventRecord(ev[4], st));

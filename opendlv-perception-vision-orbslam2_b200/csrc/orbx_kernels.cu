@@ -13,6 +13,7 @@
 #include "orbx_kernels.h"
 
 #include <cuda.h>
+#include <algorithm>
 #include <cuda_runtime.h>
 
 // rBRIEF sampling pattern, 512 (x,y) points (data; same table as orbextractor.cpp:215-473)
@@ -129,11 +130,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 
 // ------------------------------------------------------------------------------------------
 // pyramid resize, 11-bit fixed-point bilinear (A.1): level l from level l-1.
-// CTA = 128 x 32 output tile.  One elected thread fetches the source region of the tile -- at most
-// 192 x 48 bytes at scale factors up to 1.35 -- with one TMA box load (cp.async.bulk.tensor, box start
-// 16-byte aligned in x); the 128 threads then work from shared memory.  A thread owns 4 adjacent
-// output columns (one 32-bit store per output row) and 8 output rows, and walks the SOURCE rows of
-// its band top to bottom: per source row it forms the four horizontal interpolations
+// Work unit = 128 x 32 output tile of one frame; its source region -- at most 192 x 48 bytes at scale
+// factors up to 1.35 -- arrives by one TMA box load (cp.async.bulk.tensor, box start 16-byte aligned
+// in x).  CTAs are persistent over a run of tiles (tile order: x tile, y tile, frame -- consecutive
+// tiles of a run differ only in the frame, so the coefficient tables stay in registers): warp 4 is
+// the producer, keeping a two-deep ring of boxes in flight (full/empty mbarriers), warps 0-3 consume.
+// A consumer thread owns 4 adjacent output columns (one 32-bit store per output row) and 8 output
+// rows, and walks the SOURCE rows of its band top to bottom: per source row it forms the four
+// horizontal interpolations
 //   h[x] = S[sx]*c0 + S[sx+1]*c1      (3 aligned word loads, 2 funnel shifts, 4 PRMT, 4 dp2a)
 // once, keeps the previous row's in registers, and emits an output row whenever the pair
 // (previous, current) is the pair (sy, sy+1) the next output row interpolates between -- every
@@ -147,6 +151,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 #define RS_SRC_ROWS 12   // source rows a band of 8 output rows can touch at scale <= 1.35: 7*1.35 + 2
 #define RS_BOXW 192
 #define RS_BOXH 48
+#define RS_STAGES 2
 
 __device__ __forceinline__ void resize_hrow(const uint8_t *p, int sh, const uint32_t (&sel)[4], const uint32_t (&cc)[4], uint32_t (&hv)[4])
 {
@@ -157,70 +162,117 @@ __device__ __forceinline__ void resize_hrow(const uint8_t *p, int sh, const uint
         hv[k] = __dp2a_lo(cc[k], __byte_perm(lo, hi, sel[k]), 0u) >> 4;                 // (c0*S[sx0] + c1*S[sx0+1]) >> 4
 }
 
-__global__ void __launch_bounds__(128)
-k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ pyr, long long slab, int dstOff, int dstPitch,
-         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
-    __shared__ __align__(128) uint8_t tileS[RS_BOXH * RS_BOXW];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int4 sy[RS_TH];
-    const int f = blockIdx.z;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
-    if (tid < RS_TH) sy[tid] = __ldg(&ytab[min(ty0 + tid, dh - 1)]);          // {sy0, sy0+1, b0, b1}
-    const int xs = __ldg(&xtab[tx0]).x & ~15;                                  // box origin: first source column, 16-aligned
-    const int ys = __ldg(&ytab[ty0]).x;                                        //             first source row
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(160)
+k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ pyr, long long slab, int dstOff, int dstPitch,
+         int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int tilesY, int batch, int nTiles, int tilesPerCta)
+{
+    __shared__ __align__(128) uint8_t tileS[RS_STAGES][RS_BOXH * RS_BOXW];
+    __shared__ __align__(8) uint64_t full[RS_STAGES], empty[RS_STAGES];
+    __shared__ int4 sy[4][RS_ROWS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t0 = blockIdx.x * tilesPerCta, t1 = min(t0 + tilesPerCta, nTiles);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < RS_STAGES; s++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(smem_u32(&empty[s])) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) tma_load_tile_3d(tileS, srcMap, xs, ys, f0 + f, &bar, RS_BOXH * RS_BOXW);
-    const int x0 = tx0 + threadIdx.x * 4;
-    const int y0 = ty0 + threadIdx.y * RS_ROWS;
-    uint32_t sel[4], cc[4];
-    const int sxa = __ldg(&xtab[min(x0, dw - 1)]).x;                           // this thread's first source column
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int4 t = __ldg(&xtab[min(x0 + k, dw - 1)]);
-        const uint32_t o = (uint32_t)(t.x - sxa);                              // 0..4 at scale factors <= 1.35
-        sel[k] = o | (o + 1) << 4;
-        cc[k] = (uint32_t)t.z;
-    }
-    const int sh = ((sxa - xs) & 3) * 8;
-    mbar_wait(&bar, 0);
-    if (x0 >= dw || y0 >= dh) return;
-    uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch + x0;
-    const int yEnd = min(RS_ROWS, dh - y0);
-    int4 ty = sy[threadIdx.y * RS_ROWS];                                       // uniform across the warp
-    const int s0 = ty.x;
-    const uint8_t *base = tileS + (s0 - ys) * RS_BOXW + ((sxa - xs) & ~3);
-    uint32_t prev[4], cur[4];
-    resize_hrow(base, sh, sel, cc, prev);
-    int r = 0;
-#pragma unroll
-    for (int j = 1; j < RS_SRC_ROWS; j++) {
-        resize_hrow(base + j * RS_BOXW, sh, sel, cc, cur);
-        if (ty.x - s0 == j - 1) {                                              // (prev, cur) = source rows (sy0, sy0+1) of output row r
-            // 16-bit pairs: (b0*h0 >> 16 | b0*h0' >> 16 << 16) + (b1*h1 ...) + (2 | 2 << 16), each half <= 1023
-            const uint32_t b0 = (uint32_t)ty.z, b1 = (uint32_t)ty.w;
-            const uint32_t w01 = __byte_perm(b0 * prev[0], b0 * prev[1], 0x7632) + __byte_perm(b1 * cur[0], b1 * cur[1], 0x7632) + 0x00020002u;
-            const uint32_t w23 = __byte_perm(b0 * prev[2], b0 * prev[3], 0x7632) + __byte_perm(b1 * cur[2], b1 * cur[3], 0x7632) + 0x00020002u;
-            *(uint32_t *)(dst + (size_t)r * dstPitch) = __byte_perm(w01 >> 2, w23 >> 2, 0x6420);     // bytes past dw land in the pitch padding
-            if (++r >= yEnd) return;
-            ty = sy[threadIdx.y * RS_ROWS + r];
+
+    if (warp == 4) {
+        // ---- producer: one lane keeps RS_STAGES boxes in flight
+        if (lane == 0) {
+            int lastXY = -1, xs = 0, ys = 0;
+            for (int t = t0; t < t1; t++) {
+                const int i = t - t0, b = i % RS_STAGES;
+                const int xy = t / batch, f = t - xy * batch;
+                if (xy != lastXY) {
+                    const int txi = xy / tilesY, tyi = xy - txi * tilesY;
+                    xs = __ldg(&xtab[txi * RS_TW]).x & ~15;      // box origin: first source column, 16-aligned
+                    ys = __ldg(&ytab[tyi * RS_TH]).x;            //             first source row
+                    lastXY = xy;
+                }
+                if (i >= RS_STAGES) mbar_wait(&empty[b], ((i / RS_STAGES) - 1) & 1);
+                tma_load_tile_3d(tileS[b], srcMap, xs, ys, f0 + f, &full[b], RS_BOXH * RS_BOXW);
+            }
         }
+        return;
+    }
+
+    // ---- consumers
+    int lastXY = -1;
+    int xs = 0, ys = 0, sxa = 0, sh = 0, x0 = 0, y0 = 0;
+    uint32_t sel[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+    for (int t = t0; t < t1; t++) {
+        const int i = t - t0, b = i % RS_STAGES;
+        const int xy = t / batch, f = t - xy * batch;
+        if (xy != lastXY) {
+            const int txi = xy / tilesY, tyi = xy - txi * tilesY;
+            const int tx0 = txi * RS_TW, ty0 = tyi * RS_TH;
+            x0 = tx0 + lane * 4; y0 = ty0 + warp * RS_ROWS;
+            __syncwarp();
+            if (lane < RS_ROWS) sy[warp][lane] = __ldg(&ytab[min(y0 + lane, dh - 1)]);   // {sy0, sy0+1, b0, b1}
+            xs = __ldg(&xtab[tx0]).x & ~15;
+            ys = __ldg(&ytab[ty0]).x;
+            sxa = __ldg(&xtab[min(x0, dw - 1)]).x;                                       // this thread's first source column
 #pragma unroll
-        for (int k = 0; k < 4; k++) prev[k] = cur[k];
+            for (int k = 0; k < 4; k++) {
+                const int4 tt = __ldg(&xtab[min(x0 + k, dw - 1)]);
+                const uint32_t o = (uint32_t)(tt.x - sxa);                               // 0..4 at scale factors <= 1.35
+                sel[k] = o | (o + 1) << 4;
+                cc[k] = (uint32_t)tt.z;
+            }
+            sh = ((sxa - xs) & 3) * 8;
+            lastXY = xy;
+            __syncwarp();
+        }
+        mbar_wait(&full[b], (i / RS_STAGES) & 1);
+        if (x0 < dw && y0 < dh) {
+            uint8_t *dst = pyr + (size_t)f * slab + dstOff + (size_t)y0 * dstPitch + x0;
+            const int yEnd = min(RS_ROWS, dh - y0);
+            int4 ty = sy[warp][0];                                                       // uniform across the warp
+            const int s0 = ty.x;
+            const uint8_t *base = tileS[b] + (s0 - ys) * RS_BOXW + ((sxa - xs) & ~3);
+            uint32_t prev[4], cur[4];
+            resize_hrow(base, sh, sel, cc, prev);
+            int r = 0;
+#pragma unroll
+            for (int j = 1; j < RS_SRC_ROWS; j++) {
+                resize_hrow(base + j * RS_BOXW, sh, sel, cc, cur);
+                if (ty.x - s0 == j - 1) {                                                // (prev, cur) = source rows (sy0, sy0+1) of output row r
+                    // 16-bit pairs: (b0*h0 >> 16 | b0*h0' >> 16 << 16) + (b1*h1 ...) + (2 | 2 << 16), each half <= 1023
+                    const uint32_t b0 = (uint32_t)ty.z, b1 = (uint32_t)ty.w;
+                    const uint32_t w01 = __byte_perm(b0 * prev[0], b0 * prev[1], 0x7632) + __byte_perm(b1 * cur[0], b1 * cur[1], 0x7632) + 0x00020002u;
+                    const uint32_t w23 = __byte_perm(b0 * prev[2], b0 * prev[3], 0x7632) + __byte_perm(b1 * cur[2], b1 * cur[3], 0x7632) + 0x00020002u;
+                    *(uint32_t *)(dst + (size_t)r * dstPitch) = __byte_perm(w01 >> 2, w23 >> 2, 0x6420);     // bytes past dw land in the pitch padding
+                    if (++r >= yEnd) break;
+                    ty = sy[warp][r];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) prev[k] = cur[k];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[b]);
     }
 }
 
-void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, cudaStream_t st)
+void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, int nSM, cudaStream_t st)
 {
     const OrbxLevel &d = L.lv[level];
-    dim3 grid((d.w + RS_TW - 1) / RS_TW, (d.h + RS_TH - 1) / RS_TH, batch);
-    k_resize<<<grid, dim3(32, 4), 0, st>>>(srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
-                                           tabs + d.xtabOff, tabs + d.ytabOff);
+    const int tilesX = (d.w + RS_TW - 1) / RS_TW, tilesY = (d.h + RS_TH - 1) / RS_TH;
+    const int nTiles = tilesX * tilesY * batch;
+    const int tilesPerCta = std::max(1, (nTiles + nSM * 8 - 1) / (nSM * 8));
+    const int grid = (nTiles + tilesPerCta - 1) / tilesPerCta;
+    k_resize<<<grid, 160, 0, st>>>(srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
+                                   tabs + d.xtabOff, tabs + d.ytabOff, tilesY, batch, nTiles, tilesPerCta);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -604,29 +656,36 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 }
 
 // ------------------------------------------------------------------------------------------
-// DistributeOctTree (A.5): one CTA per (level, frame) replays the reference's list algorithm
-// level-synchronously.  A node is (strip, [y0,y1)); its size is a difference of the per-strip
-// prefix sums P of the row counts, so dividing a node is O(1).
+// DistributeOctTree (A.5): one CTA per (level, frame); warp 0 replays the reference's list
+// algorithm round by round with warp-synchronous scans (no block barriers inside the rounds), the
+// other warps only help with the row prefix sums in front and with the output stage behind.
+// A node is (strip, [y0,y1)); its size is a difference of the per-strip prefix sums P of the row
+// counts, so dividing a node is O(1).
 //   main pass   : every node with >1 point is divided; children go to the list front in the
 //                 order n2, n4 (=> n4 first), parents processed front to back     (:735-808)
-//   priority    : nodes sorted by (size, creation) descending, divided until size >= N (:814-878)
+//   priority    : nodes ordered by (size, creation) descending, divided until size >= N (:814-878).
+//                 The order comes from a stable LSD counting sort on the size (10 bits per pass,
+//                 __match_any ranks inside a chunk of 32), started from the tie order.
 //   output      : per node the max-response point, first in emission order on ties  (:885-901)
 // Under a monotone allocator "higher address" == "created later"; all expandable nodes of a
 // round were created in the previous round and sit at the list front in reverse creation order,
 // so "newest first" == "lowest list position first".
 // ------------------------------------------------------------------------------------------
-#define OCT_T 256
+#define OCT_T 128
+#define OCT_BUCKETS 1024
 __device__ __forceinline__ uint32_t node_pack(int s, int y0, int y1) { return (uint32_t)s << 26 | (uint32_t)y0 << 13 | (uint32_t)y1; }
 
 struct OctSh {
-    int n, rec, jstar, totC, R;
+    int n, which;
     int scan[34];
 };
 
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
 __global__ void __launch_bounds__(OCT_T)
-k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
+k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
          const unsigned long long *__restrict__ best, int2 *__restrict__ slots,
-         int *__restrict__ lvlCount, int maxRows, int maxNodes, int pow2Nodes)
+         int *__restrict__ lvlCount, int maxRows, int maxNodes)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __shared__ OctSh sh;
@@ -634,211 +693,288 @@ k_octree(const __grid_constant__ OrbxLayout L, uint32_t *__restrict__ cnt,
     const OrbxLevel &lv = L.lv[level];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = lv.H, nR = lv.nIni * H, N = lv.quota;
+    const unsigned lt = lanemask_lt();
 
-    unsigned long long *keys = (unsigned long long *)sm_raw;         // pow2Nodes
-    unsigned long long *bestS = keys + pow2Nodes;                    // maxRows: best candidate of every (strip,row)
-    int *P = (int *)(bestS + maxRows);                               // maxRows + 1
-    uint32_t *cur = (uint32_t *)(P + maxRows + 1);                   // maxNodes
-    uint32_t *nxt = cur + maxNodes;
-    int *a = (int *)(nxt + maxNodes), *b = a + maxNodes, *c = b + maxNodes, *d = c + maxNodes;
+    int *P = (int *)sm_raw;                                          // maxRows + 1 (padded to 4)
+    int *bucket = P + ((maxRows + 4) & ~3);                          // OCT_BUCKETS
+    uint32_t *listA = (uint32_t *)(bucket + OCT_BUCKETS);            // maxNodes
+    uint32_t *listB = listA + maxNodes;
+    uint16_t *ordA = (uint16_t *)(listB + maxNodes);                 // maxNodes each
+    uint16_t *ordB = ordA + maxNodes;
+    uint8_t *done = (uint8_t *)(ordB + maxNodes);                    // maxNodes
 
     const uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     const unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
 
-    for (int i = tid; i < nR; i += OCT_T) { P[i] = (int)cntF[i]; bestS[i] = bestF[i]; }
+    for (int i = tid; i < nR; i += OCT_T) P[i] = (int)cntF[i];
     __syncthreads();
     const int totalCand = block_excl_scan(P, nR, sh.scan);
-    if (tid == 0) {
-        P[nR] = totalCand;
-        int n = 0;
-        for (int s = 0; s < lv.nIni; s++)           // :691-726 initial strips, empty ones erased
-            if (P[(s + 1) * H] - P[s * H] > 0) cur[n++] = node_pack(s, 0, H);
-        sh.n = n;
-    }
+    if (tid == 0) P[nR] = totalCand;
     __syncthreads();
-    int n = sh.n;
 
 #define NODE_DECODE(node) const int s_ = (node) >> 26, y0_ = ((node) >> 13) & 8191, y1_ = (node)&8191; const int pb_ = s_ * H
 #define NODE_SIZE() (P[pb_ + y1_] - P[pb_ + y0_])
 
-    bool finish = (n == 0);
-    while (!finish) {
-        const int prevSize = n;
-        // ---------------- main pass (one packed scan: children in the low half, untouched nodes in the high half)
-        int myrec = 0;
-        if (tid == 0) sh.rec = 0;
-        for (int i = tid; i < n; i += OCT_T) {
-            const uint32_t node = cur[i];
-            NODE_DECODE(node);
-            const int sz = NODE_SIZE();
-            if (sz > 1) {
-                const int mid = y0_ + ((y1_ - y0_) >> 1);      // :75 integer halfY
-                const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                a[i] = (c2 > 0) + (c4 > 0);
-                myrec += (c2 > 1) + (c4 > 1);
-            } else a[i] = 1 << 16;
+    if (warp == 0) {
+        uint32_t *cur = listA, *nxt = listB;
+        int n = 0;
+        {   // :691-726 initial strips, empty ones erased
+            const bool has = lane < lv.nIni && P[(lane + 1) * H] - P[lane * H] > 0;
+            const unsigned b = __ballot_sync(0xffffffffu, has);
+            if (has) cur[__popc(b & lt)] = node_pack(lane, 0, H);
+            n = __popc(b);
         }
-        __syncthreads();
-        if (myrec) atomicAdd(&sh.rec, myrec);
-        const int tot = block_excl_scan(a, n, sh.scan);
-        const int totC = tot & 0xffff, totN = tot >> 16;
-        for (int i = tid; i < n; i += OCT_T) {
-            const uint32_t node = cur[i];
-            NODE_DECODE(node);
-            const int sz = NODE_SIZE();
-            if (sz > 1) {
-                const int mid = y0_ + ((y1_ - y0_) >> 1);
-                const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                int pos = totC - ((a[i] & 0xffff) + (c2 > 0) + (c4 > 0));
-                if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
-                if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
-            } else {
-                nxt[totC + (a[i] >> 16)] = node;
+        __syncwarp();
+        bool finish = (n == 0);
+        while (!finish) {
+            const int prevSize = n;
+            // ---------------- main pass, sweep 1: totals
+            int totC = 0, totN = 0, rec = 0;
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t node = cur[i];
+                NODE_DECODE(node);
+                const int sz = NODE_SIZE();
+                if (sz > 1) {
+                    const int mid = y0_ + ((y1_ - y0_) >> 1);      // :75 integer halfY
+                    const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
+                    totC += (c2 > 0) + (c4 > 0);
+                    rec += (c2 > 1) + (c4 > 1);
+                } else totN++;
             }
-        }
-        __syncthreads();
-        { uint32_t *t = cur; cur = nxt; nxt = t; }
-        n = totC + totN;
-        const int nToExpand = sh.rec;
-        if (n > maxNodes) n = maxNodes; // cannot happen for supported shapes (see orbx_api geometry checks)
-        __syncthreads();
-
-        if (n >= N || n == prevSize) {
-            finish = true;
-        } else if (n + nToExpand * 3 > N) {
-            // ---------------- priority rounds
-            while (!finish) {
-                const int prev2 = n;
-                int p2 = 2; while (p2 < n) p2 <<= 1;
-                if (tid == 0) { sh.R = 0; }
-                __syncthreads();
-                int myR = 0;
-                for (int i = tid; i < p2; i += OCT_T) {
-                    unsigned long long key = 0;
-                    if (i < n) {
-                        const uint32_t node = cur[i];
-                        NODE_DECODE(node);
-                        const int sz = NODE_SIZE();
-                        if (sz > 1) {
-                            key = (unsigned long long)sz << 16 | (unsigned)(L.tieRule ? i : 0xffff - i);
-                            myR++;
-                        }
-                    }
-                    keys[i] = key;
-                }
-                if (myR) atomicAdd(&sh.R, myR);
-                __syncthreads();
-                const int R = sh.R;
-                if (R == 0) { finish = true; break; }   // nothing expandable: size unchanged (:875)
-                for (int k = 2; k <= p2; k <<= 1)
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        for (int t = tid; t < p2; t += OCT_T) {
-                            const int x = t ^ j;
-                            if (x > t) {
-                                const unsigned long long ka = keys[t], kb = keys[x];
-                                const bool desc = (t & k) == 0;
-                                if ((ka < kb) == desc) { keys[t] = kb; keys[x] = ka; }
-                            }
-                        }
-                        __syncthreads();
-                    }
-                // sorted position j -> list index, children, gain
-                for (int j = tid; j < R; j += OCT_T) {
-                    const int low = (int)(keys[j] & 0xffff);
-                    const int i = L.tieRule ? low : 0xffff - low;
-                    const uint32_t node = cur[i];
+            totC = __reduce_add_sync(0xffffffffu, totC);
+            totN = __reduce_add_sync(0xffffffffu, totN);
+            rec = __reduce_add_sync(0xffffffffu, rec);
+            // ---------------- sweep 2: children to the front (later parents nearer the front), untouched nodes behind
+            int runC = 0, runN = 0;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                int nch = 0, c2 = 0, c4 = 0, mid = 0;
+                bool leaf = false;
+                uint32_t node = 0;
+                if (i < n) {
+                    node = cur[i];
                     NODE_DECODE(node);
                     const int sz = NODE_SIZE();
-                    const int mid = y0_ + ((y1_ - y0_) >> 1);
-                    const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                    const int nch = (c2 > 0) + (c4 > 0);
-                    a[j] = nch - 1; b[j] = nch;
+                    if (sz > 1) {
+                        mid = y0_ + ((y1_ - y0_) >> 1);
+                        c2 = P[pb_ + mid] - P[pb_ + y0_]; c4 = sz - c2;
+                        nch = (c2 > 0) + (c4 > 0);
+                    } else leaf = true;
                 }
-                if (tid == 0) sh.jstar = R - 1;
-                __syncthreads();
-                // keep the per-j child counts: scans run in place, so stash nch in d[]
-                for (int j = tid; j < R; j += OCT_T) d[j] = b[j];
-                __syncthreads();
-                block_excl_scan(a, R, sh.scan);
-                block_excl_scan(b, R, sh.scan);
-                for (int j = tid; j < R; j += OCT_T)
-                    if (n + a[j] + (d[j] - 1) >= N) atomicMin(&sh.jstar, j);  // :871 break once size >= N
-                __syncthreads();
-                const int jstar = sh.jstar;
-                if (tid == 0) sh.totC = b[jstar] + d[jstar];
-                for (int i = tid; i < n; i += OCT_T) c[i] = 1;
-                __syncthreads();
-                const int totC2 = sh.totC;
-                for (int j = tid; j <= jstar; j += OCT_T) {
-                    const int low = (int)(keys[j] & 0xffff);
-                    const int i = L.tieRule ? low : 0xffff - low;
-                    c[i] = 0;
-                    const uint32_t node = cur[i];
+                const unsigned b1 = __ballot_sync(0xffffffffu, nch == 1), b2 = __ballot_sync(0xffffffffu, nch == 2);
+                const unsigned bl = __ballot_sync(0xffffffffu, leaf);
+                if (nch) {
                     NODE_DECODE(node);
-                    const int sz = NODE_SIZE();
-                    const int mid = y0_ + ((y1_ - y0_) >> 1);
-                    const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
-                    int pos = totC2 - (b[j] + d[j]);      // later-processed parents' children sit nearer the front
+                    int pos = totC - (runC + __popc(b1 & lt) + 2 * __popc(b2 & lt) + nch);
                     if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
                     if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
+                } else if (leaf) {
+                    nxt[totC + runN + __popc(bl & lt)] = node;
                 }
-                __syncthreads();
-                for (int i = tid; i < n; i += OCT_T) a[i] = c[i];
-                __syncthreads();
-                const int totU = block_excl_scan(c, n, sh.scan);
-                for (int i = tid; i < n; i += OCT_T)
-                    if (a[i]) nxt[totC2 + c[i]] = cur[i];
-                __syncthreads();
-                { uint32_t *t = cur; cur = nxt; nxt = t; }
-                n = totC2 + totU;
-                if (n > maxNodes) n = maxNodes;
-                if (n >= N || n == prev2) finish = true;
-                __syncthreads();
+                runC += __popc(b1) + 2 * __popc(b2);
+                runN += __popc(bl);
+            }
+            __syncwarp();
+            { uint32_t *t = cur; cur = nxt; nxt = t; }
+            n = totC + totN;
+            const int nToExpand = rec;
+            if (n > maxNodes) n = maxNodes; // cannot happen for supported shapes (see orbx_api geometry checks)
+
+            if (n >= N || n == prevSize) {
+                finish = true;
+            } else if (n + nToExpand * 3 > N) {
+                // ---------------- priority rounds
+                while (!finish) {
+                    const int prev2 = n;
+                    // expandable nodes in list order, largest size
+                    int R = 0, maxSz = 0;
+                    for (int i0 = 0; i0 < n; i0 += 32) {
+                        const int i = i0 + lane;
+                        int sz = 0;
+                        if (i < n) { const uint32_t node = cur[i]; NODE_DECODE(node); sz = NODE_SIZE(); done[i] = 0; }
+                        const unsigned b = __ballot_sync(0xffffffffu, sz > 1);
+                        if (sz > 1) ordA[R + __popc(b & lt)] = (uint16_t)i;
+                        R += __popc(b);
+                        maxSz = max(maxSz, sz);
+                    }
+                    if (R == 0) { finish = true; break; }   // nothing expandable: size unchanged (:875)
+                    maxSz = __reduce_max_sync(0xffffffffu, maxSz);
+                    __syncwarp();
+                    // tie order: lowest list position first (tieRule 0) or highest first (tieRule 1)
+                    if (L.tieRule) {
+                        for (int k = lane; k < R / 2; k += 32) { const uint16_t a = ordA[k], b = ordA[R - 1 - k]; ordA[k] = b; ordA[R - 1 - k] = a; }
+                        __syncwarp();
+                    }
+                    // stable counting sort by size, descending, 10 bits per pass
+                    uint16_t *src = ordA, *dst = ordB;
+                    for (int shift = 0; (maxSz >> shift) > 0; shift += 10) {
+                        for (int k = lane; k < OCT_BUCKETS / 4; k += 32) ((int4 *)bucket)[k] = make_int4(0, 0, 0, 0);
+                        __syncwarp();
+                        for (int k = lane; k < R; k += 32) {
+                            const uint32_t node = cur[src[k]];
+                            NODE_DECODE(node);
+                            atomicAdd(&bucket[(OCT_BUCKETS - 1) - ((NODE_SIZE() >> shift) & (OCT_BUCKETS - 1))], 1);
+                        }
+                        __syncwarp();
+                        {   // exclusive scan of the buckets: lane owns 32 consecutive ones
+                            int4 v[8];
+                            int sum = 0;
+#pragma unroll
+                            for (int q = 0; q < 8; q++) { v[q] = ((int4 *)bucket)[lane * 8 + q]; sum += v[q].x + v[q].y + v[q].z + v[q].w; }
+                            int incl = sum;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                            int run = incl - sum;
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                int4 w;
+                                w.x = run; run += v[q].x; w.y = run; run += v[q].y; w.z = run; run += v[q].z; w.w = run; run += v[q].w;
+                                ((int4 *)bucket)[lane * 8 + q] = w;
+                            }
+                        }
+                        __syncwarp();
+                        for (int k0 = 0; k0 < R; k0 += 32) {
+                            const int k = k0 + lane;
+                            const unsigned act = __ballot_sync(0xffffffffu, k < R);
+                            if (k < R) {
+                                const int i = src[k];
+                                const uint32_t node = cur[i];
+                                NODE_DECODE(node);
+                                const int d = (OCT_BUCKETS - 1) - ((NODE_SIZE() >> shift) & (OCT_BUCKETS - 1));
+                                const unsigned peers = __match_any_sync(act, d);
+                                const int rank = __popc(peers & lt);
+                                const int base = bucket[d];
+                                __syncwarp(act);
+                                if (rank == 0) bucket[d] = base + __popc(peers);
+                                dst[base + rank] = (uint16_t)i;
+                            }
+                            __syncwarp();
+                        }
+                        { uint16_t *t = src; src = dst; dst = t; }
+                    }
+                    // sorted position j -> children count; stop once the list would reach N (:871)
+                    int jstar = R - 1, totC2 = 0, runG = 0;
+                    for (int j0 = 0; j0 < R; j0 += 32) {
+                        const int j = j0 + lane;
+                        int nch = 0;
+                        if (j < R) {
+                            const uint32_t node = cur[src[j]];
+                            NODE_DECODE(node);
+                            const int sz = NODE_SIZE();
+                            const int mid = y0_ + ((y1_ - y0_) >> 1);
+                            const int c2 = P[pb_ + mid] - P[pb_ + y0_], c4 = sz - c2;
+                            nch = (c2 > 0) + (c4 > 0);
+                        }
+                        const unsigned b1 = __ballot_sync(0xffffffffu, nch == 1), b2 = __ballot_sync(0xffffffffu, nch == 2);
+                        const unsigned le = lt | (1u << lane);
+                        const bool hit = j < R && n + runG + __popc(b2 & le) >= N;      // gain = nch - 1
+                        const unsigned bh = __ballot_sync(0xffffffffu, hit);
+                        if (bh) {
+                            const int l = __ffs(bh) - 1;
+                            const unsigned upto = (2u << l) - 1u;
+                            jstar = j0 + l;
+                            totC2 += __popc(b1 & upto) + 2 * __popc(b2 & upto);
+                            break;
+                        }
+                        runG += __popc(b2);
+                        totC2 += __popc(b1) + 2 * __popc(b2);
+                    }
+                    // children of the divided nodes: later-processed parents' children sit nearer the front
+                    int runC2 = 0;
+                    for (int j0 = 0; j0 <= jstar; j0 += 32) {
+                        const int j = j0 + lane;
+                        int nch = 0, c2 = 0, c4 = 0, mid = 0;
+                        uint32_t node = 0;
+                        if (j <= jstar) {
+                            const int i = src[j];
+                            done[i] = 1;
+                            node = cur[i];
+                            NODE_DECODE(node);
+                            const int sz = NODE_SIZE();
+                            mid = y0_ + ((y1_ - y0_) >> 1);
+                            c2 = P[pb_ + mid] - P[pb_ + y0_]; c4 = sz - c2;
+                            nch = (c2 > 0) + (c4 > 0);
+                        }
+                        const unsigned b1 = __ballot_sync(0xffffffffu, nch == 1), b2 = __ballot_sync(0xffffffffu, nch == 2);
+                        if (nch) {
+                            NODE_DECODE(node);
+                            int pos = totC2 - (runC2 + __popc(b1 & lt) + 2 * __popc(b2 & lt) + nch);
+                            if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
+                            if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
+                        }
+                        runC2 += __popc(b1) + 2 * __popc(b2);
+                    }
+                    __syncwarp();
+                    // the rest keeps its list order behind the new children
+                    int runU = 0;
+                    for (int i0 = 0; i0 < n; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool keep = i < n && !done[i];
+                        const unsigned b = __ballot_sync(0xffffffffu, keep);
+                        if (keep) nxt[totC2 + runU + __popc(b & lt)] = cur[i];
+                        runU += __popc(b);
+                    }
+                    __syncwarp();
+                    { uint32_t *t = cur; cur = nxt; nxt = t; }
+                    n = totC2 + runU;
+                    if (n > maxNodes) n = maxNodes;
+                    if (n >= N || n == prev2) finish = true;
+                }
             }
         }
+        if (lane == 0) { sh.n = n; sh.which = (cur == listA) ? 0 : 1; }
     }
+    __syncthreads();
 
-    // ---------------- output: best point of each node, list order (:885-901)
-    int2 *out = slots + (size_t)frame * L.slotsPerFrame + lv.slotBase;
-    const int nOut = n < lv.slotCap ? n : lv.slotCap;
-    for (int i = warp; i < nOut; i += OCT_T / 32) {
-        const uint32_t node = cur[i];
-        NODE_DECODE(node);
-        unsigned long long k = 0;
-        for (int y = y0_ + lane; y < y1_; y += 32) {
-            const unsigned long long v = bestS[pb_ + y];
-            k = v > k ? v : k;
-        }
+    // ---------------- output: best point of each node, list order (:885-901); 8 lanes per node
+    {
+        const int n = sh.n;
+        const uint32_t *cur = sh.which ? listB : listA;
+        int2 *out = slots + (size_t)frame * L.slotsPerFrame + lv.slotBase;
+        const int nOut = n < lv.slotCap ? n : lv.slotCap;
+        const int sub = lane & 7;
+        for (int i0 = warp * 4; i0 < nOut; i0 += (OCT_T / 32) * 4) {
+            const int i = i0 + (lane >> 3);
+            unsigned long long k = 0;
+            if (i < nOut) {
+                const uint32_t node = cur[i];
+                NODE_DECODE(node);
+                for (int y = y0_ + sub; y < y1_; y += 8) {
+                    const unsigned long long v = __ldg(&bestF[pb_ + y]);
+                    k = v > k ? v : k;
+                }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long v = __shfl_xor_sync(0xffffffffu, k, o);
-            k = v > k ? v : k;
+            for (int o = 4; o > 0; o >>= 1) {
+                const unsigned long long v = __shfl_xor_sync(0xffffffffu, k, o);
+                k = v > k ? v : k;
+            }
+            if (sub == 0 && i < nOut) {
+                const int x = (int)((k >> 14) & 0x3fff), y = (int)(k & 0x3fff), sc = (int)(k >> 56);
+                out[i] = make_int2(x | (y << 16), sc);
+            }
         }
-        if (lane == 0) {
-            const int x = (int)((k >> 14) & 0x3fff), y = (int)(k & 0x3fff), sc = (int)(k >> 56);
-            out[i] = make_int2(x | (y << 16), sc);
-        }
+        if (tid == 0) lvlCount[frame * L.nlevels + level] = nOut;
     }
-    if (tid == 0) lvlCount[frame * L.nlevels + level] = nOut;
 #undef NODE_DECODE
 #undef NODE_SIZE
 }
 
-size_t octree_smem_bytes(int maxRows, int maxNodes, int pow2Nodes)
+size_t octree_smem_bytes(int maxRows, int maxNodes)
 {
-    return (size_t)pow2Nodes * 8 + (size_t)maxRows * 8 + (size_t)(maxRows + 1) * 4 + (size_t)maxNodes * 4 * 6 + 16;
+    return (size_t)((maxRows + 4) & ~3) * 4 + (size_t)OCT_BUCKETS * 4 + (size_t)maxNodes * (4 * 2 + 2 * 2 + 1) + 16;
 }
 
-cudaError_t launch_octree(const OrbxLayout &L, uint32_t *cnt, const unsigned long long *best, int2 *slots,
-                          int *lvlCount, int maxRows, int maxNodes, int pow2Nodes, int batch, cudaStream_t st)
+cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsigned long long *best, int2 *slots,
+                          int *lvlCount, int maxRows, int maxNodes, int batch, cudaStream_t st)
 {
-    const size_t smem = octree_smem_bytes(maxRows, maxNodes, pow2Nodes);
+    const size_t smem = octree_smem_bytes(maxRows, maxNodes);
     if (smem > 48 * 1024) { // opt in per call: the attribute is per device and this is a cheap host-side set
         cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(L.nlevels, batch);
-    k_octree<<<grid, OCT_T, smem, st>>>(L, cnt, best, slots, lvlCount, maxRows, maxNodes, pow2Nodes);
+    k_octree<<<grid, OCT_T, smem, st>>>(L, cnt, best, slots, lvlCount, maxRows, maxNodes);
     return cudaSuccess;
 }
 
