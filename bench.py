@@ -224,7 +224,6 @@ def main():
 
     ex = orbx.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, max_width=W, max_height=H, max_batch=BATCH, device=local_rank)
     stream = torch.cuda.Stream(device=dev)
-    launches_per_step = 1 + (NLEVELS - 1) + 2 + 1 + 1 + 1    # copy + 7 resize + 2 FAST (level 0 | upper levels) + blur + octree + describe
 
     def step_dev(i):
         d = dev_pool[i % POOL]
@@ -232,6 +231,7 @@ def main():
 
     for i in range(args.warmup):
         step_dev(i)
+    launches_per_step = ex.last_launches()   # counted by the library: copy + 7 resize + 2 FAST + blur + octree + describe per half batch
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -251,9 +251,10 @@ def main():
     out = (torch.zeros(BATCH * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap),
            torch.zeros((BATCH, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(BATCH, np.int32))
     host_np = [[hb[f].numpy() for f in range(BATCH)] for hb in host_pool]
+    host_ptrs = [orbx.Extractor.frame_pointers(fr) for fr in host_np]     # the `const uint8_t *const *` a C++ caller passes
 
     def step_e2e(i):
-        ex.extract_batch(host_np[i % POOL], out=out)
+        ex.extract_batch_ptrs(host_ptrs[i % POOL], BATCH, W, H, W, out)
 
     for i in range(args.warmup):
         step_e2e(i)
@@ -264,10 +265,24 @@ def main():
     barrier()
     s_e2e = time.perf_counter() - t0
     n_kp = int(out[2].sum())
+    launches_e2e = ex.last_launches()
+
     clk = clocks.stop() if rank == 0 else None
 
     # ---- per-stage device times -> dominant kernel for the roofline line
     stages = ex.profile_stages(reps=5)
+
+    # ---- latency of the call OrbFrame makes: one frame (and one stereo pair) through the host entry point
+    lat = {}
+    for nb, key in ((1, "single_frame_ms"), (2, "stereo_pair_ms")):
+        ptrs = orbx.Extractor.frame_pointers(host_np[0][:nb])
+        o = (out[0][:nb], out[1][:nb], out[2][:nb])
+        for _ in range(10):
+            ex.extract_batch_ptrs(ptrs, nb, W, H, W, o)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            ex.extract_batch_ptrs(ptrs, nb, W, H, W, o)
+        lat[key] = (time.perf_counter() - t0) / 100 * 1e3
 
     # ---- matching: query-sharded kNN-2, one all_gather of the result records
     q, t = synth.matching_set(NQ, NT)
@@ -333,6 +348,8 @@ def main():
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * W * H,
                     "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": n_kp},
             "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": {"device_resident": launches_per_step, "e2e": launches_e2e},
+            "latency": dict(lat, note="orbx_extract_batch with 1 / 2 frames of 1241x376, pinned host buffers, H2D + kernels + D2H, mean of 100 calls"),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this stage, bytes per 64-frame step)",
                          "peak_source": peak_src,

@@ -117,6 +117,9 @@ int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *righ
 /* upper bound of keypoints per frame for this configuration */
 int orbx_max_keypoints(const orbx_extractor *h);
 
+/* Number of kernel launches the last orbx_extract* call enqueued (all chunks / halves); for benchmark accounting. */
+int orbx_last_launches(const orbx_extractor *h);
+
 /* m_vImagePyramid[level] of frame `frame` of the last call (orbextractor.hpp:109; read by
  * OrbFrame::ComputeStereoMatches, orbframe.cpp:518,618-641).  Copies the level lazily to a
  * pinned host buffer owned by the handle; pointer valid until the next extract call. */

@@ -54,6 +54,7 @@ template <typename T> struct PinBuf {
 
 } // namespace
 
+#define ORBX_LANES 4
 struct orbx_extractor {
     orbx_config cfg;
     // constructor tables
@@ -78,12 +79,12 @@ struct orbx_extractor {
     struct Lane {
         cudaStream_t main = nullptr, side = nullptr;
         cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr, evStart = nullptr, evDone = nullptr;
-    } lane[2];
+    } lane[ORBX_LANES];
     cudaStream_t streamIn = nullptr, streamOut = nullptr;
     // CUDA graphs of the per-chunk kernel pipeline of the host entry point (level-0 copy .. describe, both
     // streams of a lane): one cudaGraphLaunch replaces ~25 launches / event calls per chunk.  Keyed by
     // (first frame, frames, lane); dropped whenever geometry or an arena pointer changes.
-    struct ChunkGraph { int f0, nf, lane; cudaGraphExec_t exec; };
+    struct ChunkGraph { int f0, nf, lane, launches; cudaGraphExec_t exec; };
     std::vector<ChunkGraph> graphs;
     uint64_t graphSig = 0;
     std::vector<cudaEvent_t> evChunk;
@@ -113,6 +114,7 @@ struct orbx_extractor {
     PinBuf<int> hCounts;
     int dbgEnabled = 0, dbgCap = 0;
     int lastBatch = 0;
+    int lastLaunches = 0;            // kernel launches enqueued by the last extract call
     int nSM = 148;
     std::string err;
 };
@@ -382,7 +384,7 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         }
     }
     CK(h->dTmaps.ensure(3));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_LANES; i++) {
         CK(cudaStreamSynchronize(h->lane[i].main));
         CK(cudaStreamSynchronize(h->lane[i].side));
     }
@@ -455,6 +457,8 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
     CK(cudaGetLastError());
+    // level-0 copy (by the caller of this function) + resize chain + FAST (level 0 | upper levels) + blur + octree + describe
+    h->lastLaunches += 1 + (L.nlevels - 1) + (segs0 > 0) + (L.totalSegs - segs0 > 0) + 1 + 1 + 1;
     return ORBX_OK;
 }
 
@@ -476,14 +480,15 @@ void dropGraphs(orbx_extractor *h)
 }
 
 // the kernel pipeline of frames [f0, f0+nf) of the host staging buffer as an executable graph on lane `li`
-int chunkGraph(orbx_extractor *h, int f0, int nf, int li, size_t frameBytes, int width, cudaGraphExec_t *out)
+int chunkGraph(orbx_extractor *h, int f0, int nf, int li, size_t frameBytes, int width, cudaGraphExec_t *out, int *launches)
 {
     const uint64_t sig = arenaSignature(h);
     if (sig != h->graphSig) { dropGraphs(h); h->graphSig = sig; }
-    for (auto &g : h->graphs) if (g.f0 == f0 && g.nf == nf && g.lane == li) { *out = g.exec; return ORBX_OK; }
+    for (auto &g : h->graphs) if (g.f0 == f0 && g.nf == nf && g.lane == li) { *out = g.exec; *launches = g.launches; return ORBX_OK; }
     const orbx_extractor::Lane &ln = h->lane[li];
     const OrbxLayout &L = h->L;
     cudaGraph_t graph = nullptr;
+    const int before = h->lastLaunches;
     CK(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeRelaxed));
     launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, ln.main);
     int rc = enqueuePipeline(h, f0, nf, ln.main, ln);
@@ -494,7 +499,9 @@ int chunkGraph(orbx_extractor *h, int f0, int nf, int li, size_t frameBytes, int
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return failCuda(h, e, "cudaGraphInstantiate");
-    h->graphs.push_back({f0, nf, li, exec});
+    *launches = h->lastLaunches - before;
+    h->lastLaunches = before;
+    h->graphs.push_back({f0, nf, li, *launches, exec});
     *out = exec;
     return ORBX_OK;
 }
@@ -548,7 +555,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(h, ORBX_ERR_CUDA, "liborbx is built for sm_100a only (no other code path exists)");
     h->nSM = prop.multiProcessorCount;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_LANES; i++) {
         orbx_extractor::Lane &ln = h->lane[i];
         CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ln.side, cudaStreamNonBlocking));
@@ -573,7 +580,7 @@ void orbx_destroy(orbx_extractor *h)
 {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_LANES; i++) {
         if (h->lane[i].main) cudaStreamSynchronize(h->lane[i].main);
         if (h->lane[i].side) cudaStreamSynchronize(h->lane[i].side);
     }
@@ -587,7 +594,7 @@ void orbx_destroy(orbx_extractor *h)
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
     h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
     h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_LANES; i++) {
         orbx_extractor::Lane &ln = h->lane[i];
         cudaEvent_t evs[6] = {ln.evFork, ln.evJoin, ln.evFast0, ln.evPyr, ln.evStart, ln.evDone};
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -602,6 +609,8 @@ void orbx_destroy(orbx_extractor *h)
 const char *orbx_last_error(const orbx_extractor *h) { return h ? h->err.c_str() : "null handle"; }
 
 int orbx_max_keypoints(const orbx_extractor *h) { return h ? h->L.kpStride : ORBX_ERR_ARG; }
+
+int orbx_last_launches(const orbx_extractor *h) { return h ? h->lastLaunches : ORBX_ERR_ARG; }
 
 int orbx_scale_tables(const orbx_extractor *h, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2, int *quota)
 {
@@ -629,6 +638,7 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     if (rc != ORBX_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->lastBatch = batch;
+    h->lastLaunches = 0;
     static const int splitEnv = getenv("ORBX_SPLIT") ? atoi(getenv("ORBX_SPLIT")) : 0;
     const int nSplit = splitEnv > 0 ? std::min(splitEnv, 2) : (batch >= 16 ? 2 : 1);
     if (nSplit == 1 || batch < 2) {
@@ -693,14 +703,35 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     orbx_keypoint_pod *hk = directOut ? (orbx_keypoint_pod *)kps : h->hKps.p;
     uint8_t *hd = directOut ? desc : h->hDesc.p;
 
-    int nChunks = batch >= 32 ? 4 : (batch >= 8 ? 2 : 1);
+    // chunk boundaries: cb[c] .. cb[c+1].  ORBX_CHUNK_PLAN="4,12,16,..." gives explicit sizes (the last chunk takes the rest),
+    // ORBX_CHUNKS=n gives n equal chunks
+    // default: chunks of about 4 MB of input (8 KITTI-sized frames) keep the H2D engine, the kernels and the D2H engine
+    // busy at the same time; measured best on B200 with three lanes (scripts/probe/e2e_plans.py)
+    const int chunkFrames = std::max(1, (int)((size_t)(4u << 20) / frameBytes));
+    int nChunks = std::max(1, std::min(16, (batch + chunkFrames - 1) / chunkFrames));
     if (const char *e = getenv("ORBX_CHUNKS")) nChunks = std::max(1, std::min(batch, atoi(e)));
+    std::vector<int> cb;
+    if (const char *e = getenv("ORBX_CHUNK_PLAN")) {
+        cb.push_back(0);
+        for (const char *p = e; *p && cb.back() < batch;) {
+            const int v = atoi(p);
+            if (v > 0) cb.push_back(std::min(batch, cb.back() + v));
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+        }
+        if (cb.back() < batch) cb.push_back(batch);
+        nChunks = (int)cb.size() - 1;
+    } else {
+        for (int c = 0; c <= nChunks; c++) cb.push_back((int)((long long)batch * c / nChunks));
+    }
+    static const int nLanes = getenv("ORBX_LANES") ? std::max(1, std::min(ORBX_LANES, atoi(getenv("ORBX_LANES")))) : 3;
     if ((int)h->evChunk.size() < 2 * nChunks) {
         const size_t old = h->evChunk.size();
         h->evChunk.resize(2 * nChunks, nullptr);
         for (size_t i = old; i < h->evChunk.size(); i++) CK(cudaEventCreateWithFlags(&h->evChunk[i], cudaEventDisableTiming));
     }
     cudaStream_t sIn = h->streamIn, sOut = h->streamOut;
+    h->lastLaunches = 0;
     static const bool trace = getenv("ORBX_TRACE") != nullptr;
     if (trace) {
         while ((int)h->evTrace.size() < 1 + 3 * nChunks) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->evTrace.push_back(e); }
@@ -708,7 +739,7 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     }
     static const bool useGraphs = !(getenv("ORBX_NO_GRAPH") && atoi(getenv("ORBX_NO_GRAPH")));
     for (int c = 0; c < nChunks; c++) {
-        const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
+        const int f0 = cb[c], f1 = cb[c + 1];
         const int nf = f1 - f0;
         if (nf <= 0) continue;
         // ---- H2D into the tight staging buffer: one copy per run of frames that are contiguous on the host
@@ -731,14 +762,17 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         CK(cudaEventRecord(h->evChunk[2 * c], sIn));
         if (trace) CK(cudaEventRecord(h->evTrace[1 + 3 * c], sIn));
         // ---- kernels of this chunk (chunks alternate between the two lanes)
-        const orbx_extractor::Lane &ln = h->lane[c & 1];
+        const int li = c % nLanes;
+        const orbx_extractor::Lane &ln = h->lane[li];
         cudaStream_t sK = ln.main;
         CK(cudaStreamWaitEvent(sK, h->evChunk[2 * c], 0));
         if (useGraphs) {
             cudaGraphExec_t g = nullptr;
-            rc = chunkGraph(h, f0, nf, c & 1, frameBytes, width, &g);
+            int nl = 0;
+            rc = chunkGraph(h, f0, nf, li, frameBytes, width, &g, &nl);
             if (rc != ORBX_OK) return rc;
             CK(cudaGraphLaunch(g, sK));
+            h->lastLaunches += nl;
         } else {
             launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, sK);
             rc = enqueuePipeline(h, f0, nf, sK, ln);
@@ -761,7 +795,7 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     if (trace) clock_gettime(CLOCK_MONOTONIC, &tsE);
     int status = ORBX_OK;
     for (int c = 0; c < nChunks; c++) {
-        const int f0 = (int)((long long)batch * c / nChunks), f1 = (int)((long long)batch * (c + 1) / nChunks);
+        const int f0 = cb[c], f1 = cb[c + 1];
         if (f1 <= f0) continue;
         CK(cudaEventSynchronize(h->evChunk[2 * c]));
         for (int f = f0; f < f1; f++) {
@@ -780,8 +814,7 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         }
     }
     CK(cudaStreamSynchronize(sOut));
-    CK(cudaStreamSynchronize(h->lane[0].main));
-    CK(cudaStreamSynchronize(h->lane[1].main));
+    for (int i = 0; i < nLanes; i++) CK(cudaStreamSynchronize(h->lane[i].main));
     if (trace) {
         struct timespec tsD;
         clock_gettime(CLOCK_MONOTONIC, &tsD);

@@ -444,6 +444,14 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 #define FM_P 256  // shared score-map pitch
 
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+// shared-memory atomic add issued as-is (the compiler's own warp aggregation of atomicAdd is redundant where one lane adds for the warp)
+__device__ __forceinline__ int smem_atomic_add(int *p, int v)
+{
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 
 // largest threshold margin A of the pixel at c (window pitch FW_P); see stage 2 above
 __device__ __forceinline__ int fast_margin(const uint8_t *c)
@@ -491,7 +499,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     uint16_t *corner = cand + listCap;                               // listCap
     __shared__ __align__(8) uint64_t bar;
     __shared__ int ncand, ncorner;
-    __shared__ int anyIni[8];
+    __shared__ int anyIni[8], wsum[FS_T / 32];
     __shared__ uint8_t cellOf[ORBX_SEG_W];
 
     const OrbxSeg seg = segs[blockIdx.x];
@@ -499,6 +507,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     const OrbxLevel &lv = L.lv[seg.level];
     const int wT = seg.wT, hT = seg.hT;
     const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = lanemask_lt();
     const int th = L.minTh;
 
     // ---- stage 0: TMA fetches the window from the level's tensor map.  The box must start 16-byte aligned
@@ -514,11 +523,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     __syncthreads();
     if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);
     for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < wT) {
-        int cl = 0;
-        for (int b = lv.wCell; b <= tid; b += lv.wCell) cl++;
-        cellOf[tid] = (uint8_t)cl;
-    }
+    if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (65536u / (unsigned)lv.wCell + 1u)) >> 16);   // tid / wCell, exact for tid < 1024
     mbar_wait(&bar, 0);
     __syncthreads();
 
@@ -527,31 +532,63 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
         const int wq0 = B0 >> 2, wqL = (B0 + wT - 1) >> 2;
         const int nQ = wqL - wq0 + 1, items = nQ * hT;
-        const unsigned M = seg.mQ;                           // 2^20 / nQ + 1 (host)
         const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
         const int nLast = ((B0 + wT - 1) & 3) + 1;
         const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
         const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
-        for (int it = tid; it < items; it += FS_T) {
-            const int yIn = (int)(((unsigned)it * M) >> 20), q = it - yIn * nQ;
-            const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + wq0 + q;
-            const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
-            const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
-            const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
-            const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
-            const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
-            const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
-            uint32_t pass = X & Y & 0x80808080u;
-            if (q == 0) pass &= maskFirst;
-            if (q == nQ - 1) pass &= maskLast;
-            if (pass) {
-                int pos = atomicAdd(&ncand, __popc(pass));
-                const int e = (yIn << 8) + 4 * (wq0 + q) - B0;      // + j = yIn << 8 | xs for the valid pixels j of the quad
-                if (pass & 0x80u) cand[pos++] = (uint16_t)e;
-                if (pass & 0x8000u) cand[pos++] = (uint16_t)(e + 1);
-                if (pass & 0x800000u) cand[pos++] = (uint16_t)(e + 2);
-                if (pass & 0x80000000u) cand[pos] = (uint16_t)(e + 3);
+        // item -> (row, quad) advances by FS_T items per step: no division inside the loop.  The survivor flags of
+        // a thread's items are collected in a register (4 bits per item) and written out after ONE block-wide
+        // scan of the per-thread counts.
+        const int yIn0 = (int)(((unsigned)tid * seg.mQ) >> 20), q0 = tid - yIn0 * nQ;    // mQ = 2^20 / nQ + 1 (host)
+        const int dY = FS_T / nQ, dQ = FS_T - dY * nQ;
+        const int steps = (items + FS_T - 1) / FS_T;                                      // <= 16 (nQ <= 64, hT <= 60)
+        unsigned long long bits = 0;
+        int yIn = yIn0, q = q0;
+        for (int st = 0; st < steps; st++) {
+            if (yIn < hT) {
+                const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + wq0 + q;
+                const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
+                const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
+                const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
+                const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
+                const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
+                const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
+                uint32_t pass = X & Y & 0x80808080u;
+                if (q == 0) pass &= maskFirst;
+                if (q == nQ - 1) pass &= maskLast;
+                // flag bits 7,15,23,31 -> one nibble: the products land on distinct bits, the top four are the flags
+                bits |= (unsigned long long)((pass * 0x00204081u) >> 28) << (4 * st);
             }
+            yIn += dY; q += dQ;
+            if (q >= nQ) { q -= nQ; yIn++; }
+        }
+        // block-wide exclusive scan of the per-thread survivor counts
+        const int c = __popcll(bits);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[tid >> 5] = incl;
+        __syncthreads();
+        int pos = incl - c;
+#pragma unroll
+        for (int w = 0; w < FS_T / 32; w++) {
+            const int t = wsum[w];
+            if (w < (tid >> 5)) pos += t;
+            if (w == FS_T / 32 - 1 && tid == FS_T - 1) ncand = pos + c;
+        }
+        yIn = yIn0; q = q0;
+        for (int st = 0; st < steps && bits; st++) {
+            const unsigned nib = (unsigned)bits & 15u;
+            bits >>= 4;
+            if (nib) {
+                const int e = (yIn << 8) + 4 * (wq0 + q) - B0;      // + j = yIn << 8 | xs for the valid pixels j of the quad
+                if (nib & 1u) cand[pos++] = (uint16_t)e;
+                if (nib & 2u) cand[pos++] = (uint16_t)(e + 1);
+                if (nib & 4u) cand[pos++] = (uint16_t)(e + 2);
+                if (nib & 8u) cand[pos++] = (uint16_t)(e + 3);
+            }
+            yIn += dY; q += dQ;
+            if (q >= nQ) { q -= nQ; yIn++; }
         }
     }
     __syncthreads();
@@ -570,10 +607,10 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         const unsigned bal = __ballot_sync(0xffffffffu, isCorner);
         if (bal) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(&ncorner, __popc(bal));
+            if (lane == 0) base = smem_atomic_add(&ncorner, __popc(bal));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (isCorner) {
-                corner[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+                corner[base + __popc(bal & lt)] = (uint16_t)e;
                 smap[((e >> 8) + 1) * FM_P + (e & 255) + 1] = (uint8_t)(A - 1);
             }
         }
@@ -581,40 +618,54 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     __syncthreads();
     const int nk = ncorner;
 
-    // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0)
+    // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); the
+    // survivors are compacted into the (now free) survivor list
     const int wCell = lv.wCell;
-    for (int i = tid; i < nk; i += FS_T) {
-        const int e = corner[i];
-        const int yIn = e >> 8, xs = e & 255;
-        const int cl = cellOf[xs], xIn = xs - cl * wCell;
-        const uint8_t *s = &smap[(yIn + 1) * FM_P + xs + 1];
-        const int v = s[0];
-        const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
-        const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
-        const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
-        const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
-        if (v > m) {
-            corner[i] = (uint16_t)(e | 0x8000);
-            if (v >= L.iniTh) anyIni[cl] = 1;
+    if (tid == 0) ncand = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < nk; i0 += FS_T) {
+        const int i = i0 + tid;
+        bool isMax = false;
+        int e = 0;
+        if (i < nk) {
+            e = corner[i];
+            const int yIn = e >> 8, xs = e & 255;
+            const int cl = cellOf[xs], xIn = xs - cl * wCell;
+            const uint8_t *s = &smap[(yIn + 1) * FM_P + xs + 1];
+            const int v = s[0];
+            const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
+            const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
+            const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
+            const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
+            isMax = v > m;
+            if (isMax && v >= L.iniTh) anyIni[cl] = 1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, isMax);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = smem_atomic_add(&ncand, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (isMax) cand[base + __popc(bal & lt)] = (uint16_t)e;
         }
     }
     // per-cell threshold fallback, orbextractor.cpp:950-957: the ini-threshold result is used iff
     // it is non-empty after NMS; NMS(ini) == {k in NMS(min) : score >= ini}
     __syncthreads();
+    const int nm = ncand;
 
     // ---- stage 3b: emit into the per-(strip,row) summaries
     uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
-    for (int i = tid; i < nk; i += FS_T) {
-        const int e = corner[i];
-        if (!(e & 0x8000)) continue;
-        const int yIn = (e >> 8) & 127, xs = e & 255;
+    for (int i = tid; i < nm; i += FS_T) {
+        const int e = cand[i];
+        const int yIn = e >> 8, xs = e & 255;
         const int s = smap[(yIn + 1) * FM_P + xs + 1];
         const int cl = cellOf[xs], xIn = xs - cl * wCell;
         if (anyIni[cl] && s < L.iniTh) continue;
         const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
         int strip = 0;                                                                  // xr / hX, :710
-        for (int sB = lv.hX; sB <= xr; sB += lv.hX) strip++;
+#pragma unroll
+        for (int k = 1; k < ORBX_MAX_STRIPS; k++) strip += (xr >= k * lv.hX);
         const int row = strip * lv.H + yr;
         const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
         const unsigned long long key = ((unsigned long long)s << 56) |
@@ -673,14 +724,17 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 // ------------------------------------------------------------------------------------------
 #define OCT_T 128
 #define OCT_BUCKETS 1024
+// bytes of P, the sort buckets, the two node lists, the two order arrays and the flags, rounded up to 16
+__host__ __device__ inline size_t octree_lists_bytes(int maxRows, int maxNodes)
+{
+    return ((size_t)((maxRows + 4) & ~3) * 4 + (size_t)OCT_BUCKETS * 4 + (size_t)maxNodes * (4 * 2 + 2 * 2 + 1) + 15) & ~(size_t)15;
+}
 __device__ __forceinline__ uint32_t node_pack(int s, int y0, int y1) { return (uint32_t)s << 26 | (uint32_t)y0 << 13 | (uint32_t)y1; }
 
 struct OctSh {
     int n, which;
     int scan[34];
 };
-
-__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 __global__ void __launch_bounds__(OCT_T)
 k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
@@ -702,6 +756,7 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
     uint16_t *ordA = (uint16_t *)(listB + maxNodes);                 // maxNodes each
     uint16_t *ordB = ordA + maxNodes;
     uint8_t *done = (uint8_t *)(ordB + maxNodes);                    // maxNodes
+    unsigned long long *bestS = (unsigned long long *)(sm_raw + octree_lists_bytes(maxRows, maxNodes));   // maxRows
 
     const uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     const unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
@@ -923,6 +978,9 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
             }
         }
         if (lane == 0) { sh.n = n; sh.which = (cur == listA) ? 0 : 1; }
+    } else {
+        // meanwhile the other warps bring the per-row best candidates into shared memory for the output stage
+        for (int i = tid - 32; i < nR; i += OCT_T - 32) bestS[i] = __ldg(&bestF[i]);
     }
     __syncthreads();
 
@@ -940,7 +998,7 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
                 const uint32_t node = cur[i];
                 NODE_DECODE(node);
                 for (int y = y0_ + sub; y < y1_; y += 8) {
-                    const unsigned long long v = __ldg(&bestF[pb_ + y]);
+                    const unsigned long long v = bestS[pb_ + y];
                     k = v > k ? v : k;
                 }
             }
@@ -962,7 +1020,7 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
 
 size_t octree_smem_bytes(int maxRows, int maxNodes)
 {
-    return (size_t)((maxRows + 4) & ~3) * 4 + (size_t)OCT_BUCKETS * 4 + (size_t)maxNodes * (4 * 2 + 2 * 2 + 1) + 16;
+    return octree_lists_bytes(maxRows, maxNodes) + (size_t)maxRows * 8;
 }
 
 cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsigned long long *best, int2 *slots,

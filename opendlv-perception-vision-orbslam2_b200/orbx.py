@@ -35,7 +35,7 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_max_keypoints", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_pairs", "orbm_measure_popc"]
@@ -57,6 +57,7 @@ def lib():
     L.orbx_last_error.argtypes = [vp]
     L.orbx_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, ip]
     L.orbx_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
+    L.orbx_last_launches.argtypes = [vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.orbx_fetch_results.argtypes = [vp, vp, vp, C.c_int, vp, vp]
@@ -150,6 +151,21 @@ class Extractor:
         self._check(lib().orbx_extract_batch(self._h, ptrs, n, w, h, pitch, _ptr(kps), kps.shape[1], _ptr(desc), _ptr(counts)))
         return kps, desc, counts
 
+    @staticmethod
+    def frame_pointers(imgs):
+        """The `const uint8_t *const *` argument of orbx_extract_batch for a list of frames, built once and reusable
+        (what a C++ caller holds anyway); keeps the frames alive."""
+        ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
+        ptrs._frames = imgs
+        return ptrs
+
+    def extract_batch_ptrs(self, ptrs, n, width, height, pitch, out):
+        """orbx_extract_batch with a prepared pointer array and prepared output arrays: nothing but the C call."""
+        kps, desc, counts = out
+        self._check(lib().orbx_extract_batch(self._h, ptrs, n, width, height, pitch, kps.ctypes.data, kps.shape[1],
+                                             desc.ctypes.data, counts.ctypes.data))
+        return out
+
     def extract_batch_device(self, dptr, frame_stride, pitch, batch, width, height, stream=None):
         """Frames already in HBM (raw device pointer); results stay in HBM (see device_results)."""
         self._check(lib().orbx_extract_batch_device(self._h, C.c_void_p(dptr), frame_stride, pitch, batch, width, height,
@@ -165,6 +181,10 @@ class Extractor:
         kps = np.zeros((batch, cap), KP_DTYPE); desc = np.zeros((batch, cap, 32), np.uint8); counts = np.zeros(batch, np.int32)
         self._check(lib().orbx_fetch_results(self._h, C.c_void_p(stream) if stream else None, _ptr(kps), cap, _ptr(desc), _ptr(counts)))
         return kps, desc, counts
+
+    def last_launches(self):
+        """Kernel launches the last extract call enqueued (all chunks / halves), counted inside the library."""
+        return int(lib().orbx_last_launches(self._h))
 
     STAGES = ("resize", "fast", "octree", "blur", "describe")
 
