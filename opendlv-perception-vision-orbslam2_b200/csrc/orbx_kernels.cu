@@ -128,6 +128,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
                  ::"r"(b), "r"(phase) : "memory");
 }
 
+// ---- programmatic dependent launch: a kernel launched with the attribute below may start while its predecessor in the
+// stream is still draining; it must not touch the predecessor's output before pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------
 // pyramid resize, 11-bit fixed-point bilinear (A.1): level l from level l-1.
 // Work unit = 128 x 32 output tile of one frame; its source region -- at most 192 x 48 bytes at scale
@@ -184,12 +201,14 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_launch_dependents();       // the next level's kernel may set itself up; it waits for this grid before reading
     __syncthreads();
 
     if (warp == 4) {
         // ---- producer: one lane keeps RS_STAGES boxes in flight
         if (lane == 0) {
             int lastXY = -1, xs = 0, ys = 0;
+            pdl_wait();            // the source level is complete and visible (only the TMA loads read it)
             for (int t = t0; t < t1; t++) {
                 const int i = t - t0, b = i % RS_STAGES;
                 const int xy = t / batch, f = t - xy * batch;
@@ -271,8 +290,8 @@ void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxL
     const int nTiles = tilesX * tilesY * batch;
     const int tilesPerCta = std::max(1, (nTiles + nSM * 8 - 1) / (nSM * 8));
     const int grid = (nTiles + tilesPerCta - 1) / tilesPerCta;
-    k_resize<<<grid, 160, 0, st>>>(srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
-                                   tabs + d.xtabOff, tabs + d.ytabOff, tilesY, batch, nTiles, tilesPerCta);
+    launch_pdl(k_resize, dim3(grid), dim3(160), 0, st, srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
+               tabs + d.xtabOff, tabs + d.ytabOff, tilesY, batch, nTiles, tilesPerCta);
 }
 
 // ------------------------------------------------------------------------------------------
