@@ -288,8 +288,8 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         maxNodes = std::max(maxNodes, v.slotCap + 2);
         v.sf = h->sf[l]; v.invSf = h->invSf[l];
         v.kpSize = 31 * (int)h->sf[l];   // :978 int cast before the multiply
-        // blur tiles: 32 words x (4 strips of 32 rows)
-        for (int ty = 0; ty < v.h; ty += 128)
+        // blur tiles: 32 words x (4 bands of ORBX_BLUR_ROWS rows)
+        for (int ty = 0; ty < v.h; ty += 4 * ORBX_BLUR_ROWS)
             for (int tx = 0; tx * 4 < v.w; tx += 32) {
                 OrbxTile t; t.x0 = (uint16_t)tx; t.y0 = (uint16_t)ty; t.level = (uint8_t)l; t.pad[0] = t.pad[1] = t.pad[2] = 0;
                 tiles.push_back(t);
@@ -364,7 +364,7 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         const OrbxLevel &v = L.lv[l];
         cuuint64_t gdim[3] = {(cuuint64_t)v.w, (cuuint64_t)v.h, (cuuint64_t)frames};
         cuuint64_t gstr[2] = {(cuuint64_t)v.pitch, (cuuint64_t)L.slab};
-        cuuint32_t box[3] = {160, 134, 1};   // BL_BOXW x BL_BOXH of k_blur
+        cuuint32_t box[3] = {160, 4 * ORBX_BLUR_ROWS + 6, 1};   // BL_BOXW x BL_BOXH of k_blur
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -57,7 +57,8 @@ struct OrbxSeg {
     uint32_t mQ;         // 2^20/nQ + 1, nQ = aligned 4-pixel groups covering one tested row of the run
 };
 
-// one blur tile: 32 words (128 px) x 4 strips of 32 rows; x0 in 4-px words, y0 in rows
+#define ORBX_BLUR_ROWS 36       // output rows per warp band of k_blur; a tile is 4 bands
+// one blur tile: 32 words (128 px) x 4 bands of ORBX_BLUR_ROWS rows; x0 in 4-px words, y0 in rows
 struct OrbxTile { uint16_t x0, y0; uint8_t level, pad[3]; };
 
 // bilinear coefficient entry, SURVEY A.1.  x axis: {sx0, sx1, c0 | c1 << 16, 0}; y axis: {sy0, sy1, b0, b1}

@@ -304,7 +304,7 @@ void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxL
 // never touches shared or global memory.  A warp covers 128 columns; a CTA is 4 warps working
 // on 4 vertically adjacent strips of one tile; one launch covers every level (tile table).
 // ------------------------------------------------------------------------------------------
-#define BL_ROWS 32
+#define BL_ROWS ORBX_BLUR_ROWS   // 36: a band reads 36 + 6 = 42 = 6 x 7 input rows
 struct BlurTaps { int t[7]; };
 
 // Byte-permute selectors that apply REFLECT_101 at the right image edge to the 12-byte window
@@ -331,13 +331,13 @@ __device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint3
 
 // ------------------------------------------------------------------------------------------
 // TMA staging (cp.async.bulk.tensor): one elected thread of the CTA fetches the whole tile --
-// 128 columns + 2 x 16 bytes of halo, 128 rows + 6 rows of halo -- from the level's 3-D tensor map
+// 128 columns + 2 x 16 bytes of halo, 4 x 36 rows + 6 rows of halo -- from the level's 3-D tensor map
 // (x, y, frame) into shared memory; the hardware zero-fills what lies outside the image, and the
 // REFLECT_101 rows/columns are resolved when the tile is READ (reflected rows are inside the box:
 // the tile keeps 3 halo rows on both sides).  Completion is signalled on an mbarrier.
 // ------------------------------------------------------------------------------------------
 #define BL_BOXW 160   // bytes: 16 left + 128 + 16 right: TMA needs the box start 16-byte aligned in the inner dimension
-#define BL_BOXH 134   // rows: 3 + 128 + 3
+#define BL_BOXH (4 * BL_ROWS + 6)   // rows: 3 + 4 bands + 3
 
 __global__ void __launch_bounds__(128)
 k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
@@ -382,6 +382,55 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
     // thread's three words (bytes x0-4 .. x0+7) are words lane+3, lane+4, lane+5
     const uint32_t *ts = (const uint32_t *)tileS + threadIdx.x + 3;
     const int rowBias = 3 - (int)tile.y0;
+
+    // one input row: horizontal sums of the thread's 4 columns from shared row p, vertical sum over the last
+    // 7 rows; writes output row through dp when `store`
+    auto row = [&](const int s, const uint32_t *p, const bool store, uint8_t *dp) {
+        uint32_t W0 = p[0], W1 = p[1], W2 = p[2];
+        if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);      // left edge: index -k equals index k
+        const uint32_t T = __byte_perm(W0, W1, selT);
+        W2 = __byte_perm(T, W2, sel2);
+        W1 = __byte_perm(W0, W1, sel1);
+        // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
+        uint32_t hs[4];
+        hs[0] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
+        hs[1] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
+        hs[2] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
+        hs[3] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
+        uint32_t acc[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            pp[c][s] = __byte_perm(prev[c], hs[c], 0x5410);
+            prev[c] = hs[c];
+            // rows r-6..r with taps 0..6: pairs end in slots of rows r-5, r-3, r-1; row r alone
+            uint32_t a = 32768u + T6 * hs[c];
+            a = __dp2a_lo(pp[c][(s + 2) % 7], T01, a);
+            a = __dp2a_lo(pp[c][(s + 4) % 7], T23, a);
+            a = __dp2a_lo(pp[c][(s + 6) % 7], T45, a);
+            acc[c] = min(a, 0x00ffffffu);                    // result byte = bits 16..23, saturated
+        }
+        if (store) {
+            const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+            *(uint32_t *)dp = __byte_perm(lo, hi, 0x5410);
+        }
+    };
+
+    if (rows == BL_ROWS + 6 && y0 >= 3 && y0 + BL_ROWS + 3 <= h) {
+        // ---- interior band: no reflected rows, full height (a multiple of 7 input rows): straight pointer walks
+        const uint32_t *p = ts + (y0 - 3 + rowBias) * (BL_BOXW / 4);
+        uint8_t *dp = dst + (size_t)y0 * pitch;
+#pragma unroll
+        for (int s = 0; s < 6; s++) row(s, p + s * (BL_BOXW / 4), false, dp);
+        row(6, p + 6 * (BL_BOXW / 4), true, dp);
+        dp += pitch;
+#pragma unroll 1
+        for (int r0 = 7; r0 < BL_ROWS + 6; r0 += 7) {
+            p += 7 * (BL_BOXW / 4);
+#pragma unroll
+            for (int s = 0; s < 7; s++) { row(s, p + s * (BL_BOXW / 4), true, dp); dp += pitch; }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 7) {
 #pragma unroll
@@ -390,34 +439,7 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
             if (r < rows) {
                 int g = y0 + r - 3;                                  // REFLECT_101 (|overshoot| <= 3 < h)
                 g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
-                const uint32_t *p = ts + (g + rowBias) * (BL_BOXW / 4);
-                uint32_t W0 = p[0], W1 = p[1], W2 = p[2];
-                if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);      // left edge: index -k equals index k
-                const uint32_t T = __byte_perm(W0, W1, selT);
-                W2 = __byte_perm(T, W2, sel2);
-                W1 = __byte_perm(W0, W1, sel1);
-                // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
-                uint32_t hs[4];
-                hs[0] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
-                hs[1] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
-                hs[2] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
-                hs[3] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
-                uint32_t acc[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    pp[c][s] = __byte_perm(prev[c], hs[c], 0x5410);
-                    prev[c] = hs[c];
-                    // rows r-6..r with taps 0..6: pairs end in slots of rows r-5, r-3, r-1; row r alone
-                    uint32_t a = 32768u + T6 * hs[c];
-                    a = __dp2a_lo(pp[c][(s + 2) % 7], T01, a);
-                    a = __dp2a_lo(pp[c][(s + 4) % 7], T23, a);
-                    a = __dp2a_lo(pp[c][(s + 6) % 7], T45, a);
-                    acc[c] = min(a, 0x00ffffffu);                    // result byte = bits 16..23, saturated
-                }
-                if (r >= 6) {
-                    const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
-                    *(uint32_t *)(dst + (size_t)(y0 + r - 6) * pitch) = __byte_perm(lo, hi, 0x5410);
-                }
+                row(s, ts + (g + rowBias) * (BL_BOXW / 4), r >= 6, dst + (size_t)(y0 + r - 6) * pitch);
             }
         }
     }
