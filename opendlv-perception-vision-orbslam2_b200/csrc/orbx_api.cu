@@ -640,24 +640,26 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     h->lastBatch = batch;
     h->lastLaunches = 0;
     static const int splitEnv = getenv("ORBX_SPLIT") ? atoi(getenv("ORBX_SPLIT")) : 0;
-    const int nSplit = splitEnv > 0 ? std::min(splitEnv, 2) : (batch >= 16 ? 2 : 1);
-    if (nSplit == 1 || batch < 2) {
+    const int nSplit = std::min(batch, splitEnv > 0 ? std::min(splitEnv, ORBX_LANES) : (batch >= 16 ? 2 : 1));
+    if (nSplit == 1) {
         launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
         return enqueuePipeline(h, 0, batch, st, h->lane[0]);
     }
-    // two halves side by side: the first on the caller's stream, the second on lane 1, joined back at the end
-    const int b0 = batch / 2;
-    const orbx_extractor::Lane &l1 = h->lane[1];
-    CK(cudaEventRecord(l1.evStart, st));
-    CK(cudaStreamWaitEvent(l1.main, l1.evStart, 0));
-    launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, b0, st);
-    rc = enqueuePipeline(h, 0, b0, st, h->lane[0]);
-    if (rc != ORBX_OK) return rc;
-    launch_copy_level0(d_imgs + (size_t)b0 * frame_stride, frame_stride, pitch, h->dPyr.p + (size_t)b0 * h->L.slab, h->L, batch - b0, l1.main);
-    rc = enqueuePipeline(h, b0, batch - b0, l1.main, l1);
-    if (rc != ORBX_OK) return rc;
-    CK(cudaEventRecord(l1.evDone, l1.main));
-    CK(cudaStreamWaitEvent(st, l1.evDone, 0));
+    // nSplit parts side by side: the first on the caller's stream, the others on lanes 1.., joined back at the end
+    CK(cudaEventRecord(h->lane[0].evStart, st));
+    for (int k = 0; k < nSplit; k++) {
+        const int b0 = (int)((long long)batch * k / nSplit), b1 = (int)((long long)batch * (k + 1) / nSplit);
+        const orbx_extractor::Lane &ln = h->lane[k];
+        cudaStream_t sk = k == 0 ? st : ln.main;
+        if (k > 0) CK(cudaStreamWaitEvent(sk, h->lane[0].evStart, 0));
+        launch_copy_level0(d_imgs + (size_t)b0 * frame_stride, frame_stride, pitch, h->dPyr.p + (size_t)b0 * h->L.slab, h->L, b1 - b0, sk);
+        rc = enqueuePipeline(h, b0, b1 - b0, sk, ln);
+        if (rc != ORBX_OK) return rc;
+        if (k > 0) {
+            CK(cudaEventRecord(ln.evDone, sk));
+            CK(cudaStreamWaitEvent(st, ln.evDone, 0));
+        }
+    }
     return ORBX_OK;
 }
 

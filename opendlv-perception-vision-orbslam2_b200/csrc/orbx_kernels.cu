@@ -475,8 +475,8 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 //   2  exact test and corner score in one pass: with d_k = I(p) - I(ring_k),
 //        A = max( max_k min(d_k..d_k+8), -min_k max(d_k..d_k+8) )
 //      is the largest threshold margin of the pixel: it is a corner at threshold t iff A > t, and its
-//      cv::FAST response is A - 1.  The sliding 9-windows are evaluated on 16-bit pairs (d_k, d_k+8)
-//      with three-input packed min/max (VIMNMX3.S16x2): 16 + 16 of them cover all 16 windows.
+//      cv::FAST response is A - 1.  A thread evaluates two survivors at once, one in each 16-bit half of its
+//      registers, with three-input packed min/max (VIMNMX3.S16x2): 2 x (16 + 16) of them cover the 16 windows.
 //   3  3x3 NMS on the run's score map (neighbours in another cell count as 0, as each cell is an
 //      isolated cv::FAST call), per-cell threshold fallback, emission
 // ------------------------------------------------------------------------------------------
@@ -494,37 +494,34 @@ __device__ __forceinline__ int smem_atomic_add(int *p, int v)
     return old;
 }
 
-// largest threshold margin A of the pixel at c (window pitch FW_P); see stage 2 above
-__device__ __forceinline__ int fast_margin(const uint8_t *c)
+// largest threshold margins A of TWO pixels (window pitch FW_P), one per 16-bit half of every register; see stage 2 above.
+// E[k] = (256 + vA - ringA_k) | (256 + vB - ringB_k) << 16 : both halves in [1, 511], so the packed subtraction never
+// borrows across the halves and the packed three-input min/max (VIMNMX3.S16x2) serve both pixels at once.
+__device__ __forceinline__ void fast_margin2(const uint8_t *cA, const uint8_t *cB, int &mA, int &mB)
 {
-    // P[j] = (256 + v - ring_j) | (256 + v - ring_j+8) << 16 : both halves in [1, 511], so the packed
-    // subtraction never borrows across the halves
-    const uint32_t V2 = (uint32_t)c[0] * 0x10001u + 0x01000100u;
-    uint32_t E[10];
-#define ORBX_PAIR(o1, o2) (V2 - ((uint32_t)c[o1] | (uint32_t)c[o2] << 16))
-    E[0] = ORBX_PAIR(3 * FW_P, -3 * FW_P);          E[1] = ORBX_PAIR(3 * FW_P + 1, -3 * FW_P - 1);
-    E[2] = ORBX_PAIR(2 * FW_P + 2, -2 * FW_P - 2);  E[3] = ORBX_PAIR(FW_P + 3, -FW_P - 3);
-    E[4] = ORBX_PAIR(3, -3);                        E[5] = ORBX_PAIR(-FW_P + 3, FW_P - 3);
-    E[6] = ORBX_PAIR(-2 * FW_P + 2, 2 * FW_P - 2);  E[7] = ORBX_PAIR(-3 * FW_P + 1, 3 * FW_P - 1);
-#undef ORBX_PAIR
-    E[8] = swap16(E[0]); E[9] = swap16(E[1]);       // E[j+8] = halves of E[j] swapped: (d_j+8, d_j)
-    uint32_t tn[14], tx[14];
+    const uint32_t V2 = ((uint32_t)cA[0] | (uint32_t)cB[0] << 16) + 0x01000100u;
+    uint32_t E[16];
+#define ORBX_RING2(k, off) E[k] = V2 - ((uint32_t)cA[off] | (uint32_t)cB[off] << 16)
+    ORBX_RING2(0, 3 * FW_P);       ORBX_RING2(1, 3 * FW_P + 1);   ORBX_RING2(2, 2 * FW_P + 2);   ORBX_RING2(3, FW_P + 3);
+    ORBX_RING2(4, 3);              ORBX_RING2(5, -FW_P + 3);      ORBX_RING2(6, -2 * FW_P + 2);  ORBX_RING2(7, -3 * FW_P + 1);
+    ORBX_RING2(8, -3 * FW_P);      ORBX_RING2(9, -3 * FW_P - 1);  ORBX_RING2(10, -2 * FW_P - 2); ORBX_RING2(11, -FW_P - 3);
+    ORBX_RING2(12, -3);            ORBX_RING2(13, FW_P - 3);      ORBX_RING2(14, 2 * FW_P - 2);  ORBX_RING2(15, 3 * FW_P - 1);
+#undef ORBX_RING2
+    uint32_t tn[16], tx[16];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        tn[j] = __vmins2(__vmins2(E[j], E[j + 1]), E[j + 2]);    // min / max of d_j..d_j+2 | d_j+8..d_j+10
-        tx[j] = __vmaxs2(__vmaxs2(E[j], E[j + 1]), E[j + 2]);
+    for (int j = 0; j < 16; j++) {
+        tn[j] = __vmins2(__vmins2(E[j], E[(j + 1) & 15]), E[(j + 2) & 15]);    // min / max of d_j..d_j+2
+        tx[j] = __vmaxs2(__vmaxs2(E[j], E[(j + 1) & 15]), E[(j + 2) & 15]);
     }
-#pragma unroll
-    for (int j = 0; j < 6; j++) { tn[8 + j] = swap16(tn[j]); tx[8 + j] = swap16(tx[j]); }
     uint32_t a = 0u, b = 0x7fff7fffu;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        // windows d_k..d_k+8 (low half) and d_k+8..d_k+16 (high half)
-        a = __vmaxs2(a, __vmins2(__vmins2(tn[k], tn[k + 3]), tn[k + 6]));
-        b = __vmins2(b, __vmaxs2(__vmaxs2(tx[k], tx[k + 3]), tx[k + 6]));
+    for (int k = 0; k < 16; k++) {
+        // window d_k..d_k+8
+        a = __vmaxs2(a, __vmins2(__vmins2(tn[k], tn[(k + 3) & 15]), tn[(k + 6) & 15]));
+        b = __vmins2(b, __vmaxs2(__vmaxs2(tx[k], tx[(k + 3) & 15]), tx[(k + 6) & 15]));
     }
-    const int a0 = (int)max(a & 0xffffu, a >> 16) - 256, b0 = (int)min(b & 0xffffu, b >> 16) - 256;
-    return max(a0, -b0);
+    mA = max((int)(a & 0xffffu) - 256, 256 - (int)(b & 0xffffu));
+    mB = max((int)(a >> 16) - 256, 256 - (int)(b >> 16));
 }
 
 __global__ void __launch_bounds__(FS_T)
@@ -635,24 +632,33 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     __syncthreads();
     const int nc = ncand;
 
-    // ---- stage 2: threshold margin of every survivor; corners (margin > min threshold) get their score
-    // written to the score map and are compacted (one shared atomic per warp)
-    for (int i0 = 0; i0 < nc; i0 += FS_T) {
+    // ---- stage 2: threshold margin of every survivor, two per thread (survivors i and i + half share the
+    // 16-bit halves of the registers); corners (margin > min threshold) get their score written to the score
+    // map and are compacted (one shared atomic per warp)
+    const int half = (nc + 1) >> 1;
+    for (int i0 = 0; i0 < half; i0 += FS_T) {
         const int i = i0 + tid;
-        int e = 0, A = 0;
-        if (i < nc) {
-            e = cand[i];
-            A = fast_margin(&win[((e >> 8) + 3) * FW_P + (e & 255) + B0]);
+        int eA = 0, eB = 0, mA = 0, mB = 0;
+        bool hasB = false;
+        if (i < half) {
+            eA = cand[i];
+            hasB = i + half < nc;
+            eB = hasB ? cand[i + half] : eA;
+            fast_margin2(&win[((eA >> 8) + 3) * FW_P + (eA & 255) + B0], &win[((eB >> 8) + 3) * FW_P + (eB & 255) + B0], mA, mB);
         }
-        const bool isCorner = A > th;
-        const unsigned bal = __ballot_sync(0xffffffffu, isCorner);
-        if (bal) {
+        const bool cornerA = mA > th, cornerB = hasB && mB > th;
+        const unsigned balA = __ballot_sync(0xffffffffu, cornerA), balB = __ballot_sync(0xffffffffu, cornerB);
+        if (balA | balB) {
             int base = 0;
-            if (lane == 0) base = smem_atomic_add(&ncorner, __popc(bal));
+            if (lane == 0) base = smem_atomic_add(&ncorner, __popc(balA) + __popc(balB));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (isCorner) {
-                corner[base + __popc(bal & lt)] = (uint16_t)e;
-                smap[((e >> 8) + 1) * FM_P + (e & 255) + 1] = (uint8_t)(A - 1);
+            if (cornerA) {
+                corner[base + __popc(balA & lt)] = (uint16_t)eA;
+                smap[((eA >> 8) + 1) * FM_P + (eA & 255) + 1] = (uint8_t)(mA - 1);
+            }
+            if (cornerB) {
+                corner[base + __popc(balA) + __popc(balB & lt)] = (uint16_t)eB;
+                smap[((eB >> 8) + 1) * FM_P + (eB & 255) + 1] = (uint8_t)(mB - 1);
             }
         }
     }
