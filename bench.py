@@ -47,13 +47,45 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML polled every 2 ms from a thread
+    (nvidia-smi -lms as the fallback when NVML is not importable)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nv, self.stop_flag, self.thread = None, False, None
+        self.sm, self.reasons_seen, self.sm_max = [], set(), None
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = int(get_reasons(h))
+                        for n, bit in names.items():
+                            if r & bit:
+                                self.reasons_seen.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.nv = N
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -67,6 +99,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+            return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(self.reasons_seen), "samples": len(self.sm), "source": "NVML polled every 2 ms over the timed regions"}
         if self.proc:
             self.proc.terminate()
             try:
