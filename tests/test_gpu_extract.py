@@ -177,3 +177,83 @@ def test_shape_errors():
     with pytest.raises(orbx.OrbxError):
         ex.extract(np.zeros((100, 100), np.uint8))     # top levels smaller than one FAST cell
     ex.close()
+
+
+def test_few_features_on_noise_sorts_large_nodes(oracle):
+    """Small quotas on a noise frame: the priority rounds of DistributeOctTree start while nodes still hold
+    thousands of candidates, so the counting sort of k_octree needs more than one 10-bit pass."""
+    import orbx
+    w, h = 1241, 376
+    img = synth.scene_s2(w, h, 21)
+    for nf, tie in ((40, 0), (40, 1), (300, 0)):
+        ex = orbx.Extractor(nfeatures=nf, nlevels=8, max_width=w, max_height=h, max_batch=1, tie_rule=tie)
+        oex = oracle.Extractor(nfeatures=nf, nlevels=8, tie_rule=tie)
+        kps, desc, counts = ex.extract_batch([img])
+        _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]), stages=False)
+        ex.close()
+    # HD noise, 60 features: two strips of ~10 000 candidates each enter the priority rounds (sizes >> 1024)
+    w, h = 1920, 1080
+    img = synth.scene_s2(w, h, 22)
+    ex = orbx.Extractor(nfeatures=60, nlevels=8, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=60, nlevels=8)
+    kps, desc, counts = ex.extract_batch([img])
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]), stages=False)
+    ex.close()
+
+
+@pytest.mark.parametrize("w,h,nf,nl", [(752, 480, 1200, 8), (1226, 370, 2000, 8), (500, 130, 500, 4), (333, 222, 700, 5),
+                                       (1024, 768, 1500, 8), (2047, 513, 3000, 7)])
+def test_odd_sizes(oracle, w, h, nf, nl):
+    """Geometry edge cases: clipped last cells / FAST runs, partial blur bands, resize tail tiles, several strips."""
+    import orbx
+    ex = orbx.Extractor(nfeatures=nf, nlevels=nl, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=nf, nlevels=nl)
+    img = synth.scene_s1(w, h, 7000 + w)
+    kps, desc, counts = ex.extract_batch([img])
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
+
+
+def test_chunked_host_path_replays_graphs(oracle):
+    """20 frames: three chunks over three lanes, each a captured CUDA graph; the second call replays the graphs on
+    different frames.  Every frame must equal the single-frame result, two of them are checked against the oracle."""
+    import orbx
+    cfg = CONFIGS["kitti"]
+    ex = _mk(orbx, cfg, batch=20)
+    ex1 = _mk(orbx, cfg, batch=1)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    for rep in range(2):
+        imgs = synth.frames(30 + rep, cfg["w"], cfg["h"], 20)
+        kps, desc, counts = ex.extract_batch(imgs)
+        for f in range(20):
+            k1, d1, c1 = ex1.extract_batch([imgs[f]])
+            n = int(counts[f])
+            assert n == int(c1[0])
+            assert kps[f][:n].tobytes() == k1[0][:n].tobytes(), f"call {rep} frame {f}: keypoints differ from the single-frame call"
+            assert np.array_equal(desc[f][:n], d1[0][:n])
+        for f in (3, 19):
+            _compare_frame(oracle, ex, oex, imgs[f], f, kps[f], desc[f], int(counts[f]), stages=(f == 19))
+    ex.close(); ex1.close()
+
+
+def test_device_batch_split_in_halves(oracle):
+    """orbx_extract_batch_device with >= 16 frames runs two halves on two lanes; results equal the host path's."""
+    import torch
+    import orbx
+    cfg = CONFIGS["small"]
+    imgs = synth.frames(6, cfg["w"], cfg["h"], 17)
+    ex = _mk(orbx, cfg, batch=17)
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    st = torch.cuda.Stream()
+    ex.extract_batch_device(d.data_ptr(), cfg["w"] * cfg["h"], cfg["w"], 17, cfg["w"], cfg["h"], st.cuda_stream)
+    kps, desc, cnt = ex.fetch_results(17, st.cuda_stream)
+    assert ex.last_launches() == 2 * (1 + 5 + 2 + 1 + 1 + 1)
+    kh, dh, ch = ex.extract_batch(imgs)
+    assert np.array_equal(cnt, ch)
+    for f in range(17):
+        n = int(cnt[f])
+        assert kps[f][:n].tobytes() == kh[f][:n].tobytes() and np.array_equal(desc[f][:n], dh[f][:n])
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    for f in (0, 8, 16):
+        _compare_frame(oracle, ex, oex, imgs[f], f, kh[f], dh[f], int(ch[f]), stages=False)
+    ex.close()
