@@ -181,6 +181,15 @@ int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, i
 /* device-resident variant; d_out = nq x {idx1, d1, d2, idx2} int32 records; enqueued on `stream`, not synchronised */
 int orbm_knn2_csr_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, const int32_t *d_offsets,
                          const int32_t *d_indices, int32_t *d_out, void *stream);
+/* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points.
+ * Point p observes the rows indices[offsets[p] .. offsets[p+1]) of the descriptor pool desc[n_desc][32] (what the
+ * reference gathers from its key frames, :328-337).  Per point: all-pairs DescriptorDistance (:350-358), per row the
+ * median = element (int)(0.5*(N-1)) of the sorted row (:367), and best[p] = position inside the point's list of the
+ * first row with the least median (:369-373) -- the descriptor the reference clones into m_descriptor (:382);
+ * -1 for an empty list (the reference returns early, :322-325, :339-342).  median[p] (optional) = that median.
+ * At most 768 observations per point. */
+int orbm_distinctive(orbm_matcher *m, const uint8_t *desc, int n_desc, const int32_t *offsets, const int32_t *indices,
+                     int n_points, int32_t *best, int32_t *median);
 /* DescriptorDistance for n independent pairs a[i], b[i] (32 bytes each) -> out[i] */
 int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *out);
 
@@ -190,6 +199,27 @@ int orbm_measure_popc(orbm_matcher *m, double *popc_per_clk_per_sm);
 
 /* library build info: "orbx <version> sm_100a" */
 const char *orbx_version(void);
+
+/* ---- bag-of-words descent ----------------------------------------------------------------
+ * OrbVocabulary::transform5 (orbvocabulary.cpp:203-242), the per-feature part of transform4 (:168-201), which
+ * OrbFrame::ComputeBoW / OrbKeyFrame::ComputeBoW call once per frame (orbframe.cpp:395-402, orbkeyframe.cpp:61-70).
+ * The tree is passed as arrays (what OrbVocabulary's text loader, :39-118, builds in m_nodes): node 0 is the root;
+ * the children of node v are child_ids[child_off[v] .. child_off[v+1]) in the order of m_nodes[v].children; a node
+ * without children is a leaf and carries word_id[v] (>= 0) and weight[v]; node_desc[v] is its 32-byte descriptor;
+ * L = m_L.  The std::map bookkeeping of transform4 (addWeight / addFeature / normalize) stays on the host. */
+typedef struct orbv_vocab orbv_vocab;
+int orbv_create(int device, int n_nodes, const int32_t *child_off, const int32_t *child_ids, const uint8_t *node_desc,
+                const int32_t *word_id, const double *weight, int L, orbv_vocab **out);
+void orbv_destroy(orbv_vocab *v);
+const char *orbv_last_error(const orbv_vocab *v);
+/* n features (rows of 32 bytes) -> word_id[i], weight[i] (optional), node_id[i] (optional) = node passed at level
+ * L - levels_up, 0 = root when that level is <= 0 (:211-212).  Strict '<' on the distances: the first child with the
+ * least distance is followed (:224-232). */
+int orbv_transform(orbv_vocab *v, const uint8_t *desc, int n, int levels_up, int32_t *word_id, double *weight, int32_t *node_id);
+/* device-resident variant: descriptors in HBM with `desc_stride` bytes between rows (e.g. the extractor's d_desc),
+ * d_word_node = n x {int32 word, int32 node}; enqueued on `stream` (NULL = the handle's), not synchronised */
+int orbv_transform_device(orbv_vocab *v, const uint8_t *d_desc, size_t desc_stride, int n, int levels_up,
+                          int32_t *d_word_node, void *stream);
 
 #ifdef __cplusplus
 }

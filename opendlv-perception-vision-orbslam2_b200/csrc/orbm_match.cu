@@ -166,6 +166,55 @@ k_popc_probe(unsigned seed, int iters, unsigned *sink, long long *cycles)
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// ------------------------------------------------------------------------------------------
+// OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383): one warp per map point.  Lane = row i of the N x N distance matrix (rows strided by 32):
+// it computes its row against every observed descriptor (the other descriptor is a broadcast load), keeps the row in
+// shared memory (column-major over the lanes: conflict-free) and finds element (N-1)/2 of the sorted row by bisection
+// on the value (distances lie in [0, 256]); the warp then takes the first row with the least median.
+// ------------------------------------------------------------------------------------------
+#define DD_WARPS 4
+__global__ void __launch_bounds__(DD_WARPS * 32)
+k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ offsets, const int *__restrict__ indices, int nPoints,
+              int maxList, int2 *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * DD_WARPS + warp;
+    if (p >= nPoints) return;
+    int *ids = (int *)dsm + (size_t)warp * maxList;                                           // maxList per warp
+    uint16_t *rows = (uint16_t *)((int *)dsm + (size_t)DD_WARPS * maxList) + (size_t)warp * maxList * 32;   // maxList x 32 per warp
+    const int off = offsets[p], N = offsets[p + 1] - off;
+    if (N <= 0) { if (lane == 0) out[p] = make_int2(-1, -1); return; }
+    for (int j = lane; j < N; j += 32) ids[j] = indices[off + j];
+    __syncwarp();
+    const int k = (N - 1) >> 1;                      // (int)(0.5 * ((float)N - 1.0)), :367
+    unsigned bestKey = 0xffffffffu;
+    for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < N) {
+            const uint4 a0 = __ldg(&desc[(size_t)ids[i] * 2]), a1 = __ldg(&desc[(size_t)ids[i] * 2 + 1]);
+            for (int j = 0; j < N; j++) {
+                const uint4 b0 = __ldg(&desc[(size_t)ids[j] * 2]), b1 = __ldg(&desc[(size_t)ids[j] * 2 + 1]);
+                const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+                rows[j * 32 + lane] = (uint16_t)d;
+            }
+            int lo = 0, hi = 256;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                int cnt = 0;
+                for (int j = 0; j < N; j++) cnt += rows[j * 32 + lane] <= mid;
+                if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+            }
+            bestKey = min(bestKey, (unsigned)lo << 16 | (unsigned)i);   // first row with the least median, :369-373
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bestKey = min(bestKey, __shfl_xor_sync(0xffffffffu, bestKey, o));
+    if (lane == 0) out[p] = make_int2((int)(bestKey & 0xffffu), (int)(bestKey >> 16));
+}
+
+
 struct orbm_matcher {
     int device = 0, maxQ = 0, maxT = 0, smCount = 148;
     cudaStream_t stream = nullptr;
@@ -175,6 +224,10 @@ struct orbm_matcher {
     int4 *dOut = nullptr;
     int4 *hOut = nullptr;
     int residentNt = -1;
+    // orbm_distinctive: descriptor pool, CSR lists, results (grown on demand)
+    uint8_t *ddDesc = nullptr; size_t ddCap = 0;
+    int *ddCsr = nullptr; size_t ddCsrCap = 0;
+    int2 *ddBest = nullptr, *ddHost = nullptr; int ddBestCap = 0;
     std::string err;
 };
 
@@ -260,6 +313,10 @@ void orbm_destroy(orbm_matcher *m)
     if (m->dCsr) cudaFree(m->dCsr);
     if (m->dOut) cudaFree(m->dOut);
     if (m->hOut) cudaFreeHost(m->hOut);
+    if (m->ddDesc) cudaFree(m->ddDesc);
+    if (m->ddCsr) cudaFree(m->ddCsr);
+    if (m->ddBest) cudaFree(m->ddBest);
+    if (m->ddHost) cudaFreeHost(m->ddHost);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -355,6 +412,54 @@ int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, i
     for (int i = 0; i < nq; i++) { idx1[i] = m->hOut[i].x; d1[i] = m->hOut[i].y; d2[i] = m->hOut[i].z; idx2[i] = m->hOut[i].w; }
     return ORBX_OK;
 }
+
+int orbm_distinctive(orbm_matcher *m, const uint8_t *desc, int n_desc, const int32_t *offsets, const int32_t *indices, int n_points,
+                     int32_t *best, int32_t *median)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!desc || !offsets || !indices || !best || n_desc < 1 || n_points < 1) return mfail(m, ORBX_ERR_ARG, "bad argument");
+    if (offsets[0] != 0) return mfail(m, ORBX_ERR_ARG, "offsets must start at 0");
+    int maxList = 1;
+    for (int p = 0; p < n_points; p++) {
+        if (offsets[p + 1] < offsets[p]) return mfail(m, ORBX_ERR_ARG, "offsets must be non-decreasing");
+        maxList = std::max(maxList, offsets[p + 1] - offsets[p]);
+    }
+    if (maxList > 768) return mfail(m, ORBX_ERR_ARG, "more than 768 observations of one map point");
+    const int nnz = offsets[n_points];
+    for (int k = 0; k < nnz; k++) if (indices[k] < 0 || indices[k] >= n_desc) return mfail(m, ORBX_ERR_ARG, "descriptor index out of range");
+    MCK(cudaSetDevice(m->device));
+    if ((size_t)n_desc * 32 > m->ddCap) {
+        cudaFree(m->ddDesc); m->ddDesc = nullptr; m->ddCap = 0;
+        MCK(cudaMalloc((void **)&m->ddDesc, (size_t)n_desc * 32));
+        m->ddCap = (size_t)n_desc * 32;
+    }
+    const size_t need = (size_t)n_points + 1 + (size_t)std::max(nnz, 1);
+    if (need > m->ddCsrCap) {
+        cudaFree(m->ddCsr); m->ddCsr = nullptr; m->ddCsrCap = 0;
+        MCK(cudaMalloc((void **)&m->ddCsr, need * sizeof(int)));
+        m->ddCsrCap = need;
+    }
+    if (n_points > m->ddBestCap) {
+        cudaFree(m->ddBest); if (m->ddHost) cudaFreeHost(m->ddHost);
+        m->ddBest = nullptr; m->ddHost = nullptr; m->ddBestCap = 0;
+        MCK(cudaMalloc((void **)&m->ddBest, (size_t)n_points * sizeof(int2)));
+        MCK(cudaMallocHost((void **)&m->ddHost, (size_t)n_points * sizeof(int2)));
+        m->ddBestCap = n_points;
+    }
+    MCK(cudaMemcpyAsync(m->ddDesc, desc, (size_t)n_desc * 32, cudaMemcpyHostToDevice, m->stream));
+    MCK(cudaMemcpyAsync(m->ddCsr, offsets, (size_t)(n_points + 1) * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    if (nnz > 0) MCK(cudaMemcpyAsync(m->ddCsr + n_points + 1, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    const size_t smem = (size_t)DD_WARPS * maxList * (sizeof(int) + 32 * sizeof(uint16_t));
+    if (smem > 48 * 1024) MCK(cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_distinctive<<<(n_points + DD_WARPS - 1) / DD_WARPS, DD_WARPS * 32, smem, m->stream>>>((const uint4 *)m->ddDesc, m->ddCsr, m->ddCsr + n_points + 1,
+                                                                                              n_points, maxList, m->ddBest);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(m->ddHost, m->ddBest, (size_t)n_points * sizeof(int2), cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
+    for (int p = 0; p < n_points; p++) { best[p] = m->ddHost[p].x; if (median) median[p] = m->ddHost[p].y; }
+    return ORBX_OK;
+}
+
 
 int orbm_measure_popc(orbm_matcher *m, double *popc_per_clk_per_sm)
 {

@@ -38,7 +38,8 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_pairs", "orbm_measure_popc"]
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
 def lib():
@@ -81,6 +82,13 @@ def lib():
     L.orbm_knn2_csr_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
+    L.orbv_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    L.orbv_destroy.argtypes = [vp]
+    L.orbv_last_error.restype = C.c_char_p
+    L.orbv_last_error.argtypes = [vp]
+    L.orbv_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    L.orbv_transform_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, vp, vp]
     _lib = L
     return L
 
@@ -289,11 +297,86 @@ class Matcher:
         self._check(lib().orbm_measure_popc(self._h, C.byref(r)))
         return r.value
 
+    def distinctive(self, desc, offsets, indices):
+        """OrbMapPoint::ComputeDistinctiveDescriptors for every CSR list of rows of `desc` -> (best position, median)."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+        n = len(offsets) - 1
+        best, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(lib().orbm_distinctive(self._h, _ptr(desc), len(desc), _ptr(offsets), _ptr(indices), n, _ptr(best), _ptr(med)))
+        return best, med
+
     def distance_pairs(self, a, b):
         a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
         out = np.zeros(len(a), np.int32)
         self._check(lib().orbm_distance_pairs(self._h, _ptr(a), _ptr(b), len(a), _ptr(out)))
         return out
+
+
+class Vocabulary:
+    """OrbVocabulary's tree on the device: transform5 for whole descriptor sets (orbvocabulary.cpp:203-242)."""
+
+    def __init__(self, child_off, child_ids, node_desc, word_id, weight, L, device=0):
+        child_off = np.ascontiguousarray(child_off, np.int32); child_ids = np.ascontiguousarray(child_ids, np.int32)
+        node_desc = np.ascontiguousarray(node_desc, np.uint8); word_id = np.ascontiguousarray(word_id, np.int32)
+        weight = np.ascontiguousarray(weight, np.float64)
+        self._h = C.c_void_p()
+        rc = lib().orbv_create(device, len(word_id), _ptr(child_off), _ptr(child_ids), _ptr(node_desc), _ptr(word_id),
+                               _ptr(weight), L, C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbv_last_error(self._h).decode() if self._h else "invalid vocabulary"
+            if self._h:
+                lib().orbv_destroy(self._h)
+                self._h = None
+            raise OrbxError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbv_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbxError(rc, lib().orbv_last_error(self._h).decode())
+        return rc
+
+    def transform(self, desc, levels_up=4):
+        """-> (word id, weight, node id at level L - levels_up) per descriptor row."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        word, node, w = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+        self._check(lib().orbv_transform(self._h, _ptr(desc), n, levels_up, _ptr(word), _ptr(w), _ptr(node)))
+        return word, w, node
+
+    def transform_device(self, d_desc, stride, n, levels_up, d_out, stream=None):
+        self._check(lib().orbv_transform_device(self._h, C.c_void_p(d_desc), stride, n, levels_up, C.c_void_p(d_out),
+                                                C.c_void_p(stream) if stream else None))
+
+
+def random_vocabulary(k=10, L=3, seed=0):
+    """A synthetic k-ary tree of depth L in the array form of orbv_create (the reference's ORBvoc.txt is not in the tree):
+    node ids in creation order (children of a node are consecutive), random descriptors, leaves numbered as words."""
+    rng = np.random.default_rng(seed)
+    child_off, child_ids, level_of = [0], [], [0]
+    frontier, n = [0], 1
+    kids = {}
+    for lev in range(L):
+        nxt = []
+        for v in frontier:
+            kids[v] = list(range(n, n + k)); n += k
+            nxt += kids[v]
+        frontier = nxt
+    for v in range(n):
+        child_ids += kids.get(v, [])
+        child_off.append(len(child_ids))
+    node_desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    word_id = np.full(n, -1, np.int32)
+    leaves = [v for v in range(n) if v not in kids]
+    word_id[leaves] = np.arange(len(leaves), dtype=np.int32)
+    weight = np.where(word_id >= 0, rng.uniform(0.1, 5.0, n), 0.0)
+    return np.array(child_off, np.int32), np.array(child_ids, np.int32), node_desc, word_id, weight, L
 
 
 def ratio_test(d1, d2, ratio=0.7, th=100):

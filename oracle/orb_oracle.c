@@ -971,6 +971,72 @@ void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *of
     }
 }
 
+/* OrbMapPoint::ComputeDistinctiveDescriptors, orbmappoint.cpp:314-383, for n_points map points at once: point p
+ * observes the descriptor rows indices[offsets[p] .. offsets[p+1]) of `desc` (the reference gathers them from the
+ * key frames, :328-337).  All-pairs DescriptorDistance (:350-358), per row the median = element
+ * (int)(0.5*(N-1)) of the sorted row including the zero on the diagonal (:367), first row with the least median
+ * wins (:369-373).  best[p] = position inside the point's list, -1 for an empty list (the reference returns early). */
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+void orbo_distinctive(const uint8_t *desc, const int32_t *offsets, const int32_t *indices, int n_points,
+                      int32_t *best, int32_t *median)
+{
+    for (int p = 0; p < n_points; p++) {
+        const int N = offsets[p + 1] - offsets[p];
+        const int32_t *ix = indices + offsets[p];
+        best[p] = -1; if (median) median[p] = -1;
+        if (N <= 0) continue;
+        float *dist = malloc(sizeof(float) * (size_t)N * N);
+        int *row = malloc(sizeof(int) * (size_t)N);
+        for (int i = 0; i < N; i++) {
+            dist[(size_t)i * N + i] = 0;
+            for (int j = i + 1; j < N; j++) {
+                const int d = orbo_descriptor_distance(desc + (size_t)ix[i] * 32, desc + (size_t)ix[j] * 32);
+                dist[(size_t)i * N + j] = (float)d; dist[(size_t)j * N + i] = (float)d;
+            }
+        }
+        int bestMedian = 0x7fffffff, bestIdx = 0;
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) row[j] = (int)dist[(size_t)i * N + j];
+            qsort(row, (size_t)N, sizeof(int), cmp_int);
+            const int med = row[(int)(0.5 * ((float)N - 1.0))];
+            if (med < bestMedian) { bestMedian = med; bestIdx = i; }
+        }
+        best[p] = bestIdx; if (median) median[p] = bestMedian;
+        free(dist); free(row);
+    }
+}
+
+/* OrbVocabulary::transform5, orbvocabulary.cpp:203-242, for n features.  The tree is given as arrays: node 0 is the
+ * root, the children of node v are child_ids[child_off[v] .. child_off[v+1]) in the reference's order
+ * (m_nodes[v].children), a node without children is a leaf (isLeaf) carrying word_id[v]; node_desc[v] is its
+ * 32-byte descriptor.  Distances are OrbDescriptor::distance (orbdescriptor.cpp:75-95, the same popcount as
+ * DescriptorDistance); the first child with the least distance is followed (strict '<', :224-232).
+ * node[i] = the node passed at level L - levels_up (0 = root when that level is <= 0, :211-212). */
+void orbo_voc_transform(const int32_t *child_off, const int32_t *child_ids, const uint8_t *node_desc, const int32_t *word_id,
+                        int L, int levels_up, const uint8_t *feat, int n, int32_t *word, int32_t *node)
+{
+    const int nodeLevel = L - levels_up;
+    for (int i = 0; i < n; i++) {
+        const uint8_t *f = feat + (size_t)i * 32;
+        int32_t nid = 0, fin = 0;
+        int level = 0;
+        do {
+            ++level;
+            const int32_t *ch = child_ids + child_off[fin];
+            const int nc = child_off[fin + 1] - child_off[fin];
+            fin = ch[0];
+            double best = orbo_descriptor_distance(f, node_desc + (size_t)fin * 32);
+            for (int c = 1; c < nc; c++) {
+                const double d = orbo_descriptor_distance(f, node_desc + (size_t)ch[c] * 32);
+                if (d < best) { best = d; fin = ch[c]; }
+            }
+            if (level == nodeLevel) nid = fin;
+        } while (child_off[fin + 1] - child_off[fin] > 0);
+        word[i] = word_id[fin];
+        node[i] = nid;
+    }
+}
+
 typedef struct { const uint8_t *q, *t; int q0, q1, nt; int32_t *idx, *d1, *d2; } knn_job;
 static void *knn_worker(void *arg)
 {

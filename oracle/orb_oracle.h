@@ -126,6 +126,12 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
 /* per-query candidate lists (CSR): inner loop of SearchByProjection, orbmatcher.cpp:76-114 */
 void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *offsets, const int32_t *indices,
                    int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2);
+/* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points (CSR lists of rows of desc) */
+void orbo_distinctive(const uint8_t *desc, const int32_t *offsets, const int32_t *indices, int n_points,
+                      int32_t *best, int32_t *median);
+/* OrbVocabulary::transform5 (orbvocabulary.cpp:203-242) for n features over a tree given as arrays */
+void orbo_voc_transform(const int32_t *child_off, const int32_t *child_ids, const uint8_t *node_desc, const int32_t *word_id,
+                        int L, int levels_up, const uint8_t *feat, int n, int32_t *word, int32_t *node);
 /* multi-threaded variants for the CPU baseline (query-/frame-partitioned) */
 void orbo_knn2_mt(const uint8_t *q, int nq, const uint8_t *t, int nt,
                   int32_t *idx, int32_t *d1, int32_t *d2, int nthreads);

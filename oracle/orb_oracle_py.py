@@ -91,6 +91,8 @@ def lib():
     L.orbo_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + \
                                      [C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     L.orbo_knn2_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 6
+    L.orbo_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orbo_voc_transform.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.orbo_knn2_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     _lib = L
     return L
@@ -204,6 +206,27 @@ def knn2_csr(q, t, offsets, indices):
     i1, d1, i2, d2 = (np.empty(nq, np.int32) for _ in range(4))
     lib().orbo_knn2_csr(_ptr(q), nq, _ptr(t), _ptr(offsets), _ptr(indices), _ptr(i1), _ptr(d1), _ptr(i2), _ptr(d2))
     return i1, d1, i2, d2
+
+
+def distinctive(desc, offsets, indices):
+    """OrbMapPoint::ComputeDistinctiveDescriptors for every CSR list -> (best position in the list, its median)."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    n = len(offsets) - 1
+    best, med = np.empty(n, np.int32), np.empty(n, np.int32)
+    lib().orbo_distinctive(_ptr(desc), _ptr(offsets), _ptr(indices), n, _ptr(best), _ptr(med))
+    return best, med
+
+
+def voc_transform(child_off, child_ids, node_desc, word_id, L, levels_up, feat):
+    """OrbVocabulary::transform5 for every row of feat -> (word id, node id at level L - levels_up)."""
+    child_off = np.ascontiguousarray(child_off, np.int32); child_ids = np.ascontiguousarray(child_ids, np.int32)
+    node_desc = np.ascontiguousarray(node_desc, np.uint8); word_id = np.ascontiguousarray(word_id, np.int32)
+    feat = np.ascontiguousarray(feat, np.uint8)
+    n = len(feat)
+    word, node = np.empty(n, np.int32), np.empty(n, np.int32)
+    lib().orbo_voc_transform(_ptr(child_off), _ptr(child_ids), _ptr(node_desc), _ptr(word_id), L, levels_up, _ptr(feat), n, _ptr(word), _ptr(node))
+    return word, node
 
 
 def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
