@@ -56,6 +56,18 @@ class HammingMatcher {
       check(orbm_distance_pairs(m_, a.ptr(0), b.ptr(0), a.rows, dist.data()));
   }
 
+  // OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383) for many map points at once.  pool = all
+  // observed descriptors (N x 32 CV_8U, continuous); point p observes rows indices[offsets[p] .. offsets[p+1]).
+  // best[p] = position in the point's list of the descriptor the reference would clone into m_descriptor, -1 for
+  // a point without (good) observations.
+  void DistinctiveDescriptors(const cv::Mat &pool, const std::vector<int> &offsets, const std::vector<int> &indices, std::vector<int> &best)
+  {
+      const int np = (int)offsets.size() - 1;
+      best.assign(np > 0 ? np : 0, -1);
+      if (np <= 0 || pool.rows == 0) return;
+      check(orbm_distinctive(m_, pool.ptr(0), pool.rows, offsets.data(), indices.data(), np, best.data(), nullptr));
+  }
+
   // the reference's acceptance test (orbmatcher.cpp:234-236)
   static bool Accept(int bestDist1, int bestDist2, int th, float nnRatio)
   {

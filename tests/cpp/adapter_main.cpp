@@ -5,8 +5,12 @@
 #include "orbextractor_b200.hpp"
 #include "orbmatcher_b200.hpp"
 #include "orbframe_stereo_b200.hpp"
+#include "orbvocabulary_b200.hpp"
 
+#include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <map>
 #include <cstdlib>
 
 // the shim declares these for the reference translation unit; the adapter never calls them
@@ -17,6 +21,19 @@ void FAST(const Mat &, std::vector<KeyPoint> &, int, bool) { abort(); }
 void GaussianBlur(const Mat &, Mat &, Size, double, double, int) { abort(); }
 float fastAtan2(float, float) { abort(); }
 }
+
+// stand-ins for OrbBowVector / OrbFeatureVector (reference include/orbbowvector.hpp:46-50, orbfeaturevector.hpp:37)
+struct MockBow {
+    std::map<uint32_t, double> m;
+    void clear() { m.clear(); }
+    void addWeight(uint32_t id, double v) { m[id] += v; }
+    void normalize() { double s = 0; for (auto &kv : m) s += std::fabs(kv.second); if (s > 0) for (auto &kv : m) kv.second /= s; }
+};
+struct MockFeat {
+    std::map<uint32_t, std::vector<uint32_t>> m;
+    void clear() { m.clear(); }
+    void addFeature(uint32_t id, uint32_t i) { m[id].push_back(i); }
+};
 
 int main(int argc, char **argv)
 {
@@ -65,6 +82,35 @@ int main(int argc, char **argv)
             int nu = (int)uR.size();
             fwrite(&nm, 4, 1, o); fwrite(&nu, 4, 1, o);
             fwrite(uR.data(), 4, nu, o); fwrite(depth.data(), 4, nu, o);
+        }
+        // vocabulary adapter: a small deterministic 3-ary tree of depth 2 over the frame's own descriptors as node
+        // descriptors; bag-of-words bookkeeping as in OrbVocabulary::transform4
+        if (n >= 13) {
+            const int k = 3, L = 2, nn = 1 + k + k * k;
+            std::vector<int32_t> off(nn + 1, 0), ids, wid(nn, -1);
+            std::vector<double> wt(nn, 0.0);
+            std::vector<uint8_t> nd((size_t)nn * 32);
+            for (int v = 0; v < nn; v++) {
+                if (v < 1 + k) for (int c = 0; c < k; c++) ids.push_back(1 + v * k + c);
+                off[v + 1] = (int32_t)ids.size();
+                memcpy(&nd[(size_t)v * 32], desc.ptr(v), 32);
+                if (v >= 1 + k) { wid[v] = v - (1 + k); wt[v] = (v % 4 == 0) ? 0.0 : 0.5 + v; }   // some stopped words
+            }
+            orbslam_b200::VocabularyTransform vt(off, ids, nd, wid, wt, L);
+            std::vector<cv::Mat> feats;
+            for (int i = 0; i < n; i++) feats.push_back(desc.rowRange(i, i + 1));
+            MockBow bow; MockFeat fv;
+            vt.transform4(feats, bow, fv, 1);
+            int nb = (int)bow.m.size(), nfv = 0;
+            for (auto &kv : fv.m) nfv += (int)kv.second.size();
+            double sum = 0; for (auto &kv : bow.m) sum += kv.second;
+            fwrite(&nb, 4, 1, o); fwrite(&nfv, 4, 1, o); fwrite(&sum, 8, 1, o);
+            fwrite(vt.words().data(), 4, n, o); fwrite(vt.nodes().data(), 4, n, o);
+            // distinctive descriptors of three "map points" observing rows of this frame
+            orbslam_b200::HammingMatcher hm2(4, 4);
+            std::vector<int> offs = {0, 5, 5, 12}, idxs = {0, 1, 2, 3, 4, 7, 7, 8, 9, 10, 11, 12}, best;
+            hm2.DistinctiveDescriptors(desc, offs, idxs, best);
+            fwrite(best.data(), 4, 3, o);
         }
         fclose(o);
     } catch (const std::exception &e) {

@@ -71,3 +71,24 @@ def test_adapter_end_to_end(tmp_path, oracle):
     ou, od, on = oracle.stereo_matches(oex, oex2, okps, odesc, okps, odesc, 400.0, 0.0)
     assert nu == n and nm == on and nm > 0        # (identical images: all rejected by the median filter, as in the reference)
     assert np.array_equal(uR.view(np.uint32), ou.view(np.uint32)) and np.array_equal(dep.view(np.uint32), od.view(np.uint32))
+    # ---- vocabulary adapter (transform4 bookkeeping) and distinctive descriptors
+    nb, nfv = struct.unpack_from("<ii", b, o); o += 8
+    bsum = struct.unpack_from("<d", b, o)[0]; o += 8
+    words = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    nodes = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    best = np.frombuffer(b, np.int32, 3, o); o += 12
+    k, L, nn = 3, 2, 13
+    off, ids = [0], []
+    for v in range(nn):
+        if v < 1 + k:
+            ids += [1 + v * k + c for c in range(k)]
+        off.append(len(ids))
+    wid = np.array([-1] * (1 + k) + list(range(k * k)), np.int32)
+    wt = np.array([0.0 if (v < 1 + k or v % 4 == 0) else 0.5 + v for v in range(nn)])
+    ow, on = oracle.voc_transform(off, ids, desc[:nn], wid, L, 1, desc)
+    assert np.array_equal(words, ow) and np.array_equal(nodes, on)
+    leaf_of_word = np.flatnonzero(wid >= 0)
+    kept = wt[leaf_of_word][ow] > 0
+    assert nfv == int(kept.sum()) and nb == len(set(ow[kept].tolist())) and abs(bsum - 1.0) < 1e-12
+    ob, _ = oracle.distinctive(desc, [0, 5, 5, 12], [0, 1, 2, 3, 4, 7, 7, 8, 9, 10, 11, 12])
+    assert best.tolist() == ob.tolist() and best[1] == -1
