@@ -11,12 +11,16 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 typedef unsigned char uchar;
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
 #define CV_PI 3.1415926535897932384626433832795
 
 inline int cvRound(double v) { return (int)lrint(v); }
@@ -56,8 +60,8 @@ public:
     size_t step;
     uchar *data;
     Mat() : rows(0), cols(0), step(0), data(nullptr) {}
-    Mat(Size sz, int) { alloc(sz.height, sz.width); }
-    Mat(int r, int c, int) { alloc(r, c); }
+    Mat(Size sz, int t) { alloc(sz.height, sz.width, t); }
+    Mat(int r, int c, int t) { alloc(r, c, t); }
     Mat(int r, int c, int, void *ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar *)ext) {}
     static MatZeros zeros(int r, int c, int) { return MatZeros{r, c}; }
     // Mat = MatExpr(zeros): OpenCV's create() keeps an existing buffer of the same size and zero-fills it in place
@@ -66,22 +70,26 @@ public:
         for (int r = 0; r < rows; r++) memset(data + (size_t)r * step, 0, cols);
         return *this;
     }
-    void create(int r, int c, int) { if (r != rows || c != cols || !data) alloc(r, c); }
+    void create(int r, int c, int t) { if (r != rows || c != cols || t != tp || !data) alloc(r, c, t); }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
     Mat operator()(const Rect &r) const { Mat m(*this); m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
-    Mat clone() const { Mat m; m.alloc(rows, cols); for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, cols); return m; }
+    Mat clone() const { Mat m; m.alloc(rows, cols, tp); for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); return m; }
     template <typename T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step + c * sizeof(T)); }
     template <typename T> const T &at(int r, int c) const { return *(const T *)(data + (size_t)r * step + c * sizeof(T)); }
     uchar *ptr(int r = 0) { return data + (size_t)r * step; }
     const uchar *ptr(int r = 0) const { return data + (size_t)r * step; }
+    template <typename T> T *ptr(int r = 0) { return (T *)(data + (size_t)r * step); }
+    template <typename T> const T *ptr(int r = 0) const { return (const T *)(data + (size_t)r * step); }
     size_t step1() const { return step; }
-    int type() const { return CV_8UC1; }
+    int type() const { return tp; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
 private:
     std::shared_ptr<std::vector<uchar>> buf;
-    void alloc(int r, int c) { buf = std::make_shared<std::vector<uchar>>((size_t)r * c); data = buf->data(); rows = r; cols = c; step = (size_t)c; }
+    int tp = CV_8UC1;                                    // CV_8U (1 byte) or CV_32F (4 bytes) elements
+    size_t esz() const { return tp == CV_32F ? 4 : 1; }
+    void alloc(int r, int c, int t = CV_8UC1) { tp = t; buf = std::make_shared<std::vector<uchar>>((size_t)r * c * esz()); data = buf->data(); rows = r; cols = c; step = (size_t)c * esz(); }
 };
 
 class _InputArray {

@@ -229,6 +229,89 @@ def voc_transform(child_off, child_ids, node_desc, word_id, L, levels_up, feat):
     return word, node
 
 
+def write_vocabulary_text(path, child_off, child_ids, node_desc, weight, k, L):
+    """The DBoW2 text format OrbVocabulary::loadFromTextFile reads (orbvocabulary.cpp:39-118): a header "k L s w", then one
+    line per non-root node in id order: "parent isLeaf d0 .. d31 weight".  No trailing newline: the loader's
+    `while(!f.eof())` would otherwise parse an empty line into a node with an uninitialised parent."""
+    child_off = np.asarray(child_off); child_ids = np.asarray(child_ids)
+    n = len(child_off) - 1
+    parent = np.zeros(n, np.int64)
+    for v in range(n):
+        ch = child_ids[child_off[v]:child_off[v + 1]]
+        parent[ch] = v
+        assert (np.diff(ch) > 0).all(), "children must be listed in id order"
+    lines = [f"{k} {L} 0 0"]
+    for v in range(1, n):
+        leaf = int(child_off[v + 1] == child_off[v])
+        lines.append(f"{parent[v]} {leaf} " + " ".join(str(int(b)) for b in node_desc[v]) + f" {float(weight[v])!r}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    """The reference's own OrbVocabulary (oracle/_ref/libvocref.so, built from /root/reference by `make -C oracle ref`)."""
+    PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libvocref.so")
+
+    def __init__(self, text_path):
+        R = C.CDLL(self.PATH)
+        R.vocref_load.restype = C.c_void_p
+        R.vocref_load.argtypes = [C.c_char_p]
+        R.vocref_free.argtypes = [C.c_void_p]
+        R.vocref_size.argtypes = [C.c_void_p]
+        R.vocref_transform_each.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        R.vocref_transform4.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self.R = R
+        self.h = R.vocref_load(text_path.encode())
+
+    def size(self):
+        return self.R.vocref_size(self.h)
+
+    def transform_each(self, feat, levels_up):
+        feat = np.ascontiguousarray(feat, np.uint8)
+        n = len(feat)
+        word, node = np.empty(n, np.int32), np.empty(n, np.int32)
+        self.R.vocref_transform_each(self.h, _ptr(feat), n, levels_up, _ptr(word), _ptr(node))
+        return word, node
+
+    def transform4(self, feat, levels_up):
+        feat = np.ascontiguousarray(feat, np.uint8)
+        n = len(feat)
+        ids, vals = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+        nodes, feats = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        nb, nf = C.c_int(), C.c_int()
+        rc = self.R.vocref_transform4(self.h, _ptr(feat), n, levels_up, _ptr(ids), _ptr(vals), n, C.byref(nb),
+                                      _ptr(nodes), _ptr(feats), n, C.byref(nf))
+        assert rc == 0
+        return ids[:nb.value], vals[:nb.value], nodes[:nf.value], feats[:nf.value]
+
+    def close(self):
+        if self.h:
+            self.R.vocref_free(self.h)
+            self.h = None
+
+
+def transform4(child_off, child_ids, node_desc, word_id, weight, L, levels_up, feat):
+    """OrbVocabulary::transform4 (orbvocabulary.cpp:168-201) on top of the restated transform5: features with a positive
+    word weight enter the bag of words (weights summed per word, then L1-normalised, orbbowvector.cpp:29-69) and the
+    feature vector (node -> feature indices in feature order, orbfeaturevector.cpp:27-40), both ordered by key."""
+    word, node = voc_transform(child_off, child_ids, node_desc, word_id, L, levels_up, feat)
+    wt_of_word = np.asarray(weight, np.float64)[np.flatnonzero(np.asarray(word_id) >= 0)]
+    bow, fv = {}, {}
+    for i, (w, nd) in enumerate(zip(word.tolist(), node.tolist())):
+        if wt_of_word[w] > 0:
+            bow[w] = bow.get(w, 0.0) + wt_of_word[w]
+            fv.setdefault(nd, []).append(i)
+    norm = 0.0
+    for w in sorted(bow):
+        norm += abs(bow[w])
+    ids = np.array(sorted(bow), np.uint32)
+    vals = np.array([bow[w] / norm if norm > 0 else bow[w] for w in sorted(bow)], np.float64)
+    nodes = np.array([nd for nd in sorted(fv) for _ in fv[nd]], np.uint32)
+    feats = np.array([i for nd in sorted(fv) for i in fv[nd]], np.uint32)
+    return ids, vals, nodes, feats
+
+
 def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
     """OrbFrame::ComputeStereoMatches over two oracle extractors that just processed the left / right image."""
     nlv = exL.nlevels

@@ -85,3 +85,18 @@ def test_vocabulary_on_device_resident_descriptors(oracle):
     got = out.cpu().numpy()
     assert np.array_equal(got[:, 0], ow) and np.array_equal(got[:, 1], on)
     v.close(); ex.close()
+
+
+def test_vocabulary_descent_vs_reference_fixture():
+    """GPU against the outputs of the reference's own OrbVocabulary frozen in tests/golden/ref_vocabulary.npz."""
+    import os
+    import orbx
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vocabulary.npz"))
+    L = int(g["L"])
+    v = orbx.Vocabulary(g["child_off"], g["child_ids"], g["node_desc"], g["word_id"], g["weight"], L)
+    for lu in (0, 1, 2, 4):
+        w, wt, n = v.transform(g["feat"], lu)
+        kept = wt > 0
+        assert np.array_equal(w[kept], g[f"word_lu{lu}"][kept]) and np.array_equal(n[kept], g[f"node_lu{lu}"][kept])
+        assert (g[f"word_lu{lu}"][~kept] == -1).all()
+    v.close()

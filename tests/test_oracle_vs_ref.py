@@ -49,3 +49,33 @@ def test_stock_malloc_delta_is_small(oracle):
     a = {(k["x"], k["y"], k["octave"]) for k in ck}; b = {(k["x"], k["y"], k["octave"]) for k in sk}
     assert len(a) == len(b) == 2000
     assert len(a - b) <= 60     # ~1 % of keypoints depend on heap addresses in the reference itself
+
+
+VOCREF = os.path.join(os.path.dirname(REF), "libvocref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(VOCREF), reason="reference vocabulary sources not built here")
+@pytest.mark.parametrize("k,L", [(10, 3), (4, 5), (20, 2)])
+def test_vocabulary_oracle_equals_reference_sources(oracle, tmp_path, k, L):
+    """The reference's own OrbVocabulary (text loader + transform4/transform5, compiled unmodified) against the
+    oracle's restatement: word ids, node ids, the normalised bag of words and the feature vector."""
+    import orbx
+    child_off, child_ids, node_desc, word_id, weight, _ = orbx.random_vocabulary(k, L, seed=100 + k)
+    weight = np.round(weight, 6)
+    weight[np.flatnonzero(word_id >= 0)[::5]] = 0.0           # stopped words
+    node_desc[child_ids[child_off[0] + 1]] = node_desc[child_ids[child_off[0]]]   # tie: first child wins
+    rng = np.random.default_rng(k)
+    feat = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    path = str(tmp_path / "voc.txt")
+    oracle.write_vocabulary_text(path, child_off, child_ids, node_desc, weight, k, L)
+    ref = oracle.RefVocabulary(path)
+    assert ref.size() == int((word_id >= 0).sum())
+    wt = weight[np.flatnonzero(word_id >= 0)]
+    for lu in (0, 1, L - 1, L, L + 3):
+        rw, rn = ref.transform_each(feat, lu)
+        ow, on = oracle.voc_transform(child_off, child_ids, node_desc, word_id, L, lu, feat)
+        kept = wt[ow] > 0
+        assert np.array_equal(ow[kept], rw[kept]) and np.array_equal(on[kept], rn[kept]) and (rw[~kept] == -1).all()
+        for a, b in zip(ref.transform4(feat, lu), oracle.transform4(child_off, child_ids, node_desc, word_id, weight, L, lu, feat)):
+            assert np.array_equal(a, b)
+    ref.close()
