@@ -367,6 +367,43 @@ def main():
 
     popc_rate = m.measure_popc()
 
+    # ---- "next" rows, rank 0 only, reported beside the headline: bag-of-words descent over one frame's
+    # descriptors (N2), distinctive descriptors of a map's points (N4), stereo matching of one pair (N1)
+    next_rows = None
+    if rank == 0:
+        next_rows = {}
+        rng = np.random.default_rng(99)
+        voc = orbx.random_vocabulary(10, 5, seed=1)                       # k = 10, L = 5: 111 111 nodes (ORBvoc.txt is k = 10, L = 6)
+        V = orbx.Vocabulary(*voc[:5], voc[5], device=local_rank)
+        feats = rng.integers(0, 256, (BATCH * NFEAT, 32), dtype=np.uint8)
+        dfe = torch.from_numpy(feats).to(dev)
+        dwn = torch.empty((BATCH * NFEAT, 2), dtype=torch.int32, device=dev)
+        for _ in range(3):
+            V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for _ in range(10):
+            V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
+        n1.record(stream)
+        torch.cuda.synchronize()
+        ms = n0.elapsed_time(n1) / 10
+        next_rows["bow_transform"] = {"features_per_s": BATCH * NFEAT / (ms * 1e-3), "ms_per_64_frames": ms,
+                                      "workload": f"{BATCH} frames x {NFEAT} descriptors, synthetic vocabulary k=10 L=5, levels_up=4, device-resident"}
+        V.close()
+        npts = 20000
+        pool = rng.integers(0, 256, (npts * 4, 32), dtype=np.uint8)
+        sizes = rng.integers(2, 25, npts)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        inds = rng.integers(0, len(pool), int(offs[-1])).astype(np.int32)
+        m.distinctive(pool, offs, inds)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            m.distinctive(pool, offs, inds)
+        dt_d = (time.perf_counter() - t0) / 3
+        next_rows["distinctive_descriptors"] = {"points_per_s": npts / dt_d, "ms_per_call": dt_d * 1e3,
+                                                "workload": f"{npts} map points with 2..24 observations each, host arrays in and out"}
+
     # ---- max over ranks
     times = torch.tensor([ms_dev, s_e2e, ms_match], dtype=torch.float64, device=dev)
     if world > 1:
@@ -414,6 +451,7 @@ def main():
                                       "frac": pairs / world / int_peak, "popc_per_clk_per_sm": popc_rate,
                                       "peak_source": "148 SM x max SM clock x POPC lanes/clk/SM measured on this GPU (orbm_measure_popc) / 8 POPC per pair"}},
         }
+        line["next_rows"] = next_rows
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference()
             cores = host_cores()
@@ -424,6 +462,14 @@ def main():
                                     "sample": f"{len(frames_cpu)} frames of the same workload over {cores} host threads (one extractor instance per thread); single thread: {fps_one:.1f} frames/s on 16 frames",
                                     "single_thread": fps_one,
                                     "matching_pairs_per_s": cpu.knn2(q[:160], t, cores)}
+            # the same next-row workloads on one host core through the oracle's restatements (bounded samples)
+            O = cpu.O
+            voc = orbx.random_vocabulary(10, 5, seed=1)
+            fs = np.random.default_rng(99).integers(0, 256, (20000, 32), dtype=np.uint8)
+            t0 = time.perf_counter(); O.voc_transform(voc[0], voc[1], voc[2], voc[3], voc[5], 4, fs); dtv = time.perf_counter() - t0
+            line["next_rows"]["bow_transform"]["cpu_port_features_per_s_1core"] = len(fs) / dtv
+            t0 = time.perf_counter(); O.distinctive(pool, offs[:2001], inds[:offs[2000]]); dtd = time.perf_counter() - t0
+            line["next_rows"]["distinctive_descriptors"]["cpu_port_points_per_s_1core"] = 2000 / dtd
         print(json.dumps(line), flush=True)
     ex.close(); m.close()
     if world > 1:
