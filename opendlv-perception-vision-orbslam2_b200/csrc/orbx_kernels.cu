@@ -742,11 +742,9 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 {
     if (segCount <= 0) return cudaSuccess;
     const size_t smem = fast_smem_bytes(winRows, listCap);
-    static size_t optedIn = 48 * 1024;     // grows monotonically; the attribute is per function and device-wide
-    if (smem > optedIn) {
+    if (smem > 48 * 1024) { // opt in per call: the attribute is per device and this is a cheap host-side set
         cudaError_t e = cudaFuncSetAttribute(k_fast_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        optedIn = smem;
     }
     dim3 grid(segCount, batch);
     k_fast_segs<<<grid, FS_T, smem, st>>>(maps, f0, L, segs + segBegin, cnt, best, dbg, dbgCount, dbgCap, winRows, listCap);
