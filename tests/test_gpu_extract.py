@@ -202,7 +202,8 @@ def test_few_features_on_noise_sorts_large_nodes(oracle):
 
 
 @pytest.mark.parametrize("w,h,nf,nl", [(752, 480, 1200, 8), (1226, 370, 2000, 8), (500, 130, 500, 4), (333, 222, 700, 5),
-                                       (1024, 768, 1500, 8), (2047, 513, 3000, 7)])
+                                       (1024, 768, 1500, 8), (2047, 513, 3000, 7),
+                                       (400, 91, 300, 1)])   # one cell row of 59-px-tall cells: FAST runs need > 48 KB of shared memory
 def test_odd_sizes(oracle, w, h, nf, nl):
     """Geometry edge cases: clipped last cells / FAST runs, partial blur bands, resize tail tiles, several strips."""
     import orbx
