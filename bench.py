@@ -316,6 +316,16 @@ def main():
     s_e2e = time.perf_counter() - t0
     n_kp = int(out[2].sum())
     launches_e2e = ex.last_launches()
+    # the PCIe floor of the e2e number: one pinned H2D copy of a step's frames by itself
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        dev_pool[0].copy_(host_pool[0], non_blocking=True)
+        c0.record(stream)
+        for p in range(5):
+            dev_pool[p % POOL].copy_(host_pool[p % POOL], non_blocking=True)
+        c1.record(stream)
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1) / 5
 
     clk = clocks.stop() if rank == 0 else None
 
@@ -433,7 +443,9 @@ def main():
                        "l2": f"inputs rotate over {POOL} resident batches ({POOL * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * W * H,
-                    "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": n_kp},
+                    "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": n_kp,
+                    "h2d_alone_ms_per_step": h2d_ms, "h2d_gbs": BATCH * W * H / (h2d_ms * 1e-3) / 1e9,
+                    "pcie_floor_frames_per_s": BATCH * world / (h2d_ms * 1e-3)},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": {"device_resident": launches_per_step, "e2e": launches_e2e},
             "latency": dict(lat, note="orbx_extract_batch with 1 / 2 frames of 1241x376, pinned host buffers, H2D + kernels + D2H, mean of 100 calls"),
