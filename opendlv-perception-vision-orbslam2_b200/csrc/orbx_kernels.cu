@@ -524,6 +524,73 @@ __device__ __forceinline__ void fast_margin2(const uint8_t *cA, const uint8_t *c
     mB = max((int)(a >> 16) - 256, 256 - (int)(b >> 16));
 }
 
+// Stage 1 of k_fast_segs.  Item i = (row, aligned 4-pixel quad) of the run; thread t takes items t, t + FS_T, ... and walks
+// them with running pointers (no division in the loop).  The survivor flags of a thread's items are collected in a
+// register (4 bits per item) and written out after ONE block-wide scan of the per-thread counts, so the survivor list
+// is in a deterministic order.  Contains __syncthreads(); call uniformly.
+template <typename BitsT>
+__device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *cand, int *wsum, int *ncand, const int tid, const int lane,
+                                                  const int B0, const int wT, const int hT, const int th, const unsigned mQ)
+{
+    // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
+    const int wq0 = B0 >> 2, wqL = (B0 + wT - 1) >> 2;
+    const int nQ = wqL - wq0 + 1, items = nQ * hT;
+    const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
+    const int nLast = ((B0 + wT - 1) & 3) + 1;
+    const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
+    const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
+    const int yIn0 = (int)(((unsigned)tid * mQ) >> 20), q0 = tid - yIn0 * nQ;    // mQ = 2^20 / nQ + 1 (host)
+    const int dY = FS_T / nQ, dQ = FS_T - dY * nQ;
+    const int nMine = tid < items ? (items - tid + FS_T - 1) / FS_T : 0;        // this thread's items
+    const int stepW = dY * (FW_P / 4) + dQ, wrapW = (FW_P / 4) - nQ;              // word steps of the window pointer
+    const int stepE = dY * 256 + 4 * dQ, wrapE = 256 - 4 * nQ;                    // same steps for yIn << 8 | xs
+    BitsT bits = 0;
+    {
+        const uint32_t *rw = (const uint32_t *)(win + (yIn0 + 3) * FW_P) + wq0 + q0;
+        int q = q0;
+        for (int st = 0; st < nMine; st++) {
+            const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
+            const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
+            const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
+            const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
+            const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
+            const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
+            uint32_t pass = X & Y & 0x80808080u;
+            if (q == 0) pass &= maskFirst;
+            if (q == nQ - 1) pass &= maskLast;
+            // flag bits 7,15,23,31 -> one nibble: the products land on distinct bits, the top four are the flags
+            bits |= (BitsT)((pass * 0x00204081u) >> 28) << (4 * st);
+            rw += stepW; q += dQ;
+            if (q >= nQ) { q -= nQ; rw += wrapW; }
+        }
+    }
+    // block-wide exclusive scan of the per-thread survivor counts
+    const int c = sizeof(BitsT) == 8 ? __popcll((unsigned long long)bits) : __popc((unsigned)bits);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    int pos = incl - c;
+#pragma unroll
+    for (int w = 0; w < FS_T / 32; w++) {
+        const int t = wsum[w];
+        if (w < (tid >> 5)) pos += t;
+        if (w == FS_T / 32 - 1 && tid == FS_T - 1) *ncand = pos + c;
+    }
+    int e = (yIn0 << 8) + 4 * (wq0 + q0) - B0, q = q0;       // + j = yIn << 8 | xs for the valid pixels j of the quad
+    for (int st = 0; st < nMine; st++) {
+        const unsigned nib = (unsigned)bits & 15u;
+        bits >>= 4;
+        if (nib & 1u) cand[pos++] = (uint16_t)e;
+        if (nib & 2u) cand[pos++] = (uint16_t)(e + 1);
+        if (nib & 4u) cand[pos++] = (uint16_t)(e + 2);
+        if (nib & 8u) cand[pos++] = (uint16_t)(e + 3);
+        e += stepE; q += dQ;
+        if (q >= nQ) { q -= nQ; e += wrapE; }
+    }
+}
+
 __global__ void __launch_bounds__(FS_T)
 k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
             const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
@@ -565,70 +632,9 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     mbar_wait(&bar, 0);
     __syncthreads();
 
-    // ---- stage 1: packed quick reject, 4 pixels per thread
-    {
-        // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
-        const int wq0 = B0 >> 2, wqL = (B0 + wT - 1) >> 2;
-        const int nQ = wqL - wq0 + 1, items = nQ * hT;
-        const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
-        const int nLast = ((B0 + wT - 1) & 3) + 1;
-        const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
-        const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
-        // item -> (row, quad) advances by FS_T items per step: no division inside the loop.  The survivor flags of
-        // a thread's items are collected in a register (4 bits per item) and written out after ONE block-wide
-        // scan of the per-thread counts.
-        const int yIn0 = (int)(((unsigned)tid * seg.mQ) >> 20), q0 = tid - yIn0 * nQ;    // mQ = 2^20 / nQ + 1 (host)
-        const int dY = FS_T / nQ, dQ = FS_T - dY * nQ;
-        const int steps = (items + FS_T - 1) / FS_T;                                      // <= 16 (nQ <= 64, hT <= 60)
-        unsigned long long bits = 0;
-        int yIn = yIn0, q = q0;
-        for (int st = 0; st < steps; st++) {
-            if (yIn < hT) {
-                const uint32_t *rw = (const uint32_t *)(win + (yIn + 3) * FW_P) + wq0 + q;
-                const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
-                const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
-                const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
-                const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
-                const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
-                const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
-                uint32_t pass = X & Y & 0x80808080u;
-                if (q == 0) pass &= maskFirst;
-                if (q == nQ - 1) pass &= maskLast;
-                // flag bits 7,15,23,31 -> one nibble: the products land on distinct bits, the top four are the flags
-                bits |= (unsigned long long)((pass * 0x00204081u) >> 28) << (4 * st);
-            }
-            yIn += dY; q += dQ;
-            if (q >= nQ) { q -= nQ; yIn++; }
-        }
-        // block-wide exclusive scan of the per-thread survivor counts
-        const int c = __popcll(bits);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[tid >> 5] = incl;
-        __syncthreads();
-        int pos = incl - c;
-#pragma unroll
-        for (int w = 0; w < FS_T / 32; w++) {
-            const int t = wsum[w];
-            if (w < (tid >> 5)) pos += t;
-            if (w == FS_T / 32 - 1 && tid == FS_T - 1) ncand = pos + c;
-        }
-        yIn = yIn0; q = q0;
-        for (int st = 0; st < steps && bits; st++) {
-            const unsigned nib = (unsigned)bits & 15u;
-            bits >>= 4;
-            if (nib) {
-                const int e = (yIn << 8) + 4 * (wq0 + q) - B0;      // + j = yIn << 8 | xs for the valid pixels j of the quad
-                if (nib & 1u) cand[pos++] = (uint16_t)e;
-                if (nib & 2u) cand[pos++] = (uint16_t)(e + 1);
-                if (nib & 4u) cand[pos++] = (uint16_t)(e + 2);
-                if (nib & 8u) cand[pos++] = (uint16_t)(e + 3);
-            }
-            yIn += dY; q += dQ;
-            if (q >= nQ) { q -= nQ; yIn++; }
-        }
-    }
+    // ---- stage 1: packed quick reject, 4 pixels per thread (32-bit flag register when a thread has at most 8 items)
+    if ((((B0 + wT - 1) >> 2) - (B0 >> 2) + 1) * hT <= 8 * FS_T) fast_quick_reject<uint32_t>(win, cand, wsum, &ncand, tid, lane, B0, wT, hT, th, seg.mQ);
+    else fast_quick_reject<unsigned long long>(win, cand, wsum, &ncand, tid, lane, B0, wT, hT, th, seg.mQ);
     __syncthreads();
     const int nc = ncand;
 
