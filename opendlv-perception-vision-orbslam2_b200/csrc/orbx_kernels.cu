@@ -270,7 +270,8 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
                     const uint32_t b0 = (uint32_t)ty.z, b1 = (uint32_t)ty.w;
                     const uint32_t w01 = __byte_perm(b0 * prev[0], b0 * prev[1], 0x7632) + __byte_perm(b1 * cur[0], b1 * cur[1], 0x7632) + 0x00020002u;
                     const uint32_t w23 = __byte_perm(b0 * prev[2], b0 * prev[3], 0x7632) + __byte_perm(b1 * cur[2], b1 * cur[3], 0x7632) + 0x00020002u;
-                    *(uint32_t *)(dst + (size_t)r * dstPitch) = __byte_perm(w01 >> 2, w23 >> 2, 0x6420);     // bytes past dw land in the pitch padding
+                    *(uint32_t *)dst = __byte_perm(w01 >> 2, w23 >> 2, 0x6420);     // bytes past dw land in the pitch padding
+                    dst += dstPitch;
                     if (++r >= yEnd) break;
                     ty = sy[warp][r];
                 }
@@ -482,7 +483,7 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 // ------------------------------------------------------------------------------------------
 #define FS_T 256  // threads per CTA
 #define FW_P 256  // shared window pitch in bytes = TMA box width
-#define FM_P 256  // shared score-map pitch
+#define FM_P 256  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P == 256: list entries are yIn << 8 | xs)
 
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -650,7 +651,8 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             eA = cand[i];
             hasB = i + half < nc;
             eB = hasB ? cand[i + half] : eA;
-            fast_margin2(&win[((eA >> 8) + 3) * FW_P + (eA & 255) + B0], &win[((eB >> 8) + 3) * FW_P + (eB & 255) + B0], mA, mB);
+            // e = yIn << 8 | xs and both pitches are 256: window byte = e + 3 rows + B0, score-map byte = e + 1 row + 1
+            fast_margin2(win + eA + (3 * FW_P + B0), win + eB + (3 * FW_P + B0), mA, mB);
         }
         const bool cornerA = mA > th, cornerB = hasB && mB > th;
         const unsigned balA = __ballot_sync(0xffffffffu, cornerA), balB = __ballot_sync(0xffffffffu, cornerB);
@@ -660,11 +662,11 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             base = __shfl_sync(0xffffffffu, base, 0);
             if (cornerA) {
                 corner[base + __popc(balA & lt)] = (uint16_t)eA;
-                smap[((eA >> 8) + 1) * FM_P + (eA & 255) + 1] = (uint8_t)(mA - 1);
+                smap[eA + (FM_P + 1)] = (uint8_t)(mA - 1);
             }
             if (cornerB) {
                 corner[base + __popc(balA) + __popc(balB & lt)] = (uint16_t)eB;
-                smap[((eB >> 8) + 1) * FM_P + (eB & 255) + 1] = (uint8_t)(mB - 1);
+                smap[eB + (FM_P + 1)] = (uint8_t)(mB - 1);
             }
         }
     }
@@ -684,7 +686,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             e = corner[i];
             const int yIn = e >> 8, xs = e & 255;
             const int cl = cellOf[xs], xIn = xs - cl * wCell;
-            const uint8_t *s = &smap[(yIn + 1) * FM_P + xs + 1];
+            const uint8_t *s = smap + e + (FM_P + 1);
             const int v = s[0];
             const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
             const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
@@ -712,7 +714,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     for (int i = tid; i < nm; i += FS_T) {
         const int e = cand[i];
         const int yIn = e >> 8, xs = e & 255;
-        const int s = smap[(yIn + 1) * FM_P + xs + 1];
+        const int s = smap[e + (FM_P + 1)];
         const int cl = cellOf[xs], xIn = xs - cl * wCell;
         if (anyIni[cl] && s < L.iniTh) continue;
         const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
