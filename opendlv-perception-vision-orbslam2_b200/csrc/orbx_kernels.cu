@@ -1248,7 +1248,10 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
             const uint8_t *gA = pyr + lbase + (size_t)(s.cy - 15 + rr10) * pitch + xaA + 4 * wi10;
             uint8_t *sB = patch[warp][buf] + (rr10 * DS_PP + 4 * wi10);
             uint8_t *sA = sB + 37 * DS_PP;
-            const size_t step = (size_t)3 * pitch;
+            // full 64-bit pointers advanced by a 32-bit step (one IMAD.WIDE per copy); the asm keeps the compiler from
+            // splitting them back into (uniform base) + (offset), which costs a 64-bit add per copy
+            asm volatile("" : "+l"(gA), "+l"(gB));
+            const unsigned step = 3u * (unsigned)pitch;
 #pragma unroll
             for (int r0 = 0; r0 < 33; r0 += 3) {
                 if (r0 + rr10 < 31) cp_async4(sA + r0 * DS_PP, gA);
