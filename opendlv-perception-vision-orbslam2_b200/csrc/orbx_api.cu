@@ -92,8 +92,10 @@ struct orbx_extractor {
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
     OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (256 bytes x hCell+6 rows)
     OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
-    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes, [2] resize boxes: where the kernels read them
-    const uint8_t *tmapBase = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
+    OrbxTensorMaps tmapsDescA;       // same levels, box = unblurred IC_Angle patch of k_describe (48 x 31)
+    OrbxTensorMaps tmapsDescB;       // levels of the BLUR slab, box = rBRIEF patch of k_describe (64 x 37)
+    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes, [2] resize boxes, [3] / [4] describe boxes (pyramid / blur slab)
+    const uint8_t *tmapBase = nullptr, *tmapBaseBlur = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
     DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
     struct { uint8_t *p = nullptr; } dPyr, dBlur;    // slab bases inside the padded allocations
@@ -351,7 +353,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 int buildTensorMaps(orbx_extractor *h, int frames)
 {
     const OrbxLayout &L = h->L;
-    if (h->tmapBase == h->dPyr.p && h->tmapFrames >= frames && h->tmapW == h->curW && h->tmapH == h->curH) return ORBX_OK;
+    if (h->tmapBase == h->dPyr.p && h->tmapBaseBlur == h->dBlur.p && h->tmapFrames >= frames && h->tmapW == h->curW && h->tmapH == h->curH) return ORBX_OK;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -377,13 +379,22 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r3 = encode(&h->tmapsResize.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxR, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        cuuint32_t boxA[3] = {48, 31, 1}, boxB[3] = {64, 37, 1};      // DS_PA x 31 and DS_PB x 37 of k_describe
+        CUresult r4 = encode(&h->tmapsDescA.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxA, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r5 = encode(&h->tmapsDescB.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dBlur.p + v.off), gdim, gstr, boxB, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r4 != CUDA_SUCCESS) r3 = r4;
+        if (r5 != CUDA_SUCCESS) r3 = r5;
         if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) {
             char msg[96];
             snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed for level %d (CUresult %d / %d / %d)", l, (int)r, (int)r2, (int)r3);
             return fail(h, ORBX_ERR_CUDA, msg);
         }
     }
-    CK(h->dTmaps.ensure(3));
+    CK(h->dTmaps.ensure(5));
     for (int i = 0; i < ORBX_LANES; i++) {
         CK(cudaStreamSynchronize(h->lane[i].main));
         CK(cudaStreamSynchronize(h->lane[i].side));
@@ -391,7 +402,9 @@ int buildTensorMaps(orbx_extractor *h, int frames)
     CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dTmaps.p + 1, &h->tmapsFast, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dTmaps.p + 2, &h->tmapsResize, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
-    h->tmapBase = h->dPyr.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
+    CK(cudaMemcpy(h->dTmaps.p + 3, &h->tmapsDescA, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dTmaps.p + 4, &h->tmapsDescB, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    h->tmapBase = h->dPyr.p; h->tmapBaseBlur = h->dBlur.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
     return ORBX_OK;
 }
 
@@ -454,7 +467,7 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
-    launch_describe(pyr, blur, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
+    launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, f0, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
     CK(cudaGetLastError());
     // level-0 copy (by the caller of this function) + resize chain + FAST (level 0 | upper levels) + blur + octree + describe
@@ -966,7 +979,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
         CK(cudaEventRecord(ev[3], st));
         launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, 0, batch, st);
         CK(cudaEventRecord(ev[4], st));
-        launch_describe(h->dPyr.p, h->dBlur.p, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
+        launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, 0, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
         CK(cudaEventRecord(ev[5], st));
         CK(cudaStreamSynchronize(st));
         for (int i = 0; i < 5; i++) { float t = 0; CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / reps; }

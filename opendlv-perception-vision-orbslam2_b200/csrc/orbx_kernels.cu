@@ -1154,8 +1154,11 @@ struct DescUmax { int u[16]; };
 
 #define DS_WARPS 4          // warps per CTA
 #define DS_PER_WARP 8       // keypoint slots handled by one warp, one after the other
-#define DS_PP 40            // shared patch pitch (bytes): up to 10 aligned words per row
-#define DS_BUF (37 * DS_PP + 32 * DS_PP)   // one stage: blurred 37 rows + unblurred 31(+1) rows
+#define DS_PB 64            // blurred patch: TMA box 64 x 37 bytes (16-byte aligned start, 37 columns from offset 0..15)
+#define DS_PA 48            // unblurred patch: TMA box 48 x 31 bytes (32 columns from offset 0..15)
+#define DS_BUFB (37 * DS_PB + 64)          // 2432: keeps the second box 128-byte aligned
+#define DS_BUF (DS_BUFB + 31 * DS_PA + 48) // 3968 bytes per stage
+#define DS_TX (37 * DS_PB + 31 * DS_PA)    // bytes the two box loads of one keypoint deliver
 
 __device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
 {
@@ -1164,21 +1167,18 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
     return d;
 }
 
-__device__ __forceinline__ void cp_async4(void *smemDst, const void *gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smemDst)), "l"(gsrc) : "memory");
-}
-
 struct DescSlot { int valid, cx, cy, level, out, score; };
 
 __global__ void __launch_bounds__(DS_WARPS * 32)
-k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
+k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict__ mapsB, int f0, const __grid_constant__ OrbxLayout L,
            const int2 *__restrict__ slots, const int *__restrict__ lvlCount, DescUmax um,
            orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts)
 {
     // per warp two stages of {blurred 37x37 patch (rBRIEF samples), unblurred 31x31 patch (IC_Angle)}: the
-    // patches of the warp's next keypoint stream in (cp.async) while the current one is being processed
-    __shared__ __align__(16) uint8_t patch[DS_WARPS][2][DS_BUF];
+    // patches of the warp's next keypoint arrive by two TMA box loads (one elected lane, completion on the
+    // stage's mbarrier) while the current one is being processed
+    __shared__ __align__(128) uint8_t patch[DS_WARPS][2][DS_BUF];
+    __shared__ __align__(8) uint64_t bars[DS_WARPS][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
     // this lane's 16 pattern points (descriptor byte `lane`), kept in registers across its slots
@@ -1223,7 +1223,9 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (blockIdx.x == 0 && tid == 0) counts[frame] = total;
     const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
-    const int rr10 = lane / 10, wi10 = lane - rr10 * 10;      // staging role: 3 rows x 10 words per pass
+    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[warp][lane])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
 
     // resolve slot j of this warp and start streaming its two patches into stage `buf`
     auto issue = [&](int j, int buf) -> DescSlot {
@@ -1240,52 +1242,38 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
         const int2 sl = slots[(size_t)frame * L.slotsPerFrame + slot];
         s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
         s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
-        if (lane < 30) {
-            const int pitch = lv.pitch;
-            const size_t lbase = (size_t)frame * L.slab + lv.off;
-            const int xaB = (s.cx - 18) & ~3, xaA = (s.cx - 15) & ~3;
-            const uint8_t *gB = blur + lbase + (size_t)(s.cy - 18 + rr10) * pitch + xaB + 4 * wi10;
-            const uint8_t *gA = pyr + lbase + (size_t)(s.cy - 15 + rr10) * pitch + xaA + 4 * wi10;
-            uint8_t *sB = patch[warp][buf] + (rr10 * DS_PP + 4 * wi10);
-            uint8_t *sA = sB + 37 * DS_PP;
-            // full 64-bit pointers advanced by a 32-bit step (one IMAD.WIDE per copy); the asm keeps the compiler from
-            // splitting them back into (uniform base) + (offset), which costs a 64-bit add per copy
-            asm volatile("" : "+l"(gA), "+l"(gB));
-            const unsigned step = 3u * (unsigned)pitch;
-#pragma unroll
-            for (int r0 = 0; r0 < 33; r0 += 3) {
-                if (r0 + rr10 < 31) cp_async4(sA + r0 * DS_PP, gA);
-                gA += step;
-            }
-#pragma unroll
-            for (int r0 = 0; r0 < 39; r0 += 3) {
-                if (r0 + rr10 < 37) cp_async4(sB + r0 * DS_PP, gB);
-                gB += step;
-            }
+        if (lane == 0) {
+            // box starts are 16-byte aligned: the patch column cx-18 (cx-15) sits at byte (cx-18) & 15 ((cx-15) & 15) of its row
+            uint8_t *sB = patch[warp][buf], *sA = sB + DS_BUFB;
+            const uint32_t bb = smem_u32(&bars[warp][buf]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((uint32_t)DS_TX) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(sB)), "l"(mapsB + level), "r"((s.cx - 18) & ~15), "r"(s.cy - 18), "r"(f0 + frame), "r"(bb) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(sA)), "l"(mapsA + level), "r"((s.cx - 15) & ~15), "r"(s.cy - 15), "r"(f0 + frame), "r"(bb) : "memory");
         }
         return s;
     };
 
     DescSlot cur = issue(0, 0);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    unsigned phase = 0;                                       // bit b = parity the next completion of stage b's barrier has
     for (int j = 0; j < DS_PER_WARP; j++) {
         const int buf = j & 1;
         const DescSlot nxt = issue(j + 1, buf ^ 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group has landed
-        __syncwarp();
         if (cur.valid) {
+            mbar_wait(&bars[warp][buf], (phase >> buf) & 1u);
+            phase ^= 1u << buf;
             const OrbxLevel &lv = L.lv[cur.level];
-            const uint8_t *pB = patch[warp][buf], *pA = pB + 37 * DS_PP;
-            const int shB = (cur.cx - 18) & 3, shA = (cur.cx - 15) & 3;
+            const uint8_t *pB = patch[warp][buf], *pA = pB + DS_BUFB;
+            const int shB = (cur.cx - 18) & 15, shA = (cur.cx - 15) & 15;
             // ---- IC_Angle: lane = patch row v; 32 bytes of the row (cols cx-15 .. cx+16) against the weights
             int m10 = 0, rowsum = 0;
             if (lane < 31) {
-                const uint32_t *rw = (const uint32_t *)pA + lane * (DS_PP / 4);
+                const uint32_t *rw = (const uint32_t *)(pA + lane * DS_PA + (shA & ~3));
                 uint32_t W[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) W[k] = rw[k];
-                const int sh = shA * 8;
+                const int sh = (shA & 3) * 8;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint32_t B = __funnelshift_r(W[k], W[k + 1], sh);
@@ -1308,8 +1296,8 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
             glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
             const float a = ca, b = sa;
             const float MAGIC = 12582912.0f;                       // 0x4B400000
-            const uint8_t *center = pB + 18 * DS_PP + shB + 18;
-            const unsigned BIAS = 0x4B400000u * (unsigned)(DS_PP + 1);   // both magic offsets, removed in one subtraction (mod 2^32)
+            const uint8_t *center = pB + 18 * DS_PB + shB + 18;
+            const unsigned BIAS = 0x4B400000u * (unsigned)(DS_PB + 1);   // both magic offsets, removed in one subtraction (mod 2^32)
             int val = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -1319,7 +1307,7 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
                     const float x = px[2 * k + e], y = py[2 * k + e];
                     const int row = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)), MAGIC));
                     const int col = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)), MAGIC));
-                    t[e] = center[(int)((unsigned)row * (unsigned)DS_PP + (unsigned)col - BIAS)];
+                    t[e] = center[(int)((unsigned)row * (unsigned)DS_PB + (unsigned)col - BIAS)];
                 }
                 val |= (t[0] < t[1]) << k;
             }
@@ -1338,7 +1326,7 @@ k_describe(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur, co
     }
 }
 
-void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &L, const int2 *slots,
+void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0, const OrbxLayout &L, const int2 *slots,
                      const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
                      int batch, cudaStream_t st)
 {
@@ -1346,7 +1334,7 @@ void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &
     for (int k = 0; k < 16; k++) um.u[k] = umax[k];
     const int perBlock = DS_WARPS * DS_PER_WARP;
     dim3 grid((L.slotsPerFrame + perBlock - 1) / perBlock, batch);
-    k_describe<<<grid, DS_WARPS * 32, 0, st>>>(pyr, blur, L, slots, lvlCount, um, kps, desc, counts);
+    k_describe<<<grid, DS_WARPS * 32, 0, st>>>(mapsA, mapsB, f0, L, slots, lvlCount, um, kps, desc, counts);
 }
 
 // ------------------------------------------------------------------------------------------

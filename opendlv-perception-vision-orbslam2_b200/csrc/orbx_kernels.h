@@ -21,7 +21,7 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 size_t octree_smem_bytes(int maxRows, int maxNodes);
 cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsigned long long *best, int2 *slots,
                           int *lvlCount, int maxRows, int maxNodes, int batch, cudaStream_t st);
-void launch_describe(const uint8_t *pyr, const uint8_t *blur, const OrbxLayout &L, const int2 *slots,
+void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0, const OrbxLayout &L, const int2 *slots,
                      const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
                      int batch, cudaStream_t st);
 cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
