@@ -428,10 +428,12 @@ def main():
         dom = max(stages, key=stages.get)
         dom_ms = stages[dom]
         ach = B_ALG * BATCH / (dom_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, winst_step = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("bytes_per_step", {}).get(dom)
+            prof = json.load(open(tp))
+            traffic = prof.get("bytes_per_step", {}).get(dom)
+            winst_step = sum(prof.get("warp_instructions_per_step", {}).values()) or None
         pairs = NQ * NT * msteps / (ms_match * 1e-3)
         int_peak = 148 * sm_max * 1e6 * popc_rate / 8      # pairs/s at the POPC rate measured on this GPU, SURVEY 8(d)
         line = {
@@ -453,7 +455,13 @@ def main():
                          "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this stage, bytes per 64-frame step)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": B_ALG * BATCH, "kernel_ms": dom_ms,
-                         "whole_step_frac": B_ALG * BATCH / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
+                         "whole_step_frac": B_ALG * BATCH / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
+                         # the path is instruction-issue bound (50-100 integer operations per byte): warp instructions of one
+                         # step (ncu smsp__inst_executed.sum, profiles/ncu_traffic.json) against 4 issue slots x 148 SMs x clock
+                         "issue_roofline": None if not winst_step else {
+                             "warp_instructions_per_step": winst_step,
+                             "peak_warp_instructions_per_s": 4 * 148 * sm_max * 1e6,
+                             "frac": winst_step / (ms_dev / args.steps * 1e-3) / (4 * 148 * sm_max * 1e6)}},
             "stages_ms": stages,
             "clocks": clk,
             "matching": {"metric": "Hamming kNN-2 pairs/s (2000 x 100000)", "value": pairs, "unit": "pairs/s",

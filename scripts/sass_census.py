@@ -15,8 +15,8 @@ parts = re.split(r"//-+ \.text\.(\S+) -+", txt)
 keys = ["UTMALDG", "SYNCS", "LDGSTS", "ACQBULK", "VIMNMX3", "VABSDIFF4", "IDP.4A", "IDP.2A", "PRMT", "VOTE", "SHFL", "MATCH", "REDUX",
         "POPC", "LOP3", "ATOMS", "LDS", "STS", "LDG", "STG", "HMMA", "UTCHMMA", "IMMA"]
 print("SASS mnemonic census of liborbx.so (nvdisasm of the sm_100a cubins built by csrc/Makefile; static instruction counts per kernel).")
-print("Evidence for the design claims: TMA box loads (UTMALDG) completing on mbarriers (SYNCS) in k_resize / k_blur / k_fast_segs;")
-print("programmatic dependent launch (ACQBULK = griddepcontrol.wait) in k_resize; cp.async (LDGSTS) in k_describe; packed three-input")
+print("Evidence for the design claims: TMA box loads (UTMALDG) completing on mbarriers (SYNCS) in k_resize / k_blur / k_fast_segs /")
+print("k_describe; programmatic dependent launch (ACQBULK = griddepcontrol.wait) in k_resize; packed three-input")
 print("min/max (VIMNMX3.S16x2) and VABSDIFF4 in k_fast_segs; dp4a / dp2a (IDP.4A / IDP.2A) in k_blur, k_resize, k_describe; ballot /")
 print("match / shuffle (VOTE, MATCH, SHFL) in k_octree; XOR + POPC on the INT pipe and no tensor-core instruction (HMMA, UTC*MMA, IMMA)")
 print("in the matchers (k_knn2_*, k_distinctive, k_voc_transform, k_stereo_match).\n")
