@@ -401,6 +401,16 @@ def main():
         next_rows["bow_transform"] = {"features_per_s": BATCH * NFEAT / (ms * 1e-3), "ms_per_64_frames": ms,
                                       "workload": f"{BATCH} frames x {NFEAT} descriptors, synthetic vocabulary k=10 L=5, levels_up=4, device-resident"}
         V.close()
+        # stereo matching of the 32 L/R pairs of a batch (N1): pool 0 holds the pairs in L R L R order
+        ex.extract_batch_ptrs(host_ptrs[0], BATCH, W, H, W, out)
+        sout = (np.zeros((BATCH // 2, cap), np.float32), np.zeros((BATCH // 2, cap), np.float32))
+        orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            _, _, snl, snm = orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
+        dt_s = (time.perf_counter() - t0) / 5
+        next_rows["stereo_matches"] = {"pairs_per_s": (BATCH // 2) / dt_s, "ms_per_call": dt_s * 1e3, "matches_per_pair": float(snm.mean()),
+                                       "workload": f"{BATCH // 2} stereo pairs of one extracted batch in one orbx_stereo_match_batch call, results to host"}
         npts = 20000
         pool = rng.integers(0, 256, (npts * 4, 32), dtype=np.uint8)
         sizes = rng.integers(2, 25, npts)

@@ -113,6 +113,11 @@ int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int 
  * before the median filter. */
 int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *right, int frame_right, float mbf, float mb,
                       float *u_right, float *depth, int cap, int *n_left, int *n_matches);
+/* The same for n_pairs stereo pairs of ONE extracted batch in one launch: pair p = frames (frame_left0 + p*frame_step,
+ * frame_right0 + p*frame_step) of the last extraction of h (L R L R ...: 0, 1, 2).  u_right / depth are [n_pairs][cap]
+ * with cap >= orbx_max_keypoints(h); n_left[p] / n_matches[p] as above. */
+int orbx_stereo_match_batch(orbx_extractor *h, int n_pairs, int frame_left0, int frame_right0, int frame_step, float mbf, float mb,
+                            float *u_right, float *depth, int cap, int *n_left, int *n_matches);
 
 /* upper bound of keypoints per frame for this configuration */
 int orbx_max_keypoints(const orbx_extractor *h);

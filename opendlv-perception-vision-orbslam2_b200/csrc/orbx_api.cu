@@ -898,7 +898,7 @@ int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *righ
                      left->dKps.p + (size_t)frame_left * L.kpStride, left->dDesc.p + (size_t)frame_left * L.kpStride * 32,
                      left->dCounts.p + frame_left, right->dKps.p + (size_t)frame_right * right->L.kpStride,
                      right->dDesc.p + (size_t)frame_right * right->L.kpStride * 32, right->dCounts.p + frame_right,
-                     mbf, maxD, dU, dD, dSad, dN, st));
+                     1, 0, mbf, maxD, dU, dD, dSad, dN, st));
     int counts[2] = {0, 0};
     CK(cudaMemcpyAsync(h->hStereo.p, h->dStereo.p, sizeof(float) * 2 * L.kpStride, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&counts[0], left->dCounts.p + frame_left, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -909,6 +909,45 @@ int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *righ
     memcpy(depth, h->hStereo.p + L.kpStride, sizeof(float) * counts[0]);
     if (n_left) *n_left = counts[0];
     if (n_matches) *n_matches = counts[1];
+    return ORBX_OK;
+}
+
+// ComputeStereoMatches for n_pairs pairs of ONE batch: pair p = frames (frame_left0 + p*frame_step, frame_right0 + p*frame_step)
+int orbx_stereo_match_batch(orbx_extractor *h, int n_pairs, int frame_left0, int frame_right0, int frame_step, float mbf, float mb,
+                            float *u_right, float *depth, int cap, int *n_left, int *n_matches)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!u_right || !depth || n_pairs < 1 || frame_step < 1 || frame_left0 < 0 || frame_right0 < 0 ||
+        frame_left0 + (n_pairs - 1) * frame_step >= h->lastBatch || frame_right0 + (n_pairs - 1) * frame_step >= h->lastBatch)
+        return fail(h, ORBX_ERR_ARG, "bad argument or pairs outside the last batch");
+    CK(cudaSetDevice(h->cfg.device));
+    const OrbxLayout &L = h->L;
+    if (cap < L.kpStride) return fail(h, ORBX_ERR_CAPACITY, "u_right / depth rows must hold orbx_max_keypoints entries");
+    const size_t rows = (size_t)n_pairs * L.kpStride;
+    CK(h->dStereo.ensure(2 * rows));
+    CK(h->dStereoI.ensure(rows + n_pairs));
+    CK(h->hStereo.ensure(2 * rows + 2));
+    cudaStream_t st = h->stream;
+    const float maxD = mbf / mb;
+    float *dU = h->dStereo.p, *dD = h->dStereo.p + rows;
+    int *dSad = h->dStereoI.p, *dN = h->dStereoI.p + rows;
+    CK(launch_stereo(L, h->dPyr.p + (size_t)frame_left0 * L.slab, h->dPyr.p + (size_t)frame_right0 * L.slab,
+                     h->dKps.p + (size_t)frame_left0 * L.kpStride, h->dDesc.p + (size_t)frame_left0 * L.kpStride * 32, h->dCounts.p + frame_left0,
+                     h->dKps.p + (size_t)frame_right0 * L.kpStride, h->dDesc.p + (size_t)frame_right0 * L.kpStride * 32, h->dCounts.p + frame_right0,
+                     n_pairs, frame_step, mbf, maxD, dU, dD, dSad, dN, st));
+    CK(h->hCounts.ensure((size_t)std::max(h->cfg.max_batch, 2 * n_pairs)));
+    std::vector<int> nm((size_t)n_pairs), nl((size_t)h->lastBatch);
+    CK(cudaMemcpyAsync(h->hStereo.p, h->dStereo.p, sizeof(float) * 2 * rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nl.data(), h->dCounts.p, sizeof(int) * (size_t)h->lastBatch, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nm.data(), dN, sizeof(int) * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int p = 0; p < n_pairs; p++) {
+        const int n = nl[(size_t)frame_left0 + (size_t)p * frame_step];
+        memcpy(u_right + (size_t)p * cap, h->hStereo.p + (size_t)p * L.kpStride, sizeof(float) * n);
+        memcpy(depth + (size_t)p * cap, h->hStereo.p + rows + (size_t)p * L.kpStride, sizeof(float) * n);
+        if (n_left) n_left[p] = n;
+        if (n_matches) n_matches[p] = nm[p];
+    }
     return ORBX_OK;
 }
 

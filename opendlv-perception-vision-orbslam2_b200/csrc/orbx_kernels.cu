@@ -1359,11 +1359,18 @@ __global__ void __launch_bounds__(128)
 k_stereo_match(const __grid_constant__ OrbxLayout L, const uint8_t *__restrict__ pyrL, const uint8_t *__restrict__ pyrR,
                const orbx_keypoint_pod *__restrict__ kl, const uint4 *__restrict__ dl, const int *__restrict__ nlPtr,
                const orbx_keypoint_pod *__restrict__ kr, const uint4 *__restrict__ dr, const int *__restrict__ nrPtr,
-               float mbf, float maxD, float *__restrict__ uRight, float *__restrict__ depth, int *__restrict__ sad)
+               int frameStep, float mbf, float maxD, float *__restrict__ uRight, float *__restrict__ depth, int *__restrict__ sad)
 {
     __shared__ float part[4][121];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int iL = blockIdx.x * 4 + warp;
+    {   // pair p = blockIdx.y: both sides advance by frameStep frames, the outputs by one record row
+        const size_t fo = (size_t)blockIdx.y * frameStep;
+        pyrL += fo * L.slab; pyrR += fo * L.slab;
+        kl += fo * L.kpStride; kr += fo * L.kpStride; dl += fo * L.kpStride * 2; dr += fo * L.kpStride * 2;
+        nlPtr += fo; nrPtr += fo;
+        uRight += (size_t)blockIdx.y * L.kpStride; depth += (size_t)blockIdx.y * L.kpStride; sad += (size_t)blockIdx.y * L.kpStride;
+    }
     const int nl = *nlPtr, nr = *nrPtr;
     if (iL >= nl) return;
     const orbx_keypoint_pod kpL = kl[iL];
@@ -1448,11 +1455,13 @@ k_stereo_match(const __grid_constant__ OrbxLayout L, const uint8_t *__restrict__
 }
 
 __global__ void __launch_bounds__(256)
-k_stereo_filter(const int *__restrict__ nlPtr, const int *__restrict__ sad, float *__restrict__ uRight, float *__restrict__ depth,
-                int *__restrict__ nMatches, int pow2)
+k_stereo_filter(const int *__restrict__ nlPtr, int frameStep, int kpStride, const int *__restrict__ sad, float *__restrict__ uRight,
+                float *__restrict__ depth, int *__restrict__ nMatches, int pow2)
 {
     extern __shared__ unsigned skeys[];
     __shared__ int cnt;
+    nlPtr += (size_t)blockIdx.x * frameStep; nMatches += blockIdx.x;
+    sad += (size_t)blockIdx.x * kpStride; uRight += (size_t)blockIdx.x * kpStride; depth += (size_t)blockIdx.x * kpStride;
     const int nl = *nlPtr, tid = threadIdx.x;
     if (tid == 0) cnt = 0;
     __syncthreads();
@@ -1485,14 +1494,17 @@ k_stereo_filter(const int *__restrict__ nlPtr, const int *__restrict__ sad, floa
     }
 }
 
+// nPairs pairs: pair p reads the frames p * frameStep after the given left / right pointers and writes row p of
+// uRight / depth / sad (kpStride entries each) and nMatches[p]
 cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
                           const uint8_t *dl, const int *nl, const orbx_keypoint_pod *kr, const uint8_t *dr, const int *nr,
-                          float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st)
+                          int nPairs, int frameStep, float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st)
 {
     const int cap = L.kpStride;
     if (cap > 65535) return cudaErrorInvalidValue;
     int pow2 = 2; while (pow2 < cap) pow2 <<= 1;
-    k_stereo_match<<<(cap + 3) / 4, 128, 0, st>>>(L, pyrL, pyrR, kl, (const uint4 *)dl, nl, kr, (const uint4 *)dr, nr, mbf, maxD, uRight, depth, sad);
-    k_stereo_filter<<<1, 256, (size_t)pow2 * sizeof(unsigned), st>>>(nl, sad, uRight, depth, nMatches, pow2);
+    k_stereo_match<<<dim3((cap + 3) / 4, nPairs), 128, 0, st>>>(L, pyrL, pyrR, kl, (const uint4 *)dl, nl, kr, (const uint4 *)dr, nr, frameStep,
+                                                                 mbf, maxD, uRight, depth, sad);
+    k_stereo_filter<<<nPairs, 256, (size_t)pow2 * sizeof(unsigned), st>>>(nl, frameStep, cap, sad, uRight, depth, nMatches, pow2);
     return cudaGetLastError();
 }

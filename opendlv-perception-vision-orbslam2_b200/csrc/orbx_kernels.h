@@ -26,4 +26,4 @@ void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0,
                      int batch, cudaStream_t st);
 cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
                           const uint8_t *dl, const int *nl, const orbx_keypoint_pod *kr, const uint8_t *dr, const int *nr,
-                          float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st);
+                          int nPairs, int frameStep, float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st);

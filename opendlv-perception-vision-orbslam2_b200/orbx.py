@@ -35,7 +35,7 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
@@ -63,6 +63,7 @@ def lib():
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.orbx_fetch_results.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
+    L.orbx_stereo_match_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
@@ -232,6 +233,18 @@ def stereo_match(left, frame_left, right, frame_right, mbf, mb=0.0):
     left._check(lib().orbx_stereo_match(left._h, frame_left, right._h, frame_right, mbf, mb, _ptr(u), _ptr(d), cap,
                                         C.byref(nl), C.byref(nm)))
     return u[:nl.value].copy(), d[:nl.value].copy(), nm.value
+
+
+def stereo_match_batch(ex, n_pairs, frame_left0=0, frame_right0=1, frame_step=2, mbf=386.1448, mb=0.0, out=None):
+    """ComputeStereoMatches for n_pairs pairs of the last batch of `ex` in one launch -> (uRight[n][cap], depth[n][cap], n_left, n_matches)."""
+    cap = ex.max_keypoints
+    if out is None:
+        out = (np.zeros((n_pairs, cap), np.float32), np.zeros((n_pairs, cap), np.float32))
+    u, d = out
+    nl, nm = np.zeros(n_pairs, np.int32), np.zeros(n_pairs, np.int32)
+    ex._check(lib().orbx_stereo_match_batch(ex._h, n_pairs, frame_left0, frame_right0, frame_step, mbf, mb, _ptr(u), _ptr(d), cap,
+                                            nl.ctypes.data_as(C.POINTER(C.c_int)), nm.ctypes.data_as(C.POINTER(C.c_int))))
+    return u, d, nl, nm
 
 
 class Matcher:

@@ -52,3 +52,25 @@ def test_no_matches_is_not_an_error(oracle):
     u, d, nm = orbx.stereo_match(ex, 0, ex, 1, 300.0, 0.0)
     assert nm == 0 and (u == -1).all() and (d == -1).all()
     ex.close()
+
+
+def test_batch_of_pairs_in_one_launch(oracle):
+    """orbx_stereo_match_batch: all pairs of a batch at once, equal to the per-pair call and to the oracle."""
+    import orbx
+    w, h, nf, nl, mbf = 640, 360, 1000, 6, 300.0
+    frames = synth.stereo_batch(12, w, h, 5)             # L0 R0 ... L4 R4
+    ex = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h, max_batch=10)
+    ex.extract_batch(frames)
+    u, d, n_left, n_match = orbx.stereo_match_batch(ex, 5, 0, 1, 2, mbf, 0.0)
+    for p in range(5):
+        u1, d1, nm1 = orbx.stereo_match(ex, 2 * p, ex, 2 * p + 1, mbf, 0.0)
+        n = int(n_left[p])
+        assert n == len(u1) and int(n_match[p]) == nm1
+        assert np.array_equal(u[p, :n].view(np.uint32), u1.view(np.uint32)) and np.array_equal(d[p, :n].view(np.uint32), d1.view(np.uint32))
+    for p in (0, 4):
+        (ou, od, on), _ = _oracle_pair(oracle, frames[2 * p], frames[2 * p + 1], nf, nl, mbf, 0.0)
+        n = int(n_left[p])
+        assert int(n_match[p]) == on and np.array_equal(u[p, :n].view(np.uint32), ou.view(np.uint32)) and np.array_equal(d[p, :n].view(np.uint32), od.view(np.uint32))
+    with pytest.raises(orbx.OrbxError):
+        orbx.stereo_match_batch(ex, 6, 0, 1, 2, mbf, 0.0)      # sixth pair is outside the batch
+    ex.close()
