@@ -438,7 +438,7 @@ int setGeometry(orbx_extractor *h, int w, int hh)
 int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const orbx_extractor::Lane &ln)
 {
     const OrbxLayout &L = h->L;
-    uint8_t *pyr = h->dPyr.p + (size_t)f0 * L.slab, *blur = h->dBlur.p + (size_t)f0 * L.slab;
+    uint8_t *pyr = h->dPyr.p + (size_t)f0 * L.slab;
     uint32_t *cnt = h->dCnt.p + (size_t)f0 * L.rowsPerFrame;
     unsigned long long *best = h->dBest.p + (size_t)f0 * L.rowsPerFrame;
     int2 *slots = h->dSlots.p + (size_t)f0 * L.slotsPerFrame;

@@ -684,7 +684,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         int e = 0;
         if (i < nk) {
             e = corner[i];
-            const int yIn = e >> 8, xs = e & 255;
+            const int xs = e & 255;
             const int cl = cellOf[xs], xIn = xs - cl * wCell;
             const uint8_t *s = smap + e + (FM_P + 1);
             const int v = s[0];
@@ -872,7 +872,7 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
                 const unsigned b1 = __ballot_sync(0xffffffffu, nch == 1), b2 = __ballot_sync(0xffffffffu, nch == 2);
                 const unsigned bl = __ballot_sync(0xffffffffu, leaf);
                 if (nch) {
-                    NODE_DECODE(node);
+                    NODE_DECODE(node); (void)pb_;
                     int pos = totC - (runC + __popc(b1 & lt) + 2 * __popc(b2 & lt) + nch);
                     if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
                     if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
@@ -1005,7 +1005,7 @@ k_octree(const __grid_constant__ OrbxLayout L, const uint32_t *__restrict__ cnt,
                         }
                         const unsigned b1 = __ballot_sync(0xffffffffu, nch == 1), b2 = __ballot_sync(0xffffffffu, nch == 2);
                         if (nch) {
-                            NODE_DECODE(node);
+                            NODE_DECODE(node); (void)pb_;
                             int pos = totC2 - (runC2 + __popc(b1 & lt) + 2 * __popc(b2 & lt) + nch);
                             if (c4 > 0) nxt[pos++] = node_pack(s_, mid, y1_);
                             if (c2 > 0) nxt[pos] = node_pack(s_, y0_, mid);
