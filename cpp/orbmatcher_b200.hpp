@@ -68,6 +68,34 @@ class HammingMatcher {
       check(orbm_distinctive(m_, pool.ptr(0), pool.rows, offsets.data(), indices.data(), np, best.data(), nullptr));
   }
 
+  // DescriptorDistance of every (query row, candidate) entry of CSR candidate lists, in list order -- for drivers whose
+  // exclusion rules depend on earlier matches of the same call (SearchByProjection, orbmatcher.cpp:42-128): evaluate all
+  // distances in one launch, then replay the reference's loop on the host with ReplayBestTwo.
+  void CandidateDistances(const cv::Mat &query, const cv::Mat &train, const std::vector<int> &offsets, const std::vector<int> &indices,
+                          std::vector<int> &dist)
+  {
+      dist.assign(indices.size(), 0);
+      if (indices.empty() || query.rows == 0) return;
+      check(orbm_distance_csr(m_, query.ptr(0), query.rows, train.ptr(0), train.rows, offsets.data(), indices.data(), dist.data()));
+  }
+
+  // The best / second-best loop of orbmatcher.cpp:76-114 over one query's candidates with precomputed distances;
+  // skip(idx) is the caller's exclusion test (:87-97), level(idx) the candidate's octave (:105, :110).
+  struct BestTwo { int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1; };
+  template <class Skip, class Level>
+  static BestTwo ReplayBestTwo(const int *cand, const int *dist, int n, Skip skip, Level level)
+  {
+      BestTwo b;
+      for (int k = 0; k < n; k++) {
+          const int idx = cand[k];
+          if (skip(idx)) continue;
+          const int d = dist[k];
+          if (d < b.bestDist) { b.bestDist2 = b.bestDist; b.bestDist = d; b.bestLevel2 = b.bestLevel; b.bestLevel = level(idx); b.bestIdx = idx; }
+          else if (d < b.bestDist2) { b.bestLevel2 = level(idx); b.bestDist2 = d; }
+      }
+      return b;
+  }
+
   // the reference's acceptance test (orbmatcher.cpp:234-236)
   static bool Accept(int bestDist1, int bestDist2, int th, float nnRatio)
   {

@@ -186,6 +186,12 @@ int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, i
 /* device-resident variant; d_out = nq x {idx1, d1, d2, idx2} int32 records; enqueued on `stream`, not synchronised */
 int orbm_knn2_csr_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, const int32_t *d_offsets,
                          const int32_t *d_indices, int32_t *d_out, void *stream);
+/* DescriptorDistance of every (query, candidate) entry of the CSR lists, dist[k] for k in [0, offsets[nq]) in list order.
+ * For the drivers whose exclusion rules depend on earlier matches of the same call (SearchByProjection: a frame keypoint
+ * that already carries a map point is skipped, orbmatcher.cpp:87-89; Fuse; SearchBySim3): the device evaluates all
+ * distances at once, the host replays the reference's loop (:76-124) over the precomputed distances in its own order. */
+int orbm_distance_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *offsets,
+                      const int32_t *indices, int32_t *dist);
 /* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points.
  * Point p observes the rows indices[offsets[p] .. offsets[p+1]) of the descriptor pool desc[n_desc][32] (what the
  * reference gathers from its key frames, :328-337).  Per point: all-pairs DescriptorDistance (:350-358), per row the

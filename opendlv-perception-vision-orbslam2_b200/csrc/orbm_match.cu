@@ -140,6 +140,24 @@ k_knn2_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, con
     }
 }
 
+// Distances of every (query, candidate) entry of a CSR list, in list order: what the sequential drivers
+// (SearchByProjection & co., orbmatcher.cpp:76-114) need to replay their exclusion rules on the host without
+// computing a single Hamming distance there.  One warp per query, lanes stride over its list.
+__global__ void __launch_bounds__(128)
+k_distance_csr(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, const int *__restrict__ offsets,
+               const int *__restrict__ indices, int *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (qi >= nq) return;
+    const uint4 qa = __ldg(&q[2 * qi]), qb = __ldg(&q[2 * qi + 1]);
+    const int beg = offsets[qi], end = offsets[qi + 1];
+    for (int p = beg + lane; p < end; p += 32) {
+        const int ti = __ldg(&indices[p]);
+        out[p] = hamming256(qa, qb, __ldg(&t[2 * (size_t)ti]), __ldg(&t[2 * (size_t)ti + 1]));
+    }
+}
+
 // POPC issue-rate probe for the INT roofline of the matcher (SURVEY 8d asks for a measured R_popc):
 // every thread runs 8 independent POPC->XOR chains; a CTA reports its own cycle count.
 __global__ void __launch_bounds__(256)
@@ -410,6 +428,38 @@ int orbm_knn2_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, i
     MCK(cudaMemcpyAsync(m->hOut, m->dOut, (size_t)nq * sizeof(int4), cudaMemcpyDeviceToHost, m->stream));
     MCK(cudaStreamSynchronize(m->stream));
     for (int i = 0; i < nq; i++) { idx1[i] = m->hOut[i].x; d1[i] = m->hOut[i].y; d2[i] = m->hOut[i].z; idx2[i] = m->hOut[i].w; }
+    return ORBX_OK;
+}
+
+int orbm_distance_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *offsets,
+                      const int32_t *indices, int32_t *dist)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!q || !offsets || !indices || !dist || nq < 1 || nq > m->maxQ || nt < 0 || nt > m->maxT || (!t && nt > 0))
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    const int nnz = offsets[nq];
+    if (offsets[0] != 0 || nnz < 0) return mfail(m, ORBX_ERR_ARG, "offsets must start at 0 and be non-decreasing");
+    for (int i = 0; i < nq; i++) if (offsets[i + 1] < offsets[i]) return mfail(m, ORBX_ERR_ARG, "offsets must be non-decreasing");
+    for (int k = 0; k < nnz; k++) if (indices[k] < 0 || indices[k] >= nt) return mfail(m, ORBX_ERR_ARG, "candidate index out of range");
+    if (nnz == 0) return ORBX_OK;
+    MCK(cudaSetDevice(m->device));
+    const size_t need = (size_t)nq + 1 + 2 * (size_t)nnz;          // offsets | indices | distances
+    if (need > m->csrCap) {
+        if (m->dCsr) cudaFree(m->dCsr);
+        m->dCsr = nullptr; m->csrCap = 0;
+        MCK(cudaMalloc((void **)&m->dCsr, need * sizeof(int)));
+        m->csrCap = need;
+    }
+    int *dOff = m->dCsr, *dInd = m->dCsr + nq + 1, *dDist = dInd + nnz;
+    MCK(cudaMemcpyAsync(m->dQ, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+    MCK(cudaMemcpyAsync(m->dT, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+    m->residentNt = nt;
+    MCK(cudaMemcpyAsync(dOff, offsets, (size_t)(nq + 1) * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    MCK(cudaMemcpyAsync(dInd, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, m->stream));
+    k_distance_csr<<<(nq * 32 + 127) / 128, 128, 0, m->stream>>>((const uint4 *)m->dQ, nq, (const uint4 *)m->dT, dOff, dInd, dDist);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(dist, dDist, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    MCK(cudaStreamSynchronize(m->stream));
     return ORBX_OK;
 }
 

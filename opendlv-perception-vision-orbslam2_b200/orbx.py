@@ -38,7 +38,7 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
            "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
@@ -83,6 +83,7 @@ def lib():
     L.orbm_knn2_csr_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
+    L.orbm_distance_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
     L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.orbv_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.orbv_destroy.argtypes = [vp]
@@ -303,6 +304,14 @@ class Matcher:
         self._check(lib().orbm_knn2_csr(self._h, _ptr(q), nq, _ptr(t), len(t), _ptr(offsets), _ptr(indices),
                                         _ptr(i1), _ptr(d1), _ptr(i2), _ptr(d2)))
         return i1, d1, i2, d2
+
+    def distance_csr(self, q, t, offsets, indices):
+        """DescriptorDistance of every (query, candidate) entry of the CSR lists, in list order."""
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+        dist = np.zeros(len(indices), np.int32)
+        self._check(lib().orbm_distance_csr(self._h, _ptr(q), len(q), _ptr(t), len(t), _ptr(offsets), _ptr(indices), _ptr(dist)))
+        return dist
 
     def measure_popc(self):
         """POPC lane-operations per clock per SM measured on this GPU."""

@@ -120,3 +120,52 @@ def test_knn2_csr_full_lists_equal_bruteforce(oracle):
     bi, b1, b2 = m.knn2(q, t)
     assert np.array_equal(i1, bi) and np.array_equal(d1, b1) and np.array_equal(d2, b2)
     m.close()
+
+
+def test_distance_csr_and_host_replay_of_search_by_projection(oracle):
+    """orbm_distance_csr gives every candidate's distance; replaying the reference's SearchByProjection loop
+    (orbmatcher.cpp:76-124, with its 'keypoint already carries a map point' exclusion) on those distances equals the
+    same loop computing DescriptorDistance itself."""
+    import orbx
+    rng = np.random.default_rng(5)
+    nq, nt = 300, 1500
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    for i in range(nq):                                   # train row i = query i with a few flipped bits
+        bits = np.unpackbits(q[i]); bits[rng.choice(256, int(rng.integers(0, 30)), replace=False)] ^= 1
+        t[i] = np.packbits(bits)
+    lists = []
+    for i in range(nq):                                   # own match, the neighbours' matches (conflicts), random rows; some empty
+        if i % 17 == 0:
+            lists.append(np.zeros(0, np.int64)); continue
+        c = np.concatenate([[i, (i + 1) % nq, (i - 1) % nq], rng.integers(0, nt, int(rng.integers(0, 30)))])
+        lists.append(rng.permutation(c))
+    offsets = np.concatenate([[0], np.cumsum([len(c) for c in lists])]).astype(np.int32)
+    indices = np.concatenate(lists).astype(np.int32)
+    octave = rng.integers(0, 8, nt)
+    m = orbx.Matcher(max_queries=nq, max_train=nt)
+    dist = m.distance_csr(q, t, offsets, indices)
+    ref = np.array([oracle.descriptor_distance(q[i], t[indices[k]]) for i in range(nq) for k in range(offsets[i], offsets[i + 1])], np.int32)
+    assert np.array_equal(dist, ref)
+
+    def run(get_dist):
+        taken, matches = np.zeros(nt, bool), []
+        for i in range(nq):
+            best, best2, lv, lv2, bi = 256, 256, -1, -1, -1
+            for k in range(offsets[i], offsets[i + 1]):
+                idx = int(indices[k])
+                if taken[idx]:
+                    continue
+                d = get_dist(i, k)
+                if d < best:
+                    best2, best, lv2, lv, bi = best, d, lv, int(octave[idx]), idx
+                elif d < best2:
+                    lv2, best2 = int(octave[idx]), d
+            if best <= 100 and not (lv == lv2 and best > 0.8 * best2):
+                taken[bi] = True
+                matches.append((i, bi, best))
+        return matches
+    a = run(lambda i, k: int(dist[k]))
+    b = run(lambda i, k: oracle.descriptor_distance(q[i], t[indices[k]]))
+    assert a == b and len(a) > 50
+    m.close()
