@@ -541,7 +541,7 @@ __device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *
     const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
     const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
     const int yIn0 = (int)(((unsigned)tid * mQ) >> 20), q0 = tid - yIn0 * nQ;    // mQ = 2^20 / nQ + 1 (host)
-    const int dY = FS_T / nQ, dQ = FS_T - dY * nQ;
+    const int dY = (int)(((unsigned)FS_T * mQ) >> 20), dQ = FS_T - dY * nQ;      // FS_T / nQ without a division
     const int nMine = tid < items ? (items - tid + FS_T - 1) / FS_T : 0;        // this thread's items
     const int stepW = dY * (FW_P / 4) + dQ, wrapW = (FW_P / 4) - nQ;              // word steps of the window pointer
     const int stepE = dY * 256 + 4 * dQ, wrapE = 256 - 4 * nQ;                    // same steps for yIn << 8 | xs
