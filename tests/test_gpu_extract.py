@@ -258,3 +258,18 @@ def test_device_batch_split_in_halves(oracle):
     for f in (0, 8, 16):
         _compare_frame(oracle, ex, oex, imgs[f], f, kh[f], dh[f], int(ch[f]), stages=False)
     ex.close()
+
+
+def test_alternating_sizes_and_batches_on_one_handle(oracle):
+    """One handle fed frames of different sizes and batch sizes in turn: geometry tables, tensor maps and the captured
+    chunk graphs must follow every change."""
+    import orbx
+    ex = orbx.Extractor(nfeatures=1000, nlevels=6, max_width=1241, max_height=376, max_batch=9)
+    oex = oracle.Extractor(nfeatures=1000, nlevels=6)
+    seq = [(640, 360, 1), (1241, 376, 9), (640, 360, 3), (800, 300, 2), (1241, 376, 1), (640, 360, 9)]
+    for k, (w, h, b) in enumerate(seq):
+        imgs = synth.frames(40 + k, w, h, b)
+        kps, desc, counts = ex.extract_batch(imgs)
+        for f in (0, b - 1):
+            _compare_frame(oracle, ex, oex, imgs[f], f, kps[f], desc[f], int(counts[f]), stages=(k % 2 == 0))
+    ex.close()
