@@ -273,3 +273,27 @@ def test_alternating_sizes_and_batches_on_one_handle(oracle):
         for f in (0, b - 1):
             _compare_frame(oracle, ex, oex, imgs[f], f, kps[f], desc[f], int(counts[f]), stages=(k % 2 == 0))
     ex.close()
+
+
+def test_two_instances_in_two_threads(oracle):
+    """OrbFrame's stereo constructor runs the left and the right extractor in two std::threads at once
+    (orbframe.cpp:73-76): two handles, two host threads, many calls each."""
+    import threading
+    import orbx
+    w, h, nf, nl = 640, 360, 800, 6
+    pairs = [synth.stereo_pair(w, h, 600 + i) for i in range(6)]
+    exs = [orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h) for _ in range(2)]
+    res = [[None] * len(pairs), [None] * len(pairs)]
+
+    def work(side):
+        for i, p in enumerate(pairs):
+            res[side][i] = exs[side].extract(p[side])
+    ths = [threading.Thread(target=work, args=(s,)) for s in range(2)]
+    [t.start() for t in ths]; [t.join() for t in ths]
+    oex = oracle.Extractor(nf, 1.2, nl)
+    for side in range(2):
+        for i in (0, 5):
+            ok, od = oex.extract(pairs[i][side])
+            gk, gd = res[side][i]
+            assert gk.tobytes() == ok.tobytes() and np.array_equal(gd, od)
+    [e.close() for e in exs]
