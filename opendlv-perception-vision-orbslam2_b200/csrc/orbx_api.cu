@@ -538,7 +538,8 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     *out = nullptr;
     if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
         cfg->scale_factor > 1.35f ||   /* k_resize: the source region of a 128 x 32 tile (128 s + 17 columns) must fit its 192 x 48 TMA box */
-        cfg->min_th_fast < 1 || cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
+        cfg->min_th_fast < 1 || cfg->min_th_fast > 127 ||   /* k_fast_segs' packed quick reject compares 7-bit fields */
+        cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
         cfg->max_batch < 1 || cfg->max_width < 1 || cfg->max_height < 1)
         return ORBX_ERR_ARG;
     orbx_extractor *h = new (std::nothrow) orbx_extractor();

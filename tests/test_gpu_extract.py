@@ -297,3 +297,17 @@ def test_two_instances_in_two_threads(oracle):
             gk, gd = res[side][i]
             assert gk.tobytes() == ok.tobytes() and np.array_equal(gd, od)
     [e.close() for e in exs]
+
+
+@pytest.mark.parametrize("sf,ini,mn,nl", [(1.2, 60, 30, 8), (1.2, 9, 2, 6), (1.1, 20, 7, 10), (1.3, 20, 7, 6), (1.33, 25, 5, 5)])
+def test_other_thresholds_and_scale_factors(oracle, sf, ini, mn, nl):
+    """FAST thresholds and pyramid scale factors other than the KITTI defaults (the resize walk, the FAST margin test and
+    the per-cell fallback depend on them)."""
+    import orbx
+    w, h, nf = 752, 480, 1200
+    ex = orbx.Extractor(nfeatures=nf, scale_factor=sf, nlevels=nl, ini_th=ini, min_th=mn, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=nf, scale_factor=sf, nlevels=nl, ini_th=ini, min_th=mn)
+    for img in (synth.scene_s1(w, h, 8100 + ini), synth.scene_s2(w, h, 8200 + ini)):
+        kps, desc, counts = ex.extract_batch([img])
+        _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
