@@ -370,6 +370,8 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
     uint32_t sel1, selT, sel2;
     blur_edge_selectors(w - x0, sel1, selT, sel2);
     const bool leftEdge = x0 == 0;
+    // warps that touch neither the left nor the right image edge skip the edge permutes altogether (uniform branch)
+    const bool edgeWarp = __any_sync(0xffffffffu, active && (x0 == 0 || w - x0 < 8));
     const int rows = min(BL_ROWS, h - y0) + 6;
     // pp[c][s]: horizontal sums of (row before, row in slot s) packed as two 16-bit halves
     uint32_t pp[4][7], prev[4] = {0, 0, 0, 0};
@@ -388,10 +390,12 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
     // 7 rows; writes output row through dp when `store`
     auto row = [&](const int s, const uint32_t *p, const bool store, uint8_t *dp) {
         uint32_t W0 = p[0], W1 = p[1], W2 = p[2];
-        if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);      // left edge: index -k equals index k
-        const uint32_t T = __byte_perm(W0, W1, selT);
-        W2 = __byte_perm(T, W2, sel2);
-        W1 = __byte_perm(W0, W1, sel1);
+        if (edgeWarp) {
+            if (leftEdge) W0 = __byte_perm(W1, W2, 0x1234);  // left edge: index -k equals index k
+            const uint32_t T = __byte_perm(W0, W1, selT);
+            W2 = __byte_perm(T, W2, sel2);
+            W1 = __byte_perm(W0, W1, sel1);
+        }
         // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
         uint32_t hs[4];
         hs[0] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
@@ -416,24 +420,30 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
         }
     };
 
-    if (rows == BL_ROWS + 6 && y0 >= 3 && y0 + BL_ROWS + 3 <= h) {
-        // ---- interior band: no reflected rows, full height (a multiple of 7 input rows): straight pointer walks
-        const uint32_t *p = ts + (y0 - 3 + rowBias) * (BL_BOXW / 4);
-        uint8_t *dp = dst + (size_t)y0 * pitch;
+    // Bands below the top edge walk straight pointers for as long as the input rows are inside the image (whole groups
+    // of 7 rows: interior bands read 42 = 6 x 7 rows and finish here); REFLECT_101 and partial groups take the general
+    // loop behind.
+    int r0 = 0;
+    if (y0 >= 3) {
+        const int nGroups = min(rows, h + 3 - y0) / 7;       // input row r is image row y0 - 3 + r
+        if (nGroups > 0) {
+            const uint32_t *p = ts + (y0 - 3 + rowBias) * (BL_BOXW / 4);
+            uint8_t *dp = dst + (size_t)y0 * pitch;
 #pragma unroll
-        for (int s = 0; s < 6; s++) row(s, p + s * (BL_BOXW / 4), false, dp);
-        row(6, p + 6 * (BL_BOXW / 4), true, dp);
-        dp += pitch;
+            for (int s = 0; s < 6; s++) row(s, p + s * (BL_BOXW / 4), false, dp);
+            row(6, p + 6 * (BL_BOXW / 4), true, dp);
+            dp += pitch;
 #pragma unroll 1
-        for (int r0 = 7; r0 < BL_ROWS + 6; r0 += 7) {
-            p += 7 * (BL_BOXW / 4);
+            for (int g = 1; g < nGroups; g++) {
+                p += 7 * (BL_BOXW / 4);
 #pragma unroll
-            for (int s = 0; s < 7; s++) { row(s, p + s * (BL_BOXW / 4), true, dp); dp += pitch; }
+                for (int s = 0; s < 7; s++) { row(s, p + s * (BL_BOXW / 4), true, dp); dp += pitch; }
+            }
+            r0 = 7 * nGroups;
         }
-        return;
     }
 #pragma unroll 1
-    for (int r0 = 0; r0 < rows; r0 += 7) {
+    for (; r0 < rows; r0 += 7) {
 #pragma unroll
         for (int s = 0; s < 7; s++) {
             const int r = r0 + s;
