@@ -420,37 +420,32 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
         }
     };
 
-    // Bands below the top edge walk straight pointers for as long as the input rows are inside the image (whole groups
-    // of 7 rows: interior bands read 42 = 6 x 7 rows and finish here); REFLECT_101 and partial groups take the general
-    // loop behind.
-    int r0 = 0;
-    if (y0 >= 3) {
-        const int nGroups = min(rows, h + 3 - y0) / 7;       // input row r is image row y0 - 3 + r
-        if (nGroups > 0) {
-            const uint32_t *p = ts + (y0 - 3 + rowBias) * (BL_BOXW / 4);
-            uint8_t *dp = dst + (size_t)y0 * pitch;
-#pragma unroll
-            for (int s = 0; s < 6; s++) row(s, p + s * (BL_BOXW / 4), false, dp);
-            row(6, p + 6 * (BL_BOXW / 4), true, dp);
-            dp += pitch;
+    // Input rows go in groups of 7 (the period of the register window).  A group whose rows all lie inside the image walks
+    // straight pointers (interior bands read 42 = 6 x 7 rows that way); groups that touch the top or bottom edge
+    // (REFLECT_101) or the end of a partial band take the general path.
 #pragma unroll 1
-            for (int g = 1; g < nGroups; g++) {
-                p += 7 * (BL_BOXW / 4);
+    for (int r0 = 0; r0 < rows; r0 += 7) {
+        const int g0 = y0 - 3 + r0;                                  // image row of the group's first input row
+        if (g0 >= 0 && g0 + 6 < h && r0 + 7 <= rows) {
+            const uint32_t *p = ts + (g0 + rowBias) * (BL_BOXW / 4);
+            uint8_t *dp = dst + (size_t)(y0 + r0 - 6) * pitch;       // output row of input row r is y0 + r - 6
+            if (r0 == 0) {
+#pragma unroll
+                for (int s = 0; s < 6; s++) row(s, p + s * (BL_BOXW / 4), false, dp);
+                row(6, p + 6 * (BL_BOXW / 4), true, dp + (size_t)6 * pitch);
+            } else {
 #pragma unroll
                 for (int s = 0; s < 7; s++) { row(s, p + s * (BL_BOXW / 4), true, dp); dp += pitch; }
             }
-            r0 = 7 * nGroups;
-        }
-    }
-#pragma unroll 1
-    for (; r0 < rows; r0 += 7) {
+        } else {
 #pragma unroll
-        for (int s = 0; s < 7; s++) {
-            const int r = r0 + s;
-            if (r < rows) {
-                int g = y0 + r - 3;                                  // REFLECT_101 (|overshoot| <= 3 < h)
-                g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
-                row(s, ts + (g + rowBias) * (BL_BOXW / 4), r >= 6, dst + (size_t)(y0 + r - 6) * pitch);
+            for (int s = 0; s < 7; s++) {
+                const int r = r0 + s;
+                if (r < rows) {
+                    int g = y0 + r - 3;                              // REFLECT_101 (|overshoot| <= 3 < h)
+                    g = g < 0 ? -g : (g >= h ? 2 * h - 2 - g : g);
+                    row(s, ts + (g + rowBias) * (BL_BOXW / 4), r >= 6, dst + (size_t)(y0 + r - 6) * pitch);
+                }
             }
         }
     }
