@@ -84,3 +84,35 @@ def matching_set(nq=2000, nt=100000, seed=5000):
             bits[flip] ^= 1
             t[s] = np.packbits(bits)
     return q, t
+
+
+def observation_lists(n_points=400, seed=2027, pool=4000, max_obs=40):
+    """Descriptor pool + per-map-point observation lists (CSR) for ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383):
+    every third point observes near-duplicates of one descriptor, the others unrelated rows; lists of length 0, 1 and 2
+    (medians tie: the first observation wins) appear at fixed places; bad[k] flags observations whose key frame is bad."""
+    rng = np.random.default_rng(seed)
+    desc = rng.integers(0, 256, (pool, 32), dtype=np.uint8)
+    for c in range(0, pool, 50):
+        for j in range(1, 25):
+            bits = np.unpackbits(desc[c]); bits[rng.choice(256, int(rng.integers(0, 14)), replace=False)] ^= 1
+            desc[c + j] = np.packbits(bits)
+    offsets, indices = [0], []
+    for p in range(n_points):
+        n = (0, 1, 2, 2)[p % 4] if p % 10 < 4 and p % 20 < 10 else int(rng.integers(3, max_obs + 1))
+        if p % 3 == 0:
+            c = 50 * int(rng.integers(0, pool // 50)); ix = (c + rng.choice(25, min(n, 25), replace=False)).tolist()
+        else:
+            ix = rng.choice(pool, n, replace=False).tolist()
+        indices += ix; offsets.append(len(indices))
+    indices = np.asarray(indices, np.int32)
+    bad = (rng.random(len(indices)) < 0.08).astype(np.uint8)
+    return desc, np.asarray(offsets, np.int32), indices, bad
+
+
+def drop_bad_observations(offsets, indices, bad):
+    """What the reference's loop does with bad key frames (orbmappoint.cpp:331-333): they never enter vDescriptors."""
+    keep = np.asarray(bad) == 0
+    lens = np.add.reduceat(np.r_[keep.astype(np.int64), 0], np.asarray(offsets[:-1], np.int64)) if len(indices) else np.zeros(len(offsets) - 1, np.int64)
+    lens[np.diff(offsets) == 0] = 0
+    off2 = np.zeros(len(offsets), np.int32); off2[1:] = np.cumsum(lens)
+    return off2, np.asarray(indices, np.int32)[keep]

@@ -1,0 +1,93 @@
+// mappoint_glue.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Runs the reference's own OrbMapPoint::ComputeDistinctiveDescriptors (src/orbmappoint.cpp:314-383, compiled UNMODIFIED
+// by the `ref` target of oracle/Makefile against the cv:: header shim) on descriptor lists given from Python.
+// orbmappoint.cpp needs the class definitions of OrbKeyFrame / OrbMap (reference headers, included as they are) but only
+// six of their functions; those are defined HERE as inert stand-ins because their own translation units pull in the
+// whole SLAM system (g2o, Eigen, DBoW vocabulary, OpenCV calib3d):
+//   OrbKeyFrame::OrbKeyFrame     fills the members ComputeDistinctiveDescriptors reads (mDescriptors, mvuRight, bad flag)
+//   OrbKeyFrame::isBad / GetCameraCenter / EraseMapPointMatch / ReplaceMapPointMatch, OrbMap::DeleteOrbMapPoint
+// ORBmatcher::DescriptorDistance (src/orbmatcher.cpp:1662-1677) is forwarded to the reference's twin
+// OrbDescriptor::distance (src/orbdescriptor.cpp:75-95, compiled from the reference, the same popcount).
+// The include guard of orbconverter.hpp (Eigen / g2o conversions, unused here) is pre-defined by the Makefile.
+//
+// The reference keeps the observations in a std::map keyed by shared_ptr<OrbKeyFrame>, i.e. ordered by the key
+// frames' ADDRESSES (orbmappoint.cpp:321, :328).  The glue places the key frames of one point at increasing addresses
+// in one buffer, so that the reference's iteration order is the order of the list handed in.
+#include <orbmappoint.hpp>
+#include <orbmatcher.hpp>
+#include <orbdescriptor.hpp>
+
+#include <cstdlib>
+#include <new>
+#include <vector>
+
+static cv::Mat g_pool;                 // row 0 unused: AddObservingKeyframe ignores keypoint index 0 (orbmappoint.cpp:171)
+static std::vector<float> g_uright;
+static bool g_bad = false;
+
+long unsigned int OrbKeyFrame::nNextId = 0;
+
+OrbKeyFrame::OrbKeyFrame(std::shared_ptr<OrbFrame>, std::shared_ptr<OrbMap> map, std::shared_ptr<OrbKeyFrameDatabase>)
+    : mnFrameId(0), mTimeStamp(0), mnGridCols(0), mnGridRows(0), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
+      mnTrackReferenceForFrame(0), mnFuseTargetForKF(0), mnBALocalForKF(0), mnBAFixedForKF(0), m_loopQuery(0), m_loopWords(0),
+      mnRelocQuery(0), mnRelocWords(0), mnBAGlobalForKF(0),
+      fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), N(g_pool.rows),
+      mvKeys(), mvKeysUn(), mvuRight(g_uright), mvDepth(), mDescriptors(g_pool), m_bagOfWords(), m_features(),
+      mnScaleLevels(0), mfScaleFactor(0), mfLogScaleFactor(0), mvScaleFactors(), mvLevelSigma2(), mvInvLevelSigma2(),
+      mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mK(),
+      m_mapPoints(), m_keyFrameDatabase(), m_orbVocabulary(), m_isFirstConnection(true), m_parent(),
+      m_shoulNotBeErased(false), m_shouldBeErased(false), m_isBad(g_bad), mHalfBaseline(0), m_map(map)
+{
+    m_id = nNextId++;
+}
+bool OrbKeyFrame::isBad() { return m_isBad; }
+cv::Mat OrbKeyFrame::GetCameraCenter() { return cv::Mat(); }
+void OrbKeyFrame::EraseMapPointMatch(const size_t &) {}
+void OrbKeyFrame::ReplaceMapPointMatch(const size_t &, std::shared_ptr<OrbMapPoint>) {}
+void OrbMap::DeleteOrbMapPoint(std::shared_ptr<OrbMapPoint>) {}
+int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return OrbDescriptor::distance(a, b); }
+
+extern "C" {
+
+// desc: n_desc x 32; point p observes rows indices[offsets[p] .. offsets[p+1]) (one key frame per observation; bad[k] != 0
+// marks that key frame bad).  out: n_points x 32, the descriptor the reference leaves in m_descriptor; has[p] = 0 when the
+// reference returned early (no usable observation) and m_descriptor stayed empty.
+int mpref_distinctive(const uint8_t *desc, int n_desc, const int32_t *offsets, const int32_t *indices, const uint8_t *bad,
+                      int n_points, uint8_t *out, int32_t *has)
+{
+    g_pool.create(n_desc + 1, 32, CV_8U);
+    memset(g_pool.ptr(0), 0, 32);
+    memcpy(g_pool.ptr(1), desc, (size_t)n_desc * 32);
+    g_uright.assign((size_t)n_desc + 1, -1.0f);
+    const std::shared_ptr<OrbFrame> noFrame;                    // the stand-in constructor ignores its frame
+    for (int p = 0; p < n_points; p++) {
+        const int n = offsets[p + 1] - offsets[p];
+        void *buf = malloc(sizeof(OrbKeyFrame) * (size_t)(n + 2) + alignof(OrbKeyFrame));
+        char *base = (char *)(((uintptr_t)buf + alignof(OrbKeyFrame) - 1) & ~(uintptr_t)(alignof(OrbKeyFrame) - 1));
+        std::vector<std::shared_ptr<OrbKeyFrame>> kfs;
+        g_bad = false;
+        OrbKeyFrame *refKf = new (base) OrbKeyFrame(noFrame, nullptr, nullptr);
+        std::shared_ptr<OrbKeyFrame> ref(refKf, [](OrbKeyFrame *k) { k->~OrbKeyFrame(); });
+        cv::Mat pos(3, 1, CV_32F);
+        for (int k = 0; k < 3; k++) pos.ptr<float>(k)[0] = 0.f;
+        {
+            std::shared_ptr<OrbMapPoint> mp = std::make_shared<OrbMapPoint>(pos, ref, std::shared_ptr<OrbMap>());
+            for (int k = 0; k < n; k++) {
+                g_bad = bad && bad[offsets[p] + k];
+                OrbKeyFrame *kf = new (base + sizeof(OrbKeyFrame) * (size_t)(k + 1)) OrbKeyFrame(noFrame, nullptr, nullptr);
+                kfs.emplace_back(kf, [](OrbKeyFrame *q) { q->~OrbKeyFrame(); });
+                mp->AddObservingKeyframe(kfs.back(), (size_t)indices[offsets[p] + k] + 1);
+            }
+            mp->ComputeDistinctiveDescriptors();
+            cv::Mat d = mp->GetDescriptor();
+            has[p] = !d.empty();
+            if (!d.empty()) memcpy(out + (size_t)p * 32, d.ptr(0), 32);
+        }
+        kfs.clear(); ref.reset();
+        free(buf);
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -52,7 +52,7 @@ struct KeyPoint {
 };
 static_assert(sizeof(KeyPoint) == 28, "cv::KeyPoint layout");
 
-struct MatZeros { int rows, cols; };
+struct MatZeros { int rows, cols, type; };
 
 class Mat {
 public:
@@ -63,16 +63,19 @@ public:
     Mat(Size sz, int t) { alloc(sz.height, sz.width, t); }
     Mat(int r, int c, int t) { alloc(r, c, t); }
     Mat(int r, int c, int, void *ext, size_t stp) : rows(r), cols(c), step(stp), data((uchar *)ext) {}
-    static MatZeros zeros(int r, int c, int) { return MatZeros{r, c}; }
+    static MatZeros zeros(int r, int c, int t) { return MatZeros{r, c, t}; }
+    Mat(const MatZeros &z) : rows(0), cols(0), step(0), data(nullptr) { alloc(z.rows, z.cols, z.type); }   // vector<uchar> value-initialises: zeros
     // Mat = MatExpr(zeros): OpenCV's create() keeps an existing buffer of the same size and zero-fills it in place
     Mat &operator=(const MatZeros &z) {
-        if (rows != z.rows || cols != z.cols || !data) alloc(z.rows, z.cols);
-        for (int r = 0; r < rows; r++) memset(data + (size_t)r * step, 0, cols);
+        if (rows != z.rows || cols != z.cols || tp != z.type || !data) alloc(z.rows, z.cols, z.type);
+        for (int r = 0; r < rows; r++) memset(data + (size_t)r * step, 0, (size_t)cols * esz());
         return *this;
     }
     void create(int r, int c, int t) { if (r != rows || c != cols || t != tp || !data) alloc(r, c, t); }
     void release() { buf.reset(); data = nullptr; rows = cols = 0; step = 0; }
     Mat operator()(const Rect &r) const { Mat m(*this); m.data = data + (size_t)r.y * step + r.x; m.rows = r.height; m.cols = r.width; return m; }
+    Mat row(int r) const { return rowRange(r, r + 1); }
+    void copyTo(Mat &dst) const { dst.create(rows, cols, tp); for (int r = 0; r < rows; r++) memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz()); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
     Mat clone() const { Mat m; m.alloc(rows, cols, tp); for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); return m; }
@@ -91,6 +94,36 @@ private:
     size_t esz() const { return tp == CV_32F ? 4 : 1; }
     void alloc(int r, int c, int t = CV_8UC1) { tp = t; buf = std::make_shared<std::vector<uchar>>((size_t)r * c * esz()); data = buf->data(); rows = r; cols = c; step = (size_t)c * esz(); }
 };
+
+// the little CV_32F arithmetic the reference's map-point code uses (orbmappoint.cpp): element-wise on float matrices
+inline Mat operator-(const Mat &a, const Mat &b)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    Mat c(a.rows, a.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) c.ptr<float>(r)[k] = a.ptr<float>(r)[k] - b.ptr<float>(r)[k];
+    return c;
+}
+inline Mat operator+(const Mat &a, const Mat &b)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    Mat c(a.rows, a.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) c.ptr<float>(r)[k] = a.ptr<float>(r)[k] + b.ptr<float>(r)[k];
+    return c;
+}
+inline Mat operator/(const Mat &a, double d)
+{
+    assert(a.type() == CV_32F);
+    Mat c(a.rows, a.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) c.ptr<float>(r)[k] = (float)(a.ptr<float>(r)[k] / d);
+    return c;
+}
+inline double norm(const Mat &a)
+{
+    assert(a.type() == CV_32F);
+    double s = 0;
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) s += (double)a.ptr<float>(r)[k] * a.ptr<float>(r)[k];
+    return std::sqrt(s);
+}
 
 class _InputArray {
 public:

@@ -291,6 +291,19 @@ class RefVocabulary:
             self.h = None
 
 
+def ref_distinctive(desc, offsets, indices, bad=None):
+    """The reference's own OrbMapPoint::ComputeDistinctiveDescriptors (oracle/_ref/libmpref.so) -> (descriptor[n][32], has[n])."""
+    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libmpref.so"))
+    R.mpref_distinctive.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    desc = np.ascontiguousarray(desc, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.int32); indices = np.ascontiguousarray(indices, np.int32)
+    n = len(offsets) - 1
+    out, has = np.zeros((n, 32), np.uint8), np.zeros(n, np.int32)
+    b = None if bad is None else np.ascontiguousarray(bad, np.uint8)
+    R.mpref_distinctive(_ptr(desc), len(desc), _ptr(offsets), _ptr(indices), None if b is None else _ptr(b), n, _ptr(out), _ptr(has))
+    return out, has
+
+
 def transform4(child_off, child_ids, node_desc, word_id, weight, L, levels_up, feat):
     """OrbVocabulary::transform4 (orbvocabulary.cpp:168-201) on top of the restated transform5: features with a positive
     word weight enter the bag of words (weights summed per word, then L1-normalised, orbbowvector.cpp:29-69) and the

@@ -48,6 +48,22 @@ def test_distinctive_descriptor_vs_oracle(oracle):
     m.close()
 
 
+def test_distinctive_descriptor_vs_reference_fixture():
+    """tests/golden/ref_mappoint.npz: descriptors kept by the reference's own OrbMapPoint::ComputeDistinctiveDescriptors."""
+    import os
+    import orbx
+    import synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_mappoint.npz"))
+    off2, ind2 = synth.drop_bad_observations(g["offsets"], g["indices"], g["bad"])
+    m = orbx.Matcher(max_queries=16, max_train=16)
+    best, _ = m.distinctive(g["desc"], off2, ind2)
+    n = np.diff(off2)
+    assert ((best == -1) == (n == 0)).all() and ((g["has"] == 0) == (n == 0)).all()
+    ok = n > 0
+    assert np.array_equal(g["desc"][ind2[off2[:-1][ok] + best[ok]]], g["out"][ok])
+    m.close()
+
+
 @pytest.mark.parametrize("k,L,levels_up", [(10, 3, 1), (10, 4, 2), (3, 5, 4), (10, 2, 4), (32, 2, 1)])
 def test_vocabulary_descent_vs_oracle(oracle, k, L, levels_up):
     import orbx

@@ -79,3 +79,22 @@ def test_vocabulary_oracle_equals_reference_sources(oracle, tmp_path, k, L):
         for a, b in zip(ref.transform4(feat, lu), oracle.transform4(child_off, child_ids, node_desc, word_id, weight, L, lu, feat)):
             assert np.array_equal(a, b)
     ref.close()
+
+
+MPREF = os.path.join(os.path.dirname(REF), "libmpref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(MPREF), reason="reference map-point sources not built here")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_distinctive_oracle_equals_reference_sources(oracle, seed):
+    """The reference's own OrbMapPoint::ComputeDistinctiveDescriptors (src/orbmappoint.cpp compiled unmodified, observations
+    added through its own AddObservingKeyframe) keeps the descriptor the oracle's restatement picks; bad key frames are
+    skipped by the reference's loop (:331-333), which the batched call leaves to the caller."""
+    desc, offsets, indices, bad = synth.observation_lists(n_points=300, seed=seed)
+    out, has = oracle.ref_distinctive(desc, offsets, indices, bad)
+    off2, ind2 = synth.drop_bad_observations(offsets, indices, bad)
+    best, _ = oracle.distinctive(desc, off2, ind2)
+    n = np.diff(off2)
+    assert ((best == -1) == (n == 0)).all() and ((has == 0) == (n == 0)).all()
+    ok = n > 0
+    assert ok.sum() > 250 and np.array_equal(desc[ind2[off2[:-1][ok] + best[ok]]], out[ok])
