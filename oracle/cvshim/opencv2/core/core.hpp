@@ -77,7 +77,16 @@ public:
     Mat row(int r) const { return rowRange(r, r + 1); }
     void copyTo(Mat &dst) const { dst.create(rows, cols, tp); for (int r = 0; r < rows; r++) memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz()); }
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
-    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + a; m.cols = b - a; return m; }
+    Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * esz(); m.cols = b - a; return m; }
+    Mat col(int c) const { return colRange(c, c + 1); }
+    void copyTo(const Mat &dst) const { Mat d(dst); copyTo(d); }                 // a row / range header of an existing matrix: written in place
+    Mat reshape(int) const { return *this; }                                     // channel count only (orbframe.cpp:466-468); no element moves
+    void convertTo(Mat &dst, int t) const;                                        // CV_8U -> CV_32F, dst may alias *this
+    static Mat ones(int r, int c, int t);
+    Mat t() const;
+    double dot(const Mat &b) const;
+    template <typename T> T &at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T &at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     Mat clone() const { Mat m; m.alloc(rows, cols, tp); for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz()); return m; }
     template <typename T> T &at(int r, int c) { return *(T *)(data + (size_t)r * step + c * sizeof(T)); }
     template <typename T> const T &at(int r, int c) const { return *(const T *)(data + (size_t)r * step + c * sizeof(T)); }
@@ -95,7 +104,36 @@ private:
     void alloc(int r, int c, int t = CV_8UC1) { tp = t; buf = std::make_shared<std::vector<uchar>>((size_t)r * c * esz()); data = buf->data(); rows = r; cols = c; step = (size_t)c * esz(); }
 };
 
-// the little CV_32F arithmetic the reference's map-point code uses (orbmappoint.cpp): element-wise on float matrices
+inline void Mat::convertTo(Mat &dst, int t) const
+{
+    assert(t == CV_32F);
+    Mat o(rows, cols, CV_32F);
+    for (int r = 0; r < rows; r++) for (int k = 0; k < cols; k++) o.ptr<float>(r)[k] = tp == CV_32F ? ptr<float>(r)[k] : (float)ptr(r)[k];
+    dst = o;
+}
+inline Mat Mat::ones(int r, int c, int t)
+{
+    assert(t == CV_32F);
+    Mat o(r, c, CV_32F);
+    for (int i = 0; i < r; i++) for (int k = 0; k < c; k++) o.ptr<float>(i)[k] = 1.0f;
+    return o;
+}
+inline Mat Mat::t() const
+{
+    assert(tp == CV_32F);
+    Mat o(cols, rows, CV_32F);
+    for (int r = 0; r < rows; r++) for (int k = 0; k < cols; k++) o.ptr<float>(k)[r] = ptr<float>(r)[k];
+    return o;
+}
+inline double Mat::dot(const Mat &b) const
+{
+    assert(tp == CV_32F && b.tp == CV_32F && rows == b.rows && cols == b.cols);
+    double s = 0;
+    for (int r = 0; r < rows; r++) for (int k = 0; k < cols; k++) s += (double)ptr<float>(r)[k] * b.ptr<float>(r)[k];
+    return s;
+}
+
+// the little CV_32F arithmetic the reference's map-point / frame code uses (orbmappoint.cpp, orbframe.cpp): float matrices
 inline Mat operator-(const Mat &a, const Mat &b)
 {
     assert(a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
@@ -117,6 +155,43 @@ inline Mat operator/(const Mat &a, double d)
     for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) c.ptr<float>(r)[k] = (float)(a.ptr<float>(r)[k] / d);
     return c;
 }
+inline Mat operator*(const Mat &a, const Mat &b)
+{
+    assert(a.type() == CV_32F && b.type() == CV_32F && a.cols == b.rows);
+    Mat c(a.rows, b.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < b.cols; k++) {
+        float s = 0;
+        for (int j = 0; j < a.cols; j++) s += a.ptr<float>(r)[j] * b.ptr<float>(j)[k];
+        c.ptr<float>(r)[k] = s;
+    }
+    return c;
+}
+inline Mat operator*(double f, const Mat &a)
+{
+    assert(a.type() == CV_32F);
+    Mat c(a.rows, a.cols, CV_32F);
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) c.ptr<float>(r)[k] = (float)(a.ptr<float>(r)[k] * f);
+    return c;
+}
+inline Mat operator*(const Mat &a, double f) { return f * a; }
+inline Mat operator-(const Mat &a) { return -1.0 * a; }
+enum { NORM_L1 = 2 };
+// cv::norm(a, b, NORM_L1) on CV_32F: OpenCV accumulates |a-b| in double (normDiffL1_<float, double>)
+inline double norm(const Mat &a, const Mat &b, int kind)
+{
+    assert(kind == NORM_L1 && a.type() == CV_32F && b.type() == CV_32F && a.rows == b.rows && a.cols == b.cols);
+    double s = 0;
+    for (int r = 0; r < a.rows; r++) for (int k = 0; k < a.cols; k++) s += std::fabs((double)a.ptr<float>(r)[k] - (double)b.ptr<float>(r)[k]);
+    return s;
+}
+// (cv::Mat_<float>(r, c) << a, b, c): the comma initialiser of orbframe.cpp:739
+template <typename T> struct Mat_ : Mat { Mat_(int r, int c) : Mat(r, c, CV_32F) {} };
+template <typename T> struct MatCommaInit_ {
+    Mat m; int n;
+    MatCommaInit_ &operator,(T v) { m.ptr<T>(n / m.cols)[n % m.cols] = v; n++; return *this; }
+    operator Mat() const { return m; }
+};
+template <typename T> inline MatCommaInit_<T> operator<<(const Mat_<T> &m, T v) { MatCommaInit_<T> c{m, 0}; return (c, v); }
 inline double norm(const Mat &a)
 {
     assert(a.type() == CV_32F);

@@ -11,6 +11,7 @@
 // "stock" mode leaves glibc malloc in charge to show the reference's own nondeterminism.
 #include "orbextractor.hpp"
 
+#include <atomic>
 #include <sys/mman.h>
 
 #include <cstdio>
@@ -56,7 +57,8 @@ float fastAtan2(float y, float x) { return orbo_fast_atan2(y, x); }
 
 // ---------------------------------------------------------------- monotone bump allocator
 static char *g_arena = nullptr;
-static size_t g_arena_size = 0, g_arena_used = 0;
+static size_t g_arena_size = 0;
+static std::atomic<size_t> g_arena_used{0};   // atomic: the reference's OrbFrame extracts left and right in two threads
 static bool g_bump_on = false;
 
 static void arena_init()
@@ -72,9 +74,8 @@ static inline bool in_arena(void *p) { return g_arena && (char *)p >= g_arena &&
 void *operator new(size_t n)
 {
     if (g_bump_on) {
-        size_t a = (g_arena_used + 15) & ~(size_t)15;
+        const size_t a = g_arena_used.fetch_add((n + 15) & ~(size_t)15);   // later allocation = higher address, in every thread
         if (a + n > g_arena_size) { fprintf(stderr, "bump arena exhausted\n"); abort(); }
-        g_arena_used = a + n;
         return g_arena + a;
     }
     void *p = malloc(n ? n : 1);
@@ -89,6 +90,9 @@ void operator delete[](void *p, size_t) noexcept { operator delete(p); }
 
 // ---------------------------------------------------------------- C entry points
 extern "C" {
+
+// canonical heap order for code outside this file (frame_glue.cpp): on -> fresh bump arena, off -> malloc again
+void orbref_canonical(int on) { if (on) { arena_init(); g_arena_used = 0; } g_bump_on = on != 0; }
 
 struct orbref_cfg { int nfeatures; float scale; int nlevels, ini_th, min_th; };
 

@@ -802,9 +802,11 @@ int orbo_extract_batch_mt(const orbo_extractor *cfg, const uint8_t *const *imgs,
 
 /* ------------------------------------------------------------------ */
 /* OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705 ("next" row N1). */
-/* PARITY UNPINNED: orbframe.cpp cannot be compiled here (it pulls in the  */
-/* whole SLAM data model) and the reference has no test for it; this is a  */
-/* line-by-line restatement only.                                          */
+/* PINNED: the reference's own src/orbframe.cpp (stereo constructor +     */
+/* ComputeStereoMatches) compiles unmodified against oracle/cvshim        */
+/* (oracle/_ref/libframeref.so); mvuRight / m_depths equal this            */
+/* restatement bit for bit (tests/test_oracle_vs_ref.py,                   */
+/* tests/golden/ref_stereo.npz).                                           */
 /* ------------------------------------------------------------------ */
 typedef struct { int dist, idx; } dist_idx;
 static int dist_idx_cmp(const void *a, const void *b)

@@ -110,7 +110,7 @@ const uint8_t *orbo_blurred(const orbo_extractor *e, int level, int *w, int *h, 
 int orbo_candidates(const orbo_extractor *e, int level, const int **xs, const int **ys, const int **score);
 void orbo_set_tie_rule(orbo_extractor *e, int tie_rule);
 
-/* ---- OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705 (PARITY UNPINNED: restatement only) ----
+/* ---- OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705 (pinned against the reference's own orbframe.cpp: oracle/_ref/libframeref.so, tests/golden/ref_stereo.npz) ----
  * pyrL/pyrR[l] = level ROI pointers of the two extractors, lw/lh/lstride per level; uRight/depth get nl floats
  * (-1 where there is no match).  Returns the number of matches before the median filter. */
 int orbo_stereo_matches(const orbo_keypoint *kl, const uint8_t *dl, int nl,

@@ -325,21 +325,56 @@ def transform4(child_off, child_ids, node_desc, word_id, weight, L, levels_up, f
     return ids, vals, nodes, feats
 
 
-def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
-    """OrbFrame::ComputeStereoMatches over two oracle extractors that just processed the left / right image."""
-    nlv = exL.nlevels
-    lvL = [np.ascontiguousarray(exL.level(l)) for l in range(nlv)]
-    lvR = [np.ascontiguousarray(exR.level(l)) for l in range(nlv)]
+def stereo_matches_levels(lvL, lvR, sf, isf, kl, dl, kr, dr, mbf, mb):
+    """OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705) over explicit pyramid levels (lists of 2-D uint8 arrays)."""
+    nlv = len(lvL)
+    lvL = [np.ascontiguousarray(a) for a in lvL]; lvR = [np.ascontiguousarray(a) for a in lvR]
     pl = (C.c_void_p * nlv)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * nlv)(*[a.ctypes.data for a in lvR])
     lw = (C.c_int * nlv)(*[a.shape[1] for a in lvL]); lh = (C.c_int * nlv)(*[a.shape[0] for a in lvL])
     ls = (C.c_size_t * nlv)(*[a.strides[0] for a in lvL])
-    sf = (C.c_float * nlv)(*exL.params.sf[:nlv]); isf = (C.c_float * nlv)(*exL.params.inv_sf[:nlv])
+    sf = (C.c_float * nlv)(*sf[:nlv]); isf = (C.c_float * nlv)(*isf[:nlv])
     kl = np.ascontiguousarray(kl); kr = np.ascontiguousarray(kr)
     dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
     u = np.empty(len(kl), np.float32); d = np.empty(len(kl), np.float32)
     n = lib().orbo_stereo_matches(_ptr(kl), _ptr(dl), len(kl), _ptr(kr), _ptr(dr), len(kr), pl, pr, lw, lh, ls, sf, isf,
                                   float(mbf), float(mb), _ptr(u), _ptr(d))
     return u, d, n
+
+
+def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
+    """OrbFrame::ComputeStereoMatches over two oracle extractors that just processed the left / right image."""
+    nlv = exL.nlevels
+    return stereo_matches_levels([exL.level(l) for l in range(nlv)], [exR.level(l) for l in range(nlv)],
+                                 exL.params.sf, exL.params.inv_sf, kl, dl, kr, dr, mbf, mb)
+
+
+def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1):
+    """The reference's own OrbFrame stereo constructor + ComputeStereoMatches (oracle/_ref/libframeref.so: src/orbframe.cpp
+    and src/orbextractor.cpp compiled unmodified) -> dict(kl, dl, kr, dr, levelsL, levelsR, uRight, depth)."""
+    class Cfg(C.Structure):
+        _fields_ = [("nfeatures", C.c_int), ("scale", C.c_float), ("nlevels", C.c_int), ("ini", C.c_int), ("min", C.c_int)]
+    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
+    R.frameref_stereo.restype = C.c_int
+    R.frameref_stereo.argtypes = [C.POINTER(Cfg), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float] + \
+        [C.c_void_p] * 4 + [C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 6
+    left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+    h, w = left.shape
+    cap = nfeatures + 512
+    kl = np.zeros(cap, KP_DTYPE); kr = np.zeros(cap, KP_DTYPE)
+    dl = np.zeros((cap, 32), np.uint8); dr = np.zeros((cap, 32), np.uint8)
+    lvL = [np.zeros(w * h, np.uint8) for _ in range(nlevels)]; lvR = [np.zeros(w * h, np.uint8) for _ in range(nlevels)]
+    pl = (C.c_void_p * nlevels)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * nlevels)(*[a.ctypes.data for a in lvR])
+    lw = (C.c_int * nlevels)(); lh = (C.c_int * nlevels)()
+    u = np.zeros(cap, np.float32); d = np.zeros(cap, np.float32)
+    nr = C.c_int()
+    n = R.frameref_stereo(C.byref(Cfg(nfeatures, scale_factor, nlevels, ini_th, min_th)), int(canonical), _ptr(left), _ptr(right), w, h,
+                          float(mbf), float(mb), _ptr(kl), _ptr(dl), _ptr(kr), _ptr(dr), cap, C.byref(nr), pl, pr, lw, lh, _ptr(u), _ptr(d))
+    if n < 0:
+        raise RuntimeError("frameref_stereo: more keypoints than the output buffers hold")
+    return dict(kl=kl[:n].copy(), dl=dl[:n].copy(), kr=kr[:nr.value].copy(), dr=dr[:nr.value].copy(),
+                levelsL=[lvL[l][:lw[l] * lh[l]].reshape(lh[l], lw[l]).copy() for l in range(nlevels)],
+                levelsR=[lvR[l][:lw[l] * lh[l]].reshape(lh[l], lw[l]).copy() for l in range(nlevels)],
+                uRight=u[:n].copy(), depth=d[:n].copy())
 
 
 class Extractor:

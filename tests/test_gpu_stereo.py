@@ -1,5 +1,8 @@
 """GPU parity of orbx_stereo_match (OrbFrame::ComputeStereoMatches, orbframe.cpp:511-705) against the
-oracle restatement.  (The oracle for this "next" row is a restatement only -- parity unpinned, see DESIGN.md.)"""
+oracle restatement and against tests/golden/ref_stereo.npz, the output of the reference's own src/orbframe.cpp
+(the restatement itself is pinned to that translation unit in tests/test_oracle_vs_ref.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -29,6 +32,26 @@ def test_two_handles_like_orbframe(oracle, mb):
         assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)), f"uRight differs at {np.flatnonzero(u != ou)[:5]}"
         assert np.array_equal(d.view(np.uint32), od.view(np.uint32))
         exL.close(); exR.close()
+
+
+def test_stereo_vs_reference_fixture():
+    """Images from the seed -> GPU extraction (left / right) -> GPU stereo matching, against the key points, descriptors,
+    mvuRight and m_depths the reference's own OrbFrame produced for the same pair (scripts/gen_golden_stereo.py)."""
+    import orbx
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_stereo.npz"))
+    for c, (w, h, seed, nf, nl, mbf, mb) in enumerate(g["cases"]):
+        w, h, seed, nf, nl = int(w), int(h), int(seed), int(nf), int(nl)
+        left, right = synth.stereo_pair(w, h, seed)
+        ex = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h, max_batch=2)
+        kps, desc, cnt = ex.extract_batch([left, right])
+        kl, dl, kr, dr = kps[0, :cnt[0]], desc[0, :cnt[0]], kps[1, :cnt[1]], desc[1, :cnt[1]]
+        assert kl.tobytes() == g[f"kl_{c}"].tobytes() and kr.tobytes() == g[f"kr_{c}"].tobytes()
+        assert np.array_equal(dl, g[f"dl_{c}"]) and np.array_equal(dr, g[f"dr_{c}"])
+        u, d, nm = orbx.stereo_match(ex, 0, ex, 1, float(mbf), float(mb))
+        assert nm == int((g[f"uRight_{c}"] >= 0).sum()) and nm > 50
+        assert np.array_equal(u.view(np.uint32), g[f"uRight_{c}"].view(np.uint32))
+        assert np.array_equal(d.view(np.uint32), g[f"depth_{c}"].view(np.uint32))
+        ex.close()
 
 
 def test_one_handle_batch_of_pairs(oracle):

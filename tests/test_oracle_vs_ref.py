@@ -98,3 +98,28 @@ def test_distinctive_oracle_equals_reference_sources(oracle, seed):
     assert ((best == -1) == (n == 0)).all() and ((has == 0) == (n == 0)).all()
     ok = n > 0
     assert ok.sum() > 250 and np.array_equal(desc[ind2[off2[:-1][ok] + best[ok]]], out[ok])
+
+
+FRAMEREF = os.path.join(os.path.dirname(REF), "libframeref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
+@pytest.mark.parametrize("w,h,seed,mbf,mb", [(1241, 376, 11, 386.1, 0.537), (640, 360, 5, 200.0, 0.4), (752, 480, 9, 435.2, 0.11),
+                                            (640, 360, 6, 200.0, 4.0)])      # mb = 4: maxD = 50 px cuts candidates
+@pytest.mark.parametrize("canonical", [1, 0])
+def test_stereo_oracle_equals_reference_sources(oracle, w, h, seed, mbf, mb, canonical):
+    """The reference's own OrbFrame (stereo constructor: two reference extractors in two threads, then
+    ComputeStereoMatches, src/orbframe.cpp compiled unmodified) against the oracle's restatement on the key points,
+    descriptors and pyramids that frame holds: mvuRight and m_depths bit for bit."""
+    left, right = synth.stereo_pair(w, h, seed)
+    r = oracle.ref_stereo_frame(left, right, mbf, mb, canonical=canonical)
+    ex = oracle.Extractor(2000, 1.2, 8)
+    kl, dl = ex.extract(left)
+    if canonical:                                         # heap addresses in allocation order: the whole frame is the oracle's
+        assert kl.tobytes() == r["kl"].tobytes() and np.array_equal(dl, r["dl"])
+    for l in range(8):                                    # the reference frame's pyramid is the oracle's pyramid
+        assert np.array_equal(ex.level(l), r["levelsL"][l])
+    u, d, _ = oracle.stereo_matches_levels(r["levelsL"], r["levelsR"], ex.params.sf, ex.params.inv_sf,
+                                           r["kl"], r["dl"], r["kr"], r["dr"], mbf, mb)
+    assert (r["uRight"] >= 0).sum() > 50
+    assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"])
