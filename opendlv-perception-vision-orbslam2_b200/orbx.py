@@ -401,6 +401,36 @@ def random_vocabulary(k=10, L=3, seed=0):
     return np.array(child_off, np.int32), np.array(child_ids, np.int32), node_desc, word_id, weight, L
 
 
+def filter_projection_candidates(r):
+    """Host side of SearchByProjection: drop candidates whose key point already carries an observed map
+    point (orbmatcher.cpp:87-89) or whose right coordinate is too far from the projection (:91-96).  `r`: mapping with
+    offsets / indices (CSR lists per map point), mp_x, mp_radius (per map point), b_uright, b_occupied (per key point)."""
+    off, ind = r["offsets"], r["indices"]
+    owner = np.repeat(np.arange(len(off) - 1), np.diff(off))
+    ur = r["b_uright"][ind]
+    er = np.abs(r["mp_x"][owner] - ur).astype(np.float32)                   # float subtraction, fabs, back to float (:93)
+    keep = (r["b_occupied"][ind] == 0) & ~((ur > 0) & (er > r["mp_radius"][owner]))
+    lens = np.bincount(owner[keep], minlength=len(off) - 1)
+    off2 = np.zeros(len(off), np.int32); off2[1:] = np.cumsum(lens)
+    return off2, ind[keep]
+
+
+def accept_projection_matches(idx1, d1, idx2, d2, octave, nnratio, th_high=100):
+    """The acceptance of orbmatcher.cpp:116-123 applied map point by map point, in order (a later map point overwrites
+    an earlier one on the same key point) -> assigned[n_keypoints], nmatches."""
+    assigned = np.full(len(octave), -1, np.int32)
+    n = 0
+    for i in range(len(idx1)):
+        if d1[i] > th_high:
+            continue
+        lv = octave[idx1[i]]; lv2 = octave[idx2[i]] if idx2[i] >= 0 else -1
+        if lv == lv2 and np.float32(d1[i]) > np.float32(nnratio) * np.float32(d2[i]):
+            continue
+        assigned[idx1[i]] = i
+        n += 1
+    return assigned, n
+
+
 def ratio_test(d1, d2, ratio=0.7, th=100):
     """Host-side acceptance exactly as the reference applies it (orbmatcher.cpp:234-236):
     d1 <= TH and (float)d1 < ratio * (float)d2."""

@@ -8,9 +8,9 @@
 // reference's ComputeStereoMatches once more; keys, descriptors, both pyramids and the results are handed back so that
 // the restatement can be run on exactly the same inputs.
 // Stand-ins defined here because their own translation units pull in the whole SLAM system:
-//   ORBmatcher::TH_HIGH / TH_LOW / HISTO_LENGTH (values of src/orbmatcher.cpp:36-38), OrbVocabulary::transform4 (unused:
-//   ComputeBoW is never called), Orbconverter::toDescriptorVector (declared in frame_pre.hpp).
-// OrbKeyFrame / OrbMap stand-ins and ORBmatcher::DescriptorDistance come from mappoint_glue.cpp.
+//   OrbVocabulary::transform4 (unused: ComputeBoW is never called), Orbconverter::toDescriptorVector (frame_pre.hpp).
+// OrbKeyFrame / OrbMap stand-ins come from mappoint_glue.cpp; ORBmatcher (DescriptorDistance, TH_HIGH / TH_LOW, the
+// search functions) is the reference's own src/orbmatcher.cpp, compiled unmodified into the same library.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
 
@@ -21,9 +21,6 @@ extern "C" {
 #include "orb_oracle.h"
 }
 
-const int ORBmatcher::TH_HIGH = 100;
-const int ORBmatcher::TH_LOW = 50;
-const int ORBmatcher::HISTO_LENGTH = 30;
 void OrbVocabulary::transform4(const std::vector<cv::Mat>, OrbBowVector &, OrbFeatureVector &, int) const { abort(); }
 std::vector<cv::Mat> Orbconverter::toDescriptorVector(const cv::Mat &d)
 {
@@ -90,6 +87,126 @@ int frameref_stereo(const frameref_cfg *c, int canonical, const uint8_t *left, c
     if (canonical) orbref_canonical(0);
     std::cout.rdbuf(old);
     return n;
+}
+
+extern "C++" std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows);   // mappoint_glue.cpp
+
+static std::shared_ptr<OrbFrame> make_frame(const frameref_cfg *c, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, float mb)
+{
+    auto exL = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
+    auto exR = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
+    cv::Mat imL(h, w, CV_8UC1, (void *)left, (size_t)w), imR(h, w, CV_8UC1, (void *)right, (size_t)w);
+    cv::Mat K(3, 3, CV_32F), dist(4, 1, CV_32F);
+    for (int i = 0; i < 9; i++) K.ptr<float>(i / 3)[i % 3] = (i % 4 == 0) ? 1.f : 0.f;
+    K.at<float>(0, 0) = 700.f; K.at<float>(1, 1) = 700.f; K.at<float>(0, 2) = w * 0.5f; K.at<float>(1, 2) = h * 0.5f;
+    for (int i = 0; i < 4; i++) dist.ptr<float>(i)[0] = 0.f;
+    std::array<float, 4> box = {0.f, 0.f, 0.f, 0.f};
+    OrbFrame::m_initialComputations = true;
+    auto f = std::make_shared<OrbFrame>(imL, imR, 0.0, exL, exR, std::shared_ptr<OrbVocabulary>(), K, dist, mbf, 35.f * mbf / 700.f, box);
+    f->mb = mb;
+    f->ComputeStereoMatches();
+    return f;
+}
+
+// The reference's own ORBmatcher::SearchByProjection(frame, map points, th) (src/orbmatcher.cpp:42-124, unmodified).
+// Frame A (leftA / rightA) supplies the map points: one per key point i with i % mp_step == 0, built by the reference's
+// OrbMapPoint(position, frame, map, i) constructor (descriptor = A's row i), marked in view at (x_i + dx, y_i + dy), level =
+// octave_i, viewing cosine alternating between 0.9995 and 0.9.  Frame B (leftB / rightB) is searched.  Key points of B
+// with idx % 7 == 3 already carry a map point that has an observation (excluded by :87-89), those with idx % 11 == 5 one
+// without (not excluded).  Handed back: the map points' descriptors and tracking fields, B's descriptors / octaves /
+// mvuRight, the candidate lists the reference's own GetFeaturesInArea returns for every map point (CSR, in its order),
+// the radius r * scaleFactor[level] of :64-67, and the result: assigned[idx] = index of the map point the reference
+// stored in B.m_mapPoints[idx] (-1 none, -2 the pre-assigned ones left in place), return value = its nmatches.
+int frameref_search_by_projection(const frameref_cfg *c, int canonical, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB,
+                                  const uint8_t *rightB, int w, int h, float mbf, float mb, float th, float nnratio,
+                                  int mp_step, float dx, float dy, int cap, int list_cap,
+                                  int *n_mp_out, uint8_t *mp_desc, float *mp_x, float *mp_radius,
+                                  int *n_b_out, uint8_t *b_desc, int32_t *b_octave, float *b_uright, int32_t *b_occupied,
+                                  int32_t *offsets, int32_t *indices, int32_t *assigned)
+{
+    std::streambuf *old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    std::shared_ptr<OrbKeyFrame> kf = mpref_standin_keyframe(8);   // before the arena: its static pool outlives this call
+    if (canonical) orbref_canonical(1);
+    int nmatches = -1;
+    {
+        std::shared_ptr<OrbFrame> A = make_frame(c, leftA, rightA, w, h, mbf, mb);
+        cv::Mat Tcw(4, 4, CV_32F);
+        for (int i = 0; i < 16; i++) Tcw.ptr<float>(i / 4)[i % 4] = (i % 5 == 0) ? 1.f : 0.f;
+        A->SetPose(Tcw);
+        std::vector<std::shared_ptr<OrbMapPoint>> mps;
+        for (int i = 0; i < A->N; i += mp_step) {
+            cv::Mat pos(3, 1, CV_32F);
+            pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
+            auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
+            mp->SetTrackInView(true);
+            mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
+            mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
+            mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
+            mp->SetTrackViewCos((mps.size() & 1) ? 0.9f : 0.9995f);
+            mps.push_back(mp);
+        }
+        std::shared_ptr<OrbFrame> B = make_frame(c, leftB, rightB, w, h, mbf, mb);
+        const int nb = B->N, nmp = (int)mps.size();
+        *n_mp_out = nmp; *n_b_out = nb;
+        if (nb <= cap && nmp <= cap) {
+            cv::Mat pos(3, 1, CV_32F);
+            for (int k = 0; k < 3; k++) pos.ptr<float>(k)[0] = 1.f;
+            for (int idx = 0; idx < nb; idx++) {
+                b_occupied[idx] = 0;
+                if (idx % 7 == 3 || idx % 11 == 5) {
+                    auto held = std::make_shared<OrbMapPoint>(pos, kf, std::shared_ptr<OrbMap>());
+                    if (idx % 7 == 3) { held->AddObservingKeyframe(kf, 1); b_occupied[idx] = 1; }
+                    B->m_mapPoints[idx] = held;
+                }
+                memcpy(b_desc + (size_t)idx * 32, B->m_descriptors.ptr(idx), 32);
+                b_octave[idx] = B->m_undistortedKeys[idx].octave;
+                b_uright[idx] = B->mvuRight[idx];
+            }
+            const bool bFactor = std::abs(th - 1.0) < 0.0000000001f;            // :47
+            int total = 0;
+            offsets[0] = 0;
+            bool fits = true;
+            for (int i = 0; i < nmp && fits; i++) {
+                cv::Mat d = mps[i]->GetDescriptor();
+                memcpy(mp_desc + (size_t)i * 32, d.ptr(0), 32);
+                const int level = mps[i]->GetTrackScaleLevel();
+                float r = mps[i]->GTrackViewCos() > 0.998 ? 2.5f : 4.0f;         // RadiusByViewingCos, :126-131
+                if (bFactor) r *= th;                                            // :61-62
+                mp_x[i] = mps[i]->getTrackProjX();
+                mp_radius[i] = r * B->m_scaleFactors[level];
+                const std::vector<size_t> v = B->GetFeaturesInArea(mps[i]->getTrackProjX(), mps[i]->getTrackProjY(),
+                                                                   r * B->m_scaleFactors[level], level - 1, level);
+                if (total + (int)v.size() > list_cap) { fits = false; break; }
+                for (size_t k = 0; k < v.size(); k++) indices[total++] = (int32_t)v[k];
+                offsets[i + 1] = total;
+            }
+            if (fits) {
+                std::vector<std::shared_ptr<OrbMapPoint>> before = B->m_mapPoints;
+                ORBmatcher matcher(nnratio, true);
+                nmatches = matcher.SearchByProjection(B, mps, th);
+                for (int idx = 0; idx < nb; idx++) {
+                    assigned[idx] = -1;
+                    if (!B->m_mapPoints[idx]) continue;
+                    if (B->m_mapPoints[idx] == before[idx]) { assigned[idx] = -2; continue; }
+                    for (int i = 0; i < nmp; i++) if (mps[i] == B->m_mapPoints[idx]) { assigned[idx] = i; break; }
+                }
+            }
+        }
+    }
+    if (canonical) orbref_canonical(0);
+    std::cout.rdbuf(old);
+    return nmatches;
+}
+
+// The reference's own ORBmatcher::DescriptorDistance (src/orbmatcher.cpp:1662-1677) on n pairs of 32-byte rows.
+void frameref_descriptor_distance(const uint8_t *a, const uint8_t *b, int n, int32_t *out)
+{
+    for (int i = 0; i < n; i++) {
+        const cv::Mat ma(1, 32, CV_8U, (void *)(a + (size_t)i * 32), 32), mb(1, 32, CV_8U, (void *)(b + (size_t)i * 32), 32);
+        out[i] = ORBmatcher::DescriptorDistance(ma, mb);
+    }
 }
 
 } // extern "C"

@@ -46,7 +46,28 @@ cv::Mat OrbKeyFrame::GetCameraCenter() { return cv::Mat(); }
 void OrbKeyFrame::EraseMapPointMatch(const size_t &) {}
 void OrbKeyFrame::ReplaceMapPointMatch(const size_t &, std::shared_ptr<OrbMapPoint>) {}
 void OrbMap::DeleteOrbMapPoint(std::shared_ptr<OrbMapPoint>) {}
+#ifdef ORBREF_WITH_MATCHER
+// libframeref.so links the reference's own src/orbmatcher.cpp (the real DescriptorDistance); the key-frame members that
+// translation unit references but the functions driven here never reach are inert as well
+void OrbKeyFrame::AddMapPoint(std::shared_ptr<OrbMapPoint>, const size_t &) {}
+std::shared_ptr<OrbMapPoint> OrbKeyFrame::GetMapPoint(const size_t &) { return std::shared_ptr<OrbMapPoint>(); }
+cv::Mat OrbKeyFrame::GetRotation() { return cv::Mat(); }
+cv::Mat OrbKeyFrame::GetTranslation() { return cv::Mat(); }
+std::set<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPoints() { return std::set<std::shared_ptr<OrbMapPoint>>(); }
+std::vector<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPointMatches() { return std::vector<std::shared_ptr<OrbMapPoint>>(); }
+std::vector<size_t> OrbKeyFrame::GetFeaturesInArea(const float &, const float &, const float &) const { return std::vector<size_t>(); }
+bool OrbKeyFrame::IsInImage(const float &, const float &) const { return false; }
+// a stand-in key frame with `rows` key points (no stereo coordinate), for map points that need an observation
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows)
+{
+    g_pool.create(rows, 32, CV_8U);
+    g_uright.assign((size_t)rows, -1.0f);
+    g_bad = false;
+    return std::make_shared<OrbKeyFrame>(std::shared_ptr<OrbFrame>(), std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+}
+#else
 int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return OrbDescriptor::distance(a, b); }
+#endif
 
 extern "C" {
 

@@ -304,6 +304,47 @@ def ref_distinctive(desc, offsets, indices, bad=None):
     return out, has
 
 
+def ref_descriptor_distance(a, b):
+    """The reference's own ORBmatcher::DescriptorDistance (orbmatcher.cpp:1662-1677, oracle/_ref/libframeref.so), row by row."""
+    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    out = np.zeros(len(a), np.int32)
+    R.frameref_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    R.frameref_descriptor_distance(_ptr(a), _ptr(b), len(a), _ptr(out))
+    return out
+
+
+def ref_search_by_projection(pairA, pairB, mbf, mb, th=3.0, nnratio=0.8, mp_step=1, dx=0.0, dy=0.0,
+                             nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1):
+    """The reference's own ORBmatcher::SearchByProjection(frame, map points, th) (src/orbmatcher.cpp:42-124 compiled
+    unmodified into oracle/_ref/libframeref.so) on two reference OrbFrames; see oracle/cvshim/frame_glue.cpp.
+    -> dict(mp_desc, mp_x, mp_radius, b_desc, b_octave, b_uright, b_occupied, offsets, indices, assigned, nmatches)."""
+    class Cfg(C.Structure):
+        _fields_ = [("nfeatures", C.c_int), ("scale", C.c_float), ("nlevels", C.c_int), ("ini", C.c_int), ("min", C.c_int)]
+    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
+    R.frameref_search_by_projection.restype = C.c_int
+    R.frameref_search_by_projection.argtypes = [C.POINTER(Cfg), C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + \
+        [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int] + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)] + [C.c_void_p] * 7
+    imgs = [np.ascontiguousarray(a, np.uint8) for a in (*pairA, *pairB)]
+    h, w = imgs[0].shape
+    cap, list_cap = nfeatures + 512, 1 << 22
+    mp_desc = np.zeros((cap, 32), np.uint8); mp_x = np.zeros(cap, np.float32); mp_r = np.zeros(cap, np.float32)
+    b_desc = np.zeros((cap, 32), np.uint8); b_oct = np.zeros(cap, np.int32); b_ur = np.zeros(cap, np.float32)
+    b_occ = np.zeros(cap, np.int32); offsets = np.zeros(cap + 1, np.int32); indices = np.zeros(list_cap, np.int32)
+    assigned = np.zeros(cap, np.int32)
+    nmp, nb = C.c_int(), C.c_int()
+    nm = R.frameref_search_by_projection(C.byref(Cfg(nfeatures, scale_factor, nlevels, ini_th, min_th)), int(canonical), *[_ptr(a) for a in imgs], w, h,
+                                         float(mbf), float(mb), float(th), float(nnratio), int(mp_step), float(dx), float(dy), cap, list_cap,
+                                         C.byref(nmp), _ptr(mp_desc), _ptr(mp_x), _ptr(mp_r), C.byref(nb), _ptr(b_desc), _ptr(b_oct),
+                                         _ptr(b_ur), _ptr(b_occ), _ptr(offsets), _ptr(indices), _ptr(assigned))
+    if nm < 0:
+        raise RuntimeError("frameref_search_by_projection: output buffers too small")
+    nmp, nb = nmp.value, nb.value
+    return dict(mp_desc=mp_desc[:nmp].copy(), mp_x=mp_x[:nmp].copy(), mp_radius=mp_r[:nmp].copy(), b_desc=b_desc[:nb].copy(),
+                b_octave=b_oct[:nb].copy(), b_uright=b_ur[:nb].copy(), b_occupied=b_occ[:nb].copy(), offsets=offsets[:nmp + 1].copy(),
+                indices=indices[:offsets[nmp]].copy(), assigned=assigned[:nb].copy(), nmatches=nm)
+
+
 def transform4(child_off, child_ids, node_desc, word_id, weight, L, levels_up, feat):
     """OrbVocabulary::transform4 (orbvocabulary.cpp:168-201) on top of the restated transform5: features with a positive
     word weight enter the bag of words (weights summed per word, then L1-normalised, orbbowvector.cpp:29-69) and the

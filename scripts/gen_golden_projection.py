@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""Golden fixture for the candidate-list row (tests/golden/ref_projection.npz); run in the BUILD container only.
+
+Source of truth: the reference's own ORBmatcher::SearchByProjection(frame, map points, th) -- src/orbmatcher.cpp
+(with its own DescriptorDistance), src/orbframe.cpp, src/orbmappoint.cpp, src/orbextractor.cpp compiled UNMODIFIED
+against oracle/cvshim (oracle/_ref/libframeref.so, `make -C oracle ref`, driver in oracle/cvshim/frame_glue.cpp).
+Stored per case: the map points' descriptors and tracking fields, the searched frame's descriptors / octaves / mvuRight /
+occupied flags, the candidate lists the reference's own GetFeaturesInArea produced, and the assignment it made.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "opendlv-perception-vision-orbslam2_b200")]
+import orb_oracle_py as O  # noqa: E402
+import synth  # noqa: E402
+
+# w, h, seed A, seed B, dx, dy, th, nnratio, nfeatures
+CASES = [(640, 360, 5, 5, 0.7, 0.4, 3.0, 0.8, 1000), (800, 240, 21, 21, -1.5, 1.0, 1.0, 0.6, 1200), (640, 360, 5, 6, 0.0, 0.0, 3.0, 0.9, 1000)]
+out = {"cases": np.array(CASES, np.float64)}
+for c, (w, h, sa, sb, dx, dy, th, ratio, nf) in enumerate(CASES):
+    r = O.ref_search_by_projection(synth.stereo_pair(w, h, sa), synth.stereo_pair(w, h, sb), 386.1, 0.537, th=th, nnratio=ratio,
+                                   dx=dx, dy=dy, nfeatures=nf)
+    for k, v in r.items():
+        out[f"{k}_{c}"] = np.asarray(v)
+    print(w, h, "map points", len(r["mp_desc"]), "candidates", len(r["indices"]), "matches", r["nmatches"])
+path = os.path.join(ROOT, "tests", "golden", "ref_projection.npz")
+np.savez_compressed(path, **out)
+print("ref_projection.npz", os.path.getsize(path))

@@ -122,6 +122,47 @@ def test_knn2_csr_full_lists_equal_bruteforce(oracle):
     m.close()
 
 
+def test_search_by_projection_vs_reference_fixture():
+    """tests/golden/ref_projection.npz holds the inputs and the result of the reference's own ORBmatcher::SearchByProjection
+    (src/orbmatcher.cpp:42-124, compiled unmodified).  Both GPU routes reproduce its B.m_mapPoints and nmatches: filtered
+    lists -> orbm_knn2_csr -> acceptance, and all candidates -> orbm_distance_csr -> the loop replayed with its exclusions."""
+    import os
+    import orbx
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_projection.npz"))
+    for c, case in enumerate(g["cases"]):
+        ratio = float(case[7])
+        r = {k: g[f"{k}_{c}"] for k in ("mp_desc", "mp_x", "mp_radius", "b_desc", "b_octave", "b_uright", "b_occupied", "offsets", "indices", "assigned")}
+        ref, nref = r["assigned"], int(g[f"nmatches_{c}"])
+        m = orbx.Matcher(max_queries=len(r["mp_desc"]), max_train=len(r["b_desc"]))
+        off2, ind2 = orbx.filter_projection_candidates(r)
+        i1, d1, i2, d2 = m.knn2_csr(r["mp_desc"], r["b_desc"], off2, ind2)
+        got, n = orbx.accept_projection_matches(i1, d1, i2, d2, r["b_octave"], ratio)
+        got[(got == -1) & (ref == -2)] = -2
+        assert n == nref and np.array_equal(got, ref)
+        # second route: every candidate's distance in one launch, then the reference's loop verbatim on the host
+        dist = m.distance_csr(r["mp_desc"], r["b_desc"], r["offsets"], r["indices"])
+        got2, n2 = np.full(len(ref), -1, np.int32), 0
+        off, ind, ur = r["offsets"], r["indices"], r["b_uright"]
+        for i in range(len(off) - 1):
+            best, best2, lv, lv2, bi = 256, 256, -1, -1, -1
+            for k in range(off[i], off[i + 1]):
+                idx = int(ind[k])
+                if r["b_occupied"][idx]:
+                    continue
+                if ur[idx] > 0 and np.float32(abs(r["mp_x"][i] - ur[idx])) > r["mp_radius"][i]:
+                    continue
+                d = int(dist[k])
+                if d < best:
+                    best2, best, lv2, lv, bi = best, d, lv, int(r["b_octave"][idx]), idx
+                elif d < best2:
+                    lv2, best2 = int(r["b_octave"][idx]), d
+            if best <= 100 and not (lv == lv2 and np.float32(best) > np.float32(ratio) * np.float32(best2)):
+                got2[bi] = i; n2 += 1
+        got2[(got2 == -1) & (ref == -2)] = -2
+        assert n2 == nref and np.array_equal(got2, ref)
+        m.close()
+
+
 def test_distance_csr_and_host_replay_of_search_by_projection(oracle):
     """orbm_distance_csr gives every candidate's distance; replaying the reference's SearchByProjection loop
     (orbmatcher.cpp:76-124, with its 'keypoint already carries a map point' exclusion) on those distances equals the

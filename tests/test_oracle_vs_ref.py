@@ -123,3 +123,43 @@ def test_stereo_oracle_equals_reference_sources(oracle, w, h, seed, mbf, mb, can
                                            r["kl"], r["dl"], r["kr"], r["dr"], mbf, mb)
     assert (r["uRight"] >= 0).sum() > 50
     assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"])
+
+
+@pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
+@pytest.mark.parametrize("w,h,sa,sb,dx,dy,th,ratio,canonical", [
+    (1241, 376, 11, 11, 0.0, 0.0, 3.0, 0.8, 1), (1241, 376, 11, 11, 1.5, -1.0, 1.0, 0.8, 0),
+    (640, 360, 5, 5, 0.7, 0.4, 3.0, 0.6, 1), (640, 360, 5, 6, 0.0, 0.0, 3.0, 0.9, 1)])
+def test_search_by_projection_oracle_equals_reference_sources(oracle, w, h, sa, sb, dx, dy, th, ratio, canonical):
+    """The reference's own ORBmatcher::SearchByProjection (src/orbmatcher.cpp:42-124 with its own DescriptorDistance,
+    compiled unmodified) on two reference frames, against the candidate-list restatement: the lists are the ones the
+    reference's GetFeaturesInArea returned, the host drops the statically excluded candidates, orbo_knn2_csr gives
+    best / second best, and the acceptance of :116-123 reproduces B.m_mapPoints and nmatches exactly."""
+    import orbx
+    r = oracle.ref_search_by_projection(synth.stereo_pair(w, h, sa), synth.stereo_pair(w, h, sb), 386.1, 0.537, th=th,
+                                        nnratio=ratio, dx=dx, dy=dy, canonical=canonical)
+    off2, ind2 = orbx.filter_projection_candidates(r)
+    assert len(ind2) < len(r["indices"])                  # both exclusions actually fire
+    i1, d1, i2, d2 = oracle.knn2_csr(r["mp_desc"], r["b_desc"], off2, ind2)
+    got, n = orbx.accept_projection_matches(i1, d1, i2, d2, r["b_octave"], ratio)
+    ref = r["assigned"]
+    got[(got == -1) & (ref == -2)] = -2                   # key points that kept the map point they carried before
+    assert n == r["nmatches"] and n > 20 and np.array_equal(got, ref)
+    assert (ref[r["b_occupied"] == 1] == -2).all()
+    # the reference's own DescriptorDistance, through its loop, equals the restated one on every candidate it accepted
+    hit = np.flatnonzero(ref >= 0)
+    assert np.array_equal(np.array([oracle.descriptor_distance(r["mp_desc"][ref[k]], r["b_desc"][k]) for k in hit]), d1[ref[hit]])
+
+
+@pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
+def test_descriptor_distance_equals_reference_function(oracle):
+    """ORBmatcher::DescriptorDistance itself (src/orbmatcher.cpp:1662-1677, compiled unmodified) on random, equal,
+    complementary and one-bit pairs."""
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (4000, 32), dtype=np.uint8); b = rng.integers(0, 256, (4000, 32), dtype=np.uint8)
+    b[:100] = a[:100]; b[100:200] = ~a[100:200]
+    for k in range(256):
+        b[200 + k] = a[200 + k]; b[200 + k, k // 8] ^= np.uint8(1 << (k % 8))
+    ref = oracle.ref_descriptor_distance(a, b)
+    assert (ref[:100] == 0).all() and (ref[100:200] == 256).all() and (ref[200:456] == 1).all()
+    assert np.array_equal(ref, np.array([oracle.descriptor_distance(a[i], b[i]) for i in range(len(a))], np.int32))
+    assert np.array_equal(ref, np.unpackbits(a ^ b, axis=1).sum(1))
