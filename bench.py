@@ -424,6 +424,20 @@ def main():
         next_rows["distinctive_descriptors"] = {"points_per_s": npts / dt_d, "ms_per_call": dt_d * 1e3,
                                                 "workload": f"{npts} map points with 2..24 observations each, host arrays in and out"}
 
+        # SearchByProjection (N3) with the frame grid on the device: frame 0's key points as map points, projected
+        # 1.25 px beside themselves into frame 0 (the shape of TrackLocalMap: ~2000 points against ~2000 key points)
+        k0 = np.ascontiguousarray(out[0][0, :out[2][0]]); d0 = np.ascontiguousarray(out[1][0, :out[2][0]])
+        sfl = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+        proj_args = (k0, np.full(len(k0), -1, np.float32), None, d0, (0.0, 0.0, float(W), float(H)), d0, k0["x"] + np.float32(1.25), k0["y"].copy(),
+                     k0["octave"].copy(), (np.float32(4.0) * sfl[k0["octave"]]).astype(np.float32))
+        m.search_by_projection(*proj_args)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            _, _, pnm = m.search_by_projection(*proj_args)
+        dt_p = (time.perf_counter() - t0) / 20
+        next_rows["search_by_projection"] = {"map_points_per_s": len(k0) / dt_p, "ms_per_call": dt_p * 1e3, "matches": int(pnm),
+                                             "workload": f"{len(k0)} map points against one frame of {len(k0)} key points, grid + candidate lists + best/second best on the device, host arrays in and out"}
+
     # ---- max over ranks
     times = torch.tensor([ms_dev, s_e2e, ms_match], dtype=torch.float64, device=dev)
     if world > 1:
@@ -500,6 +514,10 @@ def main():
             line["next_rows"]["bow_transform"]["cpu_port_features_per_s_1core"] = len(fs) / dtv
             t0 = time.perf_counter(); O.distinctive(pool, offs[:2001], inds[:offs[2000]]); dtd = time.perf_counter() - t0
             line["next_rows"]["distinctive_descriptors"]["cpu_port_points_per_s_1core"] = 2000 / dtd
+            t0 = time.perf_counter()
+            for _ in range(5):
+                O.search_by_projection(*proj_args)
+            line["next_rows"]["search_by_projection"]["cpu_port_map_points_per_s_1core"] = len(k0) * 5 / (time.perf_counter() - t0)
         print(json.dumps(line), flush=True)
     ex.close(); m.close()
     if world > 1:

@@ -192,6 +192,28 @@ int orbm_knn2_csr_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint
  * distances at once, the host replays the reference's loop (:76-124) over the precomputed distances in its own order. */
 int orbm_distance_csr(orbm_matcher *m, const uint8_t *q, int nq, const uint8_t *t, int nt, const int32_t *offsets,
                       const int32_t *indices, int32_t *dist);
+/* One frame as ORBmatcher::SearchByProjection reads it (include/orbframe.hpp:141-175): n key points. */
+typedef struct {
+    const orbx_keypoint *keys;      /* m_undistortedKeys.data() (cv::KeyPoint layout) */
+    const float *u_right;           /* mvuRight */
+    const uint8_t *occupied;        /* != 0: m_mapPoints[i] is set and has observations (orbmatcher.cpp:87-89); may be NULL */
+    const uint8_t *desc;            /* m_descriptors, n x 32 */
+    int32_t n;
+    float min_x, min_y, max_x, max_y;   /* OrbFrame::m_minX .. m_maxY (orbframe.cpp:482-503) */
+} orbm_frame_view;
+/* ORBmatcher::SearchByProjection(frame, map points, th) (orbmatcher.cpp:42-124) for all map points in one pass, the
+ * frame side included: OrbFrame::AssignFeaturesToGrid / PosInGrid (orbframe.cpp:192-211, :381-393; 64 x 48 cells, cell
+ * lists in key-point order) and OrbFrame::GetFeaturesInArea (:308-380; cells column by column, level window
+ * [level-1, level], |dx| < r and |dy| < r) are evaluated on the device with the reference's float arithmetic.
+ * Map point i: descriptor mp_desc[i], projection (mp_x, mp_y)[i] (mTrackProjX/Y), mp_level[i] (mnTrackScaleLevel) and
+ * mp_radius[i] = r * m_scaleFactors[level] exactly as the caller computes it at :54-67; only map points that pass the
+ * caller's GetTrackInView / IsCorrupt tests (:51-55) are handed in.  Candidates are skipped as at :87-96, best / second
+ * best follow the strict '<' updates of :102-114, acceptance is :116-123 with TH_HIGH = th_high and mfNNratio = nnratio.
+ * mp_match[i] = key point accepted for map point i or -1; assigned[k] = the map point the reference's loop leaves in
+ * m_mapPoints[k] among those handed in (the last accepted one) or -1; *nmatches = the function's return value. */
+int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
+                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
+                              int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches);
 /* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points.
  * Point p observes the rows indices[offsets[p] .. offsets[p+1]) of the descriptor pool desc[n_desc][32] (what the
  * reference gathers from its key frames, :328-337).  Per point: all-pairs DescriptorDistance (:350-358), per row the

@@ -232,6 +232,131 @@ k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ offsets, c
     if (lane == 0) out[p] = make_int2((int)(bestKey & 0xffffu), (int)(bestKey >> 16));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByProjection(frame, map points, th) with the frame's grid (orbmatcher.cpp:42-124, orbframe.cpp:192-211,
+// :308-393).  All float expressions are formed operation by operation (__fsub_rn / __fmul_rn: no FMA contraction), as the
+// reference's x86-64 build evaluates them.
+#define FG_COLS 64          // FRAME_GRID_COLS, orbframe.hpp:52
+#define FG_ROWS 48          // FRAME_GRID_ROWS, orbframe.hpp:51
+#define FG_CELLS (FG_COLS * FG_ROWS)
+
+// One CTA: PosInGrid for every key point, cell histogram, exclusive scan, then warp 0 fills the cell lists in key-point
+// order (AssignFeaturesToGrid pushes i = 0 .. N-1 in order, orbframe.cpp:202-209).  Cell index = ix * FG_ROWS + iy, the
+// order GetFeaturesInArea walks the cells in (:339-341).
+__global__ void __launch_bounds__(1024)
+k_frame_grid(const orbx_keypoint *__restrict__ keys, int n, float minX, float minY, float invW, float invH,
+             int *__restrict__ cellOf, int *__restrict__ cellStart, int *__restrict__ cellItems)
+{
+    __shared__ int cnt[FG_CELLS];
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < FG_CELLS; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, minX), invW));      // :383
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, minY), invH));      // :384
+        const int c = (px < 0 || px >= FG_COLS || py < 0 || py >= FG_ROWS) ? -1 : px * FG_ROWS + py;   // :387
+        cellOf[i] = c;
+        if (c >= 0) atomicAdd(&cnt[c], 1);
+    }
+    __syncthreads();
+    const int a0 = cnt[3 * tid], a1 = cnt[3 * tid + 1], a2 = cnt[3 * tid + 2];
+    const int s = a0 + a1 + a2;
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const int base = wsum[warp] + inc - s;
+    cnt[3 * tid] = base; cnt[3 * tid + 1] = base + a0; cnt[3 * tid + 2] = base + a0 + a1;
+    cellStart[3 * tid] = base; cellStart[3 * tid + 1] = base + a0; cellStart[3 * tid + 2] = base + a0 + a1;
+    if (tid == 1023) cellStart[FG_CELLS] = base + s;
+    __syncthreads();
+    if (warp == 0) {
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int c = i < n ? cellOf[i] : -1;
+            const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+            if (c >= 0) {
+                const unsigned same = __match_any_sync(act, c);
+                const int leader = __ffs(same) - 1;
+                int b = 0;
+                if (lane == leader) { b = cnt[c]; cnt[c] = b + __popc(same); }
+                b = __shfl_sync(same, b, leader);
+                cellItems[b + __popc(same & ((1u << lane) - 1u))] = i;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// One thread per map point: GetFeaturesInArea + the candidate loop + the acceptance, sequentially in the reference's order.
+__global__ void __launch_bounds__(128)
+k_project_search(const orbx_keypoint *__restrict__ keys, const float *__restrict__ uRight, const uint8_t *__restrict__ occupied,
+                 const uint4 *__restrict__ desc, const int *__restrict__ cellStart, const int *__restrict__ cellItems,
+                 float minX, float minY, float invW, float invH, const uint4 *__restrict__ mpDesc, const float *__restrict__ mpX,
+                 const float *__restrict__ mpY, const int *__restrict__ mpLevel, const float *__restrict__ mpRadius, int nMp,
+                 float nnRatio, int thHigh, int *__restrict__ mpMatch, int *__restrict__ assigned, int *__restrict__ nMatches)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nMp) return;
+    const float x = mpX[i], y = mpY[i], r = mpRadius[i];
+    const int level = mpLevel[i];
+    const int minLevel = level - 1, maxLevel = level;                                  // orbmatcher.cpp:67-68
+    mpMatch[i] = -1;
+    const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));             // orbframe.cpp:313
+    if (c0x >= FG_COLS) return;
+    const int c1x = min(FG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));    // :319
+    if (c1x < 0) return;
+    const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));             // :325
+    if (c0y >= FG_ROWS) return;
+    const int c1y = min(FG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));    // :331
+    if (c1y < 0) return;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);                        // :337
+    const uint4 qa = mpDesc[2 * i], qb = mpDesc[2 * i + 1];
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;   // orbmatcher.cpp:75-79
+    for (int ix = c0x; ix <= c1x; ix++) {
+        // the cells (ix, c0y .. c1y) are adjacent in the cell order: one contiguous run of the item list
+        const int e0 = cellStart[ix * FG_ROWS + c0y], e1 = cellStart[ix * FG_ROWS + c1y + 1];
+        for (int e = e0; e < e1; e++) {
+            const int idx = cellItems[e];
+            const orbx_keypoint kp = keys[idx];
+            if (checkLevels) {
+                if (kp.octave < minLevel) continue;                                    // orbframe.cpp:354
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;                   // :358-363
+            }
+            const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;                           // :370
+            if (occupied && occupied[idx]) continue;                                   // orbmatcher.cpp:87-89
+            const float ur = uRight[idx];
+            if (ur > 0.f && fabsf(__fsub_rn(x, ur)) > r) continue;                     // :91-96
+            const uint4 ta = desc[2 * idx], tb = desc[2 * idx + 1];
+            const int dist = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                             __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            if (dist < bestDist) {                                                     // :102-114
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = kp.octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kp.octave; bestDist2 = dist;
+            }
+        }
+    }
+    if (bestDist <= thHigh) {                                                          // :116-123
+        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnRatio, (float)bestDist2)) return;
+        mpMatch[i] = bestIdx;
+        atomicMax(&assigned[bestIdx], i);          // the loop runs in map-point order: the last accepted one stays
+        atomicAdd(nMatches, 1);
+    }
+}
+
 
 struct orbm_matcher {
     int device = 0, maxQ = 0, maxT = 0, smCount = 148;
@@ -246,6 +371,8 @@ struct orbm_matcher {
     uint8_t *ddDesc = nullptr; size_t ddCap = 0;
     int *ddCsr = nullptr; size_t ddCsrCap = 0;
     int2 *ddBest = nullptr, *ddHost = nullptr; int ddBestCap = 0;
+    // orbm_search_by_projection: one workspace (frame + map points + grid + results), grown on demand
+    uint8_t *spBuf = nullptr; size_t spCap = 0;
     std::string err;
 };
 
@@ -335,6 +462,7 @@ void orbm_destroy(orbm_matcher *m)
     if (m->ddCsr) cudaFree(m->ddCsr);
     if (m->ddBest) cudaFree(m->ddBest);
     if (m->ddHost) cudaFreeHost(m->ddHost);
+    if (m->spBuf) cudaFree(m->spBuf);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -546,6 +674,75 @@ int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int
     MCK(cudaMemcpyAsync(m->hOut, m->dOut, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     MCK(cudaStreamSynchronize(m->stream));
     memcpy(out, m->hOut, (size_t)n * sizeof(int));
+    return ORBX_OK;
+}
+
+
+int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
+                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
+                              int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!frame || !mp_desc || !mp_x || !mp_y || !mp_level || !mp_radius || !mp_match || !assigned || !nmatches || n_mp < 1 ||
+        frame->n < 0 || (frame->n > 0 && (!frame->keys || !frame->u_right || !frame->desc)) || th_high < 0 || th_high > 255 ||
+        !(frame->max_x > frame->min_x) || !(frame->max_y > frame->min_y))
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    const int n = frame->n;
+    *nmatches = 0;
+    for (int i = 0; i < n_mp; i++) mp_match[i] = -1;
+    for (int k = 0; k < n; k++) assigned[k] = -1;
+    if (n == 0) return ORBX_OK;
+    MCK(cudaSetDevice(m->device));
+    // m_gridElementWidthInverse / HeightInverse, orbframe.cpp:179-180
+    const float invW = (float)FG_COLS / (frame->max_x - frame->min_x), invH = (float)FG_ROWS / (frame->max_y - frame->min_y);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t oDesc = o;    o += al((size_t)n * 32);
+    const size_t oMpDesc = o;  o += al((size_t)n_mp * 32);
+    const size_t oKeys = o;    o += al((size_t)n * sizeof(orbx_keypoint));
+    const size_t oUr = o;      o += al((size_t)n * 4);
+    const size_t oOcc = o;     o += al((size_t)n);
+    const size_t oCellOf = o;  o += al((size_t)n * 4);
+    const size_t oItems = o;   o += al((size_t)n * 4);
+    const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
+    const size_t oMpX = o;     o += al((size_t)n_mp * 4);
+    const size_t oMpY = o;     o += al((size_t)n_mp * 4);
+    const size_t oMpR = o;     o += al((size_t)n_mp * 4);
+    const size_t oMpL = o;     o += al((size_t)n_mp * 4);
+    const size_t oMatch = o;   o += al((size_t)n_mp * 4);
+    const size_t oAsg = o;     o += al((size_t)n * 4 + 4);          // assigned[n] | nmatches
+    if (o > m->spCap) {
+        if (m->spBuf) cudaFree(m->spBuf);
+        m->spBuf = nullptr; m->spCap = 0;
+        MCK(cudaMalloc((void **)&m->spBuf, o));
+        m->spCap = o;
+    }
+    uint8_t *b = m->spBuf;
+    cudaStream_t st = m->stream;
+    MCK(cudaMemcpyAsync(b + oDesc, frame->desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oMpDesc, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oKeys, frame->keys, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oUr, frame->u_right, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (frame->occupied) MCK(cudaMemcpyAsync(b + oOcc, frame->occupied, (size_t)n, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oMpX, mp_x, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oMpY, mp_y, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oMpR, mp_radius, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(b + oMpL, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemsetAsync(b + oAsg, 0xFF, (size_t)n * 4, st));
+    MCK(cudaMemsetAsync(b + oAsg + (size_t)n * 4, 0, 4, st));
+    k_frame_grid<<<1, 1024, 0, st>>>((const orbx_keypoint *)(b + oKeys), n, frame->min_x, frame->min_y, invW, invH,
+                                     (int *)(b + oCellOf), (int *)(b + oStart), (int *)(b + oItems));
+    MCK(cudaGetLastError());
+    k_project_search<<<(n_mp + 127) / 128, 128, 0, st>>>(
+        (const orbx_keypoint *)(b + oKeys), (const float *)(b + oUr), frame->occupied ? b + oOcc : nullptr, (const uint4 *)(b + oDesc),
+        (const int *)(b + oStart), (const int *)(b + oItems), frame->min_x, frame->min_y, invW, invH, (const uint4 *)(b + oMpDesc),
+        (const float *)(b + oMpX), (const float *)(b + oMpY), (const int *)(b + oMpL), (const float *)(b + oMpR), n_mp, nnratio, th_high,
+        (int *)(b + oMatch), (int *)(b + oAsg), (int *)(b + oAsg + (size_t)n * 4));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(mp_match, b + oMatch, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(assigned, b + oAsg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(nmatches, b + oAsg + (size_t)n * 4, 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
     return ORBX_OK;
 }
 

@@ -38,7 +38,7 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
            "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
@@ -84,6 +84,7 @@ def lib():
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
     L.orbm_distance_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.orbm_search_by_projection.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_int32)]
     L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.orbv_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.orbv_destroy.argtypes = [vp]
@@ -248,6 +249,12 @@ def stereo_match_batch(ex, n_pairs, frame_left0=0, frame_right0=1, frame_step=2,
     return u, d, nl, nm
 
 
+class FrameView(C.Structure):
+    """orbm_frame_view (include/orbx.h)."""
+    _fields_ = [("keys", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p), ("desc", C.c_void_p), ("n", C.c_int32),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float)]
+
+
 class Matcher:
     """Brute-force Hamming kNN-2 with the reference's best / second-best semantics."""
 
@@ -312,6 +319,25 @@ class Matcher:
         dist = np.zeros(len(indices), np.int32)
         self._check(lib().orbm_distance_csr(self._h, _ptr(q), len(q), _ptr(t), len(t), _ptr(offsets), _ptr(indices), _ptr(dist)))
         return dist
+
+    def search_by_projection(self, keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp_y, mp_level, mp_radius,
+                             nnratio=0.8, th_high=100):
+        """ORBmatcher::SearchByProjection(frame, map points, th) with the frame grid (AssignFeaturesToGrid,
+        GetFeaturesInArea) on the device -> (mp_match[n_mp], assigned[n_keypoints], nmatches).  keys: KP_DTYPE records
+        (m_undistortedKeys), bounds = (m_minX, m_minY, m_maxX, m_maxY), mp_radius = r * scaleFactor[level]."""
+        keys = np.ascontiguousarray(keys, KP_DTYPE); uright = np.ascontiguousarray(uright, np.float32)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        mp_x = np.ascontiguousarray(mp_x, np.float32); mp_y = np.ascontiguousarray(mp_y, np.float32)
+        mp_level = np.ascontiguousarray(mp_level, np.int32); mp_radius = np.ascontiguousarray(mp_radius, np.float32)
+        n, nmp = len(keys), len(mp_desc)
+        view = FrameView(keys.ctypes.data if n else None, uright.ctypes.data if n else None, None if occ is None or not n else occ.ctypes.data,
+                         desc.ctypes.data if n else None, n, *[float(v) for v in bounds])
+        match = np.zeros(nmp, np.int32); assigned = np.zeros(max(n, 1), np.int32); nm = C.c_int32()
+        self._check(lib().orbm_search_by_projection(self._h, C.byref(view), _ptr(mp_desc), _ptr(mp_x), _ptr(mp_y), _ptr(mp_level),
+                                                    _ptr(mp_radius), nmp, C.c_float(nnratio), int(th_high), _ptr(match), _ptr(assigned),
+                                                    C.byref(nm)))
+        return match, assigned[:n], nm.value
 
     def measure_popc(self):
         """POPC lane-operations per clock per SM measured on this GPU."""

@@ -115,14 +115,15 @@ static std::shared_ptr<OrbFrame> make_frame(const frameref_cfg *c, const uint8_t
 // with idx % 7 == 3 already carry a map point that has an observation (excluded by :87-89), those with idx % 11 == 5 one
 // without (not excluded).  Handed back: the map points' descriptors and tracking fields, B's descriptors / octaves /
 // mvuRight, the candidate lists the reference's own GetFeaturesInArea returns for every map point (CSR, in its order),
-// the radius r * scaleFactor[level] of :64-67, and the result: assigned[idx] = index of the map point the reference
+// the radius r * scaleFactor[level] of :64-67, B's undistorted key points and image bounds, and the result: assigned[idx] = index of the map point the reference
 // stored in B.m_mapPoints[idx] (-1 none, -2 the pre-assigned ones left in place), return value = its nmatches.
 int frameref_search_by_projection(const frameref_cfg *c, int canonical, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB,
                                   const uint8_t *rightB, int w, int h, float mbf, float mb, float th, float nnratio,
                                   int mp_step, float dx, float dy, int cap, int list_cap,
                                   int *n_mp_out, uint8_t *mp_desc, float *mp_x, float *mp_radius,
                                   int *n_b_out, uint8_t *b_desc, int32_t *b_octave, float *b_uright, int32_t *b_occupied,
-                                  int32_t *offsets, int32_t *indices, int32_t *assigned)
+                                  int32_t *offsets, int32_t *indices, int32_t *assigned,
+                                  orbo_keypoint *b_keys, float *mp_y, int32_t *mp_level, float *bounds)
 {
     std::streambuf *old = std::cout.rdbuf();
     std::ostringstream sink;
@@ -162,8 +163,10 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
                 }
                 memcpy(b_desc + (size_t)idx * 32, B->m_descriptors.ptr(idx), 32);
                 b_octave[idx] = B->m_undistortedKeys[idx].octave;
+                memcpy(&b_keys[idx], &B->m_undistortedKeys[idx], sizeof(orbo_keypoint));
                 b_uright[idx] = B->mvuRight[idx];
             }
+            bounds[0] = OrbFrame::m_minX; bounds[1] = OrbFrame::m_minY; bounds[2] = OrbFrame::m_maxX; bounds[3] = OrbFrame::m_maxY;
             const bool bFactor = std::abs(th - 1.0) < 0.0000000001f;            // :47
             int total = 0;
             offsets[0] = 0;
@@ -174,7 +177,7 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
                 const int level = mps[i]->GetTrackScaleLevel();
                 float r = mps[i]->GTrackViewCos() > 0.998 ? 2.5f : 4.0f;         // RadiusByViewingCos, :126-131
                 if (bFactor) r *= th;                                            // :61-62
-                mp_x[i] = mps[i]->getTrackProjX();
+                mp_x[i] = mps[i]->getTrackProjX(); mp_y[i] = mps[i]->getTrackProjY(); mp_level[i] = level;
                 mp_radius[i] = r * B->m_scaleFactors[level];
                 const std::vector<size_t> v = B->GetFeaturesInArea(mps[i]->getTrackProjX(), mps[i]->getTrackProjY(),
                                                                    r * B->m_scaleFactors[level], level - 1, level);

@@ -955,6 +955,83 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* ORBmatcher::SearchByProjection(frame, map points, th), orbmatcher.cpp:42-124, with the frame side it calls:       */
+/* OrbFrame::AssignFeaturesToGrid / PosInGrid (orbframe.cpp:192-211, :381-393) and GetFeaturesInArea (:308-380).    */
+/* PINNED: the reference's own translation units run the same search in oracle/_ref/libframeref.so                  */
+/* (tests/test_oracle_vs_ref.py, tests/golden/ref_projection.npz).  Floats are combined one operation at a time in  */
+/* the reference's order (this file is built with -ffp-contract=off).                                               */
+/* ------------------------------------------------------------------ */
+#define OG_COLS 64
+#define OG_ROWS 48
+#define OMAX(a, b) ((a) > (b) ? (a) : (b))
+#define OMIN(a, b) ((a) < (b) ? (a) : (b))
+int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, const uint8_t *occupied, const uint8_t *desc, int n,
+                              float min_x, float min_y, float max_x, float max_y,
+                              const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
+                              const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned)
+{
+    const float invW = (float)OG_COLS / (max_x - min_x), invH = (float)OG_ROWS / (max_y - min_y);   /* orbframe.cpp:179-180 */
+    /* AssignFeaturesToGrid: m_grid[ix][iy] lists in key-point order, :202-209 */
+    int *count = calloc(OG_COLS * OG_ROWS + 1, sizeof(int)), *cell = malloc(sizeof(int) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        const int px = (int)round((keys[i].x - min_x) * invW), py = (int)round((keys[i].y - min_y) * invH);   /* :383-384 */
+        cell[i] = (px < 0 || px >= OG_COLS || py < 0 || py >= OG_ROWS) ? -1 : px * OG_ROWS + py;
+        if (cell[i] >= 0) count[cell[i] + 1]++;
+    }
+    for (int c = 0; c < OG_COLS * OG_ROWS; c++) count[c + 1] += count[c];
+    int *fill = malloc(sizeof(int) * OG_COLS * OG_ROWS), *items = malloc(sizeof(int) * (n > 0 ? n : 1));
+    memcpy(fill, count, sizeof(int) * OG_COLS * OG_ROWS);
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) items[fill[cell[i]]++] = i;
+    for (int k = 0; k < n; k++) assigned[k] = -1;
+    int nmatches = 0;
+    for (int i = 0; i < n_mp; i++) {
+        const float x = mp_x[i], y = mp_y[i], r = mp_radius[i];
+        const int minLevel = mp_level[i] - 1, maxLevel = mp_level[i];                  /* orbmatcher.cpp:67-68 */
+        mp_match[i] = -1;
+        const int c0x = OMAX(0, (int)floor((x - min_x - r) * invW));                  /* orbframe.cpp:313-335 */
+        if (c0x >= OG_COLS) continue;
+        const int c1x = OMIN(OG_COLS - 1, (int)ceil((x - min_x + r) * invW));
+        if (c1x < 0) continue;
+        const int c0y = OMAX(0, (int)floor((y - min_y - r) * invH));
+        if (c0y >= OG_ROWS) continue;
+        const int c1y = OMIN(OG_ROWS - 1, (int)ceil((y - min_y + r) * invH));
+        if (c1y < 0) continue;
+        const int checkLevels = (minLevel > 0) || (maxLevel >= 0);
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int ix = c0x; ix <= c1x; ix++)
+            for (int iy = c0y; iy <= c1y; iy++)
+                for (int e = count[ix * OG_ROWS + iy]; e < count[ix * OG_ROWS + iy + 1]; e++) {
+                    const int idx = items[e];
+                    if (checkLevels) {
+                        if (keys[idx].octave < minLevel) continue;
+                        if (maxLevel >= 0 && keys[idx].octave > maxLevel) continue;
+                    }
+                    const float distx = keys[idx].x - x, disty = keys[idx].y - y;
+                    if (!(fabs(distx) < r && fabs(disty) < r)) continue;               /* :370 */
+                    if (occupied && occupied[idx]) continue;                           /* orbmatcher.cpp:87-89 */
+                    if (uright[idx] > 0) {
+                        const float er = (float)fabs(x - uright[idx]);                 /* :93 */
+                        if (er > r) continue;
+                    }
+                    const int dist = orbo_descriptor_distance(mp_desc + (size_t)i * 32, desc + (size_t)idx * 32);
+                    if (dist < bestDist) {
+                        bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = keys[idx].octave; bestIdx = idx;
+                    } else if (dist < bestDist2) {
+                        bestLevel2 = keys[idx].octave; bestDist2 = dist;
+                    }
+                }
+        if (bestDist <= th_high) {                                                     /* :116-123 */
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            mp_match[i] = bestIdx;
+            assigned[bestIdx] = i;
+            nmatches++;
+        }
+    }
+    free(count); free(cell); free(fill); free(items);
+    return nmatches;
+}
+
 /* candidate-list variant: the inner loop of SearchByProjection, orbmatcher.cpp:76-114.  The reference
  * carries the octave of the best and of the second-best candidate (bestLevel, bestLevel2); the index of
  * the second best is returned instead so the caller can look the octave up. */

@@ -126,6 +126,12 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
 /* per-query candidate lists (CSR): inner loop of SearchByProjection, orbmatcher.cpp:76-114 */
 void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *offsets, const int32_t *indices,
                    int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2);
+/* ORBmatcher::SearchByProjection(frame, map points, th) (orbmatcher.cpp:42-124) including the frame's grid
+ * (orbframe.cpp:192-211, :308-393); mp_radius[i] = r * scaleFactor[level] as the caller forms it.  Returns nmatches. */
+int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, const uint8_t *occupied, const uint8_t *desc, int n,
+                              float min_x, float min_y, float max_x, float max_y,
+                              const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
+                              const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned);
 /* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points (CSR lists of rows of desc) */
 void orbo_distinctive(const uint8_t *desc, const int32_t *offsets, const int32_t *indices, int n_points,
                       int32_t *best, int32_t *median);

@@ -111,6 +111,19 @@ int main(int argc, char **argv)
             std::vector<int> offs = {0, 5, 5, 12}, idxs = {0, 1, 2, 3, 4, 7, 7, 8, 9, 10, 11, 12}, best;
             hm2.DistinctiveDescriptors(desc, offs, idxs, best);
             fwrite(best.data(), 4, 3, o);
+            // SearchByProjection adapter: every second key point of the frame projected 1.25 px to the right of itself
+            std::vector<float> uR(n, -1.f), px, py, rad;
+            std::vector<unsigned char> occ(n, 0);
+            std::vector<int> lvl, pm, asg;
+            cv::Mat pd(n / 2, 32, CV_8U);
+            for (int i = 0; i + 1 < n; i += 2) {
+                memcpy(pd.ptr(i / 2), desc.ptr(i), 32);
+                px.push_back(keys[i].pt.x + 1.25f); py.push_back(keys[i].pt.y); lvl.push_back(keys[i].octave);
+                rad.push_back(4.0f * sf[keys[i].octave]);
+                if (i % 10 == 0) occ[i] = 1;
+            }
+            int nm = hm2.SearchByProjection(keys, uR, occ, desc, 0.f, 0.f, (float)w, (float)h, pd, px, py, lvl, rad, 0.8f, 100, pm, asg);
+            fwrite(&nm, 4, 1, o); fwrite(asg.data(), 4, n, o);
         }
         fclose(o);
     } catch (const std::exception &e) {

@@ -92,3 +92,12 @@ def test_adapter_end_to_end(tmp_path, oracle):
     assert nfv == int(kept.sum()) and nb == len(set(ow[kept].tolist())) and abs(bsum - 1.0) < 1e-12
     ob, _ = oracle.distinctive(desc, [0, 5, 5, 12], [0, 1, 2, 3, 4, 7, 7, 8, 9, 10, 11, 12])
     assert best.tolist() == ob.tolist() and best[1] == -1
+    # ---- SearchByProjection adapter
+    nm = struct.unpack_from("<i", b, o)[0]; o += 4
+    asg = np.frombuffer(b, np.int32, n, o); o += 4 * n
+    src = np.arange(0, n - 1, 2)
+    occ = np.zeros(n, np.uint8); occ[src[src % 10 == 0]] = 1
+    om, oa, onm = oracle.search_by_projection(kps, np.full(n, -1, np.float32), occ, desc, (0.0, 0.0, float(w), float(h)), desc[src],
+                                              kps["x"][src] + np.float32(1.25), kps["y"][src], kps["octave"][src],
+                                              np.float32(4.0) * sf[kps["octave"][src]], 0.8, 100)
+    assert nm == onm and nm > 100 and np.array_equal(asg, oa)

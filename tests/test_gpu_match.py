@@ -125,15 +125,23 @@ def test_knn2_csr_full_lists_equal_bruteforce(oracle):
 def test_search_by_projection_vs_reference_fixture():
     """tests/golden/ref_projection.npz holds the inputs and the result of the reference's own ORBmatcher::SearchByProjection
     (src/orbmatcher.cpp:42-124, compiled unmodified).  Both GPU routes reproduce its B.m_mapPoints and nmatches: filtered
-    lists -> orbm_knn2_csr -> acceptance, and all candidates -> orbm_distance_csr -> the loop replayed with its exclusions."""
+    lists -> orbm_knn2_csr -> acceptance; all candidates -> orbm_distance_csr -> the loop replayed with its exclusions; and
+    orbm_search_by_projection, which also builds the frame grid and the candidate lists on the device."""
     import os
     import orbx
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_projection.npz"))
     for c, case in enumerate(g["cases"]):
         ratio = float(case[7])
-        r = {k: g[f"{k}_{c}"] for k in ("mp_desc", "mp_x", "mp_radius", "b_desc", "b_octave", "b_uright", "b_occupied", "offsets", "indices", "assigned")}
+        r = {k: g[f"{k}_{c}"] for k in ("mp_desc", "mp_x", "mp_y", "mp_level", "mp_radius", "b_keys", "b_desc", "b_octave", "b_uright",
+                                        "b_occupied", "bounds", "offsets", "indices", "assigned")}
         ref, nref = r["assigned"], int(g[f"nmatches_{c}"])
         m = orbx.Matcher(max_queries=len(r["mp_desc"]), max_train=len(r["b_desc"]))
+        # third route: the whole function on the device, grid assignment and GetFeaturesInArea included
+        keys = r["b_keys"].view(orbx.KP_DTYPE).reshape(-1)
+        match, asg, nm = m.search_by_projection(keys, r["b_uright"], r["b_occupied"], r["b_desc"], r["bounds"], r["mp_desc"], r["mp_x"],
+                                                r["mp_y"], r["mp_level"], r["mp_radius"], ratio, 100)
+        asg[(asg == -1) & (ref == -2)] = -2
+        assert nm == nref and np.array_equal(asg, ref) and int((match >= 0).sum()) == nref
         off2, ind2 = orbx.filter_projection_candidates(r)
         i1, d1, i2, d2 = m.knn2_csr(r["mp_desc"], r["b_desc"], off2, ind2)
         got, n = orbx.accept_projection_matches(i1, d1, i2, d2, r["b_octave"], ratio)
@@ -209,4 +217,59 @@ def test_distance_csr_and_host_replay_of_search_by_projection(oracle):
     a = run(lambda i, k: int(dist[k]))
     b = run(lambda i, k: oracle.descriptor_distance(q[i], t[indices[k]]))
     assert a == b and len(a) > 50
+    m.close()
+
+
+def _projection_case(rng, n, nmp, w, h, clustered):
+    import orbx
+    keys = np.zeros(n, orbx.KP_DTYPE)
+    if clustered:                                             # many key points in few cells: long cell lists
+        cx, cy = rng.uniform(0, w, 12), rng.uniform(0, h, 12)
+        k = rng.integers(0, 12, n)
+        keys["x"] = (cx[k] + rng.normal(0, 6, n)).astype(np.float32); keys["y"] = (cy[k] + rng.normal(0, 6, n)).astype(np.float32)
+    else:
+        keys["x"] = rng.uniform(-8, w + 8, n).astype(np.float32); keys["y"] = rng.uniform(-8, h + 8, n).astype(np.float32)   # some outside the grid
+    keys["x"][::5] = np.round(keys["x"][::5])                 # integer coordinates: cell boundaries and |dx| == r ties
+    keys["octave"] = rng.integers(0, 8, n)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    uright = np.where(rng.random(n) < 0.6, keys["x"] - rng.uniform(0, 40, n), -1).astype(np.float32)
+    occupied = (rng.random(n) < 0.1).astype(np.uint8)
+    src = rng.integers(0, n, nmp)
+    mp_desc = desc[src].copy()
+    flip = rng.integers(0, 256, (nmp, 6)); on = rng.random((nmp, 6)) < 0.7
+    for j in range(6):
+        mp_desc[np.arange(nmp), flip[:, j] // 8] ^= (on[:, j] * (1 << (flip[:, j] % 8))).astype(np.uint8)
+    mp_x = (keys["x"][src] + rng.uniform(-3, 3, nmp)).astype(np.float32); mp_y = (keys["y"][src] + rng.uniform(-3, 3, nmp)).astype(np.float32)
+    mp_x[::17] = rng.uniform(-30, w + 30, len(mp_x[::17])); mp_y[::19] = rng.uniform(-30, h + 30, len(mp_y[::19]))   # off-image projections
+    mp_level = np.clip(keys["octave"][src] + rng.integers(-1, 2, nmp), 0, 7).astype(np.int32)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    mp_radius = (np.where(rng.random(nmp) < 0.5, np.float32(2.5), np.float32(4.0)).astype(np.float32) * sf[mp_level]).astype(np.float32)
+    mp_radius[::23] = np.float32(300.0)                       # huge windows: clamped cell ranges, many candidates
+    return keys, uright, occupied, desc, (0.0, 0.0, float(w), float(h)), mp_desc, mp_x, mp_y, mp_level, mp_radius
+
+
+@pytest.mark.parametrize("n,nmp,w,h,clustered", [(2000, 1500, 1241, 376, False), (3000, 2500, 640, 480, True), (1, 5, 100, 100, False),
+                                                  (5000, 33, 1920, 1080, False)])
+def test_search_by_projection_vs_oracle(oracle, n, nmp, w, h, clustered):
+    """orbm_search_by_projection against the oracle restatement (itself pinned to the reference's orbmatcher.cpp /
+    orbframe.cpp) on inputs the fixture does not reach: key points outside the grid, cell-boundary coordinates, long cell
+    lists, clamped windows, off-image projections."""
+    import orbx
+    rng = np.random.default_rng(n + nmp)
+    case = _projection_case(rng, n, nmp, w, h, clustered)
+    m = orbx.Matcher(max_queries=16, max_train=16)
+    for ratio, th, occ in ((0.8, 100, True), (0.6, 50, False)):
+        args = list(case)
+        if not occ:
+            args[2] = None
+        gm, ga, gn = m.search_by_projection(*args, nnratio=ratio, th_high=th)
+        om, oa, on = oracle.search_by_projection(*args, nnratio=ratio, th_high=th)
+        assert gn == on and np.array_equal(gm, om) and np.array_equal(ga, oa)
+    if n > 1:
+        assert on > 0
+    # an empty frame is not an error
+    e = m.search_by_projection(case[0][:0], case[1][:0], None, case[3][:0], case[4], *case[5:])
+    assert e[2] == 0 and (e[0] == -1).all()
+    with pytest.raises(orbx.OrbxError):
+        m.search_by_projection(*case[:4], (0.0, 0.0, 0.0, 10.0), *case[5:])
     m.close()

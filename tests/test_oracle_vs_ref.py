@@ -145,6 +145,11 @@ def test_search_by_projection_oracle_equals_reference_sources(oracle, w, h, sa, 
     got[(got == -1) & (ref == -2)] = -2                   # key points that kept the map point they carried before
     assert n == r["nmatches"] and n > 20 and np.array_equal(got, ref)
     assert (ref[r["b_occupied"] == 1] == -2).all()
+    # the whole function restated (grid assignment, GetFeaturesInArea, candidate loop, acceptance) from the key points on
+    match, asg, nm = oracle.search_by_projection(r["b_keys"], r["b_uright"], r["b_occupied"], r["b_desc"], r["bounds"], r["mp_desc"],
+                                                 r["mp_x"], r["mp_y"], r["mp_level"], r["mp_radius"], ratio, 100)
+    asg[(asg == -1) & (ref == -2)] = -2
+    assert nm == r["nmatches"] and np.array_equal(asg, ref) and (match >= 0).sum() == nm
     # the reference's own DescriptorDistance, through its loop, equals the restated one on every candidate it accepted
     hit = np.flatnonzero(ref >= 0)
     assert np.array_equal(np.array([oracle.descriptor_distance(r["mp_desc"][ref[k]], r["b_desc"][k]) for k in hit]), d1[ref[hit]])
