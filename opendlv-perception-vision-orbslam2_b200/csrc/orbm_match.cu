@@ -372,7 +372,7 @@ struct orbm_matcher {
     int *ddCsr = nullptr; size_t ddCsrCap = 0;
     int2 *ddBest = nullptr, *ddHost = nullptr; int ddBestCap = 0;
     // orbm_search_by_projection: one workspace (frame + map points + grid + results), grown on demand
-    uint8_t *spBuf = nullptr; size_t spCap = 0;
+    uint8_t *spBuf = nullptr, *spHost = nullptr; size_t spCap = 0;
     std::string err;
 };
 
@@ -463,6 +463,7 @@ void orbm_destroy(orbm_matcher *m)
     if (m->ddBest) cudaFree(m->ddBest);
     if (m->ddHost) cudaFreeHost(m->ddHost);
     if (m->spBuf) cudaFree(m->spBuf);
+    if (m->spHost) cudaFreeHost(m->spHost);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -695,6 +696,7 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
     MCK(cudaSetDevice(m->device));
     // m_gridElementWidthInverse / HeightInverse, orbframe.cpp:179-180
     const float invW = (float)FG_COLS / (frame->max_x - frame->min_x), invH = (float)FG_ROWS / (frame->max_y - frame->min_y);
+    // workspace layout: [inputs, copied with ONE H2D from a pinned mirror] [device-only grid] [results, ONE D2H]
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t o = 0;
     const size_t oDesc = o;    o += al((size_t)n * 32);
@@ -702,32 +704,38 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
     const size_t oKeys = o;    o += al((size_t)n * sizeof(orbx_keypoint));
     const size_t oUr = o;      o += al((size_t)n * 4);
     const size_t oOcc = o;     o += al((size_t)n);
-    const size_t oCellOf = o;  o += al((size_t)n * 4);
-    const size_t oItems = o;   o += al((size_t)n * 4);
-    const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
     const size_t oMpX = o;     o += al((size_t)n_mp * 4);
     const size_t oMpY = o;     o += al((size_t)n_mp * 4);
     const size_t oMpR = o;     o += al((size_t)n_mp * 4);
     const size_t oMpL = o;     o += al((size_t)n_mp * 4);
+    const size_t inBytes = o;
+    const size_t oCellOf = o;  o += al((size_t)n * 4);
+    const size_t oItems = o;   o += al((size_t)n * 4);
+    const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
+    const size_t oRes = o;
     const size_t oMatch = o;   o += al((size_t)n_mp * 4);
     const size_t oAsg = o;     o += al((size_t)n * 4 + 4);          // assigned[n] | nmatches
+    const size_t resBytes = o - oRes;
     if (o > m->spCap) {
         if (m->spBuf) cudaFree(m->spBuf);
-        m->spBuf = nullptr; m->spCap = 0;
+        if (m->spHost) cudaFreeHost(m->spHost);
+        m->spBuf = nullptr; m->spHost = nullptr; m->spCap = 0;
         MCK(cudaMalloc((void **)&m->spBuf, o));
+        MCK(cudaMallocHost((void **)&m->spHost, o));
         m->spCap = o;
     }
-    uint8_t *b = m->spBuf;
+    uint8_t *b = m->spBuf, *hb = m->spHost;
     cudaStream_t st = m->stream;
-    MCK(cudaMemcpyAsync(b + oDesc, frame->desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oMpDesc, mp_desc, (size_t)n_mp * 32, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oKeys, frame->keys, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oUr, frame->u_right, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    if (frame->occupied) MCK(cudaMemcpyAsync(b + oOcc, frame->occupied, (size_t)n, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oMpX, mp_x, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oMpY, mp_y, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oMpR, mp_radius, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(b + oMpL, mp_level, (size_t)n_mp * 4, cudaMemcpyHostToDevice, st));
+    memcpy(hb + oDesc, frame->desc, (size_t)n * 32);
+    memcpy(hb + oMpDesc, mp_desc, (size_t)n_mp * 32);
+    memcpy(hb + oKeys, frame->keys, (size_t)n * sizeof(orbx_keypoint));
+    memcpy(hb + oUr, frame->u_right, (size_t)n * 4);
+    if (frame->occupied) memcpy(hb + oOcc, frame->occupied, (size_t)n);
+    memcpy(hb + oMpX, mp_x, (size_t)n_mp * 4);
+    memcpy(hb + oMpY, mp_y, (size_t)n_mp * 4);
+    memcpy(hb + oMpR, mp_radius, (size_t)n_mp * 4);
+    memcpy(hb + oMpL, mp_level, (size_t)n_mp * 4);
+    MCK(cudaMemcpyAsync(b, hb, inBytes, cudaMemcpyHostToDevice, st));
     MCK(cudaMemsetAsync(b + oAsg, 0xFF, (size_t)n * 4, st));
     MCK(cudaMemsetAsync(b + oAsg + (size_t)n * 4, 0, 4, st));
     k_frame_grid<<<1, 1024, 0, st>>>((const orbx_keypoint *)(b + oKeys), n, frame->min_x, frame->min_y, invW, invH,
@@ -739,10 +747,11 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
         (const float *)(b + oMpX), (const float *)(b + oMpY), (const int *)(b + oMpL), (const float *)(b + oMpR), n_mp, nnratio, th_high,
         (int *)(b + oMatch), (int *)(b + oAsg), (int *)(b + oAsg + (size_t)n * 4));
     MCK(cudaGetLastError());
-    MCK(cudaMemcpyAsync(mp_match, b + oMatch, (size_t)n_mp * 4, cudaMemcpyDeviceToHost, st));
-    MCK(cudaMemcpyAsync(assigned, b + oAsg, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    MCK(cudaMemcpyAsync(nmatches, b + oAsg + (size_t)n * 4, 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(hb + oRes, b + oRes, resBytes, cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));
+    memcpy(mp_match, hb + oMatch, (size_t)n_mp * 4);
+    memcpy(assigned, hb + oAsg, (size_t)n * 4);
+    memcpy(nmatches, hb + oAsg + (size_t)n * 4, 4);
     return ORBX_OK;
 }
 
