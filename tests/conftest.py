@@ -22,6 +22,9 @@ def pytest_sessionstart(session):
     if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
         env = dict(os.environ, PATH=os.environ.get("PATH", "") + ":/usr/local/cuda/bin")
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "opendlv-perception-vision-orbslam2_b200", "csrc")], env=env)
+    # the reference's own translation units against the header shim, only where the reference tree is mounted
+    if os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libframeref.so")):
+        subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
 
 
 @pytest.fixture(scope="session")
