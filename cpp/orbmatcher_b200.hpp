@@ -127,6 +127,41 @@ class HammingMatcher {
       return nmatches;
   }
 
+  // OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for many windows of one frame at once, with DescriptorDistance of
+  // every feature found -- for the window-based drivers whose acceptance is sequential (SearchForInitialization,
+  // orbmatcher.cpp:411-528; SearchByProjection(CurrentFrame, LastFrame), :1337-1483; Fuse).  Window i: centre (x, y)[i],
+  // half size r[i], levels [minLevel[i], maxLevel[i]] with the reference's meaning of -1.  The features of window i are
+  // indices[offsets[i] .. offsets[i+1]) in the order the reference returns them; dist is filled when queryDescriptors is
+  // not empty (row i against those features).
+  void AreaDistances(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors, float minX, float minY, float maxX,
+                     float maxY, const cv::Mat &queryDescriptors, const std::vector<float> &x, const std::vector<float> &y,
+                     const std::vector<float> &r, const std::vector<int> &minLevel, const std::vector<int> &maxLevel,
+                     std::vector<int> &offsets, std::vector<int> &indices, std::vector<int> &dist)
+  {
+      const int n = (int)keysUn.size(), nq = (int)x.size();
+      offsets.assign(nq + 1, 0); indices.clear(); dist.clear();
+      if (n == 0 || nq == 0) return;
+      orbm_frame_view fv;
+      fv.keys = reinterpret_cast<const orbx_keypoint *>(keysUn.data());
+      fv.u_right = nullptr; fv.occupied = nullptr;
+      fv.desc = descriptors.ptr(0);
+      fv.n = n;
+      fv.min_x = minX; fv.min_y = minY; fv.max_x = maxX; fv.max_y = maxY;
+      const bool withDist = queryDescriptors.rows == nq;
+      int cap = 16 * nq + 1024;
+      for (;;) {
+          indices.assign(cap, 0); dist.assign(withDist ? cap : 0, 0);
+          int32_t total = 0;
+          const int rc = orbm_area_distances(m_, &fv, withDist ? queryDescriptors.ptr(0) : nullptr, x.data(), y.data(), r.data(),
+                                             minLevel.data(), maxLevel.data(), nq, offsets.data(), indices.data(),
+                                             withDist ? dist.data() : nullptr, cap, &total);
+          if (rc == ORBX_ERR_CAPACITY && total > cap) { cap = total; continue; }
+          check(rc);
+          indices.resize(total); if (withDist) dist.resize(total);
+          return;
+      }
+  }
+
   // the reference's acceptance test (orbmatcher.cpp:234-236)
   static bool Accept(int bestDist1, int bestDist2, int th, float nnRatio)
   {

@@ -54,7 +54,7 @@ typedef struct {
  * capacity knobs a device arena needs. */
 typedef struct {
     int nfeatures;        /* ORBextractor.nFeatures   (tracking.cpp:104) */
-    float scale_factor;   /* ORBextractor.scaleFactor (tracking.cpp:105) */
+    float scale_factor;   /* ORBextractor.scaleFactor (tracking.cpp:105); supported range (1, 1.35], ORB-SLAM2 settings use 1.2 */
     int nlevels;          /* ORBextractor.nLevels     (tracking.cpp:106), 1..ORBX_MAX_LEVELS */
     int ini_th_fast;      /* ORBextractor.iniThFAST   (tracking.cpp:107) */
     int min_th_fast;      /* ORBextractor.minThFAST   (tracking.cpp:108); 1..127 */
@@ -214,6 +214,17 @@ typedef struct {
 int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
                               const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
                               int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches);
+/* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows of one frame at once, plus DescriptorDistance of every
+ * feature found -- the building block of the window-based drivers whose acceptance is sequential (SearchForInitialization,
+ * orbmatcher.cpp:411-528: vMatchedDistance; SearchByProjection(CurrentFrame, LastFrame), :1337-1483; Fuse): the host keeps
+ * the projection arithmetic and replays its loop over the lists.  Window i: centre (q_x, q_y)[i], half size q_r[i], levels
+ * [q_min_level[i], q_max_level[i]] with the reference's meaning of -1 (:337, :352-364).  offsets[nq + 1] / indices: the
+ * features of every window in the order the reference returns them; dist[k] = DescriptorDistance(q_desc[i], frame
+ * descriptor indices[k]) when q_desc != NULL.  cap = entries the arrays hold; *n_entries = entries found (ORBX_ERR_CAPACITY
+ * when that is more than cap: call again with larger arrays). */
+int orbm_area_distances(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *q_desc, const float *q_x, const float *q_y,
+                        const float *q_r, const int32_t *q_min_level, const int32_t *q_max_level, int nq, int32_t *offsets,
+                        int32_t *indices, int32_t *dist, int cap, int32_t *n_entries);
 /* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points.
  * Point p observes the rows indices[offsets[p] .. offsets[p+1]) of the descriptor pool desc[n_desc][32] (what the
  * reference gathers from its key frames, :328-337).  Per point: all-pairs DescriptorDistance (:350-358), per row the

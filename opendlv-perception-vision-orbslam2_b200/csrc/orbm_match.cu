@@ -297,6 +297,39 @@ k_frame_grid(const orbx_keypoint *__restrict__ keys, int n, float minX, float mi
     }
 }
 
+// OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for one window: visit(idx, key point) is called for every feature the
+// reference would push into `indices`, in its order (cell columns ix, cells iy inside a column, key-point order in a cell).
+template <class Visit>
+__device__ __forceinline__ void walk_area(const orbx_keypoint *__restrict__ keys, const int *__restrict__ cellStart,
+                                          const int *__restrict__ cellItems, float minX, float minY, float invW, float invH,
+                                          float x, float y, float r, int minLevel, int maxLevel, Visit visit)
+{
+    const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));             // :313
+    if (c0x >= FG_COLS) return;
+    const int c1x = min(FG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));    // :319
+    if (c1x < 0) return;
+    const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));             // :325
+    if (c0y >= FG_ROWS) return;
+    const int c1y = min(FG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));    // :331
+    if (c1y < 0) return;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);                                          // :337
+    for (int ix = c0x; ix <= c1x; ix++) {
+        // the cells (ix, c0y .. c1y) are adjacent in the cell order: one contiguous run of the item list
+        const int e0 = cellStart[ix * FG_ROWS + c0y], e1 = cellStart[ix * FG_ROWS + c1y + 1];
+        for (int e = e0; e < e1; e++) {
+            const int idx = cellItems[e];
+            const orbx_keypoint kp = keys[idx];
+            if (checkLevels) {
+                if (kp.octave < minLevel) continue;                                    // :354
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;                   // :358-363
+            }
+            const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
+            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;                           // :370
+            visit(idx, kp);
+        }
+    }
+}
+
 // One thread per map point: GetFeaturesInArea + the candidate loop + the acceptance, sequentially in the reference's order.
 __global__ void __launch_bounds__(128)
 k_project_search(const orbx_keypoint *__restrict__ keys, const float *__restrict__ uRight, const uint8_t *__restrict__ occupied,
@@ -309,52 +342,96 @@ k_project_search(const orbx_keypoint *__restrict__ keys, const float *__restrict
     if (i >= nMp) return;
     const float x = mpX[i], y = mpY[i], r = mpRadius[i];
     const int level = mpLevel[i];
-    const int minLevel = level - 1, maxLevel = level;                                  // orbmatcher.cpp:67-68
     mpMatch[i] = -1;
-    const int c0x = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, minX), r), invW)));             // orbframe.cpp:313
-    if (c0x >= FG_COLS) return;
-    const int c1x = min(FG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, minX), r), invW)));    // :319
-    if (c1x < 0) return;
-    const int c0y = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, minY), r), invH)));             // :325
-    if (c0y >= FG_ROWS) return;
-    const int c1y = min(FG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, minY), r), invH)));    // :331
-    if (c1y < 0) return;
-    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);                        // :337
     const uint4 qa = mpDesc[2 * i], qb = mpDesc[2 * i + 1];
     int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;   // orbmatcher.cpp:75-79
-    for (int ix = c0x; ix <= c1x; ix++) {
-        // the cells (ix, c0y .. c1y) are adjacent in the cell order: one contiguous run of the item list
-        const int e0 = cellStart[ix * FG_ROWS + c0y], e1 = cellStart[ix * FG_ROWS + c1y + 1];
-        for (int e = e0; e < e1; e++) {
-            const int idx = cellItems[e];
-            const orbx_keypoint kp = keys[idx];
-            if (checkLevels) {
-                if (kp.octave < minLevel) continue;                                    // orbframe.cpp:354
-                if (maxLevel >= 0 && kp.octave > maxLevel) continue;                   // :358-363
-            }
-            const float dx = __fsub_rn(kp.x, x), dy = __fsub_rn(kp.y, y);
-            if (!(fabsf(dx) < r && fabsf(dy) < r)) continue;                           // :370
-            if (occupied && occupied[idx]) continue;                                   // orbmatcher.cpp:87-89
-            const float ur = uRight[idx];
-            if (ur > 0.f && fabsf(__fsub_rn(x, ur)) > r) continue;                     // :91-96
-            const uint4 ta = desc[2 * idx], tb = desc[2 * idx + 1];
-            const int dist = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
-                             __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
-            if (dist < bestDist) {                                                     // :102-114
-                bestDist2 = bestDist; bestDist = dist;
-                bestLevel2 = bestLevel; bestLevel = kp.octave;
-                bestIdx = idx;
-            } else if (dist < bestDist2) {
-                bestLevel2 = kp.octave; bestDist2 = dist;
-            }
+    walk_area(keys, cellStart, cellItems, minX, minY, invW, invH, x, y, r, level - 1, level,   // :64-68
+              [&](int idx, const orbx_keypoint &kp) {
+        if (occupied && occupied[idx]) return;                                         // :87-89
+        const float ur = uRight[idx];
+        if (ur > 0.f && fabsf(__fsub_rn(x, ur)) > r) return;                           // :91-96
+        const int dist = hamming256(qa, qb, desc[2 * idx], desc[2 * idx + 1]);
+        if (dist < bestDist) {                                                         // :102-114
+            bestDist2 = bestDist; bestDist = dist;
+            bestLevel2 = bestLevel; bestLevel = kp.octave;
+            bestIdx = idx;
+        } else if (dist < bestDist2) {
+            bestLevel2 = kp.octave; bestDist2 = dist;
         }
-    }
+    });
     if (bestDist <= thHigh) {                                                          // :116-123
         if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnRatio, (float)bestDist2)) return;
         mpMatch[i] = bestIdx;
         atomicMax(&assigned[bestIdx], i);          // the loop runs in map-point order: the last accepted one stays
         atomicAdd(nMatches, 1);
     }
+}
+
+// GetFeaturesInArea for nq windows: pass 1 counts, one CTA scans the counts into CSR offsets, pass 2 writes the feature
+// indices in the reference's order and, when query descriptors are given, DescriptorDistance of each.
+__global__ void __launch_bounds__(128)
+k_area_count(const orbx_keypoint *__restrict__ keys, const int *__restrict__ cellStart, const int *__restrict__ cellItems,
+             float minX, float minY, float invW, float invH, const float *__restrict__ qX, const float *__restrict__ qY,
+             const float *__restrict__ qR, const int *__restrict__ qMinL, const int *__restrict__ qMaxL, int nq, int *__restrict__ count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int c = 0;
+    walk_area(keys, cellStart, cellItems, minX, minY, invW, invH, qX[i], qY[i], qR[i], qMinL[i], qMaxL[i],
+              [&](int, const orbx_keypoint &) { c++; });
+    count[i] = c;
+}
+
+__global__ void __launch_bounds__(1024) k_area_scan(const int *__restrict__ count, int nq, int *__restrict__ offsets)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < nq; i0 += 1024) {
+        const int i = i0 + tid;
+        const int c = i < nq ? count[i] : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = carry + wsum[warp] + inc - c;
+        if (i < nq) offsets[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[nq] = carry;
+}
+
+__global__ void __launch_bounds__(128)
+k_area_fill(const orbx_keypoint *__restrict__ keys, const uint4 *__restrict__ desc, const int *__restrict__ cellStart,
+            const int *__restrict__ cellItems, float minX, float minY, float invW, float invH, const uint4 *__restrict__ qDesc,
+            const float *__restrict__ qX, const float *__restrict__ qY, const float *__restrict__ qR, const int *__restrict__ qMinL,
+            const int *__restrict__ qMaxL, int nq, const int *__restrict__ offsets, int cap, int *__restrict__ indices,
+            int *__restrict__ dist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    if (offsets[nq] > cap) return;                       // the caller's arrays are too small: nothing is written
+    int o = offsets[i];
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qDesc) { qa = qDesc[2 * i]; qb = qDesc[2 * i + 1]; }
+    walk_area(keys, cellStart, cellItems, minX, minY, invW, invH, qX[i], qY[i], qR[i], qMinL[i], qMaxL[i],
+              [&](int idx, const orbx_keypoint &) {
+        indices[o] = idx;
+        if (qDesc) dist[o] = hamming256(qa, qb, desc[2 * idx], desc[2 * idx + 1]);
+        o++;
+    });
 }
 
 
@@ -752,6 +829,98 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
     memcpy(mp_match, hb + oMatch, (size_t)n_mp * 4);
     memcpy(assigned, hb + oAsg, (size_t)n * 4);
     memcpy(nmatches, hb + oAsg + (size_t)n * 4, 4);
+    return ORBX_OK;
+}
+
+
+int orbm_area_distances(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *q_desc, const float *q_x, const float *q_y,
+                        const float *q_r, const int32_t *q_min_level, const int32_t *q_max_level, int nq, int32_t *offsets,
+                        int32_t *indices, int32_t *dist, int cap, int32_t *n_entries)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!frame || !q_x || !q_y || !q_r || !q_min_level || !q_max_level || !offsets || !n_entries || nq < 1 || cap < 0 ||
+        (cap > 0 && (!indices || (q_desc && !dist))) || frame->n < 0 || (frame->n > 0 && (!frame->keys || !frame->desc)) ||
+        !(frame->max_x > frame->min_x) || !(frame->max_y > frame->min_y))
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    const int n = frame->n;
+    *n_entries = 0;
+    for (int i = 0; i <= nq; i++) offsets[i] = 0;
+    if (n == 0) return ORBX_OK;
+    MCK(cudaSetDevice(m->device));
+    const float invW = (float)FG_COLS / (frame->max_x - frame->min_x), invH = (float)FG_ROWS / (frame->max_y - frame->min_y);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t oDesc = o;    o += al((size_t)n * 32);
+    const size_t oQDesc = o;   o += al((size_t)nq * 32);
+    const size_t oKeys = o;    o += al((size_t)n * sizeof(orbx_keypoint));
+    const size_t oQX = o;      o += al((size_t)nq * 4);
+    const size_t oQY = o;      o += al((size_t)nq * 4);
+    const size_t oQR = o;      o += al((size_t)nq * 4);
+    const size_t oQL0 = o;     o += al((size_t)nq * 4);
+    const size_t oQL1 = o;     o += al((size_t)nq * 4);
+    const size_t inBytes = o;
+    const size_t oCellOf = o;  o += al((size_t)n * 4);
+    const size_t oItems = o;   o += al((size_t)n * 4);
+    const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
+    const size_t oCount = o;   o += al((size_t)nq * 4);
+    const size_t oRes = o;
+    const size_t oOff = o;     o += al((size_t)(nq + 1) * 4);
+    const size_t oInd = o;     o += al((size_t)cap * 4);
+    const size_t oDist = o;    o += al((size_t)cap * 4);
+    if (o > m->spCap) {
+        if (m->spBuf) cudaFree(m->spBuf);
+        if (m->spHost) cudaFreeHost(m->spHost);
+        m->spBuf = nullptr; m->spHost = nullptr; m->spCap = 0;
+        MCK(cudaMalloc((void **)&m->spBuf, o));
+        MCK(cudaMallocHost((void **)&m->spHost, o));
+        m->spCap = o;
+    }
+    uint8_t *b = m->spBuf, *hb = m->spHost;
+    cudaStream_t st = m->stream;
+    memcpy(hb + oDesc, frame->desc, (size_t)n * 32);
+    if (q_desc) memcpy(hb + oQDesc, q_desc, (size_t)nq * 32);
+    memcpy(hb + oKeys, frame->keys, (size_t)n * sizeof(orbx_keypoint));
+    memcpy(hb + oQX, q_x, (size_t)nq * 4);
+    memcpy(hb + oQY, q_y, (size_t)nq * 4);
+    memcpy(hb + oQR, q_r, (size_t)nq * 4);
+    memcpy(hb + oQL0, q_min_level, (size_t)nq * 4);
+    memcpy(hb + oQL1, q_max_level, (size_t)nq * 4);
+    MCK(cudaMemcpyAsync(b, hb, inBytes, cudaMemcpyHostToDevice, st));
+    const orbx_keypoint *dKeys = (const orbx_keypoint *)(b + oKeys);
+    const int *dStart = (const int *)(b + oStart), *dItems = (const int *)(b + oItems);
+    k_frame_grid<<<1, 1024, 0, st>>>(dKeys, n, frame->min_x, frame->min_y, invW, invH, (int *)(b + oCellOf), (int *)(b + oStart),
+                                     (int *)(b + oItems));
+    MCK(cudaGetLastError());
+    const int blocks = (nq + 127) / 128;
+    k_area_count<<<blocks, 128, 0, st>>>(dKeys, dStart, dItems, frame->min_x, frame->min_y, invW, invH, (const float *)(b + oQX),
+                                         (const float *)(b + oQY), (const float *)(b + oQR), (const int *)(b + oQL0),
+                                         (const int *)(b + oQL1), nq, (int *)(b + oCount));
+    MCK(cudaGetLastError());
+    k_area_scan<<<1, 1024, 0, st>>>((const int *)(b + oCount), nq, (int *)(b + oOff));
+    MCK(cudaGetLastError());
+    k_area_fill<<<blocks, 128, 0, st>>>(dKeys, (const uint4 *)(b + oDesc), dStart, dItems, frame->min_x, frame->min_y, invW, invH,
+                                        q_desc ? (const uint4 *)(b + oQDesc) : nullptr, (const float *)(b + oQX),
+                                        (const float *)(b + oQY), (const float *)(b + oQR), (const int *)(b + oQL0),
+                                        (const int *)(b + oQL1), nq, (const int *)(b + oOff), cap, (int *)(b + oInd), (int *)(b + oDist));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(hb + oOff, b + oOff, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    const int total = ((const int *)(hb + oOff))[nq];
+    *n_entries = total;
+    if (total > cap) {
+        char msg[128];
+        snprintf(msg, sizeof msg, "%d features found, the output arrays hold %d", total, cap);
+        return mfail(m, ORBX_ERR_CAPACITY, msg);
+    }
+    memcpy(offsets, hb + oOff, (size_t)(nq + 1) * 4);
+    if (total > 0) {
+        MCK(cudaMemcpyAsync(hb + oInd, b + oInd, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        if (q_desc) MCK(cudaMemcpyAsync(hb + oDist, b + oDist, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaStreamSynchronize(st));
+        memcpy(indices, hb + oInd, (size_t)total * 4);
+        if (q_desc) memcpy(dist, hb + oDist, (size_t)total * 4);
+    }
+    (void)oRes;
     return ORBX_OK;
 }
 

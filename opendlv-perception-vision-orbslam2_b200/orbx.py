@@ -38,7 +38,7 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
            "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
@@ -84,6 +84,7 @@ def lib():
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
     L.orbm_distance_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.orbm_area_distances.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(C.c_int32)]
     L.orbm_search_by_projection.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_int32)]
     L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.orbv_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
@@ -338,6 +339,27 @@ class Matcher:
                                                     _ptr(mp_radius), nmp, C.c_float(nnratio), int(th_high), _ptr(match), _ptr(assigned),
                                                     C.byref(nm)))
         return match, assigned[:n], nm.value
+
+    def area_distances(self, keys, desc, bounds, q_desc, q_x, q_y, q_r, q_min_level, q_max_level, cap=None):
+        """OrbFrame::GetFeaturesInArea for every window of one frame + DescriptorDistance of each feature found ->
+        (offsets[nq + 1], indices, dist or None), the lists in the reference's order."""
+        keys = np.ascontiguousarray(keys, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+        qd = None if q_desc is None else np.ascontiguousarray(q_desc, np.uint8)
+        q_x = np.ascontiguousarray(q_x, np.float32); q_y = np.ascontiguousarray(q_y, np.float32); q_r = np.ascontiguousarray(q_r, np.float32)
+        l0 = np.ascontiguousarray(q_min_level, np.int32); l1 = np.ascontiguousarray(q_max_level, np.int32)
+        n, nq = len(keys), len(q_x)
+        view = FrameView(keys.ctypes.data if n else None, None, None, desc.ctypes.data if n else None, n, *[float(v) for v in bounds])
+        cap = int(cap) if cap is not None else max(1024, 16 * nq)
+        while True:
+            offsets = np.zeros(nq + 1, np.int32); indices = np.zeros(max(cap, 1), np.int32); dist = np.zeros(max(cap, 1), np.int32)
+            total = C.c_int32()
+            rc = lib().orbm_area_distances(self._h, C.byref(view), None if qd is None else _ptr(qd), _ptr(q_x), _ptr(q_y), _ptr(q_r),
+                                           _ptr(l0), _ptr(l1), nq, _ptr(offsets), _ptr(indices), _ptr(dist), cap, C.byref(total))
+            if rc == -3 and total.value > cap:               # ORBX_ERR_CAPACITY: the library says how many entries there are
+                cap = total.value
+                continue
+            self._check(rc)
+            return offsets, indices[:total.value].copy(), (None if qd is None else dist[:total.value].copy())
 
     def measure_popc(self):
         """POPC lane-operations per clock per SM measured on this GPU."""

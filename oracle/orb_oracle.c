@@ -1032,6 +1032,58 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
     return nmatches;
 }
 
+/* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows over the grid of AssignFeaturesToGrid (:192-211);
+ * offsets[nq + 1] / indices in the reference's order, dist = DescriptorDistance to q_desc[i] when q_desc != NULL.
+ * Returns the number of entries (nothing is written beyond cap). */
+int orbo_area_distances(const orbo_keypoint *keys, const uint8_t *desc, int n, float min_x, float min_y, float max_x, float max_y,
+                        const uint8_t *q_desc, const float *q_x, const float *q_y, const float *q_r, const int32_t *q_min_level,
+                        const int32_t *q_max_level, int nq, int32_t *offsets, int32_t *indices, int32_t *dist, int cap)
+{
+    const float invW = (float)OG_COLS / (max_x - min_x), invH = (float)OG_ROWS / (max_y - min_y);
+    int *count = calloc(OG_COLS * OG_ROWS + 1, sizeof(int)), *cell = malloc(sizeof(int) * (n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) {
+        const int px = (int)round((keys[i].x - min_x) * invW), py = (int)round((keys[i].y - min_y) * invH);
+        cell[i] = (px < 0 || px >= OG_COLS || py < 0 || py >= OG_ROWS) ? -1 : px * OG_ROWS + py;
+        if (cell[i] >= 0) count[cell[i] + 1]++;
+    }
+    for (int c = 0; c < OG_COLS * OG_ROWS; c++) count[c + 1] += count[c];
+    int *fill = malloc(sizeof(int) * OG_COLS * OG_ROWS), *items = malloc(sizeof(int) * (n > 0 ? n : 1));
+    memcpy(fill, count, sizeof(int) * OG_COLS * OG_ROWS);
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) items[fill[cell[i]]++] = i;
+    int total = 0;
+    offsets[0] = 0;
+    for (int i = 0; i < nq; i++) {
+        const float x = q_x[i], y = q_y[i], r = q_r[i];
+        const int minLevel = q_min_level[i], maxLevel = q_max_level[i];
+        const int c0x = OMAX(0, (int)floor((x - min_x - r) * invW));
+        const int c1x = OMIN(OG_COLS - 1, (int)ceil((x - min_x + r) * invW));
+        const int c0y = OMAX(0, (int)floor((y - min_y - r) * invH));
+        const int c1y = OMIN(OG_ROWS - 1, (int)ceil((y - min_y + r) * invH));
+        if (!(c0x >= OG_COLS || c1x < 0 || c0y >= OG_ROWS || c1y < 0)) {               /* the four early returns, :314-335 */
+            const int checkLevels = (minLevel > 0) || (maxLevel >= 0);
+            for (int ix = c0x; ix <= c1x; ix++)
+                for (int iy = c0y; iy <= c1y; iy++)
+                    for (int e = count[ix * OG_ROWS + iy]; e < count[ix * OG_ROWS + iy + 1]; e++) {
+                        const int idx = items[e];
+                        if (checkLevels) {
+                            if (keys[idx].octave < minLevel) continue;
+                            if (maxLevel >= 0 && keys[idx].octave > maxLevel) continue;
+                        }
+                        const float distx = keys[idx].x - x, disty = keys[idx].y - y;
+                        if (!(fabs(distx) < r && fabs(disty) < r)) continue;
+                        if (total < cap) {
+                            indices[total] = idx;
+                            if (q_desc) dist[total] = orbo_descriptor_distance(q_desc + (size_t)i * 32, desc + (size_t)idx * 32);
+                        }
+                        total++;
+                    }
+        }
+        offsets[i + 1] = total;
+    }
+    free(count); free(cell); free(fill); free(items);
+    return total;
+}
+
 /* candidate-list variant: the inner loop of SearchByProjection, orbmatcher.cpp:76-114.  The reference
  * carries the octave of the best and of the second-best candidate (bestLevel, bestLevel2); the index of
  * the second best is returned instead so the caller can look the octave up. */

@@ -132,6 +132,10 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
                               float min_x, float min_y, float max_x, float max_y,
                               const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
                               const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned);
+/* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows + DescriptorDistance of every feature found */
+int orbo_area_distances(const orbo_keypoint *keys, const uint8_t *desc, int n, float min_x, float min_y, float max_x, float max_y,
+                        const uint8_t *q_desc, const float *q_x, const float *q_y, const float *q_r, const int32_t *q_min_level,
+                        const int32_t *q_max_level, int nq, int32_t *offsets, int32_t *indices, int32_t *dist, int cap);
 /* OrbMapPoint::ComputeDistinctiveDescriptors (orbmappoint.cpp:314-383), batched over map points (CSR lists of rows of desc) */
 void orbo_distinctive(const uint8_t *desc, const int32_t *offsets, const int32_t *indices, int n_points,
                       int32_t *best, int32_t *median);

@@ -321,6 +321,23 @@ def search_by_projection(keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp
     return match, assigned[:n], nm
 
 
+def area_distances(keys, desc, bounds, q_desc, q_x, q_y, q_r, q_min_level, q_max_level, cap=1 << 20):
+    """OrbFrame::GetFeaturesInArea for every window + DescriptorDistance -> (offsets, indices, dist or None)."""
+    keys = np.ascontiguousarray(keys); desc = np.ascontiguousarray(desc, np.uint8)
+    qd = None if q_desc is None else np.ascontiguousarray(q_desc, np.uint8)
+    q_x = np.ascontiguousarray(q_x, np.float32); q_y = np.ascontiguousarray(q_y, np.float32); q_r = np.ascontiguousarray(q_r, np.float32)
+    l0 = np.ascontiguousarray(q_min_level, np.int32); l1 = np.ascontiguousarray(q_max_level, np.int32)
+    nq = len(q_x)
+    offsets = np.zeros(nq + 1, np.int32); indices = np.zeros(cap, np.int32); dist = np.zeros(cap, np.int32)
+    f = lib().orbo_area_distances
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    total = f(_ptr(keys), _ptr(desc), len(keys), *[float(v) for v in bounds], None if qd is None else _ptr(qd), _ptr(q_x), _ptr(q_y),
+              _ptr(q_r), _ptr(l0), _ptr(l1), nq, _ptr(offsets), _ptr(indices), _ptr(dist), cap)
+    assert total <= cap
+    return offsets, indices[:total].copy(), (None if qd is None else dist[:total].copy())
+
+
 def ref_descriptor_distance(a, b):
     """The reference's own ORBmatcher::DescriptorDistance (orbmatcher.cpp:1662-1677, oracle/_ref/libframeref.so), row by row."""
     R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))

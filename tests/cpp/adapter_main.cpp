@@ -124,6 +124,13 @@ int main(int argc, char **argv)
             }
             int nm = hm2.SearchByProjection(keys, uR, occ, desc, 0.f, 0.f, (float)w, (float)h, pd, px, py, lvl, rad, 0.8f, 100, pm, asg);
             fwrite(&nm, 4, 1, o); fwrite(asg.data(), 4, n, o);
+            // GetFeaturesInArea adapter: the same windows at levels [l-1, l]; lists in the reference's order + distances
+            std::vector<int> l0(lvl), aoff, aind, adist;
+            for (size_t i = 0; i < l0.size(); i++) l0[i] = lvl[i] - 1;
+            hm2.AreaDistances(keys, desc, 0.f, 0.f, (float)w, (float)h, pd, px, py, rad, l0, lvl, aoff, aind, adist);
+            int total = (int)aind.size(), nq = (int)px.size();
+            fwrite(&nq, 4, 1, o); fwrite(&total, 4, 1, o);
+            fwrite(aoff.data(), 4, nq + 1, o); fwrite(aind.data(), 4, total, o); fwrite(adist.data(), 4, total, o);
         }
         fclose(o);
     } catch (const std::exception &e) {

@@ -101,3 +101,11 @@ def test_adapter_end_to_end(tmp_path, oracle):
                                               kps["x"][src] + np.float32(1.25), kps["y"][src], kps["octave"][src],
                                               np.float32(4.0) * sf[kps["octave"][src]], 0.8, 100)
     assert nm == onm and nm > 100 and np.array_equal(asg, oa)
+    # ---- GetFeaturesInArea adapter
+    nq, total = struct.unpack_from("<ii", b, o); o += 8
+    aoff = np.frombuffer(b, np.int32, nq + 1, o); o += 4 * (nq + 1)
+    aind = np.frombuffer(b, np.int32, total, o); o += 4 * total
+    adist = np.frombuffer(b, np.int32, total, o); o += 4 * total
+    oo, oi, od = oracle.area_distances(kps, desc, (0.0, 0.0, float(w), float(h)), desc[src], kps["x"][src] + np.float32(1.25), kps["y"][src],
+                                       np.float32(4.0) * sf[kps["octave"][src]], kps["octave"][src] - 1, kps["octave"][src])
+    assert nq == len(src) and np.array_equal(aoff, oo) and np.array_equal(aind, oi) and np.array_equal(adist, od)

@@ -142,6 +142,12 @@ def test_search_by_projection_vs_reference_fixture():
                                                 r["mp_y"], r["mp_level"], r["mp_radius"], ratio, 100)
         asg[(asg == -1) & (ref == -2)] = -2
         assert nm == nref and np.array_equal(asg, ref) and int((match >= 0).sum()) == nref
+        # GetFeaturesInArea on the device: the reference's own lists, in its order, with every DescriptorDistance
+        off, ind, dist = m.area_distances(keys, r["b_desc"], r["bounds"], r["mp_desc"], r["mp_x"], r["mp_y"], r["mp_radius"],
+                                          r["mp_level"] - 1, r["mp_level"])
+        assert np.array_equal(off, r["offsets"]) and np.array_equal(ind, r["indices"])
+        owner = np.repeat(np.arange(len(off) - 1), np.diff(off))
+        assert np.array_equal(dist, np.unpackbits(r["mp_desc"][owner] ^ r["b_desc"][ind], axis=1).sum(1))
         off2, ind2 = orbx.filter_projection_candidates(r)
         i1, d1, i2, d2 = m.knn2_csr(r["mp_desc"], r["b_desc"], off2, ind2)
         got, n = orbx.accept_projection_matches(i1, d1, i2, d2, r["b_octave"], ratio)
@@ -272,4 +278,24 @@ def test_search_by_projection_vs_oracle(oracle, n, nmp, w, h, clustered):
     assert e[2] == 0 and (e[0] == -1).all()
     with pytest.raises(orbx.OrbxError):
         m.search_by_projection(*case[:4], (0.0, 0.0, 0.0, 10.0), *case[5:])
+    m.close()
+
+
+@pytest.mark.parametrize("n,nq,w,h,clustered", [(2000, 1500, 1241, 376, False), (3000, 2500, 640, 480, True), (7, 3000, 320, 240, False)])
+def test_area_distances_vs_oracle(oracle, n, nq, w, h, clustered):
+    """orbm_area_distances (GetFeaturesInArea + DescriptorDistance for many windows) against the oracle restatement:
+    level windows with the reference's -1 conventions, huge and off-image windows, too-small output arrays."""
+    import orbx
+    rng = np.random.default_rng(7 * n + nq)
+    keys, _, _, desc, bounds, q_desc, q_x, q_y, q_level, q_r = _projection_case(rng, n, nq, w, h, clustered)
+    kind = rng.integers(0, 4, nq)
+    l0 = np.where(kind == 0, -1, np.where(kind == 1, q_level, q_level - 1)).astype(np.int32)   # no check / [l, l] / [l-1, l]
+    l1 = np.where(kind == 0, -1, q_level).astype(np.int32)
+    l0[kind == 3] = 2; l1[kind == 3] = -1                                                       # minLevel only (:337, :352-364)
+    m = orbx.Matcher(max_queries=16, max_train=16)
+    go, gi, gd = m.area_distances(keys, desc, bounds, q_desc, q_x, q_y, q_r, l0, l1, cap=64)      # grows through ORBX_ERR_CAPACITY
+    oo, oi, od = oracle.area_distances(keys, desc, bounds, q_desc, q_x, q_y, q_r, l0, l1, cap=1 << 22)
+    assert np.array_equal(go, oo) and np.array_equal(gi, oi) and np.array_equal(gd, od) and len(oi) > 0
+    go2, gi2, gd2 = m.area_distances(keys, desc, bounds, None, q_x, q_y, q_r, l0, l1)            # lists only
+    assert gd2 is None and np.array_equal(go2, oo) and np.array_equal(gi2, oi)
     m.close()

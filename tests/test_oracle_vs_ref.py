@@ -150,6 +150,9 @@ def test_search_by_projection_oracle_equals_reference_sources(oracle, w, h, sa, 
                                                  r["mp_x"], r["mp_y"], r["mp_level"], r["mp_radius"], ratio, 100)
     asg[(asg == -1) & (ref == -2)] = -2
     assert nm == r["nmatches"] and np.array_equal(asg, ref) and (match >= 0).sum() == nm
+    off, ind, _ = oracle.area_distances(r["b_keys"], r["b_desc"], r["bounds"], None, r["mp_x"], r["mp_y"], r["mp_radius"],
+                                        r["mp_level"] - 1, r["mp_level"])
+    assert np.array_equal(off, r["offsets"]) and np.array_equal(ind, r["indices"])      # the reference's GetFeaturesInArea lists
     # the reference's own DescriptorDistance, through its loop, equals the restated one on every candidate it accepted
     hit = np.flatnonzero(ref >= 0)
     assert np.array_equal(np.array([oracle.descriptor_distance(r["mp_desc"][ref[k]], r["b_desc"][k]) for k in hit]), d1[ref[hit]])
