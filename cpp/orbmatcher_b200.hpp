@@ -127,6 +127,22 @@ class HammingMatcher {
       return nmatches;
   }
 
+  // OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211): fills grid[ix][iy] (the reference's m_grid, 64 x 48 vectors)
+  // with the key-point indices in the order the reference pushes them.
+  template <class Grid>
+  void AssignFeaturesToGrid(const std::vector<cv::KeyPoint> &keysUn, float minX, float minY, float maxX, float maxY, Grid &grid)
+  {
+      const int n = (int)keysUn.size();
+      std::vector<int32_t> start(64 * 48 + 1, 0), items(n > 0 ? n : 1, 0);
+      check(orbm_assign_grid(m_, reinterpret_cast<const orbx_keypoint *>(keysUn.data()), n, minX, minY, maxX, maxY, start.data(), items.data()));
+      for (int ix = 0; ix < 64; ix++)
+          for (int iy = 0; iy < 48; iy++) {
+              auto &cell = grid[ix][iy];
+              cell.clear();
+              for (int e = start[ix * 48 + iy]; e < start[ix * 48 + iy + 1]; e++) cell.push_back(items[e]);
+          }
+  }
+
   // OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for many windows of one frame at once, with DescriptorDistance of
   // every feature found -- for the window-based drivers whose acceptance is sequential (SearchForInitialization,
   // orbmatcher.cpp:411-528; SearchByProjection(CurrentFrame, LastFrame), :1337-1483; Fuse).  Window i: centre (x, y)[i],

@@ -103,6 +103,13 @@ int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const ui
  * orbx_extract_batch).  Waits for `stream` (the stream that call was given; NULL = the handle's). */
 int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
 
+/* OrbFrame::FilterKeyPoints (orbframe.cpp:403-445) on the device-resident results of the last extraction, frames
+ * frame0 .. frame0 + n_frames - 1 (left and right images are filtered with the same box, :406-441): key points with
+ * box[0] < x < box[1] and box[2] < y < box[3] are removed, the others keep their order; key points, descriptors and
+ * counts are compacted in HBM, so orbx_fetch_results / orbx_stereo_match see the filtered frame exactly as
+ * OrbFrame::CommonSetup leaves it (:161-168).  As in the reference nothing happens unless box[1] > 2 (:405).
+ * Enqueued on the handle's stream (ordered after the extraction and before later calls on this handle). */
+int orbx_filter_keypoints(orbx_extractor *h, int frame0, int n_frames, const float box[4]);
 /* OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705), the immediate consumer of both extractors:
  * for every left keypoint the sub-pixel u coordinate of its match in the right image and the depth
  * mbf/disparity, -1 where there is none.  Works on the device-resident results (keypoints, descriptors,
@@ -214,6 +221,12 @@ typedef struct {
 int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
                               const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
                               int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches);
+/* OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211) with PosInGrid (:381-393): the 64 x 48 feature grid of one frame as
+ * CSR.  Cell (ix, iy) = m_grid[ix][iy] is cell_items[cell_start[ix * 48 + iy] .. cell_start[ix * 48 + iy + 1]), key-point
+ * indices in increasing order exactly as the reference pushes them; key points PosInGrid rejects are in no cell.
+ * cell_start has 64 * 48 + 1 entries, cell_items n. */
+int orbm_assign_grid(orbm_matcher *m, const orbx_keypoint *keys, int n, float min_x, float min_y, float max_x, float max_y,
+                     int32_t *cell_start, int32_t *cell_items);
 /* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows of one frame at once, plus DescriptorDistance of every
  * feature found -- the building block of the window-based drivers whose acceptance is sequential (SearchForInitialization,
  * orbmatcher.cpp:411-528: vMatchedDistance; SearchByProjection(CurrentFrame, LastFrame), :1337-1483; Fuse): the host keeps

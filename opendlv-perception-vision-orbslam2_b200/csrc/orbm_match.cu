@@ -924,4 +924,43 @@ int orbm_area_distances(orbm_matcher *m, const orbm_frame_view *frame, const uin
     return ORBX_OK;
 }
 
+
+int orbm_assign_grid(orbm_matcher *m, const orbx_keypoint *keys, int n, float min_x, float min_y, float max_x, float max_y,
+                     int32_t *cell_start, int32_t *cell_items)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!cell_start || n < 0 || (n > 0 && (!keys || !cell_items)) || !(max_x > min_x) || !(max_y > min_y))
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    for (int c = 0; c <= FG_CELLS; c++) cell_start[c] = 0;
+    if (n == 0) return ORBX_OK;
+    MCK(cudaSetDevice(m->device));
+    const float invW = (float)FG_COLS / (max_x - min_x), invH = (float)FG_ROWS / (max_y - min_y);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t oKeys = o;    o += al((size_t)n * sizeof(orbx_keypoint));
+    const size_t oCellOf = o;  o += al((size_t)n * 4);
+    const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
+    const size_t oItems = o;   o += al((size_t)n * 4);
+    if (o > m->spCap) {
+        if (m->spBuf) cudaFree(m->spBuf);
+        if (m->spHost) cudaFreeHost(m->spHost);
+        m->spBuf = nullptr; m->spHost = nullptr; m->spCap = 0;
+        MCK(cudaMalloc((void **)&m->spBuf, o));
+        MCK(cudaMallocHost((void **)&m->spHost, o));
+        m->spCap = o;
+    }
+    uint8_t *b = m->spBuf, *hb = m->spHost;
+    cudaStream_t st = m->stream;
+    memcpy(hb + oKeys, keys, (size_t)n * sizeof(orbx_keypoint));
+    MCK(cudaMemcpyAsync(b + oKeys, hb + oKeys, (size_t)n * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st));
+    k_frame_grid<<<1, 1024, 0, st>>>((const orbx_keypoint *)(b + oKeys), n, min_x, min_y, invW, invH, (int *)(b + oCellOf),
+                                     (int *)(b + oStart), (int *)(b + oItems));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(hb + oStart, b + oStart, (oItems - oStart) + (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    memcpy(cell_start, hb + oStart, (size_t)(FG_CELLS + 1) * 4);
+    memcpy(cell_items, hb + oItems, (size_t)cell_start[FG_CELLS] * 4);
+    return ORBX_OK;
+}
+
 } // extern "C"

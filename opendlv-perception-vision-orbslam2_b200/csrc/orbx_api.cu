@@ -875,6 +875,17 @@ int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int 
 
 // OrbFrame::ComputeStereoMatches (orbframe.cpp:511-705) on the device-resident results of the last
 // extraction of `left` (frame frame_left) and `right` (frame frame_right); the two may be one handle.
+// OrbFrame::FilterKeyPoints on the device-resident results of the last extraction (frames frame0 .. frame0 + n_frames - 1)
+int orbx_filter_keypoints(orbx_extractor *h, int frame0, int n_frames, const float box[4])
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (!box || n_frames < 1 || frame0 < 0 || frame0 + n_frames > h->lastBatch) return fail(h, ORBX_ERR_ARG, "bad argument or no previous extraction");
+    if (!(box[1] > 2.0f)) return ORBX_OK;                 // orbframe.cpp:405: no bounding box configured, nothing is filtered
+    CK(cudaSetDevice(h->cfg.device));
+    CK(launch_filter_keypoints(h->dKps.p, h->dDesc.p, h->dCounts.p, h->L.kpStride, frame0, n_frames, box, h->stream));
+    return ORBX_OK;
+}
+
 int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *right, int frame_right, float mbf, float mb,
                       float *u_right, float *depth, int cap, int *n_left, int *n_matches)
 {

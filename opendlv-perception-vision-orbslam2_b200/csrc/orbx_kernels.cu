@@ -1353,6 +1353,59 @@ void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0,
 //                    (:565-597); then the 11x11 SAD over 11 offsets at the keypoint's level and the
 //                    parabola fit (:600-690), float32 without FMA.
 //   k_stereo_filter: one CTA per pair: sort (SAD, index), median, reject SAD >= 1.5*1.4*median (:693-705).
+
+// ------------------------------------------------------------------------------------------
+// OrbFrame::FilterKeyPoints (orbframe.cpp:403-445): key points strictly inside the bounding box are dropped, the others keep
+// their order; key points and descriptors of one frame are compacted in place.  One CTA per frame walks the frame in chunks
+// of 1024: a chunk is read into registers, a barrier, then written -- every write lands at or left of the chunk's own
+// positions, which have all been read by then.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_filter_keypoints(orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts, int kpStride,
+                   int frame0, float bx0, float bx1, float by0, float by1)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int frame = frame0 + blockIdx.x;
+    orbx_keypoint_pod *k = kps + (size_t)frame * kpStride;
+    uint4 *d = (uint4 *)(desc + (size_t)frame * kpStride * 32);
+    const int n = counts[frame];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        orbx_keypoint_pod kp = {};
+        uint4 da = make_uint4(0, 0, 0, 0), db = da;
+        bool keep = false;
+        if (i < n) {
+            kp = k[i]; da = d[2 * i]; db = d[2 * i + 1];
+            const bool inBounds = kp.x > bx0 && kp.x < bx1 && kp.y > by0 && kp.y < by1;   // :411-412
+            keep = !inBounds;                                                             // :413
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();                       // every entry of the chunk is in registers
+        int base = carry;
+        for (int w = 0; w < warp; w++) base += wsum[w];
+        if (keep) {
+            const int o = base + __popc(bal & ((1u << lane) - 1u));
+            k[o] = kp; d[2 * o] = da; d[2 * o + 1] = db;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = carry; for (int w = 0; w < 32; w++) t += wsum[w]; carry = t; }
+        __syncthreads();
+    }
+    if (tid == 0) counts[frame] = carry;
+}
+
+cudaError_t launch_filter_keypoints(orbx_keypoint_pod *kps, uint8_t *desc, int *counts, int kpStride, int frame0, int nFrames,
+                                    const float box[4], cudaStream_t st)
+{
+    k_filter_keypoints<<<nFrames, 1024, 0, st>>>(kps, desc, counts, kpStride, frame0, box[0], box[1], box[2], box[3]);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int hamming256_dev(const uint4 &qa, const uint4 &qb, const uint4 &a, const uint4 &b)
 {

@@ -24,6 +24,8 @@ cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsign
 void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0, const OrbxLayout &L, const int2 *slots,
                      const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
                      int batch, cudaStream_t st);
+cudaError_t launch_filter_keypoints(orbx_keypoint_pod *kps, uint8_t *desc, int *counts, int kpStride, int frame0, int nFrames,
+                                    const float box[4], cudaStream_t st);
 cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_t *pyrR, const orbx_keypoint_pod *kl,
                           const uint8_t *dl, const int *nl, const orbx_keypoint_pod *kr, const uint8_t *dr, const int *nr,
                           int nPairs, int frameStep, float mbf, float maxD, float *uRight, float *depth, int *sad, int *nMatches, cudaStream_t st);

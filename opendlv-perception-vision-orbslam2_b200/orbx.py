@@ -35,10 +35,10 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_assign_grid", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
            "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
@@ -62,6 +62,7 @@ def lib():
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
     L.orbx_fetch_results.argtypes = [vp, vp, vp, C.c_int, vp, vp]
+    L.orbx_filter_keypoints.argtypes = [vp, C.c_int, C.c_int, fp]
     L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_stereo_match_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
@@ -84,6 +85,7 @@ def lib():
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
     L.orbm_distance_pairs.argtypes = [vp, vp, vp, C.c_int, vp]
     L.orbm_distance_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+    L.orbm_assign_grid.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     L.orbm_area_distances.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(C.c_int32)]
     L.orbm_search_by_projection.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_int32)]
     L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
@@ -193,6 +195,12 @@ class Extractor:
         kps = np.zeros((batch, cap), KP_DTYPE); desc = np.zeros((batch, cap, 32), np.uint8); counts = np.zeros(batch, np.int32)
         self._check(lib().orbx_fetch_results(self._h, C.c_void_p(stream) if stream else None, _ptr(kps), cap, _ptr(desc), _ptr(counts)))
         return kps, desc, counts
+
+    def filter_keypoints(self, box, frame0=0, n_frames=1):
+        """OrbFrame::FilterKeyPoints on the device-resident results of the last extraction: key points strictly inside
+        box = (x0, x1, y0, y1) are removed in HBM (no-op unless box[1] > 2, as in the reference)."""
+        b = (C.c_float * 4)(*[float(v) for v in box])
+        self._check(lib().orbx_filter_keypoints(self._h, frame0, n_frames, b))
 
     def last_launches(self):
         """Kernel launches the last extract call enqueued (all chunks / halves), counted inside the library."""
@@ -339,6 +347,14 @@ class Matcher:
                                                     _ptr(mp_radius), nmp, C.c_float(nnratio), int(th_high), _ptr(match), _ptr(assigned),
                                                     C.byref(nm)))
         return match, assigned[:n], nm.value
+
+    def assign_grid(self, keys, bounds):
+        """OrbFrame::AssignFeaturesToGrid as CSR -> (cell_start[64 * 48 + 1], cell_items); cell = ix * 48 + iy."""
+        keys = np.ascontiguousarray(keys, KP_DTYPE)
+        start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(keys), 1), np.int32)
+        self._check(lib().orbm_assign_grid(self._h, _ptr(keys) if len(keys) else None, len(keys), *[C.c_float(float(v)) for v in bounds],
+                                           _ptr(start), _ptr(items)))
+        return start, items[:start[-1]].copy()
 
     def area_distances(self, keys, desc, bounds, q_desc, q_x, q_y, q_r, q_min_level, q_max_level, cap=None):
         """OrbFrame::GetFeaturesInArea for every window of one frame + DescriptorDistance of each feature found ->

@@ -35,13 +35,15 @@ struct frameref_cfg { int nfeatures; float scale; int nlevels, ini_th, min_th; }
 
 // Left / right: w x h, tightly packed.  cap = rows available in every per-keypoint output.  pyrL / pyrR: nlevels caller
 // buffers receiving the pyramid levels tightly packed (level sizes in lw / lh).  Returns the number of left keypoints
-// (nr_out = right), or -1 when cap is too small.  canonical != 0: heap addresses grow with allocation order (the tie order
+// (nr_out = right), or -1 when cap is too small.  bbox (optional): the bounding box handed to the constructor, applied by the
+// reference's FilterKeyPoints (orbframe.cpp:403-445) before the stereo matching.  grid_start[3073] / grid_items (optional): m_grid.  canonical != 0: heap addresses grow with allocation order (the tie order
 // the oracle and the GPU path implement), otherwise the stock malloc order.
 void orbref_canonical(int on);          // ref_glue.cpp: monotone bump allocator = canonical tie order in DistributeOctTree
 
 int frameref_stereo(const frameref_cfg *c, int canonical, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, float mb,
                     orbo_keypoint *kl, uint8_t *dl, orbo_keypoint *kr, uint8_t *dr, int cap, int *nr_out,
-                    uint8_t **pyrL, uint8_t **pyrR, int *lw, int *lh, float *uRight, float *depth)
+                    uint8_t **pyrL, uint8_t **pyrR, int *lw, int *lh, float *uRight, float *depth,
+                    const float *bbox, int32_t *grid_start, int32_t *grid_items)
 {
     std::streambuf *old = std::cout.rdbuf();
     std::ostringstream sink;
@@ -56,7 +58,8 @@ int frameref_stereo(const frameref_cfg *c, int canonical, const uint8_t *left, c
         for (int i = 0; i < 9; i++) K.ptr<float>(i / 3)[i % 3] = (i % 4 == 0) ? 1.f : 0.f;
         K.at<float>(0, 0) = 700.f; K.at<float>(1, 1) = 700.f; K.at<float>(0, 2) = w * 0.5f; K.at<float>(1, 2) = h * 0.5f;
         for (int i = 0; i < 4; i++) dist.ptr<float>(i)[0] = 0.f;               // no distortion: UndistortKeyPoints returns early
-        std::array<float, 4> box = {0.f, 0.f, 0.f, 0.f};                      // FilterKeyPoints is a no-op (:405)
+        std::array<float, 4> box = {0.f, 0.f, 0.f, 0.f};                      // FilterKeyPoints is a no-op (:405) ...
+        if (bbox) box = {bbox[0], bbox[1], bbox[2], bbox[3]};                  // ... unless the caller gives a bounding box
         OrbFrame::m_initialComputations = true;
         OrbFrame frame(imL, imR, 0.0, exL, exR, std::shared_ptr<OrbVocabulary>(), K, dist, mbf, 35.f * mbf / 700.f, box);
         frame.mb = mb;
@@ -73,6 +76,15 @@ int frameref_stereo(const frameref_cfg *c, int canonical, const uint8_t *left, c
             for (int i = 0; i < nr; i++) {
                 memcpy(&kr[i], &frame.m_keysRight[i], sizeof(orbo_keypoint));
                 memcpy(dr + (size_t)i * 32, frame.m_descriptorsRight.ptr(i), 32);
+            }
+            if (grid_start && grid_items) {              // m_grid as AssignFeaturesToGrid left it, cells in ix * 48 + iy order
+                int t = 0;
+                for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+                    for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+                        grid_start[ix * FRAME_GRID_ROWS + iy] = t;
+                        for (size_t k : frame.m_grid[ix][iy]) grid_items[t++] = (int32_t)k;
+                    }
+                grid_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = t;
             }
             for (int l = 0; l < c->nlevels; l++) {
                 const cv::Mat &a = exL->m_vImagePyramid[l], &b = exR->m_vImagePyramid[l];

@@ -1032,6 +1032,44 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
     return nmatches;
 }
 
+/* OrbFrame::FilterKeyPoints (orbframe.cpp:403-445): key points strictly inside box = {x0, x1, y0, y1} are dropped, the others
+ * keep their order (in place); nothing happens unless box[1] > 2 (:405).  Returns the new count.
+ * PINNED through the reference's own OrbFrame constructor (tests/test_oracle_vs_ref.py, tests/golden/ref_stereo.npz). */
+int orbo_filter_keypoints(orbo_keypoint *keys, uint8_t *desc, int n, const float box[4])
+{
+    if (!(box[1] > 2)) return n;
+    int v = 0;
+    for (int i = 0; i < n; i++) {
+        int inBounds = keys[i].x > box[0] && keys[i].x < box[1];
+        inBounds &= keys[i].y > box[2] && keys[i].y < box[3];
+        if (!inBounds) {
+            keys[v] = keys[i];
+            memmove(desc + (size_t)v * 32, desc + (size_t)i * 32, 32);
+            v++;
+        }
+    }
+    return v;
+}
+
+/* OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211) + PosInGrid (:381-393) as CSR: cell ix * 48 + iy = m_grid[ix][iy]. */
+void orbo_assign_grid(const orbo_keypoint *keys, int n, float min_x, float min_y, float max_x, float max_y,
+                      int32_t *cell_start, int32_t *cell_items)
+{
+    const float invW = (float)OG_COLS / (max_x - min_x), invH = (float)OG_ROWS / (max_y - min_y);
+    int *cell = malloc(sizeof(int) * (n > 0 ? n : 1));
+    for (int c = 0; c <= OG_COLS * OG_ROWS; c++) cell_start[c] = 0;
+    for (int i = 0; i < n; i++) {
+        const int px = (int)round((keys[i].x - min_x) * invW), py = (int)round((keys[i].y - min_y) * invH);
+        cell[i] = (px < 0 || px >= OG_COLS || py < 0 || py >= OG_ROWS) ? -1 : px * OG_ROWS + py;
+        if (cell[i] >= 0) cell_start[cell[i] + 1]++;
+    }
+    for (int c = 0; c < OG_COLS * OG_ROWS; c++) cell_start[c + 1] += cell_start[c];
+    int *fill = malloc(sizeof(int) * OG_COLS * OG_ROWS);
+    memcpy(fill, cell_start, sizeof(int) * OG_COLS * OG_ROWS);
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) cell_items[fill[cell[i]]++] = i;
+    free(cell); free(fill);
+}
+
 /* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows over the grid of AssignFeaturesToGrid (:192-211);
  * offsets[nq + 1] / indices in the reference's order, dist = DescriptorDistance to q_desc[i] when q_desc != NULL.
  * Returns the number of entries (nothing is written beyond cap). */

@@ -132,6 +132,11 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
                               float min_x, float min_y, float max_x, float max_y,
                               const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
                               const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned);
+/* OrbFrame::FilterKeyPoints (orbframe.cpp:403-445), in place; returns the new count */
+int orbo_filter_keypoints(orbo_keypoint *keys, uint8_t *desc, int n, const float box[4]);
+/* OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211) as CSR over 64 x 48 cells (cell = ix * 48 + iy) */
+void orbo_assign_grid(const orbo_keypoint *keys, int n, float min_x, float min_y, float max_x, float max_y,
+                      int32_t *cell_start, int32_t *cell_items);
 /* OrbFrame::GetFeaturesInArea (orbframe.cpp:308-380) for nq windows + DescriptorDistance of every feature found */
 int orbo_area_distances(const orbo_keypoint *keys, const uint8_t *desc, int n, float min_x, float min_y, float max_x, float max_y,
                         const uint8_t *q_desc, const float *q_x, const float *q_y, const float *q_r, const int32_t *q_min_level,

@@ -321,6 +321,26 @@ def search_by_projection(keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp
     return match, assigned[:n], nm
 
 
+def filter_keypoints(keys, desc, box):
+    """OrbFrame::FilterKeyPoints -> (keys, descriptors) without the key points strictly inside box = (x0, x1, y0, y1)."""
+    k = np.ascontiguousarray(keys).copy(); d = np.ascontiguousarray(desc, np.uint8).copy()
+    b = np.ascontiguousarray(box, np.float32)
+    f = lib().orbo_filter_keypoints
+    f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    n = f(_ptr(k), _ptr(d), len(k), _ptr(b))
+    return k[:n], d[:n]
+
+
+def assign_grid(keys, bounds):
+    """OrbFrame::AssignFeaturesToGrid as CSR -> (cell_start[3073], cell_items)."""
+    k = np.ascontiguousarray(keys)
+    start = np.zeros(64 * 48 + 1, np.int32); items = np.zeros(max(len(k), 1), np.int32)
+    f = lib().orbo_assign_grid
+    f.restype = None; f.argtypes = [C.c_void_p, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p]
+    f(_ptr(k), len(k), *[float(v) for v in bounds], _ptr(start), _ptr(items))
+    return start, items[:start[-1]].copy()
+
+
 def area_distances(keys, desc, bounds, q_desc, q_x, q_y, q_r, q_min_level, q_max_level, cap=1 << 20):
     """OrbFrame::GetFeaturesInArea for every window + DescriptorDistance -> (offsets, indices, dist or None)."""
     keys = np.ascontiguousarray(keys); desc = np.ascontiguousarray(desc, np.uint8)
@@ -426,7 +446,7 @@ def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
                                  exL.params.sf, exL.params.inv_sf, kl, dl, kr, dr, mbf, mb)
 
 
-def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1):
+def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1, bbox=None):
     """The reference's own OrbFrame stereo constructor + ComputeStereoMatches (oracle/_ref/libframeref.so: src/orbframe.cpp
     and src/orbextractor.cpp compiled unmodified) -> dict(kl, dl, kr, dr, levelsL, levelsR, uRight, depth)."""
     class Cfg(C.Structure):
@@ -434,7 +454,7 @@ def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nle
     R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
     R.frameref_stereo.restype = C.c_int
     R.frameref_stereo.argtypes = [C.POINTER(Cfg), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float] + \
-        [C.c_void_p] * 4 + [C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 6
+        [C.c_void_p] * 4 + [C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 9
     left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
     h, w = left.shape
     cap = nfeatures + 512
@@ -444,15 +464,18 @@ def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nle
     pl = (C.c_void_p * nlevels)(*[a.ctypes.data for a in lvL]); pr = (C.c_void_p * nlevels)(*[a.ctypes.data for a in lvR])
     lw = (C.c_int * nlevels)(); lh = (C.c_int * nlevels)()
     u = np.zeros(cap, np.float32); d = np.zeros(cap, np.float32)
+    box = None if bbox is None else np.ascontiguousarray(bbox, np.float32)
+    gstart = np.zeros(64 * 48 + 1, np.int32); gitems = np.zeros(cap, np.int32)
     nr = C.c_int()
     n = R.frameref_stereo(C.byref(Cfg(nfeatures, scale_factor, nlevels, ini_th, min_th)), int(canonical), _ptr(left), _ptr(right), w, h,
-                          float(mbf), float(mb), _ptr(kl), _ptr(dl), _ptr(kr), _ptr(dr), cap, C.byref(nr), pl, pr, lw, lh, _ptr(u), _ptr(d))
+                          float(mbf), float(mb), _ptr(kl), _ptr(dl), _ptr(kr), _ptr(dr), cap, C.byref(nr), pl, pr, lw, lh, _ptr(u), _ptr(d),
+                          None if box is None else _ptr(box), _ptr(gstart), _ptr(gitems))
     if n < 0:
         raise RuntimeError("frameref_stereo: more keypoints than the output buffers hold")
     return dict(kl=kl[:n].copy(), dl=dl[:n].copy(), kr=kr[:nr.value].copy(), dr=dr[:nr.value].copy(),
                 levelsL=[lvL[l][:lw[l] * lh[l]].reshape(lh[l], lw[l]).copy() for l in range(nlevels)],
                 levelsR=[lvR[l][:lw[l] * lh[l]].reshape(lh[l], lw[l]).copy() for l in range(nlevels)],
-                uRight=u[:n].copy(), depth=d[:n].copy())
+                uRight=u[:n].copy(), depth=d[:n].copy(), grid_start=gstart, grid_items=gitems[:gstart[-1]].copy())
 
 
 class Extractor:

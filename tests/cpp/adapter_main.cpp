@@ -131,6 +131,24 @@ int main(int argc, char **argv)
             int total = (int)aind.size(), nq = (int)px.size();
             fwrite(&nq, 4, 1, o); fwrite(&total, 4, 1, o);
             fwrite(aoff.data(), 4, nq + 1, o); fwrite(aind.data(), 4, total, o); fwrite(adist.data(), 4, total, o);
+            // AssignFeaturesToGrid adapter into the reference's m_grid shape
+            static std::vector<size_t> grid[64][48];
+            hm2.AssignFeaturesToGrid(keys, 0.f, 0.f, (float)w, (float)h, grid);
+            for (int ix = 0; ix < 64; ix++) for (int iy = 0; iy < 48; iy++) {
+                int c = (int)grid[ix][iy].size(); fwrite(&c, 4, 1, o);
+                for (size_t v : grid[ix][iy]) { int vi = (int)v; fwrite(&vi, 4, 1, o); }
+            }
+        }
+        // FilterKeyPoints adapter: both extractors' device-resident results, then the stereo matching on what is left
+        {
+            OrbExtractor exR(nf, 1.2f, nl, 20, 7);
+            std::vector<cv::KeyPoint> keysR; cv::Mat descR;
+            exR.ExtractFeatures(image, keysR, descR);
+            orbslam_b200::FilterKeyPoints(ex, exR, std::array<float, 4>{0.25f * w, 0.75f * w, 0.25f * h, 0.75f * h});
+            std::vector<float> uR, depth;
+            orbslam_b200::ComputeStereoMatches(ex, exR, 400.0f, 0.0f, uR, depth);
+            int nu = (int)uR.size();
+            fwrite(&nu, 4, 1, o);
         }
         fclose(o);
     } catch (const std::exception &e) {

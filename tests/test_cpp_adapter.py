@@ -109,3 +109,14 @@ def test_adapter_end_to_end(tmp_path, oracle):
     oo, oi, od = oracle.area_distances(kps, desc, (0.0, 0.0, float(w), float(h)), desc[src], kps["x"][src] + np.float32(1.25), kps["y"][src],
                                        np.float32(4.0) * sf[kps["octave"][src]], kps["octave"][src] - 1, kps["octave"][src])
     assert nq == len(src) and np.array_equal(aoff, oo) and np.array_equal(aind, oi) and np.array_equal(adist, od)
+    # ---- AssignFeaturesToGrid adapter (the reference's m_grid, cell by cell)
+    gs, gi = oracle.assign_grid(kps, (0.0, 0.0, float(w), float(h)))
+    for cell in range(64 * 48):
+        cnt = struct.unpack_from("<i", b, o)[0]; o += 4
+        got = np.frombuffer(b, np.int32, cnt, o); o += 4 * cnt
+        assert np.array_equal(got, gi[gs[cell]:gs[cell + 1]]), cell
+    # ---- FilterKeyPoints adapter: what the stereo matcher saw on the left after filtering
+    nu = struct.unpack_from("<i", b, o)[0]; o += 4
+    fk, _ = oracle.filter_keypoints(kps, desc, (0.25 * w, 0.75 * w, 0.25 * h, 0.75 * h))
+    assert nu == len(fk) and 0 < nu < n
+    assert o == len(b)

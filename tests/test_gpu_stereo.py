@@ -35,8 +35,9 @@ def test_two_handles_like_orbframe(oracle, mb):
 
 
 def test_stereo_vs_reference_fixture():
-    """Images from the seed -> GPU extraction (left / right) -> GPU stereo matching, against the key points, descriptors,
-    mvuRight and m_depths the reference's own OrbFrame produced for the same pair (scripts/gen_golden_stereo.py)."""
+    """Images from the seed -> GPU extraction (left / right) -> FilterKeyPoints in HBM -> GPU stereo matching -> grid, against
+    the key points, descriptors, mvuRight / m_depths and m_grid the reference's own OrbFrame produced for the same pair
+    (scripts/gen_golden_stereo.py; the third case carries a bounding box)."""
     import orbx
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_stereo.npz"))
     for c, (w, h, seed, nf, nl, mbf, mb) in enumerate(g["cases"]):
@@ -44,14 +45,44 @@ def test_stereo_vs_reference_fixture():
         left, right = synth.stereo_pair(w, h, seed)
         ex = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h, max_batch=2)
         kps, desc, cnt = ex.extract_batch([left, right])
+        n_before = cnt.copy()
+        ex.filter_keypoints(g["boxes"][c], 0, 2)
+        kps, desc, cnt = ex.fetch_results(2)
         kl, dl, kr, dr = kps[0, :cnt[0]], desc[0, :cnt[0]], kps[1, :cnt[1]], desc[1, :cnt[1]]
         assert kl.tobytes() == g[f"kl_{c}"].tobytes() and kr.tobytes() == g[f"kr_{c}"].tobytes()
         assert np.array_equal(dl, g[f"dl_{c}"]) and np.array_equal(dr, g[f"dr_{c}"])
+        assert (cnt < n_before).all() if g["boxes"][c][1] > 2 else (cnt == n_before).all()
         u, d, nm = orbx.stereo_match(ex, 0, ex, 1, float(mbf), float(mb))
         assert int((u >= 0).sum()) == int((g[f"uRight_{c}"] >= 0).sum()) > 50 and nm >= int((u >= 0).sum())   # nm counts before the median filter
         assert np.array_equal(u.view(np.uint32), g[f"uRight_{c}"].view(np.uint32))
         assert np.array_equal(d.view(np.uint32), g[f"depth_{c}"].view(np.uint32))
-        ex.close()
+        m = orbx.Matcher(16, 16)
+        start, items = m.assign_grid(kl, (0.0, 0.0, float(w), float(h)))
+        assert np.array_equal(start, g[f"grid_start_{c}"]) and np.array_equal(items, g[f"grid_items_{c}"])
+        m.close(); ex.close()
+
+
+def test_filter_keypoints_vs_oracle(oracle):
+    """orbx_filter_keypoints on frames of a larger batch: more than one 1024-entry chunk per frame, a box that removes
+    everything, a box that removes nothing, and the reference's 'box[1] <= 2 means no box' rule."""
+    import orbx
+    w, h, nf = 1241, 376, 3000
+    frames = synth.stereo_batch(4, w, h, 2)
+    ex = orbx.Extractor(nf, 1.2, 8, max_width=w, max_height=h, max_batch=4)
+    k0, d0, c0 = ex.extract_batch(frames)
+    k0, d0, c0 = k0.copy(), d0.copy(), c0.copy()
+    assert c0.min() > 2048
+    boxes = [(300.0, 900.0, 80.0, 300.0), (-10.0, 5000.0, -10.0, 5000.0), (600.0, 601.0, 100.0, 101.0), (0.0, 2.0, 0.0, 1000.0)]
+    for f, box in enumerate(boxes):
+        ex.filter_keypoints(box, f, 1)
+    k1, d1, c1 = ex.fetch_results(4)
+    for f, box in enumerate(boxes):
+        ok, od = oracle.filter_keypoints(k0[f, :c0[f]], d0[f, :c0[f]], box)
+        assert c1[f] == len(ok) and k1[f, :c1[f]].tobytes() == ok.tobytes() and np.array_equal(d1[f, :c1[f]], od)
+    assert c1[1] == 0 and c1[3] == c0[3] and 0 < c1[0] < c0[0]
+    with pytest.raises(orbx.OrbxError):
+        ex.filter_keypoints(boxes[0], 3, 2)
+    ex.close()
 
 
 def test_one_handle_batch_of_pairs(oracle):

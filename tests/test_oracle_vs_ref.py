@@ -123,6 +123,19 @@ def test_stereo_oracle_equals_reference_sources(oracle, w, h, seed, mbf, mb, can
                                            r["kl"], r["dl"], r["kr"], r["dr"], mbf, mb)
     assert (r["uRight"] >= 0).sum() > 50
     assert np.array_equal(u, r["uRight"]) and np.array_equal(d, r["depth"])
+    # AssignFeaturesToGrid: the reference frame's m_grid
+    start, items = oracle.assign_grid(r["kl"], (0.0, 0.0, float(w), float(h)))
+    assert np.array_equal(start, r["grid_start"]) and np.array_equal(items, r["grid_items"])
+    # FilterKeyPoints: the frame built again with a bounding box; the restatement applied to that run's own unfiltered key
+    # points is not observable, so the comparison goes through the monotone heap, where two runs give the same key points
+    if canonical:
+        box = (0.3 * w, 0.7 * w, 0.25 * h, 0.75 * h)
+        rb = oracle.ref_stereo_frame(left, right, mbf, mb, canonical=1, bbox=box)
+        fk, fd = oracle.filter_keypoints(r["kl"], r["dl"], box); fkr, fdr = oracle.filter_keypoints(r["kr"], r["dr"], box)
+        assert 0 < len(fk) < len(r["kl"]) and fk.tobytes() == rb["kl"].tobytes() and np.array_equal(fd, rb["dl"])
+        assert fkr.tobytes() == rb["kr"].tobytes() and np.array_equal(fdr, rb["dr"])
+        u2, d2, _ = oracle.stereo_matches_levels(r["levelsL"], r["levelsR"], ex.params.sf, ex.params.inv_sf, fk, fd, fkr, fdr, mbf, mb)
+        assert np.array_equal(u2, rb["uRight"]) and np.array_equal(d2, rb["depth"])
 
 
 @pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
