@@ -1,0 +1,172 @@
+// orbmatcher_drivers_b200.hpp -- the two per-frame drivers of the reference's ORBmatcher on top of liborbx, for use INSIDE
+// the reference tree (it includes the reference's own orbmatcher.hpp / orbframe.hpp / orbmappoint.hpp):
+//
+//     ORBmatcherB200 matcher(0.9f, true);          // instead of  ORBmatcher matcher(0.9, true);   (src/tracking.cpp)
+//     matcher.SearchByProjection(m_currentFrame, m_lastFrame, th, sensor == MONOCULAR);            // TrackWithMotionModel
+//     matcher.SearchByProjection(m_currentFrame, m_localMapPoints, th);                            // SearchLocalPoints
+//
+// ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides the two overloads:
+//   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
+//     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device);
+//   * SearchByProjection(CurrentFrame, LastFrame, th, mono) src/orbmatcher.cpp:1337-1483 -> the projections are computed on
+//     the host with the reference's own matrix expressions, ONE orbm_area_distances call replaces every
+//     GetFeaturesInArea + DescriptorDistance of the loop, and the loop itself (its exclusion rule depends on the matches
+//     made earlier in the same call, :1412-1414) runs on the host over the returned lists.
+// Results are identical to the base class: tests/test_gpu_drivers.py runs both classes on the same reference frames.
+#ifndef ORBMATCHER_DRIVERS_B200_HPP
+#define ORBMATCHER_DRIVERS_B200_HPP
+
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include <orbmatcher.hpp>
+
+#include "orbmatcher_b200.hpp"
+
+class ORBmatcherB200 : public ORBmatcher {
+ public:
+  ORBmatcherB200(float nnratio = 0.6f, bool checkOri = true, int device = 0)
+      : ORBmatcher(nnratio, checkOri), gpu_(new orbslam_b200::HammingMatcher(16, 16, device)) {}
+
+  // ---- src/orbmatcher.cpp:42-124
+  int SearchByProjection(std::shared_ptr<OrbFrame> &F, const std::vector<std::shared_ptr<OrbMapPoint>> &pMP, const float th = 3)
+  {
+      const bool bFactor = std::abs(th - 1.0) < 0.0000000001f;
+      std::vector<int> who, level, pointMatch, assigned;
+      std::vector<float> x, y, radius;
+      cv::Mat pointDesc((int)pMP.size() > 0 ? (int)pMP.size() : 1, 32, CV_8U);
+      for (size_t i = 0; i < pMP.size(); i++) {
+          const std::shared_ptr<OrbMapPoint> &mp = pMP[i];
+          if (!mp->GetTrackInView() || mp->IsCorrupt()) continue;
+          float r = RadiusByViewingCos(mp->GTrackViewCos());
+          if (bFactor) r *= th;
+          const int lv = mp->GetTrackScaleLevel();
+          mp->GetDescriptor().copyTo(pointDesc.row((int)who.size()));
+          x.push_back(mp->getTrackProjX()); y.push_back(mp->getTrackProjY());
+          level.push_back(lv); radius.push_back(r * F->m_scaleFactors[lv]);
+          who.push_back((int)i);
+      }
+      if (who.empty() || F->N == 0) return 0;
+      std::vector<unsigned char> occupied(F->N, 0);
+      for (int k = 0; k < F->N; k++)
+          occupied[k] = F->m_mapPoints[k] && F->m_mapPoints[k]->GetObservingKeyFrameCount() > 0;
+      const int n = gpu_->SearchByProjection(F->m_undistortedKeys, F->mvuRight, occupied, F->m_descriptors, OrbFrame::m_minX,
+                                             OrbFrame::m_minY, OrbFrame::m_maxX, OrbFrame::m_maxY,
+                                             pointDesc.rowRange(0, (int)who.size()), x, y, level, radius, mfNNratio, TH_HIGH,
+                                             pointMatch, assigned);
+      for (int k = 0; k < F->N; k++)
+          if (assigned[k] >= 0) F->m_mapPoints[k] = pMP[who[assigned[k]]];
+      return n;
+  }
+
+  // ---- src/orbmatcher.cpp:1337-1483
+  int SearchByProjection(std::shared_ptr<OrbFrame> &CurrentFrame, const std::shared_ptr<OrbFrame> &LastFrame, const float th, const bool bMono)
+  {
+      const cv::Mat Rcw = CurrentFrame->mTcw.rowRange(0, 3).colRange(0, 3);
+      const cv::Mat tcw = CurrentFrame->mTcw.rowRange(0, 3).col(3);
+      const cv::Mat twc = -Rcw.t() * tcw;
+      const cv::Mat Rlw = LastFrame->mTcw.rowRange(0, 3).colRange(0, 3);
+      const cv::Mat tlw = LastFrame->mTcw.rowRange(0, 3).col(3);
+      const cv::Mat tlc = Rlw * twc + tlw;
+      const bool bForward = tlc.at<float>(2) > CurrentFrame->mb && !bMono;
+      const bool bBackward = -tlc.at<float>(2) > CurrentFrame->mb && !bMono;
+
+      // pass 1: the windows of all last-frame map points that project into the image (:1360-1399)
+      struct Query { int i; float u, invzc, radius; };
+      std::vector<Query> q;
+      std::vector<float> qx, qy, qr;
+      std::vector<int> l0, l1;
+      for (int i = 0; i < LastFrame->N; i++) {
+          const std::shared_ptr<OrbMapPoint> &pMP = LastFrame->m_mapPoints[i];
+          if (!pMP || LastFrame->m_outliers[i]) continue;
+          const cv::Mat x3Dc = Rcw * pMP->GetWorldPosition() + tcw;
+          const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+          const float invzc = static_cast<float>(1.0 / x3Dc.at<float>(2));
+          if (invzc < 0) continue;
+          const float u = CurrentFrame->fx * xc * invzc + CurrentFrame->cx;
+          const float v = CurrentFrame->fy * yc * invzc + CurrentFrame->cy;
+          if (u < CurrentFrame->m_minX || u > CurrentFrame->m_maxX || v < CurrentFrame->m_minY || v > CurrentFrame->m_maxY) continue;
+          const int oct = LastFrame->m_keys[i].octave;
+          const float radius = th * CurrentFrame->m_scaleFactors[oct];
+          q.push_back(Query{i, u, invzc, radius});
+          qx.push_back(u); qy.push_back(v); qr.push_back(radius);
+          // GetFeaturesInArea(u, v, r, minLevel = -1, maxLevel = -1) defaults, :1392-1397
+          if (bForward) { l0.push_back(oct); l1.push_back(-1); }
+          else if (bBackward) { l0.push_back(0); l1.push_back(oct); }
+          else { l0.push_back(oct - 1); l1.push_back(oct + 1); }
+      }
+      if (q.empty() || CurrentFrame->N == 0) return 0;
+
+      // one device call: every window's feature list in the reference's order + the distance of every feature.  A map point
+      // without a descriptor takes the reference's repair path (:1402-1407) and is skipped; its row stays zero.
+      cv::Mat qd((int)q.size(), 32, CV_8U);
+      std::vector<char> hasDesc(q.size(), 1);
+      for (size_t k = 0; k < q.size(); k++) {
+          cv::Mat d = LastFrame->m_mapPoints[q[k].i]->GetDescriptor();
+          if (d.rows == 0) { hasDesc[k] = 0; for (int b = 0; b < 32; b++) qd.ptr(static_cast<int>(k))[b] = 0; }
+          else d.copyTo(qd.row(static_cast<int>(k)));
+      }
+      std::vector<int> offsets, indices, dist;
+      gpu_->AreaDistances(CurrentFrame->m_undistortedKeys, CurrentFrame->m_descriptors, OrbFrame::m_minX, OrbFrame::m_minY,
+                          OrbFrame::m_maxX, OrbFrame::m_maxY, qd, qx, qy, qr, l0, l1, offsets, indices, dist);
+
+      // pass 2: the reference's loop over the lists (:1399-1450)
+      int nmatches = 0;
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      for (size_t k = 0; k < q.size(); k++) {
+          if (offsets[k] == offsets[k + 1]) continue;
+          const std::shared_ptr<OrbMapPoint> &pMP = LastFrame->m_mapPoints[q[k].i];
+          if (!hasDesc[k]) {
+              // no descriptor when the windows were gathered: the reference repairs the point and skips it (:1402-1407); if an
+              // earlier entry of this very call already repaired it, the reference would match it, so its distances are
+              // evaluated here on the host
+              const cv::Mat d = pMP->GetDescriptor();
+              if (d.rows == 0) { pMP->ComputeDistinctiveDescriptors(); continue; }
+              for (int e = offsets[k]; e < offsets[k + 1]; e++) dist[e] = DescriptorDistance(d, CurrentFrame->m_descriptors.row(indices[e]));
+          }
+          int bestDist = 256, bestIdx2 = -1;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              const int i2 = indices[e];
+              if (CurrentFrame->m_mapPoints[i2] && CurrentFrame->m_mapPoints[i2]->GetObservingKeyFrameCount() > 0) continue;
+              if (CurrentFrame->mvuRight[i2] > 0) {
+                  const float ur = q[k].u - CurrentFrame->mbf * q[k].invzc;
+                  const float er = static_cast<float>(fabs(ur - CurrentFrame->mvuRight[i2]));
+                  if (er > q[k].radius) continue;
+              }
+              if (dist[e] < bestDist) { bestDist = dist[e]; bestIdx2 = i2; }
+          }
+          if (bestDist <= TH_HIGH) {
+              CurrentFrame->m_mapPoints[bestIdx2] = pMP;
+              nmatches++;
+              if (mbCheckOrientation) {
+                  float rot = LastFrame->m_undistortedKeys[q[k].i].angle - CurrentFrame->m_undistortedKeys[bestIdx2].angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back(bestIdx2);
+              }
+          }
+      }
+      if (mbCheckOrientation) {                             // :1454-1474
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++) {
+                  CurrentFrame->m_mapPoints[rotHist[b][j]] = std::shared_ptr<OrbMapPoint>();
+                  nmatches--;
+              }
+          }
+      }
+      return nmatches;
+  }
+
+ private:
+  std::shared_ptr<orbslam_b200::HammingMatcher> gpu_;
+};
+
+#endif

@@ -1,0 +1,124 @@
+// driver_glue.cpp -- TEST INFRASTRUCTURE ONLY (GPU box).
+//
+// Runs the reference's own ORBmatcher drivers and their liborbx-backed replacements (cpp/orbmatcher_drivers_b200.hpp:
+// class ORBmatcherB200, the code a maintainer drops into the reference tree) side by side INSIDE the reference's own data
+// model: reference OrbFrames built by the reference's stereo constructor (frame_glue.cpp), reference OrbMapPoints, the
+// reference's orbmatcher.cpp compiled unmodified.  Both classes get identical copies of the searched frame; what they leave
+// in m_mapPoints and what they return is compared element by element.
+//   part 1  SearchByProjection(frame, map points, th)             src/orbmatcher.cpp:42-124
+//   part 2  SearchByProjection(CurrentFrame, LastFrame, th, mono)  src/orbmatcher.cpp:1337-1483, in its three level modes
+//           (forward / backward / neither, :1357-1358) and with the orientation histogram
+// Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
+#include <orbframe.hpp>
+#include <orbmatcher.hpp>
+
+#include <cstring>
+#include <sstream>
+
+#include "orbmatcher_drivers_b200.hpp"
+
+extern "C" {
+#include "orb_oracle.h"
+struct frameref_cfg { int nfeatures; float scale; int nlevels, ini_th, min_th; };
+std::shared_ptr<OrbFrame> frameref_make_frame(const frameref_cfg *c, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, float mb);
+void orbref_canonical(int on);
+}
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows);
+
+static int count_mismatches(const std::shared_ptr<OrbFrame> &a, const std::shared_ptr<OrbFrame> &b, int *assigned)
+{
+    int bad = 0, set = 0;
+    for (int k = 0; k < a->N; k++) {
+        if (a->m_mapPoints[k] != b->m_mapPoints[k]) bad++;
+        if (a->m_mapPoints[k]) set++;
+    }
+    if (assigned) *assigned = set;
+    return bad;
+}
+
+extern "C" {
+
+// out[0..3]   part 1: nmatches reference, nmatches ORBmatcherB200, differing m_mapPoints entries, entries set
+// out[4+4m..] part 2, mode m = 0 forward, 1 backward, 2 neither: the same four numbers
+int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
+                    int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
+{
+    std::streambuf *old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    std::shared_ptr<OrbKeyFrame> kf = mpref_standin_keyframe(8);
+    int rc = 0;
+    try {
+        std::shared_ptr<OrbFrame> A = frameref_make_frame(c, leftA, rightA, w, h, mbf, mb);
+        std::shared_ptr<OrbFrame> B = frameref_make_frame(c, leftB, rightB, w, h, mbf, mb);
+        cv::Mat I(4, 4, CV_32F);
+        for (int i = 0; i < 16; i++) I.ptr<float>(i / 4)[i % 4] = (i % 5 == 0) ? 1.f : 0.f;
+        A->SetPose(I);
+        cv::Mat one(3, 1, CV_32F);
+        for (int k = 0; k < 3; k++) one.ptr<float>(k)[0] = 1.f;
+
+        // ---------------- part 1
+        {
+            std::vector<std::shared_ptr<OrbMapPoint>> mps;
+            for (int i = 0; i < A->N; i++) {
+                cv::Mat pos(3, 1, CV_32F);
+                pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
+                auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
+                mp->SetTrackInView(i % 13 != 0);                                  // some points are not in view (:51)
+                mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
+                mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
+                mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
+                mp->SetTrackViewCos((i & 1) ? 0.9f : 0.9995f);
+                mps.push_back(mp);
+            }
+            for (int idx = 0; idx < B->N; idx++)
+                if (idx % 7 == 3 || idx % 11 == 5) {
+                    auto held = std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>());
+                    if (idx % 7 == 3) held->AddObservingKeyframe(kf, 1);
+                    B->m_mapPoints[idx] = held;
+                }
+            std::shared_ptr<OrbFrame> B1 = std::make_shared<OrbFrame>(B), B2 = std::make_shared<OrbFrame>(B);
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            out[0] = ref.SearchByProjection(B1, mps, th_points);
+            out[1] = gpu.SearchByProjection(B2, mps, th_points);
+            out[2] = count_mismatches(B1, B2, &out[3]);
+            for (int idx = 0; idx < B->N; idx++) B->m_mapPoints[idx] = std::shared_ptr<OrbMapPoint>();
+        }
+
+        // ---------------- part 2: the last frame's key points become observed map points at their stereo depth (8 m where
+        // the frame has none), every 17th is an outlier; the current frame moves along z (forward / backward) or barely
+        for (int i = 0; i < A->N; i++) {
+            const float z = A->m_depths[i] > 0 ? A->m_depths[i] : 8.0f;
+            cv::Mat pos(3, 1, CV_32F);
+            pos.ptr<float>(0)[0] = (A->m_undistortedKeys[i].pt.x - OrbFrame::cx) * z * OrbFrame::invfx;
+            pos.ptr<float>(1)[0] = (A->m_undistortedKeys[i].pt.y - OrbFrame::cy) * z * OrbFrame::invfy;
+            pos.ptr<float>(2)[0] = z;
+            if (i % 5 == 4) continue;                                             // key points without a map point
+            auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
+            mp->AddObservingKeyframe(kf, 1);                                      // observed: the exclusion of :1412-1414 is live
+            A->m_mapPoints[i] = mp;
+            A->m_outliers[i] = (i % 17 == 0);
+        }
+        const float tz[3] = {-0.9f, 0.9f, 0.05f};
+        for (int m = 0; m < 3; m++) {
+            cv::Mat T = I.clone();
+            T.ptr<float>(0)[3] = 0.02f; T.ptr<float>(1)[3] = -0.01f; T.ptr<float>(2)[3] = tz[m];
+            std::shared_ptr<OrbFrame> C1 = std::make_shared<OrbFrame>(B), C2 = std::make_shared<OrbFrame>(B);
+            C1->SetPose(T); C2->SetPose(T);
+            C1->mb = mb; C2->mb = mb;
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            out[4 + 4 * m] = ref.SearchByProjection(C1, A, th_frames, false);
+            out[5 + 4 * m] = gpu.SearchByProjection(C2, A, th_frames, false);
+            out[6 + 4 * m] = count_mismatches(C1, C2, &out[7 + 4 * m]);
+        }
+    } catch (const std::exception &e) {
+        fprintf(stderr, "driverref_check: %s\n", e.what());
+        rc = -1;
+    }
+    std::cout.rdbuf(old);
+    return rc;
+}
+
+} // extern "C"

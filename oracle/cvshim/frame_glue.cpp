@@ -32,6 +32,7 @@ std::vector<cv::Mat> Orbconverter::toDescriptorVector(const cv::Mat &d)
 extern "C" {
 
 struct frameref_cfg { int nfeatures; float scale; int nlevels, ini_th, min_th; };
+#define FRAMEREF_CFG_DEFINED
 
 // Left / right: w x h, tightly packed.  cap = rows available in every per-keypoint output.  pyrL / pyrR: nlevels caller
 // buffers receiving the pyramid levels tightly packed (level sizes in lw / lh).  Returns the number of left keypoints
@@ -103,7 +104,7 @@ int frameref_stereo(const frameref_cfg *c, int canonical, const uint8_t *left, c
 
 extern "C++" std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows);   // mappoint_glue.cpp
 
-static std::shared_ptr<OrbFrame> make_frame(const frameref_cfg *c, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, float mb)
+std::shared_ptr<OrbFrame> frameref_make_frame(const frameref_cfg *c, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, float mb)
 {
     auto exL = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
     auto exR = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
@@ -144,7 +145,7 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
     if (canonical) orbref_canonical(1);
     int nmatches = -1;
     {
-        std::shared_ptr<OrbFrame> A = make_frame(c, leftA, rightA, w, h, mbf, mb);
+        std::shared_ptr<OrbFrame> A = frameref_make_frame(c, leftA, rightA, w, h, mbf, mb);
         cv::Mat Tcw(4, 4, CV_32F);
         for (int i = 0; i < 16; i++) Tcw.ptr<float>(i / 4)[i % 4] = (i % 5 == 0) ? 1.f : 0.f;
         A->SetPose(Tcw);
@@ -160,7 +161,7 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
             mp->SetTrackViewCos((mps.size() & 1) ? 0.9f : 0.9995f);
             mps.push_back(mp);
         }
-        std::shared_ptr<OrbFrame> B = make_frame(c, leftB, rightB, w, h, mbf, mb);
+        std::shared_ptr<OrbFrame> B = frameref_make_frame(c, leftB, rightB, w, h, mbf, mb);
         const int nb = B->N, nmp = (int)mps.size();
         *n_mp_out = nmp; *n_b_out = nb;
         if (nb <= cap && nmp <= cap) {
