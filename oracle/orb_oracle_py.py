@@ -446,12 +446,13 @@ def stereo_matches(exL, exR, kl, dl, kr, dr, mbf, mb):
                                  exL.params.sf, exL.params.inv_sf, kl, dl, kr, dr, mbf, mb)
 
 
-def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1, bbox=None):
+def ref_stereo_frame(left, right, mbf, mb, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1, bbox=None, lib_name="libframeref.so"):
     """The reference's own OrbFrame stereo constructor + ComputeStereoMatches (oracle/_ref/libframeref.so: src/orbframe.cpp
-    and src/orbextractor.cpp compiled unmodified) -> dict(kl, dl, kr, dr, levelsL, levelsR, uRight, depth)."""
+    and src/orbextractor.cpp compiled unmodified) -> dict(kl, dl, kr, dr, levelsL, levelsR, uRight, depth, grid_*).
+    lib_name="libdropinref.so": the same reference OrbFrame compiled against the drop-in OrbExtractor (GPU box only)."""
     class Cfg(C.Structure):
         _fields_ = [("nfeatures", C.c_int), ("scale", C.c_float), ("nlevels", C.c_int), ("ini", C.c_int), ("min", C.c_int)]
-    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
+    R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", lib_name))
     R.frameref_stereo.restype = C.c_int
     R.frameref_stereo.argtypes = [C.POINTER(Cfg), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float] + \
         [C.c_void_p] * 4 + [C.c_int, C.POINTER(C.c_int)] + [C.c_void_p] * 9
