@@ -7,6 +7,8 @@ INTEGRATION.md section 1 describes.  oracle/_ref/libframeref.so is the same fram
 src/orbextractor.cpp.  Both frames must be identical: key points, descriptors, the pyramids the frame reads through
 m_vImagePyramid, mvuRight, m_depths, m_grid."""
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -22,10 +24,20 @@ REFDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 @pytest.mark.parametrize("w,h,seed,nf,nl,mbf,mb,bbox", [
     (1241, 376, 11, 2000, 8, 386.1, 0.537, None), (640, 360, 5, 1000, 6, 200.0, 0.4, (200.0, 420.0, 100.0, 260.0)),
     (752, 480, 9, 1200, 8, 435.2, 0.11, None)])
-def test_reference_frame_with_drop_in_extractor(oracle, w, h, seed, nf, nl, mbf, mb, bbox):
+def test_reference_frame_with_drop_in_extractor(oracle, tmp_path, w, h, seed, nf, nl, mbf, mb, bbox):
     left, right = synth.stereo_pair(w, h, seed)
     ref = oracle.ref_stereo_frame(left, right, mbf, mb, nfeatures=nf, nlevels=nl, canonical=1, bbox=bbox)
-    got = oracle.ref_stereo_frame(left, right, mbf, mb, nfeatures=nf, nlevels=nl, canonical=0, bbox=bbox, lib_name="libdropinref.so")
+    # the reference frame code + liborbx in one process of their own: a fault there must not take the test session down
+    out = str(tmp_path / "frame.npz")
+    code = (f"import sys, numpy as np; sys.path[:0] = {sys.path[:4]!r}; import orb_oracle_py as O, synth\n"
+            f"l, r = synth.stereo_pair({w}, {h}, {seed})\n"
+            f"g = O.ref_stereo_frame(l, r, {mbf}, {mb}, nfeatures={nf}, nlevels={nl}, canonical=0, bbox={bbox!r}, lib_name='libdropinref.so')\n"
+            f"lv = {{f'L{{i}}': a for i, a in enumerate(g.pop('levelsL'))}}; lv.update({{f'R{{i}}': a for i, a in enumerate(g.pop('levelsR'))}})\n"
+            f"np.savez({out!r}, **g, **lv)\n")
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=300)
+    z = np.load(out)
+    got = {k: z[k] for k in z.files}
+    got["levelsL"] = [z[f"L{i}"] for i in range(nl)]; got["levelsR"] = [z[f"R{i}"] for i in range(nl)]
     assert len(got["kl"]) == len(ref["kl"]) > 100 and got["kl"].tobytes() == ref["kl"].tobytes() and got["kr"].tobytes() == ref["kr"].tobytes()
     assert np.array_equal(got["dl"], ref["dl"]) and np.array_equal(got["dr"], ref["dr"])
     for l in range(nl):
