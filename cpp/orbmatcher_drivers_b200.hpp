@@ -4,15 +4,18 @@
 //     ORBmatcherB200 matcher(0.9f, true);          // instead of  ORBmatcher matcher(0.9, true);   (src/tracking.cpp)
 //     matcher.SearchByProjection(m_currentFrame, m_lastFrame, th, sensor == MONOCULAR);            // TrackWithMotionModel
 //     matcher.SearchByProjection(m_currentFrame, m_localMapPoints, th);                            // SearchLocalPoints
+//     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides the two overloads:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides three drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device);
 //   * SearchByProjection(CurrentFrame, LastFrame, th, mono) src/orbmatcher.cpp:1337-1483 -> the projections are computed on
 //     the host with the reference's own matrix expressions, ONE orbm_area_distances call replaces every
 //     GetFeaturesInArea + DescriptorDistance of the loop, and the loop itself (its exclusion rule depends on the matches
 //     made earlier in the same call, :1412-1414) runs on the host over the returned lists.
+//   * SearchByBoW(keyFrame, frame, matches)                 src/orbmatcher.cpp:164-292   -> one orbm_distance_csr call for all
+//     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host.
 // Results are identical to the base class: tests/test_gpu_drivers.py runs both classes on the same reference frames.
 #ifndef ORBMATCHER_DRIVERS_B200_HPP
 #define ORBMATCHER_DRIVERS_B200_HPP
@@ -28,7 +31,7 @@
 class ORBmatcherB200 : public ORBmatcher {
  public:
   ORBmatcherB200(float nnratio = 0.6f, bool checkOri = true, int device = 0)
-      : ORBmatcher(nnratio, checkOri), gpu_(new orbslam_b200::HammingMatcher(16, 16, device)) {}
+      : ORBmatcher(nnratio, checkOri), device_(device), cap_(8192), gpu_(new orbslam_b200::HammingMatcher(8192, 8192, device)) {}
 
   // ---- src/orbmatcher.cpp:42-124
   int SearchByProjection(std::shared_ptr<OrbFrame> &F, const std::vector<std::shared_ptr<OrbMapPoint>> &pMP, const float th = 3)
@@ -165,7 +168,95 @@ class ORBmatcherB200 : public ORBmatcher {
       return nmatches;
   }
 
+  // ---- src/orbmatcher.cpp:164-292: matching inside the vocabulary nodes the key frame and the frame share.  The node walk
+  // and the map-point tests are the reference's; the DescriptorDistance of every (key-frame feature, frame feature of the
+  // same node) pair comes from ONE orbm_distance_csr call; the best / second-best loop with its exclusion of frame features
+  // matched earlier in the same call (:213-214), the ratio test and the orientation histogram run on the host.
+  int SearchByBoW(std::shared_ptr<OrbKeyFrame> keyFrame, std::shared_ptr<OrbFrame> &F, std::vector<std::shared_ptr<OrbMapPoint>> &vpMapPointMatches)
+  {
+      const std::vector<std::shared_ptr<OrbMapPoint>> mapPointsKeyFrame = keyFrame->GetMapPointMatches();
+      vpMapPointMatches = std::vector<std::shared_ptr<OrbMapPoint>>(F->N, std::shared_ptr<OrbMapPoint>());
+      const OrbFeatureVector &kfVec = keyFrame->m_features;
+
+      // pass 1: the (key-frame feature, node list) pairs in the reference's visiting order
+      struct Query { unsigned int idxKF; const std::vector<unsigned int> *listF; };
+      std::vector<Query> q;
+      std::vector<int> offsets(1, 0), indices;
+      OrbFeatureVector::const_iterator kIt = kfVec.begin(), fIt = F->mFeatVec.begin();
+      const OrbFeatureVector::const_iterator kEnd = kfVec.end(), fEnd = F->mFeatVec.end();
+      while (kIt != kEnd && fIt != fEnd) {
+          if (kIt->first == fIt->first) {
+              for (size_t iKF = 0; iKF < kIt->second.size(); iKF++) {
+                  const unsigned int realIdxKF = kIt->second[iKF];
+                  const std::shared_ptr<OrbMapPoint> &mp = mapPointsKeyFrame[realIdxKF];
+                  if (!mp || mp->IsCorrupt()) continue;
+                  q.push_back(Query{realIdxKF, &fIt->second});
+                  for (size_t iF = 0; iF < fIt->second.size(); iF++) indices.push_back((int)fIt->second[iF]);
+                  offsets.push_back((int)indices.size());
+              }
+              ++kIt; ++fIt;
+          } else if (kIt->first < fIt->first) {
+              kIt = kfVec.lower_bound(fIt->first);
+          } else {
+              fIt = F->mFeatVec.lower_bound(kIt->first);
+          }
+      }
+      if (q.empty() || indices.empty()) return 0;
+      cv::Mat qd((int)q.size(), 32, CV_8U);
+      for (size_t k = 0; k < q.size(); k++) keyFrame->mDescriptors.row((int)q[k].idxKF).copyTo(qd.row((int)k));
+      reserve((int)q.size(), F->N);
+      std::vector<int> dist;
+      gpu_->CandidateDistances(qd, F->m_descriptors, offsets, indices, dist);
+
+      // pass 2: :205-252 over the precomputed distances
+      int nmatches = 0;
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      for (size_t k = 0; k < q.size(); k++) {
+          int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              const int realIdxF = indices[e];
+              if (vpMapPointMatches[realIdxF]) continue;
+              const int d = dist[e];
+              if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = realIdxF; }
+              else if (d < bestDist2) bestDist2 = d;
+          }
+          if (bestDist1 <= TH_LOW && static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+              vpMapPointMatches[bestIdxF] = mapPointsKeyFrame[q[k].idxKF];
+              if (mbCheckOrientation) {
+                  float rot = keyFrame->mvKeysUn[q[k].idxKF].angle - F->m_keys[bestIdxF].angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back(bestIdxF);
+              }
+              nmatches++;
+          }
+      }
+      if (mbCheckOrientation) {
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++) {
+                  vpMapPointMatches[rotHist[b][j]] = std::shared_ptr<OrbMapPoint>();
+                  nmatches--;
+              }
+          }
+      }
+      return nmatches;
+  }
+
  private:
+  // orbm_distance_csr works inside the matcher's query / train capacity: grow it when a frame is larger
+  void reserve(int nq, int nt)
+  {
+      if (nq <= cap_ && nt <= cap_) return;
+      while (cap_ < nq || cap_ < nt) cap_ *= 2;
+      gpu_.reset(new orbslam_b200::HammingMatcher(cap_, cap_, device_));
+  }
+  int device_, cap_;
   std::shared_ptr<orbslam_b200::HammingMatcher> gpu_;
 };
 

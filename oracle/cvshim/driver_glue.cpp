@@ -8,6 +8,7 @@
 //   part 1  SearchByProjection(frame, map points, th)             src/orbmatcher.cpp:42-124
 //   part 2  SearchByProjection(CurrentFrame, LastFrame, th, mono)  src/orbmatcher.cpp:1337-1483, in its three level modes
 //           (forward / backward / neither, :1357-1358) and with the orientation histogram
+//   part 3  SearchByBoW(keyFrame, frame, matches)                  src/orbmatcher.cpp:164-292
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
@@ -24,6 +25,9 @@ std::shared_ptr<OrbFrame> frameref_make_frame(const frameref_cfg *c, const uint8
 void orbref_canonical(int on);
 }
 std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows);
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors,
+                                                         const std::vector<std::shared_ptr<OrbMapPoint>> &mapPoints);
+void mpref_standin_clear();
 
 static int count_mismatches(const std::shared_ptr<OrbFrame> &a, const std::shared_ptr<OrbFrame> &b, int *assigned)
 {
@@ -40,6 +44,7 @@ extern "C" {
 
 // out[0..3]   part 1: nmatches reference, nmatches ORBmatcherB200, differing m_mapPoints entries, entries set
 // out[4+4m..] part 2, mode m = 0 forward, 1 backward, 2 neither: the same four numbers
+// out[16..19] part 3: SearchByBoW(key frame, frame): the same four numbers
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
 {
@@ -112,6 +117,29 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             out[4 + 4 * m] = ref.SearchByProjection(C1, A, th_frames, false);
             out[5 + 4 * m] = gpu.SearchByProjection(C2, A, th_frames, false);
             out[6 + 4 * m] = count_mismatches(C1, C2, &out[7 + 4 * m]);
+        }
+
+        // ---------------- part 3: SearchByBoW(key frame, frame).  The key frame carries frame A's key points, descriptors and
+        // (for four key points out of five) observed map points; "vocabulary nodes" are a function of the descriptor
+        // (its first byte's low six bits), so equal descriptors of A and B share a node as under a real vocabulary.
+        {
+            std::vector<std::shared_ptr<OrbMapPoint>> kfPoints(A->m_mapPoints);
+            std::shared_ptr<OrbKeyFrame> KF = mpref_standin_keyframe_with(A->m_undistortedKeys, A->m_descriptors, kfPoints);
+            for (int i = 0; i < A->N; i++) KF->m_features.addFeature(A->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            std::shared_ptr<OrbFrame> D1 = std::make_shared<OrbFrame>(B), D2 = std::make_shared<OrbFrame>(B);
+            for (int i = 0; i < B->N; i++) {
+                D1->mFeatVec.addFeature(B->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+                D2->mFeatVec.addFeature(B->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            }
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            std::vector<std::shared_ptr<OrbMapPoint>> m1, m2;
+            out[16] = ref.SearchByBoW(KF, D1, m1);
+            out[17] = gpu.SearchByBoW(KF, D2, m2);
+            int bad = (m1.size() != m2.size()), set = 0;
+            for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
+            out[18] = bad; out[19] = set;
+            mpref_standin_clear();
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "driverref_check: %s\n", e.what());

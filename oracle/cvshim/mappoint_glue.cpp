@@ -25,6 +25,9 @@
 static cv::Mat g_pool;                 // row 0 unused: AddObservingKeyframe ignores keypoint index 0 (orbmappoint.cpp:171)
 static std::vector<float> g_uright;
 static bool g_bad = false;
+// data of the stand-in key frame for ORBmatcher::SearchByBoW (libframeref / libdriverref only)
+static std::vector<cv::KeyPoint> g_keysun;
+static std::vector<std::shared_ptr<OrbMapPoint>> g_kf_mappoints;
 
 long unsigned int OrbKeyFrame::nNextId = 0;
 
@@ -33,7 +36,7 @@ OrbKeyFrame::OrbKeyFrame(std::shared_ptr<OrbFrame>, std::shared_ptr<OrbMap> map,
       mnTrackReferenceForFrame(0), mnFuseTargetForKF(0), mnBALocalForKF(0), mnBAFixedForKF(0), m_loopQuery(0), m_loopWords(0),
       mnRelocQuery(0), mnRelocWords(0), mnBAGlobalForKF(0),
       fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), N(g_pool.rows),
-      mvKeys(), mvKeysUn(), mvuRight(g_uright), mvDepth(), mDescriptors(g_pool), m_bagOfWords(), m_features(),
+      mvKeys(), mvKeysUn(g_keysun), mvuRight(g_uright), mvDepth(), mDescriptors(g_pool), m_bagOfWords(), m_features(),
       mnScaleLevels(0), mfScaleFactor(0), mfLogScaleFactor(0), mvScaleFactors(), mvLevelSigma2(), mvInvLevelSigma2(),
       mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mK(),
       m_mapPoints(), m_keyFrameDatabase(), m_orbVocabulary(), m_isFirstConnection(true), m_parent(),
@@ -54,7 +57,7 @@ std::shared_ptr<OrbMapPoint> OrbKeyFrame::GetMapPoint(const size_t &) { return s
 cv::Mat OrbKeyFrame::GetRotation() { return cv::Mat(); }
 cv::Mat OrbKeyFrame::GetTranslation() { return cv::Mat(); }
 std::set<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPoints() { return std::set<std::shared_ptr<OrbMapPoint>>(); }
-std::vector<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPointMatches() { return std::vector<std::shared_ptr<OrbMapPoint>>(); }
+std::vector<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPointMatches() { return g_kf_mappoints; }
 std::vector<size_t> OrbKeyFrame::GetFeaturesInArea(const float &, const float &, const float &) const { return std::vector<size_t>(); }
 bool OrbKeyFrame::IsInImage(const float &, const float &) const { return false; }
 // a stand-in key frame with `rows` key points (no stereo coordinate), for map points that need an observation
@@ -65,6 +68,21 @@ std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows)
     g_bad = false;
     return std::make_shared<OrbKeyFrame>(std::shared_ptr<OrbFrame>(), std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
 }
+// a stand-in key frame carrying key points, descriptors and map points (what SearchByBoW reads, orbmatcher.cpp:167-205);
+// GetMapPointMatches() hands out the map points registered here until the next call
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors,
+                                                         const std::vector<std::shared_ptr<OrbMapPoint>> &mapPoints)
+{
+    descriptors.copyTo(g_pool);
+    g_uright.assign((size_t)descriptors.rows, -1.0f);
+    g_keysun = keysUn;
+    g_kf_mappoints = mapPoints;
+    g_bad = false;
+    std::shared_ptr<OrbKeyFrame> kf = std::make_shared<OrbKeyFrame>(std::shared_ptr<OrbFrame>(), std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+    g_keysun.clear();
+    return kf;
+}
+void mpref_standin_clear() { g_kf_mappoints.clear(); g_pool = cv::Mat(); }
 #else
 int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return OrbDescriptor::distance(a, b); }
 #endif
