@@ -138,6 +138,12 @@ int failCuda(orbx_extractor *h, cudaError_t e, const char *where)
         if (e_ != cudaSuccess) return failCuda(h, e_, #call);         \
     } while (0)
 
+#define CKM(call, what)                                               \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return failCuda(h, e_, what);          \
+    } while (0)
+
 // constructor tables, orbextractor.cpp:492-547
 void buildTables(orbx_extractor *h)
 {
@@ -458,10 +464,14 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     CK(cudaStreamWaitEvent(ln.side, ln.evFork, 0));
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, ln.side));
     CK(cudaEventRecord(ln.evFast0, ln.side));
-    for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
+    for (int l = 1; l < L.nlevels; l++) {
+        launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
+        CKM(cudaGetLastError(), "k_resize launch");
+    }
     CK(cudaEventRecord(ln.evPyr, st));
     CK(cudaStreamWaitEvent(ln.side, ln.evPyr, 0));
     launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
+    CKM(cudaGetLastError(), "k_blur launch");
     CK(cudaEventRecord(ln.evJoin, ln.side));
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
@@ -469,7 +479,7 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
     launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, f0, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
-    CK(cudaGetLastError());
+    CKM(cudaGetLastError(), "k_describe launch");
     // level-0 copy (by the caller of this function) + resize chain + FAST (level 0 | upper levels) + blur + octree + describe
     h->lastLaunches += 1 + (L.nlevels - 1) + (segs0 > 0) + (L.totalSegs - segs0 > 0) + 1 + 1 + 1;
     return ORBX_OK;
@@ -504,7 +514,7 @@ int chunkGraph(orbx_extractor *h, int f0, int nf, int li, size_t frameBytes, int
     const int before = h->lastLaunches;
     CK(cudaStreamBeginCapture(ln.main, cudaStreamCaptureModeRelaxed));
     launch_copy_level0(h->dIn.p + (size_t)f0 * frameBytes, frameBytes, (size_t)width, h->dPyr.p + (size_t)f0 * L.slab, L, nf, ln.main);
-    int rc = enqueuePipeline(h, f0, nf, ln.main, ln);
+    int rc = cudaGetLastError() == cudaSuccess ? enqueuePipeline(h, f0, nf, ln.main, ln) : fail(h, ORBX_ERR_CUDA, "k_copy_level0 launch failed");
     cudaError_t e = cudaStreamEndCapture(ln.main, &graph);
     if (rc != ORBX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return failCuda(h, e, "cudaStreamEndCapture");

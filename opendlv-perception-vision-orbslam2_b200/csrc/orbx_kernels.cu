@@ -755,13 +755,16 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 {
     if (segCount <= 0) return cudaSuccess;
     const size_t smem = fast_smem_bytes(winRows, listCap);
-    if (smem > 48 * 1024) { // opt in per call: the attribute is per device and this is a cheap host-side set
+    // opt in per call (the attribute is per device and this is a cheap host-side set).  The 48 KB default limit covers static +
+    // dynamic shared memory together, so the opt-in starts well below it: a dynamic size just under 48 KB plus the kernel's
+    // few hundred static bytes is an invalid launch otherwise.
+    if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_fast_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(segCount, batch);
     k_fast_segs<<<grid, FS_T, smem, st>>>(maps, f0, L, segs + segBegin, cnt, best, dbg, dbgCount, dbgCap, winRows, listCap);
-    return cudaSuccess;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1085,13 +1088,16 @@ cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsign
                           int *lvlCount, int maxRows, int maxNodes, int batch, cudaStream_t st)
 {
     const size_t smem = octree_smem_bytes(maxRows, maxNodes);
-    if (smem > 48 * 1024) { // opt in per call: the attribute is per device and this is a cheap host-side set
+    // opt in per call (the attribute is per device and this is a cheap host-side set).  The 48 KB default limit covers static +
+    // dynamic shared memory together, so the opt-in starts well below it: a dynamic size just under 48 KB plus the kernel's
+    // few hundred static bytes is an invalid launch otherwise.
+    if (smem > 32 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(L.nlevels, batch);
     k_octree<<<grid, OCT_T, smem, st>>>(L, cnt, best, slots, lvlCount, maxRows, maxNodes);
-    return cudaSuccess;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -50,6 +50,7 @@ for case in range(n_cases):
         if not ok: bad += 1
         else: print(desc_s, "-> ok", int(cnt.sum()))
     except orbx.OrbxError as e:
+        bad += 1                                  # a configuration orbx_create accepted must run
         print(desc_s, "-> error:", str(e)[:100])
     except Exception:
         bad += 1; traceback.print_exc()

@@ -215,6 +215,24 @@ def test_odd_sizes(oracle, w, h, nf, nl):
     ex.close()
 
 
+@pytest.mark.parametrize("w,h,nf,nl,sf,ini,mn,batch", [(556, 514, 3662, 7, 1.25, 27, 2, 4), (2088, 522, 898, 5, 1.25, 18, 10, 2)])
+def test_dynamic_shared_memory_just_under_48k(oracle, w, h, nf, nl, sf, ini, mn, batch):
+    """Geometries whose FAST kernel needs 48 992 / 49 152 bytes of dynamic shared memory: together with the kernel's static
+    shared memory that is over the 48 KB default, so the launch needs the opt-in although the dynamic part alone does not
+    (found by scripts/probe/soak.py)."""
+    import orbx
+    imgs = [synth.scene_s1(w, h, 5 + i) for i in range(batch)]
+    ex = orbx.Extractor(nf, sf, nl, ini, mn, max_width=w, max_height=h, max_batch=batch)
+    kps, desc, cnt = ex.extract_batch(imgs)
+    oex = oracle.Extractor(nf, sf, nl, ini, mn)
+    for f in range(batch):
+        ok, od = oex.extract(imgs[f])
+        assert cnt[f] == len(ok) and kps[f, :cnt[f]].tobytes() == ok.tobytes() and np.array_equal(desc[f, :cnt[f]], od)
+    k1, d1 = ex.extract(imgs[0])
+    assert k1.tobytes() == kps[0, :cnt[0]].tobytes()
+    ex.close()
+
+
 def test_chunked_host_path_replays_graphs(oracle):
     """20 frames: three chunks over three lanes, each a captured CUDA graph; the second call replays the graphs on
     different frames.  Every frame must equal the single-frame result, two of them are checked against the oracle."""
