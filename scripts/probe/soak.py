@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Randomised soak of the extractor against the oracle (not part of the test suite): random frame sizes, feature counts,
 level counts, scale factors, thresholds, batch sizes and scene kinds; every frame must be bit-identical.
-usage: soak.py [n_cases] [seed]"""
+usage: soak.py [n_cases] [seed] [big]"""
 import os, sys, time, traceback
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,12 +14,13 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 bad = 0
 t00 = time.time()
 for case in range(n_cases):
-    w = int(rng.integers(160, 2100)); h = int(rng.integers(120, min(w, 1300)))
+    big = len(sys.argv) > 3 and sys.argv[3] == "big"
+    w = int(rng.integers(160, 4100 if big else 2100)); h = int(rng.integers(120, min(w, 2200 if big else 1300)))
     if w >= 5 * h:
         h = w // 4
-    nl = int(rng.integers(1, 9)); sf = float(rng.choice([1.1, 1.15, 1.2, 1.25, 1.3, 1.4]))
-    nf = int(rng.integers(50, 4000)); ini = int(rng.integers(8, 60)); mn = int(rng.integers(1, ini))
-    batch = int(rng.integers(1, 5))
+    nl = int(rng.integers(1, 13 if big else 9)); sf = float(rng.choice([1.1, 1.15, 1.2, 1.25, 1.3, 1.4]))
+    nf = int(rng.integers(50, 8000 if big else 4000)); ini = int(rng.integers(8, 60)); mn = int(rng.integers(1, ini))
+    batch = int(rng.integers(1, 3 if big else 5))
     kinds = [("s1", "s2", "noise", "flat", "steps")[int(rng.integers(0, 5))] for _ in range(batch)]
     desc_s = f"case {case}: {w}x{h} nf={nf} nl={nl} sf={sf} th={ini}/{mn} batch={batch} {kinds}"
     try:
