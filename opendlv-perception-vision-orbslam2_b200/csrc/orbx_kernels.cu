@@ -1569,6 +1569,11 @@ cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_
     int pow2 = 2; while (pow2 < cap) pow2 <<= 1;
     k_stereo_match<<<dim3((cap + 3) / 4, nPairs), 128, 0, st>>>(L, pyrL, pyrR, kl, (const uint4 *)dl, nl, kr, (const uint4 *)dr, nr, frameStep,
                                                                  mbf, maxD, uRight, depth, sad);
-    k_stereo_filter<<<nPairs, 256, (size_t)pow2 * sizeof(unsigned), st>>>(nl, frameStep, cap, sad, uRight, depth, nMatches, pow2);
+    const size_t smem = (size_t)pow2 * sizeof(unsigned);
+    if (smem > 32 * 1024) {    // more than 8192 key points per frame: opt in (static + dynamic share the 48 KB default)
+        cudaError_t e = cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_stereo_filter<<<nPairs, 256, smem, st>>>(nl, frameStep, cap, sad, uRight, depth, nMatches, pow2);
     return cudaGetLastError();
 }

@@ -128,3 +128,19 @@ def test_batch_of_pairs_in_one_launch(oracle):
     with pytest.raises(orbx.OrbxError):
         orbx.stereo_match_batch(ex, 6, 0, 1, 2, mbf, 0.0)      # sixth pair is outside the batch
     ex.close()
+
+
+def test_stereo_with_more_than_8192_keypoints_per_frame(oracle):
+    """nfeatures = 9000: the median filter's sort buffer (capacity rounded up to 16384 keys) needs 64 KB of dynamic shared
+    memory, i.e. the opt-in."""
+    import orbx
+    w, h, nf, nl = 1920, 1080, 9000, 8
+    left, right = synth.stereo_pair(w, h, 4)
+    ex = orbx.Extractor(nf, 1.2, nl, max_width=w, max_height=h, max_batch=2)
+    kps, desc, cnt = ex.extract_batch([left, right])
+    assert ex.max_keypoints > 8192 and cnt[0] > 2000      # the sort buffer is sized by the capacity, not by the count
+    u, d, nm = orbx.stereo_match(ex, 0, ex, 1, 500.0, 0.5)
+    (ou, od, on), n_left = _oracle_pair(oracle, left, right, nf, nl, 500.0, 0.5)
+    assert len(u) == n_left and nm == on and on > 100
+    assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
+    ex.close()
