@@ -492,8 +492,11 @@ class Extractor:
         self.nfeatures, self.nlevels = nfeatures, nlevels
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orbo_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:      # module globals are already gone at interpreter shutdown
+            try:
+                lib().orbo_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def cap(self, img_shape):
