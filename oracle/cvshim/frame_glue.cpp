@@ -21,6 +21,19 @@ extern "C" {
 #include "orb_oracle.h"
 }
 
+#ifdef ORBREF_DROPIN_STEREO
+// libdropin2ref.so only: the body of OrbFrame::ComputeStereoMatches replaced as INTEGRATION.md section 2b says.  The
+// reference's own definition in orbframe.o is weakened by the Makefile (objcopy --weaken-symbol), so this one is linked and
+// the reference's unmodified stereo constructor calls it.  With a bounding box the host-side FilterKeyPoints has already
+// thinned m_keys / m_descriptors at this point (CommonSetup); the device-resident results are thinned the same way first.
+#include "orbframe_stereo_b200.hpp"
+void OrbFrame::ComputeStereoMatches()
+{
+    orbslam_b200::FilterKeyPoints(*m_ORBextractorLeft, *m_ORBextractorRight, m_boundingBox);
+    orbslam_b200::ComputeStereoMatches(*m_ORBextractorLeft, *m_ORBextractorRight, mbf, mb, mvuRight, m_depths);
+}
+#endif
+
 void OrbVocabulary::transform4(const std::vector<cv::Mat>, OrbBowVector &, OrbFeatureVector &, int) const { abort(); }
 std::vector<cv::Mat> Orbconverter::toDescriptorVector(const cv::Mat &d)
 {

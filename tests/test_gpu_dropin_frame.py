@@ -5,7 +5,12 @@ ComputeStereoMatches, AssignFeaturesToGrid) compiled UNMODIFIED, with cvshim/dro
 reference's include/orbextractor.hpp by the liborbx-backed class of cpp/orbextractor_b200.hpp -- the substitution
 INTEGRATION.md section 1 describes.  oracle/_ref/libframeref.so is the same frame code with the reference's own
 src/orbextractor.cpp.  Both frames must be identical: key points, descriptors, the pyramids the frame reads through
-m_vImagePyramid, mvuRight, m_depths, m_grid."""
+m_vImagePyramid, mvuRight, m_depths, m_grid.
+
+oracle/_ref/libdropin2ref.so goes one step further: the body of OrbFrame::ComputeStereoMatches is replaced as well (the
+reference's definition is weakened in the object file, cvshim/frame_glue.cpp supplies the liborbx-backed one of
+INTEGRATION.md section 2b, FilterKeyPoints on the device-resident results included), so the reference's unmodified stereo
+constructor runs extraction AND stereo matching on the GPU."""
 import os
 import subprocess
 import sys
@@ -21,17 +26,20 @@ REFDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.skipif(not (os.path.exists(os.path.join(REFDIR, "libdropinref.so")) and os.path.exists(os.path.join(REFDIR, "libframeref.so"))),
                     reason="the reference translation units are built where the reference tree is mounted")
+@pytest.mark.parametrize("lib_name", ["libdropinref.so", "libdropin2ref.so"])
 @pytest.mark.parametrize("w,h,seed,nf,nl,mbf,mb,bbox", [
     (1241, 376, 11, 2000, 8, 386.1, 0.537, None), (640, 360, 5, 1000, 6, 200.0, 0.4, (200.0, 420.0, 100.0, 260.0)),
     (752, 480, 9, 1200, 8, 435.2, 0.11, None)])
-def test_reference_frame_with_drop_in_extractor(oracle, tmp_path, w, h, seed, nf, nl, mbf, mb, bbox):
+def test_reference_frame_with_drop_in_extractor(oracle, tmp_path, lib_name, w, h, seed, nf, nl, mbf, mb, bbox):
+    if not os.path.exists(os.path.join(REFDIR, lib_name)):
+        pytest.skip(f"{lib_name} not built")
     left, right = synth.stereo_pair(w, h, seed)
     ref = oracle.ref_stereo_frame(left, right, mbf, mb, nfeatures=nf, nlevels=nl, canonical=1, bbox=bbox)
     # the reference frame code + liborbx in one process of their own: a fault there must not take the test session down
     out = str(tmp_path / "frame.npz")
     code = (f"import sys, numpy as np; sys.path[:0] = {sys.path[:4]!r}; import orb_oracle_py as O, synth\n"
             f"l, r = synth.stereo_pair({w}, {h}, {seed})\n"
-            f"g = O.ref_stereo_frame(l, r, {mbf}, {mb}, nfeatures={nf}, nlevels={nl}, canonical=0, bbox={bbox!r}, lib_name='libdropinref.so')\n"
+            f"g = O.ref_stereo_frame(l, r, {mbf}, {mb}, nfeatures={nf}, nlevels={nl}, canonical=0, bbox={bbox!r}, lib_name={lib_name!r})\n"
             f"lv = {{f'L{{i}}': a for i, a in enumerate(g.pop('levelsL'))}}; lv.update({{f'R{{i}}': a for i, a in enumerate(g.pop('levelsR'))}})\n"
             f"np.savez({out!r}, **g, **lv)\n")
     subprocess.run([sys.executable, "-c", code], check=True, timeout=300)
