@@ -239,6 +239,7 @@ k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ offsets, c
 #define FG_COLS 64          // FRAME_GRID_COLS, orbframe.hpp:52
 #define FG_ROWS 48          // FRAME_GRID_ROWS, orbframe.hpp:51
 #define FG_CELLS (FG_COLS * FG_ROWS)
+#define FG_SMEM_KEYS 8192
 
 // One CTA: PosInGrid for every key point, cell histogram, exclusive scan, then warp 0 fills the cell lists in key-point
 // order (AssignFeaturesToGrid pushes i = 0 .. N-1 in order, orbframe.cpp:202-209).  Cell index = ix * FG_ROWS + iy, the
@@ -249,6 +250,7 @@ k_frame_grid(const orbx_keypoint *__restrict__ keys, int n, float minX, float mi
 {
     __shared__ int cnt[FG_CELLS];
     __shared__ int wsum[32];
+    __shared__ uint16_t scell[FG_SMEM_KEYS];          // cell of the first FG_SMEM_KEYS key points (0xffff = none): the fill loop's reads stay on chip
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int c = tid; c < FG_CELLS; c += 1024) cnt[c] = 0;
     __syncthreads();
@@ -256,7 +258,7 @@ k_frame_grid(const orbx_keypoint *__restrict__ keys, int n, float minX, float mi
         const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, minX), invW));      // :383
         const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, minY), invH));      // :384
         const int c = (px < 0 || px >= FG_COLS || py < 0 || py >= FG_ROWS) ? -1 : px * FG_ROWS + py;   // :387
-        cellOf[i] = c;
+        if (i < FG_SMEM_KEYS) scell[i] = (uint16_t)c; else cellOf[i] = c;
         if (c >= 0) atomicAdd(&cnt[c], 1);
     }
     __syncthreads();
@@ -282,7 +284,8 @@ k_frame_grid(const orbx_keypoint *__restrict__ keys, int n, float minX, float mi
     if (warp == 0) {
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
-            const int c = i < n ? cellOf[i] : -1;
+            int c = -1;
+            if (i < n) { if (i < FG_SMEM_KEYS) { const int v = scell[i]; c = v == 0xffff ? -1 : v; } else c = cellOf[i]; }
             const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
             if (c >= 0) {
                 const unsigned same = __match_any_sync(act, c);

@@ -255,7 +255,7 @@ def _projection_case(rng, n, nmp, w, h, clustered):
 
 
 @pytest.mark.parametrize("n,nmp,w,h,clustered", [(2000, 1500, 1241, 376, False), (3000, 2500, 640, 480, True), (1, 5, 100, 100, False),
-                                                  (5000, 33, 1920, 1080, False)])
+                                                  (5000, 33, 1920, 1080, False), (12000, 700, 1920, 1080, True)])   # > 8192: cells beyond the on-chip table
 def test_search_by_projection_vs_oracle(oracle, n, nmp, w, h, clustered):
     """orbm_search_by_projection against the oracle restatement (itself pinned to the reference's orbmatcher.cpp /
     orbframe.cpp) on inputs the fixture does not reach: key points outside the grid, cell-boundary coordinates, long cell
