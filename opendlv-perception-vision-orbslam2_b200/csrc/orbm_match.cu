@@ -16,6 +16,8 @@
 
 #include <cuda_runtime.h>
 
+#include "orbx_smem_optin.h"
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -709,8 +711,7 @@ int orbm_distinctive(orbm_matcher *m, const uint8_t *desc, int n_desc, const int
     MCK(cudaMemcpyAsync(m->ddCsr, offsets, (size_t)(n_points + 1) * sizeof(int), cudaMemcpyHostToDevice, m->stream));
     if (nnz > 0) MCK(cudaMemcpyAsync(m->ddCsr + n_points + 1, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, m->stream));
     const size_t smem = (size_t)DD_WARPS * maxList * (sizeof(int) + 32 * sizeof(uint16_t));
-    if (smem > 32 * 1024) MCK(cudaFuncSetAttribute(k_distinctive,   // static + dynamic share the 48 KB default limit
-         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCK(orbx_raise_dyn_smem((const void *)k_distinctive, smem));
     k_distinctive<<<(n_points + DD_WARPS - 1) / DD_WARPS, DD_WARPS * 32, smem, m->stream>>>((const uint4 *)m->ddDesc, m->ddCsr, m->ddCsr + n_points + 1,
                                                                                               n_points, maxList, m->ddBest);
     MCK(cudaGetLastError());

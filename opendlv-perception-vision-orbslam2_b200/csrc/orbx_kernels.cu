@@ -11,6 +11,7 @@
 //   k_describe        IC_Angle + rBRIEF + keypoint assembly     orbextractor.cpp:136-211, :978-988, :631-639
 #include "orbx_internal.h"
 #include "orbx_kernels.h"
+#include "orbx_smem_optin.h"
 
 #include <cuda.h>
 #include <algorithm>
@@ -755,11 +756,8 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
 {
     if (segCount <= 0) return cudaSuccess;
     const size_t smem = fast_smem_bytes(winRows, listCap);
-    // opt in per call (the attribute is per device and this is a cheap host-side set).  The 48 KB default limit covers static +
-    // dynamic shared memory together, so the opt-in starts well below it: a dynamic size just under 48 KB plus the kernel's
-    // few hundred static bytes is an invalid launch otherwise.
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_fast_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = orbx_raise_dyn_smem((const void *)k_fast_segs, smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(segCount, batch);
@@ -1091,8 +1089,8 @@ cudaError_t launch_octree(const OrbxLayout &L, const uint32_t *cnt, const unsign
     // opt in per call (the attribute is per device and this is a cheap host-side set).  The 48 KB default limit covers static +
     // dynamic shared memory together, so the opt-in starts well below it: a dynamic size just under 48 KB plus the kernel's
     // few hundred static bytes is an invalid launch otherwise.
-    if (smem > 32 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = orbx_raise_dyn_smem((const void *)k_octree, smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(L.nlevels, batch);
@@ -1570,8 +1568,8 @@ cudaError_t launch_stereo(const OrbxLayout &L, const uint8_t *pyrL, const uint8_
     k_stereo_match<<<dim3((cap + 3) / 4, nPairs), 128, 0, st>>>(L, pyrL, pyrR, kl, (const uint4 *)dl, nl, kr, (const uint4 *)dr, nr, frameStep,
                                                                  mbf, maxD, uRight, depth, sad);
     const size_t smem = (size_t)pow2 * sizeof(unsigned);
-    if (smem > 32 * 1024) {    // more than 8192 key points per frame: opt in (static + dynamic share the 48 KB default)
-        cudaError_t e = cudaFuncSetAttribute(k_stereo_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   // more than 8192 key points per frame need the opt-in
+        cudaError_t e = orbx_raise_dyn_smem((const void *)k_stereo_filter, smem);
         if (e != cudaSuccess) return e;
     }
     k_stereo_filter<<<nPairs, 256, smem, st>>>(nl, frameStep, cap, sad, uRight, depth, nMatches, pow2);
