@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides three drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides four drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device);
 //   * SearchByProjection(CurrentFrame, LastFrame, th, mono) src/orbmatcher.cpp:1337-1483 -> the projections are computed on
@@ -15,11 +15,13 @@
 //     GetFeaturesInArea + DescriptorDistance of the loop, and the loop itself (its exclusion rule depends on the matches
 //     made earlier in the same call, :1412-1414) runs on the host over the returned lists.
 //   * SearchByBoW(keyFrame, frame, matches)                 src/orbmatcher.cpp:164-292   -> one orbm_distance_csr call for all
-//     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host.
+//     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host;
+//   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
 // Results are identical to the base class: tests/test_gpu_drivers.py runs both classes on the same reference frames.
 #ifndef ORBMATCHER_DRIVERS_B200_HPP
 #define ORBMATCHER_DRIVERS_B200_HPP
 
+#include <climits>
 #include <cmath>
 #include <memory>
 #include <vector>
@@ -245,6 +247,73 @@ class ORBmatcherB200 : public ORBmatcher {
               }
           }
       }
+      return nmatches;
+  }
+
+  // ---- src/orbmatcher.cpp:411-528 (monocular initialisation): windows around the previously matched positions of the level-0
+  // key points of F1, searched in F2 at level 0.  ONE orbm_area_distances call returns every window's features and
+  // distances; the loop with its vMatchedDistance / vnMatches21 bookkeeping (a later, closer match takes a key point of F2
+  // away from an earlier one) and the orientation histogram run on the host.
+  int SearchForInitialization(std::shared_ptr<OrbFrame> &F1, std::shared_ptr<OrbFrame> &F2, std::vector<cv::Point2f> &vbPrevMatched,
+                              std::vector<int> &vnMatches12, int windowSize = 10)
+  {
+      int nmatches = 0;
+      const size_t n1 = F1->m_undistortedKeys.size(), n2 = F2->m_undistortedKeys.size();
+      vnMatches12 = std::vector<int>(n1, -1);
+      std::vector<int> who, l0;
+      std::vector<float> qx, qy, qr;
+      for (size_t i1 = 0; i1 < n1; i1++) {
+          if (F1->m_undistortedKeys[i1].octave > 0) continue;
+          who.push_back((int)i1);
+          qx.push_back(vbPrevMatched[i1].x); qy.push_back(vbPrevMatched[i1].y); qr.push_back((float)windowSize);
+          l0.push_back(0);
+      }
+      if (who.empty() || n2 == 0) return 0;
+      cv::Mat qd((int)who.size(), 32, CV_8U);
+      for (size_t k = 0; k < who.size(); k++) F1->m_descriptors.row(who[k]).copyTo(qd.row((int)k));
+      std::vector<int> offsets, indices, dist;
+      gpu_->AreaDistances(F2->m_undistortedKeys, F2->m_descriptors, OrbFrame::m_minX, OrbFrame::m_minY, OrbFrame::m_maxX,
+                          OrbFrame::m_maxY, qd, qx, qy, qr, l0, l0, offsets, indices, dist);
+
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      std::vector<int> vMatchedDistance(n2, INT_MAX), vnMatches21(n2, -1);
+      for (size_t k = 0; k < who.size(); k++) {
+          const int i1 = who[k];
+          int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              const int i2 = indices[e], d = dist[e];
+              if (vMatchedDistance[i2] <= d) continue;
+              if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
+              else if (d < bestDist2) bestDist2 = d;
+          }
+          if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * mfNNratio) {
+              if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+              vnMatches12[i1] = bestIdx2;
+              vnMatches21[bestIdx2] = i1;
+              vMatchedDistance[bestIdx2] = bestDist;
+              nmatches++;
+              if (mbCheckOrientation) {
+                  float rot = F1->m_undistortedKeys[i1].angle - F2->m_undistortedKeys[bestIdx2].angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back(i1);
+              }
+          }
+      }
+      if (mbCheckOrientation) {
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++)
+                  if (vnMatches12[rotHist[b][j]] >= 0) { vnMatches12[rotHist[b][j]] = -1; nmatches--; }
+          }
+      }
+      for (size_t i1 = 0; i1 < n1; i1++)
+          if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2->m_undistortedKeys[vnMatches12[i1]].pt;
       return nmatches;
   }
 

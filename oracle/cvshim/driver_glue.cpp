@@ -9,6 +9,7 @@
 //   part 2  SearchByProjection(CurrentFrame, LastFrame, th, mono)  src/orbmatcher.cpp:1337-1483, in its three level modes
 //           (forward / backward / neither, :1357-1358) and with the orientation histogram
 //   part 3  SearchByBoW(keyFrame, frame, matches)                  src/orbmatcher.cpp:164-292
+//   part 4  SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
@@ -45,6 +46,7 @@ extern "C" {
 // out[0..3]   part 1: nmatches reference, nmatches ORBmatcherB200, differing m_mapPoints entries, entries set
 // out[4+4m..] part 2, mode m = 0 forward, 1 backward, 2 neither: the same four numbers
 // out[16..19] part 3: SearchByBoW(key frame, frame): the same four numbers
+// out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
 {
@@ -140,6 +142,26 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
             out[18] = bad; out[19] = set;
             mpref_standin_clear();
+        }
+
+        // ---------------- part 4: SearchForInitialization(F1, F2): windows around F1's own level-0 key points shifted by (dx, dy)
+        {
+            std::shared_ptr<OrbFrame> F1 = A, F2 = B;
+            std::vector<cv::Point2f> prev1, prev2;
+            for (size_t i = 0; i < A->m_undistortedKeys.size(); i++)
+                prev1.push_back(cv::Point2f(A->m_undistortedKeys[i].pt.x + dx, A->m_undistortedKeys[i].pt.y + dy));
+            prev2 = prev1;
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            std::vector<int> m1, m2;
+            out[20] = ref.SearchForInitialization(F1, F2, prev1, m1, 20);
+            out[21] = gpu.SearchForInitialization(F1, F2, prev2, m2, 20);
+            int bad = (m1.size() != m2.size()), set = 0;
+            for (size_t k = 0; k < m1.size() && k < m2.size(); k++) {
+                if (m1[k] != m2[k] || prev1[k].x != prev2[k].x || prev1[k].y != prev2[k].y) bad++;
+                if (m1[k] >= 0) set++;
+            }
+            out[22] = bad; out[23] = set;
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "driverref_check: %s\n", e.what());

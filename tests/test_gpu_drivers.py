@@ -50,3 +50,5 @@ def test_drop_in_drivers_equal_reference_drivers(w, h, sa, sb, th_points, th_fra
     assert out[4:16:4].max() > 20          # the frame-to-frame search did find matches in some mode
     n_ref, n_gpu, bad, assigned = out[16:20]
     assert n_ref == n_gpu and bad == 0 and assigned > 0, f"SearchByBoW(key frame, frame): {out[16:20]}"
+    n_ref, n_gpu, bad, assigned = out[20:24]
+    assert n_ref == n_gpu and bad == 0 and assigned > 0, f"SearchForInitialization: {out[20:24]}"
