@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides four drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides five drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device);
 //   * SearchByProjection(CurrentFrame, LastFrame, th, mono) src/orbmatcher.cpp:1337-1483 -> the projections are computed on
@@ -16,6 +16,8 @@
 //     made earlier in the same call, :1412-1414) runs on the host over the returned lists.
 //   * SearchByBoW(keyFrame, frame, matches)                 src/orbmatcher.cpp:164-292   -> one orbm_distance_csr call for all
 //     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host;
+//   * SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616 -> the same with the key frame's
+//     map points and PredictScale (relocalisation);
 //   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
 // Results are identical to the base class: tests/test_gpu_drivers.py runs both classes on the same reference frames.
 #ifndef ORBMATCHER_DRIVERS_B200_HPP
@@ -24,6 +26,7 @@
 #include <climits>
 #include <cmath>
 #include <memory>
+#include <set>
 #include <vector>
 
 #include <orbmatcher.hpp>
@@ -157,6 +160,79 @@ class ORBmatcherB200 : public ORBmatcher {
           }
       }
       if (mbCheckOrientation) {                             // :1454-1474
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++) {
+                  CurrentFrame->m_mapPoints[rotHist[b][j]] = std::shared_ptr<OrbMapPoint>();
+                  nmatches--;
+              }
+          }
+      }
+      return nmatches;
+  }
+
+  // ---- src/orbmatcher.cpp:1485-1616 (relocalisation): the key frame's map points, minus those already found, projected
+  // into the current frame; window levels [predicted - 1, predicted + 1] from the reference's own PredictScale.  Projections
+  // on the host, ONE orbm_area_distances call, then the loop: a key point that has received a map point earlier in the
+  // same call is skipped (:1553-1554).
+  int SearchByProjection(std::shared_ptr<OrbFrame> &CurrentFrame, std::shared_ptr<OrbKeyFrame> pKF,
+                         const std::set<std::shared_ptr<OrbMapPoint>> &sAlreadyFound, const float th, const int ORBdist)
+  {
+      const cv::Mat Rcw = CurrentFrame->mTcw.rowRange(0, 3).colRange(0, 3);
+      const cv::Mat tcw = CurrentFrame->mTcw.rowRange(0, 3).col(3);
+      const cv::Mat Ow = -Rcw.t() * tcw;
+      const std::vector<std::shared_ptr<OrbMapPoint>> vpMPs = pKF->GetMapPointMatches();
+      std::vector<int> who, l0, l1;
+      std::vector<float> qx, qy, qr;
+      for (size_t i = 0; i < vpMPs.size(); i++) {
+          const std::shared_ptr<OrbMapPoint> &pMP = vpMPs[i];
+          if (!pMP || pMP->IsCorrupt() || sAlreadyFound.count(pMP)) continue;
+          const cv::Mat x3Dw = pMP->GetWorldPosition();
+          const cv::Mat x3Dc = Rcw * x3Dw + tcw;
+          const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+          const float invzc = static_cast<float>(1.0 / x3Dc.at<float>(2));
+          const float u = CurrentFrame->fx * xc * invzc + CurrentFrame->cx;
+          const float v = CurrentFrame->fy * yc * invzc + CurrentFrame->cy;
+          if (u < CurrentFrame->m_minX || u > CurrentFrame->m_maxX || v < CurrentFrame->m_minY || v > CurrentFrame->m_maxY) continue;
+          const cv::Mat PO = x3Dw - Ow;
+          const float dist3D = static_cast<float>(cv::norm(PO));
+          if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+          const int level = pMP->PredictScale(dist3D, CurrentFrame);
+          who.push_back((int)i);
+          qx.push_back(u); qy.push_back(v); qr.push_back(th * CurrentFrame->m_scaleFactors[level]);
+          l0.push_back(level - 1); l1.push_back(level + 1);
+      }
+      if (who.empty() || CurrentFrame->N == 0) return 0;
+      cv::Mat qd((int)who.size(), 32, CV_8U);
+      for (size_t k = 0; k < who.size(); k++) vpMPs[who[k]]->GetDescriptor().copyTo(qd.row((int)k));
+      std::vector<int> offsets, indices, dist;
+      gpu_->AreaDistances(CurrentFrame->m_undistortedKeys, CurrentFrame->m_descriptors, OrbFrame::m_minX, OrbFrame::m_minY,
+                          OrbFrame::m_maxX, OrbFrame::m_maxY, qd, qx, qy, qr, l0, l1, offsets, indices, dist);
+      int nmatches = 0;
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      for (size_t k = 0; k < who.size(); k++) {
+          int bestDist = 256, bestIdx2 = -1;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              if (CurrentFrame->m_mapPoints[indices[e]]) continue;
+              if (dist[e] < bestDist) { bestDist = dist[e]; bestIdx2 = indices[e]; }
+          }
+          if (bestDist <= ORBdist) {
+              CurrentFrame->m_mapPoints[bestIdx2] = vpMPs[who[k]];
+              nmatches++;
+              if (mbCheckOrientation) {
+                  float rot = pKF->mvKeysUn[who[k]].angle - CurrentFrame->m_undistortedKeys[bestIdx2].angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back(bestIdx2);
+              }
+          }
+      }
+      if (mbCheckOrientation) {
           int ind1 = -1, ind2 = -1, ind3 = -1;
           ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
           for (int b = 0; b < H; b++) {

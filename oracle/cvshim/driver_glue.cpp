@@ -10,6 +10,7 @@
 //           (forward / backward / neither, :1357-1358) and with the orientation histogram
 //   part 3  SearchByBoW(keyFrame, frame, matches)                  src/orbmatcher.cpp:164-292
 //   part 4  SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528
+//   part 5  SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
@@ -46,6 +47,7 @@ extern "C" {
 // out[0..3]   part 1: nmatches reference, nmatches ORBmatcherB200, differing m_mapPoints entries, entries set
 // out[4+4m..] part 2, mode m = 0 forward, 1 backward, 2 neither: the same four numbers
 // out[16..19] part 3: SearchByBoW(key frame, frame): the same four numbers
+// out[24..27] part 5: SearchByProjection(CurrentFrame, key frame, found): the four numbers of part 1
 // out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
@@ -141,6 +143,25 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             int bad = (m1.size() != m2.size()), set = 0;
             for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
             out[18] = bad; out[19] = set;
+            mpref_standin_clear();
+        }
+
+        // ---------------- part 5: SearchByProjection(CurrentFrame, key frame, already found, th, ORBdist): the stand-in key frame
+        // carries frame A's map points (world positions from part 2); every ninth is "already found"
+        {
+            std::vector<std::shared_ptr<OrbMapPoint>> kfPoints(A->m_mapPoints);
+            std::shared_ptr<OrbKeyFrame> KF = mpref_standin_keyframe_with(A->m_undistortedKeys, A->m_descriptors, kfPoints);
+            std::set<std::shared_ptr<OrbMapPoint>> found;
+            for (size_t i = 0; i < kfPoints.size(); i += 9) if (kfPoints[i]) found.insert(kfPoints[i]);
+            cv::Mat T = I.clone();
+            T.ptr<float>(0)[3] = 0.03f; T.ptr<float>(1)[3] = 0.01f; T.ptr<float>(2)[3] = -0.2f;
+            std::shared_ptr<OrbFrame> E1 = std::make_shared<OrbFrame>(B), E2 = std::make_shared<OrbFrame>(B);
+            E1->SetPose(T); E2->SetPose(T);
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            out[24] = ref.SearchByProjection(E1, KF, found, th_frames, 100);
+            out[25] = gpu.SearchByProjection(E2, KF, found, th_frames, 100);
+            out[26] = count_mismatches(E1, E2, &out[27]);
             mpref_standin_clear();
         }
 
