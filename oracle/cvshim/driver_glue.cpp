@@ -15,6 +15,7 @@
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
 
+#include <chrono>
 #include <cstring>
 #include <sstream>
 
@@ -47,6 +48,7 @@ extern "C" {
 // out[0..3]   part 1: nmatches reference, nmatches ORBmatcherB200, differing m_mapPoints entries, entries set
 // out[4+4m..] part 2, mode m = 0 forward, 1 backward, 2 neither: the same four numbers
 // out[16..19] part 3: SearchByBoW(key frame, frame): the same four numbers
+// out[28..31] wall microseconds of one warm call: part 1 reference / ORBmatcherB200, part 3 reference / ORBmatcherB200
 // out[24..27] part 5: SearchByProjection(CurrentFrame, key frame, found): the four numbers of part 1
 // out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
@@ -92,6 +94,16 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             out[0] = ref.SearchByProjection(B1, mps, th_points);
             out[1] = gpu.SearchByProjection(B2, mps, th_points);
             out[2] = count_mismatches(B1, B2, &out[3]);
+            {   // wall time of one more call each on fresh copies (the first GPU call above allocated the workspace)
+                std::shared_ptr<OrbFrame> T1 = std::make_shared<OrbFrame>(B), T2 = std::make_shared<OrbFrame>(B);
+                auto t0 = std::chrono::steady_clock::now();
+                ref.SearchByProjection(T1, mps, th_points);
+                auto t1 = std::chrono::steady_clock::now();
+                gpu.SearchByProjection(T2, mps, th_points);
+                auto t2 = std::chrono::steady_clock::now();
+                out[28] = (int32_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+                out[29] = (int32_t)std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+            }
             for (int idx = 0; idx < B->N; idx++) B->m_mapPoints[idx] = std::shared_ptr<OrbMapPoint>();
         }
 
@@ -140,6 +152,16 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             std::vector<std::shared_ptr<OrbMapPoint>> m1, m2;
             out[16] = ref.SearchByBoW(KF, D1, m1);
             out[17] = gpu.SearchByBoW(KF, D2, m2);
+            {
+                std::vector<std::shared_ptr<OrbMapPoint>> t1v, t2v;
+                auto t0 = std::chrono::steady_clock::now();
+                ref.SearchByBoW(KF, D1, t1v);
+                auto t1 = std::chrono::steady_clock::now();
+                gpu.SearchByBoW(KF, D2, t2v);
+                auto t2 = std::chrono::steady_clock::now();
+                out[30] = (int32_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+                out[31] = (int32_t)std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+            }
             int bad = (m1.size() != m2.size()), set = 0;
             for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
             out[18] = bad; out[19] = set;

@@ -11,4 +11,4 @@ for (w,h,sa,sb,t1,t2,ratio,dx,dy) in [(1241, 376, 11, 11, 3.0, 15.0, 0.8, 0.7, -
     imgs = [np.ascontiguousarray(a, np.uint8) for a in (la, ra, lb, rb)]
     out = np.full(32, -99, np.int32)
     rc = R.driverref_check(C.byref(Cfg(2000, 1.2, 8, 20, 7)), *[a.ctypes.data for a in imgs], w, h, 386.1, 0.537, t1, t2, ratio, dx, dy, out.ctypes.data)
-    print(rc, out[:28].reshape(7,4).tolist())
+    print(rc, out[:28].reshape(7,4).tolist(), 'us: SearchByProjection ref/gpu', out[28], out[29], 'SearchByBoW ref/gpu', out[30], out[31])
