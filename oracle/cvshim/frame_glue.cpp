@@ -15,6 +15,7 @@
 #include <orbmatcher.hpp>
 
 #include <cstring>
+#include <ctime>
 #include <sstream>
 
 extern "C" {
@@ -236,6 +237,37 @@ void frameref_descriptor_distance(const uint8_t *a, const uint8_t *b, int n, int
         const cv::Mat ma(1, 32, CV_8U, (void *)(a + (size_t)i * 32), 32), mb(1, 32, CV_8U, (void *)(b + (size_t)i * 32), 32);
         out[i] = ORBmatcher::DescriptorDistance(ma, mb);
     }
+}
+
+// Wall time of the reference's own stereo OrbFrame constructor (src/orbframe.cpp:61-88: two extraction threads, CommonSetup,
+// ComputeStereoMatches, AssignFeaturesToGrid) with two long-lived extractors, as Tracking holds them: one warm-up
+// construction, then the mean of `reps` constructions in microseconds.  In libframeref.so everything is the reference's CPU
+// code; in libdropinref.so the extractor is the liborbx drop-in; in libdropin2ref.so ComputeStereoMatches is too.
+double frameref_time_constructor(const frameref_cfg *c, const uint8_t *left, const uint8_t *right, int w, int h, float mbf, int reps)
+{
+    std::streambuf *old = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    double us = -1;
+    {
+        auto exL = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
+        auto exR = std::make_shared<OrbExtractor>(c->nfeatures, c->scale, c->nlevels, c->ini_th, c->min_th);
+        cv::Mat imL(h, w, CV_8UC1, (void *)left, (size_t)w), imR(h, w, CV_8UC1, (void *)right, (size_t)w);
+        cv::Mat K(3, 3, CV_32F), dist(4, 1, CV_32F);
+        for (int i = 0; i < 9; i++) K.ptr<float>(i / 3)[i % 3] = (i % 4 == 0) ? 1.f : 0.f;
+        K.at<float>(0, 0) = 700.f; K.at<float>(1, 1) = 700.f; K.at<float>(0, 2) = w * 0.5f; K.at<float>(1, 2) = h * 0.5f;
+        for (int i = 0; i < 4; i++) dist.ptr<float>(i)[0] = 0.f;
+        std::array<float, 4> box = {0.f, 0.f, 0.f, 0.f};
+        OrbFrame::m_initialComputations = true;
+        { OrbFrame warm(imL, imR, 0.0, exL, exR, std::shared_ptr<OrbVocabulary>(), K, dist, mbf, 35.f * mbf / 700.f, box); }
+        struct timespec a, b;
+        clock_gettime(CLOCK_MONOTONIC, &a);
+        for (int r = 0; r < reps; r++) { OrbFrame f(imL, imR, 0.0, exL, exR, std::shared_ptr<OrbVocabulary>(), K, dist, mbf, 35.f * mbf / 700.f, box); }
+        clock_gettime(CLOCK_MONOTONIC, &b);
+        us = ((b.tv_sec - a.tv_sec) * 1e6 + (b.tv_nsec - a.tv_nsec) * 1e-3) / reps;
+    }
+    std::cout.rdbuf(old);
+    return us;
 }
 
 } // extern "C"
