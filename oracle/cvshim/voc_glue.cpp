@@ -13,10 +13,56 @@
 #include <cstdint>
 #include <vector>
 
+#ifdef ORBREF_DROPIN_VOC
+// libvocdropin.so only: the body of OrbVocabulary::transform4 replaced as INTEGRATION.md section 2c says (the reference's own
+// definition in orbvocabulary.o is weakened by the Makefile).  The class cannot get a new member here, so the device-side
+// tree of each OrbVocabulary lives in a table keyed by the object; vocref_free drops it.
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "orbvocabulary_b200.hpp"
+static std::mutex g_vocMu;
+static std::map<const OrbVocabulary *, std::shared_ptr<orbslam_b200::VocabularyTransform>> g_vocGpu;
+
+void OrbVocabulary::transform4(const std::vector<cv::Mat> features, OrbBowVector &bowVector, OrbFeatureVector &featureVector, int levelsUp) const
+{
+    std::shared_ptr<orbslam_b200::VocabularyTransform> t;
+    {
+        std::lock_guard<std::mutex> lk(g_vocMu);
+        auto it = g_vocGpu.find(this);
+        if (it == g_vocGpu.end()) {
+            // the tree as flat arrays: children in m_nodes[v].children order, word_id = -1 for inner nodes
+            std::vector<int32_t> off(1, 0), ids, wid;
+            std::vector<double> wt;
+            std::vector<uint8_t> desc;
+            for (const Node &n : m_nodes) {
+                ids.insert(ids.end(), n.children.begin(), n.children.end());
+                off.push_back((int32_t)ids.size());
+                wid.push_back(n.isLeaf() ? (int32_t)n.word_id : -1);
+                wt.push_back(n.weight);
+                uint8_t row[32] = {0};
+                if (!n.descriptor.empty()) memcpy(row, n.descriptor.ptr(0), 32);
+                desc.insert(desc.end(), row, row + 32);
+            }
+            it = g_vocGpu.emplace(this, std::make_shared<orbslam_b200::VocabularyTransform>(off, ids, desc, wid, wt, m_L)).first;
+        }
+        t = it->second;
+    }
+    t->transform4(features, bowVector, featureVector, levelsUp);
+}
+#endif
+
 extern "C" {
 
 void *vocref_load(const char *path) { return new OrbVocabulary(std::string(path)); }
-void vocref_free(void *v) { delete (OrbVocabulary *)v; }
+void vocref_free(void *v)
+{
+#ifdef ORBREF_DROPIN_VOC
+    { std::lock_guard<std::mutex> lk(g_vocMu); g_vocGpu.erase((const OrbVocabulary *)v); }
+#endif
+    delete (OrbVocabulary *)v;
+}
 int vocref_size(void *v) { return ((OrbVocabulary *)v)->GetSize(); }
 
 static cv::Mat row32(const uint8_t *p)

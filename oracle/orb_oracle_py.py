@@ -252,8 +252,9 @@ class RefVocabulary:
     """The reference's own OrbVocabulary (oracle/_ref/libvocref.so, built from /root/reference by `make -C oracle ref`)."""
     PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libvocref.so")
 
-    def __init__(self, text_path):
-        R = C.CDLL(self.PATH)
+    def __init__(self, text_path, lib_name=None):
+        # lib_name="libvocdropin.so": the same class with the body of transform4 replaced by the liborbx-backed one (GPU box)
+        R = C.CDLL(self.PATH if lib_name is None else os.path.join(os.path.dirname(self.PATH), lib_name))
         R.vocref_load.restype = C.c_void_p
         R.vocref_load.argtypes = [C.c_char_p]
         R.vocref_free.argtypes = [C.c_void_p]
