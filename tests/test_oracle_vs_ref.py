@@ -184,3 +184,16 @@ def test_descriptor_distance_equals_reference_function(oracle):
     assert (ref[:100] == 0).all() and (ref[100:200] == 256).all() and (ref[200:456] == 1).all()
     assert np.array_equal(ref, np.array([oracle.descriptor_distance(a[i], b[i]) for i in range(len(a))], np.int32))
     assert np.array_equal(ref, np.unpackbits(a ^ b, axis=1).sum(1))
+
+
+def test_every_reference_build_exists():
+    """`make -C oracle ref` (tests/conftest.py runs it where the reference tree is mounted) must have produced every library the
+    GPU-side tests load -- the reference's translation units around the drop-in headers of cpp/ included; a compile break in
+    one of those headers would otherwise only show up as skipped tests on the GPU box."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not mounted")
+    d = os.path.dirname(REF)
+    for name in ("liborbref.so", "libvocref.so", "libmpref.so", "libframeref.so", "libdriverref.so", "libdropinref.so",
+                 "libdropin2ref.so", "libdropin3ref.so", "libvocdropin.so"):
+        assert os.path.exists(os.path.join(d, name)), name
+        assert os.path.getmtime(os.path.join(d, name)) >= os.path.getmtime(os.path.join(os.path.dirname(d), "cvshim", "opencv2", "core", "core.hpp")) - 1, f"{name} is older than the shim"
