@@ -100,14 +100,17 @@ class HammingMatcher {
   // (AssignFeaturesToGrid / GetFeaturesInArea, orbframe.cpp:192-211, :308-380) included.  The caller walks pMP once,
   // keeps the map points that pass GetTrackInView / IsCorrupt (:51-55) and appends per point: its descriptor row,
   // getTrackProjX/Y, GetTrackScaleLevel and radius = r * F->m_scaleFactors[level] with r from :58-62.  occupied[i] != 0
-  // where F->m_mapPoints[i] is set and has observations (:87-89).  On return assigned[i] is the position (in the arrays
-  // handed in) of the map point the reference's loop would leave in F->m_mapPoints[i], -1 for none; the return value is
-  // the reference's nmatches.
+  // where F->m_mapPoints[i] is set and has observations (:87-89) on entry; observed[p] != 0 where map point p itself has
+  // observations -- the reference stores an accepted map point at once (:121), so such a point hides its key point from the
+  // map points after it; the device iterates to the fixpoint of that rule.  On return assigned[i] is the position (in the
+  // arrays handed in) of the map point the reference's loop would leave in F->m_mapPoints[i], -1 for none; the return
+  // value is the reference's nmatches.
   int SearchByProjection(const std::vector<cv::KeyPoint> &keysUn, const std::vector<float> &uRight,
                          const std::vector<unsigned char> &occupied, const cv::Mat &descriptors, float minX, float minY,
                          float maxX, float maxY, const cv::Mat &pointDescriptors, const std::vector<float> &projX,
                          const std::vector<float> &projY, const std::vector<int> &level, const std::vector<float> &radius,
-                         float nnRatio, int thHigh, std::vector<int> &pointMatch, std::vector<int> &assigned)
+                         const std::vector<unsigned char> &observed, float nnRatio, int thHigh, std::vector<int> &pointMatch,
+                         std::vector<int> &assigned)
   {
       static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint layout");
       const int n = (int)keysUn.size(), np = pointDescriptors.rows;
@@ -122,8 +125,9 @@ class HammingMatcher {
       fv.n = n;
       fv.min_x = minX; fv.min_y = minY; fv.max_x = maxX; fv.max_y = maxY;
       int32_t nmatches = 0;
-      check(orbm_search_by_projection(m_, &fv, pointDescriptors.ptr(0), projX.data(), projY.data(), level.data(), radius.data(), np,
-                                      nnRatio, thHigh, pointMatch.data(), assigned.data(), &nmatches));
+      check(orbm_search_by_projection(m_, &fv, pointDescriptors.ptr(0), projX.data(), projY.data(), level.data(), radius.data(),
+                                      observed.empty() ? nullptr : observed.data(), np, nnRatio, thHigh, pointMatch.data(),
+                                      assigned.data(), &nmatches));
       return nmatches;
   }
 

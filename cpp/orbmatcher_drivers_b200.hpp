@@ -9,7 +9,8 @@
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
 // (RadiusByViewingCos, ComputeThreeMaxima) and hides five drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
-//     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device);
+//     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device; the sequential rule "a key point that an
+//     observed map point was stored on earlier in the call is skipped", :87-89 after :121, is iterated to its fixpoint);
 //   * SearchByProjection(CurrentFrame, LastFrame, th, mono) src/orbmatcher.cpp:1337-1483 -> the projections are computed on
 //     the host with the reference's own matrix expressions, ONE orbm_area_distances call replaces every
 //     GetFeaturesInArea + DescriptorDistance of the loop, and the loop itself (its exclusion rule depends on the matches
@@ -44,6 +45,7 @@ class ORBmatcherB200 : public ORBmatcher {
       const bool bFactor = std::abs(th - 1.0) < 0.0000000001f;
       std::vector<int> who, level, pointMatch, assigned;
       std::vector<float> x, y, radius;
+      std::vector<unsigned char> observed;          // :87-89 sees the map points stored earlier in this call (:121)
       cv::Mat pointDesc((int)pMP.size() > 0 ? (int)pMP.size() : 1, 32, CV_8U);
       for (size_t i = 0; i < pMP.size(); i++) {
           const std::shared_ptr<OrbMapPoint> &mp = pMP[i];
@@ -54,6 +56,7 @@ class ORBmatcherB200 : public ORBmatcher {
           mp->GetDescriptor().copyTo(pointDesc.row((int)who.size()));
           x.push_back(mp->getTrackProjX()); y.push_back(mp->getTrackProjY());
           level.push_back(lv); radius.push_back(r * F->m_scaleFactors[lv]);
+          observed.push_back(mp->GetObservingKeyFrameCount() > 0);
           who.push_back((int)i);
       }
       if (who.empty() || F->N == 0) return 0;
@@ -62,8 +65,8 @@ class ORBmatcherB200 : public ORBmatcher {
           occupied[k] = F->m_mapPoints[k] && F->m_mapPoints[k]->GetObservingKeyFrameCount() > 0;
       const int n = gpu_->SearchByProjection(F->m_undistortedKeys, F->mvuRight, occupied, F->m_descriptors, OrbFrame::m_minX,
                                              OrbFrame::m_minY, OrbFrame::m_maxX, OrbFrame::m_maxY,
-                                             pointDesc.rowRange(0, (int)who.size()), x, y, level, radius, mfNNratio, TH_HIGH,
-                                             pointMatch, assigned);
+                                             pointDesc.rowRange(0, (int)who.size()), x, y, level, radius, observed, mfNNratio,
+                                             TH_HIGH, pointMatch, assigned);
       for (int k = 0; k < F->N; k++)
           if (assigned[k] >= 0) F->m_mapPoints[k] = pMP[who[assigned[k]]];
       return n;

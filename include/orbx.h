@@ -92,7 +92,11 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
 /* Device-resident variant: frames already in HBM (frame f at d_imgs + f*frame_stride), results
  * stay in HBM.  Work is enqueued on `stream` (a cudaStream_t, NULL = the handle's own stream)
  * and NOT synchronised.  Result pointers (valid until the next call on this handle):
- * orbx_device_results. */
+ * orbx_device_results.  The handle records an event behind the enqueued work; every later entry point
+ * of this handle (the next extraction on any stream, orbx_fetch_results, orbx_filter_keypoints,
+ * orbx_stereo_match*, orbx_get_level, the debug taps) orders itself behind that event, so library
+ * calls never race with the extraction.  A caller that reads orbx_device_results in kernels of its own
+ * must launch them on `stream` or synchronise it. */
 int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t frame_stride, size_t pitch,
                               int batch, int width, int height, void *stream);
 /* d_kps: batch x kp_stride records; d_desc: batch x kp_stride x 32 bytes; d_counts: batch ints */
@@ -216,11 +220,16 @@ typedef struct {
  * mp_radius[i] = r * m_scaleFactors[level] exactly as the caller computes it at :54-67; only map points that pass the
  * caller's GetTrackInView / IsCorrupt tests (:51-55) are handed in.  Candidates are skipped as at :87-96, best / second
  * best follow the strict '<' updates of :102-114, acceptance is :116-123 with TH_HIGH = th_high and mfNNratio = nnratio.
+ * The reference's loop is sequential: an accepted map point is stored in m_mapPoints at once (:121) and, if it has
+ * observations, :87-89 hides its key point from every later map point of the same call.  mp_observed[i] != 0 says map point
+ * i has GetObservingKeyFrameCount() > 0 (NULL: none has -- in Tracking::SearchLocalPoints all have); the device evaluates
+ * all map points at once and repeats the pass until no choice changes, which reproduces the sequential result exactly
+ * (map point i is final after pass i + 1 at the latest; two or three passes in practice).
  * mp_match[i] = key point accepted for map point i or -1; assigned[k] = the map point the reference's loop leaves in
  * m_mapPoints[k] among those handed in (the last accepted one) or -1; *nmatches = the function's return value. */
 int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
-                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
-                              int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches);
+                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, const uint8_t *mp_observed,
+                              int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches);
 /* OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211) with PosInGrid (:381-393): the 64 x 48 feature grid of one frame as
  * CSR.  Cell (ix, iy) = m_grid[ix][iy] is cell_items[cell_start[ix * 48 + iy] .. cell_start[ix * 48 + iy + 1]), key-point
  * indices in increasing order exactly as the reference pushes them; key points PosInGrid rejects are in no cell.

@@ -336,23 +336,31 @@ __device__ __forceinline__ void walk_area(const orbx_keypoint *__restrict__ keys
 }
 
 // One thread per map point: GetFeaturesInArea + the candidate loop + the acceptance, sequentially in the reference's order.
+//
+// The reference's loop over the map points is sequential (orbmatcher.cpp:48): an accepted map point is stored in
+// F->m_mapPoints at once (:121), and when it has observations it hides its key point from every LATER map point of the same
+// call (:87-89).  The device evaluates all map points at once and iterates to the fixpoint of that rule: in a round, map point
+// i skips key point k when k was occupied on entry or when the previous round left an observed map point j < i on k
+// (claimPrev[k] = least such j).  Map point 0 is final after round 1, map point i after round i + 1 at the latest, and a round
+// that changes no choice has reproduced the sequential loop exactly; in practice two or three rounds.
 __global__ void __launch_bounds__(128)
-k_project_search(const orbx_keypoint *__restrict__ keys, const float *__restrict__ uRight, const uint8_t *__restrict__ occupied,
-                 const uint4 *__restrict__ desc, const int *__restrict__ cellStart, const int *__restrict__ cellItems,
-                 float minX, float minY, float invW, float invH, const uint4 *__restrict__ mpDesc, const float *__restrict__ mpX,
-                 const float *__restrict__ mpY, const int *__restrict__ mpLevel, const float *__restrict__ mpRadius, int nMp,
-                 float nnRatio, int thHigh, int *__restrict__ mpMatch, int *__restrict__ assigned, int *__restrict__ nMatches)
+k_project_round(const orbx_keypoint *__restrict__ keys, const float *__restrict__ uRight, const uint8_t *__restrict__ occupied,
+                const uint4 *__restrict__ desc, const int *__restrict__ cellStart, const int *__restrict__ cellItems,
+                float minX, float minY, float invW, float invH, const uint4 *__restrict__ mpDesc, const float *__restrict__ mpX,
+                const float *__restrict__ mpY, const int *__restrict__ mpLevel, const float *__restrict__ mpRadius,
+                const uint8_t *__restrict__ mpObserved, int nMp, float nnRatio, int thHigh, const int *__restrict__ claimPrev,
+                int *__restrict__ claimNext, int *__restrict__ mpMatch, int *__restrict__ changed)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nMp) return;
     const float x = mpX[i], y = mpY[i], r = mpRadius[i];
     const int level = mpLevel[i];
-    mpMatch[i] = -1;
     const uint4 qa = mpDesc[2 * i], qb = mpDesc[2 * i + 1];
     int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;   // orbmatcher.cpp:75-79
     walk_area(keys, cellStart, cellItems, minX, minY, invW, invH, x, y, r, level - 1, level,   // :64-68
               [&](int idx, const orbx_keypoint &kp) {
-        if (occupied && occupied[idx]) return;                                         // :87-89
+        if (occupied && occupied[idx]) return;                                         // :87-89, state on entry
+        if (claimPrev && claimPrev[idx] < i) return;                                   // :87-89, stored earlier in this call (:121)
         const float ur = uRight[idx];
         if (ur > 0.f && fabsf(__fsub_rn(x, ur)) > r) return;                           // :91-96
         const int dist = hamming256(qa, qb, desc[2 * idx], desc[2 * idx + 1]);
@@ -364,12 +372,24 @@ k_project_search(const orbx_keypoint *__restrict__ keys, const float *__restrict
             bestLevel2 = kp.octave; bestDist2 = dist;
         }
     });
-    if (bestDist <= thHigh) {                                                          // :116-123
-        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnRatio, (float)bestDist2)) return;
-        mpMatch[i] = bestIdx;
-        atomicMax(&assigned[bestIdx], i);          // the loop runs in map-point order: the last accepted one stays
-        atomicAdd(nMatches, 1);
-    }
+    int choice = -1;
+    if (bestDist <= thHigh &&                                                          // :116-123
+        !(bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnRatio, (float)bestDist2)))
+        choice = bestIdx;
+    if (choice != mpMatch[i]) { mpMatch[i] = choice; *changed = 1; }
+    if (choice >= 0 && claimNext && mpObserved[i]) atomicMin(&claimNext[choice], i);
+}
+
+// after the fixpoint: m_mapPoints[k] = the LAST map point accepted on k (the loop runs in map-point order, :121), nmatches (:122)
+__global__ void __launch_bounds__(128)
+k_project_finish(const int *__restrict__ mpMatch, int nMp, int *__restrict__ assigned, int *__restrict__ nMatches)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nMp) return;
+    const int k = mpMatch[i];
+    if (k < 0) return;
+    atomicMax(&assigned[k], i);
+    atomicAdd(nMatches, 1);
 }
 
 // GetFeaturesInArea for nq windows: pass 1 counts, one CTA scans the counts into CSR offsets, pass 2 writes the feature
@@ -762,8 +782,8 @@ int orbm_distance_pairs(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int
 
 
 int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, const uint8_t *mp_desc, const float *mp_x,
-                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, int n_mp, float nnratio,
-                              int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches)
+                              const float *mp_y, const int32_t *mp_level, const float *mp_radius, const uint8_t *mp_observed,
+                              int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned, int32_t *nmatches)
 {
     if (!m) return ORBX_ERR_ARG;
     if (!frame || !mp_desc || !mp_x || !mp_y || !mp_level || !mp_radius || !mp_match || !assigned || !nmatches || n_mp < 1 ||
@@ -790,13 +810,16 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
     const size_t oMpY = o;     o += al((size_t)n_mp * 4);
     const size_t oMpR = o;     o += al((size_t)n_mp * 4);
     const size_t oMpL = o;     o += al((size_t)n_mp * 4);
+    const size_t oMpObs = o;   o += al((size_t)n_mp);
     const size_t inBytes = o;
     const size_t oCellOf = o;  o += al((size_t)n * 4);
     const size_t oItems = o;   o += al((size_t)n * 4);
     const size_t oStart = o;   o += al((size_t)(FG_CELLS + 1) * 4);
+    const size_t oClaimA = o;  o += al((size_t)n * 4);             // least observed map point stored on a key point, two rounds
+    const size_t oClaimB = o;  o += al((size_t)n * 4);
     const size_t oRes = o;
     const size_t oMatch = o;   o += al((size_t)n_mp * 4);
-    const size_t oAsg = o;     o += al((size_t)n * 4 + 4);          // assigned[n] | nmatches
+    const size_t oAsg = o;     o += al((size_t)n * 4 + 8);          // assigned[n] | nmatches | changed
     const size_t resBytes = o - oRes;
     if (o > m->spCap) {
         if (m->spBuf) cudaFree(m->spBuf);
@@ -817,17 +840,49 @@ int orbm_search_by_projection(orbm_matcher *m, const orbm_frame_view *frame, con
     memcpy(hb + oMpY, mp_y, (size_t)n_mp * 4);
     memcpy(hb + oMpR, mp_radius, (size_t)n_mp * 4);
     memcpy(hb + oMpL, mp_level, (size_t)n_mp * 4);
+    bool anyObserved = false;
+    if (mp_observed) {
+        memcpy(hb + oMpObs, mp_observed, (size_t)n_mp);
+        for (int i = 0; i < n_mp && !anyObserved; i++) anyObserved = mp_observed[i] != 0;
+    }
     MCK(cudaMemcpyAsync(b, hb, inBytes, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemsetAsync(b + oMatch, 0xFF, (size_t)n_mp * 4, st));                 // choices start at -1
     MCK(cudaMemsetAsync(b + oAsg, 0xFF, (size_t)n * 4, st));
-    MCK(cudaMemsetAsync(b + oAsg + (size_t)n * 4, 0, 4, st));
+    MCK(cudaMemsetAsync(b + oAsg + (size_t)n * 4, 0, 8, st));
     k_frame_grid<<<1, 1024, 0, st>>>((const orbx_keypoint *)(b + oKeys), n, frame->min_x, frame->min_y, invW, invH,
                                      (int *)(b + oCellOf), (int *)(b + oStart), (int *)(b + oItems));
     MCK(cudaGetLastError());
-    k_project_search<<<(n_mp + 127) / 128, 128, 0, st>>>(
-        (const orbx_keypoint *)(b + oKeys), (const float *)(b + oUr), frame->occupied ? b + oOcc : nullptr, (const uint4 *)(b + oDesc),
-        (const int *)(b + oStart), (const int *)(b + oItems), frame->min_x, frame->min_y, invW, invH, (const uint4 *)(b + oMpDesc),
-        (const float *)(b + oMpX), (const float *)(b + oMpY), (const int *)(b + oMpL), (const float *)(b + oMpR), n_mp, nnratio, th_high,
-        (int *)(b + oMatch), (int *)(b + oAsg), (int *)(b + oAsg + (size_t)n * 4));
+    int *dChanged = (int *)(b + oAsg + (size_t)n * 4 + 4);
+    auto round = [&](const int *claimPrev, int *claimNext) -> cudaError_t {
+        k_project_round<<<(n_mp + 127) / 128, 128, 0, st>>>(
+            (const orbx_keypoint *)(b + oKeys), (const float *)(b + oUr), frame->occupied ? b + oOcc : nullptr, (const uint4 *)(b + oDesc),
+            (const int *)(b + oStart), (const int *)(b + oItems), frame->min_x, frame->min_y, invW, invH, (const uint4 *)(b + oMpDesc),
+            (const float *)(b + oMpX), (const float *)(b + oMpY), (const int *)(b + oMpL), (const float *)(b + oMpR), b + oMpObs, n_mp,
+            nnratio, th_high, claimPrev, claimNext, (int *)(b + oMatch), dChanged);
+        return cudaGetLastError();
+    };
+    if (!anyObserved) {
+        MCK(round(nullptr, nullptr));             // no accepted map point can hide a key point: one round is the whole loop
+    } else {
+        // rounds in groups of three, the "changed" flag of a group's last round read back; a round past the fixpoint changes nothing
+        int *claim[2] = {(int *)(b + oClaimA), (int *)(b + oClaimB)};
+        MCK(cudaMemsetAsync(claim[0], 0x7F, (size_t)n * 4, st));                   // 0x7f7f7f7f: no claimant
+        int cur = 0, rounds = 0;
+        for (;;) {
+            for (int g = 0; g < 3; g++) {
+                MCK(cudaMemsetAsync(claim[cur ^ 1], 0x7F, (size_t)n * 4, st));
+                if (g == 2) MCK(cudaMemsetAsync(dChanged, 0, 4, st));
+                MCK(round(claim[cur], claim[cur ^ 1]));
+                cur ^= 1; rounds++;
+            }
+            int changedHost = 0;
+            MCK(cudaMemcpyAsync(&changedHost, dChanged, 4, cudaMemcpyDeviceToHost, st));
+            MCK(cudaStreamSynchronize(st));
+            if (!changedHost) break;
+            if (rounds > n_mp + 3) return mfail(m, ORBX_ERR_CUDA, "projection search did not reach its fixpoint");
+        }
+    }
+    k_project_finish<<<(n_mp + 127) / 128, 128, 0, st>>>((const int *)(b + oMatch), n_mp, (int *)(b + oAsg), (int *)(b + oAsg + (size_t)n * 4));
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(hb + oRes, b + oRes, resBytes, cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));

@@ -81,6 +81,11 @@ struct orbx_extractor {
         cudaEvent_t evFork = nullptr, evJoin = nullptr, evFast0 = nullptr, evPyr = nullptr, evStart = nullptr, evDone = nullptr;
     } lane[ORBX_LANES];
     cudaStream_t streamIn = nullptr, streamOut = nullptr;
+    // orbx_extract_batch_device enqueues on the CALLER's stream and does not synchronise: evLast marks the end of that work,
+    // and every later entry point orders itself behind it (stream wait, or a host wait where it is about to touch host-side
+    // state the kernels read) before it reads the results or reuses the arenas.
+    cudaEvent_t evLast = nullptr;
+    bool lastPending = false;
     // CUDA graphs of the per-chunk kernel pipeline of the host entry point (level-0 copy .. describe, both
     // streams of a lane): one cudaGraphLaunch replaces ~25 launches / event calls per chunk.  Keyed by
     // (first frame, frames, lane); dropped whenever geometry or an arena pointer changes.
@@ -143,6 +148,21 @@ int failCuda(orbx_extractor *h, cudaError_t e, const char *where)
         cudaError_t e_ = (call);                                      \
         if (e_ != cudaSuccess) return failCuda(h, e_, what);          \
     } while (0)
+
+// order `st` behind the last device-resident extraction (a no-op when that call used `st` itself or has been waited for)
+cudaError_t orderAfterLast(orbx_extractor *h, cudaStream_t st)
+{
+    if (!h->lastPending) return cudaSuccess;
+    return cudaStreamWaitEvent(st, h->evLast, 0);
+}
+// host-side wait for the last device-resident extraction: before tables, tensor maps or arenas it may still read are replaced
+cudaError_t drainLast(orbx_extractor *h)
+{
+    if (!h->lastPending) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(h->evLast);
+    if (e == cudaSuccess) h->lastPending = false;
+    return e;
+}
 
 // constructor tables, orbextractor.cpp:492-547
 void buildTables(orbx_extractor *h)
@@ -401,6 +421,7 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         }
     }
     CK(h->dTmaps.ensure(5));
+    CK(drainLast(h));
     for (int i = 0; i < ORBX_LANES; i++) {
         CK(cudaStreamSynchronize(h->lane[i].main));
         CK(cudaStreamSynchronize(h->lane[i].side));
@@ -420,17 +441,26 @@ int setGeometry(orbx_extractor *h, int w, int hh)
     OrbxLayout L; std::vector<OrbxSeg> segs; std::vector<OrbxRTab> rtab; std::vector<OrbxTile> tiles; int maxRows, maxNodes, winRows, listCap;
     int rc = buildGeometry(h, w, hh, L, segs, rtab, tiles, maxRows, maxNodes, winRows, listCap);
     if (rc != ORBX_OK) return rc;
+    // everything that can reject the shape is checked BEFORE the handle's geometry is touched: a refused size leaves the
+    // previous one fully usable
+    if (octree_smem_bytes(maxRows, maxNodes) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
+    // in-flight work (the handle's lanes, a caller's stream of the last device-resident call) may still read the old tables
+    CK(drainLast(h));
+    for (int i = 0; i < ORBX_LANES; i++) {
+        CK(cudaStreamSynchronize(h->lane[i].main));
+        CK(cudaStreamSynchronize(h->lane[i].side));
+    }
+    // from here on the handle describes no size until the new tables are on the device: a failure below (out of memory)
+    // cannot leave the old curW / curH paired with the new layout
+    h->geomUploaded = false; h->curW = 0; h->curH = 0;
     h->L = L; h->segs.swap(segs); h->rtab.swap(rtab); h->tiles.swap(tiles);
     h->maxRows = maxRows; h->maxNodes = maxNodes;
     h->fastWinRows = winRows; h->fastListCap = listCap;
     int p2 = 2; while (p2 < maxNodes) p2 <<= 1;
     h->pow2Nodes = p2;
-    if (octree_smem_bytes(maxRows, maxNodes) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
     CK(h->dSegs.ensure(h->segs.size()));
     CK(h->dRtab.ensure(std::max<size_t>(h->rtab.size(), 1)));
     CK(h->dTiles.ensure(h->tiles.size()));
-    // the stream may still be reading the old tables
-    CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpyAsync(h->dSegs.p, h->segs.data(), h->segs.size() * sizeof(OrbxSeg), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dTiles.p, h->tiles.data(), h->tiles.size() * sizeof(OrbxTile), cudaMemcpyHostToDevice, h->stream));
     if (!h->rtab.empty())
@@ -589,6 +619,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     h->stream = h->lane[0].main;
     CK(cudaStreamCreateWithFlags(&h->streamIn, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->streamOut, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->evLast, cudaEventDisableTiming));
     // size the arenas for the declared maximum so the hot path never allocates
     int rc = setGeometry(h, cfg->max_width, cfg->max_height);
     if (rc != ORBX_OK) return rc;
@@ -610,6 +641,7 @@ void orbx_destroy(orbx_extractor *h)
     }
     if (h->streamIn) cudaStreamSynchronize(h->streamIn);
     if (h->streamOut) cudaStreamSynchronize(h->streamOut);
+    if (h->evLast) { if (h->lastPending) cudaEventSynchronize(h->evLast); cudaEventDestroy(h->evLast); }
     dropGraphs(h);
     for (cudaEvent_t e : h->evChunk) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->evTrace) if (e) cudaEventDestroy(e);
@@ -661,13 +693,18 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     rc = ensureArenas(h, batch);
     if (rc != ORBX_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(orderAfterLast(h, st));        // the arenas are reused: a previous call on another stream must have finished with them
     h->lastBatch = batch;
     h->lastLaunches = 0;
     static const int splitEnv = getenv("ORBX_SPLIT") ? atoi(getenv("ORBX_SPLIT")) : 0;
     const int nSplit = std::min(batch, splitEnv > 0 ? std::min(splitEnv, ORBX_LANES) : (batch >= 16 ? 2 : 1));
     if (nSplit == 1) {
         launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
-        return enqueuePipeline(h, 0, batch, st, h->lane[0]);
+        rc = enqueuePipeline(h, 0, batch, st, h->lane[0]);
+        if (rc != ORBX_OK) return rc;
+        CK(cudaEventRecord(h->evLast, st));
+        h->lastPending = true;
+        return ORBX_OK;
     }
     // nSplit parts side by side: the first on the caller's stream, the others on lanes 1.., joined back at the end
     CK(cudaEventRecord(h->lane[0].evStart, st));
@@ -684,6 +721,8 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
             CK(cudaStreamWaitEvent(st, ln.evDone, 0));
         }
     }
+    CK(cudaEventRecord(h->evLast, st));
+    h->lastPending = true;
     return ORBX_OK;
 }
 
@@ -712,6 +751,7 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     struct timespec tsB;
     clock_gettime(CLOCK_MONOTONIC, &tsB);
     CK(cudaSetDevice(h->cfg.device));
+    CK(drainLast(h));                 // a device-resident call on a caller's stream may still be using the arenas
     int rc = setGeometry(h, width, height);
     if (rc != ORBX_OK) return rc;
     rc = ensureArenas(h, batch);
@@ -866,6 +906,7 @@ int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int 
     const OrbxLayout &L = h->L;
     const int batch = h->lastBatch;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    CK(orderAfterLast(h, st));
     CK(h->hKps.ensure((size_t)L.kpStride * batch));
     CK(h->hDesc.ensure((size_t)L.kpStride * batch * 32));
     CK(h->hCounts.ensure((size_t)batch));
@@ -892,6 +933,7 @@ int orbx_filter_keypoints(orbx_extractor *h, int frame0, int n_frames, const flo
     if (!box || n_frames < 1 || frame0 < 0 || frame0 + n_frames > h->lastBatch) return fail(h, ORBX_ERR_ARG, "bad argument or no previous extraction");
     if (!(box[1] > 2.0f)) return ORBX_OK;                 // orbframe.cpp:405: no bounding box configured, nothing is filtered
     CK(cudaSetDevice(h->cfg.device));
+    CK(orderAfterLast(h, h->stream));
     CK(launch_filter_keypoints(h->dKps.p, h->dDesc.p, h->dCounts.p, h->L.kpStride, frame0, n_frames, box, h->stream));
     return ORBX_OK;
 }
@@ -911,8 +953,9 @@ int orbx_stereo_match(orbx_extractor *left, int frame_left, orbx_extractor *righ
     CK(h->dStereo.ensure((size_t)2 * L.kpStride));
     CK(h->dStereoI.ensure((size_t)L.kpStride + 1));
     CK(h->hStereo.ensure((size_t)2 * L.kpStride + 2));
-    if (right != left) CK(cudaStreamSynchronize(right->stream));
+    if (right != left) { CK(drainLast(right)); CK(cudaStreamSynchronize(right->stream)); }
     cudaStream_t st = left->stream;
+    CK(orderAfterLast(left, st));
     const float maxD = mbf / mb;            // orbframe.cpp:545-547 (minZ = mb; +inf when mb is still 0)
     float *dU = h->dStereo.p, *dD = h->dStereo.p + L.kpStride;
     int *dSad = h->dStereoI.p, *dN = h->dStereoI.p + L.kpStride;
@@ -950,6 +993,7 @@ int orbx_stereo_match_batch(orbx_extractor *h, int n_pairs, int frame_left0, int
     CK(h->dStereoI.ensure(rows + n_pairs));
     CK(h->hStereo.ensure(2 * rows + 2));
     cudaStream_t st = h->stream;
+    CK(orderAfterLast(h, st));
     const float maxD = mbf / mb;
     float *dU = h->dStereo.p, *dD = h->dStereo.p + rows;
     int *dSad = h->dStereoI.p, *dN = h->dStereoI.p + rows;
@@ -990,6 +1034,7 @@ int orbx_get_level(orbx_extractor *h, int frame, int level, const uint8_t **host
     // one pinned buffer holding all levels of all frames of the last call, filled lazily per level
     CK(h->hLevel.ensure((size_t)h->L.slab * h->cfg.max_batch));
     uint8_t *dst = h->hLevel.p + (size_t)frame * h->L.slab + l.off;
+    CK(orderAfterLast(h, h->stream));
     CK(cudaMemcpyAsync(dst, h->dPyr.p + (size_t)frame * h->L.slab + l.off, (size_t)l.pitch * l.h, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *host_ptr = dst;
@@ -1007,6 +1052,7 @@ int orbx_debug_blurred(orbx_extractor *h, int frame, int level, uint8_t *dst, si
     const OrbxLevel &l = h->L.lv[level];
     if (dst_bytes < (size_t)l.w * l.h) return fail(h, ORBX_ERR_CAPACITY, "dst too small");
     CK(cudaSetDevice(h->cfg.device));
+    CK(drainLast(h));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy2D(dst, l.w, h->dBlur.p + (size_t)frame * h->L.slab + l.off, l.pitch, l.w, l.h, cudaMemcpyDeviceToHost));
     if (width) *width = l.w;
@@ -1025,6 +1071,7 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
     const OrbxLayout &L = h->L;
     const int batch = h->lastBatch;
     cudaStream_t st = h->stream;
+    CK(drainLast(h));
     cudaEvent_t ev[6];
     for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
@@ -1062,6 +1109,7 @@ int orbx_debug_candidates(orbx_extractor *h, int frame, int level, int *xs, int 
     if (!h->dbgEnabled || !h->dDbg.p || frame < 0 || frame >= h->lastBatch || level < 0 || level >= h->L.nlevels)
         return fail(h, ORBX_ERR_ARG, "candidate recording not enabled or bad frame/level");
     CK(cudaSetDevice(h->cfg.device));
+    CK(drainLast(h));
     CK(cudaStreamSynchronize(h->stream));
     const int slot = frame * h->L.nlevels + level;
     int n = 0;

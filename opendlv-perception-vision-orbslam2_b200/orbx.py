@@ -87,7 +87,7 @@ def lib():
     L.orbm_distance_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp]
     L.orbm_assign_grid.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp]
     L.orbm_area_distances.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.POINTER(C.c_int32)]
-    L.orbm_search_by_projection.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_int32)]
+    L.orbm_search_by_projection.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp, vp, C.POINTER(C.c_int32)]
     L.orbm_distinctive.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.orbv_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
     L.orbv_destroy.argtypes = [vp]
@@ -330,10 +330,11 @@ class Matcher:
         return dist
 
     def search_by_projection(self, keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp_y, mp_level, mp_radius,
-                             nnratio=0.8, th_high=100):
+                             nnratio=0.8, th_high=100, mp_observed=None):
         """ORBmatcher::SearchByProjection(frame, map points, th) with the frame grid (AssignFeaturesToGrid,
         GetFeaturesInArea) on the device -> (mp_match[n_mp], assigned[n_keypoints], nmatches).  keys: KP_DTYPE records
-        (m_undistortedKeys), bounds = (m_minX, m_minY, m_maxX, m_maxY), mp_radius = r * scaleFactor[level]."""
+        (m_undistortedKeys), bounds = (m_minX, m_minY, m_maxX, m_maxY), mp_radius = r * scaleFactor[level], mp_observed[i] != 0
+        where map point i has observations (it then hides the key point it is stored on from the map points after it)."""
         keys = np.ascontiguousarray(keys, KP_DTYPE); uright = np.ascontiguousarray(uright, np.float32)
         occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
         desc = np.ascontiguousarray(desc, np.uint8); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
@@ -343,9 +344,10 @@ class Matcher:
         view = FrameView(keys.ctypes.data if n else None, uright.ctypes.data if n else None, None if occ is None or not n else occ.ctypes.data,
                          desc.ctypes.data if n else None, n, *[float(v) for v in bounds])
         match = np.zeros(nmp, np.int32); assigned = np.zeros(max(n, 1), np.int32); nm = C.c_int32()
+        obs = None if mp_observed is None else np.ascontiguousarray(mp_observed, np.uint8)
         self._check(lib().orbm_search_by_projection(self._h, C.byref(view), _ptr(mp_desc), _ptr(mp_x), _ptr(mp_y), _ptr(mp_level),
-                                                    _ptr(mp_radius), nmp, C.c_float(nnratio), int(th_high), _ptr(match), _ptr(assigned),
-                                                    C.byref(nm)))
+                                                    _ptr(mp_radius), None if obs is None else _ptr(obs), nmp, C.c_float(nnratio),
+                                                    int(th_high), _ptr(match), _ptr(assigned), C.byref(nm)))
         return match, assigned[:n], nm.value
 
     def assign_grid(self, keys, bounds):

@@ -71,17 +71,23 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
         // ---------------- part 1
         {
             std::vector<std::shared_ptr<OrbMapPoint>> mps;
-            for (int i = 0; i < A->N; i++) {
-                cv::Mat pos(3, 1, CV_32F);
-                pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
-                auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
-                mp->SetTrackInView(i % 13 != 0);                                  // some points are not in view (:51)
-                mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
-                mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
-                mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
-                mp->SetTrackViewCos((i & 1) ? 0.9f : 0.9995f);
-                mps.push_back(mp);
-            }
+            // As in Tracking::SearchLocalPoints the map points carry observations (three out of four here), so the rule of
+            // :87-89 is live INSIDE the call: a map point stored at :121 hides its key point from the ones after it.  Every
+            // third key point of A yields a second, identical map point right behind the first: the two collide on one key
+            // point of B, and the twin has to settle for another key point or for none.
+            for (int i = 0; i < A->N; i++)
+                for (int twin = 0; twin < (i % 3 == 0 ? 2 : 1); twin++) {
+                    cv::Mat pos(3, 1, CV_32F);
+                    pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
+                    auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
+                    mp->SetTrackInView(i % 13 != 0);                              // some points are not in view (:51)
+                    mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
+                    mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
+                    mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
+                    mp->SetTrackViewCos((i & 1) ? 0.9f : 0.9995f);
+                    if (mps.size() % 4 != 1) mp->AddObservingKeyframe(kf, 1);
+                    mps.push_back(mp);
+                }
             for (int idx = 0; idx < B->N; idx++)
                 if (idx % 7 == 3 || idx % 11 == 5) {
                     auto held = std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>());

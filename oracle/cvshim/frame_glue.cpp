@@ -150,7 +150,8 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
                                   int *n_mp_out, uint8_t *mp_desc, float *mp_x, float *mp_radius,
                                   int *n_b_out, uint8_t *b_desc, int32_t *b_octave, float *b_uright, int32_t *b_occupied,
                                   int32_t *offsets, int32_t *indices, int32_t *assigned,
-                                  orbo_keypoint *b_keys, float *mp_y, int32_t *mp_level, float *bounds)
+                                  orbo_keypoint *b_keys, float *mp_y, int32_t *mp_level, float *bounds,
+                                  int mp_dup, int obs_mod, uint8_t *mp_observed)
 {
     std::streambuf *old = std::cout.rdbuf();
     std::ostringstream sink;
@@ -164,17 +165,21 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
         for (int i = 0; i < 16; i++) Tcw.ptr<float>(i / 4)[i % 4] = (i % 5 == 0) ? 1.f : 0.f;
         A->SetPose(Tcw);
         std::vector<std::shared_ptr<OrbMapPoint>> mps;
-        for (int i = 0; i < A->N; i += mp_step) {
-            cv::Mat pos(3, 1, CV_32F);
-            pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
-            auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
-            mp->SetTrackInView(true);
-            mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
-            mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
-            mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
-            mp->SetTrackViewCos((mps.size() & 1) ? 0.9f : 0.9995f);
-            mps.push_back(mp);
-        }
+        for (int i = 0; i < A->N; i += mp_step)
+            for (int d = 0; d < (mp_dup > 1 ? mp_dup : 1); d++) {
+                cv::Mat pos(3, 1, CV_32F);
+                pos.ptr<float>(0)[0] = 0.f; pos.ptr<float>(1)[0] = 0.f; pos.ptr<float>(2)[0] = 5.f;
+                auto mp = std::make_shared<OrbMapPoint>(pos, A, std::shared_ptr<OrbMap>(), i);
+                mp->SetTrackInView(true);
+                mp->SetTrackProjX(A->m_undistortedKeys[i].pt.x + dx);
+                mp->SetTrackProjY(A->m_undistortedKeys[i].pt.y + dy);
+                mp->SetnTrackScaleLevel(A->m_undistortedKeys[i].octave);
+                mp->SetTrackViewCos(((mps.size() / (mp_dup > 1 ? mp_dup : 1)) & 1) ? 0.9f : 0.9995f);
+                // observed map points (every local map point of Tracking::SearchLocalPoints is one): the rule of :87-89 is
+                // live INSIDE the call -- once stored at :121 they hide their key point from the map points after them
+                if (obs_mod > 0 && mps.size() % (size_t)obs_mod != 0) mp->AddObservingKeyframe(kf, 1);
+                mps.push_back(mp);
+            }
         std::shared_ptr<OrbFrame> B = frameref_make_frame(c, leftB, rightB, w, h, mbf, mb);
         const int nb = B->N, nmp = (int)mps.size();
         *n_mp_out = nmp; *n_b_out = nb;
@@ -205,6 +210,7 @@ int frameref_search_by_projection(const frameref_cfg *c, int canonical, const ui
                 float r = mps[i]->GTrackViewCos() > 0.998 ? 2.5f : 4.0f;         // RadiusByViewingCos, :126-131
                 if (bFactor) r *= th;                                            // :61-62
                 mp_x[i] = mps[i]->getTrackProjX(); mp_y[i] = mps[i]->getTrackProjY(); mp_level[i] = level;
+                mp_observed[i] = mps[i]->GetObservingKeyFrameCount() > 0;
                 mp_radius[i] = r * B->m_scaleFactors[level];
                 const std::vector<size_t> v = B->GetFeaturesInArea(mps[i]->getTrackProjX(), mps[i]->getTrackProjY(),
                                                                    r * B->m_scaleFactors[level], level - 1, level);

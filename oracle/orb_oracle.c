@@ -969,9 +969,14 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
 int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, const uint8_t *occupied, const uint8_t *desc, int n,
                               float min_x, float min_y, float max_x, float max_y,
                               const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
-                              const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned)
+                              const float *mp_radius, const uint8_t *mp_observed, int n_mp, float nnratio, int th_high,
+                              int32_t *mp_match, int32_t *assigned)
 {
     const float invW = (float)OG_COLS / (max_x - min_x), invH = (float)OG_ROWS / (max_y - min_y);   /* orbframe.cpp:179-180 */
+    /* live copy of "F->m_mapPoints[idx] is set and has observations" (orbmatcher.cpp:87-89): the loop is sequential, an accepted
+     * map point is stored at once (:121) and, when it has observations (mp_observed[i]), hides its key point from later ones */
+    uint8_t *occ = calloc(n > 0 ? n : 1, 1);
+    if (occupied) memcpy(occ, occupied, (size_t)n);
     /* AssignFeaturesToGrid: m_grid[ix][iy] lists in key-point order, :202-209 */
     int *count = calloc(OG_COLS * OG_ROWS + 1, sizeof(int)), *cell = malloc(sizeof(int) * (n > 0 ? n : 1));
     for (int i = 0; i < n; i++) {
@@ -1009,7 +1014,7 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
                     }
                     const float distx = keys[idx].x - x, disty = keys[idx].y - y;
                     if (!(fabs(distx) < r && fabs(disty) < r)) continue;               /* :370 */
-                    if (occupied && occupied[idx]) continue;                           /* orbmatcher.cpp:87-89 */
+                    if (occ[idx]) continue;                                            /* orbmatcher.cpp:87-89 */
                     if (uright[idx] > 0) {
                         const float er = (float)fabs(x - uright[idx]);                 /* :93 */
                         if (er > r) continue;
@@ -1024,10 +1029,12 @@ int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, co
         if (bestDist <= th_high) {                                                     /* :116-123 */
             if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
             mp_match[i] = bestIdx;
-            assigned[bestIdx] = i;
+            assigned[bestIdx] = i;                                                     /* :121 */
+            occ[bestIdx] = (uint8_t)(mp_observed ? (mp_observed[i] != 0) : 0);         /* what :87-89 sees from now on */
             nmatches++;
         }
     }
+    free(occ);
     free(count); free(cell); free(fill); free(items);
     return nmatches;
 }

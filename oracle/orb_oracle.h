@@ -127,11 +127,14 @@ void orbo_knn2(const uint8_t *q, int nq, const uint8_t *t, int nt,
 void orbo_knn2_csr(const uint8_t *q, int nq, const uint8_t *t, const int32_t *offsets, const int32_t *indices,
                    int32_t *idx1, int32_t *d1, int32_t *idx2, int32_t *d2);
 /* ORBmatcher::SearchByProjection(frame, map points, th) (orbmatcher.cpp:42-124) including the frame's grid
- * (orbframe.cpp:192-211, :308-393); mp_radius[i] = r * scaleFactor[level] as the caller forms it.  Returns nmatches. */
+ * (orbframe.cpp:192-211, :308-393); mp_radius[i] = r * scaleFactor[level] as the caller forms it.  mp_observed[i] != 0: map
+ * point i has GetObservingKeyFrameCount() > 0, so once accepted it hides its key point from the later map points of the same
+ * call (the loop is sequential: :121 stores it, :87-89 tests it); NULL = none has.  Returns nmatches. */
 int orbo_search_by_projection(const orbo_keypoint *keys, const float *uright, const uint8_t *occupied, const uint8_t *desc, int n,
                               float min_x, float min_y, float max_x, float max_y,
                               const uint8_t *mp_desc, const float *mp_x, const float *mp_y, const int32_t *mp_level,
-                              const float *mp_radius, int n_mp, float nnratio, int th_high, int32_t *mp_match, int32_t *assigned);
+                              const float *mp_radius, const uint8_t *mp_observed, int n_mp, float nnratio, int th_high,
+                              int32_t *mp_match, int32_t *assigned);
 /* OrbFrame::FilterKeyPoints (orbframe.cpp:403-445), in place; returns the new count */
 int orbo_filter_keypoints(orbo_keypoint *keys, uint8_t *desc, int n, const float box[4]);
 /* OrbFrame::AssignFeaturesToGrid (orbframe.cpp:192-211) as CSR over 64 x 48 cells (cell = ix * 48 + iy) */

@@ -305,8 +305,10 @@ def ref_distinctive(desc, offsets, indices, bad=None):
     return out, has
 
 
-def search_by_projection(keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp_y, mp_level, mp_radius, nnratio=0.8, th_high=100):
-    """ORBmatcher::SearchByProjection(frame, map points, th) with the frame grid -> (mp_match, assigned, nmatches)."""
+def search_by_projection(keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp_y, mp_level, mp_radius, nnratio=0.8, th_high=100,
+                         mp_observed=None):
+    """ORBmatcher::SearchByProjection(frame, map points, th) with the frame grid -> (mp_match, assigned, nmatches).
+    mp_observed[i] != 0: map point i has observations, so once accepted it hides its key point from later map points."""
     keys = np.ascontiguousarray(keys); uright = np.ascontiguousarray(uright, np.float32)
     occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
     desc = np.ascontiguousarray(desc, np.uint8); mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
@@ -316,9 +318,11 @@ def search_by_projection(keys, uright, occupied, desc, bounds, mp_desc, mp_x, mp
     match = np.empty(nmp, np.int32); assigned = np.empty(max(n, 1), np.int32)
     f = lib().orbo_search_by_projection
     f.restype = C.c_int
-    f.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 5 + [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    f.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p] * 6 + [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    obs = None if mp_observed is None else np.ascontiguousarray(mp_observed, np.uint8)
     nm = f(_ptr(keys), _ptr(uright), None if occ is None else _ptr(occ), _ptr(desc), n, *[float(v) for v in bounds],
-           _ptr(mp_desc), _ptr(mp_x), _ptr(mp_y), _ptr(mp_level), _ptr(mp_radius), nmp, float(nnratio), int(th_high), _ptr(match), _ptr(assigned))
+           _ptr(mp_desc), _ptr(mp_x), _ptr(mp_y), _ptr(mp_level), _ptr(mp_radius), None if obs is None else _ptr(obs), nmp,
+           float(nnratio), int(th_high), _ptr(match), _ptr(assigned))
     return match, assigned[:n], nm
 
 
@@ -370,20 +374,25 @@ def ref_descriptor_distance(a, b):
 
 
 def ref_search_by_projection(pairA, pairB, mbf, mb, th=3.0, nnratio=0.8, mp_step=1, dx=0.0, dy=0.0,
-                             nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1):
+                             nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, canonical=1, mp_dup=1, obs_mod=0):
     """The reference's own ORBmatcher::SearchByProjection(frame, map points, th) (src/orbmatcher.cpp:42-124 compiled
     unmodified into oracle/_ref/libframeref.so) on two reference OrbFrames; see oracle/cvshim/frame_glue.cpp.
-    -> dict(mp_desc, mp_x, mp_y, mp_level, mp_radius, b_keys, b_desc, b_octave, b_uright, b_occupied, bounds, offsets, indices,
-    assigned, nmatches)."""
+    mp_dup map points per key point of A (copies of one another: they collide on the same key point of B); with obs_mod > 0
+    map point k carries an observation (AddObservingKeyframe) unless k % obs_mod == 0, which makes the rule of :87-89 live
+    inside the call.
+    -> dict(mp_desc, mp_x, mp_y, mp_level, mp_radius, mp_observed, b_keys, b_desc, b_octave, b_uright, b_occupied, bounds,
+    offsets, indices, assigned, nmatches)."""
     class Cfg(C.Structure):
         _fields_ = [("nfeatures", C.c_int), ("scale", C.c_float), ("nlevels", C.c_int), ("ini", C.c_int), ("min", C.c_int)]
     R = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libframeref.so"))
     R.frameref_search_by_projection.restype = C.c_int
     R.frameref_search_by_projection.argtypes = [C.POINTER(Cfg), C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + \
-        [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int] + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)] + [C.c_void_p] * 11
+        [C.c_int, C.c_float, C.c_float, C.c_int, C.c_int] + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)] + [C.c_void_p] * 11 + \
+        [C.c_int, C.c_int, C.c_void_p]
     imgs = [np.ascontiguousarray(a, np.uint8) for a in (*pairA, *pairB)]
     h, w = imgs[0].shape
-    cap, list_cap = nfeatures + 512, 1 << 22
+    cap, list_cap = (nfeatures + 512) * max(1, int(mp_dup)), 1 << 22
+    mp_obs = np.zeros(cap, np.uint8)
     mp_desc = np.zeros((cap, 32), np.uint8); mp_x = np.zeros(cap, np.float32); mp_r = np.zeros(cap, np.float32)
     b_desc = np.zeros((cap, 32), np.uint8); b_oct = np.zeros(cap, np.int32); b_ur = np.zeros(cap, np.float32)
     b_occ = np.zeros(cap, np.int32); offsets = np.zeros(cap + 1, np.int32); indices = np.zeros(list_cap, np.int32)
@@ -393,14 +402,16 @@ def ref_search_by_projection(pairA, pairB, mbf, mb, th=3.0, nnratio=0.8, mp_step
     nm = R.frameref_search_by_projection(C.byref(Cfg(nfeatures, scale_factor, nlevels, ini_th, min_th)), int(canonical), *[_ptr(a) for a in imgs], w, h,
                                          float(mbf), float(mb), float(th), float(nnratio), int(mp_step), float(dx), float(dy), cap, list_cap,
                                          C.byref(nmp), _ptr(mp_desc), _ptr(mp_x), _ptr(mp_r), C.byref(nb), _ptr(b_desc), _ptr(b_oct),
-                                         _ptr(b_ur), _ptr(b_occ), _ptr(offsets), _ptr(indices), _ptr(assigned), _ptr(b_keys), _ptr(mp_y), _ptr(mp_level), _ptr(bounds))
+                                         _ptr(b_ur), _ptr(b_occ), _ptr(offsets), _ptr(indices), _ptr(assigned), _ptr(b_keys), _ptr(mp_y), _ptr(mp_level), _ptr(bounds),
+                                         int(mp_dup), int(obs_mod), _ptr(mp_obs))
     if nm < 0:
         raise RuntimeError("frameref_search_by_projection: output buffers too small")
     nmp, nb = nmp.value, nb.value
     return dict(mp_desc=mp_desc[:nmp].copy(), mp_x=mp_x[:nmp].copy(), mp_radius=mp_r[:nmp].copy(), b_desc=b_desc[:nb].copy(),
                 b_octave=b_oct[:nb].copy(), b_uright=b_ur[:nb].copy(), b_occupied=b_occ[:nb].copy(), offsets=offsets[:nmp + 1].copy(),
                 indices=indices[:offsets[nmp]].copy(), assigned=assigned[:nb].copy(), nmatches=nm,
-                b_keys=b_keys[:nb].copy(), mp_y=mp_y[:nmp].copy(), mp_level=mp_level[:nmp].copy(), bounds=bounds)
+                b_keys=b_keys[:nb].copy(), mp_y=mp_y[:nmp].copy(), mp_level=mp_level[:nmp].copy(), bounds=bounds,
+                mp_observed=mp_obs[:nmp].copy())
 
 
 def transform4(child_off, child_ids, node_desc, word_id, weight, L, levels_up, feat):

@@ -113,7 +113,7 @@ int main(int argc, char **argv)
             fwrite(best.data(), 4, 3, o);
             // SearchByProjection adapter: every second key point of the frame projected 1.25 px to the right of itself
             std::vector<float> uR(n, -1.f), px, py, rad;
-            std::vector<unsigned char> occ(n, 0);
+            std::vector<unsigned char> occ(n, 0), obs;
             std::vector<int> lvl, pm, asg;
             cv::Mat pd(n / 2, 32, CV_8U);
             for (int i = 0; i + 1 < n; i += 2) {
@@ -121,8 +121,9 @@ int main(int argc, char **argv)
                 px.push_back(keys[i].pt.x + 1.25f); py.push_back(keys[i].pt.y); lvl.push_back(keys[i].octave);
                 rad.push_back(4.0f * sf[keys[i].octave]);
                 if (i % 10 == 0) occ[i] = 1;
+                obs.push_back((i / 2) % 3 != 0);       // two map points out of three carry observations (orbmatcher.cpp:87-89 after :121)
             }
-            int nm = hm2.SearchByProjection(keys, uR, occ, desc, 0.f, 0.f, (float)w, (float)h, pd, px, py, lvl, rad, 0.8f, 100, pm, asg);
+            int nm = hm2.SearchByProjection(keys, uR, occ, desc, 0.f, 0.f, (float)w, (float)h, pd, px, py, lvl, rad, obs, 0.8f, 100, pm, asg);
             fwrite(&nm, 4, 1, o); fwrite(asg.data(), 4, n, o);
             // GetFeaturesInArea adapter: the same windows at levels [l-1, l]; lists in the reference's order + distances
             std::vector<int> l0(lvl), aoff, aind, adist;

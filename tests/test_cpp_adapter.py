@@ -99,7 +99,8 @@ def test_adapter_end_to_end(tmp_path, oracle):
     occ = np.zeros(n, np.uint8); occ[src[src % 10 == 0]] = 1
     om, oa, onm = oracle.search_by_projection(kps, np.full(n, -1, np.float32), occ, desc, (0.0, 0.0, float(w), float(h)), desc[src],
                                               kps["x"][src] + np.float32(1.25), kps["y"][src], kps["octave"][src],
-                                              np.float32(4.0) * sf[kps["octave"][src]], 0.8, 100)
+                                              np.float32(4.0) * sf[kps["octave"][src]], 0.8, 100,
+                                              mp_observed=(np.arange(len(src)) % 3 != 0).astype(np.uint8))
     assert nm == onm and nm > 100 and np.array_equal(asg, oa)
     # ---- GetFeaturesInArea adapter
     nq, total = struct.unpack_from("<ii", b, o); o += 8

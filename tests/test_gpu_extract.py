@@ -278,6 +278,72 @@ def test_device_batch_split_in_halves(oracle):
     ex.close()
 
 
+def test_device_call_on_a_caller_stream_orders_later_entry_points(oracle):
+    """orbx_extract_batch_device enqueues on the caller's stream and returns at once; the library entry points that read
+    "the last extraction" on the handle's own stream (fetch with stream = NULL, filter, stereo, pyramid levels, the next
+    extraction -- host or device, other stream, other size) order themselves behind it.  The caller's stream is kept busy in
+    front of the extraction so that an unordered reader would run far too early."""
+    import torch
+    import orbx
+    cfg = CONFIGS["kitti"]
+    w, h = cfg["w"], cfg["h"]
+    imgs = synth.stereo_batch(7, w, h, 4)
+    ex = _mk(orbx, cfg, batch=8)
+    kh, dh, ch = ex.extract_batch(imgs)
+    lvl2 = ex.level(3, 2).copy()
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    big = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+    st, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def busy_then_extract(stream):
+        with torch.cuda.stream(stream):
+            for _ in range(20):
+                big.add_(1)                                   # ~2 ms of queued work in front of the extraction
+        ex.extract_batch_device(d.data_ptr(), w * h, w, 8, w, h, stream.cuda_stream)
+
+    busy_then_extract(st)
+    kps, desc, cnt = ex.fetch_results(8, None)                # the handle's own stream, not the caller's
+    assert np.array_equal(cnt, ch)
+    for f in range(8):
+        n = int(cnt[f])
+        assert kps[f][:n].tobytes() == kh[f][:n].tobytes() and np.array_equal(desc[f][:n], dh[f][:n])
+    busy_then_extract(st)
+    assert np.array_equal(ex.level(3, 2), lvl2)
+    busy_then_extract(st)
+    ur, dep, nl, nm = orbx.stereo_match_batch(ex, 4, 0, 1, 2, 386.1448, 0.5372)
+    ex.extract_batch(imgs)
+    ur2, dep2, nl2, nm2 = orbx.stereo_match_batch(ex, 4, 0, 1, 2, 386.1448, 0.5372)
+    assert np.array_equal(nl, nl2) and np.array_equal(nm, nm2) and np.array_equal(ur, ur2) and np.array_equal(dep, dep2)
+    # the next extraction on ANOTHER stream reuses the arenas: it must wait for the first one
+    busy_then_extract(st)
+    ex.extract_batch_device(d.data_ptr(), w * h, w, 8, w, h, st2.cuda_stream)
+    kps, desc, cnt = ex.fetch_results(8, st2.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(cnt, ch) and all(kps[f][:int(cnt[f])].tobytes() == kh[f][:int(cnt[f])].tobytes() for f in range(8))
+    # a host call of another size right behind a device call: geometry tables are replaced only after the kernels are done
+    busy_then_extract(st)
+    small = synth.frames(3, 640, 360, 2)
+    ks, ds, cs = ex.extract_batch(small)
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    _compare_frame(oracle, ex, oex, small[1], 1, ks[1], ds[1], int(cs[1]), stages=False)
+    torch.cuda.synchronize()
+    ex.close()
+
+
+def test_refused_geometry_leaves_the_handle_usable(oracle):
+    """A size the library refuses (portrait: the reference divides by zero) must not disturb the geometry in place."""
+    import orbx
+    cfg = CONFIGS["small"]
+    ex = _mk(orbx, cfg, batch=2)
+    imgs = synth.frames(12, cfg["w"], cfg["h"], 2)
+    k0, d0, c0 = ex.extract_batch(imgs)
+    with pytest.raises(orbx.OrbxError):
+        ex.extract_batch([np.zeros((cfg["h"], 120), np.uint8)])
+    k1, d1, c1 = ex.extract_batch(imgs)
+    assert np.array_equal(c0, c1) and k0.tobytes() == k1.tobytes() and np.array_equal(d0, d1)
+    ex.close()
+
+
 def test_alternating_sizes_and_batches_on_one_handle(oracle):
     """One handle fed frames of different sizes and batch sizes in turn: geometry tables, tensor maps and the captured
     chunk graphs must follow every change."""

@@ -177,6 +177,59 @@ def test_search_by_projection_vs_reference_fixture():
         m.close()
 
 
+def test_search_by_projection_sequential_rule_vs_reference_fixture(oracle):
+    """tests/golden/ref_projection_observed.npz: the reference's own function with observed map points and colliding twins,
+    so that a map point stored at orbmatcher.cpp:121 hides its key point from later ones (:87-89).  orbm_search_by_projection
+    iterates that rule to its fixpoint on the device and reproduces m_mapPoints / nmatches; the oracle agrees entry by entry."""
+    import os
+    import orbx
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_projection_observed.npz"))
+    for c, case in enumerate(g["cases"]):
+        r = {k: g[f"{k}_{c}"] for k in ("mp_desc", "mp_x", "mp_y", "mp_level", "mp_radius", "mp_observed", "b_keys", "b_desc", "b_uright",
+                                        "b_occupied", "bounds", "assigned")}
+        ref, nref = r["assigned"], int(g[f"nmatches_{c}"])
+        keys = r["b_keys"].view(orbx.KP_DTYPE).reshape(-1)
+        m = orbx.Matcher(max_queries=len(r["mp_desc"]), max_train=len(r["b_desc"]))
+        args = (keys, r["b_uright"], r["b_occupied"], r["b_desc"], r["bounds"], r["mp_desc"], r["mp_x"], r["mp_y"], r["mp_level"], r["mp_radius"],
+                float(case[7]), 100)
+        match, asg, nm = m.search_by_projection(*args, mp_observed=r["mp_observed"])
+        om, oa, on = oracle.search_by_projection(*args, mp_observed=r["mp_observed"])
+        assert nm == on and np.array_equal(match, om) and np.array_equal(asg, oa)
+        asg[(asg == -1) & (ref == -2)] = -2
+        assert nm == nref and np.array_equal(asg, ref) and int((match >= 0).sum()) == nref
+        m.close()
+
+
+@pytest.mark.parametrize("n,nmp,w,h,frac", [(2000, 4000, 1241, 376, 0.8), (500, 3000, 320, 240, 1.0), (3000, 1500, 1920, 1080, 0.3), (60, 2000, 200, 120, 1.0)])
+def test_search_by_projection_sequential_rule_vs_oracle(oracle, n, nmp, w, h, frac):
+    """Dense collisions: many more map points than key points, most of them observed, long dependency chains (a map point
+    pushed off its key point takes the next one, which pushes the next map point ...).  The device fixpoint equals the
+    sequential restatement entry by entry."""
+    import orbx
+    rng = np.random.default_rng(n + nmp)
+    keys = np.zeros(n, orbx.KP_DTYPE)
+    keys["x"] = rng.uniform(0, w, n).astype(np.float32); keys["y"] = rng.uniform(0, h, n).astype(np.float32)
+    keys["octave"] = rng.integers(0, 4, n)
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    ur = np.where(rng.random(n) < 0.5, keys["x"] - rng.uniform(0, 30, n).astype(np.float32), -1).astype(np.float32)
+    occ = (rng.random(n) < 0.1).astype(np.uint8)
+    src = rng.integers(0, n, nmp)
+    mp_desc = desc[src].copy()
+    flips = rng.integers(0, 256, (nmp, 32), dtype=np.uint8) & rng.integers(0, 256, (nmp, 32), dtype=np.uint8) & rng.integers(0, 256, (nmp, 32), dtype=np.uint8)
+    mp_desc ^= flips                                                   # ~32 bit flips: under TH_HIGH, ties and near-ties are common
+    mp_x = (keys["x"][src] + rng.uniform(-3, 3, nmp)).astype(np.float32); mp_y = (keys["y"][src] + rng.uniform(-3, 3, nmp)).astype(np.float32)
+    mp_level = np.minimum(keys["octave"][src] + rng.integers(0, 2, nmp), 7).astype(np.int32)
+    mp_radius = (np.float32(12.0) * np.float32(1.2) ** mp_level).astype(np.float32)
+    obs = (rng.random(nmp) < frac).astype(np.uint8)
+    m = orbx.Matcher(max_queries=nmp, max_train=n)
+    args = (keys, ur, occ, desc, (0.0, 0.0, float(w), float(h)), mp_desc, mp_x, mp_y, mp_level, mp_radius, 0.9, 100)
+    gm, ga, gn = m.search_by_projection(*args, mp_observed=obs)
+    om, oa, on = oracle.search_by_projection(*args, mp_observed=obs)
+    assert gn == on and np.array_equal(gm, om) and np.array_equal(ga, oa)
+    assert on > 0 and on != oracle.search_by_projection(*args)[2]      # the rule changed the outcome
+    m.close()
+
+
 def test_distance_csr_and_host_replay_of_search_by_projection(oracle):
     """orbm_distance_csr gives every candidate's distance; replaying the reference's SearchByProjection loop
     (orbmatcher.cpp:76-124, with its 'keypoint already carries a map point' exclusion) on those distances equals the

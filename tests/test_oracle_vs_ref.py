@@ -172,6 +172,28 @@ def test_search_by_projection_oracle_equals_reference_sources(oracle, w, h, sa, 
 
 
 @pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
+@pytest.mark.parametrize("w,h,sa,sb,dx,dy,th,ratio,dup,obs", [
+    (640, 360, 5, 5, 0.7, 0.4, 3.0, 0.8, 2, 4), (800, 240, 21, 21, -1.5, 1.0, 1.0, 0.6, 2, 3), (1241, 376, 11, 11, 0.5, 0.0, 3.0, 0.8, 1, 7),
+    (640, 360, 7, 7, 0.0, 0.0, 3.0, 0.9, 3, 1000000)])
+def test_search_by_projection_sequential_rule_equals_reference_sources(oracle, w, h, sa, sb, dx, dy, th, ratio, dup, obs):
+    """The rule of src/orbmatcher.cpp:87-89 is live INSIDE the call once the map points carry observations (as every local
+    map point of Tracking::SearchLocalPoints does): a map point stored at :121 hides its key point from the map points
+    after it.  The reference's own function, driven with observed map points and with twins that collide on one key point,
+    equals the restatement with mp_observed -- and differs from the static rule, so the case does exercise it."""
+    r = oracle.ref_search_by_projection(synth.stereo_pair(w, h, sa), synth.stereo_pair(w, h, sb), 386.1, 0.537, th=th,
+                                        nnratio=ratio, dx=dx, dy=dy, nfeatures=1000, mp_dup=dup, obs_mod=obs)
+    ref = r["assigned"]
+    args = (r["b_keys"], r["b_uright"], r["b_occupied"], r["b_desc"], r["bounds"], r["mp_desc"], r["mp_x"], r["mp_y"], r["mp_level"],
+            r["mp_radius"], ratio, 100)
+    match, asg, nm = oracle.search_by_projection(*args, mp_observed=r["mp_observed"])
+    asg[(asg == -1) & (ref == -2)] = -2
+    assert nm == r["nmatches"] and nm > 20 and np.array_equal(asg, ref) and (match >= 0).sum() == nm
+    assert r["mp_observed"].sum() > 0.6 * len(r["mp_observed"])
+    _, asg0, nm0 = oracle.search_by_projection(*args)                 # the static rule counts the colliding map points twice
+    assert nm0 > nm
+
+
+@pytest.mark.skipif(not os.path.exists(FRAMEREF), reason="reference frame sources not built here")
 def test_descriptor_distance_equals_reference_function(oracle):
     """ORBmatcher::DescriptorDistance itself (src/orbmatcher.cpp:1662-1677, compiled unmodified) on random, equal,
     complementary and one-bit pairs."""
