@@ -5,15 +5,21 @@
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
 
 Metric (BASELINE.json): ORB frames/s on 1241x376 frames, 2000 features, 8 levels.
-Workload at every N = BASELINE config[1]: 64-frame synthetic stereo batches (32 L/R pairs) per GPU
-per step; frames are independent, so ranks share nothing on the data path (weak scaling: each
-rank extracts its own 64-frame batch; value = frames of all ranks / max-over-ranks time).
-  value : device-resident -- the step's 64 frames are already in HBM (rotating over a pool of
-          batches larger than the 126 MB L2), timed with CUDA events on the launching stream.
-  e2e   : through the C ABI entry point a caller uses (orbx_extract_batch) with pinned HOST
-          buffers: H2D of the frames and D2H of keypoints + descriptors inside the timed region.
-The same line carries the Hamming kNN-2 figures (2000 x 100000, query-sharded over the ranks with
-one all_gather of the 16-byte result records) under "matching".
+Headline workload at every N = BASELINE config[1]: 64-frame synthetic stereo batches (32 L/R pairs) per GPU per step;
+frames are independent, so ranks share nothing on the data path (weak scaling: each rank extracts its own 64-frame
+batch; value = frames of all ranks / max-over-ranks time).
+  value     : device-resident -- the step's 64 frames are already in HBM (rotating over a pool of batches larger than the
+              126 MB L2), timed with CUDA events on the launching stream.
+  e2e       : through the C ABI entry points a caller uses with pinned HOST buffers, H2D of the frames and D2H of
+              keypoints + descriptors inside the timed region: orbx_extract_batch_async / orbx_wait with two calls in
+              flight (call k+1 submitted, then call k collected); the synchronous orbx_extract_batch is reported beside it.
+  strong    : the same 64 frames per step SHARED by the ranks (64 / N per GPU): BASELINE config[1] read literally.
+  sustained : the device-resident step looped for >= 2 s (thermal / power steady state), clocks sampled over it.
+  configs   : BASELINE configs[2] (1920x1080, 4000 features, 8 levels, 16 frames per step) and configs[3] (3840x2160,
+              8000 features, 12 levels, 4 frames per step), each with device-resident and e2e rates and its own roofline.
+  matching  : Hamming kNN-2 2000 x 100000 (BASELINE configs[4]), query-sharded over the ranks, gathered everywhere.
+  parity_checked : OUTSIDE the timed regions the outputs of the timed workloads are compared with the CPU oracle (sampled
+              frames / queries) and the gathered N-rank match records with the single-GPU answer; a mismatch aborts the run.
 """
 import argparse
 import ctypes as C
@@ -31,19 +37,33 @@ for _p in (os.path.join(ROOT, "opendlv-perception-vision-orbslam2_b200"),):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# BASELINE.json configs[1..3]; P = sum of level pixels; batch = frames per GPU per step
+CONFIGS = {
+    "kitti": dict(w=1241, h=376, nf=2000, nl=8, batch=64, P=1444097, pool=6,
+                  label="synthetic stereo pairs 1241x376, 2000 features, 8 levels, 64-frame batch (BASELINE config[1])"),
+    "hd": dict(w=1920, h=1080, nf=4000, nl=8, batch=16, P=6419321, pool=4,
+               label="synthetic 1920x1080 frames, 4000 features, 8 levels, 16-frame batch (BASELINE config[2])"),
+    "uhd": dict(w=3840, h=2160, nf=8000, nl=12, batch=4, P=26804551, pool=4,
+                label="synthetic 3840x2160 frames, 8000 features, 12 levels, 4-frame batch (BASELINE config[3])"),
+}
 W, H, NFEAT, NLEVELS, BATCH = 1241, 376, 2000, 8, 64
 NQ, NT = 2000, 100000
-P_PYR = 1444097                      # sum of level pixels, SURVEY Appendix C
-B_ALG = W * H + P_PYR + NFEAT * 60   # 2 030 713 algorithmic bytes / frame, SURVEY 8(d)
-POOL = 6                             # distinct batches resident in HBM (6 x 30 MB inputs > L2)
+REFERENCE_IMPL = ("the reference's own src/orbextractor.cpp, compiled unmodified, linked to the repo's SCALAR restatement of the "
+                  "OpenCV primitives (oracle/cvshim: resize, FAST, GaussianBlur) -- not to OpenCV's SIMD code; a real OpenCV 3.3.1 "
+                  "build is roughly 2x faster on the same cores")
+
+
+def b_alg(cfg):
+    """algorithmic bytes per frame, SURVEY 8(d): read the frame, write every pyramid level once, 60 bytes per feature"""
+    return cfg["w"] * cfg["h"] + cfg["P"] + 60 * cfg["nf"]
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured", float(d.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback", 1965.0
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
 class ClockSampler:
@@ -55,7 +75,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
         self.nv, self.stop_flag, self.thread = None, False, None
-        self.sm, self.reasons_seen, self.sm_max = [], set(), None
+        self.sm, self.power, self.reasons_seen, self.sm_max = [], [], set(), None
 
     def start(self):
         try:
@@ -73,6 +93,7 @@ class ClockSampler:
                 while not self.stop_flag:
                     try:
                         self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        self.power.append(N.nvmlDeviceGetPowerUsage(h) / 1000.0)
                         r = int(get_reasons(h))
                         for n, bit in names.items():
                             if r & bit:
@@ -83,7 +104,7 @@ class ClockSampler:
             self.nv = N
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
-            return
+            return self
         except Exception:
             self.nv = None
         try:
@@ -93,6 +114,7 @@ class ClockSampler:
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -105,6 +127,7 @@ class ClockSampler:
             if not self.sm:
                 return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
             return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.sm_max,
+                    "power_w_max": float(max(self.power)) if self.power else None,
                     "reasons": sorted(self.reasons_seen), "samples": len(self.sm), "source": "NVML polled every 2 ms over the timed regions"}
         if self.proc:
             self.proc.terminate()
@@ -122,7 +145,8 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU side: the reference's own orbextractor.cpp (oracle/_ref) when it was built, else the C port
+# CPU side (the checker and the reported baseline, never the product path): the reference's own orbextractor.cpp
+# (oracle/_ref) when it was built, else the C port
 # --------------------------------------------------------------------------------------------
 class CpuReference:
     def __init__(self):
@@ -146,26 +170,28 @@ class CpuReference:
             except OSError:
                 pass
 
-    def extract_frames(self, frames, threads):
+    def extract_frames(self, frames, threads, nfeat=NFEAT, nlevels=NLEVELS):
         """frames/s over `frames` with `threads` host threads, one extractor instance per thread."""
         O = self.O
-        cap = NFEAT + 256
+        cap = nfeat + 64 * nlevels
         n = len(frames)
+        h, w = frames[0].shape
+        threads = max(1, min(threads, n))
         if self.kind == "reference":
             def work(t):
-                h = self.R.orbref_create(C.byref(self.Cfg(NFEAT, 1.2, NLEVELS, 20, 7)))
+                hd = self.R.orbref_create(C.byref(self.Cfg(nfeat, 1.2, nlevels, 20, 7)))
                 kps = np.zeros(cap, O.KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
                 tot = 0
                 for i in range(t, n, threads):
                     f = frames[i]
-                    tot += self.R.orbref_run(h, f.ctypes.data, W, H, f.strides[0], kps.ctypes.data, desc.ctypes.data, cap)
-                self.R.orbref_destroy(h)
+                    tot += self.R.orbref_run(hd, f.ctypes.data, w, h, f.strides[0], kps.ctypes.data, desc.ctypes.data, cap)
+                self.R.orbref_destroy(hd)
                 return tot
             t0 = time.perf_counter()
             ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
             [t.start() for t in ths]; [t.join() for t in ths]
             return n / (time.perf_counter() - t0)
-        ex = O.Extractor(NFEAT, 1.2, NLEVELS)
+        ex = O.Extractor(nfeat, 1.2, nlevels)
         t0 = time.perf_counter()
         ex.extract_batch_mt(frames, threads)
         return n / (time.perf_counter() - t0)
@@ -175,12 +201,47 @@ class CpuReference:
         self.O.knn2(q, t, nthreads=threads)
         return len(q) * len(t) / (time.perf_counter() - t0)
 
+    @staticmethod
+    def cv2_primitives_ms(frame, nlevels):
+        """What OpenCV's own (SIMD) resize + FAST + GaussianBlur cost for one frame's pyramid on one host thread: the part of
+        the reference's time that the scalar shim of the CPU arm overstates.  None when cv2 is not importable."""
+        try:
+            import cv2
+        except Exception:
+            return None
+        cv2.setNumThreads(1)
+        fast = cv2.FastFeatureDetector_create(7, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+
+        def once():
+            img = frame
+            for l in range(nlevels):
+                if l:
+                    sc = 1.2 ** l
+                    img = cv2.resize(img, (int(round(frame.shape[1] / sc)), int(round(frame.shape[0] / sc))), interpolation=cv2.INTER_LINEAR)
+                fast.detect(img)
+                cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        once()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            once()
+        return (time.perf_counter() - t0) / 3 * 1e3
+
 
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def synth_frames(name, rank=0):
+    """the frames of one step of a configuration (deterministic; SURVEY 8(d) generators)"""
+    import synth
+    cfg = CONFIGS[name]
+    if name == "kitti":
+        return synth.stereo_batch(2 + rank, cfg["w"], cfg["h"], cfg["batch"] // 2)
+    base = [synth.scene_s1(cfg["w"], cfg["h"], 1000 * (3 if name == "hd" else 4) + 10 * rank + i) for i in range(min(cfg["batch"], 4))]
+    return [np.roll(base[f % len(base)], 5 * (f // len(base)), axis=1) if f >= len(base) else base[f] for f in range(cfg["batch"])]
 
 
 def run_reference(args, rank):
@@ -190,7 +251,7 @@ def run_reference(args, rank):
     import synth
     cpu = CpuReference()
     cores = host_cores()
-    frames = synth.stereo_batch(2, W, H, BATCH // 2)
+    frames = synth_frames("kitti")
     for _ in range(args.warmup):
         cpu.extract_frames(frames[:cores], cores)
     t0 = time.perf_counter()
@@ -201,13 +262,21 @@ def run_reference(args, rank):
     q, t = synth.matching_set(NQ, NT)
     pairs = cpu.knn2(q[:200], t, cores)
     sample = f"{BATCH}-frame synthetic stereo batch per step on {cores} host threads, one extractor instance per thread"
+    other = {}
+    for name in ("hd", "uhd"):
+        cfg = CONFIGS[name]
+        fr = synth_frames(name)
+        other[name] = {"value": cpu.extract_frames(fr, cores, cfg["nf"], cfg["nl"]), "unit": "frames/s", "cores": min(cores, len(fr)),
+                       "sample": f"one {len(fr)}-frame step of {cfg['label']}, one extractor instance per thread"}
     line = {"impl": "reference", "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic stereo pairs 1241x376, 2000 features, 8 levels, 64-frame batch (BASELINE config[1])",
-                       "frames_per_step": BATCH},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu.kind, "sample": sample},
+            "config": {"workload": CONFIGS["kitti"]["label"], "frames_per_step": BATCH},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu.kind, "sample": sample,
+                             "reference_impl": REFERENCE_IMPL,
+                             "cv2_primitives_ms_per_frame_1thread": cpu.cv2_primitives_ms(frames[0], NLEVELS)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "configs": other,
             "matching": {"value": pairs, "unit": "pairs/s", "cores": cores, "sample": "200 of 2000 queries x 100000 train"}}
     print(json.dumps(line), flush=True)
 
@@ -233,6 +302,155 @@ def bind_to_gpu_cpus(index):
     return None
 
 
+class ParityError(RuntimeError):
+    pass
+
+
+def check_frames(oex, frames, picks, kps, desc, counts, what):
+    """THE CHECKER (outside every timed region): frames[picks] through the CPU oracle against the GPU's records.
+    Bit-exact on every field and every descriptor byte; returns the number of key points compared."""
+    total = 0
+    for f in picks:
+        okps, odesc = oex.extract(frames[f])
+        n = int(counts[f])
+        if n != len(okps):
+            raise ParityError(f"{what}: frame {f} has {n} key points, the oracle {len(okps)}")
+        g = kps[f][:n]
+        for fld in ("x", "y", "size", "angle", "response"):
+            if not np.array_equal(g[fld].view(np.uint32), okps[fld].view(np.uint32)):
+                raise ParityError(f"{what}: frame {f} field {fld} differs from the oracle")
+        for fld in ("octave", "class_id"):
+            if not np.array_equal(g[fld], okps[fld]):
+                raise ParityError(f"{what}: frame {f} field {fld} differs from the oracle")
+        flips = int(np.unpackbits(desc[f][:n] ^ odesc).sum())
+        if flips:
+            raise ParityError(f"{what}: frame {f} has {flips} descriptor bit flips")
+        total += n
+    return total
+
+
+def measure_config(name, args, rank, local_rank, world, torch, dist, orbx, dev, stream, barrier, oracle_mod, frames_per_rank=None,
+                   with_sync=True, with_profile=True, sustained_s=0.0, check=8):
+    """Device-resident and end-to-end rate of one configuration on this rank's GPU (+ parity of what was timed)."""
+    cfg = CONFIGS[name]
+    w, h, nf, nl = cfg["w"], cfg["h"], cfg["nf"], cfg["nl"]
+    batch = frames_per_rank or cfg["batch"]
+    # distinct resident batches: their frames alone exceed the 126 MB L2 (a strong-scaled share is a few MB per step)
+    pool = max(cfg["pool"], -(-140_000_000 // (batch * w * h)))
+    base = synth_frames(name, rank)
+    nb = len(base)
+    host_pool, dev_pool, frames_of = [], [], []
+    for p in range(pool):
+        hb = torch.empty((batch, h, w), dtype=torch.uint8).pin_memory()
+        fr = []
+        for f in range(batch):
+            src = base[(f + 7 * p + batch * rank * (frames_per_rank is not None)) % nb]
+            img = np.roll(src, 3 * p, axis=1) if p else src
+            hb[f] = torch.from_numpy(img)
+            fr.append(img)
+        host_pool.append(hb)
+        frames_of.append(fr)
+        dev_pool.append(hb.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    ex = orbx.Extractor(nf, 1.2, nl, 20, 7, max_width=w, max_height=h, max_batch=batch, device=local_rank)
+    cap = ex.max_keypoints
+
+    def step_dev(i):
+        ex.extract_batch_device(dev_pool[i % pool].data_ptr(), h * w, w, batch, w, h, stream.cuda_stream)
+
+    for i in range(args.warmup):
+        step_dev(i)
+    launches_per_step = ex.last_launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record(stream)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    res = {"ms_dev": ms_dev, "batch": batch, "launches_per_step": launches_per_step, "cap": cap, "pool": pool}
+
+    # ---- parity of the batch that was just timed (its last step), sampled frames through the oracle
+    oex = oracle_mod.Extractor(nfeatures=nf, nlevels=nl)
+    parity = {}
+    last = (args.steps - 1) % pool
+    picks = sorted(set(int(v) for v in np.linspace(0, batch - 1, min(check, batch))))
+    kps, desc, cnt = ex.fetch_results(batch, stream.cuda_stream)
+    parity["device_batch_frames"] = len(picks)
+    parity["device_batch_keypoints"] = check_frames(oex, frames_of[last], picks, kps, desc, cnt, f"{name} device-resident batch")
+
+    # ---- sustained: the same step for >= sustained_s seconds
+    if sustained_s > 0:
+        per = max(ms_dev / args.steps, 1e-3)
+        n_sus = int(sustained_s * 1e3 / per) + 1
+        clocks = ClockSampler(local_rank).start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record(stream)
+        for i in range(n_sus):
+            step_dev(i)
+        s1.record(stream)
+        barrier()
+        res["sustained"] = {"steps": n_sus, "ms": s0.elapsed_time(s1), "clocks": clocks.stop()}
+
+    # ---- e2e through the host entry points (pinned host frames in, keypoints + descriptors out)
+    # two sets of pinned result arrays with the library's stride (results are DMA'd straight into them): call k+1 fills one
+    # while the caller reads call k's
+    outs = [(torch.zeros(batch * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(batch, cap),
+             torch.zeros((batch, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(batch, np.int32)) for _ in range(2)]
+    host_np = [[hb[f].numpy() for f in range(batch)] for hb in host_pool]
+    host_ptrs = [orbx.Extractor.frame_pointers(fr) for fr in host_np]     # the `const uint8_t *const *` a C++ caller passes
+
+    def run_async(n):
+        prev = None
+        for i in range(n):
+            t = ex.extract_batch_async(host_ptrs[i % pool], batch, w, h, w, outs[i & 1])
+            if prev is not None:
+                ex.wait(prev)
+            prev = t
+        ex.wait(prev)
+
+    run_async(args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    run_async(args.steps)
+    barrier()
+    res["s_e2e"] = time.perf_counter() - t0
+    res["launches_e2e"] = ex.last_launches()
+    o = outs[(args.steps - 1) & 1]
+    res["n_kp"] = int(o[2].sum())
+    picks2 = sorted(set((f + max(1, batch // (2 * len(picks)))) % batch for f in picks))      # other frames than the device check took
+    parity["e2e_frames"] = len(picks2)
+    parity["e2e_keypoints"] = check_frames(oex, frames_of[(args.steps - 1) % pool], picks2, o[0], o[1], o[2], f"{name} e2e (async) results")
+    if with_sync:
+        for i in range(args.warmup):
+            ex.extract_batch_ptrs(host_ptrs[i % pool], batch, w, h, w, outs[0])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            ex.extract_batch_ptrs(host_ptrs[i % pool], batch, w, h, w, outs[0])
+        barrier()
+        res["s_e2e_sync"] = time.perf_counter() - t0
+    # the PCIe floor of the e2e number: pinned H2D copies of a step's frames by themselves
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        dev_pool[0].copy_(host_pool[0], non_blocking=True)
+        c0.record(stream)
+        for p in range(5):
+            dev_pool[p % pool].copy_(host_pool[p % pool], non_blocking=True)
+        c1.record(stream)
+    torch.cuda.synchronize()
+    res["h2d_ms"] = c0.elapsed_time(c1) / 5
+    if with_profile:
+        step_dev(0)
+        res["stages"] = ex.profile_stages(reps=5)
+    res["parity"] = parity
+    res["ex"], res["host_np"], res["host_ptrs"], res["outs"] = ex, host_np, host_ptrs, outs
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,6 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline only: no HD / UHD configs, no sustained loop, no next rows")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -281,77 +500,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- inputs: POOL distinct 64-frame stereo batches, pinned on the host and resident in HBM
-    base = synth.stereo_batch(2 + rank, W, H, BATCH // 2)
-    host_pool, dev_pool = [], []
-    for p in range(POOL):
-        hb = torch.empty((BATCH, H, W), dtype=torch.uint8).pin_memory()
-        for f in range(BATCH):
-            src = base[(f + 7 * p) % BATCH]
-            hb[f] = torch.from_numpy(np.roll(src, 3 * p, axis=1) if p else src)
-        host_pool.append(hb)
-        dev_pool.append(hb.to(dev, non_blocking=True))
-    torch.cuda.synchronize()
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
-    ex = orbx.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, max_width=W, max_height=H, max_batch=BATCH, device=local_rank)
+    # the checker (CPU oracle): used OUTSIDE the timed regions only
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orb_oracle_py as oracle_mod
+    oracle_mod.lib()
+
     stream = torch.cuda.Stream(device=dev)
-
-    def step_dev(i):
-        d = dev_pool[i % POOL]
-        ex.extract_batch_device(d.data_ptr(), H * W, W, BATCH, W, H, stream.cuda_stream)
-
-    for i in range(args.warmup):
-        step_dev(i)
-    launches_per_step = ex.last_launches()   # counted by the library: copy + 7 resize + 2 FAST + blur + octree + describe per half batch
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        step_dev(i)
-    e1.record(stream)
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
 
-    # ---- e2e through the host entry point (pinned host frames in, keypoints + descriptors out)
-    cap = ex.max_keypoints
-    # pinned result arrays with the library's stride: keypoints and descriptors are DMA'd straight into them
-    out = (torch.zeros(BATCH * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(BATCH, cap),
-           torch.zeros((BATCH, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(BATCH, np.int32))
-    host_np = [[hb[f].numpy() for f in range(BATCH)] for hb in host_pool]
-    host_ptrs = [orbx.Extractor.frame_pointers(fr) for fr in host_np]     # the `const uint8_t *const *` a C++ caller passes
-
-    def step_e2e(i):
-        ex.extract_batch_ptrs(host_ptrs[i % POOL], BATCH, W, H, W, out)
-
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
-    barrier()
-    s_e2e = time.perf_counter() - t0
-    n_kp = int(out[2].sum())
-    launches_e2e = ex.last_launches()
-    # the PCIe floor of the e2e number: one pinned H2D copy of a step's frames by itself
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        dev_pool[0].copy_(host_pool[0], non_blocking=True)
-        c0.record(stream)
-        for p in range(5):
-            dev_pool[p % POOL].copy_(host_pool[p % POOL], non_blocking=True)
-        c1.record(stream)
-    torch.cuda.synchronize()
-    h2d_ms = c0.elapsed_time(c1) / 5
-
+    # ---- headline: BASELINE config[1], 64 frames per GPU per step
+    head = measure_config("kitti", args, rank, local_rank, world, torch, dist, orbx, dev, stream, barrier, oracle_mod,
+                          sustained_s=0.0 if args.quick else 2.0)
     clk = clocks.stop() if rank == 0 else None
-
-    # ---- per-stage device times -> dominant kernel for the roofline line
-    stages = ex.profile_stages(reps=5)
+    ex, host_np, out = head["ex"], head["host_np"], head["outs"][0]
+    cap = head["cap"]
+    parity = dict(head["parity"])
 
     # ---- latency of the call OrbFrame makes: one frame (and one stereo pair) through the host entry point
     lat = {}
@@ -365,7 +536,28 @@ def main():
             ex.extract_batch_ptrs(ptrs, nb, W, H, W, o)
         lat[key] = (time.perf_counter() - t0) / 100 * 1e3
 
-    # ---- matching: query-sharded kNN-2, one all_gather of the result records
+    # ---- strong scaling of config[1]: the 64 frames of a step shared by the ranks (64 / N per GPU)
+    strong = None
+    if world > 1:
+        per = BATCH // world
+        sres = measure_config("kitti", args, rank, local_rank, world, torch, dist, orbx, dev, stream, barrier, oracle_mod,
+                              frames_per_rank=per, with_sync=False, with_profile=False, check=2)
+        sres["ex"].close()
+        strong = sres
+
+    # ---- BASELINE configs[2], [3]
+    others = {}
+    if not args.quick:
+        for name in ("hd", "uhd"):
+            r = measure_config(name, args, rank, local_rank, world, torch, dist, orbx, dev, stream, barrier, oracle_mod,
+                               with_sync=True, check=2 if name == "hd" else 1)
+            r["ex"].close()
+            for k in ("ex", "host_np", "host_ptrs", "outs"):
+                r.pop(k)
+            others[name] = r
+            torch.cuda.empty_cache()
+
+    # ---- matching: query-sharded kNN-2, the result records gathered on every rank
     q, t = synth.matching_set(NQ, NT)
     m = orbx.Matcher(max_queries=NQ, max_train=NT, device=local_rank)
     nq_loc = shard.query_block(NQ, world)
@@ -395,84 +587,57 @@ def main():
     m1.record(stream)
     barrier()
     ms_match = m0.elapsed_time(m1)
-
+    # parity of the matching result every rank now holds: against the unsharded single-GPU answer, and against the oracle
+    got = (d_all if world > 1 else d_loc)[:NQ].cpu().numpy()
+    dq_all = torch.from_numpy(q).to(dev)
+    d_one = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
+    m.knn2_device(dq_all.data_ptr(), NQ, dt_.data_ptr(), NT, d_one.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    one = d_one.cpu().numpy()
+    if not np.array_equal(got[:, :3], one[:, :3]):
+        raise ParityError("gathered query-sharded match records differ from the single-GPU answer")
+    pick_q = np.linspace(0, NQ - 1, 64).astype(int)
+    oi, o1, o2 = oracle_mod.knn2(q[pick_q], t)
+    if not (np.array_equal(got[pick_q, 0], oi) and np.array_equal(got[pick_q, 1], o1) and np.array_equal(got[pick_q, 2], o2)):
+        raise ParityError("kNN-2 records differ from the oracle")
+    parity["knn2_gathered_vs_single_gpu_queries"] = NQ
+    parity["knn2_vs_oracle_queries"] = len(pick_q)
     popc_rate = m.measure_popc()
 
-    # ---- "next" rows, rank 0 only, reported beside the headline: bag-of-words descent over one frame's
-    # descriptors (N2), distinctive descriptors of a map's points (N4), stereo matching of one pair (N1)
+    # ---- "next" rows, rank 0 only, reported beside the headline
     next_rows = None
-    if rank == 0:
-        next_rows = {}
-        rng = np.random.default_rng(99)
-        voc = orbx.random_vocabulary(10, 5, seed=1)                       # k = 10, L = 5: 111 111 nodes (ORBvoc.txt is k = 10, L = 6)
-        V = orbx.Vocabulary(*voc[:5], voc[5], device=local_rank)
-        feats = rng.integers(0, 256, (BATCH * NFEAT, 32), dtype=np.uint8)
-        dfe = torch.from_numpy(feats).to(dev)
-        dwn = torch.empty((BATCH * NFEAT, 2), dtype=torch.int32, device=dev)
-        for _ in range(3):
-            V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
-        torch.cuda.synchronize()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record(stream)
-        for _ in range(10):
-            V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
-        n1.record(stream)
-        torch.cuda.synchronize()
-        ms = n0.elapsed_time(n1) / 10
-        next_rows["bow_transform"] = {"features_per_s": BATCH * NFEAT / (ms * 1e-3), "ms_per_64_frames": ms,
-                                      "workload": f"{BATCH} frames x {NFEAT} descriptors, synthetic vocabulary k=10 L=5, levels_up=4, device-resident"}
-        V.close()
-        # stereo matching of the 32 L/R pairs of a batch (N1): pool 0 holds the pairs in L R L R order
-        ex.extract_batch_ptrs(host_ptrs[0], BATCH, W, H, W, out)
-        sout = (np.zeros((BATCH // 2, cap), np.float32), np.zeros((BATCH // 2, cap), np.float32))
-        orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            _, _, snl, snm = orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
-        dt_s = (time.perf_counter() - t0) / 5
-        next_rows["stereo_matches"] = {"pairs_per_s": (BATCH // 2) / dt_s, "ms_per_call": dt_s * 1e3, "matches_per_pair": float(snm.mean()),
-                                       "workload": f"{BATCH // 2} stereo pairs of one extracted batch in one orbx_stereo_match_batch call, results to host"}
-        npts = 20000
-        pool = rng.integers(0, 256, (npts * 4, 32), dtype=np.uint8)
-        sizes = rng.integers(2, 25, npts)
-        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-        inds = rng.integers(0, len(pool), int(offs[-1])).astype(np.int32)
-        m.distinctive(pool, offs, inds)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            m.distinctive(pool, offs, inds)
-        dt_d = (time.perf_counter() - t0) / 3
-        next_rows["distinctive_descriptors"] = {"points_per_s": npts / dt_d, "ms_per_call": dt_d * 1e3,
-                                                "workload": f"{npts} map points with 2..24 observations each, host arrays in and out"}
-
-        # SearchByProjection (N3) with the frame grid on the device: frame 0's key points as map points, projected
-        # 1.25 px beside themselves into frame 0 (the shape of TrackLocalMap: ~2000 points against ~2000 key points)
-        k0 = np.ascontiguousarray(out[0][0, :out[2][0]]); d0 = np.ascontiguousarray(out[1][0, :out[2][0]])
-        sfl = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
-        proj_args = (k0, np.full(len(k0), -1, np.float32), None, d0, (0.0, 0.0, float(W), float(H)), d0, k0["x"] + np.float32(1.25), k0["y"].copy(),
-                     k0["octave"].copy(), (np.float32(4.0) * sfl[k0["octave"]]).astype(np.float32))
-        m.search_by_projection(*proj_args)
-        t0 = time.perf_counter()
-        for _ in range(20):
-            _, _, pnm = m.search_by_projection(*proj_args)
-        dt_p = (time.perf_counter() - t0) / 20
-        next_rows["search_by_projection"] = {"map_points_per_s": len(k0) / dt_p, "ms_per_call": dt_p * 1e3, "matches": int(pnm),
-                                             "workload": f"{len(k0)} map points against one frame of {len(k0)} key points, grid + candidate lists + best/second best on the device, host arrays in and out"}
+    if rank == 0 and not args.quick:
+        next_rows, nr_ctx = measure_next_rows(torch, orbx, ex, m, head, dev, stream, local_rank)
 
     # ---- max over ranks
-    times = torch.tensor([ms_dev, s_e2e, ms_match], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev, s_e2e, ms_match = [float(x) for x in times.tolist()]
+    keys = ["ms_dev", "s_e2e", "s_e2e_sync"]
+    vals = [head[k] for k in keys] + [ms_match] + ([head["sustained"]["ms"]] if "sustained" in head else [0.0])
+    vals += [strong["ms_dev"], strong["s_e2e"]] if strong else [0.0, 0.0]
+    for name in ("hd", "uhd"):
+        vals += [others[name]["ms_dev"], others[name]["s_e2e"], others[name]["s_e2e_sync"]] if name in others else [0.0, 0.0, 0.0]
+    vals = max_over_ranks(vals)
+    ms_dev, s_e2e, s_e2e_sync, ms_match, ms_sus, ms_strong, s_strong = vals[:7]
+    kp_checked = sum(v for k, v in parity.items() if k.endswith("_keypoints"))
+    for name in others:
+        for k, v in others[name]["parity"].items():
+            parity[f"{name}_{k}"] = v
+    if strong:
+        parity["strong_device_batch_frames"] = strong["parity"]["device_batch_frames"]
+        parity["strong_e2e_frames"] = strong["parity"]["e2e_frames"]
+    parity["mismatches"] = 0          # any mismatch raised ParityError above
+    parity["ranks_checked"] = world
 
     if rank == 0:
         peak, peak_src, sm_max = measured_peaks()
-        frames = BATCH * args.steps * world
+        steps = args.steps
+        frames = BATCH * steps * world
         fps_dev = frames / (ms_dev * 1e-3)
         fps_e2e = frames / s_e2e
+        stages = head["stages"]
         dom = max(stages, key=stages.get)
         dom_ms = stages[dom]
-        ach = B_ALG * BATCH / (dom_ms * 1e-3) / 1e9
+        balg = b_alg(CONFIGS["kitti"])
+        ach = balg * BATCH / (dom_ms * 1e-3) / 1e9
         traffic, winst_step = None, None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
@@ -481,35 +646,43 @@ def main():
             winst_step = sum(prof.get("warp_instructions_per_step", {}).values()) or None
         pairs = NQ * NT * msteps / (ms_match * 1e-3)
         int_peak = 148 * sm_max * 1e6 * popc_rate / 8      # pairs/s at the POPC rate measured on this GPU, SURVEY 8(d)
+        h2d_ms = head["h2d_ms"]
         line = {
             "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps_dev, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_dev / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "synthetic stereo pairs 1241x376, 2000 features, 8 levels, 64-frame batch per GPU per step (BASELINE config[1])",
+            "config": {"workload": CONFIGS["kitti"]["label"] + ", one such batch per GPU per step",
                        "frames_per_gpu_per_step": BATCH, "global_frames_per_step": BATCH * world,
-                       "l2": f"inputs rotate over {POOL} resident batches ({POOL * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
+                       "l2": f"inputs rotate over {head['pool']} resident batches ({head['pool'] * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "host_binding": None if numa is None else f"each rank bound to the {numa} host cores NVML lists for its GPU"},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * W * H,
-                    "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": n_kp,
+                    "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": head["n_kp"],
+                    "api": "orbx_extract_batch_async + orbx_wait, two calls in flight, pinned host buffers",
+                    "sync_value": frames / s_e2e_sync, "sync_api": "orbx_extract_batch (one call at a time)",
                     "h2d_alone_ms_per_step": h2d_ms, "h2d_gbs": BATCH * W * H / (h2d_ms * 1e-3) / 1e9,
-                    "pcie_floor_frames_per_s": BATCH * world / (h2d_ms * 1e-3)},
-            "gpu_launches": launches_per_step * args.steps,
-            "gpu_launches_per_step": {"device_resident": launches_per_step, "e2e": launches_e2e},
+                    "pcie_floor_frames_per_s": BATCH * world / (h2d_ms * 1e-3),
+                    "frac_of_pcie_floor": fps_e2e / (BATCH * world / (h2d_ms * 1e-3))},
+            "gpu_launches": head["launches_per_step"] * steps,
+            "gpu_launches_per_step": {"device_resident": head["launches_per_step"], "e2e": head["launches_e2e"]},
             "latency": dict(lat, note="orbx_extract_batch with 1 / 2 frames of 1241x376, pinned host buffers, H2D + kernels + D2H, mean of 100 calls"),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this stage, bytes per 64-frame step)",
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": B_ALG * BATCH, "kernel_ms": dom_ms,
-                         "whole_step_frac": B_ALG * BATCH / (ms_dev / args.steps * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": balg * BATCH, "kernel_ms": dom_ms,
+                         "whole_step_frac": balg * BATCH / (ms_dev / steps * 1e-3) / 1e9 / peak,
                          # the path is instruction-issue bound (50-100 integer operations per byte): warp instructions of one
                          # step (ncu smsp__inst_executed.sum, profiles/ncu_traffic.json) against 4 issue slots x 148 SMs x clock
                          "issue_roofline": None if not winst_step else {
                              "warp_instructions_per_step": winst_step,
                              "peak_warp_instructions_per_s": 4 * 148 * sm_max * 1e6,
-                             "frac": winst_step / (ms_dev / args.steps * 1e-3) / (4 * 148 * sm_max * 1e6)}},
+                             "frac": winst_step / (ms_dev / steps * 1e-3) / (4 * 148 * sm_max * 1e6)}},
             "stages_ms": stages,
             "clocks": clk,
+            "parity_checked": dict(parity, keypoints_compared_rank0=kp_checked,
+                                   how="outside the timed regions: sampled frames of the timed device-resident batch and of the timed e2e "
+                                       "results through the CPU oracle (every field and descriptor byte bit-exact); match records gathered "
+                                       "over the ranks against the unsharded single-GPU answer and sampled queries against the oracle"),
             "matching": {"metric": "Hamming kNN-2 pairs/s (2000 x 100000)", "value": pairs, "unit": "pairs/s",
                          "queries_per_s": NQ * msteps / (ms_match * 1e-3), "ms_per_batch": ms_match / msteps,
                          "scaling": "strong", "sharding": f"{nq_loc} queries per GPU, train replicated, all_gather of 16-byte records" if world > 1 else "single GPU",
@@ -517,33 +690,151 @@ def main():
                                       "frac": pairs / world / int_peak, "popc_per_clk_per_sm": popc_rate,
                                       "peak_source": "148 SM x max SM clock x POPC lanes/clk/SM measured on this GPU (orbm_measure_popc) / 8 POPC per pair"}},
         }
+        if "sustained" in head:
+            sus = head["sustained"]
+            line["sustained"] = {"value": BATCH * sus["steps"] * world / (ms_sus * 1e-3), "unit": "frames/s", "seconds": ms_sus * 1e-3,
+                                 "steps": sus["steps"], "ms_per_step": ms_sus / sus["steps"], "clocks": sus["clocks"],
+                                 "what": "the device-resident step of the headline looped back to back"}
+        if strong:
+            per = BATCH // world
+            line["strong"] = {"workload": f"BASELINE config[1] read literally: {BATCH} frames per step shared by {world} GPUs ({per} each)",
+                              "value": per * world * steps / (ms_strong * 1e-3), "unit": "frames/s", "ms_per_step": ms_strong / steps,
+                              "e2e": {"value": per * world * steps / s_strong, "unit": "frames/s"}, "scaling": "strong"}
+        else:
+            line["strong"] = {"workload": f"BASELINE config[1] read literally: {BATCH} frames per step on 1 GPU = the headline",
+                              "value": fps_dev, "unit": "frames/s", "ms_per_step": ms_dev / steps, "e2e": {"value": fps_e2e, "unit": "frames/s"},
+                              "scaling": "strong"}
+        cfgs = {}
+        k = 7
+        for name in ("hd", "uhd"):
+            if name not in others:
+                continue
+            o, cfg = others[name], CONFIGS[name]
+            md, se, ss = vals[k:k + 3]
+            k += 3
+            b = cfg["batch"]
+            st = o["stages"]
+            dm = max(st, key=st.get)
+            ba = b_alg(cfg)
+            a = ba * b / (st[dm] * 1e-3) / 1e9
+            cfgs[name] = {"workload": cfg["label"] + ", one such batch per GPU per step", "value": b * steps * world / (md * 1e-3),
+                          "unit": "frames/s", "ms_per_step": md / steps,
+                          "e2e": {"value": b * steps * world / se, "unit": "frames/s", "sync_value": b * steps * world / ss,
+                                  "h2d_bytes_per_step": b * cfg["w"] * cfg["h"], "d2h_bytes_per_step": b * o["cap"] * 60 + b * 4,
+                                  "pcie_floor_frames_per_s": b * world / (o["h2d_ms"] * 1e-3)},
+                          "roofline": {"bound": "hbm", "kernel": dm, "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                                       "algorithmic_bytes_per_launch": ba * b, "kernel_ms": st[dm],
+                                       "whole_step_frac": ba * b / (md / steps * 1e-3) / 1e9 / peak},
+                          "stages_ms": st, "gpu_launches_per_step": o["launches_per_step"]}
+        line["configs"] = cfgs
         line["next_rows"] = next_rows
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference()
             cores = host_cores()
+            base = synth_frames("kitti")
             frames_cpu = base * 4                      # 256 frames
             fps_all = cpu.extract_frames(frames_cpu, cores)
             fps_one = cpu.extract_frames(base[:16], 1)
+            cv2_ms = cpu.cv2_primitives_ms(base[0], NLEVELS)
             line["cpu_baseline"] = {"value": fps_all, "unit": "frames/s", "cores": cores, "kind": cpu.kind,
                                     "sample": f"{len(frames_cpu)} frames of the same workload over {cores} host threads (one extractor instance per thread); single thread: {fps_one:.1f} frames/s on 16 frames",
                                     "single_thread": fps_one,
+                                    "reference_impl": REFERENCE_IMPL,
+                                    "cv2_primitives_ms_per_frame_1thread": cv2_ms,
+                                    "cv2_note": "cv2 4.13 resize + FAST(7, nms) + GaussianBlur over the same 8-level pyramid on one thread: the OpenCV-side share of "
+                                                f"a real reference build; the arm's own single-thread frame takes {1e3 / fps_one:.1f} ms",
                                     "matching_pairs_per_s": cpu.knn2(q[:160], t, cores)}
-            # the same next-row workloads on one host core through the oracle's restatements (bounded samples)
-            O = cpu.O
-            voc = orbx.random_vocabulary(10, 5, seed=1)
-            fs = np.random.default_rng(99).integers(0, 256, (20000, 32), dtype=np.uint8)
-            t0 = time.perf_counter(); O.voc_transform(voc[0], voc[1], voc[2], voc[3], voc[5], 4, fs); dtv = time.perf_counter() - t0
-            line["next_rows"]["bow_transform"]["cpu_port_features_per_s_1core"] = len(fs) / dtv
-            t0 = time.perf_counter(); O.distinctive(pool, offs[:2001], inds[:offs[2000]]); dtd = time.perf_counter() - t0
-            line["next_rows"]["distinctive_descriptors"]["cpu_port_points_per_s_1core"] = 2000 / dtd
-            t0 = time.perf_counter()
-            for _ in range(5):
-                O.search_by_projection(*proj_args)
-            line["next_rows"]["search_by_projection"]["cpu_port_map_points_per_s_1core"] = len(k0) * 5 / (time.perf_counter() - t0)
+            if not args.quick:
+                for name in cfgs:
+                    cfg = CONFIGS[name]
+                    fr = synth_frames(name)
+                    cfgs[name]["cpu_baseline"] = {"value": cpu.extract_frames(fr, cores, cfg["nf"], cfg["nl"]), "unit": "frames/s",
+                                                  "cores": min(cores, len(fr)), "kind": cpu.kind,
+                                                  "sample": f"one {len(fr)}-frame step, one extractor instance per thread"}
+                cpu_next_rows(line, cpu, orbx, nr_ctx)
         print(json.dumps(line), flush=True)
     ex.close(); m.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_next_rows(torch, orbx, ex, m, head, dev, stream, local_rank):
+    """bag-of-words descent over one batch's descriptors (N2), stereo matching of a batch's pairs (N1), distinctive descriptors
+    of a map's points (N4), SearchByProjection with the frame grid (N3)"""
+    next_rows = {}
+    rng = np.random.default_rng(99)
+    out, cap = head["outs"][0], head["cap"]
+    voc = orbx.random_vocabulary(10, 5, seed=1)                       # k = 10, L = 5: 111 111 nodes (ORBvoc.txt is k = 10, L = 6)
+    V = orbx.Vocabulary(*voc[:5], voc[5], device=local_rank)
+    feats = rng.integers(0, 256, (BATCH * NFEAT, 32), dtype=np.uint8)
+    dfe = torch.from_numpy(feats).to(dev)
+    dwn = torch.empty((BATCH * NFEAT, 2), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record(stream)
+    for _ in range(10):
+        V.transform_device(dfe.data_ptr(), 32, BATCH * NFEAT, 4, dwn.data_ptr(), stream.cuda_stream)
+    n1.record(stream)
+    torch.cuda.synchronize()
+    ms = n0.elapsed_time(n1) / 10
+    next_rows["bow_transform"] = {"features_per_s": BATCH * NFEAT / (ms * 1e-3), "ms_per_64_frames": ms,
+                                  "workload": f"{BATCH} frames x {NFEAT} descriptors, synthetic vocabulary k=10 L=5, levels_up=4, device-resident"}
+    V.close()
+    # stereo matching of the 32 L/R pairs of a batch (N1): pool 0 holds the pairs in L R L R order
+    ex.extract_batch_ptrs(head["host_ptrs"][0], BATCH, W, H, W, out)
+    sout = (np.zeros((BATCH // 2, cap), np.float32), np.zeros((BATCH // 2, cap), np.float32))
+    orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        _, _, snl, snm = orbx.stereo_match_batch(ex, BATCH // 2, 0, 1, 2, 386.1448, 0.5372, out=sout)
+    dt_s = (time.perf_counter() - t0) / 5
+    next_rows["stereo_matches"] = {"pairs_per_s": (BATCH // 2) / dt_s, "ms_per_call": dt_s * 1e3, "matches_per_pair": float(snm.mean()),
+                                   "workload": f"{BATCH // 2} stereo pairs of one extracted batch in one orbx_stereo_match_batch call, results to host"}
+    npts = 20000
+    pool = rng.integers(0, 256, (npts * 4, 32), dtype=np.uint8)
+    sizes = rng.integers(2, 25, npts)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    inds = rng.integers(0, len(pool), int(offs[-1])).astype(np.int32)
+    m.distinctive(pool, offs, inds)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        m.distinctive(pool, offs, inds)
+    dt_d = (time.perf_counter() - t0) / 3
+    next_rows["distinctive_descriptors"] = {"points_per_s": npts / dt_d, "ms_per_call": dt_d * 1e3,
+                                            "workload": f"{npts} map points with 2..24 observations each, host arrays in and out"}
+    # SearchByProjection (N3) with the frame grid on the device: frame 0's key points as OBSERVED map points (as in
+    # Tracking::SearchLocalPoints), projected 1.25 px beside themselves into frame 0: ~2000 points against ~2000 key points
+    k0 = np.ascontiguousarray(out[0][0, :out[2][0]]); d0 = np.ascontiguousarray(out[1][0, :out[2][0]])
+    sfl = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    proj_args = (k0, np.full(len(k0), -1, np.float32), None, d0, (0.0, 0.0, float(W), float(H)), d0, k0["x"] + np.float32(1.25), k0["y"].copy(),
+                 k0["octave"].copy(), (np.float32(4.0) * sfl[k0["octave"]]).astype(np.float32))
+    obs = np.ones(len(k0), np.uint8)
+    m.search_by_projection(*proj_args, mp_observed=obs)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        _, _, pnm = m.search_by_projection(*proj_args, mp_observed=obs)
+    dt_p = (time.perf_counter() - t0) / 20
+    next_rows["search_by_projection"] = {"map_points_per_s": len(k0) / dt_p, "ms_per_call": dt_p * 1e3, "matches": int(pnm),
+                                         "workload": f"{len(k0)} observed map points against one frame of {len(k0)} key points, grid + candidate lists + best/second best + the sequential occupancy rule on the device, host arrays in and out"}
+    return next_rows, dict(pool=pool, offs=offs, inds=inds, proj_args=proj_args, obs=obs, k0=k0)
+
+
+def cpu_next_rows(line, cpu, orbx, ctx):
+    """the same next-row workloads on one host core through the oracle's restatements (bounded samples)"""
+    O = cpu.O
+    voc = orbx.random_vocabulary(10, 5, seed=1)
+    fs = np.random.default_rng(99).integers(0, 256, (20000, 32), dtype=np.uint8)
+    t0 = time.perf_counter(); O.voc_transform(voc[0], voc[1], voc[2], voc[3], voc[5], 4, fs); dtv = time.perf_counter() - t0
+    line["next_rows"]["bow_transform"]["cpu_port_features_per_s_1core"] = len(fs) / dtv
+    pool, offs, inds = ctx["pool"], ctx["offs"], ctx["inds"]
+    t0 = time.perf_counter(); O.distinctive(pool, offs[:2001], inds[:offs[2000]]); dtd = time.perf_counter() - t0
+    line["next_rows"]["distinctive_descriptors"]["cpu_port_points_per_s_1core"] = 2000 / dtd
+    t0 = time.perf_counter()
+    for _ in range(5):
+        O.search_by_projection(*ctx["proj_args"], mp_observed=ctx["obs"])
+    line["next_rows"]["search_by_projection"]["cpu_port_map_points_per_s_1core"] = len(ctx["k0"]) * 5 / (time.perf_counter() - t0)
 
 
 if __name__ == "__main__":

@@ -89,6 +89,19 @@ int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, s
 int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
                        size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
 
+/* Asynchronous form of orbx_extract_batch: the call only enqueues the work (H2D copies, kernels, D2H copies) and returns a
+ * ticket; orbx_wait(ticket) blocks until the results of that call are in kps / desc / n_out, which, like the images, must
+ * stay valid and untouched until then.  Up to TWO calls may be in flight on a handle: submit call k+1, then wait for call
+ * k -- the H2D copies of call k+1 then run while the last kernels and D2H copies of call k drain, which is where a
+ * synchronous call leaves the copy engine idle (the reference consumes the extractors' output the same way: both run in
+ * threads, the frame is assembled afterwards, orbframe.cpp:73-78).  A third submit completes the oldest ticket itself.
+ * Pinned (page-locked) image and result buffers are DMA'd directly; pageable ones go through the handle's staging.
+ * orbx_extract_batch is exactly orbx_extract_batch_async + orbx_wait. */
+int orbx_extract_batch_async(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
+                             size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out, int *ticket);
+/* ORBX_OK, or ORBX_ERR_CAPACITY when a frame produced more than kp_cap keypoints, ORBX_ERR_ARG for an unknown ticket */
+int orbx_wait(orbx_extractor *h, int ticket);
+
 /* Device-resident variant: frames already in HBM (frame f at d_imgs + f*frame_stride), results
  * stay in HBM.  Work is enqueued on `stream` (a cudaStream_t, NULL = the handle's own stream)
  * and NOT synchronised.  Result pointers (valid until the next call on this handle):

@@ -86,14 +86,26 @@ struct orbx_extractor {
     // state the kernels read) before it reads the results or reuses the arenas.
     cudaEvent_t evLast = nullptr;
     bool lastPending = false;
+    // asynchronous host calls (orbx_extract_batch_async / orbx_wait): up to two tickets in flight, slot = ticket & 1
+    struct Ticket {
+        bool active = false, directOut = false;
+        int id = 0, batch = 0, kp_cap = 0, kpStride = 0;
+        orbx_keypoint *kps = nullptr; uint8_t *desc = nullptr; int *n_out = nullptr;
+        std::vector<int> cb;           // chunk boundaries of the call
+    } tk[2];
+    int nextTicket = 1, asyncParity = -1;
+    unsigned chunkSeq = 0;             // chunks rotate over the lanes across calls
+    std::vector<int> prevCb;           // chunk boundaries of the last submitted call (its events: parity asyncParity)
+    std::vector<cudaEvent_t> evIn[2], evK[2], evOut[2];   // per ticket parity and chunk: H2D done, kernels done, D2H done
+    PinBuf<uint8_t> hInT[2], hDescT[2];                   // host staging for callers without pinned buffers, per parity
+    PinBuf<orbx_keypoint_pod> hKpsT[2];
+    PinBuf<int> hCountsT[2];
     // CUDA graphs of the per-chunk kernel pipeline of the host entry point (level-0 copy .. describe, both
     // streams of a lane): one cudaGraphLaunch replaces ~25 launches / event calls per chunk.  Keyed by
     // (first frame, frames, lane); dropped whenever geometry or an arena pointer changes.
     struct ChunkGraph { int f0, nf, lane, launches; cudaGraphExec_t exec; };
     std::vector<ChunkGraph> graphs;
     uint64_t graphSig = 0;
-    std::vector<cudaEvent_t> evChunk;
-    std::vector<cudaEvent_t> evTrace;      // ORBX_TRACE only: timing events, 1 + 3 per chunk
     OrbxTensorMaps tmaps;            // TMA descriptors of the pyramid levels (source of k_blur), host copy
     OrbxTensorMaps tmapsFast;        // same levels, box = FAST window (256 bytes x hCell+6 rows)
     OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
@@ -116,7 +128,7 @@ struct orbx_extractor {
     DevBuf<float> dStereo;          // uRight | depth of the last orbx_stereo_match
     DevBuf<int> dStereoI;           // sad per left keypoint | match count
     PinBuf<float> hStereo;
-    PinBuf<uint8_t> hIn, hDesc, hLevel;
+    PinBuf<uint8_t> hDesc, hLevel;
     PinBuf<orbx_keypoint_pod> hKps;
     PinBuf<int> hCounts;
     int dbgEnabled = 0, dbgCap = 0;
@@ -152,6 +164,11 @@ int failCuda(orbx_extractor *h, cudaError_t e, const char *where)
 // order `st` behind the last device-resident extraction (a no-op when that call used `st` itself or has been waited for)
 cudaError_t orderAfterLast(orbx_extractor *h, cudaStream_t st)
 {
+    // the last asynchronous host call: its kernels AND its D2H copies (the D2H stream is in order: the last chunk's event)
+    if (h->asyncParity >= 0 && h->prevCb.size() > 1) {
+        const cudaError_t e = cudaStreamWaitEvent(st, h->evOut[h->asyncParity][h->prevCb.size() - 2], 0);
+        if (e != cudaSuccess) return e;
+    }
     if (!h->lastPending) return cudaSuccess;
     return cudaStreamWaitEvent(st, h->evLast, 0);
 }
@@ -450,6 +467,9 @@ int setGeometry(orbx_extractor *h, int w, int hh)
         CK(cudaStreamSynchronize(h->lane[i].main));
         CK(cudaStreamSynchronize(h->lane[i].side));
     }
+    if (h->streamIn) CK(cudaStreamSynchronize(h->streamIn));
+    if (h->streamOut) CK(cudaStreamSynchronize(h->streamOut));
+    h->prevCb.clear();
     // from here on the handle describes no size until the new tables are on the device: a failure below (out of memory)
     // cannot leave the old curW / curH paired with the new layout
     h->geomUploaded = false; h->curW = 0; h->curH = 0;
@@ -625,9 +645,8 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     if (rc != ORBX_OK) return rc;
     rc = ensureArenas(h, cfg->max_batch);
     if (rc != ORBX_OK) return rc;
-    CK(h->hKps.ensure((size_t)h->L.kpStride * cfg->max_batch));
-    CK(h->hDesc.ensure((size_t)h->L.kpStride * cfg->max_batch * 32));
     CK(h->hCounts.ensure((size_t)cfg->max_batch));
+    for (int p = 0; p < 2; p++) CK(h->hCountsT[p].ensure((size_t)cfg->max_batch));
     return ORBX_OK;
 }
 
@@ -643,13 +662,16 @@ void orbx_destroy(orbx_extractor *h)
     if (h->streamOut) cudaStreamSynchronize(h->streamOut);
     if (h->evLast) { if (h->lastPending) cudaEventSynchronize(h->evLast); cudaEventDestroy(h->evLast); }
     dropGraphs(h);
-    for (cudaEvent_t e : h->evChunk) if (e) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->evTrace) if (e) cudaEventDestroy(e);
+    for (int p = 0; p < 2; p++) {
+        for (std::vector<cudaEvent_t> *ev : {&h->evIn[p], &h->evK[p], &h->evOut[p]})
+            for (cudaEvent_t e : *ev) if (e) cudaEventDestroy(e);
+        h->hInT[p].release(); h->hDescT[p].release(); h->hKpsT[p].release(); h->hCountsT[p].release();
+    }
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
     h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
-    h->hIn.release(); h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
+    h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     for (int i = 0; i < ORBX_LANES; i++) {
         orbx_extractor::Lane &ln = h->lane[i];
         cudaEvent_t evs[6] = {ln.evFork, ln.evJoin, ln.evFast0, ln.evPyr, ln.evStart, ln.evDone};
@@ -737,37 +759,90 @@ int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const ui
     return ORBX_OK;
 }
 
-// Host entry point.  The batch is cut into chunks that flow through three streams -- H2D of chunk
-// c+1, kernels of chunk c and D2H of chunk c-1 overlap -- and the host copies finished chunks into
-// the caller's arrays while later chunks are still on the GPU.
-int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
-                       size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
+} // extern "C"
+
+namespace {
+
+// Host entry points.  A call is cut into chunks that flow through three streams -- H2D of chunk c+1, kernels of chunk c
+// and D2H of chunk c-1 overlap.  orbx_extract_batch_async only ENQUEUES a call and hands back a ticket; orbx_wait blocks
+// until that call's results are in the caller's arrays.  Two calls may be in flight: while the tail of call k (last
+// chunks' kernels, last D2H) drains, the H2D of call k+1 already runs, so the copy engine feeding the GPU never idles
+// between calls (the reference has the same shape: extract in threads, consume later, orbframe.cpp:73-78).
+// Both calls share ONE set of device arenas; a chunk of call k+1 depends, through events, only on the chunks of call k that
+// cover the same frame slots: its H2D waits for their kernels (which consumed the staged input), its kernels wait for their
+// D2H (which read the result records).  Host-side staging (callers without pinned buffers) is double-buffered by ticket parity.
+int finishTicket(orbx_extractor *h, int p)
+{
+    orbx_extractor::Ticket &t = h->tk[p];
+    if (!t.active) return ORBX_OK;
+    t.active = false;
+    CK(cudaSetDevice(h->cfg.device));
+    int status = ORBX_OK;
+    const int stride = t.kpStride;
+    for (size_t c = 0; c + 1 < t.cb.size(); c++) {
+        const int f0 = t.cb[c], f1 = t.cb[c + 1];
+        if (f1 <= f0) continue;
+        CK(cudaEventSynchronize(h->evOut[p][c]));
+        for (int f = f0; f < f1; f++) {
+            const int n = h->hCountsT[p].p[f];
+            if (n > t.kp_cap) {
+                char msg[128];
+                snprintf(msg, sizeof msg, "frame %d produced %d keypoints, kp_cap is %d", f, n, t.kp_cap);
+                status = fail(h, ORBX_ERR_CAPACITY, msg);
+                continue;
+            }
+            if (!t.directOut) {
+                memcpy(t.kps + (size_t)f * t.kp_cap, h->hKpsT[p].p + (size_t)f * stride, sizeof(orbx_keypoint) * n);
+                memcpy(t.desc + (size_t)f * t.kp_cap * 32, h->hDescT[p].p + (size_t)f * stride * 32, (size_t)n * 32);
+            }
+            t.n_out[f] = n;
+        }
+    }
+    return status;
+}
+
+} // namespace
+
+extern "C" {
+
+int orbx_extract_batch_async(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
+                             size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out, int *ticket)
 {
     if (!h) return ORBX_ERR_ARG;
-    if (!imgs || !kps || !desc || !n_out || batch < 1 || batch > h->cfg.max_batch || width < 1 || height < 1 ||
+    if (!imgs || !kps || !desc || !n_out || !ticket || batch < 1 || batch > h->cfg.max_batch || width < 1 || height < 1 ||
         pitch < (size_t)width || kp_cap < 1)
         return fail(h, ORBX_ERR_ARG, "bad argument");
     for (int f = 0; f < batch; f++) if (!imgs[f]) return fail(h, ORBX_ERR_ARG, "null image pointer");
-    struct timespec tsB;
-    clock_gettime(CLOCK_MONOTONIC, &tsB);
     CK(cudaSetDevice(h->cfg.device));
+    const int id = h->nextTicket, p = id & 1;
+    // at most two calls in flight: the call before the previous one is completed here if the caller has not waited for it
+    int rc = finishTicket(h, p);
+    if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
     CK(drainLast(h));                 // a device-resident call on a caller's stream may still be using the arenas
-    int rc = setGeometry(h, width, height);
+    if (width != h->curW || height != h->curH || !h->geomUploaded) {
+        // another image size re-lays the arenas: nothing of the previous call may still be moving
+        CK(cudaStreamSynchronize(h->streamIn));
+        CK(cudaStreamSynchronize(h->streamOut));
+        h->prevCb.clear();
+    }
+    rc = setGeometry(h, width, height);
     if (rc != ORBX_OK) return rc;
     rc = ensureArenas(h, batch);
     if (rc != ORBX_OK) return rc;
     const OrbxLayout &L = h->L;
     const size_t frameBytes = (size_t)width * height;
     CK(h->dIn.ensure(frameBytes * batch + 64));
-    CK(h->hKps.ensure((size_t)L.kpStride * batch));
-    CK(h->hDesc.ensure((size_t)L.kpStride * batch * 32));
-    CK(h->hCounts.ensure((size_t)batch));
+    CK(h->hCountsT[p].ensure((size_t)std::max(batch, h->cfg.max_batch)));
     const bool pinnedIn = isPinned(imgs[0]) && isPinned(imgs[batch - 1]);
-    if (!pinnedIn) CK(h->hIn.ensure(frameBytes * batch));
+    if (!pinnedIn) CK(h->hInT[p].ensure(frameBytes * batch));
     // results can be DMA'd straight into the caller's arrays when those are pinned and use our stride
     const bool directOut = kp_cap == L.kpStride && isPinned(kps) && isPinned(desc);
-    orbx_keypoint_pod *hk = directOut ? (orbx_keypoint_pod *)kps : h->hKps.p;
-    uint8_t *hd = directOut ? desc : h->hDesc.p;
+    if (!directOut) {
+        CK(h->hKpsT[p].ensure((size_t)L.kpStride * batch));
+        CK(h->hDescT[p].ensure((size_t)L.kpStride * batch * 32));
+    }
+    orbx_keypoint_pod *hk = directOut ? (orbx_keypoint_pod *)kps : h->hKpsT[p].p;
+    uint8_t *hd = directOut ? desc : h->hDescT[p].p;
 
     // chunk boundaries: cb[c] .. cb[c+1].  ORBX_CHUNK_PLAN="4,12,16,..." gives explicit sizes (the last chunk takes the rest),
     // ORBX_CHUNKS=n gives n equal chunks
@@ -779,11 +854,11 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
     std::vector<int> cb;
     if (const char *e = getenv("ORBX_CHUNK_PLAN")) {
         cb.push_back(0);
-        for (const char *p = e; *p && cb.back() < batch;) {
-            const int v = atoi(p);
+        for (const char *q = e; *q && cb.back() < batch;) {
+            const int v = atoi(q);
             if (v > 0) cb.push_back(std::min(batch, cb.back() + v));
-            while (*p && *p != ',') p++;
-            if (*p == ',') p++;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
         }
         if (cb.back() < batch) cb.push_back(batch);
         nChunks = (int)cb.size() - 1;
@@ -791,24 +866,25 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         for (int c = 0; c <= nChunks; c++) cb.push_back((int)((long long)batch * c / nChunks));
     }
     static const int nLanes = getenv("ORBX_LANES") ? std::max(1, std::min(ORBX_LANES, atoi(getenv("ORBX_LANES")))) : 3;
-    if ((int)h->evChunk.size() < 2 * nChunks) {
-        const size_t old = h->evChunk.size();
-        h->evChunk.resize(2 * nChunks, nullptr);
-        for (size_t i = old; i < h->evChunk.size(); i++) CK(cudaEventCreateWithFlags(&h->evChunk[i], cudaEventDisableTiming));
-    }
+    for (std::vector<cudaEvent_t> *ev : {&h->evIn[p], &h->evK[p], &h->evOut[p]})
+        while ((int)ev->size() < nChunks) {
+            cudaEvent_t e = nullptr;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev->push_back(e);
+        }
     cudaStream_t sIn = h->streamIn, sOut = h->streamOut;
     h->lastLaunches = 0;
-    static const bool trace = getenv("ORBX_TRACE") != nullptr;
-    if (trace) {
-        while ((int)h->evTrace.size() < 1 + 3 * nChunks) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->evTrace.push_back(e); }
-        CK(cudaEventRecord(h->evTrace[0], sIn));
-    }
     static const bool useGraphs = !(getenv("ORBX_NO_GRAPH") && atoi(getenv("ORBX_NO_GRAPH")));
+    const int pp = p ^ 1;                                       // parity of the previous call (its events)
+    const std::vector<int> &pcb = h->prevCb;
     for (int c = 0; c < nChunks; c++) {
         const int f0 = cb[c], f1 = cb[c + 1];
         const int nf = f1 - f0;
         if (nf <= 0) continue;
-        // ---- H2D into the tight staging buffer: one copy per run of frames that are contiguous on the host
+        // ---- H2D into the tight staging buffer, once the previous call's kernels have consumed these slots
+        for (size_t j = 0; j + 1 < pcb.size(); j++)
+            if (pcb[j] < f1 && pcb[j + 1] > f0 && pcb[j + 1] > pcb[j]) CK(cudaStreamWaitEvent(sIn, h->evK[pp][j], 0));
+        // one copy per run of frames that are contiguous on the host
         for (int f = f0; f < f1;) {
             int g = f + 1;
             if (pitch == (size_t)width && pinnedIn)
@@ -819,19 +895,21 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
             } else if (pinnedIn) {
                 CK(cudaMemcpy2DAsync(dst, width, imgs[f], pitch, width, height, cudaMemcpyHostToDevice, sIn));
             } else {
-                uint8_t *stage = h->hIn.p + (size_t)f * frameBytes;
+                uint8_t *stage = h->hInT[p].p + (size_t)f * frameBytes;
                 for (int y = 0; y < height; y++) memcpy(stage + (size_t)y * width, imgs[f] + (size_t)y * pitch, width);
                 CK(cudaMemcpyAsync(dst, stage, frameBytes, cudaMemcpyHostToDevice, sIn));
             }
             f = g;
         }
-        CK(cudaEventRecord(h->evChunk[2 * c], sIn));
-        if (trace) CK(cudaEventRecord(h->evTrace[1 + 3 * c], sIn));
-        // ---- kernels of this chunk (chunks alternate between the two lanes)
-        const int li = c % nLanes;
+        CK(cudaEventRecord(h->evIn[p][c], sIn));
+        // ---- kernels of this chunk (chunks rotate over the lanes, across calls too), once the previous call's results
+        // of these slots have left for the host
+        const int li = (int)(h->chunkSeq++ % (unsigned)nLanes);
         const orbx_extractor::Lane &ln = h->lane[li];
         cudaStream_t sK = ln.main;
-        CK(cudaStreamWaitEvent(sK, h->evChunk[2 * c], 0));
+        CK(cudaStreamWaitEvent(sK, h->evIn[p][c], 0));
+        for (size_t j = 0; j + 1 < pcb.size(); j++)
+            if (pcb[j] < f1 && pcb[j + 1] > f0 && pcb[j + 1] > pcb[j]) CK(cudaStreamWaitEvent(sK, h->evOut[pp][j], 0));
         if (useGraphs) {
             cudaGraphExec_t g = nullptr;
             int nl = 0;
@@ -844,58 +922,48 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
             rc = enqueuePipeline(h, f0, nf, sK, ln);
             if (rc != ORBX_OK) return rc;
         }
-        CK(cudaEventRecord(h->evChunk[2 * c + 1], sK));
-        if (trace) CK(cudaEventRecord(h->evTrace[2 + 3 * c], sK));
+        CK(cudaEventRecord(h->evK[p][c], sK));
         // ---- D2H of this chunk's results
-        CK(cudaStreamWaitEvent(sOut, h->evChunk[2 * c + 1], 0));
-        CK(cudaMemcpyAsync(h->hCounts.p + f0, h->dCounts.p + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, sOut));
+        CK(cudaStreamWaitEvent(sOut, h->evK[p][c], 0));
+        CK(cudaMemcpyAsync(h->hCountsT[p].p + f0, h->dCounts.p + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, sOut));
         CK(cudaMemcpyAsync(hk + (size_t)f0 * L.kpStride, h->dKps.p + (size_t)f0 * L.kpStride,
                            sizeof(orbx_keypoint_pod) * (size_t)L.kpStride * nf, cudaMemcpyDeviceToHost, sOut));
         CK(cudaMemcpyAsync(hd + (size_t)f0 * L.kpStride * 32, h->dDesc.p + (size_t)f0 * L.kpStride * 32,
                            (size_t)L.kpStride * nf * 32, cudaMemcpyDeviceToHost, sOut));
-        CK(cudaEventRecord(h->evChunk[2 * c], sOut));   // reuse: the H2D event of this chunk has been consumed
-        if (trace) CK(cudaEventRecord(h->evTrace[3 + 3 * c], sOut));
+        CK(cudaEventRecord(h->evOut[p][c], sOut));
     }
     h->lastBatch = batch;
-    struct timespec tsE;
-    if (trace) clock_gettime(CLOCK_MONOTONIC, &tsE);
-    int status = ORBX_OK;
-    for (int c = 0; c < nChunks; c++) {
-        const int f0 = cb[c], f1 = cb[c + 1];
-        if (f1 <= f0) continue;
-        CK(cudaEventSynchronize(h->evChunk[2 * c]));
-        for (int f = f0; f < f1; f++) {
-            const int n = h->hCounts.p[f];
-            if (n > kp_cap) {
-                char msg[128];
-                snprintf(msg, sizeof msg, "frame %d produced %d keypoints, kp_cap is %d", f, n, kp_cap);
-                status = fail(h, ORBX_ERR_CAPACITY, msg);
-                continue;
-            }
-            if (!directOut) {
-                memcpy(kps + (size_t)f * kp_cap, h->hKps.p + (size_t)f * L.kpStride, sizeof(orbx_keypoint) * n);
-                memcpy(desc + (size_t)f * kp_cap * 32, h->hDesc.p + (size_t)f * L.kpStride * 32, (size_t)n * 32);
-            }
-            n_out[f] = n;
-        }
+    orbx_extractor::Ticket &t = h->tk[p];
+    t.active = true; t.id = id; t.batch = batch; t.kp_cap = kp_cap; t.kpStride = L.kpStride; t.directOut = directOut;
+    t.kps = kps; t.desc = desc; t.n_out = n_out; t.cb = cb;
+    h->prevCb = cb;
+    h->asyncParity = p;
+    h->nextTicket = id + 1;
+    *ticket = id;
+    return ORBX_OK;
+}
+
+int orbx_wait(orbx_extractor *h, int ticket)
+{
+    if (!h) return ORBX_ERR_ARG;
+    const int p = ticket & 1;
+    if (ticket < 1 || !h->tk[p].active || h->tk[p].id != ticket) return fail(h, ORBX_ERR_ARG, "unknown ticket, or a ticket that has been waited for already");
+    return finishTicket(h, p);
+}
+
+int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch, int width, int height,
+                       size_t pitch, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
+{
+    if (!h) return ORBX_ERR_ARG;
+    // the synchronous call: nothing else in flight when it returns (an outstanding asynchronous call is completed first)
+    for (int p = 0; p < 2; p++) {
+        const int rc = finishTicket(h, (h->nextTicket + p) & 1);
+        if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
     }
-    CK(cudaStreamSynchronize(sOut));
-    for (int i = 0; i < nLanes; i++) CK(cudaStreamSynchronize(h->lane[i].main));
-    if (trace) {
-        struct timespec tsD;
-        clock_gettime(CLOCK_MONOTONIC, &tsD);
-        for (int c = 0; c < nChunks; c++) {
-            float a = 0, b = 0, d = 0;
-            cudaEventElapsedTime(&a, h->evTrace[0], h->evTrace[1 + 3 * c]);
-            cudaEventElapsedTime(&b, h->evTrace[0], h->evTrace[2 + 3 * c]);
-            cudaEventElapsedTime(&d, h->evTrace[0], h->evTrace[3 + 3 * c]);
-            fprintf(stderr, "[orbx]   chunk %d: h2d done %.3f, kernels done %.3f, d2h done %.3f ms\n", c, a, b, d);
-        }
-        fprintf(stderr, "[orbx] batch %d: enqueue %.3f ms, drain %.3f ms\n", batch,
-                (tsE.tv_sec - tsB.tv_sec) * 1e3 + (tsE.tv_nsec - tsB.tv_nsec) * 1e-6,
-                (tsD.tv_sec - tsE.tv_sec) * 1e3 + (tsD.tv_nsec - tsE.tv_nsec) * 1e-6);
-    }
-    return status;
+    int ticket = 0;
+    const int rc = orbx_extract_batch_async(h, imgs, batch, width, height, pitch, kps, kp_cap, desc, n_out, &ticket);
+    if (rc != ORBX_OK) return rc;
+    return orbx_wait(h, ticket);
 }
 
 int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out)
@@ -935,6 +1003,8 @@ int orbx_filter_keypoints(orbx_extractor *h, int frame0, int n_frames, const flo
     CK(cudaSetDevice(h->cfg.device));
     CK(orderAfterLast(h, h->stream));
     CK(launch_filter_keypoints(h->dKps.p, h->dDesc.p, h->dCounts.p, h->L.kpStride, frame0, n_frames, box, h->stream));
+    // the next extraction may run on another lane of this handle: it must not overwrite the records while they are compacted
+    CK(cudaStreamSynchronize(h->stream));
     return ORBX_OK;
 }
 

@@ -35,6 +35,7 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
+           "orbx_extract_batch_async", "orbx_wait",
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
@@ -58,6 +59,8 @@ def lib():
     L.orbx_last_error.argtypes = [vp]
     L.orbx_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, ip]
     L.orbx_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
+    L.orbx_extract_batch_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp, ip]
+    L.orbx_wait.argtypes = [vp, C.c_int]
     L.orbx_last_launches.argtypes = [vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
@@ -179,6 +182,18 @@ class Extractor:
         self._check(lib().orbx_extract_batch(self._h, ptrs, n, width, height, pitch, kps.ctypes.data, kps.shape[1],
                                              desc.ctypes.data, counts.ctypes.data))
         return out
+
+    def extract_batch_async(self, ptrs, n, width, height, pitch, out):
+        """orbx_extract_batch_async: enqueue the call and return its ticket; `out` and the frames stay untouched until wait()."""
+        kps, desc, counts = out
+        t = C.c_int()
+        self._check(lib().orbx_extract_batch_async(self._h, ptrs, n, width, height, pitch, kps.ctypes.data, kps.shape[1],
+                                                   desc.ctypes.data, counts.ctypes.data, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        """orbx_wait: block until the call behind `ticket` has delivered its results."""
+        self._check(lib().orbx_wait(self._h, int(ticket)))
 
     def extract_batch_device(self, dptr, frame_stride, pitch, batch, width, height, stream=None):
         """Frames already in HBM (raw device pointer); results stay in HBM (see device_results)."""

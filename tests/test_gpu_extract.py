@@ -344,6 +344,67 @@ def test_refused_geometry_leaves_the_handle_usable(oracle):
     ex.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_async_calls_two_in_flight(oracle, pinned):
+    """orbx_extract_batch_async / orbx_wait: two calls in flight on one handle (call k+1 submitted before call k is waited
+    for), different frames and batch sizes in turn, pinned buffers (direct DMA) and pageable ones (the handle's staging,
+    double-buffered).  Every call's results equal the synchronous call's; a third submit completes the oldest ticket."""
+    import torch
+    import orbx
+    cfg = CONFIGS["kitti"]
+    w, h = cfg["w"], cfg["h"]
+    ex = _mk(orbx, cfg, batch=24)
+    ref = _mk(orbx, cfg, batch=24)
+    cap = ex.max_keypoints
+    sizes = [24, 17, 24, 3, 24, 24, 9]
+    frames = [synth.frames(60 + k, w, h, b) for k, b in enumerate(sizes)]
+
+    def buffers(b):
+        if pinned:
+            return (torch.zeros(b * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(b, cap),
+                    torch.zeros((b, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(b, np.int32))
+        return (np.zeros((b, cap + 5), orbx.KP_DTYPE), np.zeros((b, cap + 5, 32), np.uint8), np.zeros(b, np.int32))
+
+    def host_frames(fr):
+        if not pinned:
+            return fr
+        hb = torch.empty((len(fr), h, w), dtype=torch.uint8).pin_memory()
+        for i, f in enumerate(fr):
+            hb[i] = torch.from_numpy(f)
+        return [hb[i].numpy() for i in range(len(fr))]
+
+    outs = [buffers(b) for b in sizes]
+    held = [host_frames(fr) for fr in frames]
+    ptrs = [orbx.Extractor.frame_pointers(fr) for fr in held]
+    tickets = []
+    for k, b in enumerate(sizes):
+        tickets.append(ex.extract_batch_async(ptrs[k], b, w, h, w, outs[k]))
+        if k >= 1 and k != 4:
+            ex.wait(tickets[k - 1])                  # call k is in flight while call k-1 is collected
+    # call 3 was never waited for explicitly when call 5 was submitted: the library completed it (same slot); 6 is still open
+    with pytest.raises(orbx.OrbxError):
+        ex.wait(tickets[3])
+    ex.wait(tickets[6])
+    with pytest.raises(orbx.OrbxError):
+        ex.wait(tickets[6])
+    for k, b in enumerate(sizes):
+        kr, dr, cr = ref.extract_batch(frames[k])
+        ko, do, co = outs[k]
+        assert np.array_equal(co, cr), f"call {k}"
+        for f in range(b):
+            n = int(cr[f])
+            assert ko[f][:n].tobytes() == kr[f][:n].tobytes() and np.array_equal(do[f][:n], dr[f][:n]), f"call {k} frame {f}"
+    oex = oracle.Extractor(nfeatures=cfg["nfeatures"], nlevels=cfg["nlevels"])
+    _compare_frame(oracle, ref, oex, frames[6][8], 8, outs[6][0][8], outs[6][1][8], int(outs[6][2][8]), stages=False)
+    # the synchronous call and the device-resident consumers after asynchronous traffic
+    t = ex.extract_batch_async(ptrs[0], 24, w, h, w, outs[0])
+    k2, d2, c2 = ex.extract_batch(frames[1])
+    assert np.array_equal(c2, ref.extract_batch(frames[1])[2])
+    with pytest.raises(orbx.OrbxError):
+        ex.wait(t)                                   # the synchronous call completed everything that was in flight
+    ex.close(); ref.close()
+
+
 def test_alternating_sizes_and_batches_on_one_handle(oracle):
     """One handle fed frames of different sizes and batch sizes in turn: geometry tables, tensor maps and the captured
     chunk graphs must follow every change."""
