@@ -570,25 +570,53 @@ def main():
     d_loc = torch.empty((nq_loc, 4), dtype=torch.int32, device=dev)
     d_all = torch.empty((world * nq_loc, 4), dtype=torch.int32, device=dev)
 
-    def step_match():
-        m.knn2_device(dq.data_ptr(), nq_loc, dt_.data_ptr(), NT, d_loc.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                shard.gather_match_records(d_loc, NQ, out=d_all)
+    # N > 1: the gather is fused into the matching kernel -- every rank's kernel stores its records into the result window
+    # of every rank through NVLink (CUDA IPC mappings), no collective call (orbm_knn2_sharded); the NCCL all_gather of the
+    # separate-kernel path is timed beside it
+    if world > 1:
+        handle = m.window_create(NQ, world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        for r in range(world):
+            if r != rank:
+                m.window_attach_ipc(r, handles[r])
+        dist.barrier()
 
-    for _ in range(max(args.warmup, 3)):
-        step_match()
-    barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def step_match():
+        if world > 1:
+            m.knn2_sharded(dq.data_ptr(), qhi - qlo, qlo, dt_.data_ptr(), NT, stream.cuda_stream)
+        else:
+            m.knn2_device(dq.data_ptr(), nq_loc, dt_.data_ptr(), NT, d_loc.data_ptr(), stream.cuda_stream)
+
+    def step_match_nccl():
+        m.knn2_device(dq.data_ptr(), nq_loc, dt_.data_ptr(), NT, d_loc.data_ptr(), stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            shard.gather_match_records(d_loc, NQ, out=d_all)
+
+    def time_match(fn, n):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            fn()
+        b.record(stream)
+        barrier()
+        return a.elapsed_time(b)
+
     msteps = max(args.steps, 20)
-    m0.record(stream)
-    for _ in range(msteps):
-        step_match()
-    m1.record(stream)
-    barrier()
-    ms_match = m0.elapsed_time(m1)
+    ms_match = time_match(step_match, msteps)
+    ms_match_nccl = time_match(step_match_nccl, msteps) if world > 1 else 0.0
+    if world > 1:
+        m.window_status(stream.cuda_stream)
     # parity of the matching result every rank now holds: against the unsharded single-GPU answer, and against the oracle
-    got = (d_all if world > 1 else d_loc)[:NQ].cpu().numpy()
+    if world > 1:
+        got = m.window_fetch(NQ, stream.cuda_stream)                 # what the fused kernels left in THIS rank's window
+        if not np.array_equal(got[:, :3], d_all[:NQ].cpu().numpy()[:, :3]):
+            raise ParityError("peer-stored match records differ from the NCCL-gathered ones")
+    else:
+        got = d_loc[:NQ].cpu().numpy()
     dq_all = torch.from_numpy(q).to(dev)
     d_one = torch.empty((NQ, 4), dtype=torch.int32, device=dev)
     m.knn2_device(dq_all.data_ptr(), NQ, dt_.data_ptr(), NT, d_one.data_ptr(), stream.cuda_stream)
@@ -604,6 +632,20 @@ def main():
     parity["knn2_vs_oracle_queries"] = len(pick_q)
     popc_rate = m.measure_popc()
 
+    # ---- the library's own multi-GPU entry points, one process over all GPUs (the other ranks keep their GPUs idle meanwhile)
+    lib_multi = None
+    if world > 1 and not args.quick:
+        store = dist.distributed_c10d._get_default_store()
+        barrier()
+        if rank == 0:
+            try:
+                lib_multi = measure_library_multi(args, world, torch, orbx, oracle_mod, q, t, one)
+            finally:
+                store.set("orbx_lib_multi_done", "1")
+        else:
+            store.wait(["orbx_lib_multi_done"])
+        barrier()
+
     # ---- "next" rows, rank 0 only, reported beside the headline
     next_rows = None
     if rank == 0 and not args.quick:
@@ -612,6 +654,7 @@ def main():
     # ---- max over ranks
     keys = ["ms_dev", "s_e2e", "s_e2e_sync"]
     vals = [head[k] for k in keys] + [ms_match] + ([head["sustained"]["ms"]] if "sustained" in head else [0.0])
+    ms_match_nccl = max_over_ranks([ms_match_nccl])[0]
     vals += [strong["ms_dev"], strong["s_e2e"]] if strong else [0.0, 0.0]
     for name in ("hd", "uhd"):
         vals += [others[name]["ms_dev"], others[name]["s_e2e"], others[name]["s_e2e_sync"]] if name in others else [0.0, 0.0, 0.0]
@@ -685,7 +728,13 @@ def main():
                                        "over the ranks against the unsharded single-GPU answer and sampled queries against the oracle"),
             "matching": {"metric": "Hamming kNN-2 pairs/s (2000 x 100000)", "value": pairs, "unit": "pairs/s",
                          "queries_per_s": NQ * msteps / (ms_match * 1e-3), "ms_per_batch": ms_match / msteps,
-                         "scaling": "strong", "sharding": f"{nq_loc} queries per GPU, train replicated, all_gather of 16-byte records" if world > 1 else "single GPU",
+                         "scaling": "strong",
+                         "sharding": (f"{nq_loc} queries per GPU, train replicated; ONE kernel per GPU matches its block and stores the 16-byte records into "
+                                      "every rank's result window through NVLink peer mappings (CUDA IPC), flag + wait in the kernel, no collective call "
+                                      "(orbm_knn2_sharded)") if world > 1 else "single GPU",
+                         "nccl_all_gather_path": None if world == 1 else {
+                             "ms_per_batch": ms_match_nccl / msteps, "value": NQ * NT * msteps / (ms_match_nccl * 1e-3), "unit": "pairs/s",
+                             "what": "two kernels + dist.all_gather_into_tensor of the records (round 1's path), same queries"},
                          "roofline": {"bound": "int", "achieved": pairs / world, "peak": int_peak, "unit": "pairs/s/GPU",
                                       "frac": pairs / world / int_peak, "popc_per_clk_per_sm": popc_rate,
                                       "peak_source": "148 SM x max SM clock x POPC lanes/clk/SM measured on this GPU (orbm_measure_popc) / 8 POPC per pair"}},
@@ -727,6 +776,7 @@ def main():
                                        "whole_step_frac": ba * b / (md / steps * 1e-3) / 1e9 / peak},
                           "stages_ms": st, "gpu_launches_per_step": o["launches_per_step"]}
         line["configs"] = cfgs
+        line["library_multi_gpu"] = lib_multi
         line["next_rows"] = next_rows
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference()
@@ -756,6 +806,69 @@ def main():
     ex.close(); m.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_library_multi(args, world, torch, orbx, oracle_mod, q, t, one):
+    """The multi-GPU entry points of the library itself, driven by ONE process (rank 0) over all `world` GPUs while the other
+    ranks idle: orbx_multi_extract_batch_async (frames of a host batch sharded over the GPUs, one host thread per GPU inside
+    the library) and orbm_multi_knn2 (query blocks, records exchanged by the kernels through peer stores)."""
+    cfg = CONFIGS["kitti"]
+    w, h, nf, nl = cfg["w"], cfg["h"], cfg["nf"], cfg["nl"]
+    res = {}
+    devices = list(range(world))
+    oex = oracle_mod.Extractor(nfeatures=nf, nlevels=nl)
+    base = synth_frames("kitti")
+    for key, batch in (("weak", BATCH * world), ("strong", BATCH)):
+        mx = orbx.MultiExtractor(devices, nf, 1.2, nl, 20, 7, max_width=w, max_height=h, max_batch=batch)
+        cap = mx.max_keypoints
+        pool = 3
+        hosts, frames_of = [], []
+        for p in range(pool):
+            hb = torch.empty((batch, h, w), dtype=torch.uint8).pin_memory()
+            fr = []
+            for f in range(batch):
+                src = base[(f + 5 * p) % len(base)]
+                img = np.roll(src, 2 * p + f // len(base), axis=1)
+                hb[f] = torch.from_numpy(img)
+                fr.append(img)
+            hosts.append(hb); frames_of.append(fr)
+        ptrs = [orbx.Extractor.frame_pointers([hb[f].numpy() for f in range(batch)]) for hb in hosts]
+        outs = [(torch.zeros(batch * cap * 28, dtype=torch.uint8).pin_memory().numpy().view(orbx.KP_DTYPE).reshape(batch, cap),
+                 torch.zeros((batch, cap, 32), dtype=torch.uint8).pin_memory().numpy(), np.zeros(batch, np.int32)) for _ in range(2)]
+
+        def run(n):
+            prev = None
+            for i in range(n):
+                tk = mx.extract_batch_async(ptrs[i % pool], batch, w, h, w, outs[i & 1])
+                if prev is not None:
+                    mx.wait(prev)
+                prev = tk
+            mx.wait(prev)
+        run(args.warmup)
+        t0 = time.perf_counter()
+        run(args.steps)
+        dt = time.perf_counter() - t0
+        o = outs[(args.steps - 1) & 1]
+        picks = sorted(set(int(v) for v in np.linspace(0, batch - 1, 4)))
+        check_frames(oex, frames_of[(args.steps - 1) % pool], picks, o[0], o[1], o[2], f"orbx_multi ({key})")
+        res[key] = {"value": batch * args.steps / dt, "unit": "frames/s", "frames_per_call": batch, "ms_per_call": dt / args.steps * 1e3,
+                    "parity_frames_checked": len(picks)}
+        mx.close()
+    mm = orbx.MultiMatcher(devices, NQ, NT)
+    mm.set_train(t)
+    for _ in range(3):
+        got = mm.knn2(q)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        got = mm.knn2(q)
+    dt = (time.perf_counter() - t0) / 20
+    if not (np.array_equal(got[0], one[:, 0]) and np.array_equal(got[1], one[:, 1]) and np.array_equal(got[2], one[:, 2])):
+        raise ParityError("orbm_multi_knn2 differs from the single-GPU answer")
+    mm.close()
+    res["knn2"] = {"ms_per_call": dt * 1e3, "value": NQ * NT / dt, "unit": "pairs/s",
+                   "what": "orbm_multi_knn2: 2000 host queries in, records out, train resident on every GPU; all queries equal to the single-GPU answer"}
+    res["what"] = f"one process driving {world} GPUs through orbx_multi_* / orbm_multi_* (host threads and peer windows inside liborbx), pinned host buffers, e2e"
+    return res
 
 
 def measure_next_rows(torch, orbx, ex, m, head, dev, stream, local_rank):

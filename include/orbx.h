@@ -102,6 +102,28 @@ int orbx_extract_batch_async(orbx_extractor *h, const uint8_t *const *imgs, int 
 /* ORBX_OK, or ORBX_ERR_CAPACITY when a frame produced more than kp_cap keypoints, ORBX_ERR_ARG for an unknown ticket */
 int orbx_wait(orbx_extractor *h, int ticket);
 
+/* ---- several GPUs behind one handle: frames are independent, so a batch is cut into contiguous blocks,
+ * device slot g taking frames [batch*g/G, batch*(g+1)/G); each slot owns an ordinary orbx_extractor on its GPU and a host
+ * thread that submits the slot's block, so the copies and kernels of all GPUs run side by side.  No data-path collective.
+ * cfg->max_batch is the largest batch of a call (all slots together), cfg->device is ignored; devices[] lists the CUDA
+ * ordinals (an ordinal may appear more than once).  The entry points mirror the single-GPU ones, results land in the
+ * caller's arrays exactly where orbx_extract_batch would put them; up to two asynchronous calls may be in flight. */
+typedef struct orbx_multi orbx_multi;
+int orbx_multi_create(const orbx_config *cfg, const int *devices, int n_devices, orbx_multi **out);
+void orbx_multi_destroy(orbx_multi *m);
+const char *orbx_multi_last_error(const orbx_multi *m);
+int orbx_multi_devices(const orbx_multi *m);
+int orbx_multi_max_keypoints(const orbx_multi *m);
+int orbx_multi_extract_batch(orbx_multi *m, const uint8_t *const *imgs, int batch, int width, int height, size_t pitch,
+                             orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);
+int orbx_multi_extract_batch_async(orbx_multi *m, const uint8_t *const *imgs, int batch, int width, int height, size_t pitch,
+                                   orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out, int *ticket);
+int orbx_multi_wait(orbx_multi *m, int ticket);
+/* the extractor of a slot (device-resident results, stereo matching, pyramid levels of the frames that slot extracted) and
+ * the frames of a batch it is handed */
+orbx_extractor *orbx_multi_handle(orbx_multi *m, int slot);
+int orbx_multi_frame_range(const orbx_multi *m, int batch, int slot, int *first, int *count);
+
 /* Device-resident variant: frames already in HBM (frame f at d_imgs + f*frame_stride), results
  * stay in HBM.  Work is enqueued on `stream` (a cudaStream_t, NULL = the handle's own stream)
  * and NOT synchronised.  Result pointers (valid until the next call on this handle):
@@ -199,6 +221,42 @@ int orbm_knn2_resident(orbm_matcher *m, const uint8_t *q, int nq, int32_t *idx, 
  * buffer of the result gather when queries are sharded over GPUs). */
 int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_q, int nq, const uint8_t *d_t, int nt,
                      int32_t *d_out, void *stream);
+/* ---- query-sharded kNN-2 over the GPUs of one box, the result gather fused into the kernel ----
+ * Every rank (one matcher per GPU; ranks may live in one process or in one process per GPU) holds the whole train set and
+ * a RESULT WINDOW of nq_total records.  orbm_knn2_sharded matches the rank's block of queries in ONE kernel launch whose
+ * last stage stores the 16-byte {idx, d1, d2, pad} records directly into the window of every rank -- its own and, through
+ * NVLink peer mappings, the peers' -- and then waits until the records of all ranks have arrived in its own window; no
+ * collective library is involved.  In stream order behind the call, orbm_window_records points at all nq_total records
+ * (queries in global order) on this rank's GPU.
+ *   orbm_window_create      allocates the window of `rank`; ipc_handle (64 bytes, may be NULL) receives its CUDA IPC handle
+ *   orbm_window_attach_ipc  maps the window of a peer rank that lives in ANOTHER process (handle from its orbm_window_create)
+ *   orbm_window_attach_peer maps the window of a peer rank of THIS process (enables peer access between the two devices)
+ *   orbm_knn2_sharded       d_q = this rank's nq_local queries (global indices q_offset ..), d_t = nt train rows, both on the
+ *                           matcher's device, 16-byte aligned; enqueued on `stream` (NULL = the matcher's), not synchronised.
+ *                           All ranks must make the call (a rank whose peer never arrives gives up after 5 s).
+ *   orbm_window_status      synchronises `stream` and reports a peer that did not arrive (ORBX_ERR_CUDA)
+ *   orbm_window_fetch       the same, then copies the first nq records of the last call to the host (nq x 4 int32)
+ * The window double-buffers by call parity, so a rank may already run call e+1 while a peer still reads the result of call e
+ * in kernels enqueued before its own call e+1. */
+int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, void *ipc_handle);
+int orbm_window_attach_ipc(orbm_matcher *m, int peer_rank, const void *ipc_handle);
+int orbm_window_attach_peer(orbm_matcher *m, int peer_rank, orbm_matcher *peer);
+int orbm_knn2_sharded(orbm_matcher *m, const uint8_t *d_q, int nq_local, int q_offset, const uint8_t *d_t, int nt, void *stream);
+int orbm_window_status(orbm_matcher *m, void *stream);
+int orbm_window_fetch(orbm_matcher *m, void *stream, int32_t *records, int nq);
+int orbm_window_records(orbm_matcher *m, const int32_t **d_records);
+/* The same inside ONE process: a matcher per listed device, windows attached to one another through peer access.
+ * orbm_multi_knn2: queries (host) are cut into blocks, every GPU matches its block against its copy of the train set
+ * (orbm_multi_set_train) and the kernels exchange the records among themselves; the host reads the complete result from
+ * the first GPU's window. */
+typedef struct orbm_multi orbm_multi;
+int orbm_multi_create(const int *devices, int n_devices, int max_queries, int max_train, orbm_multi **out);
+void orbm_multi_destroy(orbm_multi *mm);
+const char *orbm_multi_last_error(const orbm_multi *mm);
+int orbm_multi_devices(const orbm_multi *mm);
+int orbm_multi_set_train(orbm_multi *mm, const uint8_t *t, int nt);
+int orbm_multi_knn2(orbm_multi *mm, const uint8_t *q, int nq, int32_t *idx, int32_t *d1, int32_t *d2);
+orbm_matcher *orbm_multi_matcher(orbm_multi *mm, int slot);
 /* Candidate-list matching: the inner loop of SearchByProjection / SearchByBoW / SearchForTriangulation
  * (orbmatcher.cpp:76-114, :208-232, :1337-1483).  Query i is compared with the train rows
  * indices[offsets[i] .. offsets[i+1]) in that order (CSR); the sequential exclusion rules of the callers

@@ -97,6 +97,131 @@ __global__ void k_knn2_merge(const uint2 *__restrict__ part, int nq, int nchunks
     out[qi] = make_int4(idx, d1, d2, 0);
 }
 
+// ------------------------------------------------------------------------------------------
+// Query-sharded kNN-2 with the result gather fused into the kernel (no collective library call).
+// Rank r of n_ranks matches its block of queries against the whole (replicated) train set in ONE launch:
+//   * the grid is the (query block x train chunk) grid of k_knn2_partial; a CTA writes its per-chunk partial pairs, and the
+//     last CTA to finish a query block (ticket counter) folds the partials of that block -- there is no separate merge launch;
+//   * the folding CTA stores the 16-byte records straight into the result window of EVERY rank (its own and the peers',
+//     mapped through NVLink: peer access inside one process, CUDA IPC between processes) at the block's global offset;
+//   * the CTA that finishes the rank's last query block publishes the rank's flag (= the call's epoch) in every window with
+//     a system-scope release, then waits until all n_ranks flags of its OWN window carry the epoch.  When the launch completes
+//     in stream order, this rank's window holds the records of all ranks.
+// Windows carry two record buffers selected by the epoch's parity: a rank can be one call ahead of a peer that is still
+// consuming the previous result, never two (it cannot pass the flag wait of call e before the peer has started call e).
+// ------------------------------------------------------------------------------------------
+#define KNN_MAX_RANKS 16
+#define KNN_WIN_HDR 1024         // bytes in front of the records: one 32-bit flag per rank, 64 bytes apart
+struct KnnPeers { unsigned char *win[KNN_MAX_RANKS]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(KNN_QB)
+k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk, uint2 *part,
+               unsigned *counters /* [qBlocks + 1], zero between launches */, KnnPeers peers, int nRanks, int rank,
+               int qOffset, int nqTotal, unsigned epoch)
+{
+    __shared__ uint4 tile[KNN_TILE * 2];
+    __shared__ int isLast;
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.x * KNN_QB + tid;
+    const int t0 = blockIdx.y * chunk;
+    const int t1 = min(t0 + chunk, nt);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qi < nq) { qa = __ldg(&q[2 * qi]); qb = __ldg(&q[2 * qi + 1]); }
+    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+    for (int base = t0; base < t1; base += KNN_TILE) {
+        const int cnt = min(KNN_TILE, t1 - base);
+        __syncthreads();
+        for (int i = tid; i < cnt * 2; i += KNN_QB) tile[i] = __ldg(&t[2 * (size_t)base + i]);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+            const int d = hamming256(qa, qb, a, b);
+            const unsigned key = ((unsigned)d << KNN_IDX_BITS) | (unsigned)(base + j);
+            k2 = min(k2, max(k1, key));
+            k1 = min(k1, key);
+        }
+    }
+    if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = make_uint2(k1, k2);
+    // ---- the last CTA of this query block folds the partials (ticket pattern: partials are fenced before the ticket is taken)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) isLast = atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const int nchunks = (int)gridDim.y;
+    if (qi < nq) {
+        k1 = KNN_INIT_KEY; k2 = KNN_INIT_KEY;
+        for (int c = 0; c < nchunks; c++) {
+            const uint2 p = __ldcg(&part[(size_t)c * nq + qi]);
+            k2 = min(k2, max(k1, p.x));
+            k1 = min(k1, p.x);
+            k2 = min(k2, max(k1, p.y));
+            k1 = min(k1, p.y);
+        }
+        int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
+        int idx = (int)(k1 & KNN_IDX_MASK);
+        if (d1 >= 256) { d1 = 256; idx = -1; }
+        if (d2 >= 256) d2 = 256;
+        const int4 rec = make_int4(idx, d1, d2, 0);
+        const size_t off = KNN_WIN_HDR + ((size_t)(epoch & 1u) * nqTotal + (size_t)(qOffset + qi)) * sizeof(int4);
+        for (int r = 0; r < nRanks; r++) *(int4 *)(peers.win[r] + off) = rec;     // own window and, through NVLink, every peer's
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        counters[blockIdx.x] = 0;                                                // ready for the next launch
+        isLast = atomicAdd(&counters[gridDim.x], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!isLast) return;
+    // ---- every query block of this rank is stored everywhere: publish, then wait for the other ranks
+    if (tid == 0) counters[gridDim.x] = 0;
+    if (tid < nRanks) st_release_sys((unsigned *)(peers.win[tid] + 64 * rank), epoch);
+    if (tid < nRanks) {
+        const unsigned *f = (const unsigned *)(peers.win[rank] + 64 * tid);
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            __nanosleep(64);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 5000000000ull) {                                      // a peer never launched: give up after 5 s, loudly
+                *(unsigned *)(peers.win[rank] + KNN_WIN_HDR - 4) = 1u + (unsigned)tid;
+                break;
+            }
+        }
+    }
+}
+
+// a rank without queries of its own still takes part in the exchange: it publishes its flag and waits for the others
+__global__ void k_knn2_publish(KnnPeers peers, int nRanks, int rank, unsigned epoch)
+{
+    const int tid = threadIdx.x;
+    if (tid < nRanks) st_release_sys((unsigned *)(peers.win[tid] + 64 * rank), epoch);
+    if (tid < nRanks) {
+        const unsigned *f = (const unsigned *)(peers.win[rank] + 64 * tid);
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            __nanosleep(64);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 5000000000ull) { *(unsigned *)(peers.win[rank] + KNN_WIN_HDR - 4) = 1u + (unsigned)tid; break; }
+        }
+    }
+}
+
 __global__ void k_distance_pairs(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n, int *__restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,6 +600,13 @@ struct orbm_matcher {
     int2 *ddBest = nullptr, *ddHost = nullptr; int ddBestCap = 0;
     // orbm_search_by_projection: one workspace (frame + map points + grid + results), grown on demand
     uint8_t *spBuf = nullptr, *spHost = nullptr; size_t spCap = 0;
+    // orbm_knn2_sharded: this rank's result window, the peers' mappings, ticket counters, call epoch
+    unsigned char *win = nullptr; size_t winBytes = 0;
+    int winRanks = 0, winRank = 0, winNq = 0;
+    unsigned char *peerWin[16] = {};
+    bool peerIpc[16] = {};
+    unsigned *dCounters = nullptr; int countersCap = 0;
+    unsigned epoch = 0;
     std::string err;
 };
 
@@ -566,6 +698,9 @@ void orbm_destroy(orbm_matcher *m)
     if (m->ddHost) cudaFreeHost(m->ddHost);
     if (m->spBuf) cudaFree(m->spBuf);
     if (m->spHost) cudaFreeHost(m->spHost);
+    for (int r = 0; r < 16; r++) if (m->peerIpc[r] && m->peerWin[r]) cudaIpcCloseMemHandle(m->peerWin[r]);
+    if (m->win) cudaFree(m->win);
+    if (m->dCounters) cudaFree(m->dCounters);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -738,6 +873,142 @@ int orbm_distinctive(orbm_matcher *m, const uint8_t *desc, int n_desc, const int
     MCK(cudaMemcpyAsync(m->ddHost, m->ddBest, (size_t)n_points * sizeof(int2), cudaMemcpyDeviceToHost, m->stream));
     MCK(cudaStreamSynchronize(m->stream));
     for (int p = 0; p < n_points; p++) { best[p] = m->ddHost[p].x; if (median) median[p] = m->ddHost[p].y; }
+    return ORBX_OK;
+}
+
+
+// ---- query-sharded kNN-2 with the fused gather (k_knn2_sharded)
+int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, void *ipc_handle)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (nq_total < 1 || n_ranks < 1 || n_ranks > KNN_MAX_RANKS || rank < 0 || rank >= n_ranks) return mfail(m, ORBX_ERR_ARG, "bad argument");
+    MCK(cudaSetDevice(m->device));
+    for (int r = 0; r < 16; r++) {
+        if (m->peerIpc[r] && m->peerWin[r]) cudaIpcCloseMemHandle(m->peerWin[r]);
+        m->peerWin[r] = nullptr; m->peerIpc[r] = false;
+    }
+    if (m->win) { cudaFree(m->win); m->win = nullptr; }
+    m->winBytes = KNN_WIN_HDR + (size_t)2 * nq_total * sizeof(int4);
+    MCK(cudaMalloc((void **)&m->win, m->winBytes));
+    MCK(cudaMemset(m->win, 0, m->winBytes));
+    m->winRanks = n_ranks; m->winRank = rank; m->winNq = nq_total; m->epoch = 0;
+    m->peerWin[rank] = m->win;
+    if (ipc_handle) {
+        cudaIpcMemHandle_t hd;
+        MCK(cudaIpcGetMemHandle(&hd, m->win));
+        static_assert(sizeof(hd) == 64, "CUDA IPC handles are 64 bytes");
+        memcpy(ipc_handle, &hd, sizeof hd);
+    }
+    return ORBX_OK;
+}
+
+int orbm_window_attach_ipc(orbm_matcher *m, int peer_rank, const void *ipc_handle)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win || !ipc_handle || peer_rank < 0 || peer_rank >= m->winRanks || peer_rank == m->winRank)
+        return mfail(m, ORBX_ERR_ARG, "no window, or bad peer rank");
+    MCK(cudaSetDevice(m->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle, sizeof hd);
+    void *p = nullptr;
+    MCK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    m->peerWin[peer_rank] = (unsigned char *)p; m->peerIpc[peer_rank] = true;
+    return ORBX_OK;
+}
+
+int orbm_window_attach_peer(orbm_matcher *m, int peer_rank, orbm_matcher *peer)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win || !peer || !peer->win || peer_rank < 0 || peer_rank >= m->winRanks || peer_rank == m->winRank ||
+        peer->winRank != peer_rank || peer->winNq != m->winNq || peer->winRanks != m->winRanks)
+        return mfail(m, ORBX_ERR_ARG, "windows of the two matchers do not belong to one group");
+    MCK(cudaSetDevice(m->device));
+    if (peer->device != m->device) {
+        int can = 0;
+        MCK(cudaDeviceCanAccessPeer(&can, m->device, peer->device));
+        if (!can) return mfail(m, ORBX_ERR_CUDA, "no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return mfail(m, ORBX_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    m->peerWin[peer_rank] = peer->win; m->peerIpc[peer_rank] = false;
+    return ORBX_OK;
+}
+
+int orbm_knn2_sharded(orbm_matcher *m, const uint8_t *d_q, int nq_local, int q_offset, const uint8_t *d_t, int nt, void *stream)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win) return mfail(m, ORBX_ERR_ARG, "no result window (orbm_window_create)");
+    if ((nq_local > 0 && (!d_q || !d_t)) || nq_local < 0 || q_offset < 0 || q_offset + nq_local > m->winNq || nt < 1 || nt > (int)KNN_IDX_MASK - 1)
+        return mfail(m, ORBX_ERR_ARG, "bad argument");
+    if (((uintptr_t)d_q | (uintptr_t)d_t) & 15) return mfail(m, ORBX_ERR_ARG, "device buffers must be 16-byte aligned");
+    for (int r = 0; r < m->winRanks; r++) if (!m->peerWin[r]) return mfail(m, ORBX_ERR_ARG, "a peer's window has not been attached");
+    MCK(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->stream;
+    if (nq_local == 0) {          // no queries of its own (fewer queries than ranks): the rank still publishes and waits
+        KnnPeers pe;
+        for (int r = 0; r < KNN_MAX_RANKS; r++) pe.win[r] = r < m->winRanks ? m->peerWin[r] : nullptr;
+        m->epoch++;
+        k_knn2_publish<<<1, 32, 0, st>>>(pe, m->winRanks, m->winRank, m->epoch);
+        MCK(cudaGetLastError());
+        return ORBX_OK;
+    }
+    int qb, chunks, chunk;
+    knnGrid(m, nq_local, nt, &qb, &chunks, &chunk);
+    const size_t need = (size_t)chunks * nq_local;
+    if (need > m->partCap) {
+        if (m->dPart) cudaFree(m->dPart);
+        m->dPart = nullptr; m->partCap = 0;
+        MCK(cudaMalloc((void **)&m->dPart, need * sizeof(uint2)));
+        m->partCap = need;
+    }
+    if (qb + 1 > m->countersCap) {
+        if (m->dCounters) cudaFree(m->dCounters);
+        m->dCounters = nullptr; m->countersCap = 0;
+        MCK(cudaMalloc((void **)&m->dCounters, (size_t)(qb + 1) * sizeof(unsigned)));
+        MCK(cudaMemset(m->dCounters, 0, (size_t)(qb + 1) * sizeof(unsigned)));
+        m->countersCap = qb + 1;
+    }
+    KnnPeers peers;
+    for (int r = 0; r < KNN_MAX_RANKS; r++) peers.win[r] = r < m->winRanks ? m->peerWin[r] : nullptr;
+    m->epoch++;
+    k_knn2_sharded<<<dim3(qb, chunks), KNN_QB, 0, st>>>((const uint4 *)d_q, nq_local, (const uint4 *)d_t, nt, chunk, m->dPart, m->dCounters,
+                                                        peers, m->winRanks, m->winRank, q_offset, m->winNq, m->epoch);
+    MCK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int orbm_window_status(orbm_matcher *m, void *stream)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win) return mfail(m, ORBX_ERR_ARG, "no window");
+    MCK(cudaSetDevice(m->device));
+    MCK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : m->stream));
+    unsigned bad = 0;
+    MCK(cudaMemcpy(&bad, m->win + KNN_WIN_HDR - 4, 4, cudaMemcpyDeviceToHost));
+    if (bad) {
+        char msg[96];
+        snprintf(msg, sizeof msg, "orbm_knn2_sharded: rank %u did not deliver its records within 5 s", bad - 1);
+        return mfail(m, ORBX_ERR_CUDA, msg);
+    }
+    return ORBX_OK;
+}
+
+int orbm_window_fetch(orbm_matcher *m, void *stream, int32_t *records, int nq)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win || !records || nq < 1 || nq > m->winNq || m->epoch == 0) return mfail(m, ORBX_ERR_ARG, "no window, no call yet or bad count");
+    int rc = orbm_window_status(m, stream);
+    if (rc != ORBX_OK) return rc;
+    MCK(cudaMemcpy(records, m->win + KNN_WIN_HDR + (size_t)(m->epoch & 1u) * m->winNq * sizeof(int4), (size_t)nq * sizeof(int4), cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbm_window_records(orbm_matcher *m, const int32_t **d_records)
+{
+    if (!m) return ORBX_ERR_ARG;
+    if (!m->win || !d_records || m->epoch == 0) return mfail(m, ORBX_ERR_ARG, "no window or no call yet");
+    *d_records = (const int32_t *)(m->win + KNN_WIN_HDR + (size_t)(m->epoch & 1u) * m->winNq * sizeof(int4));
     return ORBX_OK;
 }
 
@@ -1022,5 +1293,98 @@ int orbm_assign_grid(orbm_matcher *m, const orbx_keypoint *keys, int n, float mi
     memcpy(cell_items, hb + oItems, (size_t)cell_start[FG_CELLS] * 4);
     return ORBX_OK;
 }
+
+// ---- several GPUs behind one matcher handle (one process): queries sharded, train replicated, k_knn2_sharded with peer stores
+struct orbm_multi {
+    std::vector<orbm_matcher *> m;
+    int maxQ = 0, nt = -1;
+    std::string err;
+};
+
+static int mmfail(orbm_multi *mm, int code, const std::string &msg) { if (mm) mm->err = msg; return code; }
+
+int orbm_multi_create(const int *devices, int n_devices, int max_queries, int max_train, orbm_multi **out)
+{
+    if (!out || !devices || n_devices < 1 || n_devices > KNN_MAX_RANKS || max_queries < 1 || max_train < 1) return ORBX_ERR_ARG;
+    orbm_multi *mm = new (std::nothrow) orbm_multi();
+    if (!mm) return ORBX_ERR_NOMEM;
+    *out = mm;
+    mm->maxQ = max_queries;
+    const int block = (max_queries + n_devices - 1) / n_devices;
+    for (int g = 0; g < n_devices; g++) {
+        orbm_matcher *m = nullptr;
+        int rc = orbm_create(devices[g], block, max_train, &m);
+        if (m) mm->m.push_back(m);
+        if (rc != ORBX_OK) return mmfail(mm, rc, std::string("device ") + std::to_string(devices[g]) + ": " + orbm_last_error(m));
+        rc = orbm_window_create(m, max_queries, n_devices, g, nullptr);
+        if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(m));
+    }
+    for (int g = 0; g < n_devices; g++)
+        for (int r = 0; r < n_devices; r++)
+            if (r != g) {
+                const int rc = orbm_window_attach_peer(mm->m[g], r, mm->m[r]);
+                if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(mm->m[g]));
+            }
+    return ORBX_OK;
+}
+
+void orbm_multi_destroy(orbm_multi *mm)
+{
+    if (!mm) return;
+    for (orbm_matcher *m : mm->m) if (m && m->stream) { cudaSetDevice(m->device); cudaStreamSynchronize(m->stream); }
+    for (orbm_matcher *m : mm->m) orbm_destroy(m);
+    delete mm;
+}
+
+const char *orbm_multi_last_error(const orbm_multi *mm) { return mm ? mm->err.c_str() : "null handle"; }
+int orbm_multi_devices(const orbm_multi *mm) { return mm ? (int)mm->m.size() : ORBX_ERR_ARG; }
+
+int orbm_multi_set_train(orbm_multi *mm, const uint8_t *t, int nt)
+{
+    if (!mm) return ORBX_ERR_ARG;
+    for (orbm_matcher *m : mm->m) {
+        const int rc = orbm_set_train(m, t, nt);
+        if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(m));
+    }
+    mm->nt = nt;
+    return ORBX_OK;
+}
+
+int orbm_multi_knn2(orbm_multi *mm, const uint8_t *q, int nq, int32_t *idx, int32_t *d1, int32_t *d2)
+{
+    if (!mm) return ORBX_ERR_ARG;
+    if (mm->nt < 1) return mmfail(mm, ORBX_ERR_ARG, "no resident train set (orbm_multi_set_train)");
+    if (!q || !idx || !d1 || !d2 || nq < 1 || nq > mm->maxQ) return mmfail(mm, ORBX_ERR_ARG, "bad query block");
+    const int G = (int)mm->m.size();
+    const int block = (nq + G - 1) / G;
+    // every GPU gets its block of queries and launches; the kernels exchange the records among themselves
+    for (int g = 0; g < G; g++) {
+        orbm_matcher *m = mm->m[g];
+        const int lo = std::min(g * block, nq), hi = std::min(lo + block, nq);
+        cudaError_t e = cudaSetDevice(m->device);
+        if (e == cudaSuccess && hi > lo) e = cudaMemcpyAsync(m->dQ, q + (size_t)lo * 32, (size_t)(hi - lo) * 32, cudaMemcpyHostToDevice, m->stream);
+        if (e != cudaSuccess) return mmfail(mm, ORBX_ERR_CUDA, cudaGetErrorString(e));
+        const int rc = orbm_knn2_sharded(m, m->dQ, hi - lo, lo, m->dT, mm->nt, nullptr);
+        if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(m));
+    }
+    // the complete result is in every GPU's window; the host reads GPU 0's
+    orbm_matcher *m0 = mm->m[0];
+    const int32_t *rec = nullptr;
+    int rc = orbm_window_records(m0, &rec);
+    if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(m0));
+    std::vector<int4> host((size_t)nq);
+    cudaError_t e = cudaSetDevice(m0->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), rec, (size_t)nq * sizeof(int4), cudaMemcpyDeviceToHost, m0->stream);
+    if (e != cudaSuccess) return mmfail(mm, ORBX_ERR_CUDA, cudaGetErrorString(e));
+    for (int g = 0; g < G; g++) {
+        rc = orbm_window_status(mm->m[g], nullptr);
+        if (rc != ORBX_OK) return mmfail(mm, rc, orbm_last_error(mm->m[g]));
+    }
+    for (int i = 0; i < nq; i++) { idx[i] = host[i].x; d1[i] = host[i].y; d2[i] = host[i].z; }
+    return ORBX_OK;
+}
+
+/* the matcher of device slot g (its window holds the complete result after orbm_multi_knn2) */
+orbm_matcher *orbm_multi_matcher(orbm_multi *mm, int g) { return mm && g >= 0 && g < (int)mm->m.size() ? mm->m[g] : nullptr; }
 
 } // extern "C"

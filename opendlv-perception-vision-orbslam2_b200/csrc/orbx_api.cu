@@ -94,6 +94,7 @@ struct orbx_extractor {
         std::vector<int> cb;           // chunk boundaries of the call
     } tk[2];
     int nextTicket = 1, asyncParity = -1;
+    bool inSyncCall = false;           // orbx_extract_batch in progress (chunk size heuristic)
     unsigned chunkSeq = 0;             // chunks rotate over the lanes across calls
     std::vector<int> prevCb;           // chunk boundaries of the last submitted call (its events: parity asyncParity)
     std::vector<cudaEvent_t> evIn[2], evK[2], evOut[2];   // per ticket parity and chunk: H2D done, kernels done, D2H done
@@ -846,9 +847,11 @@ int orbx_extract_batch_async(orbx_extractor *h, const uint8_t *const *imgs, int 
 
     // chunk boundaries: cb[c] .. cb[c+1].  ORBX_CHUNK_PLAN="4,12,16,..." gives explicit sizes (the last chunk takes the rest),
     // ORBX_CHUNKS=n gives n equal chunks
-    // default: chunks of about 4 MB of input (8 KITTI-sized frames) keep the H2D engine, the kernels and the D2H engine
-    // busy at the same time; measured best on B200 with three lanes (scripts/probe/e2e_plans.py)
-    const int chunkFrames = std::max(1, (int)((size_t)(4u << 20) / frameBytes));
+    // default: a synchronous call (nothing behind it to cover its tail) uses chunks of about 4 MB of input (8 KITTI-sized
+    // frames) so that the last chunk's kernels and D2H are short; with a second call in flight the tail is covered by that
+    // call's H2D and larger chunks (about 8 MB, fewer launches and copies) are faster: 104.7 k vs 99.5 k frames/s on B200
+    // (profiles/r2_e2e_plans.txt)
+    const int chunkFrames = std::max(1, (int)((size_t)(h->inSyncCall ? (4u << 20) : (8u << 20)) / frameBytes));
     int nChunks = std::max(1, std::min(16, (batch + chunkFrames - 1) / chunkFrames));
     if (const char *e = getenv("ORBX_CHUNKS")) nChunks = std::max(1, std::min(batch, atoi(e)));
     std::vector<int> cb;
@@ -961,7 +964,9 @@ int orbx_extract_batch(orbx_extractor *h, const uint8_t *const *imgs, int batch,
         if (rc != ORBX_OK && rc != ORBX_ERR_CAPACITY) return rc;
     }
     int ticket = 0;
+    h->inSyncCall = true;
     const int rc = orbx_extract_batch_async(h, imgs, batch, width, height, pitch, kps, kp_cap, desc, n_out, &ticket);
+    h->inSyncCall = false;
     if (rc != ORBX_OK) return rc;
     return orbx_wait(h, ticket);
 }

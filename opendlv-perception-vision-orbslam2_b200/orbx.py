@@ -35,11 +35,14 @@ class OrbxError(RuntimeError):
 
 _lib = None
 EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "orbx_extract", "orbx_extract_batch",
-           "orbx_extract_batch_async", "orbx_wait",
+           "orbx_extract_batch_async", "orbx_wait", "orbx_multi_create", "orbx_multi_destroy", "orbx_multi_last_error", "orbx_multi_devices",
+           "orbx_multi_max_keypoints", "orbx_multi_extract_batch", "orbx_multi_extract_batch_async", "orbx_multi_wait", "orbx_multi_handle",
+           "orbx_multi_frame_range", "orbm_multi_create", "orbm_multi_destroy", "orbm_multi_last_error", "orbm_multi_devices", "orbm_multi_set_train",
+           "orbm_multi_knn2", "orbm_multi_matcher",
            "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
-           "orbm_knn2_device", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_assign_grid", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
+           "orbm_knn2_device", "orbm_window_create", "orbm_window_attach_ipc", "orbm_window_attach_peer", "orbm_knn2_sharded", "orbm_window_status", "orbm_window_fetch", "orbm_window_records", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_assign_grid", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
            "orbv_create", "orbv_destroy", "orbv_last_error", "orbv_transform", "orbv_transform_device"]
 
 
@@ -61,6 +64,27 @@ def lib():
     L.orbx_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
     L.orbx_extract_batch_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp, ip]
     L.orbx_wait.argtypes = [vp, C.c_int]
+    L.orbx_multi_create.argtypes = [C.POINTER(Config), ip, C.c_int, C.POINTER(vp)]
+    L.orbx_multi_destroy.argtypes = [vp]
+    L.orbx_multi_last_error.restype = C.c_char_p
+    L.orbx_multi_last_error.argtypes = [vp]
+    L.orbx_multi_devices.argtypes = [vp]
+    L.orbx_multi_max_keypoints.argtypes = [vp]
+    L.orbx_multi_extract_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp]
+    L.orbx_multi_extract_batch_async.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_int, vp, vp, ip]
+    L.orbx_multi_wait.argtypes = [vp, C.c_int]
+    L.orbx_multi_handle.restype = vp
+    L.orbx_multi_handle.argtypes = [vp, C.c_int]
+    L.orbx_multi_frame_range.argtypes = [vp, C.c_int, C.c_int, ip, ip]
+    L.orbm_multi_create.argtypes = [ip, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.orbm_multi_destroy.argtypes = [vp]
+    L.orbm_multi_last_error.restype = C.c_char_p
+    L.orbm_multi_last_error.argtypes = [vp]
+    L.orbm_multi_devices.argtypes = [vp]
+    L.orbm_multi_set_train.argtypes = [vp, vp, C.c_int]
+    L.orbm_multi_knn2.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.orbm_multi_matcher.restype = vp
+    L.orbm_multi_matcher.argtypes = [vp, C.c_int]
     L.orbx_last_launches.argtypes = [vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp]
     L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
@@ -83,6 +107,13 @@ def lib():
     L.orbm_set_train.argtypes = [vp, vp, C.c_int]
     L.orbm_knn2_resident.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.orbm_knn2_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]
+    L.orbm_window_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.orbm_window_attach_ipc.argtypes = [vp, C.c_int, vp]
+    L.orbm_window_attach_peer.argtypes = [vp, C.c_int, vp]
+    L.orbm_knn2_sharded.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.orbm_window_status.argtypes = [vp, vp]
+    L.orbm_window_records.argtypes = [vp, C.POINTER(vp)]
+    L.orbm_window_fetch.argtypes = [vp, vp, vp, C.c_int]
     L.orbm_knn2_csr.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, vp]
     L.orbm_knn2_csr_device.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
     L.orbm_measure_popc.argtypes = [vp, C.POINTER(C.c_double)]
@@ -326,6 +357,37 @@ class Matcher:
         self._check(lib().orbm_knn2_device(self._h, C.c_void_p(dq), nq, C.c_void_p(dt), nt, C.c_void_p(dout),
                                            C.c_void_p(stream) if stream else None))
 
+    # ---- query-sharded kNN-2 with the gather fused into the kernel
+    def window_create(self, nq_total, n_ranks, rank):
+        """-> the 64-byte CUDA IPC handle of this rank's result window (bytes)"""
+        buf = C.create_string_buffer(64)
+        self._check(lib().orbm_window_create(self._h, nq_total, n_ranks, rank, buf))
+        self._win = (nq_total, n_ranks, rank)
+        return buf.raw
+
+    def window_attach_ipc(self, peer_rank, handle):
+        self._check(lib().orbm_window_attach_ipc(self._h, peer_rank, C.create_string_buffer(handle, 64)))
+
+    def window_attach_peer(self, peer_rank, peer):
+        self._check(lib().orbm_window_attach_peer(self._h, peer_rank, peer._h))
+
+    def knn2_sharded(self, dq, nq_local, q_offset, dt, nt, stream=None):
+        self._check(lib().orbm_knn2_sharded(self._h, C.c_void_p(dq), nq_local, q_offset, C.c_void_p(dt), nt, C.c_void_p(stream or 0)))
+
+    def window_status(self, stream=None):
+        self._check(lib().orbm_window_status(self._h, C.c_void_p(stream or 0)))
+
+    def window_fetch(self, nq, stream=None):
+        """the records of all ranks after the last knn2_sharded call -> int32 [nq, 4] = {idx, d1, d2, pad}"""
+        rec = np.zeros((nq, 4), np.int32)
+        self._check(lib().orbm_window_fetch(self._h, C.c_void_p(stream or 0), _ptr(rec), nq))
+        return rec
+
+    def window_records_ptr(self):
+        p = C.c_void_p()
+        self._check(lib().orbm_window_records(self._h, C.byref(p)))
+        return p.value
+
     def knn2_csr(self, q, t, offsets, indices):
         """Per-query candidate lists (CSR): (idx1, d1, idx2, d2) as SearchByProjection's inner loop leaves them."""
         q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
@@ -456,6 +518,107 @@ class Vocabulary:
     def transform_device(self, d_desc, stride, n, levels_up, d_out, stream=None):
         self._check(lib().orbv_transform_device(self._h, C.c_void_p(d_desc), stride, n, levels_up, C.c_void_p(d_out),
                                                 C.c_void_p(stream) if stream else None))
+
+
+class MultiExtractor:
+    """orbx_multi_*: one handle over several GPUs of the box (frames of a batch sharded over the device slots)."""
+
+    def __init__(self, devices, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, max_width=1241, max_height=376,
+                 max_batch=64, taps=None, tie_rule=0):
+        cfg = Config(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width, max_height, max_batch, 0,
+                     (C.c_int * 7)(*(taps or [0] * 7)), tie_rule)
+        self._h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        rc = lib().orbx_multi_create(C.byref(cfg), dev, len(devices), C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbx_multi_last_error(self._h).decode() if self._h else "orbx_multi_create failed"
+            if self._h:
+                lib().orbx_multi_destroy(self._h)
+            self._h = None
+            raise OrbxError(rc, msg)
+        self.n_devices = len(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbx_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OrbxError(rc, lib().orbx_multi_last_error(self._h).decode())
+
+    @property
+    def max_keypoints(self):
+        return lib().orbx_multi_max_keypoints(self._h)
+
+    def extract_batch_ptrs(self, ptrs, n, width, height, pitch, out):
+        kps, desc, counts = out
+        self._check(lib().orbx_multi_extract_batch(self._h, ptrs, n, width, height, pitch, kps.ctypes.data, kps.shape[1],
+                                                   desc.ctypes.data, counts.ctypes.data))
+        return out
+
+    def extract_batch(self, imgs, out=None):
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in imgs]
+        h, w = imgs[0].shape
+        n, cap = len(imgs), self.max_keypoints
+        if out is None:
+            out = (np.zeros((n, cap), KP_DTYPE), np.zeros((n, cap, 32), np.uint8), np.zeros(n, np.int32))
+        ptrs = Extractor.frame_pointers(imgs)
+        return self.extract_batch_ptrs(ptrs, n, w, h, w, out)
+
+    def extract_batch_async(self, ptrs, n, width, height, pitch, out):
+        kps, desc, counts = out
+        t = C.c_int()
+        self._check(lib().orbx_multi_extract_batch_async(self._h, ptrs, n, width, height, pitch, kps.ctypes.data, kps.shape[1],
+                                                         desc.ctypes.data, counts.ctypes.data, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self._check(lib().orbx_multi_wait(self._h, int(ticket)))
+
+    def frame_range(self, batch, slot):
+        a, b = C.c_int(), C.c_int()
+        self._check(lib().orbx_multi_frame_range(self._h, batch, slot, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class MultiMatcher:
+    """orbm_multi_*: query-sharded kNN-2 over several GPUs of one process, records exchanged by the kernels through peer stores."""
+
+    def __init__(self, devices, max_queries=2000, max_train=100000):
+        self._h = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        rc = lib().orbm_multi_create(dev, len(devices), max_queries, max_train, C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbm_multi_last_error(self._h).decode() if self._h else "orbm_multi_create failed"
+            if self._h:
+                lib().orbm_multi_destroy(self._h)
+            self._h = None
+            raise OrbxError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbm_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OrbxError(rc, lib().orbm_multi_last_error(self._h).decode())
+
+    def set_train(self, t):
+        t = np.ascontiguousarray(t, np.uint8)
+        self._check(lib().orbm_multi_set_train(self._h, _ptr(t), len(t)))
+
+    def knn2(self, q):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(q)
+        idx, d1, d2 = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(lib().orbm_multi_knn2(self._h, _ptr(q), n, _ptr(idx), _ptr(d1), _ptr(d2)))
+        return idx, d1, d2
 
 
 def random_vocabulary(k=10, L=3, seed=0):
