@@ -893,6 +893,25 @@ int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, voi
     MCK(cudaMemset(m->win, 0, m->winBytes));
     m->winRanks = n_ranks; m->winRank = rank; m->winNq = nq_total; m->epoch = 0;
     m->peerWin[rank] = m->win;
+    // scratch of k_knn2_sharded for the largest call this window admits, allocated HERE: cudaFree / cudaMalloc between two
+    // ranks' launches would wait for a kernel that is itself waiting for the other rank's flag (two slots on one device)
+    {
+        const int qbMax = (nq_total + KNN_QB - 1) / KNN_QB;
+        const size_t need = (size_t)m->smCount * 4 * KNN_QB + (size_t)(qbMax + 1) * KNN_QB;     // >= chunks * nq_local of knnGrid
+        if (need > m->partCap) {
+            if (m->dPart) cudaFree(m->dPart);
+            m->dPart = nullptr; m->partCap = 0;
+            MCK(cudaMalloc((void **)&m->dPart, need * sizeof(uint2)));
+            m->partCap = need;
+        }
+        if (qbMax + 1 > m->countersCap) {
+            if (m->dCounters) cudaFree(m->dCounters);
+            m->dCounters = nullptr; m->countersCap = 0;
+            MCK(cudaMalloc((void **)&m->dCounters, (size_t)(qbMax + 1) * sizeof(unsigned)));
+            MCK(cudaMemset(m->dCounters, 0, (size_t)(qbMax + 1) * sizeof(unsigned)));
+            m->countersCap = qbMax + 1;
+        }
+    }
     if (ipc_handle) {
         cudaIpcMemHandle_t hd;
         MCK(cudaIpcGetMemHandle(&hd, m->win));
@@ -955,20 +974,7 @@ int orbm_knn2_sharded(orbm_matcher *m, const uint8_t *d_q, int nq_local, int q_o
     }
     int qb, chunks, chunk;
     knnGrid(m, nq_local, nt, &qb, &chunks, &chunk);
-    const size_t need = (size_t)chunks * nq_local;
-    if (need > m->partCap) {
-        if (m->dPart) cudaFree(m->dPart);
-        m->dPart = nullptr; m->partCap = 0;
-        MCK(cudaMalloc((void **)&m->dPart, need * sizeof(uint2)));
-        m->partCap = need;
-    }
-    if (qb + 1 > m->countersCap) {
-        if (m->dCounters) cudaFree(m->dCounters);
-        m->dCounters = nullptr; m->countersCap = 0;
-        MCK(cudaMalloc((void **)&m->dCounters, (size_t)(qb + 1) * sizeof(unsigned)));
-        MCK(cudaMemset(m->dCounters, 0, (size_t)(qb + 1) * sizeof(unsigned)));
-        m->countersCap = qb + 1;
-    }
+    if ((size_t)chunks * nq_local > m->partCap || qb + 1 > m->countersCap) return mfail(m, ORBX_ERR_ARG, "scratch of the window is too small for this call");
     KnnPeers peers;
     for (int r = 0; r < KNN_MAX_RANKS; r++) peers.win[r] = r < m->winRanks ? m->peerWin[r] : nullptr;
     m->epoch++;

@@ -1,1 +1,2 @@
-for s in 1 2 3 4; do echo "SPLIT $s"; ORBX_SPLIT=$s python scripts/probe/dev_batch.py kitti 20; ORBX_SPLIT=$s python scripts/probe/dev_batch.py hd 10;  ORBX_SPLIT=$s python scripts/probe/dev_batch.py uhd 10; done
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t.log 2>&1; tail -25 gpurun_out/r2_t.log
