@@ -896,6 +896,11 @@ int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, voi
     // scratch of k_knn2_sharded for the largest call this window admits, allocated HERE: cudaFree / cudaMalloc between two
     // ranks' launches would wait for a kernel that is itself waiting for the other rank's flag (two slots on one device)
     {
+        // likewise the two kernels are loaded now: with lazy module loading the FIRST launch of a kernel may have to wait for the
+        // device to drain, i.e. for a peer slot's kernel that is waiting for this one
+        cudaFuncAttributes fa;
+        MCK(cudaFuncGetAttributes(&fa, (const void *)k_knn2_sharded));
+        MCK(cudaFuncGetAttributes(&fa, (const void *)k_knn2_publish));
         const int qbMax = (nq_total + KNN_QB - 1) / KNN_QB;
         const size_t need = (size_t)m->smCount * 4 * KNN_QB + (size_t)(qbMax + 1) * KNN_QB;     // >= chunks * nq_local of knnGrid
         if (need > m->partCap) {
@@ -911,6 +916,13 @@ int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, voi
             MCK(cudaMemset(m->dCounters, 0, (size_t)(qbMax + 1) * sizeof(unsigned)));
             m->countersCap = qbMax + 1;
         }
+        // one empty launch of each (no ranks, no queries) so that nothing is left to load at the first real call
+        KnnPeers none;
+        for (int r = 0; r < KNN_MAX_RANKS; r++) none.win[r] = nullptr;
+        k_knn2_publish<<<1, 32, 0, m->stream>>>(none, 0, 0, 0u);
+        k_knn2_sharded<<<dim3(1, 1), KNN_QB, 0, m->stream>>>(nullptr, 0, nullptr, 0, KNN_TILE, m->dPart, m->dCounters, none, 0, 0, 0, nq_total, 0u);
+        MCK(cudaGetLastError());
+        MCK(cudaStreamSynchronize(m->stream));
     }
     if (ipc_handle) {
         cudaIpcMemHandle_t hd;
