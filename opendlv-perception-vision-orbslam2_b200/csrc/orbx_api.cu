@@ -275,6 +275,7 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
             return fail(h, ORBX_ERR_SHAPE, msg);
         }
         v.wCell = (int)ceilf(width / v.nCols);
+        v.cellMagic = 65536 / std::max(v.wCell, 1) + 1;
         v.hCell = (int)ceilf(height / v.nRows);
         if (v.wCell > 60 || v.hCell > 60 || (long long)v.nCols * v.nRows >= 65536) return fail(h, ORBX_ERR_SHAPE, "FAST grid outside supported range");
         v.segBase = (int)segs.size();
@@ -303,7 +304,8 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
                 sg.ci = (uint16_t)i; sg.cj0 = (uint16_t)j0;
                 const int B0 = iniX + 3 - ((iniX - 4) & ~15);   // shared byte of the first tested pixel (TMA box is 16-byte aligned)
                 const int nQ = ((B0 + (int)sg.wT - 1) >> 2) - (B0 >> 2) + 1;
-                sg.mQ = (uint32_t)((1u << 20) / nQ + 1);
+                const int nBands = 256 / nQ;                      // FS_T / nQ bands of rows, k_fast_segs stage 1
+                sg.mQ = (uint32_t)((1u << 20) / nQ + 1) | (uint32_t)(((int)sg.hT + nBands - 1) / nBands) << 24;
                 segs.push_back(sg);
                 listCap = std::max(listCap, (int)sg.wT * (int)sg.hT);
             }
@@ -415,8 +417,10 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        cuuint32_t boxF[3] = {256, (cuuint32_t)v.winH, 1};            // FW_P x window rows of k_fast_segs
-        CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, boxF, estr,
+        // k_fast_segs reads 32-bit elements: a box of 68 x window rows (FW_P = 272 bytes per row) is wider than the 256-element limit of a byte map
+        cuuint64_t gdimF[3] = {(cuuint64_t)(v.pitch / 4), (cuuint64_t)v.h, (cuuint64_t)frames};
+        cuuint32_t boxF[3] = {68, (cuuint32_t)v.winH, 1};
+        CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)(h->dPyr.p + v.off), gdimF, gstr, boxF, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint32_t boxR[3] = {192, 48, 1};                             // RS_BOXW x RS_BOXH of k_resize

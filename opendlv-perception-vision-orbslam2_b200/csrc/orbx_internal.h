@@ -18,6 +18,7 @@ struct OrbxLevel {
     int off;             // byte offset of the level inside one frame's slab
     // gridded FAST, orbextractor.cpp:914-928
     int nCols, nRows, wCell, hCell;
+    int cellMagic;       // 65536 / wCell + 1: x / wCell == x * cellMagic >> 16 for x < 1024
     int segBase, nSegs;  // FAST segments (runs of cells in one cell row) of this level inside the segment table
     int winH;            // rows of the FAST window box (hCell + 6): height of this level's TMA box
     // DistributeOctTree, orbextractor.cpp:684-699
@@ -54,7 +55,8 @@ struct OrbxSeg {
     uint8_t hT;          // tested rows (window height - 6)
     uint8_t level;
     uint16_t ci, cj0;    // cell row / first cell column: (ci*nCols + cj) is a cell's position in the reference's emission order
-    uint32_t mQ;         // 2^20/nQ + 1, nQ = aligned 4-pixel groups covering one tested row of the run
+    uint32_t mQ;         // bits 0-23: 2^20/nQ + 1, nQ = aligned 4-pixel groups covering one tested row of the run;
+                         // bits 24-31: rows per band, ceil(hT / (256 / nQ))
 };
 
 #define ORBX_BLUR_ROWS 36       // output rows per warp band of k_blur; a tile is 4 bands

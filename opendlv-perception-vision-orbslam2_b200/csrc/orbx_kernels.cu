@@ -488,8 +488,9 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 //      isolated cv::FAST call), per-cell threshold fallback, emission
 // ------------------------------------------------------------------------------------------
 #define FS_T 256  // threads per CTA
-#define FW_P 256  // shared window pitch in bytes = TMA box width
-#define FM_P 256  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P == 256: list entries are yIn << 8 | xs)
+#define FW_P 272  // shared window pitch in bytes = TMA box width (68 words: vertical neighbours are 4 banks apart)
+#define FM_P 272  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P: list entries are yIn * FW_P + xs)
+__device__ __forceinline__ int fast_row_of(int e) { return (int)(((unsigned)e * 15421u) >> 22); }   // e / 272 for e < 17000
 
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -531,74 +532,83 @@ __device__ __forceinline__ void fast_margin2(const uint8_t *cA, const uint8_t *c
     mB = max((int)(a >> 16) - 256, 256 - (int)(b >> 16));
 }
 
-// Stage 1 of k_fast_segs.  Item i = (row, aligned 4-pixel quad) of the run; thread t takes items t, t + FS_T, ... and walks
-// them with running pointers (no division in the loop).  The survivor flags of a thread's items are collected in a
-// register (4 bits per item) and written out after ONE block-wide scan of the per-thread counts, so the survivor list
-// is in a deterministic order.  Contains __syncthreads(); call uniformly.
-template <typename BitsT>
-__device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *cand, int *wsum, int *ncand, const int tid, const int lane,
-                                                  const int B0, const int wT, const int hT, const int th, const unsigned mQ)
+// Stage 1 of k_fast_segs.  The items are (row, k-th aligned 4-pixel quad in play): all quads of the run in the first pass, the
+// quads that touch a still-empty cell (qlist) in the second.  Thread t owns quad column k = t % nQx and the band of hB
+// consecutive rows number t / nQx (R = FS_T / nQx bands, hB = ceil(hT / R); threads beyond R * nQx idle), so its border masks
+// are constants and it walks DOWN its column: the centre words of rows y-3 .. y+3 stay in registers and a row costs three word
+// loads (centre of row y+3, left and right neighbour word of row y).  Per item 4 VABSDIFF4 and bit 7 of ((d + K) | d) per
+// byte, K = 127 - th: set iff d > th.  (A byte whose sum overflows carries one into its upper neighbour, which can only turn
+// that neighbour's "d == th" into a pass -- the filter stays a superset; the overflowing byte itself has bit 7 of d set.)
+// The survivor flags of up to 8 rows are collected in a register (4 bits per item) and written out after ONE block-wide
+// scan of the per-thread counts, so the survivor list is in a deterministic order (thread, row, pixel): consecutive entries are
+// vertical neighbours, FW_P / 4 = 68 words = 4 banks apart.  Returns the number of survivors (same in every thread).
+// Contains __syncthreads(); call uniformly.
+__device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *cand, int *wsum, const uint8_t *qlist, const bool dense,
+                                                 const int nQx, const unsigned mQx, const int hB, const int tid, const int lane,
+                                                 const int B0, const int wT, const int hT, const int th)
 {
     // quads are aligned to shared-memory words: the first and last quad of a row may be partly outside
-    const int wq0 = B0 >> 2, wqL = (B0 + wT - 1) >> 2;
-    const int nQ = wqL - wq0 + 1, items = nQ * hT;
-    const uint32_t maskFirst = ~((1u << (8 * (B0 & 3))) - 1u);
-    const int nLast = ((B0 + wT - 1) & 3) + 1;
-    const uint32_t maskLast = nLast < 4 ? (1u << (8 * nLast)) - 1u : 0xffffffffu;
-    const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;   // (x & 0x7f) + K sets bit 7 iff (x & 0x7f) > th
-    const int yIn0 = (int)(((unsigned)tid * mQ) >> 20), q0 = tid - yIn0 * nQ;    // mQ = 2^20 / nQ + 1 (host)
-    const int dY = (int)(((unsigned)FS_T * mQ) >> 20), dQ = FS_T - dY * nQ;      // FS_T / nQ without a division
-    const int nMine = tid < items ? (items - tid + FS_T - 1) / FS_T : 0;        // this thread's items
-    const int stepW = dY * (FW_P / 4) + dQ, wrapW = (FW_P / 4) - nQ;              // word steps of the window pointer
-    const int stepE = dY * 256 + 4 * dQ, wrapE = 256 - 4 * nQ;                    // same steps for yIn << 8 | xs
-    BitsT bits = 0;
-    {
-        const uint32_t *rw = (const uint32_t *)(win + (yIn0 + 3) * FW_P) + wq0 + q0;
-        int q = q0;
-        for (int st = 0; st < nMine; st++) {
-            const uint32_t W0 = rw[-1], C = rw[0], W2 = rw[1];
-            const uint32_t U = rw[3 * (FW_P / 4)], D = rw[-3 * (FW_P / 4)];
-            const uint32_t d0 = __vabsdiffu4(C, U), d8 = __vabsdiffu4(C, D);
-            const uint32_t d4 = __vabsdiffu4(C, __byte_perm(C, W2, 0x6543)), d12 = __vabsdiffu4(C, __byte_perm(W0, C, 0x4321));
-            const uint32_t X = ((d0 & 0x7f7f7f7fu) + K) | d0 | ((d8 & 0x7f7f7f7fu) + K) | d8;
-            const uint32_t Y = ((d4 & 0x7f7f7f7fu) + K) | d4 | ((d12 & 0x7f7f7f7fu) + K) | d12;
-            uint32_t pass = X & Y & 0x80808080u;
-            if (q == 0) pass &= maskFirst;
-            if (q == nQ - 1) pass &= maskLast;
-            // flag bits 7,15,23,31 -> one nibble: the products land on distinct bits, the top four are the flags
-            bits |= (BitsT)((pass * 0x00204081u) >> 28) << (4 * st);
-            rw += stepW; q += dQ;
-            if (q >= nQ) { q -= nQ; rw += wrapW; }
+    const int wq0 = B0 >> 2, nQ = ((B0 + wT - 1) >> 2) - wq0 + 1;
+    const int band = (int)(((unsigned)tid * mQx) >> 20), k = tid - band * nQx;     // mQx = 2^20 / nQx + 1
+    const int R = (int)(((unsigned)FS_T * mQx) >> 20);
+    const int q = dense ? k : (int)qlist[k];
+    uint32_t mask = 0x80808080u;
+    if (q == 0) mask &= ~((1u << (8 * (B0 & 3))) - 1u);
+    if (q == nQ - 1) {
+        const int nLast = ((B0 + wT - 1) & 3) + 1;
+        if (nLast < 4) mask &= (1u << (8 * nLast)) - 1u;
+    }
+    const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;
+    constexpr int P4 = FW_P / 4;
+    int total = 0;
+    for (int rb = 0; rb < hB; rb += 8) {
+        const int y0 = band * hB + rb;                                  // first row of this thread in this round
+        const int n = band < R ? min(min(8, hB - rb), hT - y0) : 0;
+        uint32_t bits = 0;
+        if (n > 0) {
+            const uint32_t *rw = (const uint32_t *)(win + (y0 + 3) * FW_P) + wq0 + q;
+            uint32_t cm3 = rw[-3 * P4], cm2 = rw[-2 * P4], cm1 = rw[-P4], c0 = rw[0], cp1 = rw[P4], cp2 = rw[2 * P4];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j >= n) break;
+                const uint32_t cp3 = rw[(j + 3) * P4];
+                const uint32_t W0 = rw[j * P4 - 1], W2 = rw[j * P4 + 1];
+                const uint32_t d0 = __vabsdiffu4(c0, cp3), d8 = __vabsdiffu4(c0, cm3);
+                const uint32_t d4 = __vabsdiffu4(c0, __byte_perm(c0, W2, 0x6543)), d12 = __vabsdiffu4(c0, __byte_perm(W0, c0, 0x4321));
+                const uint32_t X = (d0 + K) | d0 | (d8 + K) | d8;
+                const uint32_t Y = (d4 + K) | d4 | (d12 + K) | d12;
+                const uint32_t pass = X & Y & mask;
+                // flag bits 7,15,23,31 -> one nibble: the products land on distinct bits, the top four are the flags
+                bits |= ((pass * 0x00204081u) >> 28) << (4 * j);
+                cm3 = cm2; cm2 = cm1; cm1 = c0; c0 = cp1; cp1 = cp2; cp2 = cp3;
+            }
         }
-    }
-    // block-wide exclusive scan of the per-thread survivor counts
-    const int c = sizeof(BitsT) == 8 ? __popcll((unsigned long long)bits) : __popc((unsigned)bits);
-    int incl = c;
+        // block-wide exclusive scan of the per-thread survivor counts
+        const int c = __popc(bits);
+        int incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    if (lane == 31) wsum[tid >> 5] = incl;
-    __syncthreads();
-    int pos = incl - c;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[tid >> 5] = incl;
+        __syncthreads();
+        int pos = total + incl - c;
 #pragma unroll
-    for (int w = 0; w < FS_T / 32; w++) {
-        const int t = wsum[w];
-        if (w < (tid >> 5)) pos += t;
-        if (w == FS_T / 32 - 1 && tid == FS_T - 1) *ncand = pos + c;
+        for (int w = 0; w < FS_T / 32; w++) {
+            const int t = wsum[w];
+            if (w < (tid >> 5)) pos += t;
+            total += t;
+        }
+        const int e0 = y0 * FW_P + 4 * (wq0 + q) - B0;                 // entry yIn * FW_P + xs of pixel 0 of the thread's first row
+        while (bits) {
+            const int b = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
+            cand[pos++] = (uint16_t)(e0 + (b >> 2) * FW_P + (b & 3));
+        }
+        if (rb + 8 < hB) __syncthreads();                              // wsum is written again
     }
-    int e = (yIn0 << 8) + 4 * (wq0 + q0) - B0, q = q0;       // + j = yIn << 8 | xs for the valid pixels j of the quad
-    for (int st = 0; st < nMine; st++) {
-        const unsigned nib = (unsigned)bits & 15u;
-        bits >>= 4;
-        if (nib & 1u) cand[pos++] = (uint16_t)e;
-        if (nib & 2u) cand[pos++] = (uint16_t)(e + 1);
-        if (nib & 4u) cand[pos++] = (uint16_t)(e + 2);
-        if (nib & 8u) cand[pos++] = (uint16_t)(e + 3);
-        e += stepE; q += dQ;
-        if (q >= nQ) { q -= nQ; e += wrapE; }
-    }
+    return total;
 }
 
-__global__ void __launch_bounds__(FS_T)
+__global__ void __launch_bounds__(FS_T, 4)
 k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
             const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
             unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
@@ -607,12 +617,13 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     extern __shared__ __align__(128) uint8_t fsm[];
     uint8_t *win = fsm;                                              // winRows x FW_P (TMA destination)
     uint8_t *smap = win + winRows * FW_P;                            // (winRows - 4) x FM_P: scores with a zero border
-    uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn << 8 | xs
+    uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn * FW_P + xs
     uint16_t *corner = cand + listCap;                               // listCap
     __shared__ __align__(8) uint64_t bar;
     __shared__ int ncand, ncorner;
-    __shared__ int anyIni[8], wsum[FS_T / 32];
-    __shared__ uint8_t cellOf[ORBX_SEG_W];
+    __shared__ int wsum[FS_T / 32], nq2s;
+    __shared__ unsigned cellsDone;
+    __shared__ uint8_t cellOf[ORBX_SEG_W], qlist[64];
 
     const OrbxSeg seg = segs[blockIdx.x];
     const int frame = blockIdx.y;
@@ -620,7 +631,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     const int wT = seg.wT, hT = seg.hT;
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt = lanemask_lt();
-    const int th = L.minTh;
+    const int wCell = lv.wCell;
 
     // ---- stage 0: TMA fetches the window from the level's tensor map.  The box must start 16-byte aligned
     // in x and the word left of the first tested pixel's word is read too: box x = (x0 - 4) & ~15, and tested
@@ -629,117 +640,165 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ncand = 0; ncorner = 0;
+        ncand = 0; ncorner = 0; cellsDone = 0u;
     }
-    if (tid < 8) anyIni[tid] = 0;
     __syncthreads();
-    if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);
+    if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
     for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
-    if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (65536u / (unsigned)lv.wCell + 1u)) >> 16);   // tid / wCell, exact for tid < 1024
+    if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (unsigned)lv.cellMagic) >> 16);            // tid / wCell
+    const int nCells = (int)(((unsigned)(wT - 1) * (unsigned)lv.cellMagic) >> 16) + 1;
+    const unsigned allCells = (1u << nCells) - 1u;
     mbar_wait(&bar, 0);
     __syncthreads();
 
-    // ---- stage 1: packed quick reject, 4 pixels per thread (32-bit flag register when a thread has at most 8 items)
-    if ((((B0 + wT - 1) >> 2) - (B0 >> 2) + 1) * hT <= 8 * FS_T) fast_quick_reject<uint32_t>(win, cand, wsum, &ncand, tid, lane, B0, wT, hT, th, seg.mQ);
-    else fast_quick_reject<unsigned long long>(win, cand, wsum, &ncand, tid, lane, B0, wT, hT, th, seg.mQ);
-    __syncthreads();
-    const int nc = ncand;
-
-    // ---- stage 2: threshold margin of every survivor, two per thread (survivors i and i + half share the
-    // 16-bit halves of the registers); corners (margin > min threshold) get their score written to the score
-    // map and are compacted (one shared atomic per warp)
-    const int half = (nc + 1) >> 1;
-    for (int i0 = 0; i0 < half; i0 += FS_T) {
-        const int i = i0 + tid;
-        int eA = 0, eB = 0, mA = 0, mB = 0;
-        bool hasB = false;
-        if (i < half) {
-            eA = cand[i];
-            hasB = i + half < nc;
-            eB = hasB ? cand[i + half] : eA;
-            // e = yIn << 8 | xs and both pitches are 256: window byte = e + 3 rows + B0, score-map byte = e + 1 row + 1
-            fast_margin2(win + eA + (3 * FW_P + B0), win + eB + (3 * FW_P + B0), mA, mB);
-        }
-        const bool cornerA = mA > th, cornerB = hasB && mB > th;
-        const unsigned balA = __ballot_sync(0xffffffffu, cornerA), balB = __ballot_sync(0xffffffffu, cornerB);
-        if (balA | balB) {
-            int base = 0;
-            if (lane == 0) base = smem_atomic_add(&ncorner, __popc(balA) + __popc(balB));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cornerA) {
-                corner[base + __popc(balA & lt)] = (uint16_t)eA;
-                smap[eA + (FM_P + 1)] = (uint8_t)(mA - 1);
-            }
-            if (cornerB) {
-                corner[base + __popc(balA) + __popc(balB & lt)] = (uint16_t)eB;
-                smap[eB + (FM_P + 1)] = (uint8_t)(mB - 1);
-            }
-        }
-    }
-    __syncthreads();
-    const int nk = ncorner;
-
-    // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); the
-    // survivors are compacted into the (now free) survivor list
-    const int wCell = lv.wCell;
-    if (tid == 0) ncand = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < nk; i0 += FS_T) {
-        const int i = i0 + tid;
-        bool isMax = false;
-        int e = 0;
-        if (i < nk) {
-            e = corner[i];
-            const int xs = e & 255;
-            const int cl = cellOf[xs], xIn = xs - cl * wCell;
-            const uint8_t *s = smap + e + (FM_P + 1);
-            const int v = s[0];
-            const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
-            const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
-            const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
-            const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
-            isMax = v > m;
-            if (isMax && v >= L.iniTh) anyIni[cl] = 1;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, isMax);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = smem_atomic_add(&ncand, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (isMax) cand[base + __popc(bal & lt)] = (uint16_t)e;
-        }
-    }
-    // per-cell threshold fallback, orbextractor.cpp:950-957: the ini-threshold result is used iff
-    // it is non-empty after NMS; NMS(ini) == {k in NMS(min) : score >= ini}
-    __syncthreads();
-    const int nm = ncand;
-
-    // ---- stage 3b: emit into the per-(strip,row) summaries
     uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;
     unsigned long long *bestF = best + (size_t)frame * L.rowsPerFrame + lv.rowBase;
-    for (int i = tid; i < nm; i += FS_T) {
-        const int e = cand[i];
-        const int yIn = e >> 8, xs = e & 255;
-        const int s = smap[e + (FM_P + 1)];
-        const int cl = cellOf[xs], xIn = xs - cl * wCell;
-        if (anyIni[cl] && s < L.iniTh) continue;
-        const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
-        int strip = 0;                                                                  // xr / hX, :710
+    const int nQ = ((B0 + wT - 1) >> 2) - (B0 >> 2) + 1;
+
+    // The reference runs cv::FAST per cell at the initial threshold and only where that leaves nothing (after NMS) again at
+    // the minimum threshold (orbextractor.cpp:940-957).  Same order here: pass 0 = all cells at iniTh, pass 1 = the cells
+    // of the run that came out empty, at minTh.  (A cell whose ini-corners all fell to NMS ties is such a cell: pass 1
+    // recomputes its corners above minTh from scratch, the ones above iniTh included.)
+    unsigned cmask = allCells;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int th = pass ? L.minTh : L.iniTh;
+        const int thQ = min(th, 127);                                 // the packed quick reject compares 7-bit fields; a lower
+                                                                      // threshold only lets more pixels through to the exact test
+        bool dense = true;
+        unsigned mQx = seg.mQ & 0xffffffu;
+        int nQx = nQ, hB = (int)(seg.mQ >> 24);
+        if (pass) {
+            cmask = allCells & ~cellsDone;                            // final since the barrier after stage 3a
+            if (!cmask) break;                                        // uniform
+            dense = cmask == allCells;
+            __syncthreads();                                          // stage 3b of pass 0 is done with the lists and counters
+            if (tid == 0) ncorner = 0;
+            if (!dense && tid < 32) {
+                // aligned quads that touch an empty cell, in ascending order (two per lane)
+                const int wq0 = B0 >> 2;
+                bool in0 = false, in1 = false;
+                if (lane < nQ) {
+                    const int a = max(4 * (wq0 + lane) - B0, 0), b = min(4 * (wq0 + lane) + 3 - B0, wT - 1);
+                    in0 = ((cmask >> cellOf[a]) | (cmask >> cellOf[b])) & 1u;
+                }
+                if (lane + 32 < nQ) {
+                    const int a = max(4 * (wq0 + lane + 32) - B0, 0), b = min(4 * (wq0 + lane + 32) + 3 - B0, wT - 1);
+                    in1 = ((cmask >> cellOf[a]) | (cmask >> cellOf[b])) & 1u;
+                }
+                const unsigned b0 = __ballot_sync(0xffffffffu, in0), b1 = __ballot_sync(0xffffffffu, in1);
+                if (in0) qlist[__popc(b0 & lt)] = (uint8_t)lane;
+                if (in1) qlist[__popc(b0) + __popc(b1 & lt)] = (uint8_t)(lane + 32);
+                if (lane == 0) nq2s = __popc(b0) + __popc(b1);
+            }
+            __syncthreads();
+            if (!dense) {
+                nQx = nq2s; mQx = (1u << 20) / (unsigned)nQx + 1u;
+                const int R = FS_T / nQx;
+                hB = (hT + R - 1) / R;
+            }
+        }
+
+        // ---- stage 1: packed quick reject, 4 pixels per item
+        const int nc = fast_quick_reject(win, cand, wsum, qlist, dense, nQx, mQx, hB, tid, lane, B0, wT, hT, thQ);
+        __syncthreads();
+
+        // ---- stage 2: threshold margin of every survivor, two per thread (survivors i and i + half share the
+        // 16-bit halves of the registers); corners (margin > threshold, in a cell of this pass) get their score written
+        // to the score map and are compacted (one shared atomic per warp)
+        const int half = (nc + 1) >> 1;
+        for (int i0 = 0; i0 < half; i0 += FS_T) {
+            const int i = i0 + tid;
+            int eA = 0, eB = 0, mA = 0, mB = 0;
+            bool hasB = false;
+            if (i < half) {
+                eA = cand[i];
+                hasB = i + half < nc;
+                eB = hasB ? cand[i + half] : eA;
+                // e = yIn * FW_P + xs and both pitches are equal: window byte = e + 3 rows + B0, score-map byte = e + 1 row + 1
+                fast_margin2(win + eA + (3 * FW_P + B0), win + eB + (3 * FW_P + B0), mA, mB);
+            }
+            bool cornerA = mA > th, cornerB = hasB && mB > th;
+            if (pass) {                                               // a quad may reach into a neighbouring cell that is done
+                cornerA = cornerA && ((cmask >> cellOf[eA - fast_row_of(eA) * FW_P]) & 1u);
+                cornerB = cornerB && ((cmask >> cellOf[eB - fast_row_of(eB) * FW_P]) & 1u);
+            }
+            const unsigned balA = __ballot_sync(0xffffffffu, cornerA), balB = __ballot_sync(0xffffffffu, cornerB);
+            if (balA | balB) {
+                int base = 0;
+                if (lane == 0) base = smem_atomic_add(&ncorner, __popc(balA) + __popc(balB));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cornerA) {
+                    corner[base + __popc(balA & lt)] = (uint16_t)eA;
+                    smap[eA + (FM_P + 1)] = (uint8_t)(mA - 1);
+                }
+                if (cornerB) {
+                    corner[base + __popc(balA) + __popc(balB & lt)] = (uint16_t)eB;
+                    smap[eB + (FM_P + 1)] = (uint8_t)(mB - 1);
+                }
+            }
+        }
+        __syncthreads();
+        const int nk = ncorner;
+
+        // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); the
+        // survivors are compacted into the (now free) survivor list
+        if (tid == 0) ncand = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < nk; i0 += FS_T) {
+            const int i = i0 + tid;
+            bool isMax = false;
+            int e = 0;
+            unsigned done = 0u;
+            if (i < nk) {
+                e = corner[i];
+                const int xs = e - fast_row_of(e) * FW_P;
+                const int cl = cellOf[xs], xIn = xs - cl * wCell;
+                const uint8_t *s = smap + e + (FM_P + 1);
+                const int v = s[0];
+                const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
+                const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
+                const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
+                const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
+                isMax = v > m;
+                if (isMax) done = 1u << cl;                            // the cell keeps its initial-threshold result
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, isMax);
+            if (bal) {
+                if (pass == 0) { done = __reduce_or_sync(0xffffffffu, done); if (lane == 0) atomicOr(&cellsDone, done); }
+                int base = 0;
+                if (lane == 0) base = smem_atomic_add(&ncand, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (isMax) cand[base + __popc(bal & lt)] = (uint16_t)e;
+            }
+        }
+        __syncthreads();
+        const int nm = ncand;
+
+        // ---- stage 3b: emit into the per-(strip,row) summaries
+        for (int i = tid; i < nm; i += FS_T) {
+            const int e = cand[i];
+            const int yIn = fast_row_of(e), xs = e - yIn * FW_P;
+            const int s = smap[e + (FM_P + 1)];
+            const int cl = cellOf[xs], xIn = xs - cl * wCell;
+            const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
+            int strip = 0;                                                                  // xr / hX, :710
 #pragma unroll
-        for (int k = 1; k < ORBX_MAX_STRIPS; k++) strip += (xr >= k * lv.hX);
-        const int row = strip * lv.H + yr;
-        const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
-        const unsigned long long key = ((unsigned long long)s << 56) |
-                                       ((unsigned long long)(0x0fffffffu - order) << 28) |
-                                       ((unsigned long long)xr << 14) | (unsigned long long)yr;
-        atomicAdd(&cntF[row], 1u);
-        atomicMax(&bestF[row], key);
-        if (dbg) {
-            const int slot = frame * L.nlevels + seg.level;
-            const int pos = atomicAdd(&dbgCount[slot], 1);
-            if (pos < dbgCap) {
-                OrbxDbgCand c; c.xy = xr | (yr << 16); c.score = s;
-                dbg[(size_t)slot * dbgCap + pos] = c;
+            for (int k = 1; k < ORBX_MAX_STRIPS; k++) strip += (xr >= k * lv.hX);
+            const int row = strip * lv.H + yr;
+            const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
+            const unsigned long long key = ((unsigned long long)s << 56) |
+                                           ((unsigned long long)(0x0fffffffu - order) << 28) |
+                                           ((unsigned long long)xr << 14) | (unsigned long long)yr;
+            atomicAdd(&cntF[row], 1u);
+            atomicMax(&bestF[row], key);
+            if (dbg) {
+                const int slot = frame * L.nlevels + seg.level;
+                const int pos = atomicAdd(&dbgCount[slot], 1);
+                if (pos < dbgCap) {
+                    OrbxDbgCand c; c.xy = xr | (yr << 16); c.score = s;
+                    dbg[(size_t)slot * dbgCap + pos] = c;
+                }
             }
         }
     }
