@@ -283,7 +283,11 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         // cells of one cell row whose windows are processed (:935, :944), grouped into runs of <= ORBX_SEG_W tested columns
         int nProc = 0;
         for (int j = 0; j < v.nCols; j++) if (ORBX_MINB + j * v.wCell < maxBX - 6) nProc++;
-        const int perSegMax = std::max(1, std::min(8, ORBX_SEG_W / v.wCell));
+        // k_fast_segs stage 1 gives a thread one quad column and a band of at most 8 rows: a run is kept narrow enough for
+        // 256 / ceil(hCell / 8) quad columns to cover it in one round (a wider run still works, in several rounds)
+        const int bandsNeeded = (v.hCell + 7) / 8;
+        const int widthCap = std::min(ORBX_SEG_W, 4 * (256 / bandsNeeded - 2));
+        const int perSegMax = std::max(1, std::min(8, widthCap / v.wCell));
         const int nSegRow = (nProc + perSegMax - 1) / perSegMax;
         const int perSeg = nSegRow ? (nProc + nSegRow - 1) / nSegRow : 0;
         for (int i = 0; i < v.nRows; i++) {

@@ -15,6 +15,7 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 // rBRIEF sampling pattern, 512 (x,y) points (data; same table as orbextractor.cpp:215-473)
@@ -598,29 +599,35 @@ __device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *c
             total += t;
         }
         const int e0 = y0 * FW_P + 4 * (wq0 + q) - B0;                 // entry yIn * FW_P + xs of pixel 0 of the thread's first row
-        while (bits) {
+        while (bits) {                                                 // two survivors per trip
             const int b = __ffs((int)bits) - 1;
             bits &= bits - 1u;
-            cand[pos++] = (uint16_t)(e0 + (b >> 2) * FW_P + (b & 3));
+            cand[pos] = (uint16_t)(e0 + (b >> 2) * FW_P + (b & 3));
+            if (bits) {
+                const int b2 = __ffs((int)bits) - 1;
+                bits &= bits - 1u;
+                cand[pos + 1] = (uint16_t)(e0 + (b2 >> 2) * FW_P + (b2 & 3));
+            }
+            pos += 2;
         }
         if (rb + 8 < hB) __syncthreads();                              // wsum is written again
     }
     return total;
 }
 
-__global__ void __launch_bounds__(FS_T, 4)
+__global__ void __launch_bounds__(FS_T, 5)
 k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
             const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
             unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
-            int *__restrict__ dbgCount, int dbgCap, int winRows, int listCap)
+            int *__restrict__ dbgCount, int dbgCap, int winRows, int listCap, int kcap)
 {
     extern __shared__ __align__(128) uint8_t fsm[];
     uint8_t *win = fsm;                                              // winRows x FW_P (TMA destination)
     uint8_t *smap = win + winRows * FW_P;                            // (winRows - 4) x FM_P: scores with a zero border
     uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn * FW_P + xs
-    uint16_t *corner = cand + listCap;                               // listCap
+    uint16_t *corner = cand + listCap;                               // kcap (<= listCap): on overflow stage 3a scans the score map instead
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int ncand, ncorner;
+    __shared__ int nmax, ncorner;                                     // stage 3a / stage 2 list lengths
     __shared__ int wsum[FS_T / 32], nq2s;
     __shared__ unsigned cellsDone;
     __shared__ uint8_t cellOf[ORBX_SEG_W], qlist[64];
@@ -640,7 +647,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ncand = 0; ncorner = 0; cellsDone = 0u;
+        nmax = 0; ncorner = 0; cellsDone = 0u;
     }
     __syncthreads();
     if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
@@ -673,7 +680,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             if (!cmask) break;                                        // uniform
             dense = cmask == allCells;
             __syncthreads();                                          // stage 3b of pass 0 is done with the lists and counters
-            if (tid == 0) ncorner = 0;
+            if (tid == 0) { ncorner = 0; nmax = 0; }
             if (!dense && tid < 32) {
                 // aligned quads that touch an empty cell, in ascending order (two per lane)
                 const int wq0 = B0 >> 2;
@@ -729,11 +736,13 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
                 if (lane == 0) base = smem_atomic_add(&ncorner, __popc(balA) + __popc(balB));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (cornerA) {
-                    corner[base + __popc(balA & lt)] = (uint16_t)eA;
+                    const int at = base + __popc(balA & lt);
+                    if (at < kcap) corner[at] = (uint16_t)eA;
                     smap[eA + (FM_P + 1)] = (uint8_t)(mA - 1);
                 }
                 if (cornerB) {
-                    corner[base + __popc(balA) + __popc(balB & lt)] = (uint16_t)eB;
+                    const int at = base + __popc(balA) + __popc(balB & lt);
+                    if (at < kcap) corner[at] = (uint16_t)eB;
                     smap[eB + (FM_P + 1)] = (uint8_t)(mB - 1);
                 }
             }
@@ -743,16 +752,23 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
 
         // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); the
         // survivors are compacted into the (now free) survivor list
-        if (tid == 0) ncand = 0;
-        __syncthreads();
-        for (int i0 = 0; i0 < nk; i0 += FS_T) {
+        // (a corner list that did not fit -- more than kcap corners, dense noise -- is replaced by a scan of the score map)
+        const bool scan = nk > kcap;
+        const int nIt = scan ? wT * hT : nk;
+        for (int i0 = 0; i0 < nIt; i0 += FS_T) {
             const int i = i0 + tid;
-            bool isMax = false;
-            int e = 0;
+            bool isMax = false, have = i < nIt;
+            int e = 0, xs = 0;
             unsigned done = 0u;
-            if (i < nk) {
-                e = corner[i];
-                const int xs = e - fast_row_of(e) * FW_P;
+            if (have) {
+                if (!scan) { e = corner[i]; xs = e - fast_row_of(e) * FW_P; }
+                else {
+                    const int y = i / wT;
+                    xs = i - y * wT; e = y * FW_P + xs;
+                    have = smap[e + (FM_P + 1)] != 0 && ((cmask >> cellOf[xs]) & 1u);
+                }
+            }
+            if (have) {
                 const int cl = cellOf[xs], xIn = xs - cl * wCell;
                 const uint8_t *s = smap + e + (FM_P + 1);
                 const int v = s[0];
@@ -767,13 +783,13 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             if (bal) {
                 if (pass == 0) { done = __reduce_or_sync(0xffffffffu, done); if (lane == 0) atomicOr(&cellsDone, done); }
                 int base = 0;
-                if (lane == 0) base = smem_atomic_add(&ncand, __popc(bal));
+                if (lane == 0) base = smem_atomic_add(&nmax, __popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (isMax) cand[base + __popc(bal & lt)] = (uint16_t)e;
             }
         }
         __syncthreads();
-        const int nm = ncand;
+        const int nm = nmax;
 
         // ---- stage 3b: emit into the per-(strip,row) summaries
         for (int i = tid; i < nm; i += FS_T) {
@@ -804,9 +820,23 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     }
 }
 
+// Capacity of the corner list.  The survivor list must hold every tested pixel of a run (noise lets them all through the quick
+// reject); the corner list gets what is left of the shared memory that still admits FIVE resident CTAs per SM, but at least
+// a quarter of the pixels -- past that stage 3a falls back to scanning the score map.  ORBX_FAST_KCAP overrides (tests).
+int fast_corner_cap(int winRows, int listCap)
+{
+    static const int forced = getenv("ORBX_FAST_KCAP") ? atoi(getenv("ORBX_FAST_KCAP")) : 0;
+    if (forced > 0) return std::min(listCap, (forced + 7) & ~7);
+    const long budget = (233472 - 5 * 1024) / 5 - 512;       // per CTA: 228 KB per SM, 1 KB reserved per CTA, static shared memory
+    const long fixed = (long)winRows * FW_P + (long)(winRows - 4) * FM_P + 2L * listCap;
+    const long room = (budget - fixed) / 2;
+    if (room < listCap / 4) return listCap;                   // five CTAs do not fit anyway
+    return (int)std::min<long>(listCap, room & ~7L);
+}
+
 size_t fast_smem_bytes(int winRows, int listCap)
 {
-    return (size_t)winRows * FW_P + (size_t)(winRows - 4) * FM_P + (size_t)listCap * 4;
+    return (size_t)winRows * FW_P + (size_t)(winRows - 4) * FM_P + (size_t)listCap * 2 + (size_t)fast_corner_cap(winRows, listCap) * 2;
 }
 
 cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
@@ -820,7 +850,8 @@ cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, co
         if (e != cudaSuccess) return e;
     }
     dim3 grid(segCount, batch);
-    k_fast_segs<<<grid, FS_T, smem, st>>>(maps, f0, L, segs + segBegin, cnt, best, dbg, dbgCount, dbgCap, winRows, listCap);
+    k_fast_segs<<<grid, FS_T, smem, st>>>(maps, f0, L, segs + segBegin, cnt, best, dbg, dbgCount, dbgCap, winRows, listCap,
+                                          fast_corner_cap(winRows, listCap));
     return cudaGetLastError();
 }
 

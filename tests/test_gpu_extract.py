@@ -456,3 +456,30 @@ def test_other_thresholds_and_scale_factors(oracle, sf, ini, mn, nl):
         kps, desc, counts = ex.extract_batch([img])
         _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
     ex.close()
+
+
+def test_corner_list_overflow_scans_the_score_map():
+    """k_fast_segs keeps its corner list smaller than a run (that is what lets five CTAs share an SM); a run with more
+    corners than the list holds must fall back to scanning the score map.  ORBX_FAST_KCAP=8 (read once per process)
+    forces that on every run: the stress inputs, the candidate sets, other thresholds and a dense-noise frame at low
+    thresholds are re-run in a child process and must stay identical to the oracle."""
+    import os, subprocess, sys
+    env = dict(os.environ, ORBX_FAST_KCAP="8")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-x", "-q", "-m", "gpu", "-k",
+                        "batch_and_stress or candidates_match or other_thresholds or few_features_on_noise or dense_noise"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1000:]
+
+
+def test_dense_noise_low_thresholds(oracle):
+    """Uniform noise at thresholds 4 / 2: about a third of all pixels are FAST corners, the densest the lists get."""
+    import orbx
+    w, h, nf, nl = 640, 360, 3000, 4
+    ex = orbx.Extractor(nfeatures=nf, nlevels=nl, ini_th=4, min_th=2, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=nf, nlevels=nl, ini_th=4, min_th=2)
+    img = synth.scene_s2(w, h, 4242)
+    kps, desc, counts = ex.extract_batch([img])
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
+    ex.close()
