@@ -529,12 +529,14 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     }
     CK(cudaEventRecord(ln.evPyr, st));
     CK(cudaStreamWaitEvent(ln.side, ln.evPyr, 0));
-    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
-    CKM(cudaGetLastError(), "k_blur launch");
-    CK(cudaEventRecord(ln.evJoin, ln.side));
+    // FAST of levels 1.. is enqueued BEFORE the blur: CTAs are dispatched in launch order, so the blur fills FAST's tail and keeps
+    // the SMs busy while the octree (a few latency-bound CTAs) runs, instead of the other way round
     CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, batch, st));
+    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
+    CKM(cudaGetLastError(), "k_blur launch");
+    CK(cudaEventRecord(ln.evJoin, ln.side));
     CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
     launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, f0, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
@@ -857,9 +859,9 @@ int orbx_extract_batch_async(orbx_extractor *h, const uint8_t *const *imgs, int 
     // ORBX_CHUNKS=n gives n equal chunks
     // default: a synchronous call (nothing behind it to cover its tail) uses chunks of about 4 MB of input (8 KITTI-sized
     // frames) so that the last chunk's kernels and D2H are short; with a second call in flight the tail is covered by that
-    // call's H2D and larger chunks (about 8 MB, fewer launches and copies) are faster: 104.7 k vs 99.5 k frames/s on B200
-    // (profiles/r2_e2e_plans.txt)
-    const int chunkFrames = std::max(1, (int)((size_t)(h->inSyncCall ? (4u << 20) : (8u << 20)) / frameBytes));
+    // call's H2D and larger chunks (about 10 MB, fewer launches and copies) are faster: 110.8 k frames/s with 3 chunks of a
+    // 64-frame KITTI batch, 108.5 k with 4, 99.5 k with 8, 64.7 k with one (profiles/r2_e2e_plans.txt)
+    const int chunkFrames = std::max(1, (int)((size_t)(h->inSyncCall ? (4u << 20) : (21u << 19)) / frameBytes));
     int nChunks = std::max(1, std::min(16, (batch + chunkFrames - 1) / chunkFrames));
     if (const char *e = getenv("ORBX_CHUNKS")) nChunks = std::max(1, std::min(batch, atoi(e)));
     std::vector<int> cb;
