@@ -168,6 +168,13 @@ int orbx_stereo_match_batch(orbx_extractor *h, int n_pairs, int frame_left0, int
 /* upper bound of keypoints per frame for this configuration */
 int orbx_max_keypoints(const orbx_extractor *h);
 
+/* Page-locked host memory for callers without the CUDA headers (the header-only adapters in cpp/): images and result
+ * arrays allocated here are DMA'd directly -- orbx_extract* writes straight into `kps` / `desc` when they are page-locked
+ * and kp_cap == orbx_max_keypoints(h), with no staging copy.  (The reference's cv::Mat / std::vector buffers are
+ * pageable, orbextractor.cpp:595-609; the adapter keeps its own page-locked scratch and copies once.) */
+int orbx_host_alloc(size_t bytes, void **ptr);
+void orbx_host_free(void *ptr);
+
 /* Number of kernel launches the last orbx_extract* call enqueued (all chunks / halves); for benchmark accounting. */
 int orbx_last_launches(const orbx_extractor *h);
 

@@ -1109,6 +1109,17 @@ int orbx_extract(orbx_extractor *h, const uint8_t *img, int width, int height, s
     return orbx_extract_batch(h, imgs, 1, width, height, pitch, kps, kp_cap, desc, n_out);
 }
 
+int orbx_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr || bytes == 0) return ORBX_ERR_ARG;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return e == cudaErrorMemoryAllocation ? ORBX_ERR_NOMEM : ORBX_ERR_CUDA; }
+    return ORBX_OK;
+}
+
+void orbx_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
 int orbx_get_level(orbx_extractor *h, int frame, int level, const uint8_t **host_ptr, int *width, int *height, size_t *pitch)
 {
     if (!h) return ORBX_ERR_ARG;

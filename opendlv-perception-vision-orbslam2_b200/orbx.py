@@ -39,7 +39,7 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_multi_max_keypoints", "orbx_multi_extract_batch", "orbx_multi_extract_batch_async", "orbx_multi_wait", "orbx_multi_handle",
            "orbx_multi_frame_range", "orbm_multi_create", "orbm_multi_destroy", "orbm_multi_last_error", "orbm_multi_devices", "orbm_multi_set_train",
            "orbm_multi_knn2", "orbm_multi_matcher",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_last_launches", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_host_alloc", "orbx_host_free", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_window_create", "orbm_window_attach_ipc", "orbm_window_attach_peer", "orbm_knn2_sharded", "orbm_window_status", "orbm_window_fetch", "orbm_window_records", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_assign_grid", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
@@ -93,6 +93,8 @@ def lib():
     L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_stereo_match_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.orbx_host_free.argtypes = [vp]; L.orbx_host_free.restype = None
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
     L.orbx_scale_tables.argtypes = [vp, fp, fp, fp, fp, ip]
     L.orbx_profile_stages.argtypes = [vp, C.c_int, fp, C.c_int]

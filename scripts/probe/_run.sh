@@ -1,1 +1,2 @@
-for c in 1 2 3 4 6 8; do ORBX_CHUNKS=$c python bench.py --quick --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunks $c', 'value', round(d['value']), 'async', round(d['e2e']['value']), 'sync', round(d['e2e']['sync_value']), 'lat', d['latency'])"; done
+timeout 900 python -m pytest tests/test_cpp_adapter.py tests/test_gpu_dropin_frame.py tests/test_gpu_drivers.py tests/test_gpu_dropin_vocabulary.py tests/test_abi.py -x -q 2>&1 | tail -4
+python scripts/probe/frame_constructor_times.py

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Wall time of the reference's own stereo OrbFrame constructor in three builds of the same unmodified src/orbframe.cpp:
-all-reference (CPU), with the drop-in extractor, with the drop-in extractor and stereo matcher, and the latter without the per-call
-pyramid download (ORBX_ADAPTER_LAZY_PYRAMID) (GPU box only)."""
+"""Wall time of the reference's own stereo OrbFrame constructor in four builds of the same unmodified src/orbframe.cpp:
+all-reference (CPU), with the drop-in extractor (pyramid levels downloaded when the reference's stereo matcher reads them), with the
+drop-in extractor and stereo matcher (no pyramid leaves HBM), and the latter with ORBX_ADAPTER_EAGER_PYRAMID (all levels downloaded
+in every call, the adapter's earlier behaviour) (GPU box only)."""
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -30,7 +30,8 @@ def test_adapter_compiles_with_reference_signatures(tmp_path):
                 "void ExtractFeatures(cv::InputArray image, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray descriptors)",
                 "int getLevels()", "double getScaleFactor()", "std::vector<float> getScaleFactors()",
                 "std::vector<float> getInverseScaleFactors()", "std::vector<float> getScaleSigmaSquares()",
-                "std::vector<float> getInverseScaleSigmaSquares()", "std::vector<cv::Mat> m_vImagePyramid;"):
+                "std::vector<float> getInverseScaleSigmaSquares()",
+                "Pyramid m_vImagePyramid;   // std::vector<cv::Mat> m_vImagePyramid; in the reference"):
         assert sig in hdr, sig
 
 
