@@ -47,6 +47,7 @@ CONFIGS = {
                 label="synthetic 3840x2160 frames, 8000 features, 12 levels, 4-frame batch (BASELINE config[3])"),
 }
 W, H, NFEAT, NLEVELS, BATCH = 1241, 376, 2000, 8, 64
+PIPE_DEPTH = 3          # device-resident batches in flight per GPU (orbx_pipe)
 NQ, NT = 2000, 100000
 REFERENCE_IMPL = ("the reference's own src/orbextractor.cpp, compiled unmodified, linked to the repo's SCALAR restatement of the "
                   "OpenCV primitives (oracle/cvshim: resize, FAST, GaussianBlur) -- not to OpenCV's SIMD code; a real OpenCV 3.3.1 "
@@ -381,19 +382,47 @@ def measure_config(name, args, rank, local_rank, world, torch, dist, orbx, dev, 
     parity["device_batch_frames"] = len(picks)
     parity["device_batch_keypoints"] = check_frames(oex, frames_of[last], picks, kps, desc, cnt, f"{name} device-resident batch")
 
-    # ---- sustained: the same step for >= sustained_s seconds
+    # ---- the same steps with PIPE_DEPTH batches in flight (orbx_pipe: consecutive batches go to separate extractor handles, so
+    # the head of one batch -- level-0 copy, the dependent resize launches -- runs under the tail of the one before)
+    pipe = orbx.Pipe(PIPE_DEPTH, nf, 1.2, nl, 20, 7, max_width=w, max_height=h, max_batch=batch, device=local_rank)
+
+    def run_pipe(n):
+        tk = []
+        for i in range(n):
+            tk.append(pipe.submit(dev_pool[i % pool].data_ptr(), h * w, w, batch, w, h, stream.cuda_stream))
+            if i >= PIPE_DEPTH - 1:
+                pipe.join(tk[i - (PIPE_DEPTH - 1)], stream.cuda_stream)       # the stream consumes results in submission order
+        for j in range(max(0, n - (PIPE_DEPTH - 1)), n):
+            pipe.join(tk[j], stream.cuda_stream)
+        return tk
+
+    run_pipe(max(args.warmup, PIPE_DEPTH))
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record(stream)
+    tk = run_pipe(args.steps)
+    p1.record(stream)
+    barrier()
+    res["ms_pipe"] = p0.elapsed_time(p1)
+    picks_p = sorted(set((f + max(1, batch // (3 * len(picks)))) % batch for f in picks))
+    kps, desc, cnt = pipe.extractor(tk[-1]).fetch_results(batch, stream.cuda_stream)
+    parity["pipe_batch_frames"] = len(picks_p)
+    parity["pipe_batch_keypoints"] = check_frames(oex, frames_of[last], picks_p, kps, desc, cnt, f"{name} pipelined device-resident batch")
+
+    # ---- sustained: the pipelined step for >= sustained_s seconds
     if sustained_s > 0:
-        per = max(ms_dev / args.steps, 1e-3)
+        per = max(res["ms_pipe"] / args.steps, 1e-3)
         n_sus = int(sustained_s * 1e3 / per) + 1
         clocks = ClockSampler(local_rank).start()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         s0.record(stream)
-        for i in range(n_sus):
-            step_dev(i)
+        run_pipe(n_sus)
         s1.record(stream)
         barrier()
         res["sustained"] = {"steps": n_sus, "ms": s0.elapsed_time(s1), "clocks": clocks.stop()}
+    pipe.close()
 
     # ---- e2e through the host entry points (pinned host frames in, keypoints + descriptors out)
     # two sets of pinned result arrays with the library's stride (results are DMA'd straight into them): call k+1 fills one
@@ -652,14 +681,18 @@ def main():
         next_rows, nr_ctx = measure_next_rows(torch, orbx, ex, m, head, dev, stream, local_rank)
 
     # ---- max over ranks
-    keys = ["ms_dev", "s_e2e", "s_e2e_sync"]
-    vals = [head[k] for k in keys] + [ms_match] + ([head["sustained"]["ms"]] if "sustained" in head else [0.0])
+    named = [("ms_dev", head["ms_dev"]), ("s_e2e", head["s_e2e"]), ("s_e2e_sync", head["s_e2e_sync"]), ("ms_pipe", head["ms_pipe"]),
+             ("ms_match", ms_match), ("ms_sus", head["sustained"]["ms"] if "sustained" in head else 0.0)]
     ms_match_nccl = max_over_ranks([ms_match_nccl])[0]
-    vals += [strong["ms_dev"], strong["s_e2e"]] if strong else [0.0, 0.0]
+    named += [("ms_strong", strong["ms_dev"] if strong else 0.0), ("s_strong", strong["s_e2e"] if strong else 0.0),
+              ("ms_strong_pipe", strong["ms_pipe"] if strong else 0.0)]
     for name in ("hd", "uhd"):
-        vals += [others[name]["ms_dev"], others[name]["s_e2e"], others[name]["s_e2e_sync"]] if name in others else [0.0, 0.0, 0.0]
-    vals = max_over_ranks(vals)
-    ms_dev, s_e2e, s_e2e_sync, ms_match, ms_sus, ms_strong, s_strong = vals[:7]
+        o = others.get(name)
+        named += [(f"{name}_ms_dev", o["ms_dev"] if o else 0.0), (f"{name}_s_e2e", o["s_e2e"] if o else 0.0),
+                  (f"{name}_s_e2e_sync", o["s_e2e_sync"] if o else 0.0), (f"{name}_ms_pipe", o["ms_pipe"] if o else 0.0)]
+    mx = dict(zip([k for k, _ in named], max_over_ranks([v for _, v in named])))
+    ms_dev, s_e2e, s_e2e_sync, ms_pipe, ms_match, ms_sus = (mx[k] for k in ("ms_dev", "s_e2e", "s_e2e_sync", "ms_pipe", "ms_match", "ms_sus"))
+    ms_strong, s_strong, ms_strong_pipe = mx["ms_strong"], mx["s_strong"], mx["ms_strong_pipe"]
     kp_checked = sum(v for k, v in parity.items() if k.endswith("_keypoints"))
     for name in others:
         for k, v in others[name]["parity"].items():
@@ -674,7 +707,8 @@ def main():
         peak, peak_src, sm_max = measured_peaks()
         steps = args.steps
         frames = BATCH * steps * world
-        fps_dev = frames / (ms_dev * 1e-3)
+        fps_dev = frames / (ms_pipe * 1e-3)          # the headline: PIPE_DEPTH batches in flight (orbx_pipe)
+        fps_one = frames / (ms_dev * 1e-3)           # one orbx_extract_batch_device call at a time
         fps_e2e = frames / s_e2e
         stages = head["stages"]
         dom = max(stages, key=stages.get)
@@ -692,10 +726,12 @@ def main():
         h2d_ms = head["h2d_ms"]
         line = {
             "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps_dev, "unit": "frames/s", "n_gpus": world,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_dev / steps,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_pipe / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": CONFIGS["kitti"]["label"] + ", one such batch per GPU per step",
                        "frames_per_gpu_per_step": BATCH, "global_frames_per_step": BATCH * world,
+                       "in_flight": f"{PIPE_DEPTH} batches per GPU (orbx_pipe_submit / orbx_pipe_join: consecutive batches on separate extractor "
+                                    "handles, every batch complete and joined into the timed stream before the closing event)",
                        "l2": f"inputs rotate over {head['pool']} resident batches ({head['pool'] * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "host_binding": None if numa is None else f"each rank bound to the {numa} host cores NVML lists for its GPU"},
@@ -706,6 +742,8 @@ def main():
                     "h2d_alone_ms_per_step": h2d_ms, "h2d_gbs": BATCH * W * H / (h2d_ms * 1e-3) / 1e9,
                     "pcie_floor_frames_per_s": BATCH * world / (h2d_ms * 1e-3),
                     "frac_of_pcie_floor": fps_e2e / (BATCH * world / (h2d_ms * 1e-3))},
+            "single_call": {"value": fps_one, "unit": "frames/s", "ms_per_step": ms_dev / steps,
+                            "what": "the same batches through orbx_extract_batch_device, one call at a time on one handle (round 1's headline)"},
             "gpu_launches": head["launches_per_step"] * steps,
             "gpu_launches_per_step": {"device_resident": head["launches_per_step"], "e2e": head["launches_e2e"]},
             "latency": dict(lat, note="orbx_extract_batch with 1 / 2 frames of 1241x376, pinned host buffers, H2D + kernels + D2H, mean of 100 calls"),
@@ -713,13 +751,13 @@ def main():
                          "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu --set full of this stage, bytes per 64-frame step)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": balg * BATCH, "kernel_ms": dom_ms,
-                         "whole_step_frac": balg * BATCH / (ms_dev / steps * 1e-3) / 1e9 / peak,
+                         "whole_step_frac": balg * BATCH / (ms_pipe / steps * 1e-3) / 1e9 / peak,
                          # the path is instruction-issue bound (50-100 integer operations per byte): warp instructions of one
                          # step (ncu smsp__inst_executed.sum, profiles/ncu_traffic.json) against 4 issue slots x 148 SMs x clock
                          "issue_roofline": None if not winst_step else {
                              "warp_instructions_per_step": winst_step,
                              "peak_warp_instructions_per_s": 4 * 148 * sm_max * 1e6,
-                             "frac": winst_step / (ms_dev / steps * 1e-3) / (4 * 148 * sm_max * 1e6)}},
+                             "frac": winst_step / (ms_pipe / steps * 1e-3) / (4 * 148 * sm_max * 1e6)}},
             "stages_ms": stages,
             "clocks": clk,
             "parity_checked": dict(parity, keypoints_compared_rank0=kp_checked,
@@ -743,24 +781,23 @@ def main():
             sus = head["sustained"]
             line["sustained"] = {"value": BATCH * sus["steps"] * world / (ms_sus * 1e-3), "unit": "frames/s", "seconds": ms_sus * 1e-3,
                                  "steps": sus["steps"], "ms_per_step": ms_sus / sus["steps"], "clocks": sus["clocks"],
-                                 "what": "the device-resident step of the headline looped back to back"}
+                                 "what": "the pipelined device-resident step of the headline looped back to back"}
         if strong:
             per = BATCH // world
             line["strong"] = {"workload": f"BASELINE config[1] read literally: {BATCH} frames per step shared by {world} GPUs ({per} each)",
-                              "value": per * world * steps / (ms_strong * 1e-3), "unit": "frames/s", "ms_per_step": ms_strong / steps,
+                              "value": per * world * steps / (ms_strong_pipe * 1e-3), "unit": "frames/s", "ms_per_step": ms_strong_pipe / steps,
+                              "single_call": {"value": per * world * steps / (ms_strong * 1e-3), "ms_per_step": ms_strong / steps},
                               "e2e": {"value": per * world * steps / s_strong, "unit": "frames/s"}, "scaling": "strong"}
         else:
             line["strong"] = {"workload": f"BASELINE config[1] read literally: {BATCH} frames per step on 1 GPU = the headline",
-                              "value": fps_dev, "unit": "frames/s", "ms_per_step": ms_dev / steps, "e2e": {"value": fps_e2e, "unit": "frames/s"},
+                              "value": fps_dev, "unit": "frames/s", "ms_per_step": ms_pipe / steps, "e2e": {"value": fps_e2e, "unit": "frames/s"},
                               "scaling": "strong"}
         cfgs = {}
-        k = 7
         for name in ("hd", "uhd"):
             if name not in others:
                 continue
             o, cfg = others[name], CONFIGS[name]
-            md, se, ss = vals[k:k + 3]
-            k += 3
+            md1, se, ss, md = (mx[f"{name}_{k}"] for k in ("ms_dev", "s_e2e", "s_e2e_sync", "ms_pipe"))
             b = cfg["batch"]
             st = o["stages"]
             dm = max(st, key=st.get)
@@ -768,6 +805,7 @@ def main():
             a = ba * b / (st[dm] * 1e-3) / 1e9
             cfgs[name] = {"workload": cfg["label"] + ", one such batch per GPU per step", "value": b * steps * world / (md * 1e-3),
                           "unit": "frames/s", "ms_per_step": md / steps,
+                          "single_call": {"value": b * steps * world / (md1 * 1e-3), "ms_per_step": md1 / steps},
                           "e2e": {"value": b * steps * world / se, "unit": "frames/s", "sync_value": b * steps * world / ss,
                                   "h2d_bytes_per_step": b * cfg["w"] * cfg["h"], "d2h_bytes_per_step": b * o["cap"] * 60 + b * 4,
                                   "pcie_floor_frames_per_s": b * world / (o["h2d_ms"] * 1e-3)},

@@ -138,6 +138,29 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
 int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
                         const int **d_counts, int *kp_stride);
 
+/* Several device-resident extractions in flight on one GPU (csrc/orbx_pipe.cu): a pipe owns `depth` (1..8) extractor handles of
+ * the same configuration and gives consecutive submissions to them in turn, so that the head of one batch (level-0 copy, the
+ * dependent resize launches) runs under the tail of the one before (octree, end of the describe grid).  The device-side twin of
+ * orbx_extract_batch_async / orbx_wait; same call shape as the reference's "extract in threads, consume later"
+ * (orbframe.cpp:73-78).
+ *   orbx_pipe_submit  the frames must be ready at the caller's position in `stream` (NULL = the legacy default stream); the work
+ *                     runs on the slot's own stream, nothing is waited for.  *ticket = 1, 2, ...
+ *   orbx_pipe_join    makes `stream` wait for that submission and returns its result pointers (as orbx_device_results).  They
+ *                     stay valid until the slot is submitted to again, i.e. for depth - 1 further submissions; work the
+ *                     caller enqueues on them must be in `stream` before the submission that reuses the slot.
+ *   orbx_pipe_handle  the extractor that holds the submission (orbx_stereo_match_batch, orbx_filter_keypoints, orbx_get_level,
+ *                     orbx_fetch_results of exactly that batch); NULL once the slot has been reused. */
+typedef struct orbx_pipe orbx_pipe;
+int orbx_pipe_create(const orbx_config *cfg, int depth, orbx_pipe **out);
+void orbx_pipe_destroy(orbx_pipe *p);
+const char *orbx_pipe_last_error(const orbx_pipe *p);
+int orbx_pipe_depth(const orbx_pipe *p);
+int orbx_pipe_submit(orbx_pipe *p, const uint8_t *d_imgs, size_t frame_stride, size_t pitch, int batch, int width, int height,
+                     void *stream, int *ticket);
+int orbx_pipe_join(orbx_pipe *p, int ticket, void *stream, const orbx_keypoint **d_kps, const uint8_t **d_desc,
+                   const int **d_counts, int *kp_stride);
+orbx_extractor *orbx_pipe_handle(orbx_pipe *p, int ticket);
+
 /* Copy the results of the last orbx_extract_batch_device call to host arrays (layout as in
  * orbx_extract_batch).  Waits for `stream` (the stream that call was given; NULL = the handle's). */
 int orbx_fetch_results(orbx_extractor *h, void *stream, orbx_keypoint *kps, int kp_cap, uint8_t *desc, int *n_out);

@@ -39,7 +39,8 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_multi_max_keypoints", "orbx_multi_extract_batch", "orbx_multi_extract_batch_async", "orbx_multi_wait", "orbx_multi_handle",
            "orbx_multi_frame_range", "orbm_multi_create", "orbm_multi_destroy", "orbm_multi_last_error", "orbm_multi_devices", "orbm_multi_set_train",
            "orbm_multi_knn2", "orbm_multi_matcher",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_host_alloc", "orbx_host_free", "orbx_last_launches", "orbx_get_level",
+           "orbx_extract_batch_device", "orbx_device_results", "orbx_pipe_create", "orbx_pipe_destroy", "orbx_pipe_last_error", "orbx_pipe_depth",
+           "orbx_pipe_submit", "orbx_pipe_join", "orbx_pipe_handle", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_host_alloc", "orbx_host_free", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
            "orbm_knn2_device", "orbm_window_create", "orbm_window_attach_ipc", "orbm_window_attach_peer", "orbm_knn2_sharded", "orbm_window_status", "orbm_window_fetch", "orbm_window_records", "orbm_knn2_csr", "orbm_knn2_csr_device", "orbm_distance_csr", "orbm_search_by_projection", "orbm_area_distances", "orbm_assign_grid", "orbm_distinctive", "orbm_distance_pairs", "orbm_measure_popc",
@@ -93,6 +94,13 @@ def lib():
     L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_stereo_match_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_pipe_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
+    L.orbx_pipe_destroy.argtypes = [vp]; L.orbx_pipe_destroy.restype = None
+    L.orbx_pipe_last_error.argtypes = [vp]; L.orbx_pipe_last_error.restype = C.c_char_p
+    L.orbx_pipe_depth.argtypes = [vp]
+    L.orbx_pipe_submit.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, vp, ip]
+    L.orbx_pipe_join.argtypes = [vp, C.c_int, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), ip]
+    L.orbx_pipe_handle.argtypes = [vp, C.c_int]; L.orbx_pipe_handle.restype = vp
     L.orbx_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.orbx_host_free.argtypes = [vp]; L.orbx_host_free.restype = None
     L.orbx_get_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip, ip, C.POINTER(C.c_size_t)]
@@ -158,7 +166,8 @@ class Extractor:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().orbx_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().orbx_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -282,6 +291,59 @@ class Extractor:
         xs, ys, sc = (np.zeros(cap, np.int32) for _ in range(3))
         n = self._check(lib().orbx_debug_candidates(self._h, frame, level, _ptr(xs), _ptr(ys), _ptr(sc), cap))
         return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+class Pipe:
+    """orbx_pipe: `depth` device-resident extractions in flight on one GPU (submit / join by ticket)."""
+
+    def __init__(self, depth=3, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 max_width=1241, max_height=376, max_batch=1, device=0, taps=None, tie_rule=0):
+        cfg = Config(nfeatures, scale_factor, nlevels, ini_th, min_th, max_width, max_height, max_batch, device,
+                     (C.c_int * 7)(*(taps if taps is not None else [0] * 7)), tie_rule)
+        self._h = C.c_void_p()
+        rc = lib().orbx_pipe_create(C.byref(cfg), depth, C.byref(self._h))
+        if rc != 0:
+            msg = lib().orbx_pipe_last_error(self._h).decode() if self._h else "invalid configuration"
+            if self._h:
+                lib().orbx_pipe_destroy(self._h)
+                self._h = None
+            raise OrbxError(rc, msg)
+        self.depth = depth
+        self._cfg = (nlevels, nfeatures, max_batch)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orbx_pipe_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbxError(rc, lib().orbx_pipe_last_error(self._h).decode())
+        return rc
+
+    def submit(self, dptr, frame_stride, pitch, batch, width, height, stream=None):
+        t = C.c_int()
+        self._check(lib().orbx_pipe_submit(self._h, C.c_void_p(dptr), frame_stride, pitch, batch, width, height,
+                                           C.c_void_p(stream) if stream else None, C.byref(t)))
+        return t.value
+
+    def join(self, ticket, stream=None):
+        """-> (d_kps, d_desc, d_counts, kp_stride) of that submission; `stream` waits for it."""
+        k, d, c, s = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        self._check(lib().orbx_pipe_join(self._h, ticket, C.c_void_p(stream) if stream else None, C.byref(k), C.byref(d), C.byref(c), C.byref(s)))
+        return k.value, d.value, c.value, s.value
+
+    def extractor(self, ticket):
+        """A non-owning Extractor view of the slot that holds `ticket` (fetch_results, levels, stereo matching of that batch)."""
+        h = lib().orbx_pipe_handle(self._h, ticket)
+        if not h:
+            raise OrbxError(-1, "the ticket's slot has been reused")
+        ex = Extractor.__new__(Extractor)
+        ex._h, ex._owned = C.c_void_p(h), False
+        ex.nlevels, ex.nfeatures, ex.max_batch = self._cfg
+        return ex
 
 
 def stereo_match(left, frame_left, right, frame_right, mbf, mb=0.0):

@@ -483,3 +483,40 @@ def test_dense_noise_low_thresholds(oracle):
     kps, desc, counts = ex.extract_batch([img])
     _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]))
     ex.close()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_pipe_keeps_several_device_batches_in_flight(oracle, depth):
+    """orbx_pipe: consecutive submissions go to `depth` extractor handles in turn and overlap on the GPU; every submission's
+    results (joined out of order with respect to the later submissions that are already running) equal the oracle's, a reused
+    slot refuses its old ticket, and the slot's extractor serves that batch's pyramid levels."""
+    import torch
+    import orbx
+    w, h, nf, nl, b = 640, 360, 800, 6, 5
+    pipe = orbx.Pipe(depth=depth, nfeatures=nf, nlevels=nl, max_width=w, max_height=h, max_batch=b)
+    oex = oracle.Extractor(nfeatures=nf, nlevels=nl)
+    st = torch.cuda.Stream()
+    batches = [np.stack(synth.frames(300 + k, w, h, b)) for k in range(5)]
+    dev = [torch.from_numpy(x).cuda() for x in batches]
+    torch.cuda.synchronize()
+    tickets, checked = [], 0
+
+    def check(k):
+        ex = pipe.extractor(tickets[k])
+        pipe.join(tickets[k], st.cuda_stream)
+        kps, desc, counts = ex.fetch_results(b, st.cuda_stream)
+        for f in (0, b - 1):
+            _compare_frame(oracle, ex, oex, batches[k][f], f, kps[f], desc[f], int(counts[f]), stages=(f == 0 and k == 0))
+        return 1
+
+    for k in range(len(dev)):
+        tickets.append(pipe.submit(dev[k].data_ptr(), h * w, w, b, w, h, st.cuda_stream))
+        if k >= depth - 1:
+            checked += check(k - (depth - 1))          # the oldest submission still held, while the newer ones run
+    for k in range(len(dev) - (depth - 1), len(dev)):
+        checked += check(k)
+    assert checked == len(dev)
+    if depth < len(dev):
+        with pytest.raises(orbx.OrbxError):
+            pipe.join(tickets[0], st.cuda_stream)      # that slot has been submitted to again
+    pipe.close()
