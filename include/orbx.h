@@ -57,7 +57,7 @@ typedef struct {
     float scale_factor;   /* ORBextractor.scaleFactor (tracking.cpp:105); supported range (1, 1.35], ORB-SLAM2 settings use 1.2 */
     int nlevels;          /* ORBextractor.nLevels     (tracking.cpp:106), 1..ORBX_MAX_LEVELS */
     int ini_th_fast;      /* ORBextractor.iniThFAST   (tracking.cpp:107) */
-    int min_th_fast;      /* ORBextractor.minThFAST   (tracking.cpp:108); 1..127 */
+    int min_th_fast;      /* ORBextractor.minThFAST   (tracking.cpp:108); 1..254, <= ini_th_fast */
     int max_width;        /* largest image width  this handle will be given */
     int max_height;       /* largest image height this handle will be given */
     int max_batch;        /* frames per orbx_extract_batch call (>=1)       */

@@ -335,9 +335,12 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         maxRows = std::max(maxRows, v.nIni * v.H);
         v.slotBase = slots;
         v.slotCap = std::max(v.quota, 2 * v.nIni);   // list never exceeds max(N, first-pass size)
-        if (v.slotCap > ORBX_MAX_NODES) return fail(h, ORBX_ERR_SHAPE, "per-level feature quota exceeds 4096");
         slots += v.slotCap;
-        maxNodes = std::max(maxNodes, v.slotCap + 2);
+        // nodes are disjoint row ranges of the nIni strips (DivideNode never splits in x in this fork, A.5), so a level's node
+        // list holds at most nIni * H of them however large the quota is
+        const int nodeCap = std::min(v.slotCap, v.nIni * v.H + 2 * v.nIni) + 2;
+        if (nodeCap > ORBX_MAX_NODES) return fail(h, ORBX_ERR_SHAPE, "more than 65534 octree nodes on one level");
+        maxNodes = std::max(maxNodes, nodeCap);
         v.sf = h->sf[l]; v.invSf = h->invSf[l];
         v.kpSize = 31 * (int)h->sf[l];   // :978 int cast before the multiply
         // blur tiles: 32 words x (4 bands of ORBX_BLUR_ROWS rows)
@@ -469,7 +472,12 @@ int setGeometry(orbx_extractor *h, int w, int hh)
     if (rc != ORBX_OK) return rc;
     // everything that can reject the shape is checked BEFORE the handle's geometry is touched: a refused size leaves the
     // previous one fully usable
-    if (octree_smem_bytes(maxRows, maxNodes) > 200 * 1024) return fail(h, ORBX_ERR_SHAPE, "level too tall for the octree shared-memory arena");
+    if (octree_smem_bytes(maxRows, maxNodes) > 200 * 1024) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "octree needs %zu bytes of shared memory (%d nodes per level, %d strip rows): more than 200 KB -- fewer features or a shorter level",
+                 octree_smem_bytes(maxRows, maxNodes), maxNodes, maxRows);
+        return fail(h, ORBX_ERR_SHAPE, msg);
+    }
     // in-flight work (the handle's lanes, a caller's stream of the last device-resident call) may still read the old tables
     CK(drainLast(h));
     for (int i = 0; i < ORBX_LANES; i++) {
@@ -609,7 +617,7 @@ int orbx_create(const orbx_config *cfg, orbx_extractor **out)
     *out = nullptr;
     if (cfg->nlevels < 1 || cfg->nlevels > ORBX_MAXL || cfg->nfeatures < 1 || !(cfg->scale_factor > 1.0f) ||
         cfg->scale_factor > 1.35f ||   /* k_resize: the source region of a 128 x 32 tile (128 s + 17 columns) must fit its 192 x 48 TMA box */
-        cfg->min_th_fast < 1 || cfg->min_th_fast > 127 ||   /* k_fast_segs' packed quick reject compares 7-bit fields */
+        cfg->min_th_fast < 1 || cfg->min_th_fast > 254 ||   /* 8-bit scores; k_fast_segs' packed quick reject clamps its own threshold to 127 */
         cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 ||
         cfg->max_batch < 1 || cfg->max_width < 1 || cfg->max_height < 1)
         return ORBX_ERR_ARG;

@@ -8,7 +8,8 @@
 #define ORBX_MINB 16           // EDGE_THRESHOLD-3, orbextractor.cpp:914
 #define ORBX_CELL_W 30.0f      // W, orbextractor.cpp:910
 #define ORBX_MAX_STRIPS 8      // nIni supported by the node packing (3 bits)
-#define ORBX_MAX_NODES 4096    // per-level node list capacity (quota + 2*nIni must fit)
+#define ORBX_MAX_NODES 65534   // per-level node list capacity: 16-bit order arrays in k_octree.  The working limit is the octree's
+                               // shared memory: 13 bytes per node + 12 per strip row <= 200 KB
 
 // Per-level geometry.  Everything here is a pure function of (config, image size) and is
 // computed once on the host with the reference's exact float32 expressions.

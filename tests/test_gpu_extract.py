@@ -520,3 +520,28 @@ def test_pipe_keeps_several_device_batches_in_flight(oracle, depth):
         with pytest.raises(orbx.OrbxError):
             pipe.join(tickets[0], st.cuda_stream)      # that slot has been submitted to again
     pipe.close()
+
+
+def test_quota_above_4096_and_thresholds_above_127(oracle):
+    """Two limits round 1 had and the reference does not: a per-level feature quota above 4096 (40 000 features over 4 levels of
+    a 4K noise frame put 12 876 on level 0 -- round 1 refused the configuration; the node list itself cannot outgrow the rows of
+    the level's strips, which is what the octree arena is sized by now) and FAST thresholds above 127 (the packed quick reject
+    clamps its own threshold, the exact margin test does not)."""
+    import orbx
+    w, h = 3840, 2160
+    ex = orbx.Extractor(nfeatures=40000, nlevels=4, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=40000, nlevels=4)
+    img = synth.scene_s2(w, h, 77)
+    kps, desc, counts = ex.extract_batch([img])
+    n = int(counts[0])
+    assert n > 6000 and int((kps[0][:n]["octave"] == 0).sum()) > 2000
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], n, stages=False)
+    ex.close()
+    w, h = 1241, 376
+    ex = orbx.Extractor(nfeatures=1500, nlevels=5, ini_th=150, min_th=131, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.Extractor(nfeatures=1500, nlevels=5, ini_th=150, min_th=131)
+    img = synth.scene_s2(w, h, 79)
+    kps, desc, counts = ex.extract_batch([img])
+    assert int(counts[0]) > 50
+    _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]), stages=False)
+    ex.close()
