@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides five drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides six drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device; the sequential rule "a key point that an
 //     observed map point was stored on earlier in the call is skipped", :87-89 after :121, is iterated to its fixpoint);
@@ -17,6 +17,8 @@
 //     made earlier in the same call, :1412-1414) runs on the host over the returned lists.
 //   * SearchByBoW(keyFrame, frame, matches)                 src/orbmatcher.cpp:164-292   -> one orbm_distance_csr call for all
 //     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host;
+//   * SearchByBoW(keyFrame1, keyFrame2, matches12)          src/orbmatcher.cpp:531-663   -> the same between two key frames (loop
+//     closing), candidates restricted to the features of key frame 2 that carry a usable map point;
 //   * SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616 -> the same with the key frame's
 //     map points and PredictScale (relocalisation);
 //   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
@@ -322,6 +324,90 @@ class ORBmatcherB200 : public ORBmatcher {
               if (b == ind1 || b == ind2 || b == ind3) continue;
               for (size_t j = 0; j < rotHist[b].size(); j++) {
                   vpMapPointMatches[rotHist[b][j]] = std::shared_ptr<OrbMapPoint>();
+                  nmatches--;
+              }
+          }
+      }
+      return nmatches;
+  }
+
+  // ---- src/orbmatcher.cpp:531-663 (loop closing: two key frames).  As above with a key frame on both sides: the candidates of
+  // a feature of key frame 1 are the features of key frame 2 under the same vocabulary node that carry a usable map point
+  // (:586-592, static); the DescriptorDistance of every such pair comes from ONE orbm_distance_csr call; the exclusion of
+  // features of key frame 2 matched earlier in the call (vbMatched2, :588), the TH_LOW / ratio test (:609-611) and the
+  // orientation histogram run on the host.
+  int SearchByBoW(std::shared_ptr<OrbKeyFrame> pKF1, std::shared_ptr<OrbKeyFrame> pKF2, std::vector<std::shared_ptr<OrbMapPoint>> &vpMatches12)
+  {
+      const std::vector<std::shared_ptr<OrbMapPoint>> vpMapPoints1 = pKF1->GetMapPointMatches();
+      const std::vector<std::shared_ptr<OrbMapPoint>> vpMapPoints2 = pKF2->GetMapPointMatches();
+      vpMatches12 = std::vector<std::shared_ptr<OrbMapPoint>>(vpMapPoints1.size(), std::shared_ptr<OrbMapPoint>());
+      std::vector<unsigned char> usable2(vpMapPoints2.size(), 0), vbMatched2(vpMapPoints2.size(), 0);
+      for (size_t i = 0; i < vpMapPoints2.size(); i++) usable2[i] = vpMapPoints2[i] && !vpMapPoints2[i]->IsCorrupt();
+
+      // pass 1: the (feature of key frame 1, usable features of key frame 2 under the same node) lists in the reference's order
+      std::vector<unsigned int> q;
+      std::vector<int> offsets(1, 0), indices;
+      OrbFeatureVector::const_iterator f1it = pKF1->m_features.begin(), f2it = pKF2->m_features.begin();
+      const OrbFeatureVector::const_iterator f1end = pKF1->m_features.end(), f2end = pKF2->m_features.end();
+      while (f1it != f1end && f2it != f2end) {
+          if (f1it->first == f2it->first) {
+              for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                  const unsigned int idx1 = f1it->second[i1];
+                  const std::shared_ptr<OrbMapPoint> &mp1 = vpMapPoints1[idx1];
+                  if (!mp1 || mp1->IsCorrupt()) continue;
+                  q.push_back(idx1);
+                  for (size_t i2 = 0; i2 < f2it->second.size(); i2++)
+                      if (usable2[f2it->second[i2]]) indices.push_back((int)f2it->second[i2]);
+                  offsets.push_back((int)indices.size());
+              }
+              ++f1it; ++f2it;
+          } else if (f1it->first < f2it->first) {
+              f1it = pKF1->m_features.lower_bound(f2it->first);
+          } else {
+              f2it = pKF2->m_features.lower_bound(f1it->first);
+          }
+      }
+      if (q.empty() || indices.empty()) return 0;
+      cv::Mat qd((int)q.size(), 32, CV_8U);
+      for (size_t k = 0; k < q.size(); k++) pKF1->mDescriptors.row((int)q[k]).copyTo(qd.row((int)k));
+      reserve((int)q.size(), pKF2->mDescriptors.rows);
+      std::vector<int> dist;
+      gpu_->CandidateDistances(qd, pKF2->mDescriptors, offsets, indices, dist);
+
+      // pass 2: :580-630 over the precomputed distances
+      int nmatches = 0;
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      for (size_t k = 0; k < q.size(); k++) {
+          int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              const int idx2 = indices[e];
+              if (vbMatched2[idx2]) continue;
+              const int d = dist[e];
+              if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = idx2; }
+              else if (d < bestDist2) bestDist2 = d;
+          }
+          if (bestDist1 < TH_LOW && static_cast<float>(bestDist1) < mfNNratio * static_cast<float>(bestDist2)) {
+              vpMatches12[q[k]] = vpMapPoints2[bestIdx2];
+              vbMatched2[bestIdx2] = 1;
+              if (mbCheckOrientation) {
+                  float rot = pKF1->mvKeysUn[q[k]].angle - pKF2->mvKeysUn[bestIdx2].angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back((int)q[k]);
+              }
+              nmatches++;
+          }
+      }
+      if (mbCheckOrientation) {
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++) {
+                  vpMatches12[rotHist[b][j]] = std::shared_ptr<OrbMapPoint>();
                   nmatches--;
               }
           }

@@ -11,6 +11,7 @@
 //   part 3  SearchByBoW(keyFrame, frame, matches)                  src/orbmatcher.cpp:164-292
 //   part 4  SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528
 //   part 5  SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616
+//   part 6  SearchByBoW(keyFrame1, keyFrame2, matches12)           src/orbmatcher.cpp:531-663
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
@@ -51,6 +52,7 @@ extern "C" {
 // out[28..31] wall microseconds of one warm call: part 1 reference / ORBmatcherB200, part 3 reference / ORBmatcherB200
 // out[24..27] part 5: SearchByProjection(CurrentFrame, key frame, found): the four numbers of part 1
 // out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
+// out[32..35] part 6: SearchByBoW(key frame 1, key frame 2): nmatches x 2, differing vpMatches12 entries, entries set
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
 {
@@ -211,6 +213,35 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
                 if (m1[k] >= 0) set++;
             }
             out[22] = bad; out[23] = set;
+        }
+        // ---------------- part 6: SearchByBoW(key frame 1, key frame 2) (loop closing, :531-663).  Two stand-in key frames carry the
+        // key points and descriptors of frames A and B; three of four features of A and every second of B own a map point, some
+        // of them corrupt (:571, :591); nodes as in part 3
+        {
+            std::vector<std::shared_ptr<OrbMapPoint>> p1((size_t)A->N), p2((size_t)B->N);
+            for (int i = 0; i < A->N; i++)
+                if (i % 4 != 2) {
+                    p1[i] = std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>());
+                    if (i % 11 == 4) p1[i]->SetCorruptFlag();
+                }
+            for (int i = 0; i < B->N; i++)
+                if (i % 2 == 0) {
+                    p2[i] = std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>());
+                    if (i % 14 == 6) p2[i]->SetCorruptFlag();
+                }
+            std::shared_ptr<OrbKeyFrame> K1 = mpref_standin_keyframe_with(A->m_undistortedKeys, A->m_descriptors, p1);
+            std::shared_ptr<OrbKeyFrame> K2 = mpref_standin_keyframe_with(B->m_undistortedKeys, B->m_descriptors, p2);
+            for (int i = 0; i < A->N; i++) K1->m_features.addFeature(A->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            for (int i = 0; i < B->N; i++) K2->m_features.addFeature(B->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            std::vector<std::shared_ptr<OrbMapPoint>> m1, m2;
+            out[32] = ref.SearchByBoW(K1, K2, m1);
+            out[33] = gpu.SearchByBoW(K1, K2, m2);
+            int bad = (m1.size() != m2.size()), set = 0;
+            for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
+            out[34] = bad; out[35] = set;
+            mpref_standin_clear();
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "driverref_check: %s\n", e.what());

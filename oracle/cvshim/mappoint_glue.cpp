@@ -39,7 +39,7 @@ OrbKeyFrame::OrbKeyFrame(std::shared_ptr<OrbFrame>, std::shared_ptr<OrbMap> map,
       mvKeys(), mvKeysUn(g_keysun), mvuRight(g_uright), mvDepth(), mDescriptors(g_pool), m_bagOfWords(), m_features(),
       mnScaleLevels(0), mfScaleFactor(0), mfLogScaleFactor(0), mvScaleFactors(), mvLevelSigma2(), mvInvLevelSigma2(),
       mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mK(),
-      m_mapPoints(), m_keyFrameDatabase(), m_orbVocabulary(), m_isFirstConnection(true), m_parent(),
+      m_mapPoints(g_kf_mappoints), m_keyFrameDatabase(), m_orbVocabulary(), m_isFirstConnection(true), m_parent(),
       m_shoulNotBeErased(false), m_shouldBeErased(false), m_isBad(g_bad), mHalfBaseline(0), m_map(map)
 {
     m_id = nNextId++;
@@ -57,7 +57,7 @@ std::shared_ptr<OrbMapPoint> OrbKeyFrame::GetMapPoint(const size_t &) { return s
 cv::Mat OrbKeyFrame::GetRotation() { return cv::Mat(); }
 cv::Mat OrbKeyFrame::GetTranslation() { return cv::Mat(); }
 std::set<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPoints() { return std::set<std::shared_ptr<OrbMapPoint>>(); }
-std::vector<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPointMatches() { return g_kf_mappoints; }
+std::vector<std::shared_ptr<OrbMapPoint>> OrbKeyFrame::GetMapPointMatches() { return m_mapPoints; }   // per key frame: a copy of what was registered when it was built
 std::vector<size_t> OrbKeyFrame::GetFeaturesInArea(const float &, const float &, const float &) const { return std::vector<size_t>(); }
 bool OrbKeyFrame::IsInImage(const float &, const float &) const { return false; }
 // a stand-in key frame with `rows` key points (no stereo coordinate), for map points that need an observation
@@ -73,13 +73,14 @@ std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows)
 std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors,
                                                          const std::vector<std::shared_ptr<OrbMapPoint>> &mapPoints)
 {
-    descriptors.copyTo(g_pool);
+    g_pool = descriptors.clone();           // a buffer of its own: two stand-in key frames may be alive at once (SearchByBoW(KF, KF))
     g_uright.assign((size_t)descriptors.rows, -1.0f);
     g_keysun = keysUn;
     g_kf_mappoints = mapPoints;
     g_bad = false;
     std::shared_ptr<OrbKeyFrame> kf = std::make_shared<OrbKeyFrame>(std::shared_ptr<OrbFrame>(), std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
     g_keysun.clear();
+    g_kf_mappoints.clear();
     return kf;
 }
 void mpref_standin_clear() { g_kf_mappoints.clear(); g_pool = cv::Mat(); }
