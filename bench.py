@@ -463,15 +463,18 @@ def measure_config(name, args, rank, local_rank, world, torch, dist, orbx, dev, 
         barrier()
         res["s_e2e_sync"] = time.perf_counter() - t0
     # the PCIe floor of the e2e number: pinned H2D copies of a step's frames by themselves
+    # (all ranks copy at the same time, as in the e2e loop: with several ranks on one host this is the host's feed rate)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     with torch.cuda.stream(stream):
         dev_pool[0].copy_(host_pool[0], non_blocking=True)
         c0.record(stream)
-        for p in range(5):
+        for p in range(10):
             dev_pool[p % pool].copy_(host_pool[p % pool], non_blocking=True)
         c1.record(stream)
     torch.cuda.synchronize()
-    res["h2d_ms"] = c0.elapsed_time(c1) / 5
+    barrier()
+    res["h2d_ms"] = c0.elapsed_time(c1) / 10
     if with_profile:
         step_dev(0)
         res["stages"] = ex.profile_stages(reps=5)
@@ -682,7 +685,7 @@ def main():
 
     # ---- max over ranks
     named = [("ms_dev", head["ms_dev"]), ("s_e2e", head["s_e2e"]), ("s_e2e_sync", head["s_e2e_sync"]), ("ms_pipe", head["ms_pipe"]),
-             ("ms_match", ms_match), ("ms_sus", head["sustained"]["ms"] if "sustained" in head else 0.0)]
+             ("ms_match", ms_match), ("ms_sus", head["sustained"]["ms"] if "sustained" in head else 0.0), ("h2d_ms", head["h2d_ms"])]
     ms_match_nccl = max_over_ranks([ms_match_nccl])[0]
     named += [("ms_strong", strong["ms_dev"] if strong else 0.0), ("s_strong", strong["s_e2e"] if strong else 0.0),
               ("ms_strong_pipe", strong["ms_pipe"] if strong else 0.0)]
@@ -723,7 +726,7 @@ def main():
             winst_step = sum(prof.get("warp_instructions_per_step", {}).values()) or None
         pairs = NQ * NT * msteps / (ms_match * 1e-3)
         int_peak = 148 * sm_max * 1e6 * popc_rate / 8      # pairs/s at the POPC rate measured on this GPU, SURVEY 8(d)
-        h2d_ms = head["h2d_ms"]
+        h2d_ms = mx["h2d_ms"]                      # slowest rank, all ranks copying at once
         line = {
             "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps_dev, "unit": "frames/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": ms_pipe / steps,
@@ -740,6 +743,8 @@ def main():
                     "api": "orbx_extract_batch_async + orbx_wait, two calls in flight, pinned host buffers",
                     "sync_value": frames / s_e2e_sync, "sync_api": "orbx_extract_batch (one call at a time)",
                     "h2d_alone_ms_per_step": h2d_ms, "h2d_gbs": BATCH * W * H / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_aggregate_gbs": world * BATCH * W * H / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_note": "pinned host -> device copies of one step's frames by themselves, every rank copying at the same time, slowest rank",
                     "pcie_floor_frames_per_s": BATCH * world / (h2d_ms * 1e-3),
                     "frac_of_pcie_floor": fps_e2e / (BATCH * world / (h2d_ms * 1e-3))},
             "single_call": {"value": fps_one, "unit": "frames/s", "ms_per_step": ms_dev / steps,
