@@ -77,19 +77,40 @@ k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
     if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = make_uint2(k1, k2);
 }
 
-__global__ void k_knn2_merge(const uint2 *__restrict__ part, int nq, int nchunks, int4 *__restrict__ out)
+// Fold the per-chunk partial pairs of one query (part[c * stride], c < nchunks) into the two smallest keys.  Sixteen loads are in
+// flight per thread: with several hundred chunks (few queries, many chunks to fill the GPU) a load-by-load loop is a chain of
+// L2 round trips -- 296 chunks x ~300 ns were most of the 30 us the sharded kernel spent behind its last chunk.
+__device__ __forceinline__ void knn_fold(const uint2 *part, size_t stride, int nchunks, unsigned &k1, unsigned &k2)
 {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
-    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
-    for (int c = 0; c < nchunks; c++) {
-        const uint2 p = part[(size_t)c * nq + qi];
-        // fold two sorted pairs: the new pair is the two smallest of {k1,k2,p.x,p.y}
+    int c = 0;
+    for (; c + 16 <= nchunks; c += 16) {
+        uint2 p[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) p[u] = __ldcg(part + (size_t)(c + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            // fold two sorted pairs: the new pair is the two smallest of {k1,k2,p.x,p.y}
+            k2 = min(k2, max(k1, p[u].x));
+            k1 = min(k1, p[u].x);
+            k2 = min(k2, max(k1, p[u].y));
+            k1 = min(k1, p[u].y);
+        }
+    }
+    for (; c < nchunks; c++) {
+        const uint2 p = __ldcg(part + (size_t)c * stride);
         k2 = min(k2, max(k1, p.x));
         k1 = min(k1, p.x);
         k2 = min(k2, max(k1, p.y));
         k1 = min(k1, p.y);
     }
+}
+
+__global__ void k_knn2_merge(const uint2 *__restrict__ part, int nq, int nchunks, int4 *__restrict__ out)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+    knn_fold(part + qi, (size_t)nq, nchunks, k1, k2);
     int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
     int idx = (int)(k1 & KNN_IDX_MASK);
     if (d1 >= 256) { d1 = 256; idx = -1; }  // 'dist < bestDist1' with bestDist1 = 256 never fires
@@ -164,13 +185,7 @@ k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
     const int nchunks = (int)gridDim.y;
     if (qi < nq) {
         k1 = KNN_INIT_KEY; k2 = KNN_INIT_KEY;
-        for (int c = 0; c < nchunks; c++) {
-            const uint2 p = __ldcg(&part[(size_t)c * nq + qi]);
-            k2 = min(k2, max(k1, p.x));
-            k1 = min(k1, p.x);
-            k2 = min(k2, max(k1, p.y));
-            k1 = min(k1, p.y);
-        }
+        knn_fold(part + qi, (size_t)nq, nchunks, k1, k2);
         int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
         int idx = (int)(k1 & KNN_IDX_MASK);
         if (d1 >= 256) { d1 = 256; idx = -1; }

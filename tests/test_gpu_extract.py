@@ -545,3 +545,42 @@ def test_quota_above_4096_and_thresholds_above_127(oracle):
     assert int(counts[0]) > 50
     _compare_frame(oracle, ex, oex, img, 0, kps[0], desc[0], int(counts[0]), stages=False)
     ex.close()
+
+
+def test_gpu_against_the_frozen_reference_fixture():
+    """The CUDA path against tests/golden/ref_extractor.npz directly -- key points and descriptors the reference's own
+    src/orbextractor.cpp (compiled unmodified, canonical tie order) produced for a tiny, a KITTI-sized and a noise frame, and
+    the pyramid levels it left in m_vImagePyramid -- with no oracle in between."""
+    import hashlib
+    import os
+    import orbx
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_extractor.npz"))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    def same(kps, desc, n, rk, rd):
+        assert n == len(rk), (n, len(rk))
+        for f in rk.dtype.names:
+            a, b = kps[:n][f], rk[f]
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b), f
+        assert np.array_equal(desc[:n], rd)
+
+    tiny = g["tiny_img"]
+    ex = orbx.Extractor(nfeatures=300, nlevels=4, max_width=tiny.shape[1], max_height=tiny.shape[0], max_batch=1)
+    kps, desc, cnt = ex.extract_batch([tiny])
+    same(kps[0], desc[0], int(cnt[0]), g["tiny_kps"], g["tiny_desc"])
+    for l in range(4):
+        assert np.array_equal(ex.level(0, l), g[f"tiny_level{l}"]), l
+    ex.close()
+    kitti = synth.scene_s1(1241, 376, 1000)
+    assert sha(kitti) == str(g["kitti_img_sha256"])
+    ex = orbx.Extractor(nfeatures=2000, nlevels=8, max_width=1241, max_height=376, max_batch=1)
+    kps, desc, cnt = ex.extract_batch([kitti])
+    same(kps[0], desc[0], int(cnt[0]), g["kitti_kps"], g["kitti_desc"])
+    assert [sha(ex.level(0, l)) for l in range(8)] == g["kitti_level_sha256"].tolist()
+    ex.close()
+    noise = synth.scene_s2(640, 360, 11)
+    assert sha(noise) == str(g["noise_img_sha256"])
+    ex = orbx.Extractor(nfeatures=1000, nlevels=6, max_width=640, max_height=360, max_batch=1)
+    kps, desc, cnt = ex.extract_batch([noise])
+    same(kps[0], desc[0], int(cnt[0]), g["noise_kps"], g["noise_desc"])
+    ex.close()

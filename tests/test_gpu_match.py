@@ -46,7 +46,8 @@ def test_knn2_distance_256_is_never_a_match(oracle):
 
 
 def test_knn2_full_size_properties(oracle):
-    """C5 at full size (2000 x 100000): oracle on a query sample + size-independent properties."""
+    """C5 at full size (2000 x 100000): every query against an exact matrix-product restatement, a sample against the
+    oracle's sequential loop, and size-independent properties."""
     import orbx
     q, t = synth.matching_set(2000, 100000, seed=5000)
     m = orbx.Matcher(max_queries=2000, max_train=100000)
@@ -59,6 +60,19 @@ def test_knn2_full_size_properties(oracle):
     sel = np.arange(0, 2000, 40)
     oi, o1, o2 = oracle.knn2(q[sel], t, nthreads=8)
     assert np.array_equal(idx[sel], oi) and np.array_equal(d1[sel], o1) and np.array_equal(d2[sel], o2)
+    # (3b) ALL 2000 queries against an independent exact restatement: Hamming distance = |a| + |b| - 2 a.b on the unpacked bits
+    # (float32 matrix products of 0/1 values up to 256 are exact), best = first minimum in index order (orbmatcher.cpp:208-232:
+    # strict '<' keeps the earliest), second = minimum over the other rows
+    tb = np.unpackbits(t, axis=1).astype(np.float32)
+    tn = tb.sum(1)
+    for a in range(0, 2000, 250):
+        qb = np.unpackbits(q[a:a + 250], axis=1).astype(np.float32)
+        D = (qb.sum(1)[:, None] + tn[None, :] - 2.0 * (qb @ tb.T)).astype(np.int32)
+        bi = D.argmin(1)
+        b1 = D[np.arange(len(bi)), bi]
+        D[np.arange(len(bi)), bi] = 1 << 20
+        b2 = D.min(1)
+        assert np.array_equal(idx[a:a + 250], bi) and np.array_equal(d1[a:a + 250], b1) and np.array_equal(d2[a:a + 250], b2), a
     # (4) resident path and permutation of the query order give the same per-query answers
     m.set_train(t)
     perm = np.random.default_rng(1).permutation(2000)
