@@ -32,6 +32,7 @@ std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int rows);
 std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors,
                                                          const std::vector<std::shared_ptr<OrbMapPoint>> &mapPoints);
 void mpref_standin_clear();
+void mpref_set_template_frame(const std::shared_ptr<OrbFrame> &f);
 
 static int count_mismatches(const std::shared_ptr<OrbFrame> &a, const std::shared_ptr<OrbFrame> &b, int *assigned)
 {
@@ -59,7 +60,7 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
     std::streambuf *old = std::cout.rdbuf();
     std::ostringstream sink;
     std::cout.rdbuf(sink.rdbuf());
-    std::shared_ptr<OrbKeyFrame> kf = mpref_standin_keyframe(8);
+    std::shared_ptr<OrbKeyFrame> kf;
     int rc = 0;
     try {
         std::shared_ptr<OrbFrame> A = frameref_make_frame(c, leftA, rightA, w, h, mbf, mb);
@@ -67,6 +68,8 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
         cv::Mat I(4, 4, CV_32F);
         for (int i = 0; i < 16; i++) I.ptr<float>(i / 4)[i % 4] = (i % 5 == 0) ? 1.f : 0.f;
         A->SetPose(I);
+        mpref_set_template_frame(A);                 // the key frames below are built by the reference's own constructor from copies of A
+        kf = mpref_standin_keyframe(8);
         cv::Mat one(3, 1, CV_32F);
         for (int k = 0; k < 3; k++) one.ptr<float>(k)[0] = 1.f;
 

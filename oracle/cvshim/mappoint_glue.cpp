@@ -29,6 +29,7 @@ static bool g_bad = false;
 static std::vector<cv::KeyPoint> g_keysun;
 static std::vector<std::shared_ptr<OrbMapPoint>> g_kf_mappoints;
 
+#ifndef ORBREF_REAL_KEYFRAME
 long unsigned int OrbKeyFrame::nNextId = 0;
 
 OrbKeyFrame::OrbKeyFrame(std::shared_ptr<OrbFrame>, std::shared_ptr<OrbMap> map, std::shared_ptr<OrbKeyFrameDatabase>)
@@ -48,8 +49,10 @@ bool OrbKeyFrame::isBad() { return m_isBad; }
 cv::Mat OrbKeyFrame::GetCameraCenter() { return cv::Mat(); }
 void OrbKeyFrame::EraseMapPointMatch(const size_t &) {}
 void OrbKeyFrame::ReplaceMapPointMatch(const size_t &, std::shared_ptr<OrbMapPoint>) {}
+#endif
 void OrbMap::DeleteOrbMapPoint(std::shared_ptr<OrbMapPoint>) {}
 #ifdef ORBREF_WITH_MATCHER
+#ifndef ORBREF_REAL_KEYFRAME
 // libframeref.so links the reference's own src/orbmatcher.cpp (the real DescriptorDistance); the key-frame members that
 // translation unit references but the functions driven here never reach are inert as well
 void OrbKeyFrame::AddMapPoint(std::shared_ptr<OrbMapPoint>, const size_t &) {}
@@ -84,10 +87,42 @@ std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::K
     return kf;
 }
 void mpref_standin_clear() { g_kf_mappoints.clear(); g_pool = cv::Mat(); }
+#else    // ORBREF_REAL_KEYFRAME: libdriverref.so links the reference's own src/orbkeyframe.cpp, UNMODIFIED.  Key frames are built by
+         // the reference's constructor from reference OrbFrames; what that translation unit needs beyond the classes already
+         // linked (OrbMap / OrbKeyFrameDatabase / OrbVocabulary members only SetBadFlag and ComputeBoW reach) is inert here.
+#include <orbkeyframedatabase.hpp>
+#include <orbvocabulary.hpp>
+void OrbMap::DeleteOrbKeyFrame(std::shared_ptr<OrbKeyFrame>) {}
+void OrbKeyFrameDatabase::Erase(std::shared_ptr<OrbKeyFrame>) {}
+static std::shared_ptr<OrbFrame> g_template;      // a reference frame whose calibration, scale tables and image bounds the key frames share
+void mpref_set_template_frame(const std::shared_ptr<OrbFrame> &f) { g_template = f; }
+// a key frame with the template frame's own content, for map points that need an observation
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe(int)
+{
+    return std::make_shared<OrbKeyFrame>(std::make_shared<OrbFrame>(g_template), std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+}
+// a key frame carrying the given key points, descriptors and map points: a copy of the template frame with those members
+// replaced goes through the reference's own key-frame constructor (orbkeyframe.cpp:29-60)
+std::shared_ptr<OrbKeyFrame> mpref_standin_keyframe_with(const std::vector<cv::KeyPoint> &keysUn, const cv::Mat &descriptors,
+                                                         const std::vector<std::shared_ptr<OrbMapPoint>> &mapPoints)
+{
+    std::shared_ptr<OrbFrame> f = std::make_shared<OrbFrame>(g_template);
+    f->N = (int)keysUn.size();
+    f->m_keys = keysUn; f->m_undistortedKeys = keysUn;
+    f->m_descriptors = descriptors.clone();
+    f->m_mapPoints = mapPoints;
+    f->mvuRight.assign(keysUn.size(), -1.0f);
+    f->m_depths.assign(keysUn.size(), -1.0f);
+    f->mBowVec.clear(); f->mFeatVec.clear();
+    return std::make_shared<OrbKeyFrame>(f, std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+}
+void mpref_standin_clear() {}
+#endif   // ORBREF_REAL_KEYFRAME
 #else
 int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return OrbDescriptor::distance(a, b); }
 #endif
 
+#ifndef ORBREF_REAL_KEYFRAME
 extern "C" {
 
 // desc: n_desc x 32; point p observes rows indices[offsets[p] .. offsets[p+1]) (one key frame per observation; bad[k] != 0
@@ -131,3 +166,4 @@ int mpref_distinctive(const uint8_t *desc, int n_desc, const int32_t *offsets, c
 }
 
 } // extern "C"
+#endif   // !ORBREF_REAL_KEYFRAME (mpref_distinctive places stand-in key frames by hand)

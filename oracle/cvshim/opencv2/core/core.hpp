@@ -83,6 +83,7 @@ public:
     Mat reshape(int) const { return *this; }                                     // channel count only (orbframe.cpp:466-468); no element moves
     void convertTo(Mat &dst, int t) const;                                        // CV_8U -> CV_32F, dst may alias *this
     static Mat ones(int r, int c, int t);
+    static Mat eye(int r, int c, int t);                                          // orbkeyframe.cpp:82
     Mat t() const;
     double dot(const Mat &b) const;
     template <typename T> T &at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
@@ -116,6 +117,13 @@ inline Mat Mat::ones(int r, int c, int t)
     assert(t == CV_32F);
     Mat o(r, c, CV_32F);
     for (int i = 0; i < r; i++) for (int k = 0; k < c; k++) o.ptr<float>(i)[k] = 1.0f;
+    return o;
+}
+inline Mat Mat::eye(int r, int c, int t)
+{
+    assert(t == CV_32F);
+    Mat o(r, c, CV_32F);
+    for (int i = 0; i < r; i++) for (int k = 0; k < c; k++) o.ptr<float>(i)[k] = i == k ? 1.0f : 0.0f;
     return o;
 }
 inline Mat Mat::t() const
