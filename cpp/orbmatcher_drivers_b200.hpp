@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides six drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides seven drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device; the sequential rule "a key point that an
 //     observed map point was stored on earlier in the call is skipped", :87-89 after :121, is iterated to its fixpoint);
@@ -19,6 +19,8 @@
 //     (key-frame feature, frame feature of the same vocabulary node) pairs, the sequential loop on the host;
 //   * SearchByBoW(keyFrame1, keyFrame2, matches12)          src/orbmatcher.cpp:531-663   -> the same between two key frames (loop
 //     closing), candidates restricted to the features of key frame 2 that carry a usable map point;
+//   * SearchForTriangulation(keyFrame1, keyFrame2, F12, pairs, onlyStereo) src/orbmatcher.cpp:665-831 -> the same node walk between
+//     the untracked features of two key frames, epipolar tests on the host;
 //   * SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616 -> the same with the key frame's
 //     map points and PredictScale (relocalisation);
 //   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
@@ -30,6 +32,7 @@
 #include <cmath>
 #include <memory>
 #include <set>
+#include <utility>
 #include <vector>
 
 #include <orbmatcher.hpp>
@@ -412,6 +415,110 @@ class ORBmatcherB200 : public ORBmatcher {
               }
           }
       }
+      return nmatches;
+  }
+
+  // ---- src/orbmatcher.cpp:665-831 (local mapping: matches between the untracked key points of two key frames, to be
+  // triangulated).  Candidates of a feature of key frame 1: the features of key frame 2 under the same vocabulary node that own
+  // no map point and pass the stereo filter (:719-728; vbMatched2 is never set in this fork, so the list is static).  ONE
+  // orbm_distance_csr call gives every pair's DescriptorDistance; the loop with its running bestDist (:735), the epipole
+  // distance (:740-746) and CheckDistEpipolarLine (:748) runs on the host in the reference's order, then the orientation
+  // histogram.
+  int SearchForTriangulation(std::shared_ptr<OrbKeyFrame> pKF1, std::shared_ptr<OrbKeyFrame> pKF2, cv::Mat F12,
+                             std::vector<std::pair<size_t, size_t>> &vMatchedPairs, const bool bOnlyStereo)
+  {
+      const cv::Mat Cw = pKF1->GetCameraCenter();
+      const cv::Mat R2w = pKF2->GetRotation();
+      const cv::Mat t2w = pKF2->GetTranslation();
+      const cv::Mat C2 = R2w * Cw + t2w;
+      const float invz = 1.0f / C2.at<float>(2);
+      const float ex = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;
+      const float ey = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
+
+      std::vector<unsigned char> free2((size_t)pKF2->N, 0);
+      for (int i = 0; i < pKF2->N; i++)
+          free2[i] = !pKF2->GetMapPoint((size_t)i) && (!bOnlyStereo || pKF2->mvuRight[i] >= 0);
+
+      std::vector<unsigned int> q;
+      std::vector<int> offsets(1, 0), indices;
+      OrbFeatureVector::const_iterator f1it = pKF1->m_features.begin(), f2it = pKF2->m_features.begin();
+      const OrbFeatureVector::const_iterator f1end = pKF1->m_features.end(), f2end = pKF2->m_features.end();
+      while (f1it != f1end && f2it != f2end) {
+          if (f1it->first == f2it->first) {
+              for (size_t i1 = 0; i1 < f1it->second.size(); i1++) {
+                  const unsigned int idx1 = f1it->second[i1];
+                  if (pKF1->GetMapPoint(idx1)) continue;
+                  if (bOnlyStereo && !(pKF1->mvuRight[idx1] >= 0)) continue;
+                  q.push_back(idx1);
+                  for (size_t i2 = 0; i2 < f2it->second.size(); i2++)
+                      if (free2[f2it->second[i2]]) indices.push_back((int)f2it->second[i2]);
+                  offsets.push_back((int)indices.size());
+              }
+              ++f1it; ++f2it;
+          } else if (f1it->first < f2it->first) {
+              f1it = pKF1->m_features.lower_bound(f2it->first);
+          } else {
+              f2it = pKF2->m_features.lower_bound(f1it->first);
+          }
+      }
+      vMatchedPairs.clear();
+      if (q.empty() || indices.empty()) return 0;
+      cv::Mat qd((int)q.size(), 32, CV_8U);
+      for (size_t k = 0; k < q.size(); k++) pKF1->mDescriptors.row((int)q[k]).copyTo(qd.row((int)k));
+      reserve((int)q.size(), pKF2->mDescriptors.rows);
+      std::vector<int> dist;
+      gpu_->CandidateDistances(qd, pKF2->mDescriptors, offsets, indices, dist);
+
+      int nmatches = 0;
+      std::vector<int> vMatches12((size_t)pKF1->N, -1);
+      std::vector<int> rotHist[64];
+      const int H = HISTO_LENGTH;
+      const float factor = 1.0f / H;
+      for (size_t k = 0; k < q.size(); k++) {
+          const unsigned int idx1 = q[k];
+          const bool bStereo1 = pKF1->mvuRight[idx1] >= 0;
+          const cv::KeyPoint &kp1 = pKF1->mvKeysUn[idx1];
+          int bestDist = TH_LOW, bestIdx2 = -1;
+          for (int e = offsets[k]; e < offsets[k + 1]; e++) {
+              const int idx2 = indices[e];
+              const int d = dist[e];
+              if (d > TH_LOW || d > bestDist) continue;
+              const cv::KeyPoint &kp2 = pKF2->mvKeysUn[idx2];
+              const bool bStereo2 = pKF2->mvuRight[idx2] >= 0;
+              if (!bStereo1 && !bStereo2) {
+                  const float distex = ex - kp2.pt.x;
+                  const float distey = ey - kp2.pt.y;
+                  if (distex * distex + distey * distey < 100 * pKF2->mvScaleFactors[kp2.octave]) continue;
+              }
+              if (CheckDistEpipolarLine(kp1, kp2, F12, pKF2)) { bestIdx2 = idx2; bestDist = d; }
+          }
+          if (bestIdx2 >= 0) {
+              const cv::KeyPoint &kp2 = pKF2->mvKeysUn[bestIdx2];
+              vMatches12[idx1] = bestIdx2;
+              nmatches++;
+              if (mbCheckOrientation) {
+                  float rot = kp1.angle - kp2.angle;
+                  if (rot < 0.0) rot += 360.0f;
+                  int bin = static_cast<int>(round(rot * factor));
+                  if (bin == H) bin = 0;
+                  rotHist[bin].push_back((int)idx1);
+              }
+          }
+      }
+      if (mbCheckOrientation) {
+          int ind1 = -1, ind2 = -1, ind3 = -1;
+          ComputeThreeMaxima(rotHist, H, ind1, ind2, ind3);
+          for (int b = 0; b < H; b++) {
+              if (b == ind1 || b == ind2 || b == ind3) continue;
+              for (size_t j = 0; j < rotHist[b].size(); j++) {
+                  vMatches12[rotHist[b][j]] = -1;
+                  nmatches--;
+              }
+          }
+      }
+      vMatchedPairs.reserve(nmatches > 0 ? nmatches : 0);
+      for (size_t i = 0; i < vMatches12.size(); i++)
+          if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
       return nmatches;
   }
 

@@ -12,9 +12,11 @@
 //   part 4  SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528
 //   part 5  SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616
 //   part 6  SearchByBoW(keyFrame1, keyFrame2, matches12)           src/orbmatcher.cpp:531-663
+//   part 7  SearchForTriangulation(keyFrame1, keyFrame2, F12, ...)  src/orbmatcher.cpp:665-831 (real key frames: the reference's orbkeyframe.cpp)
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
 #include <orbmatcher.hpp>
+#include <orbkeyframe.hpp>
 
 #include <chrono>
 #include <cstring>
@@ -53,6 +55,7 @@ extern "C" {
 // out[28..31] wall microseconds of one warm call: part 1 reference / ORBmatcherB200, part 3 reference / ORBmatcherB200
 // out[24..27] part 5: SearchByProjection(CurrentFrame, key frame, found): the four numbers of part 1
 // out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
+// out[36..43] part 7: SearchForTriangulation(key frame 1, key frame 2), all features / stereo only: nmatches x 2, differing pairs, pairs
 // out[32..35] part 6: SearchByBoW(key frame 1, key frame 2): nmatches x 2, differing vpMatches12 entries, entries set
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
@@ -245,6 +248,36 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
             for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
             out[34] = bad; out[35] = set;
             mpref_standin_clear();
+        }
+        // ---------------- part 7: SearchForTriangulation(key frame 1, key frame 2, F12, pairs, onlyStereo) (:665-831) on two REAL key
+        // frames built by the reference's own constructor from frames A and B: every third feature of A and every fourth of B keeps
+        // a map point (those are skipped, :703-707 / :722-724), key frame 2 sits 3 cm to the right and 20 cm back, F12 has
+        // horizontal epipolar lines (l = x1' F12 = [0, 1, -y1]); nodes as in part 3; once with all features, once stereo only
+        {
+            std::shared_ptr<OrbFrame> FA = std::make_shared<OrbFrame>(A), FB = std::make_shared<OrbFrame>(B);
+            for (int i = 0; i < FA->N; i++) FA->m_mapPoints[i] = (i % 3 == 1) ? std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>()) : std::shared_ptr<OrbMapPoint>();
+            for (int i = 0; i < FB->N; i++) FB->m_mapPoints[i] = (i % 4 == 2) ? std::make_shared<OrbMapPoint>(one, kf, std::shared_ptr<OrbMap>()) : std::shared_ptr<OrbMapPoint>();
+            FA->mFeatVec.clear(); FB->mFeatVec.clear();
+            for (int i = 0; i < FA->N; i++) FA->mFeatVec.addFeature(FA->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            for (int i = 0; i < FB->N; i++) FB->mFeatVec.addFeature(FB->m_descriptors.ptr(i)[0] & 63u, (uint32_t)i);
+            cv::Mat T = I.clone();
+            T.ptr<float>(0)[3] = 0.03f; T.ptr<float>(1)[3] = 0.01f; T.ptr<float>(2)[3] = -0.2f;
+            FA->SetPose(I); FB->SetPose(T);
+            std::shared_ptr<OrbKeyFrame> K1 = std::make_shared<OrbKeyFrame>(FA, std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+            std::shared_ptr<OrbKeyFrame> K2 = std::make_shared<OrbKeyFrame>(FB, std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>());
+            cv::Mat F12(3, 3, CV_32F);
+            for (int i = 0; i < 9; i++) F12.ptr<float>(i / 3)[i % 3] = 0.f;
+            F12.ptr<float>(2)[1] = 1.f; F12.ptr<float>(1)[2] = -1.f;
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            for (int only = 0; only < 2; only++) {
+                std::vector<std::pair<size_t, size_t>> p1, p2;
+                out[36 + 4 * only] = ref.SearchForTriangulation(K1, K2, F12, p1, only != 0);
+                out[37 + 4 * only] = gpu.SearchForTriangulation(K1, K2, F12, p2, only != 0);
+                int bad = (p1.size() != p2.size());
+                for (size_t k = 0; k < p1.size() && k < p2.size(); k++) if (p1[k] != p2[k]) bad++;
+                out[38 + 4 * only] = bad; out[39 + 4 * only] = (int)p1.size();
+            }
         }
     } catch (const std::exception &e) {
         fprintf(stderr, "driverref_check: %s\n", e.what());

@@ -25,7 +25,7 @@ R.driverref_check.argtypes = [C.POINTER(Cfg)] + [C.c_void_p] * 4 + [C.c_int, C.c
 w, h, sa, sb, th_points, th_frames, ratio, dx, dy = {args!r}
 (la, ra), (lb, rb) = synth.stereo_pair(w, h, sa), synth.stereo_pair(w, h, sb)
 imgs = [np.ascontiguousarray(a, np.uint8) for a in (la, ra, lb, rb)]
-out = np.full(40, -99, np.int32)
+out = np.full(64, -99, np.int32)
 rc = R.driverref_check(C.byref(Cfg(2000, 1.2, 8, 20, 7)), *[a.ctypes.data for a in imgs], w, h, 386.1, 0.537,
                        th_points, th_frames, ratio, dx, dy, out.ctypes.data)
 print("RESULT", rc, *out.tolist())
@@ -56,3 +56,6 @@ def test_drop_in_drivers_equal_reference_drivers(w, h, sa, sb, th_points, th_fra
     assert n_ref == n_gpu and bad == 0 and assigned > 0, f"SearchByProjection(current, key frame): {out[24:28]}"
     n_ref, n_gpu, bad, assigned = out[32:36]
     assert n_ref == n_gpu and bad == 0 and assigned > 0, f"SearchByBoW(key frame, key frame): {out[32:36]}"
+    for only, name in enumerate(("all features", "stereo only")):
+        n_ref, n_gpu, bad, pairs = out[36 + 4 * only: 40 + 4 * only]
+        assert n_ref == n_gpu and bad == 0 and (pairs > 0 or only == 1), f"SearchForTriangulation ({name}): {out[36 + 4 * only: 40 + 4 * only]}"
