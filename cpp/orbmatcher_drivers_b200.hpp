@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides seven drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides ten drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device; the sequential rule "a key point that an
 //     observed map point was stored on earlier in the call is skipped", :87-89 after :121, is iterated to its fixpoint);
@@ -21,6 +21,9 @@
 //     closing), candidates restricted to the features of key frame 2 that carry a usable map point;
 //   * SearchForTriangulation(keyFrame1, keyFrame2, F12, pairs, onlyStereo) src/orbmatcher.cpp:665-831 -> the same node walk between
 //     the untracked features of two key frames, epipolar tests on the host;
+//   * SearchByProjection(keyFrame, Scw, points, matched, th) :294-409, Fuse(keyFrame, points, th) :833-982 and
+//     Fuse(keyFrame, Scw, points, th, replace) :984-1108 -> projections on the host, ONE orbm_area_distances call over the key
+//     frame's grid, the sequential loops (with their Replace / AddObservingKeyframe side effects) on the host;
 //   * SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616 -> the same with the key frame's
 //     map points and PredictScale (relocalisation);
 //   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
@@ -29,6 +32,7 @@
 #define ORBMATCHER_DRIVERS_B200_HPP
 
 #include <climits>
+#include <cstring>
 #include <cmath>
 #include <memory>
 #include <set>
@@ -36,6 +40,7 @@
 #include <vector>
 
 #include <orbmatcher.hpp>
+#include <orbkeyframe.hpp>
 
 #include "orbmatcher_b200.hpp"
 
@@ -520,6 +525,203 @@ class ORBmatcherB200 : public ORBmatcher {
       for (size_t i = 0; i < vMatches12.size(); i++)
           if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
       return nmatches;
+  }
+
+  // ---- the three drivers that project map points into a KEY FRAME and search its feature grid: SearchByProjection(keyFrame,
+  // Scw, points, matched, th) :294-409, Fuse(keyFrame, points, th) :833-982 and Fuse(keyFrame, Scw, points, th, replace)
+  // :984-1108.  Pass 1 (host): the reference's own projection and its geometric tests (depth, IsInImage, distance invariance,
+  // viewing angle), PredictScale and the window radius -- none of which changes while the loop runs.  ONE orbm_area_distances
+  // call then evaluates OrbKeyFrame::GetFeaturesInArea (orbkeyframe.cpp:625-675: the frame's grid walk without a level window)
+  // for all windows, restricted to the levels [predicted - 1, predicted] the loops keep anyway, with every DescriptorDistance.
+  // Pass 2 (host): the reference's loop in its own order over the lists -- the tests that DO change during the call
+  // (IsCorrupt, KeyFrameInObservingKeyFrames, vpMatched, GetMapPoint) are evaluated live, and the same Replace /
+  // AddObservingKeyframe / AddMapPoint calls are made.
+  // A key frame indexes its windows from (int)m_minX (orbkeyframe.cpp:630) while its grid was filled with the float bounds
+  // (orbframe.cpp:381-393): with image bounds that are not whole numbers (distorted input) the base class runs instead.
+  struct KfWindows {
+      std::vector<int> slot;                      // point i -> window, or -1 when a geometric test drops it
+      std::vector<float> u, v, ur;                // per window
+      std::vector<int> level, offsets, indices, dist;
+  };
+  static bool wholeBounds(const std::shared_ptr<OrbKeyFrame> &kf)
+  {
+      return (float)kf->mnMinX == OrbFrame::m_minX && (float)kf->mnMinY == OrbFrame::m_minY;
+  }
+  void keyFrameWindows(const std::shared_ptr<OrbKeyFrame> &pKF, const cv::Mat &Rcw, const cv::Mat &tcw, const cv::Mat &Ow, const float bf,
+                       const bool doubleInverse, const std::vector<std::shared_ptr<OrbMapPoint>> &pts, const float th, KfWindows &W)
+  {
+      const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+      W.slot.assign(pts.size(), -1);
+      std::vector<float> qr;
+      std::vector<int> l0;
+      std::vector<size_t> who;
+      for (size_t i = 0; i < pts.size(); i++) {
+          const std::shared_ptr<OrbMapPoint> &pMP = pts[i];
+          if (!pMP) continue;
+          cv::Mat p3Dw = pMP->GetWorldPosition();
+          if (p3Dw.empty()) continue;
+          cv::Mat p3Dc = Rcw * p3Dw + tcw;
+          if (p3Dc.at<float>(2) < 0.0f) continue;
+          const float invz = doubleInverse ? static_cast<const float>(1.0 / p3Dc.at<float>(2)) : 1 / p3Dc.at<float>(2);
+          const float x = p3Dc.at<float>(0) * invz;
+          const float y = p3Dc.at<float>(1) * invz;
+          const float u = fx * x + cx;
+          const float v = fy * y + cy;
+          if (!pKF->IsInImage(u, v)) continue;
+          const float maxDistance = pMP->GetMaxDistanceInvariance();
+          const float minDistance = pMP->GetMinDistanceInvariance();
+          cv::Mat PO = p3Dw - Ow;
+          const float dist3D = static_cast<const float>(cv::norm(PO));
+          if (dist3D < minDistance || dist3D > maxDistance) continue;
+          cv::Mat Pn = pMP->GetMeanViewingDirection();
+          if (PO.dot(Pn) < 0.5 * dist3D) continue;
+          const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+          W.slot[i] = (int)who.size();
+          who.push_back(i);
+          W.u.push_back(u); W.v.push_back(v); W.ur.push_back(u - bf * invz);
+          W.level.push_back(nPredictedLevel);
+          qr.push_back(th * pKF->mvScaleFactors[nPredictedLevel]);
+          l0.push_back(nPredictedLevel - 1);
+      }
+      W.offsets.assign(1, 0);
+      if (who.empty() || pKF->N == 0) { W.offsets.assign(who.size() + 1, 0); return; }
+      cv::Mat qd((int)who.size(), 32, CV_8U);
+      for (size_t k = 0; k < who.size(); k++) {
+          const cv::Mat d = pts[who[k]]->GetDescriptor();
+          if (d.empty()) std::memset(qd.ptr((int)k), 0, 32);
+          else d.copyTo(qd.row((int)k));
+      }
+      reserve((int)who.size(), pKF->N);
+      gpu_->AreaDistances(pKF->mvKeysUn, pKF->mDescriptors, OrbFrame::m_minX, OrbFrame::m_minY, OrbFrame::m_maxX, OrbFrame::m_maxY,
+                          qd, W.u, W.v, qr, l0, W.level, W.offsets, W.indices, W.dist);
+  }
+
+  // ---- src/orbmatcher.cpp:294-409 (loop closing)
+  int SearchByProjection(std::shared_ptr<OrbKeyFrame> pKF, cv::Mat Scw, const std::vector<std::shared_ptr<OrbMapPoint>> &vpPoints,
+                         std::vector<std::shared_ptr<OrbMapPoint>> &vpMatched, int th)
+  {
+      if (!wholeBounds(pKF)) return ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th);
+      cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+      const float scw = static_cast<const float>(sqrt(sRcw.row(0).dot(sRcw.row(0))));
+      cv::Mat Rcw = sRcw / scw;
+      cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+      cv::Mat Ow = -Rcw.t() * tcw;
+      std::set<std::shared_ptr<OrbMapPoint>> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+      spAlreadyFound.erase(std::shared_ptr<OrbMapPoint>());
+      KfWindows W;
+      keyFrameWindows(pKF, Rcw, tcw, Ow, 0.0f, false, vpPoints, (float)th, W);
+      int nmatches = 0;
+      for (size_t iMP = 0; iMP < vpPoints.size(); iMP++) {
+          const std::shared_ptr<OrbMapPoint> &pMP = vpPoints[iMP];
+          if (pMP->IsCorrupt() || spAlreadyFound.count(pMP)) continue;
+          const int k = W.slot[iMP];
+          if (k < 0) continue;
+          int bestDist = 256, bestIdx = -1;
+          for (int e = W.offsets[k]; e < W.offsets[k + 1]; e++) {
+              const int idx = W.indices[e];
+              if (vpMatched[idx]) continue;
+              if (W.dist[e] < bestDist) { bestDist = W.dist[e]; bestIdx = idx; }
+          }
+          if (bestDist <= TH_LOW) {
+              vpMatched[bestIdx] = pMP;
+              nmatches++;
+          }
+      }
+      return nmatches;
+  }
+
+  // ---- src/orbmatcher.cpp:833-982 (local mapping: SearchInNeighbors)
+  int Fuse(std::shared_ptr<OrbKeyFrame> pKF, const std::vector<std::shared_ptr<OrbMapPoint>> &vpMapPoints, const float th = 3.0)
+  {
+      if (!wholeBounds(pKF)) return ORBmatcher::Fuse(pKF, vpMapPoints, th);
+      cv::Mat Rcw = pKF->GetRotation();
+      cv::Mat tcw = pKF->GetTranslation();
+      cv::Mat Ow = pKF->GetCameraCenter();
+      KfWindows W;
+      keyFrameWindows(pKF, Rcw, tcw, Ow, pKF->mbf, false, vpMapPoints, th, W);
+      int nFused = 0;
+      for (size_t i = 0; i < vpMapPoints.size(); i++) {
+          std::shared_ptr<OrbMapPoint> pMP = vpMapPoints[i];
+          if (!pMP) continue;
+          if (pMP->IsCorrupt() || pMP->KeyFrameInObservingKeyFrames(pKF)) continue;
+          const int k = W.slot[i];
+          if (k < 0) continue;
+          const float u = W.u[k], v = W.v[k], ur = W.ur[k];
+          int bestDist = 256, bestIdx = -1;
+          for (int e = W.offsets[k]; e < W.offsets[k + 1]; e++) {
+              const int idx = W.indices[e];
+              const cv::KeyPoint &kp = pKF->mvKeysUn[idx];
+              const int &kpLevel = kp.octave;
+              if (pKF->mvuRight[idx] >= 0) {
+                  const float &kpx = kp.pt.x;
+                  const float &kpy = kp.pt.y;
+                  const float &kpr = pKF->mvuRight[idx];
+                  const float ex = u - kpx;
+                  const float ey = v - kpy;
+                  const float er = ur - kpr;
+                  const float e2 = ex * ex + ey * ey + er * er;
+                  if (e2 * pKF->mvInvLevelSigma2[kpLevel] > 7.8) continue;
+              } else {
+                  const float &kpx = kp.pt.x;
+                  const float &kpy = kp.pt.y;
+                  const float ex = u - kpx;
+                  const float ey = v - kpy;
+                  const float e2 = ex * ex + ey * ey;
+                  if (e2 * pKF->mvInvLevelSigma2[kpLevel] > 5.99) continue;
+              }
+              if (W.dist[e] < bestDist) { bestDist = W.dist[e]; bestIdx = idx; }
+          }
+          if (bestDist <= TH_LOW) {
+              std::shared_ptr<OrbMapPoint> pMPinKF = pKF->GetMapPoint(bestIdx);
+              if (pMPinKF) {
+                  if (!pMPinKF->IsCorrupt()) {
+                      if (pMPinKF->GetObservingKeyframes() > pMP->GetObservingKeyframes()) pMP->Replace(pMPinKF);
+                      else pMPinKF->Replace(pMP);
+                  }
+              } else {
+                  pMP->AddObservingKeyframe(pKF, bestIdx);
+                  pKF->AddMapPoint(pMP, bestIdx);
+              }
+              nFused++;
+          }
+      }
+      return nFused;
+  }
+
+  // ---- src/orbmatcher.cpp:984-1108 (loop closing: SearchAndFuse)
+  int Fuse(std::shared_ptr<OrbKeyFrame> pKF, cv::Mat Scw, const std::vector<std::shared_ptr<OrbMapPoint>> &vpPoints, float th,
+           std::vector<std::shared_ptr<OrbMapPoint>> &vpReplacePoint)
+  {
+      if (!wholeBounds(pKF)) return ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint);
+      cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+      const float scw = static_cast<const float>(sqrt(sRcw.row(0).dot(sRcw.row(0))));
+      cv::Mat Rcw = sRcw / scw;
+      cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+      cv::Mat Ow = -Rcw.t() * tcw;
+      const std::set<std::shared_ptr<OrbMapPoint>> spAlreadyFound = pKF->GetMapPoints();
+      KfWindows W;
+      keyFrameWindows(pKF, Rcw, tcw, Ow, 0.0f, true, vpPoints, th, W);
+      int nFused = 0;
+      for (size_t iMP = 0; iMP < vpPoints.size(); iMP++) {
+          std::shared_ptr<OrbMapPoint> pMP = vpPoints[iMP];
+          if (pMP->IsCorrupt() || spAlreadyFound.count(pMP)) continue;
+          const int k = W.slot[iMP];
+          if (k < 0) continue;
+          int bestDist = INT_MAX, bestIdx = -1;
+          for (int e = W.offsets[k]; e < W.offsets[k + 1]; e++)
+              if (W.dist[e] < bestDist) { bestDist = W.dist[e]; bestIdx = W.indices[e]; }
+          if (bestDist <= TH_LOW) {
+              std::shared_ptr<OrbMapPoint> pMPinKF = pKF->GetMapPoint(bestIdx);
+              if (pMPinKF) {
+                  if (!pMPinKF->IsCorrupt()) vpReplacePoint[iMP] = pMPinKF;
+              } else {
+                  pMP->AddObservingKeyframe(pKF, bestIdx);
+                  pKF->AddMapPoint(pMP, bestIdx);
+              }
+              nFused++;
+          }
+      }
+      return nFused;
   }
 
   // ---- src/orbmatcher.cpp:411-528 (monocular initialisation): windows around the previously matched positions of the level-0

@@ -12,6 +12,9 @@
 //   part 4  SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528
 //   part 5  SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616
 //   part 6  SearchByBoW(keyFrame1, keyFrame2, matches12)           src/orbmatcher.cpp:531-663
+//   part 8  SearchByProjection(keyFrame, Scw, points, matched, th)   src/orbmatcher.cpp:294-409
+//   part 9  Fuse(keyFrame, Scw, points, th, replace)                src/orbmatcher.cpp:984-1108
+//   part 10 Fuse(keyFrame, points, th)                              src/orbmatcher.cpp:833-982
 //   part 7  SearchForTriangulation(keyFrame1, keyFrame2, F12, ...)  src/orbmatcher.cpp:665-831 (real key frames: the reference's orbkeyframe.cpp)
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
@@ -19,6 +22,8 @@
 #include <orbkeyframe.hpp>
 
 #include <chrono>
+#include <cstdlib>
+#include <new>
 #include <cstring>
 #include <sstream>
 
@@ -56,6 +61,9 @@ extern "C" {
 // out[24..27] part 5: SearchByProjection(CurrentFrame, key frame, found): the four numbers of part 1
 // out[20..23] part 4: SearchForInitialization(F1, F2): nmatches x 2, differing vnMatches12 / vbPrevMatched entries, matches
 // out[36..43] part 7: SearchForTriangulation(key frame 1, key frame 2), all features / stereo only: nmatches x 2, differing pairs, pairs
+// out[44..47] part 8: SearchByProjection(key frame, Scw, ...): nmatches x 2, differing vpMatched entries, entries set
+// out[48..52] part 9: Fuse(key frame, Scw, ...): nFused x 2, differences (key-frame matches, corrupt flags, observation counts, vpReplacePoint), matches held, replacements
+// out[53..57] part 10: Fuse(key frame, points): nFused x 2, differences, matches held, corrupt points afterwards
 // out[32..35] part 6: SearchByBoW(key frame 1, key frame 2): nmatches x 2, differing vpMatches12 entries, entries set
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
@@ -277,6 +285,117 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
                 int bad = (p1.size() != p2.size());
                 for (size_t k = 0; k < p1.size() && k < p2.size(); k++) if (p1[k] != p2[k]) bad++;
                 out[38 + 4 * only] = bad; out[39 + 4 * only] = (int)p1.size();
+            }
+        }
+        // ---------------- parts 8-10: the drivers that project map points into a KEY FRAME and walk its grid.  The key frame is built by
+        // the reference's constructor from a copy of frame B (pose: 3 cm right, 1 cm down, 20 cm back; every fifth feature owns a map
+        // point that observes the key frame), the candidates are frame A's key points at their stereo depth (8 m without one), built
+        // by the reference's OrbMapPoint(position, frame, map, index) constructor; every 13th is corrupt.  Each run gets a model of
+        // its own (the Fuse drivers store observations and replace map points).  The observer `k0` and the key frame live side by
+        // side in one buffer, k0 first: Fuse(keyFrame, points) compares std::maps keyed by key-frame ADDRESS (:962), and with k0 the
+        // lowest key of every map the comparison is decided by k0's feature index in both models alike.
+        {
+            struct Model {
+                void *raw = nullptr;
+                std::shared_ptr<OrbKeyFrame> k0, K;
+                std::vector<std::shared_ptr<OrbMapPoint>> inKF, cand;
+                ~Model() { inKF.clear(); cand.clear(); K.reset(); k0.reset(); free(raw); }
+            };
+            cv::Mat T = I.clone();
+            T.ptr<float>(0)[3] = 0.03f; T.ptr<float>(1)[3] = 0.01f; T.ptr<float>(2)[3] = -0.2f;
+            auto build = [&](Model &M) {
+                M.raw = malloc(sizeof(OrbKeyFrame) * 2 + alignof(OrbKeyFrame));
+                char *base = (char *)(((uintptr_t)M.raw + alignof(OrbKeyFrame) - 1) & ~(uintptr_t)(alignof(OrbKeyFrame) - 1));
+                std::shared_ptr<OrbFrame> F0 = std::make_shared<OrbFrame>(A), FB = std::make_shared<OrbFrame>(B);
+                for (int i = 0; i < F0->N; i++) F0->m_mapPoints[i] = std::shared_ptr<OrbMapPoint>();
+                for (int i = 0; i < FB->N; i++) FB->m_mapPoints[i] = std::shared_ptr<OrbMapPoint>();
+                F0->SetPose(I); FB->SetPose(T);
+                M.k0 = std::shared_ptr<OrbKeyFrame>(new (base) OrbKeyFrame(F0, std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>()),
+                                                    [](OrbKeyFrame *k) { k->~OrbKeyFrame(); });
+                M.K = std::shared_ptr<OrbKeyFrame>(new (base + sizeof(OrbKeyFrame)) OrbKeyFrame(FB, std::shared_ptr<OrbMap>(), std::shared_ptr<OrbKeyFrameDatabase>()),
+                                                   [](OrbKeyFrame *k) { k->~OrbKeyFrame(); });
+                M.inKF.assign((size_t)B->N, std::shared_ptr<OrbMapPoint>());
+                for (int i = 0; i < B->N; i += 5) {
+                    const float z = B->m_depths[i] > 0 ? B->m_depths[i] : 8.0f;
+                    cv::Mat pos(3, 1, CV_32F);
+                    pos.ptr<float>(0)[0] = (B->m_undistortedKeys[i].pt.x - OrbFrame::cx) * z * OrbFrame::invfx;
+                    pos.ptr<float>(1)[0] = (B->m_undistortedKeys[i].pt.y - OrbFrame::cy) * z * OrbFrame::invfy;
+                    pos.ptr<float>(2)[0] = z;
+                    auto mp = std::make_shared<OrbMapPoint>(pos, FB, std::shared_ptr<OrbMap>(), i);
+                    mp->AddObservingKeyframe(M.k0, (size_t)(1 + i % 2));
+                    mp->AddObservingKeyframe(M.K, (size_t)i);
+                    M.K->AddMapPoint(mp, (size_t)i);
+                    M.inKF[i] = mp;
+                }
+                for (int i = 0; i < A->N; i++) {
+                    const float z = A->m_depths[i] > 0 ? A->m_depths[i] : 8.0f;
+                    cv::Mat pos(3, 1, CV_32F);
+                    pos.ptr<float>(0)[0] = (A->m_undistortedKeys[i].pt.x - OrbFrame::cx) * z * OrbFrame::invfx;
+                    pos.ptr<float>(1)[0] = (A->m_undistortedKeys[i].pt.y - OrbFrame::cy) * z * OrbFrame::invfy;
+                    pos.ptr<float>(2)[0] = z;
+                    auto mp = std::make_shared<OrbMapPoint>(pos, F0, std::shared_ptr<OrbMap>(), i);
+                    mp->AddObservingKeyframe(M.k0, (size_t)(1 + i % 3));
+                    if (i % 13 == 7) mp->SetCorruptFlag();
+                    M.cand.push_back(mp);
+                    if (i % 29 == 3) M.cand.push_back(mp);                       // a point listed twice
+                }
+            };
+            // what the two models hold afterwards, position by position
+            auto label = [](const Model &M, const std::shared_ptr<OrbMapPoint> &p) -> int {
+                if (!p) return -1;
+                for (size_t k = 0; k < M.cand.size(); k++) if (M.cand[k] == p) return (int)k;
+                for (size_t k = 0; k < M.inKF.size(); k++) if (M.inKF[k] == p) return 1000000 + (int)k;
+                return -2;
+            };
+            auto differences = [&](Model &X, Model &Y, int *held) {
+                int bad = 0, set = 0;
+                for (int i = 0; i < X.K->N; i++) {
+                    const int a = label(X, X.K->GetMapPoint((size_t)i)), b = label(Y, Y.K->GetMapPoint((size_t)i));
+                    if (a != b) bad++;
+                    if (a != -1) set++;
+                }
+                for (size_t k = 0; k < X.cand.size(); k++)
+                    if (X.cand[k]->IsCorrupt() != Y.cand[k]->IsCorrupt() ||
+                        X.cand[k]->GetObservingKeyFrameCount() != Y.cand[k]->GetObservingKeyFrameCount()) bad++;
+                for (size_t k = 0; k < X.inKF.size(); k++)
+                    if (X.inKF[k] && (X.inKF[k]->IsCorrupt() != Y.inKF[k]->IsCorrupt() ||
+                                      X.inKF[k]->GetObservingKeyFrameCount() != Y.inKF[k]->GetObservingKeyFrameCount())) bad++;
+                *held = set;
+                return bad;
+            };
+            cv::Mat Scw = T.clone();                                              // a similarity with scale 1.25: [s R | s t]
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) Scw.ptr<float>(r)[c] *= 1.25f;
+            ORBmatcher ref(nnratio, true);
+            ORBmatcherB200 gpu(nnratio, true);
+            {   // part 8: SearchByProjection(key frame, Scw, points, matched, th) (:294-409): vpMatched starts as the key frame's own matches
+                Model X, Y; build(X); build(Y);
+                std::vector<std::shared_ptr<OrbMapPoint>> m1 = X.K->GetMapPointMatches(), m2 = Y.K->GetMapPointMatches();
+                out[44] = ref.SearchByProjection(X.K, Scw, X.cand, m1, 10);
+                out[45] = gpu.SearchByProjection(Y.K, Scw, Y.cand, m2, 10);
+                int bad = (m1.size() != m2.size()), set = 0;
+                for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (label(X, m1[k]) != label(Y, m2[k])) bad++; if (m1[k]) set++; }
+                out[46] = bad; out[47] = set;
+            }
+            {   // part 9: Fuse(key frame, Scw, points, th, replace) (:984-1108)
+                Model X, Y; build(X); build(Y);
+                std::vector<std::shared_ptr<OrbMapPoint>> r1(X.cand.size()), r2(Y.cand.size());
+                out[48] = ref.Fuse(X.K, Scw, X.cand, 4.0f, r1);
+                out[49] = gpu.Fuse(Y.K, Scw, Y.cand, 4.0f, r2);
+                int held = 0, bad = differences(X, Y, &held), repl = 0;
+                for (size_t k = 0; k < r1.size(); k++) { if (label(X, r1[k]) != label(Y, r2[k])) bad++; if (r1[k]) repl++; }
+                out[50] = bad; out[51] = held; out[52] = repl;
+            }
+            {   // part 10: Fuse(key frame, points, th) (:833-982), with its Replace calls
+                Model X, Y; build(X); build(Y);
+                out[53] = ref.Fuse(X.K, X.cand, 3.0f);
+                out[54] = gpu.Fuse(Y.K, Y.cand, 3.0f);
+                int held = 0;
+                out[55] = differences(X, Y, &held);
+                out[56] = held;
+                int corrupt = 0;
+                for (size_t k = 0; k < X.cand.size(); k++) corrupt += X.cand[k]->IsCorrupt();
+                for (size_t k = 0; k < X.inKF.size(); k++) if (X.inKF[k]) corrupt += X.inKF[k]->IsCorrupt();
+                out[57] = corrupt;
             }
         }
     } catch (const std::exception &e) {

@@ -59,3 +59,10 @@ def test_drop_in_drivers_equal_reference_drivers(w, h, sa, sb, th_points, th_fra
     for only, name in enumerate(("all features", "stereo only")):
         n_ref, n_gpu, bad, pairs = out[36 + 4 * only: 40 + 4 * only]
         assert n_ref == n_gpu and bad == 0 and (pairs > 0 or only == 1), f"SearchForTriangulation ({name}): {out[36 + 4 * only: 40 + 4 * only]}"
+    n_ref, n_gpu, bad, held = out[44:48]
+    assert n_ref == n_gpu and bad == 0 and held > 0, f"SearchByProjection(key frame, Scw): {out[44:48]}"
+    n_ref, n_gpu, bad, held, repl = out[48:53]
+    assert n_ref == n_gpu and bad == 0 and held > 0, f"Fuse(key frame, Scw): {out[48:53]}"
+    n_ref, n_gpu, bad, held, corrupt = out[53:58]
+    assert n_ref == n_gpu and bad == 0 and held > 0, f"Fuse(key frame, points): {out[53:58]}"
+    print("key-frame drivers:", out[32:58].tolist())
