@@ -7,7 +7,7 @@
 //     matcher.SearchByBoW(m_referenceKeyFrame, m_currentFrame, matches);                           // TrackReferenceKeyFrame
 //
 // ORBmatcherB200 derives from ORBmatcher, keeps its constructor arguments, thresholds and protected helpers
-// (RadiusByViewingCos, ComputeThreeMaxima) and hides ten drivers:
+// (RadiusByViewingCos, ComputeThreeMaxima) and hides all eleven drivers:
 //   * SearchByProjection(frame, map points, th)            src/orbmatcher.cpp:42-124   -> one orbm_search_by_projection call
 //     (frame grid, GetFeaturesInArea, candidate loop and acceptance on the device; the sequential rule "a key point that an
 //     observed map point was stored on earlier in the call is skipped", :87-89 after :121, is iterated to its fixpoint);
@@ -24,6 +24,7 @@
 //   * SearchByProjection(keyFrame, Scw, points, matched, th) :294-409, Fuse(keyFrame, points, th) :833-982 and
 //     Fuse(keyFrame, Scw, points, th, replace) :984-1108 -> projections on the host, ONE orbm_area_distances call over the key
 //     frame's grid, the sequential loops (with their Replace / AddObservingKeyframe side effects) on the host;
+//   * SearchBySim3(keyFrame1, keyFrame2, matches12, s12, R12, t12, th) :1110-1335 -> one orbm_area_distances call per direction;
 //   * SearchByProjection(CurrentFrame, keyFrame, found, th, d) src/orbmatcher.cpp:1485-1616 -> the same with the key frame's
 //     map points and PredictScale (relocalisation);
 //   * SearchForInitialization(F1, F2, prevMatched, matches)  src/orbmatcher.cpp:411-528   -> one orbm_area_distances call.
@@ -722,6 +723,100 @@ class ORBmatcherB200 : public ORBmatcher {
           }
       }
       return nFused;
+  }
+
+  // ---- src/orbmatcher.cpp:1110-1335 (loop closing: matches between the map points of two key frames under a similarity).
+  // Both directions are static loops (nothing found earlier in the call excludes anything later): the map points of key frame 1
+  // are projected into key frame 2 and vice versa on the host with the reference's expressions, each direction is ONE
+  // orbm_area_distances call, the first least distance of every window is taken (:1207-1218, strict '<'), and the agreement
+  // check (:1315-1330) follows.
+  int SearchBySim3(std::shared_ptr<OrbKeyFrame> pKF1, std::shared_ptr<OrbKeyFrame> pKF2, std::vector<std::shared_ptr<OrbMapPoint>> &vpMatches12,
+                   const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)
+  {
+      if (!wholeBounds(pKF1) || !wholeBounds(pKF2)) return ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th);
+      const float &fx = pKF1->fx, &fy = pKF1->fy, &cx = pKF1->cx, &cy = pKF1->cy;
+      cv::Mat R1w = pKF1->GetRotation();
+      cv::Mat t1w = pKF1->GetTranslation();
+      cv::Mat R2w = pKF2->GetRotation();
+      cv::Mat t2w = pKF2->GetTranslation();
+      cv::Mat sR12 = s12 * R12;
+      cv::Mat sR21 = (1.0 / s12) * R12.t();
+      cv::Mat t21 = -sR21 * t12;
+      const std::vector<std::shared_ptr<OrbMapPoint>> vpMapPoints1 = pKF1->GetMapPointMatches();
+      const int N1 = (int)vpMapPoints1.size();
+      const std::vector<std::shared_ptr<OrbMapPoint>> vpMapPoints2 = pKF2->GetMapPointMatches();
+      const int N2 = (int)vpMapPoints2.size();
+      std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+      for (int i = 0; i < N1; i++) {
+          std::shared_ptr<OrbMapPoint> pMP = vpMatches12[i];
+          if (pMP) {
+              vbAlreadyMatched1[i] = true;
+              int idx2 = pMP->GetObeservationIndexOfKeyFrame(pKF2);
+              if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+          }
+      }
+      // one direction: the map points `from` (already-matched ones skipped) through (Rw, tw) and (sR, t) into `into`
+      auto direction = [&](const std::vector<std::shared_ptr<OrbMapPoint>> &from, const std::vector<bool> &already, const cv::Mat &Rw,
+                           const cv::Mat &tw, const cv::Mat &sR, const cv::Mat &t, const std::shared_ptr<OrbKeyFrame> &into,
+                           std::vector<int> &match) {
+          match.assign(from.size(), -1);
+          std::vector<int> who, l0, l1, offsets, indices, dist;
+          std::vector<float> qx, qy, qr;
+          for (size_t i = 0; i < from.size(); i++) {
+              const std::shared_ptr<OrbMapPoint> &pMP = from[i];
+              if (!pMP || already[i]) continue;
+              if (pMP->IsCorrupt()) continue;
+              cv::Mat p3Dw = pMP->GetWorldPosition();
+              cv::Mat p3Da = Rw * p3Dw + tw;
+              cv::Mat p3Db = sR * p3Da + t;
+              if (p3Db.at<float>(2) < 0.0) continue;
+              const float invz = static_cast<const float>(1.0 / p3Db.at<float>(2));
+              const float x = p3Db.at<float>(0) * invz;
+              const float y = p3Db.at<float>(1) * invz;
+              const float u = fx * x + cx;
+              const float v = fy * y + cy;
+              if (!into->IsInImage(u, v)) continue;
+              const float maxDistance = pMP->GetMaxDistanceInvariance();
+              const float minDistance = pMP->GetMinDistanceInvariance();
+              const float dist3D = static_cast<const float>(cv::norm(p3Db));
+              if (dist3D < minDistance || dist3D > maxDistance) continue;
+              const int nPredictedLevel = pMP->PredictScale(dist3D, into);
+              who.push_back((int)i);
+              qx.push_back(u); qy.push_back(v); qr.push_back(th * into->mvScaleFactors[nPredictedLevel]);
+              l0.push_back(nPredictedLevel - 1); l1.push_back(nPredictedLevel);
+          }
+          if (who.empty() || into->N == 0) return;
+          cv::Mat qd((int)who.size(), 32, CV_8U);
+          for (size_t k = 0; k < who.size(); k++) {
+              const cv::Mat d = from[who[k]]->GetDescriptor();
+              if (d.empty()) std::memset(qd.ptr((int)k), 0, 32);
+              else d.copyTo(qd.row((int)k));
+          }
+          reserve((int)who.size(), into->N);
+          gpu_->AreaDistances(into->mvKeysUn, into->mDescriptors, OrbFrame::m_minX, OrbFrame::m_minY, OrbFrame::m_maxX, OrbFrame::m_maxY,
+                              qd, qx, qy, qr, l0, l1, offsets, indices, dist);
+          for (size_t k = 0; k < who.size(); k++) {
+              int bestDist = INT_MAX, bestIdx = -1;
+              for (int e = offsets[k]; e < offsets[k + 1]; e++)
+                  if (dist[e] < bestDist) { bestDist = dist[e]; bestIdx = indices[e]; }
+              if (bestDist <= TH_HIGH) match[who[k]] = bestIdx;
+          }
+      };
+      std::vector<int> vnMatch1, vnMatch2;
+      direction(vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, pKF2, vnMatch1);
+      direction(vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, t12, pKF1, vnMatch2);
+      int nFound = 0;
+      for (int i1 = 0; i1 < N1; i1++) {
+          const int idx2 = vnMatch1[i1];
+          if (idx2 >= 0) {
+              const int idx1 = vnMatch2[idx2];
+              if (idx1 == i1) {
+                  vpMatches12[i1] = vpMapPoints2[idx2];
+                  nFound++;
+              }
+          }
+      }
+      return nFound;
   }
 
   // ---- src/orbmatcher.cpp:411-528 (monocular initialisation): windows around the previously matched positions of the level-0

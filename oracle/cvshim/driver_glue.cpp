@@ -15,6 +15,7 @@
 //   part 8  SearchByProjection(keyFrame, Scw, points, matched, th)   src/orbmatcher.cpp:294-409
 //   part 9  Fuse(keyFrame, Scw, points, th, replace)                src/orbmatcher.cpp:984-1108
 //   part 10 Fuse(keyFrame, points, th)                              src/orbmatcher.cpp:833-982
+//   part 11 SearchBySim3(keyFrame1, keyFrame2, matches12, s12, R12, t12, th) src/orbmatcher.cpp:1110-1335
 //   part 7  SearchForTriangulation(keyFrame1, keyFrame2, F12, ...)  src/orbmatcher.cpp:665-831 (real key frames: the reference's orbkeyframe.cpp)
 // Built by `make -C oracle ref` into oracle/_ref/libdriverref.so (links liborbx.so); used by tests/test_gpu_drivers.py.
 #include <orbframe.hpp>
@@ -64,6 +65,7 @@ extern "C" {
 // out[44..47] part 8: SearchByProjection(key frame, Scw, ...): nmatches x 2, differing vpMatched entries, entries set
 // out[48..52] part 9: Fuse(key frame, Scw, ...): nFused x 2, differences (key-frame matches, corrupt flags, observation counts, vpReplacePoint), matches held, replacements
 // out[53..57] part 10: Fuse(key frame, points): nFused x 2, differences, matches held, corrupt points afterwards
+// out[58..61] part 11: SearchBySim3(key frame 1, key frame 2, ...): nFound x 2, differing vpMatches12 entries, entries set
 // out[32..35] part 6: SearchByBoW(key frame 1, key frame 2): nmatches x 2, differing vpMatches12 entries, entries set
 int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *rightA, const uint8_t *leftB, const uint8_t *rightB,
                     int w, int h, float mbf, float mb, float th_points, float th_frames, float nnratio, float dx, float dy, int32_t *out)
@@ -384,6 +386,36 @@ int driverref_check(const frameref_cfg *c, const uint8_t *leftA, const uint8_t *
                 int held = 0, bad = differences(X, Y, &held), repl = 0;
                 for (size_t k = 0; k < r1.size(); k++) { if (label(X, r1[k]) != label(Y, r2[k])) bad++; if (r1[k]) repl++; }
                 out[50] = bad; out[51] = held; out[52] = repl;
+            }
+            {   // part 11: SearchBySim3(key frame 1, key frame 2, matches12, s12, R12, t12, th) (:1110-1335).  Key frame 1 = k0 (frame A at
+                // the origin) with a map point on three of four features, key frame 2 = K with its own points; the similarity is the
+                // true relative pose (scale 1); every 19th entry of vpMatches12 is set beforehand (:1139-1149)
+                Model X; build(X);
+                for (int i = 0; i < A->N; i++)
+                    if (i % 4 != 1) {
+                        const float z = A->m_depths[i] > 0 ? A->m_depths[i] : 8.0f;
+                        cv::Mat pos(3, 1, CV_32F);
+                        pos.ptr<float>(0)[0] = (A->m_undistortedKeys[i].pt.x - OrbFrame::cx) * z * OrbFrame::invfx;
+                        pos.ptr<float>(1)[0] = (A->m_undistortedKeys[i].pt.y - OrbFrame::cy) * z * OrbFrame::invfy;
+                        pos.ptr<float>(2)[0] = z;
+                        std::shared_ptr<OrbFrame> F0 = std::make_shared<OrbFrame>(A);
+                        F0->SetPose(I);
+                        auto mp = std::make_shared<OrbMapPoint>(pos, F0, std::shared_ptr<OrbMap>(), i);
+                        mp->AddObservingKeyframe(X.k0, (size_t)i);
+                        X.k0->AddMapPoint(mp, (size_t)i);
+                    }
+                // T12 = T1w * Tw2 with T1w = I: the inverse of K's pose
+                cv::Mat R12 = T.rowRange(0, 3).colRange(0, 3).t();
+                cv::Mat t12 = -R12 * T.rowRange(0, 3).col(3);
+                const float s12 = 1.0f;
+                std::vector<std::shared_ptr<OrbMapPoint>> m1((size_t)X.k0->N), m2;
+                for (int i = 0; i < X.k0->N; i += 19) m1[i] = X.inKF[(size_t)(5 * (i % 40))];
+                m2 = m1;
+                out[58] = ref.SearchBySim3(X.k0, X.K, m1, s12, R12, t12, 7.5f);
+                out[59] = gpu.SearchBySim3(X.k0, X.K, m2, s12, R12, t12, 7.5f);
+                int bad = (m1.size() != m2.size()), set = 0;
+                for (size_t k = 0; k < m1.size() && k < m2.size(); k++) { if (m1[k] != m2[k]) bad++; if (m1[k]) set++; }
+                out[60] = bad; out[61] = set;
             }
             {   // part 10: Fuse(key frame, points, th) (:833-982), with its Replace calls
                 Model X, Y; build(X); build(Y);

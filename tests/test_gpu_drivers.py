@@ -65,4 +65,6 @@ def test_drop_in_drivers_equal_reference_drivers(w, h, sa, sb, th_points, th_fra
     assert n_ref == n_gpu and bad == 0 and held > 0, f"Fuse(key frame, Scw): {out[48:53]}"
     n_ref, n_gpu, bad, held, corrupt = out[53:58]
     assert n_ref == n_gpu and bad == 0 and held > 0, f"Fuse(key frame, points): {out[53:58]}"
-    print("key-frame drivers:", out[32:58].tolist())
+    n_ref, n_gpu, bad, held = out[58:62]
+    assert n_ref == n_gpu and bad == 0 and held > 0, f"SearchBySim3: {out[58:62]}"
+    print("key-frame drivers:", out[32:62].tolist())
