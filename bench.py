@@ -47,7 +47,7 @@ CONFIGS = {
                 label="synthetic 3840x2160 frames, 8000 features, 12 levels, 4-frame batch (BASELINE config[3])"),
 }
 W, H, NFEAT, NLEVELS, BATCH = 1241, 376, 2000, 8, 64
-PIPE_DEPTH = 3          # device-resident batches in flight per GPU (orbx_pipe)
+PIPE_DEPTH = 4          # device-resident batches in flight per GPU (orbx_pipe)
 NQ, NT = 2000, 100000
 REFERENCE_IMPL = ("the reference's own src/orbextractor.cpp, compiled unmodified, linked to the repo's SCALAR restatement of the "
                   "OpenCV primitives (oracle/cvshim: resize, FAST, GaussianBlur) -- not to OpenCV's SIMD code; a real OpenCV 3.3.1 "

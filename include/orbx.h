@@ -135,6 +135,10 @@ int orbx_multi_frame_range(const orbx_multi *m, int batch, int slot, int *first,
 int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t frame_stride, size_t pitch,
                               int batch, int width, int height, void *stream);
 /* d_kps: batch x kp_stride records; d_desc: batch x kp_stride x 32 bytes; d_counts: batch ints */
+/* How many parts orbx_extract_batch_device cuts a batch into (each part runs its stages on a stream pair of its own, so one
+ * part's latency-bound stages overlap another's): 0 = default (two for batches of 16 frames and more), 1..4.  A pipe sets 1 on its
+ * handles -- there the overlap comes from the other batches in flight, and whole-batch launches are 3 % faster. */
+int orbx_set_device_split(orbx_extractor *h, int parts);
 int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const uint8_t **d_desc,
                         const int **d_counts, int *kp_stride);
 

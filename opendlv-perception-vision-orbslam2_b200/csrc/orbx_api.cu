@@ -69,6 +69,7 @@ struct orbx_extractor {
     std::vector<OrbxRTab> rtab;
     std::vector<OrbxTile> tiles;
     int maxRows = 0, maxNodes = 0, pow2Nodes = 0;
+    int deviceSplit = 0;             // parts an orbx_extract_batch_device call is cut into (0: two for batches of 16 frames and more)
     int fastWinRows = 0, fastListCap = 0;   // shared-memory geometry of k_fast_segs
     bool geomUploaded = false;
     // device state
@@ -738,7 +739,7 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     h->lastBatch = batch;
     h->lastLaunches = 0;
     static const int splitEnv = getenv("ORBX_SPLIT") ? atoi(getenv("ORBX_SPLIT")) : 0;
-    const int nSplit = std::min(batch, splitEnv > 0 ? std::min(splitEnv, ORBX_LANES) : (batch >= 16 ? 2 : 1));
+    const int nSplit = std::min(batch, splitEnv > 0 ? std::min(splitEnv, ORBX_LANES) : h->deviceSplit > 0 ? std::min(h->deviceSplit, ORBX_LANES) : (batch >= 16 ? 2 : 1));
     if (nSplit == 1) {
         launch_copy_level0(d_imgs, frame_stride, pitch, h->dPyr.p, h->L, batch, st);
         rc = enqueuePipeline(h, 0, batch, st, h->lane[0]);
@@ -764,6 +765,14 @@ int orbx_extract_batch_device(orbx_extractor *h, const uint8_t *d_imgs, size_t f
     }
     CK(cudaEventRecord(h->evLast, st));
     h->lastPending = true;
+    return ORBX_OK;
+}
+
+int orbx_set_device_split(orbx_extractor *h, int parts)
+{
+    if (!h) return ORBX_ERR_ARG;
+    if (parts < 0 || parts > ORBX_LANES) return fail(h, ORBX_ERR_ARG, "parts must be 0 (default) .. 4");
+    h->deviceSplit = parts;
     return ORBX_OK;
 }
 

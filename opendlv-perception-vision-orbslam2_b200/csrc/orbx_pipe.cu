@@ -49,6 +49,7 @@ int orbx_pipe_create(const orbx_config *cfg, int depth, orbx_pipe **out)
     for (orbx_pipe::Slot &s : p->slots) {
         const int rc = orbx_create(cfg, &s.h);
         if (rc != ORBX_OK) return pfail(p, rc, s.h ? orbx_last_error(s.h) : "invalid configuration");
+        if (depth > 1) orbx_set_device_split(s.h, 1);      // the other batches in flight provide the overlap; whole-batch launches
         PCK(cudaSetDevice(p->device));
         PCK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         PCK(cudaEventCreateWithFlags(&s.evIn, cudaEventDisableTiming));

@@ -39,7 +39,7 @@ EXPORTS = ["orbx_version", "orbx_create", "orbx_destroy", "orbx_last_error", "or
            "orbx_multi_max_keypoints", "orbx_multi_extract_batch", "orbx_multi_extract_batch_async", "orbx_multi_wait", "orbx_multi_handle",
            "orbx_multi_frame_range", "orbm_multi_create", "orbm_multi_destroy", "orbm_multi_last_error", "orbm_multi_devices", "orbm_multi_set_train",
            "orbm_multi_knn2", "orbm_multi_matcher",
-           "orbx_extract_batch_device", "orbx_device_results", "orbx_pipe_create", "orbx_pipe_destroy", "orbx_pipe_last_error", "orbx_pipe_depth",
+           "orbx_extract_batch_device", "orbx_set_device_split", "orbx_device_results", "orbx_pipe_create", "orbx_pipe_destroy", "orbx_pipe_last_error", "orbx_pipe_depth",
            "orbx_pipe_submit", "orbx_pipe_join", "orbx_pipe_handle", "orbx_fetch_results", "orbx_filter_keypoints", "orbx_stereo_match", "orbx_stereo_match_batch", "orbx_max_keypoints", "orbx_host_alloc", "orbx_host_free", "orbx_last_launches", "orbx_get_level",
            "orbx_scale_tables", "orbx_profile_stages", "orbx_debug_blurred", "orbx_debug_enable_candidates", "orbx_debug_candidates",
            "orbm_create", "orbm_destroy", "orbm_last_error", "orbm_knn2", "orbm_set_train", "orbm_knn2_resident",
@@ -94,6 +94,7 @@ def lib():
     L.orbx_stereo_match.argtypes = [vp, C.c_int, vp, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_stereo_match_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, C.c_int, ip, ip]
     L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_set_device_split.argtypes = [vp, C.c_int]
     L.orbx_pipe_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
     L.orbx_pipe_destroy.argtypes = [vp]; L.orbx_pipe_destroy.restype = None
     L.orbx_pipe_last_error.argtypes = [vp]; L.orbx_pipe_last_error.restype = C.c_char_p

@@ -16,7 +16,7 @@ else:
     base = [synth.scene_s1(W, H, 9000 + i) for i in range(min(b, 4))]
     frames = [np.roll(base[f % len(base)], 5 * f, axis=1) for f in range(b)]
 d = torch.from_numpy(np.stack(frames)).cuda()
-for nh in (1, 2, 3):
+for nh in tuple(int(v) for v in os.environ.get("NH", "1,2,3").split(",")):
     exs = [orbx.Extractor(nf, 1.2, nl, 20, 7, max_width=W, max_height=H, max_batch=b) for _ in range(nh)]
     sts = [torch.cuda.Stream() for _ in range(nh)]
     for k in range(2 * nh):
