@@ -153,7 +153,8 @@ int orbx_device_results(orbx_extractor *h, const orbx_keypoint **d_kps, const ui
  *                     stay valid until the slot is submitted to again, i.e. for depth - 1 further submissions; work the
  *                     caller enqueues on them must be in `stream` before the submission that reuses the slot.
  *   orbx_pipe_handle  the extractor that holds the submission (orbx_stereo_match_batch, orbx_filter_keypoints, orbx_get_level,
- *                     orbx_fetch_results of exactly that batch); NULL once the slot has been reused. */
+ *                     orbx_fetch_results of exactly that batch); NULL once the slot has been reused.
+ * Like an extractor handle a pipe is entered by one thread at a time; different pipes and handles are independent. */
 typedef struct orbx_pipe orbx_pipe;
 int orbx_pipe_create(const orbx_config *cfg, int depth, orbx_pipe **out);
 void orbx_pipe_destroy(orbx_pipe *p);
