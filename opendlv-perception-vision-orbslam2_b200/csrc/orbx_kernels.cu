@@ -627,7 +627,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn * FW_P + xs
     uint16_t *corner = cand + listCap;                               // kcap (<= listCap): on overflow stage 3a scans the score map instead
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int nmax, ncorner;                                     // stage 3a / stage 2 list lengths
+    __shared__ int ncorner;                                           // stage 2 list length
     __shared__ int wsum[FS_T / 32], nq2s;
     __shared__ unsigned cellsDone;
     __shared__ uint8_t cellOf[ORBX_SEG_W], qlist[64];
@@ -647,7 +647,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        nmax = 0; ncorner = 0; cellsDone = 0u;
+        ncorner = 0; cellsDone = 0u;
     }
     __syncthreads();
     if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
@@ -676,11 +676,10 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         unsigned mQx = seg.mQ & 0xffffffu;
         int nQx = nQ, hB = (int)(seg.mQ >> 24);
         if (pass) {
-            cmask = allCells & ~cellsDone;                            // final since the barrier after stage 3a
+            cmask = allCells & ~cellsDone;                            // final since the barrier that ends pass 0
             if (!cmask) break;                                        // uniform
             dense = cmask == allCells;
-            __syncthreads();                                          // stage 3b of pass 0 is done with the lists and counters
-            if (tid == 0) { ncorner = 0; nmax = 0; }
+            if (tid == 0) ncorner = 0;
             if (!dense && tid < 32) {
                 // aligned quads that touch an empty cell, in ascending order (two per lane)
                 const int wq0 = B0 >> 2;
@@ -750,72 +749,61 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         __syncthreads();
         const int nk = ncorner;
 
-        // ---- stage 3a: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); the
-        // survivors are compacted into the (now free) survivor list
+        // ---- stage 3: 3x3 non-maximum suppression (strict >; outside the cell interior counts as 0); a maximum goes straight
+        // into the per-(strip,row) summaries -- its cell is final in this pass: pass 0 keeps every cell that has one, pass 1
+        // only works on cells that had none.
         // (a corner list that did not fit -- more than kcap corners, dense noise -- is replaced by a scan of the score map)
         const bool scan = nk > kcap;
         const int nIt = scan ? wT * hT : nk;
+        unsigned done = 0u;
         for (int i0 = 0; i0 < nIt; i0 += FS_T) {
             const int i = i0 + tid;
-            bool isMax = false, have = i < nIt;
-            int e = 0, xs = 0;
-            unsigned done = 0u;
+            bool have = i < nIt;
+            int e = 0, xs = 0, yIn = 0;
             if (have) {
-                if (!scan) { e = corner[i]; xs = e - fast_row_of(e) * FW_P; }
+                if (!scan) { e = corner[i]; yIn = fast_row_of(e); xs = e - yIn * FW_P; }
                 else {
-                    const int y = i / wT;
-                    xs = i - y * wT; e = y * FW_P + xs;
+                    yIn = i / wT;
+                    xs = i - yIn * wT; e = yIn * FW_P + xs;
                     have = smap[e + (FM_P + 1)] != 0 && ((cmask >> cellOf[xs]) & 1u);
                 }
             }
             if (have) {
                 const int cl = cellOf[xs], xIn = xs - cl * wCell;
-                const uint8_t *s = smap + e + (FM_P + 1);
-                const int v = s[0];
+                const uint8_t *sp = smap + e + (FM_P + 1);
+                const int v = sp[0];
                 const bool lOk = xIn > 0, rOk = xIn < wCell - 1;
-                const int l0 = lOk ? max(max((int)s[-FM_P - 1], (int)s[-1]), (int)s[FM_P - 1]) : 0;
-                const int r0 = rOk ? max(max((int)s[-FM_P + 1], (int)s[1]), (int)s[FM_P + 1]) : 0;
-                const int m = max(max(l0, r0), max((int)s[-FM_P], (int)s[FM_P]));
-                isMax = v > m;
-                if (isMax) done = 1u << cl;                            // the cell keeps its initial-threshold result
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, isMax);
-            if (bal) {
-                if (pass == 0) { done = __reduce_or_sync(0xffffffffu, done); if (lane == 0) atomicOr(&cellsDone, done); }
-                int base = 0;
-                if (lane == 0) base = smem_atomic_add(&nmax, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (isMax) cand[base + __popc(bal & lt)] = (uint16_t)e;
-            }
-        }
-        __syncthreads();
-        const int nm = nmax;
-
-        // ---- stage 3b: emit into the per-(strip,row) summaries
-        for (int i = tid; i < nm; i += FS_T) {
-            const int e = cand[i];
-            const int yIn = fast_row_of(e), xs = e - yIn * FW_P;
-            const int s = smap[e + (FM_P + 1)];
-            const int cl = cellOf[xs], xIn = xs - cl * wCell;
-            const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
-            int strip = 0;                                                                  // xr / hX, :710
+                const int l0 = lOk ? max(max((int)sp[-FM_P - 1], (int)sp[-1]), (int)sp[FM_P - 1]) : 0;
+                const int r0 = rOk ? max(max((int)sp[-FM_P + 1], (int)sp[1]), (int)sp[FM_P + 1]) : 0;
+                const int m = max(max(l0, r0), max((int)sp[-FM_P], (int)sp[FM_P]));
+                if (v > m) {
+                    done |= 1u << cl;                                  // the cell keeps its initial-threshold result
+                    const int xr = seg.cj0 * wCell + 3 + xs, yr = seg.ci * lv.hCell + 3 + yIn;     // relative to (16,16), :963-964
+                    int strip = 0;                                                                  // xr / hX, :710
 #pragma unroll
-            for (int k = 1; k < ORBX_MAX_STRIPS; k++) strip += (xr >= k * lv.hX);
-            const int row = strip * lv.H + yr;
-            const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
-            const unsigned long long key = ((unsigned long long)s << 56) |
-                                           ((unsigned long long)(0x0fffffffu - order) << 28) |
-                                           ((unsigned long long)xr << 14) | (unsigned long long)yr;
-            atomicAdd(&cntF[row], 1u);
-            atomicMax(&bestF[row], key);
-            if (dbg) {
-                const int slot = frame * L.nlevels + seg.level;
-                const int pos = atomicAdd(&dbgCount[slot], 1);
-                if (pos < dbgCap) {
-                    OrbxDbgCand c; c.xy = xr | (yr << 16); c.score = s;
-                    dbg[(size_t)slot * dbgCap + pos] = c;
+                    for (int k = 1; k < ORBX_MAX_STRIPS; k++) strip += (xr >= k * lv.hX);
+                    const int row = strip * lv.H + yr;
+                    const unsigned order = (unsigned)(seg.ci * lv.nCols + seg.cj0 + cl) << 12 | (unsigned)(yIn << 6 | xIn);
+                    const unsigned long long key = ((unsigned long long)v << 56) |
+                                                   ((unsigned long long)(0x0fffffffu - order) << 28) |
+                                                   ((unsigned long long)xr << 14) | (unsigned long long)yr;
+                    atomicAdd(&cntF[row], 1u);
+                    atomicMax(&bestF[row], key);
+                    if (dbg) {
+                        const int slot = frame * L.nlevels + seg.level;
+                        const int pos = atomicAdd(&dbgCount[slot], 1);
+                        if (pos < dbgCap) {
+                            OrbxDbgCand c; c.xy = xr | (yr << 16); c.score = v;
+                            dbg[(size_t)slot * dbgCap + pos] = c;
+                        }
+                    }
                 }
             }
+        }
+        if (pass == 0) {
+            done = __reduce_or_sync(0xffffffffu, done);
+            if (lane == 0 && done) atomicOr(&cellsDone, done);
+            __syncthreads();                                          // cellsDone is complete before pass 1 reads it
         }
     }
 }
