@@ -540,11 +540,10 @@ __device__ __forceinline__ void fast_margin2(const uint8_t *cA, const uint8_t *c
 // loads (centre of row y+3, left and right neighbour word of row y).  Per item 4 VABSDIFF4 and bit 7 of ((d + K) | d) per
 // byte, K = 127 - th: set iff d > th.  (A byte whose sum overflows carries one into its upper neighbour, which can only turn
 // that neighbour's "d == th" into a pass -- the filter stays a superset; the overflowing byte itself has bit 7 of d set.)
-// The survivor flags of up to 8 rows are collected in a register (4 bits per item) and written out after ONE block-wide
-// scan of the per-thread counts, so the survivor list is in a deterministic order (thread, row, pixel): consecutive entries are
-// vertical neighbours, FW_P / 4 = 68 words = 4 banks apart.  Returns the number of survivors (same in every thread).
-// Contains __syncthreads(); call uniformly.
-__device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *cand, int *wsum, const uint8_t *qlist, const bool dense,
+// The survivor flags of up to 8 rows are collected in a register (4 bits per item) and written out warp by warp (order inside
+// a warp: thread, row, pixel -- consecutive entries are vertical neighbours, FW_P / 4 = 68 words = 4 banks apart).  *ncand
+// accumulates the number of survivors; the caller synchronises before reading the list.  Warp-synchronous: call with full warps.
+__device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *cand, int *ncand, const uint8_t *qlist, const bool dense,
                                                  const int nQx, const unsigned mQx, const int hB, const int tid, const int lane,
                                                  const int B0, const int wT, const int hT, const int th)
 {
@@ -561,7 +560,6 @@ __device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *c
     }
     const uint32_t K = (uint32_t)(127 - th) * 0x01010101u;
     constexpr int P4 = FW_P / 4;
-    int total = 0;
     for (int rb = 0; rb < hB; rb += 8) {
         const int y0 = band * hB + rb;                                  // first row of this thread in this round
         const int n = band < R ? min(min(8, hB - rb), hT - y0) : 0;
@@ -584,20 +582,17 @@ __device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *c
                 cm3 = cm2; cm2 = cm1; cm1 = c0; c0 = cp1; cp1 = cp2; cp2 = cp3;
             }
         }
-        // block-wide exclusive scan of the per-thread survivor counts
+        // the warp's survivors go to the list as one block: inclusive scan of the per-thread counts, ONE shared atomic per warp
+        // for the block's position (the order of the warps' blocks does not reach the results: scores go to the score map, the
+        // row summaries are order-independent), no block barrier
         const int c = __popc(bits);
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[tid >> 5] = incl;
-        __syncthreads();
-        int pos = total + incl - c;
-#pragma unroll
-        for (int w = 0; w < FS_T / 32; w++) {
-            const int t = wsum[w];
-            if (w < (tid >> 5)) pos += t;
-            total += t;
-        }
+        int base = 0;
+        if (lane == 31 && incl) base = smem_atomic_add(ncand, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - c;
         const int e0 = y0 * FW_P + 4 * (wq0 + q) - B0;                 // entry yIn * FW_P + xs of pixel 0 of the thread's first row
         while (bits) {                                                 // two survivors per trip
             const int b = __ffs((int)bits) - 1;
@@ -610,9 +605,7 @@ __device__ __forceinline__ int fast_quick_reject(const uint8_t *win, uint16_t *c
             }
             pos += 2;
         }
-        if (rb + 8 < hB) __syncthreads();                              // wsum is written again
     }
-    return total;
 }
 
 __global__ void __launch_bounds__(FS_T, 5)
@@ -627,8 +620,8 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn * FW_P + xs
     uint16_t *corner = cand + listCap;                               // kcap (<= listCap): on overflow stage 3a scans the score map instead
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int ncorner;                                           // stage 2 list length
-    __shared__ int wsum[FS_T / 32], nq2s;
+    __shared__ int ncand, ncorner;                                    // stage 1 / stage 2 list lengths
+    __shared__ int nq2s;
     __shared__ unsigned cellsDone;
     __shared__ uint8_t cellOf[ORBX_SEG_W], qlist[64];
 
@@ -647,7 +640,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        ncorner = 0; cellsDone = 0u;
+        ncand = 0; ncorner = 0; cellsDone = 0u;
     }
     __syncthreads();
     if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
@@ -679,7 +672,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
             cmask = allCells & ~cellsDone;                            // final since the barrier that ends pass 0
             if (!cmask) break;                                        // uniform
             dense = cmask == allCells;
-            if (tid == 0) ncorner = 0;
+            if (tid == 0) { ncand = 0; ncorner = 0; }
             if (!dense && tid < 32) {
                 // aligned quads that touch an empty cell, in ascending order (two per lane)
                 const int wq0 = B0 >> 2;
@@ -706,8 +699,9 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         }
 
         // ---- stage 1: packed quick reject, 4 pixels per item
-        const int nc = fast_quick_reject(win, cand, wsum, qlist, dense, nQx, mQx, hB, tid, lane, B0, wT, hT, thQ);
+        fast_quick_reject(win, cand, &ncand, qlist, dense, nQx, mQx, hB, tid, lane, B0, wT, hT, thQ);
         __syncthreads();
+        const int nc = ncand;
 
         // ---- stage 2: threshold margin of every survivor, two per thread (survivors i and i + half share the
         // 16-bit halves of the registers); corners (margin > threshold, in a cell of this pass) get their score written
