@@ -285,9 +285,9 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
         int nProc = 0;
         for (int j = 0; j < v.nCols; j++) if (ORBX_MINB + j * v.wCell < maxBX - 6) nProc++;
         // k_fast_segs stage 1 gives a thread one quad column and a band of at most 8 rows: a run is kept narrow enough for
-        // 256 / ceil(hCell / 8) quad columns to cover it in one round (a wider run still works, in several rounds)
+        // ORBX_FAST_THREADS / ceil(hCell / 8) quad columns to cover it in one round (a wider run still works, in several rounds)
         const int bandsNeeded = (v.hCell + 7) / 8;
-        const int widthCap = std::min(ORBX_SEG_W, 4 * (256 / bandsNeeded - 2));
+        const int widthCap = std::min(ORBX_SEG_W, 4 * (ORBX_FAST_THREADS / bandsNeeded - 2));
         const int perSegMax = std::max(1, std::min(8, widthCap / v.wCell));
         const int nSegRow = (nProc + perSegMax - 1) / perSegMax;
         const int perSeg = nSegRow ? (nProc + nSegRow - 1) / nSegRow : 0;
@@ -309,7 +309,7 @@ int buildGeometry(orbx_extractor *h, int w, int h0, OrbxLayout &L, std::vector<O
                 sg.ci = (uint16_t)i; sg.cj0 = (uint16_t)j0;
                 const int B0 = iniX + 3 - ((iniX - 4) & ~15);   // shared byte of the first tested pixel (TMA box is 16-byte aligned)
                 const int nQ = ((B0 + (int)sg.wT - 1) >> 2) - (B0 >> 2) + 1;
-                const int nBands = 256 / nQ;                      // FS_T / nQ bands of rows, k_fast_segs stage 1
+                const int nBands = std::max(1, ORBX_FAST_THREADS / nQ);   // bands of rows, k_fast_segs stage 1
                 sg.mQ = (uint32_t)((1u << 20) / nQ + 1) | (uint32_t)(((int)sg.hT + nBands - 1) / nBands) << 24;
                 segs.push_back(sg);
                 listCap = std::max(listCap, (int)sg.wT * (int)sg.hT);
@@ -425,9 +425,9 @@ int buildTensorMaps(orbx_extractor *h, int frames)
         CUresult r = encode(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)(h->dPyr.p + v.off), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        // k_fast_segs reads 32-bit elements: a box of 68 x window rows (FW_P = 272 bytes per row) is wider than the 256-element limit of a byte map
+        // k_fast_segs reads 32-bit elements: a box of ORBX_FAST_PITCH / 4 elements x window rows (k_fast_segs indexes its window in words; the box start is 16-byte aligned either way)
         cuuint64_t gdimF[3] = {(cuuint64_t)(v.pitch / 4), (cuuint64_t)v.h, (cuuint64_t)frames};
-        cuuint32_t boxF[3] = {68, (cuuint32_t)v.winH, 1};
+        cuuint32_t boxF[3] = {ORBX_FAST_PITCH / 4, (cuuint32_t)v.winH, 1};
         CUresult r2 = encode(&h->tmapsFast.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)(h->dPyr.p + v.off), gdimF, gstr, boxF, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -49,7 +49,9 @@ struct OrbxLayout {
 // One FAST segment: a run of up to ORBX_SEG_W tested columns of horizontally adjacent cells of one cell row
 // (orbextractor.cpp:930-947).  The tested pixels of the cells tile the run without gaps: cell j of the run
 // covers tested columns [j*wCell, (j+1)*wCell), the last one clipped by the level border.
-#define ORBX_SEG_W 224
+#define ORBX_SEG_W 112
+#define ORBX_FAST_THREADS 128     // threads of a k_fast_segs CTA
+#define ORBX_FAST_PITCH 144       // bytes per row of its window and score map: 36 words, so vertical neighbours sit 4 banks apart
 struct OrbxSeg {
     uint16_t x0, y0;     // window origin in level coordinates (iniX of the first cell, iniY)
     uint16_t wT;         // tested columns of the run (sum over its cells of window width - 6)
@@ -57,7 +59,7 @@ struct OrbxSeg {
     uint8_t level;
     uint16_t ci, cj0;    // cell row / first cell column: (ci*nCols + cj) is a cell's position in the reference's emission order
     uint32_t mQ;         // bits 0-23: 2^20/nQ + 1, nQ = aligned 4-pixel groups covering one tested row of the run;
-                         // bits 24-31: rows per band, ceil(hT / (256 / nQ))
+                         // bits 24-31: rows per band, ceil(hT / (ORBX_FAST_THREADS / nQ))
 };
 
 #define ORBX_BLUR_ROWS 36       // output rows per warp band of k_blur; a tile is 4 bands

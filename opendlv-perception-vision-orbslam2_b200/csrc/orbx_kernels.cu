@@ -123,6 +123,16 @@ __device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMa
                  ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
 }
 
+// The tensor maps live in global memory and are REWRITTEN by the host whenever the frame size changes (orbx_api.cu:
+// buildTensorMaps).  The TMA unit reads them through its own proxy and may still hold the previous contents of the same 128
+// bytes; the thread that issues the loads acquires the descriptor first (system scope: the writer was a host cudaMemcpy).
+// Without it a handle that alternates between two frame sizes occasionally fetched boxes with the other size's strides
+// (scripts/probe/soak_handle.py, seed 4031: a replayed CUDA graph, a few pyramid levels of a few frames).
+__device__ __forceinline__ void tmap_acquire(const CUtensorMap *map)
+{
+    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
     const uint32_t b = smem_u32(bar);
@@ -211,6 +221,7 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
         if (lane == 0) {
             int lastXY = -1, xs = 0, ys = 0;
             pdl_wait();            // the source level is complete and visible (only the TMA loads read it)
+            tmap_acquire(srcMap);
             for (int t = t0; t < t1; t++) {
                 const int i = t - t0, b = i % RS_STAGES;
                 const int xy = t / batch, f = t - xy * batch;
@@ -358,8 +369,10 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid == 0) {
+        tmap_acquire(maps + tile.level);
         tma_load_tile_3d(tileS, maps + tile.level, (int)tile.x0 * 4 - 16, (int)tile.y0 - 3, f, &bar, BL_BOXH * BL_BOXW);
+    }
 
     const int x0 = (tile.x0 + threadIdx.x) * 4;
     const int y0 = tile.y0 + threadIdx.y * BL_ROWS;
@@ -488,10 +501,11 @@ void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, co
 //   3  3x3 NMS on the run's score map (neighbours in another cell count as 0, as each cell is an
 //      isolated cv::FAST call), per-cell threshold fallback, emission
 // ------------------------------------------------------------------------------------------
-#define FS_T 256  // threads per CTA
-#define FW_P 272  // shared window pitch in bytes = TMA box width (68 words: vertical neighbours are 4 banks apart)
-#define FM_P 272  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P: list entries are yIn * FW_P + xs)
-__device__ __forceinline__ int fast_row_of(int e) { return (int)(((unsigned)e * 15421u) >> 22); }   // e / 272 for e < 17000
+#define FS_T ORBX_FAST_THREADS  // threads per CTA
+#define FW_P ORBX_FAST_PITCH  // shared window pitch in bytes = TMA box width (36 words: vertical neighbours are 4 banks apart)
+#define FM_P ORBX_FAST_PITCH  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P: list entries are yIn * FW_P + xs)
+static_assert(FW_P == 144, "fast_row_of divides by 144");
+__device__ __forceinline__ int fast_row_of(int e) { return (int)(((unsigned)e * 3641u) >> 19); }   // e / 144 for e < 9000 (60 rows)
 
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -608,7 +622,7 @@ __device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *
     }
 }
 
-__global__ void __launch_bounds__(FS_T, 5)
+__global__ void __launch_bounds__(FS_T, 10)
 k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
             const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
             unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
@@ -643,7 +657,10 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         ncand = 0; ncorner = 0; cellsDone = 0u;
     }
     __syncthreads();
-    if (tid == 0) tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
+    if (tid == 0) {
+        tmap_acquire(maps + seg.level);
+        tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
+    }
     for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
     if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (unsigned)lv.cellMagic) >> 16);            // tid / wCell
     const int nCells = (int)(((unsigned)(wT - 1) * (unsigned)lv.cellMagic) >> 16) + 1;
@@ -803,17 +820,19 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
 }
 
 // Capacity of the corner list.  The survivor list must hold every tested pixel of a run (noise lets them all through the quick
-// reject); the corner list gets what is left of the shared memory that still admits FIVE resident CTAs per SM, but at least
-// a quarter of the pixels -- past that stage 3a falls back to scanning the score map.  ORBX_FAST_KCAP overrides (tests).
+// reject); the corner list gets what is left of the shared memory that still admits ten (else nine, ...) resident CTAs of 128
+// threads per SM, but at least a sixth of the pixels -- past that stage 3 falls back to scanning the score map.  ORBX_FAST_KCAP overrides (tests).
 int fast_corner_cap(int winRows, int listCap)
 {
     static const int forced = getenv("ORBX_FAST_KCAP") ? atoi(getenv("ORBX_FAST_KCAP")) : 0;
     if (forced > 0) return std::min(listCap, (forced + 7) & ~7);
-    const long budget = (233472 - 5 * 1024) / 5 - 512;       // per CTA: 228 KB per SM, 1 KB reserved per CTA, static shared memory
     const long fixed = (long)winRows * FW_P + (long)(winRows - 4) * FM_P + 2L * listCap;
-    const long room = (budget - fixed) / 2;
-    if (room < listCap / 4) return listCap;                   // five CTAs do not fit anyway
-    return (int)std::min<long>(listCap, room & ~7L);
+    for (int ctas = 10; ctas >= 6; ctas--) {
+        const long budget = (233472 - ctas * 1024) / ctas - 512;   // per CTA: 228 KB per SM, 1 KB reserved per CTA, static shared memory
+        const long room = (budget - fixed) / 2;
+        if (room >= listCap / 6) return (int)std::min<long>(listCap, room & ~7L);
+    }
+    return listCap;
 }
 
 size_t fast_smem_bytes(int winRows, int listCap)
@@ -1308,6 +1327,7 @@ k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
+    unsigned acquired = 0u;           // lane 0: levels whose two tensor maps this warp has acquired
     // resolve slot j of this warp and start streaming its two patches into stage `buf`
     auto issue = [&](int j, int buf) -> DescSlot {
         DescSlot s; s.valid = 0; s.cx = s.cy = s.level = s.out = s.score = 0;
@@ -1324,6 +1344,7 @@ k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict_
         s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
         s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
         if (lane == 0) {
+            if (!((acquired >> level) & 1u)) { tmap_acquire(mapsB + level); tmap_acquire(mapsA + level); acquired |= 1u << level; }
             // box starts are 16-byte aligned: the patch column cx-18 (cx-15) sits at byte (cx-18) & 15 ((cx-15) & 15) of its row
             uint8_t *sB = patch[warp][buf], *sA = sB + DS_BUFB;
             const uint32_t bb = smem_u32(&bars[warp][buf]);

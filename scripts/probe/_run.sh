@@ -1,3 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_extract.py -x -q 2>&1 | tail -3
-for c in kitti hd uhd; do python scripts/probe/dev_batch.py $c 20; done
-NH=4 ORBX_SPLIT=1 python scripts/probe/two_handles.py kitti 20
+for v in "X=1" "X=2" "ORBX_LANES=1"; do echo "== $v"; env $v python scripts/probe/soak_handle_dbg.py 150 4031 2>&1 | grep "^call\|bad frames" | cut -c1-150 | tail -4; done

@@ -584,3 +584,43 @@ def test_gpu_against_the_frozen_reference_fixture():
     kps, desc, cnt = ex.extract_batch([noise])
     same(kps[0], desc[0], int(cnt[0]), g["noise_kps"], g["noise_desc"])
     ex.close()
+
+
+def test_rewritten_tensor_maps_are_acquired_before_use(oracle):
+    """One handle alternating between two frame sizes through the host path (replayed CUDA graphs) and the device path: every
+    size change rewrites the tensor maps in global memory, and the kernels must acquire them (fence.proxy.tensormap) before the
+    TMA unit uses them.  Without the fence the call sequence below (scripts/probe/soak_handle.py, seed 4031) returned a few
+    pyramid levels of a few frames described from boxes fetched with the other size's strides -- at call 73, every time."""
+    import torch
+    import orbx
+    rng = np.random.default_rng(4031)
+    sizes = [(1241, 376), (752, 480)]
+    pool = {s: [synth.scene_s1(s[0], s[1], 100 + i) if i % 3 else synth.scene_s2(s[0], s[1], 100 + i) for i in range(12)] for s in sizes}
+    want = {s: [oracle.Extractor(1500, 1.2, 8).extract(img) for img in pool[s]] for s in sizes}
+    ex = orbx.Extractor(1500, 1.2, 8, max_width=1241, max_height=480, max_batch=24)
+    for call in range(90):
+        s = sizes[int(rng.integers(0, 2))]; w, h = s
+        b = int(rng.integers(1, 25)); idx = rng.integers(0, 12, b)
+        mode = ("pinned", "pageable", "pitched", "device")[int(rng.integers(0, 4))]
+        if mode == "pinned":
+            hb = torch.empty((b, h, w), dtype=torch.uint8).pin_memory()
+            for f in range(b):
+                hb[f] = torch.from_numpy(pool[s][idx[f]])
+            kps, desc, cnt = ex.extract_batch([hb[f].numpy() for f in range(b)])
+        elif mode == "pageable":
+            kps, desc, cnt = ex.extract_batch([pool[s][i].copy() for i in idx])
+        elif mode == "pitched":
+            big = np.zeros((b, h, w + 37), np.uint8)
+            for f in range(b):
+                big[f, :, :w] = pool[s][idx[f]]
+            kps, desc, cnt = ex.extract_batch([big[f, :, :w] for f in range(b)])
+        else:
+            dev = torch.from_numpy(np.stack([pool[s][i] for i in idx])).cuda()
+            torch.cuda.synchronize()
+            ex.extract_batch_device(dev.data_ptr(), w * h, w, b, w, h)
+            kps, desc, cnt = ex.fetch_results(b)
+        for f in range(b):
+            okp, od = want[s][idx[f]]
+            n = int(cnt[f])
+            assert n == len(okp) and kps[f, :n].tobytes() == okp.tobytes() and np.array_equal(desc[f, :n], od), (call, s, b, mode, f)
+    ex.close()
