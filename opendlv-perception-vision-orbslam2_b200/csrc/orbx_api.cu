@@ -113,7 +113,7 @@ struct orbx_extractor {
     OrbxTensorMaps tmapsResize;      // same levels, box = source region of a k_resize tile (192 x 48)
     OrbxTensorMaps tmapsDescA;       // same levels, box = unblurred IC_Angle patch of k_describe (48 x 31)
     OrbxTensorMaps tmapsDescB;       // levels of the BLUR slab, box = rBRIEF patch of k_describe (64 x 37)
-    DevBuf<OrbxTensorMaps> dTmaps;   // [0] blur boxes, [1] FAST boxes, [2] resize boxes, [3] / [4] describe boxes (pyramid / blur slab)
+    unsigned tmapGen = 0;            // bumped whenever the maps are re-encoded (frame size, arena pointers, frame count)
     const uint8_t *tmapBase = nullptr, *tmapBaseBlur = nullptr; int tmapFrames = 0, tmapW = 0, tmapH = 0;
     DevBuf<uint8_t> dIn;
     DevBuf<uint8_t> dPyrRaw, dBlurRaw, dDesc;
@@ -450,17 +450,9 @@ int buildTensorMaps(orbx_extractor *h, int frames)
             return fail(h, ORBX_ERR_CUDA, msg);
         }
     }
-    CK(h->dTmaps.ensure(5));
-    CK(drainLast(h));
-    for (int i = 0; i < ORBX_LANES; i++) {
-        CK(cudaStreamSynchronize(h->lane[i].main));
-        CK(cudaStreamSynchronize(h->lane[i].side));
-    }
-    CK(cudaMemcpy(h->dTmaps.p, &h->tmaps, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->dTmaps.p + 1, &h->tmapsFast, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->dTmaps.p + 2, &h->tmapsResize, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->dTmaps.p + 3, &h->tmapsDescA, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->dTmaps.p + 4, &h->tmapsDescB, sizeof(OrbxTensorMaps), cudaMemcpyHostToDevice));
+    // the maps travel as kernel parameters (by value): launches already enqueued keep their own copies, nothing to wait for;
+    // graphs captured with the previous maps are dropped through the signature
+    h->tmapGen++;
     h->tmapBase = h->dPyr.p; h->tmapBaseBlur = h->dBlur.p; h->tmapFrames = frames; h->tmapW = h->curW; h->tmapH = h->curH;
     return ORBX_OK;
 }
@@ -530,24 +522,24 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
     const int segs0 = L.lv[0].nSegs;
     CK(cudaEventRecord(ln.evFork, st));
     CK(cudaStreamWaitEvent(ln.side, ln.evFork, 0));
-    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, ln.side));
+    CK(launch_fast(h->tmapsFast, f0, L, h->dSegs.p, 0, segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, ln.side));
     CK(cudaEventRecord(ln.evFast0, ln.side));
     for (int l = 1; l < L.nlevels; l++) {
-        launch_resize(h->dTmaps.p[2].m, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
+        launch_resize(h->tmapsResize, f0, pyr, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
         CKM(cudaGetLastError(), "k_resize launch");
     }
     CK(cudaEventRecord(ln.evPyr, st));
     CK(cudaStreamWaitEvent(ln.side, ln.evPyr, 0));
     // FAST of levels 1.. is enqueued BEFORE the blur: CTAs are dispatched in launch order, so the blur fills FAST's tail and keeps
     // the SMs busy while the octree (a few latency-bound CTAs) runs, instead of the other way round
-    CK(launch_fast(h->dTmaps.p[1].m, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
+    CK(launch_fast(h->tmapsFast, f0, L, h->dSegs.p, segs0, L.totalSegs - segs0, cnt, best, dbg, dbgCount, h->dbgCap, h->fastWinRows, h->fastListCap, batch, st));
     CK(cudaStreamWaitEvent(st, ln.evFast0, 0));
     CK(launch_octree(L, cnt, best, slots, lvlCount, h->maxRows, h->maxNodes, batch, st));
-    launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
+    launch_blur(h->tmaps, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, f0, batch, ln.side);
     CKM(cudaGetLastError(), "k_blur launch");
     CK(cudaEventRecord(ln.evJoin, ln.side));
     CK(cudaStreamWaitEvent(st, ln.evJoin, 0));
-    launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, f0, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
+    launch_describe(h->tmapsDescA, h->tmapsDescB, f0, L, slots, lvlCount, h->umax, h->dKps.p + (size_t)f0 * L.kpStride,
                     h->dDesc.p + (size_t)f0 * L.kpStride * 32, h->dCounts.p + f0, batch, st);
     CKM(cudaGetLastError(), "k_describe launch");
     // level-0 copy (by the caller of this function) + resize chain + FAST (level 0 | upper levels) + blur + octree + describe
@@ -558,11 +550,12 @@ int enqueuePipeline(orbx_extractor *h, int f0, int batch, cudaStream_t st, const
 uint64_t arenaSignature(const orbx_extractor *h)
 {
     const void *ptrs[] = {h->dIn.p, h->dPyr.p, h->dBlur.p, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->dCounts.p,
-                          h->dKps.p, h->dDesc.p, h->dSegs.p, h->dRtab.p, h->dTiles.p, h->dTmaps.p, h->dDbg.p, h->dDbgCount.p};
+                          h->dKps.p, h->dDesc.p, h->dSegs.p, h->dRtab.p, h->dTiles.p, h->dDbg.p, h->dDbgCount.p};
     uint64_t x = 1469598103934665603ull;
     auto mix = [&x](uint64_t v) { x = (x ^ v) * 1099511628211ull; };
     for (const void *q : ptrs) mix((uint64_t)(uintptr_t)q);
     mix((uint64_t)h->curW); mix((uint64_t)h->curH); mix((uint64_t)h->dbgEnabled); mix((uint64_t)h->dbgCap);
+    mix((uint64_t)h->tmapGen);                 // kernel parameters of a captured graph hold the maps by value
     return x;
 }
 
@@ -690,7 +683,7 @@ void orbx_destroy(orbx_extractor *h)
     h->dIn.release();
     h->dPyrRaw.release(); h->dBlurRaw.release(); h->dDesc.release(); h->dCnt.release(); h->dBest.release();
     h->dSlots.release(); h->dLvlCount.release(); h->dCounts.release(); h->dDbgCount.release();
-    h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dTmaps.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
+    h->dKps.release(); h->dSegs.release(); h->dRtab.release(); h->dTiles.release(); h->dStereo.release(); h->dStereoI.release(); h->hStereo.release(); h->dDbg.release();
     h->hDesc.release(); h->hLevel.release(); h->hKps.release(); h->hCounts.release();
     for (int i = 0; i < ORBX_LANES; i++) {
         orbx_extractor::Lane &ln = h->lane[i];
@@ -1190,17 +1183,17 @@ int orbx_profile_stages(orbx_extractor *h, int reps, float *ms, int n_ms)
     for (int i = 0; i < 5; i++) ms[i] = 0.f;
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(ev[0], st));
-        for (int l = 1; l < L.nlevels; l++) launch_resize(h->dTmaps.p[2].m, 0, h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
+        for (int l = 1; l < L.nlevels; l++) launch_resize(h->tmapsResize, 0, h->dPyr.p, L, l, (const int4 *)h->dRtab.p, batch, h->nSM, st);
         CK(cudaEventRecord(ev[1], st));
         CK(cudaMemsetAsync(h->dCnt.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(uint32_t), st));
         CK(cudaMemsetAsync(h->dBest.p, 0, (size_t)L.rowsPerFrame * batch * sizeof(unsigned long long), st));
-        CK(launch_fast(h->dTmaps.p[1].m, 0, L, h->dSegs.p, 0, L.totalSegs, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, h->fastWinRows, h->fastListCap, batch, st));
+        CK(launch_fast(h->tmapsFast, 0, L, h->dSegs.p, 0, L.totalSegs, h->dCnt.p, h->dBest.p, nullptr, nullptr, 0, h->fastWinRows, h->fastListCap, batch, st));
         CK(cudaEventRecord(ev[2], st));
         CK(launch_octree(L, h->dCnt.p, h->dBest.p, h->dSlots.p, h->dLvlCount.p, h->maxRows, h->maxNodes, batch, st));
         CK(cudaEventRecord(ev[3], st));
-        launch_blur(h->dTmaps.p->m, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, 0, batch, st);
+        launch_blur(h->tmaps, h->dBlur.p, L, h->dTiles.p, (int)h->tiles.size(), h->taps, 0, batch, st);
         CK(cudaEventRecord(ev[4], st));
-        launch_describe(h->dTmaps.p[3].m, h->dTmaps.p[4].m, 0, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
+        launch_describe(h->tmapsDescA, h->tmapsDescB, 0, L, h->dSlots.p, h->dLvlCount.p, h->umax, h->dKps.p, h->dDesc.p, h->dCounts.p, batch, st);
         CK(cudaEventRecord(ev[5], st));
         CK(cudaStreamSynchronize(st));
         for (int i = 0; i < 5; i++) { float t = 0; CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1])); ms[i] += t / reps; }

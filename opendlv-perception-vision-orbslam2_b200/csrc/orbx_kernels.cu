@@ -123,16 +123,11 @@ __device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMa
                  ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
 }
 
-// The tensor maps live in global memory and are REWRITTEN by the host whenever the frame size changes (orbx_api.cu:
-// buildTensorMaps).  The TMA unit reads them through its own proxy and may still hold the previous contents of the same 128
-// bytes; the thread that issues the loads acquires the descriptor first (system scope: the writer was a host cudaMemcpy).
-// Without it a handle that alternates between two frame sizes occasionally fetched boxes with the other size's strides
-// (scripts/probe/soak_handle.py, seed 4031: a replayed CUDA graph, a few pyramid levels of a few frames).
-__device__ __forceinline__ void tmap_acquire(const CUtensorMap *map)
-{
-    asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(map) : "memory");
-}
-
+// Tensor maps reach the kernels as __grid_constant__ parameters, never through global memory: the TMA unit reads descriptors
+// through a proxy of its own, and a descriptor REWRITTEN in place (the host does that whenever the frame size changes) can be
+// served stale unless every consuming thread issues fence.proxy.tensormap::generic.acquire.sys first -- measured at +13 % on
+// the whole step.  (Found by scripts/probe/soak_handle.py, seed 4031: a handle alternating between two frame sizes described a
+// few pyramid levels of a few frames from boxes fetched with the other size's strides.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
     const uint32_t b = smem_u32(bar);
@@ -197,7 +192,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 __global__ void __launch_bounds__(160)
-k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ pyr, long long slab, int dstOff, int dstPitch,
+k_resize(const __grid_constant__ CUtensorMap srcMap, int f0, uint8_t *__restrict__ pyr, long long slab, int dstOff, int dstPitch,
          int dw, int dh, const int4 *__restrict__ xtab, const int4 *__restrict__ ytab, int tilesY, int batch, int nTiles, int tilesPerCta)
 {
     __shared__ __align__(128) uint8_t tileS[RS_STAGES][RS_BOXH * RS_BOXW];
@@ -221,7 +216,6 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
         if (lane == 0) {
             int lastXY = -1, xs = 0, ys = 0;
             pdl_wait();            // the source level is complete and visible (only the TMA loads read it)
-            tmap_acquire(srcMap);
             for (int t = t0; t < t1; t++) {
                 const int i = t - t0, b = i % RS_STAGES;
                 const int xy = t / batch, f = t - xy * batch;
@@ -232,7 +226,7 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
                     lastXY = xy;
                 }
                 if (i >= RS_STAGES) mbar_wait(&empty[b], ((i / RS_STAGES) - 1) & 1);
-                tma_load_tile_3d(tileS[b], srcMap, xs, ys, f0 + f, &full[b], RS_BOXH * RS_BOXW);
+                tma_load_tile_3d(tileS[b], &srcMap, xs, ys, f0 + f, &full[b], RS_BOXH * RS_BOXW);
             }
         }
         return;
@@ -297,14 +291,14 @@ k_resize(const CUtensorMap *__restrict__ srcMap, int f0, uint8_t *__restrict__ p
     }
 }
 
-void launch_resize(const CUtensorMap *srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, int nSM, cudaStream_t st)
+void launch_resize(const OrbxTensorMaps &srcMaps, int f0, uint8_t *pyr, const OrbxLayout &L, int level, const int4 *tabs, int batch, int nSM, cudaStream_t st)
 {
     const OrbxLevel &d = L.lv[level];
     const int tilesX = (d.w + RS_TW - 1) / RS_TW, tilesY = (d.h + RS_TH - 1) / RS_TH;
     const int nTiles = tilesX * tilesY * batch;
     const int tilesPerCta = std::max(1, (nTiles + nSM * 8 - 1) / (nSM * 8));
     const int grid = (nTiles + tilesPerCta - 1) / tilesPerCta;
-    launch_pdl(k_resize, dim3(grid), dim3(160), 0, st, srcMaps + (level - 1), f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
+    launch_pdl(k_resize, dim3(grid), dim3(160), 0, st, srcMaps.m[level - 1], f0, pyr, L.slab, d.off, d.pitch, d.w, d.h,
                tabs + d.xtabOff, tabs + d.ytabOff, tilesY, batch, nTiles, tilesPerCta);
 }
 
@@ -354,7 +348,7 @@ __device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint3
 #define BL_BOXH (4 * BL_ROWS + 6)   // rows: 3 + 4 bands + 3
 
 __global__ void __launch_bounds__(128)
-k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
+k_blur(const __grid_constant__ OrbxTensorMaps tm, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
        const OrbxTile *__restrict__ tiles, BlurTaps taps, int f0)
 {
     __shared__ __align__(128) uint8_t tileS[BL_BOXH * BL_BOXW];
@@ -369,10 +363,8 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        tmap_acquire(maps + tile.level);
-        tma_load_tile_3d(tileS, maps + tile.level, (int)tile.x0 * 4 - 16, (int)tile.y0 - 3, f, &bar, BL_BOXH * BL_BOXW);
-    }
+    if (tid == 0)
+        tma_load_tile_3d(tileS, &tm.m[tile.level], (int)tile.x0 * 4 - 16, (int)tile.y0 - 3, f, &bar, BL_BOXH * BL_BOXW);
 
     const int x0 = (tile.x0 + threadIdx.x) * 4;
     const int y0 = tile.y0 + threadIdx.y * BL_ROWS;
@@ -466,7 +458,7 @@ k_blur(const CUtensorMap *__restrict__ maps, uint8_t *__restrict__ blur, const _
     }
 }
 
-void launch_blur(const CUtensorMap *maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
+void launch_blur(const OrbxTensorMaps &maps, uint8_t *blur, const OrbxLayout &L, const OrbxTile *tiles, int nTiles,
                  const int taps[7], int f0, int batch, cudaStream_t st)
 {
     BlurTaps t;
@@ -623,7 +615,7 @@ __device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *
 }
 
 __global__ void __launch_bounds__(FS_T, 10)
-k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant__ OrbxLayout L,
+k_fast_segs(const __grid_constant__ OrbxTensorMaps tm, int f0, const __grid_constant__ OrbxLayout L,
             const OrbxSeg *__restrict__ segs, uint32_t *__restrict__ cnt,
             unsigned long long *__restrict__ best, OrbxDbgCand *__restrict__ dbg,
             int *__restrict__ dbgCount, int dbgCap, int winRows, int listCap, int kcap)
@@ -657,10 +649,7 @@ k_fast_segs(const CUtensorMap *__restrict__ maps, int f0, const __grid_constant_
         ncand = 0; ncorner = 0; cellsDone = 0u;
     }
     __syncthreads();
-    if (tid == 0) {
-        tmap_acquire(maps + seg.level);
-        tma_load_tile_3d(win, maps + seg.level, bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
-    }
+    if (tid == 0) tma_load_tile_3d(win, &tm.m[seg.level], bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
     for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
     if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (unsigned)lv.cellMagic) >> 16);            // tid / wCell
     const int nCells = (int)(((unsigned)(wT - 1) * (unsigned)lv.cellMagic) >> 16) + 1;
@@ -840,7 +829,7 @@ size_t fast_smem_bytes(int winRows, int listCap)
     return (size_t)winRows * FW_P + (size_t)(winRows - 4) * FM_P + (size_t)listCap * 2 + (size_t)fast_corner_cap(winRows, listCap) * 2;
 }
 
-cudaError_t launch_fast(const CUtensorMap *maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
+cudaError_t launch_fast(const OrbxTensorMaps &maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
                         uint32_t *cnt, unsigned long long *best, OrbxDbgCand *dbg, int *dbgCount, int dbgCap,
                         int winRows, int listCap, int batch, cudaStream_t st)
 {
@@ -1270,7 +1259,7 @@ __device__ __forceinline__ int dp4a_u8_s8(uint32_t pix, uint32_t wgt, int acc)
 struct DescSlot { int valid, cx, cy, level, out, score; };
 
 __global__ void __launch_bounds__(DS_WARPS * 32)
-k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict__ mapsB, int f0, const __grid_constant__ OrbxLayout L,
+k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ OrbxTensorMaps tmB, int f0, const __grid_constant__ OrbxLayout L,
            const int2 *__restrict__ slots, const int *__restrict__ lvlCount, DescUmax um,
            orbx_keypoint_pod *__restrict__ kps, uint8_t *__restrict__ desc, int *__restrict__ counts)
 {
@@ -1327,7 +1316,6 @@ k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
-    unsigned acquired = 0u;           // lane 0: levels whose two tensor maps this warp has acquired
     // resolve slot j of this warp and start streaming its two patches into stage `buf`
     auto issue = [&](int j, int buf) -> DescSlot {
         DescSlot s; s.valid = 0; s.cx = s.cy = s.level = s.out = s.score = 0;
@@ -1344,15 +1332,14 @@ k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict_
         s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
         s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
         if (lane == 0) {
-            if (!((acquired >> level) & 1u)) { tmap_acquire(mapsB + level); tmap_acquire(mapsA + level); acquired |= 1u << level; }
             // box starts are 16-byte aligned: the patch column cx-18 (cx-15) sits at byte (cx-18) & 15 ((cx-15) & 15) of its row
             uint8_t *sB = patch[warp][buf], *sA = sB + DS_BUFB;
             const uint32_t bb = smem_u32(&bars[warp][buf]);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((uint32_t)DS_TX) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(sB)), "l"(mapsB + level), "r"((s.cx - 18) & ~15), "r"(s.cy - 18), "r"(f0 + frame), "r"(bb) : "memory");
+                         ::"r"(smem_u32(sB)), "l"(&tmB.m[level]), "r"((s.cx - 18) & ~15), "r"(s.cy - 18), "r"(f0 + frame), "r"(bb) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(sA)), "l"(mapsA + level), "r"((s.cx - 15) & ~15), "r"(s.cy - 15), "r"(f0 + frame), "r"(bb) : "memory");
+                         ::"r"(smem_u32(sA)), "l"(&tmA.m[level]), "r"((s.cx - 15) & ~15), "r"(s.cy - 15), "r"(f0 + frame), "r"(bb) : "memory");
         }
         return s;
     };
@@ -1428,7 +1415,7 @@ k_describe(const CUtensorMap *__restrict__ mapsA, const CUtensorMap *__restrict_
     }
 }
 
-void launch_describe(const CUtensorMap *mapsA, const CUtensorMap *mapsB, int f0, const OrbxLayout &L, const int2 *slots,
+void launch_describe(const OrbxTensorMaps &mapsA, const OrbxTensorMaps &mapsB, int f0, const OrbxLayout &L, const int2 *slots,
                      const int *lvlCount, const int umax[16], orbx_keypoint_pod *kps, uint8_t *desc, int *counts,
                      int batch, cudaStream_t st)
 {

@@ -1,1 +1,4 @@
-for v in "X=1" "X=2" "ORBX_LANES=1"; do echo "== $v"; env $v python scripts/probe/soak_handle_dbg.py 150 4031 2>&1 | grep "^call\|bad frames" | cut -c1-150 | tail -4; done
+timeout 1200 python -m pytest tests/test_gpu_extract.py tests/test_gpu_stereo.py -x -q 2>&1 | tail -3
+for sd in 4031 5031; do python scripts/probe/soak_handle.py 150 $sd 2>&1 | tail -1; done
+for c in kitti hd uhd; do python scripts/probe/dev_batch.py $c 20; done
+NH=4 ORBX_SPLIT=1 python scripts/probe/two_handles.py kitti 20
