@@ -643,18 +643,19 @@ k_fast_segs(const __grid_constant__ OrbxTensorMaps tm, int f0, const __grid_cons
     // in x and the word left of the first tested pixel's word is read too: box x = (x0 - 4) & ~15, and tested
     // column xs sits at shared byte B0 + xs of its row.
     const int bx = ((int)seg.x0 - 4) & ~15, B0 = (int)seg.x0 + 3 - bx;
+    // Only thread 0 touches the mbarrier -- it initialises it, issues the load and, after its share of the set-up work, waits for
+    // the bytes; the block barrier behind that hands the window to everybody else (one barrier instead of two).
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ncand = 0; ncorner = 0; cellsDone = 0u;
+        tma_load_tile_3d(win, &tm.m[seg.level], bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
     }
-    __syncthreads();
-    if (tid == 0) tma_load_tile_3d(win, &tm.m[seg.level], bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
     for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
     if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (unsigned)lv.cellMagic) >> 16);            // tid / wCell
     const int nCells = (int)(((unsigned)(wT - 1) * (unsigned)lv.cellMagic) >> 16) + 1;
     const unsigned allCells = (1u << nCells) - 1u;
-    mbar_wait(&bar, 0);
+    if (tid == 0) mbar_wait(&bar, 0);
     __syncthreads();
 
     uint32_t *cntF = cnt + (size_t)frame * L.rowsPerFrame + lv.rowBase;

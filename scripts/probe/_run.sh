@@ -1,2 +1,3 @@
-ORBX_SPLIT=1 ncu --set full --clock-control none --import-source on --launch-skip 26 --launch-count 13 -f -o gpurun_out/prof_all_r2 python scripts/probe/one_step.py > gpurun_out/prof_all_r2.log 2>&1; tail -2 gpurun_out/prof_all_r2.log
-python bench.py --quick --no-cpu-baseline --steps 2 --warmup 1 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r2.csv python bench.py --quick --no-cpu-baseline --steps 2 --warmup 1 > gpurun_out/launches_r2.log 2>&1; tail -c 300 gpurun_out/launches_r2.log
+timeout 900 python -m pytest tests/test_gpu_extract.py -x -q 2>&1 | tail -2
+for c in kitti hd uhd; do python scripts/probe/dev_batch.py $c 20; done
+NH=4 ORBX_SPLIT=1 python scripts/probe/two_handles.py kitti 20
