@@ -469,8 +469,8 @@ void launch_blur(const OrbxTensorMaps &maps, uint8_t *blur, const OrbxLayout &L,
 
 // ------------------------------------------------------------------------------------------
 // Gridded FAST-9/16 with 3x3 NMS per cell and the ini/min threshold fallback (A.3).
-// One CTA per (segment, frame); a segment is a run of horizontally adjacent cells of one cell
-// row (<= 224 tested columns, 7 cells of 30-31 px), so the candidate lists of several cells share
+// One CTA (128 threads) per (segment, frame); a segment is a run of horizontally adjacent cells of one cell
+// row (<= 112 tested columns: 2-4 cells of 28-60 px), so the candidate lists of several cells share
 // the CTA's lanes.  Output is not a keypoint list: DistributeOctTree in this fork only ever
 // splits along y inside fixed x-strips (A.5), so all it needs per (strip, row) is the number of
 // candidates and the best candidate (max response, first in the reference's emission order).
@@ -480,18 +480,20 @@ void launch_blur(const OrbxTensorMaps &maps, uint8_t *blur, const OrbxLayout &L,
 // `order` = (cell index << 12 | yIn << 6 | xIn) is the position in the reference's emission
 // order (cells row-major, raster inside a cell, orbextractor.cpp:930-968).
 //
-// Stages inside the CTA:
-//   0  the run's window (256 bytes x hCell+6 rows) is fetched by one TMA box load (cp.async.bulk.tensor)
-//   1  quick reject on 4 pixels per thread (packed bytes): a FAST-9 arc always contains ring
+// Inside the CTA:
+//   0  the run's window (144 bytes x hCell+6 rows) is fetched by one TMA box load (cp.async.bulk.tensor)
+//   then twice, in the reference's order (orbextractor.cpp:940-957) -- every cell at the initial threshold, afterwards only the
+//   cells whose NMS result came out empty at the minimum threshold:
+//   1  quick reject on 4 pixels per item (packed bytes): a FAST-9 arc always contains ring
 //      pixel k or k+8, so |I(p) - I(ring_k)| > t must hold for k in {0,8} and for k in {4,12};
-//      survivors (~10 % of pixels) are compacted into a list
+//      survivors (5-14 % of the pixels at threshold 20) are appended to a list warp by warp
 //   2  exact test and corner score in one pass: with d_k = I(p) - I(ring_k),
 //        A = max( max_k min(d_k..d_k+8), -min_k max(d_k..d_k+8) )
 //      is the largest threshold margin of the pixel: it is a corner at threshold t iff A > t, and its
 //      cv::FAST response is A - 1.  A thread evaluates two survivors at once, one in each 16-bit half of its
 //      registers, with three-input packed min/max (VIMNMX3.S16x2): 2 x (16 + 16) of them cover the 16 windows.
 //   3  3x3 NMS on the run's score map (neighbours in another cell count as 0, as each cell is an
-//      isolated cv::FAST call), per-cell threshold fallback, emission
+//      isolated cv::FAST call); a maximum goes straight into the row summaries
 // ------------------------------------------------------------------------------------------
 #define FS_T ORBX_FAST_THREADS  // threads per CTA
 #define FW_P ORBX_FAST_PITCH  // shared window pitch in bytes = TMA box width (36 words: vertical neighbours are 4 banks apart)
@@ -547,7 +549,7 @@ __device__ __forceinline__ void fast_margin2(const uint8_t *cA, const uint8_t *c
 // byte, K = 127 - th: set iff d > th.  (A byte whose sum overflows carries one into its upper neighbour, which can only turn
 // that neighbour's "d == th" into a pass -- the filter stays a superset; the overflowing byte itself has bit 7 of d set.)
 // The survivor flags of up to 8 rows are collected in a register (4 bits per item) and written out warp by warp (order inside
-// a warp: thread, row, pixel -- consecutive entries are vertical neighbours, FW_P / 4 = 68 words = 4 banks apart).  *ncand
+// a warp: thread, row, pixel -- consecutive entries are vertical neighbours, FW_P / 4 = 36 words = 4 banks apart).  *ncand
 // accumulates the number of survivors; the caller synchronises before reading the list.  Warp-synchronous: call with full warps.
 __device__ __forceinline__ void fast_quick_reject(const uint8_t *win, uint16_t *cand, int *ncand, const uint8_t *qlist, const bool dense,
                                                  const int nQx, const unsigned mQx, const int hB, const int tid, const int lane,
