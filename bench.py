@@ -245,6 +245,22 @@ def synth_frames(name, rank=0):
     return [np.roll(base[f % len(base)], 5 * (f // len(base)), axis=1) if f >= len(base) else base[f] for f in range(cfg["batch"])]
 
 
+def headline_pool():
+    cfg = CONFIGS["kitti"]
+    return max(cfg["pool"], -(-140_000_000 // (BATCH * W * H)))
+
+
+def headline_config(world, pool, numa):
+    """`config` of the headline line; the reference arm prints the same dictionary (it runs the GPU arm's workload)."""
+    return {"workload": CONFIGS["kitti"]["label"] + ", one such batch per GPU per step",
+            "frames_per_gpu_per_step": BATCH, "global_frames_per_step": BATCH * world,
+            "in_flight": f"{PIPE_DEPTH} batches per GPU (orbx_pipe_submit / orbx_pipe_join: consecutive batches on separate extractor "
+                         "handles, every batch complete and joined into the timed stream before the closing event)",
+            "l2": f"inputs rotate over {pool} resident batches ({pool * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
+            "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+            "host_binding": None if numa is None else f"each rank bound to the {numa} host cores NVML lists for its GPU"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
@@ -272,7 +288,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": CONFIGS["kitti"]["label"], "frames_per_step": BATCH},
+            "config": headline_config(args.gpus, headline_pool(), None),      # the GPU arm's own config, key for key
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu.kind, "sample": sample,
                              "reference_impl": REFERENCE_IMPL,
                              "cv2_primitives_ms_per_frame_1thread": cpu.cv2_primitives_ms(frames[0], NLEVELS)},
@@ -731,13 +747,7 @@ def main():
             "metric": "ORB frames/s (1241x376, 2000 kp)", "value": fps_dev, "unit": "frames/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": ms_pipe / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": CONFIGS["kitti"]["label"] + ", one such batch per GPU per step",
-                       "frames_per_gpu_per_step": BATCH, "global_frames_per_step": BATCH * world,
-                       "in_flight": f"{PIPE_DEPTH} batches per GPU (orbx_pipe_submit / orbx_pipe_join: consecutive batches on separate extractor "
-                                    "handles, every batch complete and joined into the timed stream before the closing event)",
-                       "l2": f"inputs rotate over {head['pool']} resident batches ({head['pool'] * BATCH * W * H / 1e6:.0f} MB) + 2x{BATCH * 2.2:.0f} MB of pyramid/blur slabs rewritten every step: working set > 126 MB L2",
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "host_binding": None if numa is None else f"each rank bound to the {numa} host cores NVML lists for its GPU"},
+            "config": headline_config(world, head["pool"], numa),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": BATCH * W * H,
                     "d2h_bytes_per_step": BATCH * cap * 60 + BATCH * 4, "keypoints_last_step": head["n_kp"],
                     "api": "orbx_extract_batch_async + orbx_wait, two calls in flight, pinned host buffers",
