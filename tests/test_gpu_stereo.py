@@ -144,3 +144,25 @@ def test_stereo_with_more_than_8192_keypoints_per_frame(oracle):
     assert len(u) == n_left and nm == on and on > 100
     assert np.array_equal(u.view(np.uint32), ou.view(np.uint32)) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
     ex.close()
+
+
+def test_stereo_on_a_pipe_slot(oracle):
+    """Stereo batches submitted through an orbx_pipe: the extractor that holds a ticket's batch serves ComputeStereoMatches of
+    exactly that batch while the next submission is already running on another slot."""
+    import torch
+    import orbx
+    w, h, nf, nl, mbf, mb = 752, 480, 1200, 6, 386.1448, 0.5372
+    pairs = [synth.stereo_pair(w, h, 2100 + k) for k in range(3)]
+    pipe = orbx.Pipe(depth=2, nfeatures=nf, nlevels=nl, max_width=w, max_height=h, max_batch=2)
+    dev = [torch.from_numpy(np.stack([l, r])).cuda() for (l, r) in pairs]
+    torch.cuda.synchronize()
+    tk = [pipe.submit(dev[0].data_ptr(), h * w, w, 2, w, h)]
+    for k in range(3):
+        if k + 1 < 3:
+            tk.append(pipe.submit(dev[k + 1].data_ptr(), h * w, w, 2, w, h))     # the next pair is in flight during the match
+        pipe.join(tk[k])
+        u, d, n_left, n_match = orbx.stereo_match_batch(pipe.extractor(tk[k]), 1, 0, 1, 2, mbf, mb)
+        (ou, od, on), n_l = _oracle_pair(oracle, pairs[k][0], pairs[k][1], nf, nl, mbf, mb)
+        assert int(n_left[0]) == n_l and int(n_match[0]) == on and on > 20
+        assert np.array_equal(u[0][:n_l].view(np.uint32), ou.view(np.uint32)) and np.array_equal(d[0][:n_l].view(np.uint32), od.view(np.uint32))
+    pipe.close()
