@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_stereo.py -x -q 2>&1 | tail -5
+python scripts/probe/oct_cycles.py
