@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -4
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
-tail -5 gpurun_out/r2_bench_n8.err
+python scripts/probe/h2d_feed.py 2>&1 | tail -4
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
