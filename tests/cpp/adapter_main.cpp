@@ -59,6 +59,18 @@ int main(int argc, char **argv)
         std::vector<float> sf = ex.getScaleFactors(), is2 = ex.getInverseScaleSigmaSquares();
         fwrite(sf.data(), 4, levels, o);
         fwrite(is2.data(), 4, levels, o);
+        // the pyramid member is a view with the reference vector's surface: size, iteration, conversion to std::vector<cv::Mat>&
+        {
+            long rowsIter = 0, rowsVec = 0;
+            for (cv::Mat &m : ex.m_vImagePyramid) rowsIter += m.rows;
+            std::vector<cv::Mat> &asVector = ex.m_vImagePyramid;
+            for (size_t l = 0; l < asVector.size(); l++) rowsVec += asVector[l].rows;
+            if ((int)ex.m_vImagePyramid.size() != levels || rowsIter != rowsVec || rowsIter <= h || ex.m_vImagePyramid.at(0).rows != h ||
+                ex.m_vImagePyramid.front().cols != w || ex.m_vImagePyramid.back().rows >= h) {
+                fprintf(stderr, "pyramid view: %ld / %ld rows over %zu levels\n", rowsIter, rowsVec, ex.m_vImagePyramid.size());
+                return 3;
+            }
+        }
         for (int l = 0; l < levels; l++) {
             const cv::Mat &m = ex.m_vImagePyramid[l];
             fwrite(&m.cols, 4, 1, o); fwrite(&m.rows, 4, 1, o);

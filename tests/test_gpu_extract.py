@@ -496,7 +496,9 @@ def test_pipe_keeps_several_device_batches_in_flight(oracle, depth):
     pipe = orbx.Pipe(depth=depth, nfeatures=nf, nlevels=nl, max_width=w, max_height=h, max_batch=b)
     oex = oracle.Extractor(nfeatures=nf, nlevels=nl)
     st = torch.cuda.Stream()
-    batches = [np.stack(synth.frames(300 + k, w, h, b)) for k in range(5)]
+    # the third and fifth submissions have another frame size and fewer frames: every slot follows its own geometry
+    shapes = [(w, h, b), (w, h, b), (512, 300, 3), (w, h, b), (512, 300, 2)]
+    batches = [np.stack(synth.frames(300 + k, sw, sh, sb)) for k, (sw, sh, sb) in enumerate(shapes)]
     dev = [torch.from_numpy(x).cuda() for x in batches]
     torch.cuda.synchronize()
     tickets, checked = [], 0
@@ -504,13 +506,15 @@ def test_pipe_keeps_several_device_batches_in_flight(oracle, depth):
     def check(k):
         ex = pipe.extractor(tickets[k])
         pipe.join(tickets[k], st.cuda_stream)
-        kps, desc, counts = ex.fetch_results(b, st.cuda_stream)
-        for f in (0, b - 1):
-            _compare_frame(oracle, ex, oex, batches[k][f], f, kps[f], desc[f], int(counts[f]), stages=(f == 0 and k == 0))
+        sb = shapes[k][2]
+        kps, desc, counts = ex.fetch_results(sb, st.cuda_stream)
+        for f in (0, sb - 1):
+            _compare_frame(oracle, ex, oex, batches[k][f], f, kps[f], desc[f], int(counts[f]), stages=(f == 0 and k in (0, 2)))
         return 1
 
     for k in range(len(dev)):
-        tickets.append(pipe.submit(dev[k].data_ptr(), h * w, w, b, w, h, st.cuda_stream))
+        sw, sh, sb = shapes[k]
+        tickets.append(pipe.submit(dev[k].data_ptr(), sh * sw, sw, sb, sw, sh, st.cuda_stream))
         if k >= depth - 1:
             checked += check(k - (depth - 1))          # the oldest submission still held, while the newer ones run
     for k in range(len(dev) - (depth - 1), len(dev)):
