@@ -26,6 +26,7 @@
 
 #define KNN_QB 128          // queries per CTA (one per thread)
 #define KNN_TILE 256        // train descriptors per shared-memory tile (8 KB)
+#define KNN_MIN_CHUNK 128   // shortest run of train descriptors worth a CTA of its own
 #define KNN_IDX_BITS 22
 #define KNN_IDX_MASK 0x3fffffu
 #define KNN_INIT_KEY ((256u << KNN_IDX_BITS) | KNN_IDX_MASK)
@@ -48,18 +49,12 @@ __device__ __forceinline__ int hamming256(const uint4 &qa, const uint4 &qb, cons
     return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
 }
 
-__global__ void __launch_bounds__(KNN_QB)
-k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
-               uint2 *__restrict__ part)
+// The two smallest keys (distance << 22 | train index) of one query over the train descriptors [t0, t1): the CTA's threads share
+// the train tile in shared memory (every thread reads the same descriptor: a broadcast).  (Fetching the next tile into registers
+// while the current one is scanned was measured and is no faster: four resident CTAs per SM cover each other's tile loads.)
+__device__ __forceinline__ void knn_scan_chunk(const uint4 *__restrict__ t, int t0, int t1, const uint4 &qa, const uint4 &qb,
+                                               uint4 *tile, int tid, unsigned &k1, unsigned &k2)
 {
-    __shared__ uint4 tile[KNN_TILE * 2];
-    const int tid = threadIdx.x;
-    const int qi = blockIdx.x * KNN_QB + tid;
-    const int t0 = blockIdx.y * chunk;
-    const int t1 = min(t0 + chunk, nt);
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    if (qi < nq) { qa = __ldg(&q[2 * qi]); qb = __ldg(&q[2 * qi + 1]); }
-    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
     for (int base = t0; base < t1; base += KNN_TILE) {
         const int cnt = min(KNN_TILE, t1 - base);
         __syncthreads();
@@ -74,43 +69,75 @@ k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
             k1 = min(k1, key);
         }
     }
+}
+
+__global__ void __launch_bounds__(KNN_QB, 4)
+k_knn2_partial(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk,
+               uint2 *__restrict__ part)
+{
+    __shared__ uint4 tile[KNN_TILE * 2];
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.x * KNN_QB + tid;
+    const int t0 = blockIdx.y * chunk;
+    const int t1 = min(t0 + chunk, nt);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qi < nq) { qa = __ldg(&q[2 * qi]); qb = __ldg(&q[2 * qi + 1]); }
+    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+    knn_scan_chunk(t, t0, t1, qa, qb, tile, tid, k1, k2);
     if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = make_uint2(k1, k2);
 }
 
-// Fold the per-chunk partial pairs of one query (part[c * stride], c < nchunks) into the two smallest keys.  Sixteen loads are in
+// Fold the per-chunk partial pairs of one query (part[c * stride], c < nchunks) into the two smallest keys.  KNN_FOLD loads are in
 // flight per thread: with several hundred chunks (few queries, many chunks to fill the GPU) a load-by-load loop is a chain of
-// L2 round trips -- 296 chunks x ~300 ns were most of the 30 us the sharded kernel spent behind its last chunk.
+// L2 round trips -- 296 chunks x ~300 ns were most of the 30 us the sharded kernel spent behind its last chunk.  The last, partial batch
+// loads from clamped positions instead of falling back to one load at a time.
+#define KNN_FOLD 32
+__device__ __forceinline__ void knn_fold_pair(unsigned &k1, unsigned &k2, unsigned x, unsigned y)
+{
+    // fold a sorted pair: the new pair is the two smallest of {k1, k2, x, y}
+    k2 = min(k2, max(k1, x));
+    k1 = min(k1, x);
+    k2 = min(k2, max(k1, y));
+    k1 = min(k1, y);
+}
+template <int B>
 __device__ __forceinline__ void knn_fold(const uint2 *part, size_t stride, int nchunks, unsigned &k1, unsigned &k2)
 {
     int c = 0;
-    for (; c + 16 <= nchunks; c += 16) {
-        uint2 p[16];
+    for (; c + B <= nchunks; c += B) {
+        uint2 p[B];
 #pragma unroll
-        for (int u = 0; u < 16; u++) p[u] = __ldcg(part + (size_t)(c + u) * stride);
+        for (int u = 0; u < B; u++) p[u] = __ldcg(part + (size_t)(c + u) * stride);
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            // fold two sorted pairs: the new pair is the two smallest of {k1,k2,p.x,p.y}
-            k2 = min(k2, max(k1, p[u].x));
-            k1 = min(k1, p[u].x);
-            k2 = min(k2, max(k1, p[u].y));
-            k1 = min(k1, p[u].y);
-        }
+        for (int u = 0; u < B; u++) knn_fold_pair(k1, k2, p[u].x, p[u].y);
     }
-    for (; c < nchunks; c++) {
-        const uint2 p = __ldcg(part + (size_t)c * stride);
-        k2 = min(k2, max(k1, p.x));
-        k1 = min(k1, p.x);
-        k2 = min(k2, max(k1, p.y));
-        k1 = min(k1, p.y);
+    if (c < nchunks) {
+        // last batch: unconditional loads from clamped positions (so that they all go out together), the surplus replaced afterwards
+        uint2 p[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) p[u] = __ldcg(part + (size_t)min(c + u, nchunks - 1) * stride);
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+            const bool in = c + u < nchunks;
+            knn_fold_pair(k1, k2, in ? p[u].x : KNN_INIT_KEY, in ? p[u].y : KNN_INIT_KEY);
+        }
     }
 }
 
-__global__ void k_knn2_merge(const uint2 *__restrict__ part, int nq, int nchunks, int4 *__restrict__ out)
+// lanesPerQuery (1, 2, 4 or 8) adjacent lanes share a query: lane `sub` folds the chunks c = sub (mod lanesPerQuery), a butterfly
+// joins the pairs.  With few queries and hundreds of chunks a thread per query leaves two CTAs walking a long chain of loads.
+__global__ void __launch_bounds__(128, 1)
+k_knn2_merge(const uint2 *__restrict__ part, int nq, int nchunks, int lanesPerQuery, int4 *__restrict__ out)
 {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= nq) return;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int L = lanesPerQuery, qi = g / L, sub = g & (L - 1);
     unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
-    knn_fold(part + qi, (size_t)nq, nchunks, k1, k2);
+    if (qi < nq) knn_fold<KNN_FOLD>(part + qi + (size_t)sub * nq, (size_t)nq * L, (nchunks - sub + L - 1) / L, k1, k2);
+    for (int o = L >> 1; o > 0; o >>= 1) {
+        const unsigned x = __shfl_xor_sync(0xffffffffu, k1, o), y = __shfl_xor_sync(0xffffffffu, k2, o);
+        knn_fold_pair(k1, k2, x, y);
+    }
+    if (qi >= nq || sub) return;
     int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
     int idx = (int)(k1 & KNN_IDX_MASK);
     if (d1 >= 256) { d1 = 256; idx = -1; }  // 'dist < bestDist1' with bestDist1 = 256 never fires
@@ -146,46 +173,18 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     return v;
 }
 
-__global__ void __launch_bounds__(KNN_QB)
-k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk, uint2 *part,
-               unsigned *counters /* [qBlocks + 1], zero between launches */, KnnPeers peers, int nRanks, int rank,
-               int qOffset, int nqTotal, unsigned epoch)
+#define KNN_GROUP 16             // chunks per fold group (first level of the in-kernel merge)
+
+// what the CTA that finished a query block last does: fold, store everywhere, and -- for the rank's last block -- publish and wait.
+// Kept out of line: inlined, its 32 loads in flight set the register allocation of the scan loop in front of it (3 % slower).
+__device__ __noinline__ void knn_sharded_tail(const uint2 *folded, int nFolded, int nq, unsigned *counters, KnnPeers peers, int nRanks,
+                                              int rank, int qOffset, int nqTotal, unsigned epoch, int *isLast)
 {
-    __shared__ uint4 tile[KNN_TILE * 2];
-    __shared__ int isLast;
     const int tid = threadIdx.x;
     const int qi = blockIdx.x * KNN_QB + tid;
-    const int t0 = blockIdx.y * chunk;
-    const int t1 = min(t0 + chunk, nt);
-    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-    if (qi < nq) { qa = __ldg(&q[2 * qi]); qb = __ldg(&q[2 * qi + 1]); }
-    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
-    for (int base = t0; base < t1; base += KNN_TILE) {
-        const int cnt = min(KNN_TILE, t1 - base);
-        __syncthreads();
-        for (int i = tid; i < cnt * 2; i += KNN_QB) tile[i] = __ldg(&t[2 * (size_t)base + i]);
-        __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < cnt; j++) {
-            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
-            const int d = hamming256(qa, qb, a, b);
-            const unsigned key = ((unsigned)d << KNN_IDX_BITS) | (unsigned)(base + j);
-            k2 = min(k2, max(k1, key));
-            k1 = min(k1, key);
-        }
-    }
-    if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = make_uint2(k1, k2);
-    // ---- the last CTA of this query block folds the partials (ticket pattern: partials are fenced before the ticket is taken)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) isLast = atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1;
-    __syncthreads();
-    if (!isLast) return;
-    __threadfence();
-    const int nchunks = (int)gridDim.y;
     if (qi < nq) {
-        k1 = KNN_INIT_KEY; k2 = KNN_INIT_KEY;
-        knn_fold(part + qi, (size_t)nq, nchunks, k1, k2);
+        unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+        knn_fold<KNN_FOLD>(folded + qi, (size_t)nq, nFolded, k1, k2);
         int d1 = (int)(k1 >> KNN_IDX_BITS), d2 = (int)(k2 >> KNN_IDX_BITS);
         int idx = (int)(k1 & KNN_IDX_MASK);
         if (d1 >= 256) { d1 = 256; idx = -1; }
@@ -198,10 +197,10 @@ k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
     __syncthreads();
     if (tid == 0) {
         counters[blockIdx.x] = 0;                                                // ready for the next launch
-        isLast = atomicAdd(&counters[gridDim.x], 1u) == gridDim.x - 1;
+        *isLast = atomicAdd(&counters[gridDim.x], 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (!isLast) return;
+    if (!*isLast) return;
     // ---- every query block of this rank is stored everywhere: publish, then wait for the other ranks
     if (tid == 0) counters[gridDim.x] = 0;
     if (tid < nRanks) st_release_sys((unsigned *)(peers.win[tid] + 64 * rank), epoch);
@@ -217,6 +216,57 @@ k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t,
                 break;
             }
         }
+    }
+}
+
+// counters: [0, qBlocks) groups finished per query block, [qBlocks] query blocks finished, then qBlocks x nGroups chunk counts per
+// group; all zero between launches.  gpart: nGroups x nq group partials.
+__global__ void __launch_bounds__(KNN_QB, 4)
+k_knn2_sharded(const uint4 *__restrict__ q, int nq, const uint4 *__restrict__ t, int nt, int chunk, uint2 *part, uint2 *gpart,
+               unsigned *counters, KnnPeers peers, int nRanks, int rank, int qOffset, int nqTotal, unsigned epoch)
+{
+    __shared__ uint4 tile[KNN_TILE * 2];
+    __shared__ int isLast;
+    const int tid = threadIdx.x;
+    const int qi = blockIdx.x * KNN_QB + tid;
+    const int t0 = blockIdx.y * chunk;
+    const int t1 = min(t0 + chunk, nt);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qi < nq) { qa = __ldg(&q[2 * qi]); qb = __ldg(&q[2 * qi + 1]); }
+    unsigned k1 = KNN_INIT_KEY, k2 = KNN_INIT_KEY;
+    knn_scan_chunk(t, t0, t1, qa, qb, tile, tid, k1, k2);
+    if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = make_uint2(k1, k2);
+    // ---- two-level fold of the per-chunk pairs, no separate launch and no serial walk over hundreds of chunks: the CTA that
+    // finishes a group of KNN_GROUP chunks last folds that group (ticket pattern: the pairs are fenced before the ticket is
+    // taken), the CTA that finishes a query block's last group folds the group results
+    const int nchunks = (int)gridDim.y, nGroups = (nchunks + KNN_GROUP - 1) / KNN_GROUP;
+    const int g = blockIdx.y / KNN_GROUP, gs = min(KNN_GROUP, nchunks - g * KNN_GROUP);
+    unsigned *gcount = counters + gridDim.x + 1 + blockIdx.x * nGroups + g;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) isLast = atomicAdd(gcount, 1u) == (unsigned)gs - 1u;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    if (nGroups > 1) {
+        if (qi < nq) {
+            k1 = KNN_INIT_KEY; k2 = KNN_INIT_KEY;
+            knn_fold<KNN_GROUP>(part + (size_t)g * KNN_GROUP * nq + qi, (size_t)nq, gs, k1, k2);
+            gpart[(size_t)g * nq + qi] = make_uint2(k1, k2);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            *gcount = 0;                                                         // ready for the next launch
+            isLast = atomicAdd(&counters[blockIdx.x], 1u) == (unsigned)nGroups - 1u;
+        }
+        __syncthreads();
+        if (!isLast) return;
+        __threadfence();
+        knn_sharded_tail(gpart, nGroups, nq, counters, peers, nRanks, rank, qOffset, nqTotal, epoch, &isLast);
+    } else {
+        if (tid == 0) *gcount = 0;
+        knn_sharded_tail(part, nchunks, nq, counters, peers, nRanks, rank, qOffset, nqTotal, epoch, &isLast);
     }
 }
 
@@ -637,11 +687,12 @@ int mfail(orbm_matcher *m, int code, const std::string &msg) { if (m) m->err = m
 void knnGrid(const orbm_matcher *m, int nq, int nt, int *qBlocks, int *chunks, int *chunk)
 {
     const int qb = (nq + KNN_QB - 1) / KNN_QB;
+    // four resident CTAs per SM; the chunk length is NOT rounded to whole tiles (the last tile of a chunk is simply shorter):
+    // rounding 338 up to 512 left 392 CTAs for 148 SMs at 250 queries -- SMs with three CTAs next to SMs with two
     int want = std::max(1, (m->smCount * 4 + qb - 1) / qb);
-    int maxChunks = std::max(1, (nt + KNN_TILE - 1) / KNN_TILE);
+    int maxChunks = std::max(1, (nt + KNN_MIN_CHUNK - 1) / KNN_MIN_CHUNK);
     int c = std::min(want, maxChunks);
-    int per = ((nt + c - 1) / c + KNN_TILE - 1) / KNN_TILE * KNN_TILE;
-    if (per < KNN_TILE) per = KNN_TILE;
+    int per = std::max((nt + c - 1) / c, KNN_MIN_CHUNK);
     c = std::max(1, (nt + per - 1) / per);
     *qBlocks = qb; *chunks = c; *chunk = per;
 }
@@ -663,7 +714,9 @@ int enqueueKnn(orbm_matcher *m, const uint8_t *dq, int nq, const uint8_t *dt, in
         dim3 grid(qb, chunks);
         k_knn2_partial<<<grid, KNN_QB, 0, st>>>((const uint4 *)dq, nq, (const uint4 *)dt, nt, chunk, m->dPart);
     }
-    k_knn2_merge<<<(nq + 127) / 128, 128, 0, st>>>(m->dPart, nq, chunks, dout);
+    int lanes = 1;
+    while (lanes < 8 && nq * lanes * 2 <= 8192 && chunks / (lanes * 2) >= 4) lanes *= 2;
+    k_knn2_merge<<<(nq * lanes + 127) / 128, 128, 0, st>>>(m->dPart, nq, chunks, lanes, dout);
     MCK(cudaGetLastError());
     return ORBX_OK;
 }
@@ -917,25 +970,28 @@ int orbm_window_create(orbm_matcher *m, int nq_total, int n_ranks, int rank, voi
         MCK(cudaFuncGetAttributes(&fa, (const void *)k_knn2_sharded));
         MCK(cudaFuncGetAttributes(&fa, (const void *)k_knn2_publish));
         const int qbMax = (nq_total + KNN_QB - 1) / KNN_QB;
-        const size_t need = (size_t)m->smCount * 4 * KNN_QB + (size_t)(qbMax + 1) * KNN_QB;     // >= chunks * nq_local of knnGrid
+        const size_t needPart = (size_t)m->smCount * 4 * KNN_QB + (size_t)(qbMax + 1) * KNN_QB;     // >= chunks * nq_local of knnGrid
+        const size_t need = needPart + needPart / KNN_GROUP + (size_t)(qbMax + 1) * KNN_QB;            // + the group partials behind them
         if (need > m->partCap) {
             if (m->dPart) cudaFree(m->dPart);
             m->dPart = nullptr; m->partCap = 0;
             MCK(cudaMalloc((void **)&m->dPart, need * sizeof(uint2)));
             m->partCap = need;
         }
-        if (qbMax + 1 > m->countersCap) {
+        // per query block one counter and one per group of chunks (chunks <= smCount * 4 / qb + 1), one for the rank
+        const int nCounters = qbMax + 1 + (m->smCount * 4 + qbMax) / KNN_GROUP + 2 * qbMax + 16;
+        if (nCounters > m->countersCap) {
             if (m->dCounters) cudaFree(m->dCounters);
             m->dCounters = nullptr; m->countersCap = 0;
-            MCK(cudaMalloc((void **)&m->dCounters, (size_t)(qbMax + 1) * sizeof(unsigned)));
-            MCK(cudaMemset(m->dCounters, 0, (size_t)(qbMax + 1) * sizeof(unsigned)));
-            m->countersCap = qbMax + 1;
+            MCK(cudaMalloc((void **)&m->dCounters, (size_t)nCounters * sizeof(unsigned)));
+            MCK(cudaMemset(m->dCounters, 0, (size_t)nCounters * sizeof(unsigned)));
+            m->countersCap = nCounters;
         }
         // one empty launch of each (no ranks, no queries) so that nothing is left to load at the first real call
         KnnPeers none;
         for (int r = 0; r < KNN_MAX_RANKS; r++) none.win[r] = nullptr;
         k_knn2_publish<<<1, 32, 0, m->stream>>>(none, 0, 0, 0u);
-        k_knn2_sharded<<<dim3(1, 1), KNN_QB, 0, m->stream>>>(nullptr, 0, nullptr, 0, KNN_TILE, m->dPart, m->dCounters, none, 0, 0, 0, nq_total, 0u);
+        k_knn2_sharded<<<dim3(1, 1), KNN_QB, 0, m->stream>>>(nullptr, 0, nullptr, 0, KNN_TILE, m->dPart, m->dPart, m->dCounters, none, 0, 0, 0, nq_total, 0u);
         MCK(cudaGetLastError());
         MCK(cudaStreamSynchronize(m->stream));
     }
@@ -1001,11 +1057,14 @@ int orbm_knn2_sharded(orbm_matcher *m, const uint8_t *d_q, int nq_local, int q_o
     }
     int qb, chunks, chunk;
     knnGrid(m, nq_local, nt, &qb, &chunks, &chunk);
-    if ((size_t)chunks * nq_local > m->partCap || qb + 1 > m->countersCap) return mfail(m, ORBX_ERR_ARG, "scratch of the window is too small for this call");
+    const int nGroups = (chunks + KNN_GROUP - 1) / KNN_GROUP;
+    if ((size_t)(chunks + nGroups) * nq_local > m->partCap || qb + 1 + qb * nGroups > m->countersCap)
+        return mfail(m, ORBX_ERR_ARG, "scratch of the window is too small for this call");
     KnnPeers peers;
     for (int r = 0; r < KNN_MAX_RANKS; r++) peers.win[r] = r < m->winRanks ? m->peerWin[r] : nullptr;
     m->epoch++;
-    k_knn2_sharded<<<dim3(qb, chunks), KNN_QB, 0, st>>>((const uint4 *)d_q, nq_local, (const uint4 *)d_t, nt, chunk, m->dPart, m->dCounters,
+    k_knn2_sharded<<<dim3(qb, chunks), KNN_QB, 0, st>>>((const uint4 *)d_q, nq_local, (const uint4 *)d_t, nt, chunk, m->dPart,
+                                                        m->dPart + (size_t)chunks * nq_local, m->dCounters,
                                                         peers, m->winRanks, m->winRank, q_offset, m->winNq, m->epoch);
     MCK(cudaGetLastError());
     return ORBX_OK;

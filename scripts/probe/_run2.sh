@@ -1,3 +1,5 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
-tail -2 gpurun_out/r2_bench_n2.err
-timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_match.py tests/test_gpu_multi.py -x -q 2>&1 | tail -3
+for rep in 1 2; do
+timeout 200 python scripts/probe/sharded_one.py 2>&1 | tail -3; timeout 100 python scripts/probe/match_rate.py 2>&1 | tail -1
+done
+timeout 100 python scripts/probe/soak_match.py 100 7712 2>&1 | tail -1
