@@ -1,4 +1,2 @@
-python scripts/probe/h2d_feed.py 2>&1 | tail -4
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 scripts/probe/h2d_feed.py 2>&1 | grep "rank(s)"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 > gpurun_out/r2_bench_n8b.json 2> gpurun_out/r2_bench_n8b.err
+tail -c 400 gpurun_out/r2_bench_n8b.json; tail -3 gpurun_out/r2_bench_n8b.err
