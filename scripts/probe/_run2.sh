@@ -1,5 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_match.py tests/test_gpu_multi.py -x -q 2>&1 | tail -3
 for rep in 1 2; do
-timeout 200 python scripts/probe/sharded_one.py 2>&1 | tail -3; timeout 100 python scripts/probe/match_rate.py 2>&1 | tail -1
+echo "--- baseline (10)"; timeout 200 python scripts/probe/stage_times64.py 2>&1 | tail -2
+echo "--- 9"; ORBX_LIB=$PWD/scripts/probe/_libs/liborbx_f9.so timeout 200 python scripts/probe/stage_times64.py 2>&1 | tail -2
+echo "--- 8"; ORBX_LIB=$PWD/scripts/probe/_libs/liborbx_f8.so timeout 200 python scripts/probe/stage_times64.py 2>&1 | tail -2
 done
-timeout 100 python scripts/probe/soak_match.py 100 7712 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_extract.py -x -q 2>&1 | tail -2
+cd scripts/probe; timeout 300 python soak.py 100 7720 2>&1 | tail -1
