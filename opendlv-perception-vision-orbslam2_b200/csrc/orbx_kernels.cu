@@ -123,6 +123,13 @@ __device__ __forceinline__ void tma_load_tile_3d(void *smemDst, const CUtensorMa
                  ::"r"(d), "l"(map), "r"(x), "r"(y), "r"(z), "r"(b) : "memory");
 }
 
+// a further box on a barrier whose expected byte count already includes it
+__device__ __forceinline__ void tma_copy_tile_3d(void *smemDst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smemDst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
 // Tensor maps reach the kernels as __grid_constant__ parameters, never through global memory: the TMA unit reads descriptors
 // through a proxy of its own, and a descriptor REWRITTEN in place (the host does that whenever the frame size changes) can be
 // served stale unless every consuming thread issues fence.proxy.tensormap::generic.acquire.sys first -- measured at +13 % on
@@ -499,6 +506,7 @@ void launch_blur(const OrbxTensorMaps &maps, uint8_t *blur, const OrbxLayout &L,
 #define FW_P ORBX_FAST_PITCH  // shared window pitch in bytes = TMA box width (36 words: vertical neighbours are 4 banks apart)
 #define FM_P ORBX_FAST_PITCH  // shared score-map pitch (the index arithmetic relies on FW_P == FM_P: list entries are yIn * FW_P + xs)
 static_assert(FW_P == 144, "fast_row_of divides by 144");
+__host__ __device__ __forceinline__ int fast_window_bytes(int winRows) { return (winRows * FW_P + 127) & ~127; }   // the score map behind it is a TMA destination too
 __device__ __forceinline__ int fast_row_of(int e) { return (int)(((unsigned)e * 3641u) >> 19); }   // e / 144 for e < 9000 (60 rows)
 
 __device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, x, 0x1032); }
@@ -625,7 +633,7 @@ k_fast_segs(const __grid_constant__ OrbxTensorMaps tm, int f0, const __grid_cons
 {
     extern __shared__ __align__(128) uint8_t fsm[];
     uint8_t *win = fsm;                                              // winRows x FW_P (TMA destination)
-    uint8_t *smap = win + winRows * FW_P;                            // (winRows - 4) x FM_P: scores with a zero border
+    uint8_t *smap = win + fast_window_bytes(winRows);                // (winRows - 4) x FM_P: scores with a zero border (128-byte aligned: TMA writes it)
     uint16_t *cand = (uint16_t *)(smap + (winRows - 4) * FM_P);      // listCap: yIn * FW_P + xs
     uint16_t *corner = cand + listCap;                               // kcap (<= listCap): on overflow stage 3a scans the score map instead
     __shared__ __align__(8) uint64_t bar;
@@ -652,9 +660,12 @@ k_fast_segs(const __grid_constant__ OrbxTensorMaps tm, int f0, const __grid_cons
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ncand = 0; ncorner = 0; cellsDone = 0u;
-        tma_load_tile_3d(win, &tm.m[seg.level], bx >> 2, (int)seg.y0, f0 + frame, &bar, FW_P * lv.winH);   // x in 32-bit elements
+        // the score map is zeroed by the TMA unit as well: a second box of the same shape from far outside the level is all
+        // out-of-bounds fill (1.5 % faster than 128 threads storing zeros).  It is winH = hT + 6 rows, four more than the
+        // score map: the surplus lands in the front of the survivor list, which nobody writes before the barrier below.
+        tma_load_tile_3d(win, &tm.m[seg.level], bx >> 2, (int)seg.y0, f0 + frame, &bar, 2 * FW_P * lv.winH);   // x in 32-bit elements
+        tma_copy_tile_3d(smap, &tm.m[seg.level], bx >> 2, -4096, f0 + frame, &bar);
     }
-    for (int i = tid; i < (hT + 2) * (FM_P / 16); i += FS_T) ((uint4 *)smap)[i] = make_uint4(0, 0, 0, 0);
     if (tid < wT) cellOf[tid] = (uint8_t)(((unsigned)tid * (unsigned)lv.cellMagic) >> 16);            // tid / wCell
     const int nCells = (int)(((unsigned)(wT - 1) * (unsigned)lv.cellMagic) >> 16) + 1;
     const unsigned allCells = (1u << nCells) - 1u;
@@ -819,7 +830,7 @@ int fast_corner_cap(int winRows, int listCap)
 {
     static const int forced = getenv("ORBX_FAST_KCAP") ? atoi(getenv("ORBX_FAST_KCAP")) : 0;
     if (forced > 0) return std::min(listCap, (forced + 7) & ~7);
-    const long fixed = (long)winRows * FW_P + (long)(winRows - 4) * FM_P + 2L * listCap;
+    const long fixed = (long)fast_window_bytes(winRows) + (long)(winRows - 4) * FM_P + 2L * listCap;
     for (int ctas = 10; ctas >= 6; ctas--) {
         const long budget = (233472 - ctas * 1024) / ctas - 512;   // per CTA: 228 KB per SM, 1 KB reserved per CTA, static shared memory
         const long room = (budget - fixed) / 2;
@@ -830,7 +841,9 @@ int fast_corner_cap(int winRows, int listCap)
 
 size_t fast_smem_bytes(int winRows, int listCap)
 {
-    return (size_t)winRows * FW_P + (size_t)(winRows - 4) * FM_P + (size_t)listCap * 2 + (size_t)fast_corner_cap(winRows, listCap) * 2;
+    const size_t lists = (size_t)listCap * 2 + (size_t)fast_corner_cap(winRows, listCap) * 2;
+    // the zero box written over the score map is a full window (four rows more than the map): tiny levels keep room for it
+    return (size_t)fast_window_bytes(winRows) + std::max((size_t)(winRows - 4) * FM_P + lists, (size_t)winRows * FW_P);
 }
 
 cudaError_t launch_fast(const OrbxTensorMaps &maps, int f0, const OrbxLayout &L, const OrbxSeg *segs, int segBegin, int segCount,
