@@ -1289,6 +1289,56 @@ k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ O
     __shared__ __align__(8) uint64_t bars[DS_WARPS][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.y;
+    // per-level counts of this frame -> exclusive prefix (lane l holds level l)
+    const int *lc = lvlCount + frame * L.nlevels;
+    const int myCnt = lane < L.nlevels ? lc[lane] : 0;
+    int incl = myCnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (blockIdx.x == 0 && tid == 0) counts[frame] = total;
+    const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
+    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[warp][lane])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // lane j < DS_PER_WARP fetches the warp's j-th slot record now: one global load per warp instead of one, with its latency,
+    // in front of every key point's TMA requests
+    int2 mySlot = make_int2(0, 0);
+    {
+        const int slot = (blockIdx.x * DS_PER_WARP + lane) * DS_WARPS + warp;
+        if (lane < DS_PER_WARP && slot < L.slotsPerFrame) mySlot = __ldg(&slots[(size_t)frame * L.slotsPerFrame + slot]);
+    }
+    // resolve slot j of this warp and start streaming its two patches into stage `buf`
+    auto issue = [&](int j, int buf) -> DescSlot {
+        DescSlot s; s.valid = 0; s.cx = s.cy = s.level = s.out = s.score = 0;
+        const int slot = (blockIdx.x * DS_PER_WARP + j) * DS_WARPS + warp;     // warp-uniform
+        if (j >= DS_PER_WARP || slot >= L.slotsPerFrame) return s;
+        const unsigned ge = __ballot_sync(0xffffffffu, slot >= myBase);        // level = last l with slotBase[l] <= slot
+        const int level = 31 - __clz((int)ge);
+        const OrbxLevel &lv = L.lv[level];
+        const int i = slot - lv.slotBase;
+        const int cntL = __shfl_sync(0xffffffffu, myCnt, level);
+        const int before = __shfl_sync(0xffffffffu, incl - myCnt, level);
+        if (i >= cntL) return s;
+        const int2 sl = make_int2(__shfl_sync(0xffffffffu, mySlot.x, j), __shfl_sync(0xffffffffu, mySlot.y, j));
+        s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
+        s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
+        if (lane == 0) {
+            // box starts are 16-byte aligned: the patch column cx-18 (cx-15) sits at byte (cx-18) & 15 ((cx-15) & 15) of its row
+            uint8_t *sB = patch[warp][buf], *sA = sB + DS_BUFB;
+            const uint32_t bb = smem_u32(&bars[warp][buf]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((uint32_t)DS_TX) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(sB)), "l"(&tmB.m[level]), "r"((s.cx - 18) & ~15), "r"(s.cy - 18), "r"(f0 + frame), "r"(bb) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(sA)), "l"(&tmA.m[level]), "r"((s.cx - 15) & ~15), "r"(s.cy - 15), "r"(f0 + frame), "r"(bb) : "memory");
+        }
+        return s;
+    };
+
+    // the first key point's patches are requested before the lane's constants are set up: their latency overlaps the set-up
+    DescSlot cur = issue(0, 0);
     // this lane's 16 pattern points (descriptor byte `lane`), kept in registers across its slots
     float px[16], py[16];
     {
@@ -1322,48 +1372,6 @@ k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ O
             wu[k] = a; w1[k] = b;
         }
     }
-    // per-level counts of this frame -> exclusive prefix (lane l holds level l)
-    const int *lc = lvlCount + frame * L.nlevels;
-    const int myCnt = lane < L.nlevels ? lc[lane] : 0;
-    int incl = myCnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (blockIdx.x == 0 && tid == 0) counts[frame] = total;
-    const int myBase = lane < L.nlevels ? L.lv[lane].slotBase : 0x7fffffff;
-    if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[warp][lane])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-
-    // resolve slot j of this warp and start streaming its two patches into stage `buf`
-    auto issue = [&](int j, int buf) -> DescSlot {
-        DescSlot s; s.valid = 0; s.cx = s.cy = s.level = s.out = s.score = 0;
-        const int slot = (blockIdx.x * DS_PER_WARP + j) * DS_WARPS + warp;     // warp-uniform
-        if (j >= DS_PER_WARP || slot >= L.slotsPerFrame) return s;
-        const unsigned ge = __ballot_sync(0xffffffffu, slot >= myBase);        // level = last l with slotBase[l] <= slot
-        const int level = 31 - __clz((int)ge);
-        const OrbxLevel &lv = L.lv[level];
-        const int i = slot - lv.slotBase;
-        const int cntL = __shfl_sync(0xffffffffu, myCnt, level);
-        const int before = __shfl_sync(0xffffffffu, incl - myCnt, level);
-        if (i >= cntL) return s;
-        const int2 sl = slots[(size_t)frame * L.slotsPerFrame + slot];
-        s.valid = 1; s.level = level; s.out = before + i; s.score = sl.y;
-        s.cx = (sl.x & 0xffff) + ORBX_MINB; s.cy = (sl.x >> 16) + ORBX_MINB;   // :984-985
-        if (lane == 0) {
-            // box starts are 16-byte aligned: the patch column cx-18 (cx-15) sits at byte (cx-18) & 15 ((cx-15) & 15) of its row
-            uint8_t *sB = patch[warp][buf], *sA = sB + DS_BUFB;
-            const uint32_t bb = smem_u32(&bars[warp][buf]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"((uint32_t)DS_TX) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(sB)), "l"(&tmB.m[level]), "r"((s.cx - 18) & ~15), "r"(s.cy - 18), "r"(f0 + frame), "r"(bb) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(sA)), "l"(&tmA.m[level]), "r"((s.cx - 15) & ~15), "r"(s.cy - 15), "r"(f0 + frame), "r"(bb) : "memory");
-        }
-        return s;
-    };
-
-    DescSlot cur = issue(0, 0);
     unsigned phase = 0;                                       // bit b = parity the next completion of stage b's barrier has
     for (int j = 0; j < DS_PER_WARP; j++) {
         const int buf = j & 1;
