@@ -419,8 +419,7 @@ k_distinctive(const uint4 *__restrict__ desc, const int *__restrict__ offsets, c
             bestKey = min(bestKey, (unsigned)lo << 16 | (unsigned)i);   // first row with the least median, :369-373
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bestKey = min(bestKey, __shfl_xor_sync(0xffffffffu, bestKey, o));
+    bestKey = __reduce_min_sync(0xffffffffu, bestKey);
     if (lane == 0) out[p] = make_int2((int)(bestKey & 0xffffu), (int)(bestKey >> 16));
 }
 

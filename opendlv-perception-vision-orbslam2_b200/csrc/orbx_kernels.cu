@@ -1397,12 +1397,9 @@ k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ O
                     rowsum = dp4a_u8_s8(B, w1[k], rowsum);
                 }
             }
-            int m01 = (lane - 15) * rowsum;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-            }
+            // warp sums in one instruction each (REDUX; integer addition, so the order of the terms is immaterial)
+            m10 = __reduce_add_sync(0xffffffffu, m10);
+            const int m01 = __reduce_add_sync(0xffffffffu, (lane - 15) * rowsum);
             const float angle = fast_atan2_deg((float)m01, (float)m10);
 
             // ---- rBRIEF: lane = descriptor byte, 16 rotated samples each, gathered from shared memory.
@@ -1563,8 +1560,7 @@ k_stereo_match(const __grid_constant__ OrbxLayout L, const uint8_t *__restrict__
         const unsigned key = (unsigned)d << 16 | (unsigned)iR;
         best = min(best, key);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    best = __reduce_min_sync(0xffffffffu, best);
     const int bestDist = (int)(best >> 16), bestIdxR = (int)(best & 0xffff);
     if (bestDist >= thOrbDist) return;
 
