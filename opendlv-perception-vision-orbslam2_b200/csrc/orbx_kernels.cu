@@ -314,7 +314,7 @@ void launch_resize(const OrbxTensorMaps &srcMaps, int f0, uint8_t *pyr, const Or
 //   out = min(255, (sum_y t[y] * (sum_x t[x] * I) + 32768) >> 16)
 // One thread owns 4 adjacent columns (one 32-bit word of every output row) and walks BL_ROWS
 // rows downwards.  Per input row it reads the 12 bytes x0-4 .. x0+7 as three aligned words,
-// forms the four horizontal sums with byte-permutes + dp4a (taps packed 4 per register), and
+// forms the four horizontal sums with ten dp4a against pre-shifted tap vectors (the data stays aligned), and
 // keeps the last 7 of them per column in registers for the vertical sum -- the intermediate
 // never touches shared or global memory.  A warp covers 128 columns; a CTA is 4 warps working
 // on 4 vertically adjacent strips of one tile; one launch covers every level (tile table).
@@ -377,8 +377,22 @@ k_blur(const __grid_constant__ OrbxTensorMaps tm, uint8_t *__restrict__ blur, co
     const int y0 = tile.y0 + threadIdx.y * BL_ROWS;
     const bool active = x0 < w && y0 < h;
     uint8_t *dst = blur + (size_t)f * L.slab + lv.off + x0;
-    const uint32_t Tlo = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8 | (uint32_t)taps.t[2] << 16 | (uint32_t)taps.t[3] << 24;
-    const uint32_t Thi = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8 | (uint32_t)taps.t[6] << 16;
+    // horizontal taps as byte vectors against the ALIGNED words {W0,W1,W2} (window bytes 0..11): column x0+c takes window
+    // bytes c+1 .. c+7, so byte b of word w carries tap 4w + b - (c+1) when that lies in 0..6 and zero otherwise -- the
+    // data is never shifted, ten dp4a per four pixels and no byte permutes
+    auto tapv = [&](int w, int c) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int k = 4 * w + b - (c + 1);
+            if (k >= 0 && k <= 6) v |= (uint32_t)taps.t[k] << (8 * b);
+        }
+        return v;
+    };
+    const uint32_t TA0 = tapv(0, 0), TB0 = tapv(1, 0);
+    const uint32_t TA1 = tapv(0, 1), TB1 = tapv(1, 1), TC1 = tapv(2, 1);
+    const uint32_t TA2 = tapv(0, 2), TB2 = tapv(1, 2), TC2 = tapv(2, 2);
+    const uint32_t TB3 = tapv(1, 3), TC3 = tapv(2, 3);
     const uint32_t T01 = (uint32_t)taps.t[0] | (uint32_t)taps.t[1] << 8, T23 = (uint32_t)taps.t[2] | (uint32_t)taps.t[3] << 8;
     const uint32_t T45 = (uint32_t)taps.t[4] | (uint32_t)taps.t[5] << 8, T6 = (uint32_t)taps.t[6];
     uint32_t sel1, selT, sel2;
@@ -412,10 +426,10 @@ k_blur(const __grid_constant__ OrbxTensorMaps tm, uint8_t *__restrict__ blur, co
         }
         // column x0+i needs bytes (i+1 .. i+7) of {W0,W1,W2}
         uint32_t hs[4];
-        hs[0] = __dp4a(__byte_perm(W1, W2, 0x4321), Thi, __dp4a(__byte_perm(W0, W1, 0x4321), Tlo, 0u));
-        hs[1] = __dp4a(__byte_perm(W1, W2, 0x5432), Thi, __dp4a(__byte_perm(W0, W1, 0x5432), Tlo, 0u));
-        hs[2] = __dp4a(__byte_perm(W1, W2, 0x6543), Thi, __dp4a(__byte_perm(W0, W1, 0x6543), Tlo, 0u));
-        hs[3] = __dp4a(W2, Thi, __dp4a(W1, Tlo, 0u));
+        hs[0] = __dp4a(W1, TB0, __dp4a(W0, TA0, 0u));
+        hs[1] = __dp4a(W2, TC1, __dp4a(W1, TB1, __dp4a(W0, TA1, 0u)));
+        hs[2] = __dp4a(W2, TC2, __dp4a(W1, TB2, __dp4a(W0, TA2, 0u)));
+        hs[3] = __dp4a(W2, TC3, __dp4a(W1, TB3, 0u));
         uint32_t acc[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) {
