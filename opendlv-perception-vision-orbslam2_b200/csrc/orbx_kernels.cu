@@ -1423,8 +1423,9 @@ k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ O
             glibc_sincosf(__fmul_rn(angle, factorPI), &sa, &ca);
             const float a = ca, b = sa;
             const float MAGIC = 12582912.0f;                       // 0x4B400000
-            const uint8_t *center = pB + 18 * DS_PB + shB + 18;
-            const unsigned BIAS = 0x4B400000u * (unsigned)(DS_PB + 1);   // both magic offsets, removed in one subtraction (mod 2^32)
+            // shared-window address of the patch centre with both magic offsets taken off once (mod 2^32): a sample's address is
+            // row_bits * DS_PB + col_bits + base32, two integer instructions
+            const uint32_t base32 = smem_u32(pB + 18 * DS_PB + shB + 18) - 0x4B400000u * (unsigned)(DS_PB + 1);
             int val = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -1434,7 +1435,9 @@ k_describe(const __grid_constant__ OrbxTensorMaps tmA, const __grid_constant__ O
                     const float x = px[2 * k + e], y = py[2 * k + e];
                     const int row = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x, b), __fmul_rn(y, a)), MAGIC));
                     const int col = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x, a), __fmul_rn(y, b)), MAGIC));
-                    t[e] = center[(int)((unsigned)row * (unsigned)DS_PB + (unsigned)col - BIAS)];
+                    unsigned v;
+                    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((unsigned)row * (unsigned)DS_PB + (unsigned)col + base32));
+                    t[e] = (int)v;
                 }
                 val |= (t[0] < t[1]) << k;
             }
