@@ -71,7 +71,7 @@ def test_multi_extractor_equals_single_gpu_calls(oracle):
     ref.close()
 
 
-@pytest.mark.parametrize("nq,nt", [(2000, 100000), (250, 30000), (5, 999), (2, 300), (129, 257)])
+@pytest.mark.parametrize("nq,nt", [(2000, 100000), (250, 30000), (5, 999), (2, 300), (129, 257), (5, 100000)])   # the last: 37 fold groups
 def test_sharded_knn2_in_one_process(oracle, nq, nt):
     """orbm_multi_knn2: every device slot matches its block of queries in one launch and stores its records into every
     slot's window (peer stores + flags, no collective call); the host reads the whole result from slot 0.  Equal to the
