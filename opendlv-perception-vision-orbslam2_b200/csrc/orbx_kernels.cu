@@ -354,6 +354,9 @@ __device__ __forceinline__ void blur_edge_selectors(int e, uint32_t &sel1, uint3
 #define BL_BOXW 160   // bytes: 16 left + 128 + 16 right: TMA needs the box start 16-byte aligned in the inner dimension
 #define BL_BOXH (4 * BL_ROWS + 6)   // rows: 3 + 4 bands + 3
 
+// SAT: the taps sum to more than 256, so the result can exceed 255 and is saturated (cv::saturate_cast); with a sum of at most 256
+// -- OpenCV 4's table -- the largest value is 32768 + 256 * 255 * 256 = 0xff8000: bits 16..23 are the result as they stand
+template <bool SAT>
 __global__ void __launch_bounds__(128)
 k_blur(const __grid_constant__ OrbxTensorMaps tm, uint8_t *__restrict__ blur, const __grid_constant__ OrbxLayout L,
        const OrbxTile *__restrict__ tiles, BlurTaps taps, int f0)
@@ -440,7 +443,7 @@ k_blur(const __grid_constant__ OrbxTensorMaps tm, uint8_t *__restrict__ blur, co
             a = __dp2a_lo(pp[c][(s + 2) % 7], T01, a);
             a = __dp2a_lo(pp[c][(s + 4) % 7], T23, a);
             a = __dp2a_lo(pp[c][(s + 6) % 7], T45, a);
-            acc[c] = min(a, 0x00ffffffu);                    // result byte = bits 16..23, saturated
+            acc[c] = SAT ? min(a, 0x00ffffffu) : a;          // result byte = bits 16..23, saturated where it can overflow
         }
         if (store) {
             const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
@@ -485,7 +488,10 @@ void launch_blur(const OrbxTensorMaps &maps, uint8_t *blur, const OrbxLayout &L,
     BlurTaps t;
     for (int k = 0; k < 7; k++) t.t[k] = taps[k];
     dim3 grid(nTiles, batch);
-    k_blur<<<grid, dim3(32, 4), 0, st>>>(maps, blur, L, tiles, t, f0);
+    int sum = 0;
+    for (int k = 0; k < 7; k++) sum += taps[k];
+    if (sum > 256) k_blur<true><<<grid, dim3(32, 4), 0, st>>>(maps, blur, L, tiles, t, f0);
+    else k_blur<false><<<grid, dim3(32, 4), 0, st>>>(maps, blur, L, tiles, t, f0);
 }
 
 // ------------------------------------------------------------------------------------------
