@@ -7,7 +7,7 @@ H = rows[hdr]; ki = H.index("Kernel Name"); vi = H.index("Metric Value")
 agg = collections.defaultdict(list)
 for r in rows[hdr + 1:]:
     if len(r) > vi:
-        agg[r[ki].split("(")[0].split("<")[0]].append(float(r[vi].replace(",", "")))
+        agg[r[ki].split("(")[0].split("<")[0].split()[-1]].append(float(r[vi].replace(",", "")))
 tot = sum(sum(v) for v in agg.values())
 print(f"{'kernel':24s} {'launches':>8s} {'sum_us':>10s} {'mean_us':>9s} {'share':>7s}")
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):

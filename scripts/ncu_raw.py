@@ -22,7 +22,7 @@ for r in rows[2:]:
     for i, n in idx:
         v = r[i]
         if n == "kernel":
-            v = v.split("(")[0].split("<")[0][:16]      # template arguments (k_blur<(bool)0>) are not part of the name
+            v = v.split("(")[0].split("<")[0].split()[-1][:16]      # "void k_blur<(bool)0>(...)": neither return type nor template arguments
         else:
             try:
                 f = float(v.replace(",", ""))
